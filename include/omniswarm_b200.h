@@ -1,0 +1,288 @@
+/*
+ * omniswarm_b200.h -- C ABI of libomniswarm_b200.so
+ *
+ * B200-native (sm_100a) replacement for the ONE compute-heavy path of HKUST-Aerial-Robotics/Omni-swarm:
+ * the swarm_loop keyframe front-end and the swarm_localization pose-graph solve.  The reference has no
+ * plugin ABI for this path (the boundary is C++ member calls inside one process);
+ * every entry point below names the reference call site it replaces (paths relative to /root/reference).
+ * INTEGRATION.md shows the thin C++ adapter classes a maintainer adds so that loop_cam.cpp /
+ * loop_detector.cpp / swarm_localization_solver.cpp keep their signatures.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an osb_status (0 = OK) and never throws;
+ *   - "host" entry points take HOST pointers and do their own H2D/D2H (the drop-in calls);
+ *     "_dev" entry points take DEVICE pointers plus a cudaStream_t (passed as void*) and never synchronise:
+ *     they exist so that a caller that already owns device memory (bench.py, the multi-GPU keyframe exchange)
+ *     can keep everything resident;
+ *   - all device memory is owned by the opaque handles for their lifetime (as the reference's
+ *     TensorRTInferenceGeneric does, swarm_loop/src/tensorrt_generic.cpp:99-120);
+ *   - handles are internally serialised (one stream + one mutex per handle): the reference calls
+ *     LoopDetector from the ROS thread and the LCM thread without a lock;
+ *   - there is NO CPU fallback: without a CUDA device every create() returns OSB_ERR_NO_DEVICE.
+ */
+#ifndef OMNISWARM_B200_H
+#define OMNISWARM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int osb_status;
+#define OSB_OK 0
+#define OSB_ERR_INVALID 1    /* bad argument (null pointer, size mismatch, batch > max_batch ...) */
+#define OSB_ERR_CUDA 2       /* a CUDA call failed; osb_last_error() has the text */
+#define OSB_ERR_CAPACITY 3   /* database / solver capacity exceeded */
+#define OSB_ERR_NO_DEVICE 4  /* no CUDA device: this library has no CPU path */
+
+#define OSB_SP_DESC_RAW_LEN 256   /* SP_DESC_RAW_LEN, swarm_loop/include/swarm_loop/loop_defines.h */
+#define OSB_FEATURE_DESC_SIZE 64  /* FEATURE_DESC_SIZE, loop_defines.h:67 */
+#define OSB_DEEP_DESC_SIZE 4096   /* DEEP_DESC_SIZE,    loop_defines.h:30 */
+#define OSB_MAX_DIRS 4            /* MAX_DIRS for STEREO_FISHEYE, swarm_loop/src/swarm_loop.cpp:277-278 */
+#define OSB_MAX_KPTS 200          /* superpoint_max_num, swarm_loop/launch/nodelet-sfisheye.launch:30 */
+#define OSB_REMOTE_MAGIN_NUMBER 1000000  /* REMOTE_MAGIN_NUMBER, swarm_loop/include/swarm_loop/loop_detector.h:22 */
+
+const char* osb_last_error(void);          /* thread-local text of the last failure */
+const char* osb_version(void);
+int osb_device_count(void);                /* 0 when no CUDA device is visible */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * SuperPoint  -- replaces class SuperPointTensorRT (swarm_loop/include/swarm_loop/superpoint_tensorrt.h:20-28,
+ *               constructed at swarm_loop/src/loop_cam.cpp:26, called at loop_cam.cpp:542).
+ * `weights`: float32 blob, for each layer of swarm_loop/superpoint.ipynb:143-158 in definition order
+ *            (conv1a,conv1b,conv2a,conv2b,conv3a,conv3b,conv4a,conv4b,convPa,convPb,convDa,convDb):
+ *            weight in PyTorch OIHW order, then bias.  1 300 865 floats.  (Replaces the .trt engine path:
+ *            TensorRT engine binaries are device-specific and unusable on B200.)
+ * `pca_comp` [64][256] row-major = components_.csv, `pca_mean` [256] = mean_.csv (superpoint_tensorrt.cpp:110-111).
+ * infer():   images  [batch][height][width] uint8 (the reference asserts the size, superpoint_tensorrt.cpp:122)
+ *            n_kpts  [batch]                          number of keypoints per image (<= max_num)
+ *            kpts    [batch][max_num][2] float (x,y)  ordered by descending confidence (NMS2, :304-308)
+ *            desc    [batch][max_num][64] float       PCA-projected descriptors (:221)
+ *            rows >= n_kpts[b] are left untouched.
+ * -----------------------------------------------------------------------------------------------------------*/
+typedef struct osb_superpoint osb_superpoint;
+osb_status osb_superpoint_create(osb_superpoint** out, const float* weights, size_t n_weights, int width,
+                                 int height, float thres, int max_num, const float* pca_comp,
+                                 const float* pca_mean, int max_batch);
+osb_status osb_superpoint_destroy(osb_superpoint* h);
+osb_status osb_superpoint_infer(osb_superpoint* h, const uint8_t* images, int batch, int32_t* n_kpts,
+                                float* kpts, float* desc);
+osb_status osb_superpoint_infer_dev(osb_superpoint* h, const uint8_t* images_dev, int batch, int32_t* n_kpts_dev,
+                                    float* kpts_dev, float* desc_dev, void* stream);
+/* Stage-wise parity hooks (tests only; not used by the reference call sites):
+ *  set_heatmap: upload a caller-supplied `semi` [batch][H][W] and `desc` [batch][256][H/8][W/8] (the two engine
+ *               outputs, superpoint_tensorrt.cpp:139-140) and run ONLY getKeyPoints+NMS2+computeDescriptors.
+ *  read:        copy an intermediate of the last infer() back: what = 0 semi [H][W], 1 desc [256][H/8][W/8],
+ *               2 confidences of the returned keypoints [max_num], 3 NMS survivor plane as float [H][W]. */
+osb_status osb_superpoint_postprocess(osb_superpoint* h, const float* semi, const float* desc_nchw, int batch,
+                                      int32_t* n_kpts, float* kpts, float* desc);
+osb_status osb_superpoint_read(osb_superpoint* h, int what, int image, float* out, size_t n_floats);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * NetVLAD global descriptor -- replaces class MobileNetVLADTensorRT
+ *   (swarm_loop/include/swarm_loop/mobilenetvlad_tensorrt.h:10-21, loop_cam.cpp:27 ctor, loop_cam.cpp:554 call).
+ * images [batch][H][W] uint8 (converted to float UNSCALED, mobilenetvlad_tensorrt.cpp:8-10) -> out [batch][4096].
+ * The hfnet MobileNetVLAD architecture is not part of the reference; DESIGN.md pins the stand-in whose weight
+ * blob layout is omniswarm_b200/synth.py::netvlad_layer_table().
+ * -----------------------------------------------------------------------------------------------------------*/
+typedef struct osb_netvlad osb_netvlad;
+osb_status osb_netvlad_create(osb_netvlad** out, const float* weights, size_t n_weights, int width, int height,
+                              int max_batch);
+osb_status osb_netvlad_destroy(osb_netvlad* h);
+osb_status osb_netvlad_infer(osb_netvlad* h, const uint8_t* images, int batch, float* out);
+osb_status osb_netvlad_infer_dev(osb_netvlad* h, const uint8_t* images_dev, int batch, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Keyframe database -- replaces faiss::IndexFlatIP(4096) (swarm_loop/include/swarm_loop/loop_detector.h:27-29;
+ *   add: loop_detector.cpp:166,169; search: loop_detector.cpp:213; ntotal: loop_detector.cpp:291).
+ * Exact float32 inner product, top-k by descending score, ties by ascending row id, ids = -1 and
+ * scores = -inf where fewer than k rows exist.  Rows live in HBM, row-major [capacity][dim].
+ * -----------------------------------------------------------------------------------------------------------*/
+typedef struct osb_db osb_db;
+osb_status osb_db_create(osb_db** out, int dim, int64_t capacity);
+osb_status osb_db_destroy(osb_db* h);
+osb_status osb_db_add(osb_db* h, int64_t n, const float* x, int64_t* first_id);
+osb_status osb_db_add_dev(osb_db* h, int64_t n, const float* x_dev, int64_t* first_id, void* stream);
+osb_status osb_db_search(osb_db* h, int64_t nq, const float* q, int k, float* scores, int64_t* ids);
+osb_status osb_db_search_dev(osb_db* h, int64_t nq, const float* q_dev, int k, float* scores_dev,
+                             int64_t* ids_dev, void* stream);
+int64_t osb_db_size(osb_db* h);
+osb_status osb_db_reset(osb_db* h);        /* ntotal = 0 (rows stay allocated) */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Local descriptor matcher -- replaces cv::BFMatcher(cv::NORM_L2, crossCheck = true).match(query, train)
+ *   (swarm_loop/src/loop_cam.cpp:147-150 stereo up/down; swarm_loop/src/loop_detector.cpp:564-567 loop pairs).
+ * For every query row the nearest train row by L2 (first minimum wins), kept only if mutual; output sorted by
+ * query index.  Batched over `n_pairs` independent (query, train) pairs:
+ *   q [n_pairs][max_n][dim], t [n_pairs][max_n][dim], nq/nt [n_pairs] valid row counts,
+ *   out: qi/ti/dist [n_pairs][max_n], n_out [n_pairs].   max_n <= 256, dim == 64.
+ * -----------------------------------------------------------------------------------------------------------*/
+typedef struct osb_matcher osb_matcher;
+osb_status osb_matcher_create(osb_matcher** out, int max_pairs, int max_n, int dim);
+osb_status osb_matcher_destroy(osb_matcher* h);
+osb_status osb_matcher_match(osb_matcher* h, int n_pairs, const float* q, const int32_t* nq, const float* t,
+                             const int32_t* nt, int32_t* qi, int32_t* ti, float* dist, int32_t* n_out);
+osb_status osb_matcher_match_dev(osb_matcher* h, int n_pairs, const float* q_dev, const int32_t* nq_dev,
+                                 const float* t_dev, const int32_t* nt_dev, int32_t* qi_dev, int32_t* ti_dev,
+                                 float* dist_dev, int32_t* n_out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Pose-graph solve -- replaces the body of SwarmLocalizationSolver::solve_once
+ *   (swarm_localization/src/swarm_localization_solver.cpp:1668-1725): the three setup_problem_with_* walks
+ *   (:1064-1214) become a flat factor list built by the adapter, ceres::Solve (:1712) becomes a GPU
+ *   Levenberg-Marquardt with a block-Jacobi preconditioned CG on the 4x4-block normal equations.
+ * poses   [n_nodes][4] double (x,y,z,yaw) in/out  -- the 4-vectors of EstimatePoses (swarm_localization_solver.hpp:46-50)
+ * fixed   [n_nodes] 1 = SetParameterBlockConstant (solver.cpp:1196-1206)
+ * type/ia/ib [n_factors]: factor kind and the two pose blocks
+ * huber   [n_factors] 1 = ceres::HuberLoss(1.0) (solver.cpp:1077-1082,1138-1141), 0 = no loss (ego motion :1178)
+ * payload [n_factors][OSB_PAYLOAD_LEN] double:
+ *   OSB_FACTOR_DISTANCE  (DistanceMeasurementFactor, swarm_localization_factors.hpp:203-224): [d, sqrt_inf]
+ *   OSB_FACTOR_RELPOSE   (RelativePoseFactor4d, :226-271): [meas x,y,z,yaw, sqrt_inf 4x4 row-major]
+ *   OSB_FACTOR_DETECTION (DroneDetection4dFactor, :273-367): [dir 3, tan_base 2x3, inv_dep, flags, extrinsic_z,
+ *                         dposea 4, dposeb 4, DETECTION_SPHERE_STD, DETECTION_INV_DEP_STD]; flags bit0 enable_depth,
+ *                         bit1 enable_dpose
+ * -----------------------------------------------------------------------------------------------------------*/
+#define OSB_FACTOR_DISTANCE 0
+#define OSB_FACTOR_RELPOSE 1
+#define OSB_FACTOR_DETECTION 2
+#define OSB_PAYLOAD_LEN 24
+
+typedef struct {
+  int32_t max_iterations;        /* ceres max_num_iterations = 1000 (solver.cpp:1697) */
+  int32_t max_pcg_iterations;    /* per LM step */
+  double max_time_s;             /* max_solver_time_in_seconds (solver.cpp:1702); <= 0 disables */
+  double function_tolerance;     /* Ceres default 1e-6 */
+  double gradient_tolerance;     /* Ceres default 1e-10 */
+  double parameter_tolerance;    /* Ceres default 1e-8 */
+  double pcg_tolerance;          /* relative residual of the inner solve */
+  double initial_trust_radius;   /* Ceres default 1e4 */
+} osb_solve_options;
+
+typedef struct {
+  double initial_cost;           /* 1/2 sum rho(|r|^2), as ceres Summary::initial_cost */
+  double final_cost;             /* Summary::final_cost (solver.cpp:1721) */
+  double solve_ms;               /* device time of the solve kernel(s), CUDA events */
+  int32_t iterations;            /* LM iterations taken (accepted + rejected) */
+  int32_t pcg_iterations;        /* total inner iterations */
+  int32_t n_residuals;           /* problem.NumResiduals() (solver.cpp:1724) */
+  int32_t termination;           /* 0 converged (function tol), 1 gradient tol, 2 parameter tol, 3 max iterations,
+                                    4 time limit, 5 failure (non-finite cost) */
+} osb_solve_summary;
+
+typedef struct osb_solver osb_solver;
+void osb_solve_default_options(osb_solve_options* o);
+osb_status osb_solver_create(osb_solver** out, int max_nodes, int max_factors);
+osb_status osb_solver_destroy(osb_solver* h);
+osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses, const uint8_t* fixed, int n_factors,
+                            const int32_t* type, const int32_t* ia, const int32_t* ib, const double* payload,
+                            const uint8_t* huber, const osb_solve_options* opt, osb_solve_summary* summary);
+/* residual + analytic Jacobian of every factor at `poses` (parity hook for the factor kernels):
+ * r [n_factors][4], Ja/Jb [n_factors][4][4] (rows >= the factor's residual count are zero), un-robustified. */
+osb_status osb_solver_linearize(osb_solver* h, int n_nodes, const double* poses, int n_factors,
+                                const int32_t* type, const int32_t* ia, const int32_t* ib, const double* payload,
+                                double* r, double* Ja, double* Jb);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Keyframe front-end -- the per-keyframe pipeline of LoopCam::on_flattened_images (loop_cam.cpp:178-229 ->
+ *   generate_stereo_image_descriptor :341-523) followed by LoopDetector::on_image_recv's database work
+ *   (loop_detector.cpp:89-104,150-287) and compute_correspond_features' matcher (loop_detector.cpp:539-587),
+ *   kept resident on the GPU.  Triangulation / PnP / homography RANSAC stay host code in the reference and
+ *   are out of scope.
+ *
+ * One keyframe = n_dirs directions x (up image, down image) (STEREO_FISHEYE: n_dirs=4, 8 images).
+ * osb_keyframe_record is the fixed-size record every drone contributes to the swarm-wide exchange
+ * (replaces LoopNet::broadcast_fisheye_desc, swarm_loop/src/loop_net.cpp:20-120): on the 8-GPU box it is
+ * the unit of ONE ncclAllGather.
+ * -----------------------------------------------------------------------------------------------------------*/
+typedef struct {
+  int32_t drone_id;
+  int32_t msg_id;
+  int32_t n_dirs;
+  int32_t reserved;
+  int32_t n_kpts[OSB_MAX_DIRS];                                        /* landmark_num per direction (up image) */
+  int32_t n_kpts_down[OSB_MAX_DIRS];
+  float global_desc[OSB_MAX_DIRS][OSB_DEEP_DESC_SIZE];                 /* image_desc */
+  float local_desc[OSB_MAX_DIRS][OSB_MAX_KPTS][OSB_FEATURE_DESC_SIZE]; /* feature_descriptor (up image) */
+  float kpts[OSB_MAX_DIRS][OSB_MAX_KPTS][2];                           /* landmarks_2d (up image) */
+  int32_t stereo_match[OSB_MAX_DIRS][OSB_MAX_KPTS];                    /* down-image keypoint index matched to each
+                                                                          up keypoint by the cross-check matcher, or -1
+                                                                          (input of the host triangulation that sets
+                                                                          landmarks_flag, loop_cam.cpp:405-454) */
+} osb_keyframe_record;
+
+typedef struct {
+  int32_t hit_id;                /* database image id (remote ids + OSB_REMOTE_MAGIN_NUMBER) or -1 */
+  int32_t hit_dir;               /* imgid2dir of the hit (direction_old) or -1 */
+  float hit_score;               /* `distance` of query_from_database (-1 when untouched) */
+  int32_t accepted;              /* id != -1 && distance > -1 (loop_detector.cpp:265) */
+  int32_t swapped;               /* 1 when the hit is a remote keyframe and the query keyframe is our own: the reference
+                                    then calls compute_loop(old, new) (loop_detector.cpp:113-118), i.e. the DATABASE
+                                    frame is the matcher's query side ("new") and the current keyframe the train side */
+  int32_t dir_new[OSB_MAX_DIRS]; /* direction pairing of compute_correspond_features (loop_detector.cpp:455-465), */
+  int32_t dir_old[OSB_MAX_DIRS]; /* one slot per pair with landmarks on both sides, -1 = unused slot */
+  int32_t n_matches[OSB_MAX_DIRS];                 /* cross-check matches new-vs-old per direction pair */
+  int32_t match_new[OSB_MAX_DIRS][OSB_MAX_KPTS];   /* queryIdx */
+  int32_t match_old[OSB_MAX_DIRS][OSB_MAX_KPTS];   /* trainIdx */
+} osb_loop_result;
+
+typedef struct osb_frontend osb_frontend;
+typedef struct {
+  int32_t width, height, n_dirs, max_num;
+  float sp_thres;                /* superpoint_thres */
+  int32_t self_id;
+  int32_t db_capacity;           /* rows per database (local and remote) */
+  double inner_product_thres;    /* INNER_PRODUCT_THRES (query_thres) */
+  double init_mode_product_thres;/* INIT_MODE_PRODUCT_THRES */
+  int32_t match_index_dist;      /* MATCH_INDEX_DIST */
+  int32_t query_dir;             /* direction queried: 1 for STEREO_FISHEYE, 0 for pinhole (loop_detector.cpp:249-257) */
+  int32_t zero_bottom_quarter;   /* 1 for STEREO_FISHEYE: blank rows [3H/4, H) of every image (loop_cam.cpp:535-538) */
+  int32_t accept_min_3d_pts;     /* ACCEPT_MIN_3D_PTS: stereo match skipped when n_kpts <= this (loop_cam.cpp:385-391) */
+} osb_frontend_config;
+
+osb_status osb_frontend_create(osb_frontend** out, const osb_frontend_config* cfg, const float* sp_weights,
+                               size_t n_sp_weights, const float* pca_comp, const float* pca_mean,
+                               const float* nv_weights, size_t n_nv_weights);
+osb_status osb_frontend_destroy(osb_frontend* h);
+/* extract: images_up/down [n_dirs][H][W] uint8 HOST (pinned or pageable) -> record written to `record_dev`
+ * (DEVICE pointer, sizeof(osb_keyframe_record)); no synchronisation.  msg_id is stored in the record. */
+osb_status osb_frontend_extract(osb_frontend* h, const uint8_t* images_up, const uint8_t* images_down,
+                                int32_t msg_id, osb_keyframe_record* record_dev, void* stream);
+/* same with images already on the device */
+osb_status osb_frontend_extract_dev(osb_frontend* h, const uint8_t* images_up_dev, const uint8_t* images_down_dev,
+                                    int32_t msg_id, osb_keyframe_record* record_dev, void* stream);
+/* ingest: add `n_records` records (DEVICE array, e.g. the all-gather output; records whose drone_id == self go to the
+ * local database, others to the remote one; index `skip` is ignored, pass -1 to ingest all) -- add_to_database. */
+osb_status osb_frontend_ingest(osb_frontend* h, const osb_keyframe_record* records_dev, int n_records, int skip,
+                               void* stream);
+/* query: run query_from_database for the keyframe in `record_dev` (must already be ingested if it is an own keyframe,
+ * as on_image_recv does) and, on a hit, the per-direction cross-check match against the stored keyframe; the result
+ * is written to `result_dev` (DEVICE).  init_mode / nonkeyframe as loop_detector.cpp:176. */
+osb_status osb_frontend_query(osb_frontend* h, const osb_keyframe_record* record_dev, int init_mode,
+                              int nonkeyframe, osb_loop_result* result_dev, void* stream);
+/* the whole single-drone step with HOST buffers: extract + ingest(own) + query, one synchronisation at the end. */
+osb_status osb_frontend_process(osb_frontend* h, const uint8_t* images_up, const uint8_t* images_down,
+                                int32_t msg_id, osb_keyframe_record* record_host, osb_loop_result* result_host);
+/* synchronise `stream` and refresh the host-side row counts (call once per keyframe round when driving the
+ * extract / ingest / query stages separately, e.g. around the multi-GPU all-gather) */
+osb_status osb_frontend_finish(osb_frontend* h, void* stream);
+int64_t osb_frontend_db_size(osb_frontend* h, int remote);
+osb_status osb_frontend_db_reset(osb_frontend* h);
+/* bulk-load rows into a database without running the networks (benchmark / replay set-up): global descriptors
+ * [n][4096] and optional local descriptors [n][max_num][64] + counts [n] (HOST). */
+osb_status osb_frontend_db_load(osb_frontend* h, int remote, int64_t n, const float* global_desc,
+                                const float* local_desc, const int32_t* n_kpts);
+/* stage timing (CUDA events on the caller's stream, recorded only while enabled).  After a synchronising call
+ * (process / finish) stage_ms returns the device time of the LAST extract+ingest+query sequence:
+ * [0] SuperPoint network  [1] keypoints + descriptors  [2] NetVLAD  [3] stereo match + record pack
+ * [4] add_to_database  [5] database scans (remote + local)  [6] acceptance rule + per-direction match  [7] unused */
+osb_status osb_frontend_set_profiling(osb_frontend* h, int enable);
+osb_status osb_frontend_stage_ms(osb_frontend* h, float* ms8);
+/* number of kernels launched by this library since it was loaded (all handles), for bench.py's gpu_launches */
+int64_t osb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMNISWARM_B200_H */

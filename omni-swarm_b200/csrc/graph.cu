@@ -1,0 +1,733 @@
+// graph.cu -- osb_solver: GPU pose-graph solve replacing the body of SwarmLocalizationSolver::solve_once
+// (swarm_localization/src/swarm_localization_solver.cpp:1668-1725).
+//
+// Factors (swarm_localization/include/swarm_localization/swarm_localization_factors.hpp):
+//   DistanceMeasurementFactor :203-224, RelativePoseFactor4d :226-271 (DeltaPose :139-149, pose_error_4d :52-61),
+//   DroneDetection4dFactor :273-367 (PoseMulti :165-172, DeltaPose_Naive :153-160, unit_position_error* :73-103).
+// The reference evaluates them with Ceres AutoDiff jets; here residuals and ANALYTIC Jacobians are evaluated by
+// one thread per factor.  HuberLoss(1.0) is applied as Ceres' corrector does when
+// rho'' <= 0: residual and Jacobian scaled by sqrt(rho'(s)).
+//
+// The solve is ONE persistent cooperative kernel: Levenberg-Marquardt outer loop (Ceres' LM step control: diagonal
+// D = clip(diag(J^T J)), radius update by 1 - (2 rho - 1)^3, decrease factor doubling) and a block-Jacobi
+// preconditioned conjugate gradient on the 4x4-block normal equations.  J^T J is never assembled off-diagonal:
+// a factor thread computes t = Ja p_a + Jb p_b and the two 4-vectors Ja^T t, Jb^T t, and a node thread gathers the
+// contributions of its incident factors through a CSR incidence list in a fixed order (no atomics: results are
+// bit-reproducible run to run).  The graph (8 000 scalars, 12 000 factors for BASELINE config C5, ~5.5 MB per
+// linearisation) lives in L2; the bound is grid-synchronisation latency (3 per CG iteration), not HBM.
+#include <cooperative_groups.h>
+#include <algorithm>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace osb {
+
+constexpr int GS_THREADS = 256;
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 6.28318530717958647692;
+
+__device__ __forceinline__ double normalize_angle(double a) {   // factors.hpp:34-40
+  return a - kTwoPi * floor((a + kPi) / kTwoPi);
+}
+
+// residual (nr rows) and 4x4 Jacobian blocks (row-major, rows >= nr zero) of one factor, un-robustified
+__device__ int linearize_factor(int type, const double* __restrict__ pa, const double* __restrict__ pb,
+                                const double* __restrict__ pl, double r[4], double Ja[16], double Jb[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { Ja[i] = 0.0; Jb[i] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = 0.0;
+  if (type == OSB_FACTOR_DISTANCE) {
+    const double dx = pa[0] - pb[0], dy = pa[1] - pb[1], dz = pa[2] - pb[2];
+    const double nrm = sqrt(dx * dx + dy * dy + dz * dz);
+    const double si = pl[1];
+    r[0] = (nrm - pl[0]) * si;
+    const double inv = si / nrm;
+    Ja[0] = dx * inv; Ja[1] = dy * inv; Ja[2] = dz * inv;
+    Jb[0] = -dx * inv; Jb[1] = -dy * inv; Jb[2] = -dz * inv;
+    return 1;
+  }
+  if (type == OSB_FACTOR_RELPOSE) {
+    double s, c;
+    sincos(pa[3], &s, &c);
+    const double dx = pb[0] - pa[0], dy = pb[1] - pa[1], dz = pb[2] - pa[2];
+    double e[4];
+    e[0] = pl[0] - (c * dx + s * dy);
+    e[1] = pl[1] - (-s * dx + c * dy);
+    e[2] = pl[2] - dz;
+    e[3] = normalize_angle(pl[3] - normalize_angle(pb[3] - pa[3]));
+    const double* S = pl + 4;
+    // d est / d pose_a (columns x,y,z,yaw) and pose_b
+    const double Ea[4][4] = {{-c, -s, 0.0, -s * dx + c * dy}, {s, -c, 0.0, -c * dx - s * dy}, {0.0, 0.0, -1.0, 0.0},
+                             {0.0, 0.0, 0.0, -1.0}};
+    const double Eb[4][4] = {{c, s, 0.0, 0.0}, {-s, c, 0.0, 0.0}, {0.0, 0.0, 1.0, 0.0}, {0.0, 0.0, 0.0, 1.0}};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double ri = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ri += S[i * 4 + k] * e[k];
+      r[i] = ri;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a += S[i * 4 + k] * Ea[k][j]; b += S[i * 4 + k] * Eb[k][j]; }
+        Ja[i * 4 + j] = -a; Jb[i * 4 + j] = -b;
+      }
+    }
+    return 4;
+  }
+  // OSB_FACTOR_DETECTION
+  const int flags = (int)pl[10];
+  const double inv_dep = pl[9], ext_z = pl[11], sphere_std = pl[20], invdep_std = pl[21];
+  double A[4], Bp[4];
+  double Ga03 = 0.0, Ga13 = 0.0, Gb03 = 0.0, Gb13 = 0.0;   // d T' / d yaw of the raw pose (PoseMulti)
+  if (flags & 2) {
+    double s, c;
+    sincos(pa[3], &s, &c);
+    A[0] = pa[0] + c * pl[12] - s * pl[13]; A[1] = pa[1] + s * pl[12] + c * pl[13]; A[2] = pa[2] + pl[14];
+    A[3] = normalize_angle(pa[3] + pl[15]);
+    Ga03 = -s * pl[12] - c * pl[13]; Ga13 = c * pl[12] - s * pl[13];
+    sincos(pb[3], &s, &c);
+    Bp[0] = pb[0] + c * pl[16] - s * pl[17]; Bp[1] = pb[1] + s * pl[16] + c * pl[17]; Bp[2] = pb[2] + pl[18];
+    Bp[3] = normalize_angle(pb[3] + pl[19]);
+    Gb03 = -s * pl[16] - c * pl[17]; Gb13 = c * pl[16] - s * pl[17];
+  } else {
+    A[0] = pa[0]; A[1] = pa[1]; A[2] = pa[2] + ext_z; A[3] = pa[3];
+    Bp[0] = pb[0]; Bp[1] = pb[1]; Bp[2] = pb[2]; Bp[3] = pb[3];
+  }
+  double s, c;
+  sincos(A[3], &s, &c);
+  const double dx = Bp[0] - A[0], dy = Bp[1] - A[1], dz = Bp[2] - A[2];
+  const double rel[3] = {c * dx + s * dy, -s * dx + c * dy, dz};
+  const double rho = 1.0 / sqrt(rel[0] * rel[0] + rel[1] * rel[1] + rel[2] * rel[2]);
+  // d rel / d A (4 cols), d rel / d B' (4 cols)
+  const double RA[3][4] = {{-c, -s, 0.0, -s * dx + c * dy}, {s, -c, 0.0, -c * dx - s * dy}, {0.0, 0.0, -1.0, 0.0}};
+  const double RB[3][4] = {{c, s, 0.0, 0.0}, {-s, c, 0.0, 0.0}, {0.0, 0.0, 1.0, 0.0}};
+  // chain through PoseMulti: columns 0..2 identity, column 3 gets + d rel/dT' * dT'/dyaw (yaw' = yaw + const)
+  double DA[3][4], DB[3][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    DA[i][0] = RA[i][0]; DA[i][1] = RA[i][1]; DA[i][2] = RA[i][2];
+    DA[i][3] = RA[i][3] + RA[i][0] * Ga03 + RA[i][1] * Ga13;
+    DB[i][0] = RB[i][0]; DB[i][1] = RB[i][1]; DB[i][2] = RB[i][2];
+    DB[i][3] = RB[i][3] + RB[i][0] * Gb03 + RB[i][1] * Gb13;
+  }
+  const int nr = (flags & 1) ? 3 : 2;
+  double u[3], Jrel[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) u[i] = rel[i] * rho - pl[i];
+  // dU = rho (I - rel rel^T rho^2)
+  double dU[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) dU[i][j] = rho * ((i == j ? 1.0 : 0.0) - rel[i] * rel[j] * rho * rho);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double* Bt = pl + 3 + 3 * i;
+    r[i] = (Bt[0] * u[0] + Bt[1] * u[1] + Bt[2] * u[2]) / sphere_std;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Jrel[i][j] = (Bt[0] * dU[0][j] + Bt[1] * dU[1][j] + Bt[2] * dU[2][j]) / sphere_std;
+  }
+  if (nr == 3) {
+    r[2] = (inv_dep - rho) / invdep_std;
+    const double r3 = rho * rho * rho / invdep_std;
+    Jrel[2][0] = r3 * rel[0]; Jrel[2][1] = r3 * rel[1]; Jrel[2][2] = r3 * rel[2];
+  } else {
+    Jrel[2][0] = Jrel[2][1] = Jrel[2][2] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i >= nr) break;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      Ja[i * 4 + j] = Jrel[i][0] * DA[0][j] + Jrel[i][1] * DA[1][j] + Jrel[i][2] * DA[2][j];
+      Jb[i * 4 + j] = Jrel[i][0] * DB[0][j] + Jrel[i][1] * DB[1][j] + Jrel[i][2] * DB[2][j];
+    }
+  }
+  return nr;
+}
+
+struct SolverDev {
+  int n, m;
+  // graph
+  const uint8_t* fixed; const int32_t* ftype; const int32_t* ia; const int32_t* ib; const uint8_t* huber;
+  const double* payload;
+  const int32_t* node_ptr; const int32_t* inc;   // CSR incidence: entries (factor << 1 | side)
+  // state
+  double* x[2];          // pose buffers (current / trial), [n][4]
+  double* lin[2];        // linearisation buffers: per factor 36 doubles (r[4], Ja[16], Jb[16])
+  double *g, *D, *Hnn, *Minv, *p, *z, *res, *Ap, *delta;   // node vectors
+  double* contrib;       // [m][8]
+  double* partial;       // [2][4][grid]
+  osb_solve_options opt;
+  osb_solve_summary* summary;
+  double* poses_out;
+};
+
+template <int K>
+__device__ void grid_reduce_sum(double (&v)[K], double* partial, int parity, double* sh, cg::grid_group& grid) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = GS_THREADS / 32, G = gridDim.x;
+  double* pbuf = partial + (size_t)parity * 4 * G;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double w = warp_sum_d(v[k]);
+    if (lane == 0) sh[k * 32 + warp] = w;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double xv = (lane < nw) ? sh[k * 32 + lane] : 0.0;
+      xv = warp_sum_d(xv);
+      if (lane == 0) pbuf[k * G + blockIdx.x] = xv;
+    }
+  }
+  grid.sync();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double xv = 0.0;
+      for (int i = lane; i < G; i += 32) xv += __ldcg(pbuf + k * G + i);
+      xv = warp_sum_d(xv);
+      if (lane == 0) sh[k] = xv;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = sh[k];
+  __syncthreads();
+}
+
+// evaluate all factors at poses `xp` into linearisation buffer `lin`; returns this thread's cost share and
+// (optionally) its share of sum |J_cur delta|^2 computed with the CURRENT linearisation `lin_cur`.
+__device__ void factor_evaluate(const SolverDev& P, const double* __restrict__ xp, double* __restrict__ lin,
+                                const double* __restrict__ lin_cur, const double* __restrict__ delta, double& cost,
+                                double& jd) {
+  const int T = gridDim.x * GS_THREADS;
+  for (int f = blockIdx.x * GS_THREADS + threadIdx.x; f < P.m; f += T) {
+    const int a = P.ia[f], b = P.ib[f];
+    double pa[4], pb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pa[i] = __ldcg(xp + 4 * a + i); pb[i] = __ldcg(xp + 4 * b + i); }
+    double r[4], Ja[16], Jb[16];
+    const int nr = linearize_factor(P.ftype[f], pa, pb, P.payload + (size_t)f * OSB_PAYLOAD_LEN, r, Ja, Jb);
+    (void)nr;
+    const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+    double w = 1.0;
+    if (P.huber[f] && s > 1.0) {        // ceres::HuberLoss(1.0): rho(s) = 2 sqrt(s) - 1, rho' = 1/sqrt(s)
+      cost += 0.5 * (2.0 * sqrt(s) - 1.0);
+      w = 1.0 / sqrt(sqrt(s));
+    } else {
+      cost += 0.5 * s;
+    }
+    double* L = lin + (size_t)f * 36;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) L[i] = r[i] * w;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { L[4 + i] = Ja[i] * w; L[20 + i] = Jb[i] * w; }
+    if (lin_cur != nullptr) {
+      const double* C = lin_cur + (size_t)f * 36;
+      double da[4], db[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { da[i] = __ldcg(delta + 4 * a + i); db[i] = __ldcg(delta + 4 * b + i); }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t += C[4 + i * 4 + j] * da[j] + C[20 + i * 4 + j] * db[j];
+        jd += t * t;
+      }
+    }
+  }
+}
+
+// 4x4 SPD inverse by Gauss-Jordan (no pivoting: the LM term keeps the diagonal positive)
+__device__ void inv4(const double* __restrict__ M, double* __restrict__ out) {
+  double a[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a[i][j] = M[i * 4 + j]; a[i][4 + j] = (i == j) ? 1.0 : 0.0; }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double piv = 1.0 / a[c][c];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[c][j] *= piv;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i == c) continue;
+      const double f = a[i][c];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[i][j] -= f * a[c][j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[i * 4 + j] = a[i][4 + j];
+}
+
+__global__ void __launch_bounds__(GS_THREADS)
+graph_solve_kernel(SolverDev P) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[4 * 32];
+  const int T = gridDim.x * GS_THREADS;
+  const int gtid = blockIdx.x * GS_THREADS + threadIdx.x;
+  int parity = 0;
+  unsigned long long t0 = 0;
+  if (gtid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+
+  int cur = 0;                 // index of the current pose / linearisation buffers
+  double radius = P.opt.initial_trust_radius;
+  double decrease = 2.0;
+  int iters = 0, pcg_total = 0, termination = 3;
+
+  // ---- initial evaluation ----
+  double v2[2] = {0.0, 0.0};
+  factor_evaluate(P, P.x[0], P.lin[0], nullptr, nullptr, v2[0], v2[1]);
+  grid_reduce_sum<2>(v2, P.partial, parity, sh, grid); parity ^= 1;
+  double cost = v2[0];
+  const double initial_cost = cost;
+  bool need_gradient = true;
+  double gmax = 0.0;
+
+  while (iters < P.opt.max_iterations) {
+    const double* L = P.lin[cur];
+    if (need_gradient) {
+      // ---- node phase G: gradient, diagonal blocks, LM diagonal ----
+      double vmax = 0.0;
+      for (int n = gtid; n < P.n; n += T) {
+        double gn[4] = {0.0, 0.0, 0.0, 0.0};
+        double Hn[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) Hn[i] = 0.0;
+        if (!P.fixed[n]) {
+          for (int e = P.node_ptr[n]; e < P.node_ptr[n + 1]; ++e) {
+            const int ent = P.inc[e];
+            const double* Lf = L + (size_t)(ent >> 1) * 36;
+            const double* J = Lf + 4 + 16 * (ent & 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const double ri = Lf[i];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                gn[j] += J[i * 4 + j] * ri;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) Hn[j * 4 + k] += J[i * 4 + j] * J[i * 4 + k];
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          P.g[4 * n + i] = gn[i];
+          P.D[4 * n + i] = fmin(fmax(Hn[i * 5], 1e-6), 1e32);
+          vmax = fmax(vmax, fabs(gn[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) P.Hnn[16 * n + i] = Hn[i];
+      }
+      // max-reduction through the sum machinery: reduce max per block, then max over partials
+      {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = gridDim.x;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        if (lane == 0) sh[warp] = vmax;
+        __syncthreads();
+        double* pbuf = P.partial + (size_t)parity * 4 * G;
+        if (warp == 0) {
+          double xv = (lane < GS_THREADS / 32) ? sh[lane] : 0.0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) xv = fmax(xv, __shfl_xor_sync(0xffffffffu, xv, o));
+          if (lane == 0) pbuf[blockIdx.x] = xv;
+        }
+        grid.sync();
+        if (warp == 0) {
+          double xv = 0.0;
+          for (int i = lane; i < G; i += 32) xv = fmax(xv, __ldcg(pbuf + i));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) xv = fmax(xv, __shfl_xor_sync(0xffffffffu, xv, o));
+          if (lane == 0) sh[0] = xv;
+        }
+        __syncthreads();
+        gmax = sh[0];
+        __syncthreads();
+        parity ^= 1;
+      }
+      need_gradient = false;
+      if (gmax <= P.opt.gradient_tolerance) { termination = 1; break; }
+    }
+
+    // ---- PCG init (node phase): Minv, res = -g, z = Minv res, p = 0, delta = 0 ----
+    const double lam = 1.0 / radius;
+    double v3[3] = {0.0, 0.0, 0.0};
+    for (int n = gtid; n < P.n; n += T) {
+      double rn[4] = {0.0, 0.0, 0.0, 0.0}, zn[4] = {0.0, 0.0, 0.0, 0.0};
+      if (!P.fixed[n]) {
+        double M[16], Mi[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) M[i] = P.Hnn[16 * n + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) M[i * 5] += lam * P.D[4 * n + i];
+        inv4(M, Mi);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) P.Minv[16 * n + i] = Mi[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rn[i] = -P.g[4 * n + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) zn[i] += Mi[i * 4 + j] * rn[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        P.res[4 * n + i] = rn[i]; P.z[4 * n + i] = zn[i]; P.p[4 * n + i] = 0.0; P.delta[4 * n + i] = 0.0;
+        v3[0] += rn[i] * zn[i]; v3[1] += rn[i] * rn[i];
+      }
+    }
+    grid_reduce_sum<2>(*reinterpret_cast<double(*)[2]>(v3), P.partial, parity, sh, grid); parity ^= 1;
+    double rz = v3[0];
+    const double rr0 = v3[1];
+    double beta = 0.0;
+    int it = 0;
+    // ---- PCG iterations: 3 grid synchronisations each ----
+    while (it < P.opt.max_pcg_iterations && rr0 > 0.0) {
+      // factor phase: p_a = z_a + beta p_a (on the fly), t = Ja p_a + Jb p_b, contributions Ja^T t, Jb^T t
+      for (int f = gtid; f < P.m; f += T) {
+        const int a = P.ia[f], b = P.ib[f];
+        const double* Lf = L + (size_t)f * 36;
+        double pa[4], pb[4], t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          pa[i] = __ldcg(P.z + 4 * a + i) + beta * __ldcg(P.p + 4 * a + i);
+          pb[i] = __ldcg(P.z + 4 * b + i) + beta * __ldcg(P.p + 4 * b + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s += Lf[4 + i * 4 + j] * pa[j] + Lf[20 + i * 4 + j] * pb[j];
+          t[i] = s;
+        }
+        double* C = P.contrib + (size_t)f * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double ca = 0.0, cb = 0.0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { ca += Lf[4 + i * 4 + j] * t[i]; cb += Lf[20 + i * 4 + j] * t[i]; }
+          __stcg(C + j, ca); __stcg(C + 4 + j, cb);
+        }
+      }
+      grid.sync();
+      // node phase 1: p = z + beta p (stored), Ap = sum contributions + lam D p, partial p.Ap
+      double v1[1] = {0.0};
+      for (int n = gtid; n < P.n; n += T) {
+        if (P.fixed[n]) continue;
+        double pn[4], ap[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          pn[i] = P.z[4 * n + i] + beta * P.p[4 * n + i];
+          ap[i] = lam * P.D[4 * n + i] * pn[i];
+        }
+        for (int e = P.node_ptr[n]; e < P.node_ptr[n + 1]; ++e) {
+          const int ent = P.inc[e];
+          const double* C = P.contrib + (size_t)(ent >> 1) * 8 + 4 * (ent & 1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ap[i] += __ldcg(C + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { P.p[4 * n + i] = pn[i]; P.Ap[4 * n + i] = ap[i]; v1[0] += pn[i] * ap[i]; }
+      }
+      grid_reduce_sum<1>(v1, P.partial, parity, sh, grid); parity ^= 1;
+      const double pAp = v1[0];
+      if (!(pAp > 0.0)) break;
+      const double alpha = rz / pAp;
+      // node phase 2: delta += alpha p, res -= alpha Ap, z = Minv res; partial rz_new, rr
+      double v22[2] = {0.0, 0.0};
+      for (int n = gtid; n < P.n; n += T) {
+        if (P.fixed[n]) continue;
+        double rn[4], zn[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          P.delta[4 * n + i] += alpha * P.p[4 * n + i];
+          rn[i] = P.res[4 * n + i] - alpha * P.Ap[4 * n + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) zn[i] += P.Minv[16 * n + i * 4 + j] * rn[j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          P.res[4 * n + i] = rn[i]; P.z[4 * n + i] = zn[i];
+          v22[0] += rn[i] * zn[i]; v22[1] += rn[i] * rn[i];
+        }
+      }
+      grid_reduce_sum<2>(v22, P.partial, parity, sh, grid); parity ^= 1;
+      ++it;
+      beta = v22[0] / rz;
+      rz = v22[0];
+      if (v22[1] <= P.opt.pcg_tolerance * P.opt.pcg_tolerance * rr0) break;
+    }
+    pcg_total += it;
+    ++iters;
+
+    // ---- trial point: x_new = x + delta; g.delta, |delta|^2, |x|^2 ----
+    double* xc = P.x[cur];
+    double* xn = P.x[cur ^ 1];
+    double v4[3] = {0.0, 0.0, 0.0};
+    for (int n = gtid; n < P.n; n += T) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double d = P.fixed[n] ? 0.0 : P.delta[4 * n + i];
+        const double xv = xc[4 * n + i];
+        __stcg(xn + 4 * n + i, xv + d);
+        v4[0] += P.g[4 * n + i] * d; v4[1] += d * d;
+        if (!P.fixed[n]) v4[2] += xv * xv;
+      }
+    }
+    grid_reduce_sum<3>(v4, P.partial, parity, sh, grid); parity ^= 1;
+    // ---- evaluate trial, model decrease, elapsed time ----
+    double v5[3] = {0.0, 0.0, 0.0};
+    factor_evaluate(P, xn, P.lin[cur ^ 1], L, P.delta, v5[0], v5[1]);
+    if (gtid == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      v5[2] = (double)(t1 - t0) * 1e-9;
+    }
+    grid_reduce_sum<3>(v5, P.partial, parity, sh, grid); parity ^= 1;
+    const double new_cost = v5[0];
+    const double model = -v4[0] - 0.5 * v5[1];
+    const double elapsed = v5[2];
+    const double rho = (model > 0.0) ? (cost - new_cost) / model : -1.0;
+    const bool finite = isfinite(new_cost);
+    if (finite && rho > 1e-3) {
+      // accept (Ceres LevenbergMarquardtStrategy::StepAccepted)
+      const double tmp = 2.0 * rho - 1.0;
+      radius = fmin(radius / fmax(1.0 / 3.0, 1.0 - tmp * tmp * tmp), 1e16);
+      decrease = 2.0;
+      const double dcost = cost - new_cost;
+      cur ^= 1;
+      const double old_cost = cost;
+      cost = new_cost;
+      need_gradient = true;
+      if (fabs(dcost) <= P.opt.function_tolerance * old_cost) { termination = 0; break; }
+      if (sqrt(v4[1]) <= P.opt.parameter_tolerance * (sqrt(v4[2]) + P.opt.parameter_tolerance)) { termination = 2; break; }
+    } else {
+      radius /= decrease;
+      decrease *= 2.0;
+      if (radius < 1e-32 || !isfinite(radius)) { termination = 5; break; }
+      if (sqrt(v4[1]) <= P.opt.parameter_tolerance * (sqrt(v4[2]) + P.opt.parameter_tolerance)) { termination = 2; break; }
+    }
+    if (P.opt.max_time_s > 0.0 && elapsed > P.opt.max_time_s) { termination = 4; break; }
+  }
+
+  // ---- write back ----
+  const double* xf = P.x[cur];
+  for (int i = gtid; i < 4 * P.n; i += T) P.poses_out[i] = __ldcg(xf + i);
+  if (gtid == 0) {
+    P.summary->initial_cost = initial_cost;
+    P.summary->final_cost = cost;
+    P.summary->iterations = iters;
+    P.summary->pcg_iterations = pcg_total;
+    P.summary->termination = termination;
+  }
+}
+
+__global__ void graph_linearize_kernel(int m, const double* __restrict__ poses, const int32_t* __restrict__ ftype,
+                                       const int32_t* __restrict__ ia, const int32_t* __restrict__ ib,
+                                       const double* __restrict__ payload, double* __restrict__ r,
+                                       double* __restrict__ Ja, double* __restrict__ Jb) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= m) return;
+  double rr[4], A[16], B[16];
+  linearize_factor(ftype[f], poses + 4 * ia[f], poses + 4 * ib[f], payload + (size_t)f * OSB_PAYLOAD_LEN, rr, A, B);
+  for (int i = 0; i < 4; ++i) r[(size_t)f * 4 + i] = rr[i];
+  for (int i = 0; i < 16; ++i) { Ja[(size_t)f * 16 + i] = A[i]; Jb[(size_t)f * 16 + i] = B[i]; }
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+struct osb_solver {
+  int max_nodes = 0, max_factors = 0, grid = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::mutex mu;
+  // device
+  uint8_t *d_fixed = nullptr, *d_huber = nullptr;
+  int32_t *d_type = nullptr, *d_ia = nullptr, *d_ib = nullptr, *d_ptr = nullptr, *d_inc = nullptr;
+  double *d_payload = nullptr, *d_x0 = nullptr, *d_x1 = nullptr, *d_lin0 = nullptr, *d_lin1 = nullptr;
+  double *d_nodevec = nullptr;   // g, D, p, z, res, Ap, delta (7 x 4n) + Hnn, Minv (2 x 16n)
+  double *d_contrib = nullptr, *d_partial = nullptr, *d_out = nullptr;
+  osb_solve_summary* d_summary = nullptr;
+};
+
+extern "C" void osb_solve_default_options(osb_solve_options* o) {
+  if (!o) return;
+  o->max_iterations = 1000;         // swarm_localization_solver.cpp:1697
+  o->max_pcg_iterations = 500;
+  o->max_time_s = 0.0;
+  o->function_tolerance = 1e-6;     // Ceres defaults
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->pcg_tolerance = 1e-2;
+  o->initial_trust_radius = 1e4;
+}
+
+extern "C" osb_status osb_solver_create(osb_solver** out, int max_nodes, int max_factors) {
+  OSB_REQUIRE(out != nullptr && max_nodes > 0 && max_factors > 0, "bad sizes");
+  osb_status s = require_device();
+  if (s != OSB_OK) return s;
+  osb_solver* h = new osb_solver();
+  h->max_nodes = max_nodes; h->max_factors = max_factors;
+  const size_t n = max_nodes, m = max_factors;
+  OSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  OSB_CUDA(cudaEventCreate(&h->ev0));
+  OSB_CUDA(cudaEventCreate(&h->ev1));
+  int per_sm = 0;
+  OSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_solve_kernel, GS_THREADS, 0));
+  if (per_sm < 1) { set_error("osb_solver_create", "solve kernel cannot be made resident"); return OSB_ERR_CUDA; }
+  const int want = cdiv((int)std::max(n, m), GS_THREADS);
+  h->grid = std::max(1, std::min(want, num_sms()));
+  OSB_CUDA(cudaMalloc(&h->d_fixed, n));
+  OSB_CUDA(cudaMalloc(&h->d_huber, m));
+  OSB_CUDA(cudaMalloc(&h->d_type, m * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&h->d_ia, m * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&h->d_ib, m * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&h->d_ptr, (n + 1) * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&h->d_inc, 2 * m * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&h->d_payload, m * OSB_PAYLOAD_LEN * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_x0, 4 * n * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_x1, 4 * n * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_lin0, 36 * m * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_lin1, 36 * m * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_nodevec, (7 * 4 + 2 * 16) * n * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_contrib, 8 * m * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_partial, 2 * 4 * (size_t)num_sms() * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_out, 4 * n * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_summary, sizeof(osb_solve_summary)));
+  *out = h;
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_solver_destroy(osb_solver* h) {
+  if (!h) return OSB_OK;
+  cudaFree(h->d_fixed); cudaFree(h->d_huber); cudaFree(h->d_type); cudaFree(h->d_ia); cudaFree(h->d_ib);
+  cudaFree(h->d_ptr); cudaFree(h->d_inc); cudaFree(h->d_payload); cudaFree(h->d_x0); cudaFree(h->d_x1);
+  cudaFree(h->d_lin0); cudaFree(h->d_lin1); cudaFree(h->d_nodevec); cudaFree(h->d_contrib); cudaFree(h->d_partial);
+  cudaFree(h->d_out); cudaFree(h->d_summary);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return OSB_OK;
+}
+
+static osb_status validate_graph(int n_nodes, int n_factors, const int32_t* type, const int32_t* ia, const int32_t* ib) {
+  for (int f = 0; f < n_factors; ++f) {
+    OSB_REQUIRE(type[f] >= 0 && type[f] <= 2, "unknown factor type");
+    OSB_REQUIRE(ia[f] >= 0 && ia[f] < n_nodes && ib[f] >= 0 && ib[f] < n_nodes, "factor node index out of range");
+    // the reference skips factors whose two parameter blocks coincide (solver.cpp:1071-1073,1176)
+    OSB_REQUIRE(ia[f] != ib[f], "factor connects a pose block to itself (the adapter must skip it)");
+  }
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses, const uint8_t* fixed, int n_factors,
+                                       const int32_t* type, const int32_t* ia, const int32_t* ib,
+                                       const double* payload, const uint8_t* huber, const osb_solve_options* opt,
+                                       osb_solve_summary* summary) {
+  OSB_REQUIRE(h && poses && fixed && type && ia && ib && payload && huber && summary, "null argument");
+  OSB_REQUIRE(n_nodes > 0 && n_nodes <= h->max_nodes && n_factors > 0 && n_factors <= h->max_factors,
+              "graph larger than the solver capacity");
+  osb_status s = validate_graph(n_nodes, n_factors, type, ia, ib);
+  if (s != OSB_OK) return s;
+  std::lock_guard<std::mutex> lk(h->mu);
+  osb_solve_options o;
+  if (opt) o = *opt; else osb_solve_default_options(&o);
+  // CSR incidence (deterministic: factors in index order within a node)
+  const size_t n = n_nodes, m = n_factors;
+  std::vector<int32_t> ptr(n + 1, 0), inc(2 * m);
+  for (size_t f = 0; f < m; ++f) { ptr[ia[f] + 1]++; ptr[ib[f] + 1]++; }
+  for (size_t i = 0; i < n; ++i) ptr[i + 1] += ptr[i];
+  {
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+    for (size_t f = 0; f < m; ++f) {
+      inc[fill[ia[f]]++] = (int32_t)(f << 1);
+      inc[fill[ib[f]]++] = (int32_t)((f << 1) | 1);
+    }
+  }
+  int n_res = 0;
+  for (size_t f = 0; f < m; ++f)
+    n_res += type[f] == OSB_FACTOR_DISTANCE ? 1 : type[f] == OSB_FACTOR_RELPOSE ? 4
+             : (((int)payload[f * OSB_PAYLOAD_LEN + 10] & 1) ? 3 : 2);
+  cudaStream_t st = h->stream;
+  OSB_CUDA(cudaMemcpyAsync(h->d_fixed, fixed, n, cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_huber, huber, m, cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_type, type, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_ia, ia, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_ib, ib, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_ptr, ptr.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_inc, inc.data(), 2 * m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_payload, payload, m * OSB_PAYLOAD_LEN * sizeof(double), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_x0, poses, 4 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+
+  SolverDev P;
+  P.n = n_nodes; P.m = n_factors;
+  P.fixed = h->d_fixed; P.ftype = h->d_type; P.ia = h->d_ia; P.ib = h->d_ib; P.huber = h->d_huber;
+  P.payload = h->d_payload; P.node_ptr = h->d_ptr; P.inc = h->d_inc;
+  P.x[0] = h->d_x0; P.x[1] = h->d_x1; P.lin[0] = h->d_lin0; P.lin[1] = h->d_lin1;
+  double* nv = h->d_nodevec;
+  const size_t N4 = 4 * (size_t)h->max_nodes, N16 = 16 * (size_t)h->max_nodes;
+  P.g = nv; P.D = nv + N4; P.p = nv + 2 * N4; P.z = nv + 3 * N4; P.res = nv + 4 * N4; P.Ap = nv + 5 * N4;
+  P.delta = nv + 6 * N4; P.Hnn = nv + 7 * N4; P.Minv = nv + 7 * N4 + N16;
+  P.contrib = h->d_contrib; P.partial = h->d_partial; P.opt = o; P.summary = h->d_summary; P.poses_out = h->d_out;
+  const int want = cdiv(std::max(n_nodes, n_factors), GS_THREADS);
+  const int grid = std::max(1, std::min(want, h->grid));
+  void* args[] = {&P};
+  OSB_CUDA(cudaEventRecord(h->ev0, st));
+  OSB_CUDA(cudaLaunchCooperativeKernel((void*)graph_solve_kernel, dim3(grid), dim3(GS_THREADS), args, 0, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  OSB_CUDA(cudaEventRecord(h->ev1, st));
+  OSB_CUDA(cudaMemcpyAsync(poses, h->d_out, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaMemcpyAsync(summary, h->d_summary, sizeof(osb_solve_summary), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  OSB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  summary->solve_ms = ms;
+  summary->n_residuals = n_res;
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_solver_linearize(osb_solver* h, int n_nodes, const double* poses, int n_factors,
+                                           const int32_t* type, const int32_t* ia, const int32_t* ib,
+                                           const double* payload, double* r, double* Ja, double* Jb) {
+  OSB_REQUIRE(h && poses && type && ia && ib && payload && r && Ja && Jb, "null argument");
+  OSB_REQUIRE(n_nodes > 0 && n_nodes <= h->max_nodes && n_factors > 0 && n_factors <= h->max_factors,
+              "graph larger than the solver capacity");
+  osb_status s = validate_graph(n_nodes, n_factors, type, ia, ib);
+  if (s != OSB_OK) return s;
+  std::lock_guard<std::mutex> lk(h->mu);
+  const size_t n = n_nodes, m = n_factors;
+  cudaStream_t st = h->stream;
+  OSB_CUDA(cudaMemcpyAsync(h->d_type, type, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_ia, ia, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_ib, ib, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_payload, payload, m * OSB_PAYLOAD_LEN * sizeof(double), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_x0, poses, 4 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  double* d_r = h->d_lin0;            // [m][4]
+  double* d_ja = h->d_lin0 + 4 * m;   // [m][16]
+  double* d_jb = h->d_lin1;           // [m][16]
+  OSB_LAUNCH(graph_linearize_kernel, cdiv(n_factors, 128), 128, 0, st, n_factors, h->d_x0, h->d_type, h->d_ia, h->d_ib,
+             h->d_payload, d_r, d_ja, d_jb);
+  OSB_CHECK_LAUNCH();
+  OSB_CUDA(cudaMemcpyAsync(r, d_r, 4 * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaMemcpyAsync(Ja, d_ja, 16 * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaMemcpyAsync(Jb, d_jb, 16 * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaStreamSynchronize(st));
+  return OSB_OK;
+}

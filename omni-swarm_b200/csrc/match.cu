@@ -1,0 +1,496 @@
+// match.cu -- keyframe database (exact inner-product top-k) and local-descriptor cross-check matcher.
+//
+// Replaces faiss::IndexFlatIP::{add,search} (swarm_loop/src/loop_detector.cpp:166-169,213) and
+// cv::BFMatcher(NORM_L2, crossCheck=true).match (swarm_loop/src/loop_cam.cpp:147-150,
+// swarm_loop/src/loop_detector.cpp:564-567).
+//
+// db_scan_kernel is the HBM-roofline kernel of the front-end: it streams the [N][4096] f32 database exactly
+// once (algorithmic bytes = N * 16384 B per search batch) and keeps a per-CTA top-k so
+// that only grid*k candidates reach the merge kernel.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace osb {
+
+// -------------------------------------------------------------------------------------------------------------
+// db_scan_kernel<Q,R>: each warp owns R consecutive rows at a time and dots them with Q queries held in shared
+// memory; a lane streams float4 columns lane, lane+32, ... of all R rows (R independent 16-byte loads in flight,
+// 512 contiguous bytes per row per warp instruction).  Scores of the CTA's row chunk are parked in shared memory
+// and the CTA emits its own top-k by rank counting (score desc, row id asc: the library's documented tie rule).
+// -------------------------------------------------------------------------------------------------------------
+constexpr int DB_THREADS = 512;
+constexpr int DB_CHUNK_MAX = 512;  // rows per CTA
+
+template <int Q, int R>
+__global__ void __launch_bounds__(DB_THREADS)
+db_scan_kernel(const float* __restrict__ db, int64_t n_val, const int64_t* __restrict__ n_dev, int dim,
+               const float* __restrict__ q, int nq, int k, float* __restrict__ part_scores,
+               int64_t* __restrict__ part_ids) {
+  // the row count may live on the device (keyframe front-end: rows are appended without a host round trip);
+  // the launch grid was sized for an upper bound, the chunk is derived from the true count.
+  const int64_t n = n_dev ? *n_dev : n_val;
+  const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+  extern __shared__ __align__(16) float smem[];
+  float* sq = smem;                         // [Q][dim]
+  float* ss = smem + (size_t)Q * dim;       // [Q][DB_CHUNK_MAX]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = DB_THREADS / 32;
+  const int dim4 = dim >> 2;
+  for (int i = tid; i < Q * dim4; i += DB_THREADS) {
+    int qq = i / dim4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (qq < nq) v = reinterpret_cast<const float4*>(q)[i];
+    reinterpret_cast<float4*>(sq)[i] = v;
+  }
+  __syncthreads();
+  const int64_t row0 = (int64_t)blockIdx.x * chunk;
+  const int64_t row1 = min(n, row0 + chunk);
+  const int nrows = (int)max((int64_t)0, row1 - row0);
+  const int ngroups = (nrows + R - 1) / R;
+  for (int g = warp; g < ngroups; g += nwarps) {
+    const int64_t r0 = row0 + (int64_t)g * R;
+    const float4* rp[R];
+    bool valid[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      valid[r] = (r0 + r) < row1;
+      rp[r] = reinterpret_cast<const float4*>(db + (valid[r] ? (r0 + r) : r0) * (int64_t)dim);
+    }
+    float acc[R][Q];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int qq = 0; qq < Q; ++qq) acc[r][qq] = 0.f;
+#pragma unroll 2
+    for (int j = lane; j < dim4; j += 32) {
+      float4 v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = ld_stream_f4(rp[r] + j);
+#pragma unroll
+      for (int qq = 0; qq < Q; ++qq) {
+        const float4 w = reinterpret_cast<const float4*>(sq + (size_t)qq * dim)[j];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[r][qq] = fmaf(v[r].x, w.x, acc[r][qq]);
+          acc[r][qq] = fmaf(v[r].y, w.y, acc[r][qq]);
+          acc[r][qq] = fmaf(v[r].z, w.z, acc[r][qq]);
+          acc[r][qq] = fmaf(v[r].w, w.w, acc[r][qq]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int qq = 0; qq < Q; ++qq) {
+        float s = warp_sum(acc[r][qq]);
+        if (lane == 0 && valid[r]) ss[qq * DB_CHUNK_MAX + g * R + r] = s;
+      }
+  }
+  __syncthreads();
+  // per-CTA top-k by rank counting
+  for (int qq = 0; qq < nq; ++qq) {
+    const float* s = ss + qq * DB_CHUNK_MAX;
+    float* ps = part_scores + ((size_t)qq * gridDim.x + blockIdx.x) * k;
+    int64_t* pi = part_ids + ((size_t)qq * gridDim.x + blockIdx.x) * k;
+    for (int i = tid; i < k; i += DB_THREADS)
+      if (i >= nrows) { ps[i] = -INFINITY; pi[i] = -1; }
+    for (int i = tid; i < nrows; i += DB_THREADS) {
+      const float si = s[i];
+      int rank = 0;
+      for (int j = 0; j < nrows; ++j) {
+        const float sj = s[j];
+        rank += (sj > si) || (sj == si && j < i);
+      }
+      if (rank < k) { ps[rank] = si; pi[rank] = row0 + i; }
+    }
+  }
+}
+
+// merge: one CTA per query ranks the grid*k candidates (valid ones only) and writes the global top-k.
+__global__ void __launch_bounds__(1024)
+db_merge_kernel(const float* __restrict__ part_scores, const int64_t* __restrict__ part_ids, int ncand, int k,
+                float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  const int qq = blockIdx.x;
+  const float* ps = part_scores + (size_t)qq * ncand;
+  const int64_t* pi = part_ids + (size_t)qq * ncand;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) { out_scores[qq * k + i] = -INFINITY; out_ids[qq * k + i] = -1; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
+    const int64_t idi = pi[i];
+    if (idi < 0) continue;
+    const float si = ps[i];
+    int rank = 0;
+    for (int j = 0; j < ncand; ++j) {
+      const int64_t idj = __ldg(pi + j);
+      const float sj = __ldg(ps + j);
+      rank += (idj >= 0) && ((sj > si) || (sj == si && idj < idi));
+    }
+    if (rank < k) { out_scores[qq * k + rank] = si; out_ids[qq * k + rank] = idi; }
+  }
+}
+
+template <int Q>
+static osb_status launch_scan(const float* db, int64_t n, const int64_t* n_dev, int dim, const float* q, int nq,
+                              int k, int grid, float* ps, int64_t* pi, cudaStream_t st) {
+  constexpr int R = 4;
+  size_t smem = ((size_t)Q * dim + (size_t)Q * DB_CHUNK_MAX) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    OSB_CUDA(cudaFuncSetAttribute(db_scan_kernel<Q, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  OSB_LAUNCH((db_scan_kernel<Q, R>), grid, DB_THREADS, smem, st, db, n, n_dev, dim, q, nq, k, ps, pi);
+  OSB_CHECK_LAUNCH();
+  return OSB_OK;
+}
+
+int db_scan_grid(int64_t n, int64_t* chunk_out) {
+  int grid = num_sms();
+  int64_t chunk = cdiv64(n > 0 ? n : 1, grid);
+  if (chunk > DB_CHUNK_MAX) {
+    chunk = DB_CHUNK_MAX;
+    grid = (int)cdiv64(n, chunk);
+  }
+  *chunk_out = chunk;
+  return grid;
+}
+
+// device-side search of up to 8 queries; scratch must hold 8*grid_max*k floats / int64
+osb_status db_search_device(const float* rows, int64_t n, const int64_t* n_dev, int dim, const float* q_dev, int nq,
+                            int k, float* part_scores, int64_t* part_ids, float* scores_dev, int64_t* ids_dev,
+                            cudaStream_t st) {
+  int64_t chunk;
+  const int grid = db_scan_grid(n, &chunk);   // n is an upper bound of *n_dev when n_dev is given
+  for (int q0 = 0; q0 < nq; q0 += 8) {
+    const int nb = min(8, nq - q0);
+    const float* qp = q_dev + (size_t)q0 * dim;
+    osb_status s;
+    if (nb == 1) s = launch_scan<1>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, st);
+    else if (nb == 2) s = launch_scan<2>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, st);
+    else if (nb <= 4) s = launch_scan<4>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, st);
+    else s = launch_scan<8>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, st);
+    if (s != OSB_OK) return s;
+    OSB_LAUNCH(db_merge_kernel, nb, 1024, 0, st, part_scores, part_ids, grid * k, k, scores_dev + (size_t)q0 * k,
+               ids_dev + (size_t)q0 * k);
+    OSB_CHECK_LAUNCH();
+  }
+  return OSB_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// cross-check matcher
+// -------------------------------------------------------------------------------------------------------------
+constexpr int BF_ROWS = 16;   // query rows per CTA
+constexpr int BF_DIM = 64;
+
+// dist[pair][i][j] = sqrt(sum_k (q_ik - t_jk)^2), accumulated k = 0..63 with separately rounded sub/mul/add
+// (no FMA contraction) so that the distances are bit-identical to the oracle's scalar order.
+__global__ void __launch_bounds__(256)
+bf_dist_kernel(const float* const* __restrict__ qptr, const int32_t* __restrict__ nq,
+               const float* const* __restrict__ tptr, const int32_t* __restrict__ nt, int max_n,
+               float* __restrict__ dist) {
+  __shared__ __align__(16) float sq[BF_ROWS][BF_DIM];
+  const int pair = blockIdx.y;
+  const int n_q = nq[pair], n_t = nt[pair];
+  const int i0 = blockIdx.x * BF_ROWS;
+  if (i0 >= n_q) return;
+  const float* qp = qptr[pair];
+  const float* tp = tptr[pair];
+  for (int e = threadIdx.x; e < BF_ROWS * BF_DIM / 4; e += blockDim.x) {
+    const int r = e / (BF_DIM / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i0 + r < n_q) v = reinterpret_cast<const float4*>(qp + (size_t)(i0 + r) * BF_DIM)[e % (BF_DIM / 4)];
+    reinterpret_cast<float4*>(&sq[0][0])[e] = v;
+  }
+  __syncthreads();
+  const int j = threadIdx.x;
+  if (j >= n_t) return;
+  float tv[BF_DIM];
+#pragma unroll
+  for (int k4 = 0; k4 < BF_DIM / 4; ++k4) {
+    const float4 v = reinterpret_cast<const float4*>(tp + (size_t)j * BF_DIM)[k4];
+    tv[4 * k4] = v.x; tv[4 * k4 + 1] = v.y; tv[4 * k4 + 2] = v.z; tv[4 * k4 + 3] = v.w;
+  }
+  float acc[BF_ROWS];
+#pragma unroll
+  for (int r = 0; r < BF_ROWS; ++r) acc[r] = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < BF_DIM / 4; ++k4) {
+#pragma unroll
+    for (int r = 0; r < BF_ROWS; ++r) {
+      const float4 qv = reinterpret_cast<const float4*>(&sq[r][0])[k4];
+      float d;
+      d = __fsub_rn(qv.x, tv[4 * k4]);     acc[r] = __fadd_rn(acc[r], __fmul_rn(d, d));
+      d = __fsub_rn(qv.y, tv[4 * k4 + 1]); acc[r] = __fadd_rn(acc[r], __fmul_rn(d, d));
+      d = __fsub_rn(qv.z, tv[4 * k4 + 2]); acc[r] = __fadd_rn(acc[r], __fmul_rn(d, d));
+      d = __fsub_rn(qv.w, tv[4 * k4 + 3]); acc[r] = __fadd_rn(acc[r], __fmul_rn(d, d));
+    }
+  }
+  float* dp = dist + (size_t)pair * max_n * max_n;
+#pragma unroll
+  for (int r = 0; r < BF_ROWS; ++r)
+    if (i0 + r < n_q) dp[(size_t)(i0 + r) * max_n + j] = __fsqrt_rn(acc[r]);
+}
+
+// one CTA per pair: forward / backward argmin (first minimum wins), mutual test, ordered compaction.
+__global__ void __launch_bounds__(256)
+bf_crosscheck_kernel(const float* __restrict__ dist, const int32_t* __restrict__ nq, const int32_t* __restrict__ nt,
+                     int max_n, int out_stride, int32_t* __restrict__ qi, int32_t* __restrict__ ti,
+                     float* __restrict__ dout, int32_t* __restrict__ n_out, int32_t* __restrict__ map_out) {
+  __shared__ int fwd[256], bwd[256];
+  __shared__ float fdist[256];
+  __shared__ int warp_cnt[8];
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  const int n_q = nq[pair], n_t = nt[pair];
+  const float* dp = dist + (size_t)pair * max_n * max_n;
+  if (tid < n_q && n_t > 0) {
+    float best = dp[(size_t)tid * max_n];
+    int bj = 0;
+    for (int j = 1; j < n_t; ++j) {
+      const float d = dp[(size_t)tid * max_n + j];
+      if (d < best) { best = d; bj = j; }
+    }
+    fwd[tid] = bj; fdist[tid] = best;
+  }
+  if (tid < n_t && n_q > 0) {
+    float best = dp[tid];
+    int bi = 0;
+    for (int i = 1; i < n_q; ++i) {
+      const float d = dp[(size_t)i * max_n + tid];
+      if (d < best) { best = d; bi = i; }
+    }
+    bwd[tid] = bi;
+  }
+  __syncthreads();
+  const bool keep = (tid < n_q) && (n_t > 0) && (bwd[fwd[tid]] == tid);
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  const int lane = tid & 31, warp = tid >> 5;
+  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int w = 0; w < 8; ++w) { if (w < warp) base += warp_cnt[w]; total += warp_cnt[w]; }
+  if (keep) {
+    const int pos = base + __popc(bal & ((1u << lane) - 1u));
+    qi[(size_t)pair * out_stride + pos] = tid;
+    ti[(size_t)pair * out_stride + pos] = fwd[tid];
+    dout[(size_t)pair * out_stride + pos] = fdist[tid];
+  }
+  if (map_out != nullptr && tid < max_n) map_out[(size_t)pair * out_stride + tid] = keep ? fwd[tid] : -1;
+  if (tid == 0) n_out[pair] = total;
+}
+
+osb_status bf_match_device(int n_pairs, int max_n, int out_stride, const float* const* q, const int32_t* nq,
+                           const float* const* t,
+                           const int32_t* nt, float* dist_scratch, int32_t* qi, int32_t* ti, float* dout,
+                           int32_t* n_out, int32_t* map_out, cudaStream_t st) {
+  if (n_pairs <= 0) return OSB_OK;
+  dim3 g1(cdiv(max_n, BF_ROWS), n_pairs);
+  OSB_LAUNCH(bf_dist_kernel, g1, 256, 0, st, q, nq, t, nt, max_n, dist_scratch);
+  OSB_CHECK_LAUNCH();
+  OSB_LAUNCH(bf_crosscheck_kernel, n_pairs, 256, 0, st, dist_scratch, nq, nt, max_n, out_stride, qi, ti, dout, n_out,
+             map_out);
+  OSB_CHECK_LAUNCH();
+  return OSB_OK;
+}
+
+}  // namespace osb
+
+// =============================================================================================================
+// C ABI: osb_db
+// =============================================================================================================
+using namespace osb;
+
+struct osb_db {
+  int dim = 0;
+  int64_t cap = 0, ntotal = 0;
+  float* rows = nullptr;
+  float* part_scores = nullptr;
+  int64_t* part_ids = nullptr;
+  float *d_q = nullptr, *d_scores = nullptr;
+  int64_t* d_ids = nullptr;
+  int kmax = 64, qmax = 64;
+  int grid_max = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+};
+
+extern "C" osb_status osb_db_create(osb_db** out, int dim, int64_t capacity) {
+  OSB_REQUIRE(out != nullptr && dim > 0 && dim % 4 == 0 && dim <= 8192 && capacity > 0, "bad dim/capacity");
+  osb_status s = require_device();
+  if (s != OSB_OK) return s;
+  osb_db* h = new osb_db();
+  h->dim = dim; h->cap = capacity;
+  int64_t chunk;
+  h->grid_max = db_scan_grid(capacity, &chunk);
+  OSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  OSB_CUDA(cudaMalloc(&h->rows, (size_t)capacity * dim * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&h->part_scores, (size_t)8 * h->grid_max * h->kmax * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&h->part_ids, (size_t)8 * h->grid_max * h->kmax * sizeof(int64_t)));
+  OSB_CUDA(cudaMalloc(&h->d_q, (size_t)h->qmax * dim * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&h->d_scores, (size_t)h->qmax * h->kmax * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&h->d_ids, (size_t)h->qmax * h->kmax * sizeof(int64_t)));
+  *out = h;
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_db_destroy(osb_db* h) {
+  if (!h) return OSB_OK;
+  cudaFree(h->rows); cudaFree(h->part_scores); cudaFree(h->part_ids);
+  cudaFree(h->d_q); cudaFree(h->d_scores); cudaFree(h->d_ids);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return OSB_OK;
+}
+
+extern "C" int64_t osb_db_size(osb_db* h) { return h ? h->ntotal : -1; }
+
+extern "C" osb_status osb_db_reset(osb_db* h) {
+  OSB_REQUIRE(h != nullptr, "null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->ntotal = 0;
+  return OSB_OK;
+}
+
+static osb_status db_add_impl(osb_db* h, int64_t n, const float* x, int64_t* first_id, cudaMemcpyKind kind,
+                              cudaStream_t st, bool sync) {
+  OSB_REQUIRE(h != nullptr && n >= 0 && (x != nullptr || n == 0), "bad arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->ntotal + n > h->cap) { set_error("osb_db_add", "capacity exceeded"); return OSB_ERR_CAPACITY; }
+  if (n > 0)
+    OSB_CUDA(cudaMemcpyAsync(h->rows + (size_t)h->ntotal * h->dim, x, (size_t)n * h->dim * sizeof(float), kind, st));
+  if (first_id) *first_id = h->ntotal;
+  h->ntotal += n;
+  if (sync) OSB_CUDA(cudaStreamSynchronize(st));
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_db_add(osb_db* h, int64_t n, const float* x, int64_t* first_id) {
+  OSB_REQUIRE(h != nullptr, "null handle");
+  return db_add_impl(h, n, x, first_id, cudaMemcpyHostToDevice, h->stream, true);
+}
+
+extern "C" osb_status osb_db_add_dev(osb_db* h, int64_t n, const float* x_dev, int64_t* first_id, void* stream) {
+  OSB_REQUIRE(h != nullptr, "null handle");
+  return db_add_impl(h, n, x_dev, first_id, cudaMemcpyDeviceToDevice, (cudaStream_t)stream, false);
+}
+
+extern "C" osb_status osb_db_search_dev(osb_db* h, int64_t nq, const float* q_dev, int k, float* scores_dev,
+                                        int64_t* ids_dev, void* stream) {
+  OSB_REQUIRE(h != nullptr && q_dev && scores_dev && ids_dev, "null argument");
+  OSB_REQUIRE(k > 0 && k <= h->kmax && nq > 0, "k must be in 1..64 and nq > 0");
+  std::lock_guard<std::mutex> lk(h->mu);
+  return db_search_device(h->rows, h->ntotal, nullptr, h->dim, q_dev, (int)nq, k, h->part_scores, h->part_ids, scores_dev,
+                          ids_dev, (cudaStream_t)stream);
+}
+
+extern "C" osb_status osb_db_search(osb_db* h, int64_t nq, const float* q, int k, float* scores, int64_t* ids) {
+  OSB_REQUIRE(h != nullptr && q && scores && ids, "null argument");
+  OSB_REQUIRE(k > 0 && k <= h->kmax && nq > 0, "k must be in 1..64 and nq > 0");
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (int64_t q0 = 0; q0 < nq; q0 += h->qmax) {
+    const int nb = (int)std::min<int64_t>(h->qmax, nq - q0);
+    OSB_CUDA(cudaMemcpyAsync(h->d_q, q + (size_t)q0 * h->dim, (size_t)nb * h->dim * sizeof(float),
+                             cudaMemcpyHostToDevice, h->stream));
+    osb_status s = db_search_device(h->rows, h->ntotal, nullptr, h->dim, h->d_q, nb, k, h->part_scores, h->part_ids,
+                                    h->d_scores, h->d_ids, h->stream);
+    if (s != OSB_OK) return s;
+    OSB_CUDA(cudaMemcpyAsync(scores + (size_t)q0 * k, h->d_scores, (size_t)nb * k * sizeof(float),
+                             cudaMemcpyDeviceToHost, h->stream));
+    OSB_CUDA(cudaMemcpyAsync(ids + (size_t)q0 * k, h->d_ids, (size_t)nb * k * sizeof(int64_t),
+                             cudaMemcpyDeviceToHost, h->stream));
+    OSB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return OSB_OK;
+}
+
+// =============================================================================================================
+// C ABI: osb_matcher
+// =============================================================================================================
+struct osb_matcher {
+  int max_pairs = 0, max_n = 0, dim = 0;
+  float *d_q = nullptr, *d_t = nullptr, *d_dist = nullptr, *d_dout = nullptr;
+  int32_t *d_nq = nullptr, *d_nt = nullptr, *d_qi = nullptr, *d_ti = nullptr, *d_nout = nullptr;
+  const float** d_ptrs = nullptr;   // [2][max_pairs] pointer tables (query, train)
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+};
+
+static osb_status matcher_tables(osb_matcher* h, int n_pairs, const float* q, const float* t, cudaStream_t st) {
+  std::vector<const float*> tab(2 * (size_t)h->max_pairs, nullptr);
+  for (int p = 0; p < n_pairs; ++p) {
+    tab[p] = q + (size_t)p * h->max_n * h->dim;
+    tab[h->max_pairs + p] = t + (size_t)p * h->max_n * h->dim;
+  }
+  OSB_CUDA(cudaMemcpyAsync(h->d_ptrs, tab.data(), tab.size() * sizeof(float*), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaStreamSynchronize(st));   // `tab` is a stack-lifetime staging buffer
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_matcher_create(osb_matcher** out, int max_pairs, int max_n, int dim) {
+  OSB_REQUIRE(out != nullptr && max_pairs > 0 && max_n > 0 && max_n <= 256 && dim == BF_DIM,
+              "max_n must be <= 256 and dim == 64");
+  osb_status s = require_device();
+  if (s != OSB_OK) return s;
+  osb_matcher* h = new osb_matcher();
+  h->max_pairs = max_pairs; h->max_n = max_n; h->dim = dim;
+  const size_t pn = (size_t)max_pairs * max_n;
+  OSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  OSB_CUDA(cudaMalloc(&h->d_q, pn * dim * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&h->d_t, pn * dim * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&h->d_dist, pn * max_n * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&h->d_dout, pn * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&h->d_qi, pn * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&h->d_ti, pn * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&h->d_nq, max_pairs * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&h->d_nt, max_pairs * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&h->d_nout, max_pairs * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&h->d_ptrs, 2 * (size_t)max_pairs * sizeof(float*)));
+  *out = h;
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_matcher_destroy(osb_matcher* h) {
+  if (!h) return OSB_OK;
+  cudaFree(h->d_q); cudaFree(h->d_t); cudaFree(h->d_dist); cudaFree(h->d_dout); cudaFree(h->d_qi);
+  cudaFree(h->d_ti); cudaFree(h->d_nq); cudaFree(h->d_nt); cudaFree(h->d_nout); cudaFree(h->d_ptrs);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_matcher_match_dev(osb_matcher* h, int n_pairs, const float* q_dev, const int32_t* nq_dev,
+                                            const float* t_dev, const int32_t* nt_dev, int32_t* qi_dev,
+                                            int32_t* ti_dev, float* dist_dev, int32_t* n_out_dev, void* stream) {
+  OSB_REQUIRE(h != nullptr && n_pairs >= 0 && n_pairs <= h->max_pairs, "n_pairs out of range");
+  std::lock_guard<std::mutex> lk(h->mu);
+  osb_status s = matcher_tables(h, n_pairs, q_dev, t_dev, (cudaStream_t)stream);
+  if (s != OSB_OK) return s;
+  return bf_match_device(n_pairs, h->max_n, h->max_n, h->d_ptrs, nq_dev, h->d_ptrs + h->max_pairs, nt_dev, h->d_dist, qi_dev,
+                         ti_dev, dist_dev, n_out_dev, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" osb_status osb_matcher_match(osb_matcher* h, int n_pairs, const float* q, const int32_t* nq,
+                                        const float* t, const int32_t* nt, int32_t* qi, int32_t* ti, float* dist,
+                                        int32_t* n_out) {
+  OSB_REQUIRE(h != nullptr && n_pairs >= 0 && n_pairs <= h->max_pairs, "n_pairs out of range");
+  OSB_REQUIRE(q && nq && t && nt && qi && ti && dist && n_out, "null argument");
+  for (int p = 0; p < n_pairs; ++p)
+    OSB_REQUIRE(nq[p] >= 0 && nq[p] <= h->max_n && nt[p] >= 0 && nt[p] <= h->max_n, "row count out of range");
+  std::lock_guard<std::mutex> lk(h->mu);
+  const size_t pn = (size_t)n_pairs * h->max_n;
+  cudaStream_t st = h->stream;
+  OSB_CUDA(cudaMemcpyAsync(h->d_q, q, pn * h->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_t, t, pn * h->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_nq, nq, n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_nt, nt, n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  osb_status s = matcher_tables(h, n_pairs, h->d_q, h->d_t, st);
+  if (s != OSB_OK) return s;
+  s = bf_match_device(n_pairs, h->max_n, h->max_n, h->d_ptrs, h->d_nq, h->d_ptrs + h->max_pairs, h->d_nt, h->d_dist, h->d_qi,
+                      h->d_ti, h->d_dout, h->d_nout, nullptr, st);
+  if (s != OSB_OK) return s;
+  OSB_CUDA(cudaMemcpyAsync(qi, h->d_qi, pn * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaMemcpyAsync(ti, h->d_ti, pn * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaMemcpyAsync(dist, h->d_dout, pn * sizeof(float), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaMemcpyAsync(n_out, h->d_nout, n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaStreamSynchronize(st));
+  return OSB_OK;
+}

@@ -1,0 +1,210 @@
+// netvlad.cu -- osb_netvlad: replacement of class MobileNetVLADTensorRT
+// (swarm_loop/include/swarm_loop/mobilenetvlad_tensorrt.h:10-21, swarm_loop/src/mobilenetvlad_tensorrt.cpp:4-15).
+// The reference only fixes the I/O contract (HxW float 0..255 in, 4096 floats out); the hfnet MobileNetVLAD
+// architecture is not in the repository.  The stand-in pinned here (and in oracle/frontend_ref.py::netvlad_net):
+//   conv0 3x3 s2 1->32 ReLU6 | 7 x [depthwise 3x3 (s) ReLU6 + pointwise 1x1 ReLU6] -> 512 ch at 1/16 resolution |
+//   1x1 projection to D=128, per-location L2 norm | NetVLAD K=32: soft-assign (1x1 conv + softmax),
+//   residual aggregation, intra-normalisation, flatten (K*D = 4096), L2 norm.
+#include "superpoint.cuh"
+
+namespace osb {
+
+static const int NVB_CIN[7] = {32, 64, 128, 128, 256, 256, 512};
+static const int NVB_COUT[7] = {64, 128, 128, 256, 256, 512, 512};
+static const int NVB_STRIDE[7] = {1, 2, 1, 2, 1, 2, 1};
+constexpr int NV_K = 32, NV_D = 128;
+
+size_t nv_expected_weights() {
+  size_t n = 32 * 9 + 32;
+  for (int i = 0; i < 7; ++i) n += (size_t)NVB_CIN[i] * 9 + NVB_CIN[i] + (size_t)NVB_COUT[i] * NVB_CIN[i] + NVB_COUT[i];
+  n += (size_t)NV_D * 512 + NV_D + (size_t)NV_K * NV_D + NV_K + (size_t)NV_K * NV_D;
+  return n;
+}
+
+// softmax over K=32 assignment logits of every location, in place; one thread per location
+__global__ void nv_softmax_kernel(float* __restrict__ a, int64_t locs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= locs) return;
+  float* p = a + (size_t)i * NV_K;
+  float v[NV_K];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NV_K; ++k) { v[k] = p[k]; m = fmaxf(m, v[k]); }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV_K; ++k) { v[k] = expf(v[k] - m); s += v[k]; }
+#pragma unroll
+  for (int k = 0; k < NV_K; ++k) p[k] = v[k] / s;
+}
+
+// VLAD aggregation + intra-norm + final L2: one CTA (1024 threads) per image; warp = cluster k, lane = 4 dims
+__global__ void __launch_bounds__(1024)
+nv_vlad_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ cent, int P,
+               float* __restrict__ out) {
+  __shared__ float red[32];
+  const int b = blockIdx.x, k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xb = x + (size_t)b * P * NV_D;
+  const float* ab = a + (size_t)b * P * NV_K;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float asum = 0.f;
+  for (int p = 0; p < P; ++p) {
+    const float w = __ldg(ab + (size_t)p * NV_K + k);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)p * NV_D) + lane);
+    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+    asum += w;
+  }
+  const float4 c = reinterpret_cast<const float4*>(cent + (size_t)k * NV_D)[lane];
+  acc.x -= asum * c.x; acc.y -= asum * c.y; acc.z -= asum * c.z; acc.w -= asum * c.w;
+  float s = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+  s = warp_sum(s);
+  const float n = sqrtf(s);
+  acc.x /= n; acc.y /= n; acc.z /= n; acc.w /= n;                  // intra-normalisation
+  float t = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+  t = warp_sum(t);
+  if (lane == 0) red[k] = t;
+  __syncthreads();
+  float tot = red[lane];
+  tot = warp_sum(tot);
+  const float g = sqrtf(tot);
+  acc.x /= g; acc.y /= g; acc.z /= g; acc.w /= g;
+  reinterpret_cast<float4*>(out + (size_t)b * NV_K * NV_D + (size_t)k * NV_D)[lane] = acc;
+}
+
+static osb_status upload(float** dst, const float* src, size_t n) {
+  OSB_CUDA(cudaMalloc(dst, n * sizeof(float)));
+  OSB_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return OSB_OK;
+}
+
+osb_status NetVLAD::init(const float* weights, size_t n_weights, int width, int height, int max_batch_) {
+  OSB_REQUIRE(weights != nullptr, "null weights");
+  OSB_REQUIRE(n_weights == nv_expected_weights(), "weight blob has the wrong length (expected 607968 floats)");
+  OSB_REQUIRE(width % 16 == 0 && height % 16 == 0 && width > 0 && height > 0, "width/height must be multiples of 16");
+  W = width; H = height; max_batch = max_batch_;
+  OSB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  const float* p = weights;
+  osb_status s;
+  {
+    std::vector<float> w9(9 * 32);
+    for (int o = 0; o < 32; ++o)
+      for (int t = 0; t < 9; ++t) w9[t * 32 + o] = p[o * 9 + t];
+    if ((s = upload(&w0, w9.data(), 9 * 32)) != OSB_OK) return s;
+    if ((s = upload(&b0, p + 32 * 9, 32)) != OSB_OK) return s;
+    p += 32 * 9 + 32;
+  }
+  for (int i = 0; i < 7; ++i) {
+    const int ci = NVB_CIN[i], co = NVB_COUT[i];
+    blk[i].cin = ci; blk[i].cout = co; blk[i].stride = NVB_STRIDE[i];
+    std::vector<float> dw((size_t)9 * ci);
+    for (int c = 0; c < ci; ++c)
+      for (int t = 0; t < 9; ++t) dw[(size_t)t * ci + c] = p[(size_t)c * 9 + t];
+    if ((s = upload(&blk[i].dw, dw.data(), dw.size())) != OSB_OK) return s;
+    p += (size_t)ci * 9;
+    if ((s = upload(&blk[i].dwb, p, ci)) != OSB_OK) return s;
+    p += ci;
+    if ((s = conv_layer_upload(&blk[i].pw, p, p + (size_t)co * ci, ci, co, 1)) != OSB_OK) return s;
+    p += (size_t)co * ci + co;
+  }
+  if ((s = conv_layer_upload(&proj, p, p + (size_t)NV_D * 512, 512, NV_D, 1)) != OSB_OK) return s;
+  p += (size_t)NV_D * 512 + NV_D;
+  if ((s = conv_layer_upload(&assign, p, p + (size_t)NV_K * NV_D, NV_D, NV_K, 1)) != OSB_OK) return s;
+  p += (size_t)NV_K * NV_D + NV_K;
+  if ((s = upload(&centroids, p, (size_t)NV_K * NV_D)) != OSB_OK) return s;
+  {
+    // engine input is the u8 image converted to float UNSCALED (mobilenetvlad_tensorrt.cpp:8-10); the stand-in
+    // network's first op multiplies by 1/255 in f32.
+    std::vector<float> l(256);
+    const float sc = (float)(1.0 / 255.0);
+    for (int v = 0; v < 256; ++v) l[v] = (float)v * sc;
+    if ((s = upload(&lut, l.data(), 256)) != OSB_OK) return s;
+  }
+  const size_t B = max_batch;
+  const size_t act = B * (H / 2) * (W / 2) * 64;   // largest activation: block 0 output (64 ch at 1/2 res)
+  OSB_CUDA(cudaMalloc(&d_img, B * H * W));
+  OSB_CUDA(cudaMalloc(&actA, act * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&actB, act * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&d_assign, B * (H / 16) * (W / 16) * NV_K * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&d_out, B * NV_K * NV_D * sizeof(float)));
+  return OSB_OK;
+}
+
+void NetVLAD::release() {
+  cudaFree(w0); cudaFree(b0); cudaFree(lut); cudaFree(centroids);
+  for (int i = 0; i < 7; ++i) { cudaFree(blk[i].dw); cudaFree(blk[i].dwb); conv_layer_free(&blk[i].pw); }
+  conv_layer_free(&proj); conv_layer_free(&assign);
+  cudaFree(d_img); cudaFree(actA); cudaFree(actB); cudaFree(d_assign); cudaFree(d_out);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+osb_status NetVLAD::infer_dev(const uint8_t* img_dev, int B, float* out_dev, cudaStream_t st) {
+  OSB_REQUIRE(B > 0 && B <= max_batch, "batch out of range");
+  osb_status s;
+#define RUN(x) do { s = (x); if (s != OSB_OK) return s; } while (0)
+  int h = H / 2, w = W / 2;
+  RUN(conv_first_forward(w0, b0, lut, img_dev, actA, B, H, W, 32, 2, ACT_RELU6, st));
+  for (int i = 0; i < 7; ++i) {
+    RUN(dwconv3x3_forward(blk[i].dw, blk[i].dwb, actA, actB, B, h, w, blk[i].cin, blk[i].stride, ACT_RELU6, st));
+    h /= blk[i].stride; w /= blk[i].stride;
+    RUN(conv_forward(blk[i].pw, actB, actA, B, h, w, blk[i].cout, ACT_RELU6, st));
+  }
+  RUN(conv_forward(proj, actA, actB, B, h, w, NV_D, ACT_NONE, st));
+  RUN(l2norm_cells(actB, (int64_t)B * h * w, NV_D, st));
+  RUN(conv_forward(assign, actB, d_assign, B, h, w, NV_K, ACT_NONE, st));
+  const int64_t locs = (int64_t)B * h * w;
+  OSB_LAUNCH(nv_softmax_kernel, (unsigned)cdiv64(locs, 128), 128, 0, st, d_assign, locs);
+  OSB_CHECK_LAUNCH();
+  OSB_LAUNCH(nv_vlad_kernel, B, 1024, 0, st, actB, d_assign, centroids, h * w, out_dev);
+  OSB_CHECK_LAUNCH();
+#undef RUN
+  return OSB_OK;
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+struct osb_netvlad {
+  NetVLAD nv;
+  std::mutex mu;
+};
+
+extern "C" osb_status osb_netvlad_create(osb_netvlad** out, const float* weights, size_t n_weights, int width,
+                                         int height, int max_batch) {
+  OSB_REQUIRE(out != nullptr && max_batch > 0, "bad arguments");
+  osb_status s = require_device();
+  if (s != OSB_OK) return s;
+  osb_netvlad* h = new osb_netvlad();
+  s = h->nv.init(weights, n_weights, width, height, max_batch);
+  if (s != OSB_OK) { h->nv.release(); delete h; return s; }
+  *out = h;
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_netvlad_destroy(osb_netvlad* h) {
+  if (!h) return OSB_OK;
+  h->nv.release();
+  delete h;
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_netvlad_infer_dev(osb_netvlad* h, const uint8_t* images_dev, int batch, float* out_dev,
+                                            void* stream) {
+  OSB_REQUIRE(h && images_dev && out_dev, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  return h->nv.infer_dev(images_dev, batch, out_dev, (cudaStream_t)stream);
+}
+
+extern "C" osb_status osb_netvlad_infer(osb_netvlad* h, const uint8_t* images, int batch, float* out) {
+  OSB_REQUIRE(h && images && out, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  NetVLAD& nv = h->nv;
+  OSB_REQUIRE(batch > 0 && batch <= nv.max_batch, "batch out of range");
+  cudaStream_t st = nv.stream;
+  OSB_CUDA(cudaMemcpyAsync(nv.d_img, images, (size_t)batch * nv.H * nv.W, cudaMemcpyHostToDevice, st));
+  osb_status s = nv.infer_dev(nv.d_img, batch, nv.d_out, st);
+  if (s != OSB_OK) return s;
+  OSB_CUDA(cudaMemcpyAsync(out, nv.d_out, (size_t)batch * NV_K * NV_D * sizeof(float), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaStreamSynchronize(st));
+  return OSB_OK;
+}

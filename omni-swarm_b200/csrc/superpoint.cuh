@@ -1,0 +1,48 @@
+// superpoint.cuh -- internal SuperPoint / NetVLAD objects (shared by the C-ABI wrappers and the keyframe front-end)
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace osb {
+
+size_t sp_expected_weights();
+size_t nv_expected_weights();
+
+struct SuperPoint {
+  int W = 0, H = 0, Wc = 0, Hc = 0, max_num = 0, max_batch = 0, last_batch = 0;
+  float thres = 0.f;
+  cudaStream_t stream = nullptr;
+  // weights
+  float *w1a = nullptr, *b1a = nullptr, *lut = nullptr, *pca_compT = nullptr, *pca_mean_d = nullptr;
+  ConvLayer L[12];
+  // activations / outputs (device)
+  uint8_t* d_img = nullptr;
+  float *actA = nullptr, *actB = nullptr, *d_logits = nullptr, *d_semi = nullptr, *d_desc = nullptr;
+  KeypointScratch ks;
+  int32_t* d_nk = nullptr;
+  float *d_kpts = nullptr, *d_conf = nullptr, *d_out = nullptr;
+
+  osb_status init(const float* weights, size_t n_weights, int width, int height, float thres, int max_num,
+                  const float* pca_comp, const float* pca_mean, int max_batch);
+  void release();
+  osb_status network(const uint8_t* img_dev, int B, cudaStream_t st);
+  osb_status postprocess(int B, int32_t* nk, float* kpts, float* conf, float* out, cudaStream_t st);
+  osb_status infer_dev(const uint8_t* img_dev, int B, int32_t* nk, float* kpts, float* out, cudaStream_t st);
+};
+
+struct NetVLAD {
+  int W = 0, H = 0, max_batch = 0;
+  cudaStream_t stream = nullptr;
+  float *w0 = nullptr, *b0 = nullptr, *lut = nullptr;
+  struct Block { float *dw = nullptr, *dwb = nullptr; ConvLayer pw; int cin = 0, cout = 0, stride = 1; } blk[7];
+  ConvLayer proj, assign;
+  float* centroids = nullptr;
+  uint8_t* d_img = nullptr;
+  float *actA = nullptr, *actB = nullptr, *d_assign = nullptr, *d_out = nullptr;
+
+  osb_status init(const float* weights, size_t n_weights, int width, int height, int max_batch);
+  void release();
+  osb_status infer_dev(const uint8_t* img_dev, int B, float* out_dev, cudaStream_t st);
+};
+
+}  // namespace osb

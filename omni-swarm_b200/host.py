@@ -1,0 +1,309 @@
+"""Host-side mirror of the reference's C++ call sites, one class per replaced object.
+
+Names, argument meaning and error behaviour follow the reference (paths relative to /root/reference):
+  SuperPoint        <- SuperPointTensorRT            swarm_loop/include/swarm_loop/superpoint_tensorrt.h:20-28
+  NetVLAD           <- MobileNetVLADTensorRT         swarm_loop/include/swarm_loop/mobilenetvlad_tensorrt.h:10-21
+  IndexFlatIP       <- faiss::IndexFlatIP            swarm_loop/include/swarm_loop/loop_detector.h:27-29
+  BFMatcher         <- cv::BFMatcher(NORM_L2, true)  swarm_loop/src/loop_cam.cpp:147-150
+  PoseGraphSolver   <- SwarmLocalizationSolver::solve_once  swarm_localization/src/swarm_localization_solver.cpp:1668
+  KeyframeFrontend  <- LoopCam::on_flattened_images + LoopDetector::on_image_recv database work
+All compute happens in libomniswarm_b200.so; these classes only marshal numpy arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+from . import lib as _l
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class SuperPoint:
+    """`inference(image) -> (keypoints [N,2] f32 (x,y) by descending confidence, descriptors [N,64])`."""
+
+    def __init__(self, weights: np.ndarray, pca_comp: np.ndarray, pca_mean: np.ndarray, width: int, height: int,
+                 thres: float = 0.015, max_num: int = 200, max_batch: int = 8):
+        self._lib = _l.load()
+        self.width, self.height, self.thres, self.max_num, self.max_batch = width, height, thres, max_num, max_batch
+        w, pc, pm = _f32(weights).reshape(-1), _f32(pca_comp), _f32(pca_mean)
+        assert pc.shape == (64, 256) and pm.shape == (256,)
+        self._h = C.c_void_p()
+        _l.check(self._lib.osb_superpoint_create(C.byref(self._h), _l.ptr(w), w.size, width, height, thres, max_num,
+                                                 _l.ptr(pc), _l.ptr(pm), max_batch))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.osb_superpoint_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _outputs(self, B):
+        return (np.zeros(B, np.int32), np.zeros((B, self.max_num, 2), np.float32),
+                np.zeros((B, self.max_num, 64), np.float32))
+
+    def inference_batch(self, images: np.ndarray):
+        """images [B,H,W] uint8 -> list of (kpts, desc)."""
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        # the reference asserts the image size (superpoint_tensorrt.cpp:122)
+        assert images.ndim == 3 and images.shape[1:] == (self.height, self.width), \
+            "Input image must have same size with network"
+        B = images.shape[0]
+        n, k, d = self._outputs(B)
+        _l.check(self._lib.osb_superpoint_infer(self._h, _l.ptr(images), B, _l.ptr(n), _l.ptr(k), _l.ptr(d)))
+        return [(k[b, :n[b]].copy(), d[b, :n[b]].copy()) for b in range(B)]
+
+    def inference(self, image: np.ndarray):
+        return self.inference_batch(image[None])[0]
+
+    def postprocess(self, semi: np.ndarray, desc_nchw: np.ndarray):
+        """parity hook: getKeyPoints + NMS2 + computeDescriptors on caller-supplied engine outputs."""
+        semi, desc_nchw = _f32(semi), _f32(desc_nchw)
+        if semi.ndim == 2:
+            semi, desc_nchw = semi[None], desc_nchw[None]
+        B = semi.shape[0]
+        n, k, d = self._outputs(B)
+        _l.check(self._lib.osb_superpoint_postprocess(self._h, _l.ptr(semi), _l.ptr(desc_nchw), B, _l.ptr(n),
+                                                      _l.ptr(k), _l.ptr(d)))
+        return [(k[b, :n[b]].copy(), d[b, :n[b]].copy()) for b in range(B)]
+
+    def read(self, what: str, image: int = 0) -> np.ndarray:
+        H, W = self.height, self.width
+        shapes = {"semi": (0, (H, W)), "desc": (1, (256, H // 8, W // 8)), "conf": (2, (self.max_num,)),
+                  "survivors": (3, (H, W)), "counts": (4, (4,))}
+        code, shape = shapes[what]
+        out = np.zeros(shape, np.float32)
+        _l.check(self._lib.osb_superpoint_read(self._h, code, image, _l.ptr(out), out.size))
+        return out
+
+
+class NetVLAD:
+    """`inference(image) -> [4096] f32` (mobilenetvlad_tensorrt.cpp:4-15)."""
+
+    def __init__(self, weights: np.ndarray, width: int, height: int, max_batch: int = 4):
+        self._lib = _l.load()
+        self.width, self.height = width, height
+        w = _f32(weights).reshape(-1)
+        self._h = C.c_void_p()
+        _l.check(self._lib.osb_netvlad_create(C.byref(self._h), _l.ptr(w), w.size, width, height, max_batch))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.osb_netvlad_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def inference_batch(self, images: np.ndarray) -> np.ndarray:
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        assert images.ndim == 3 and images.shape[1:] == (self.height, self.width)
+        out = np.zeros((images.shape[0], _l.DEEP_DESC_SIZE), np.float32)
+        _l.check(self._lib.osb_netvlad_infer(self._h, _l.ptr(images), images.shape[0], _l.ptr(out)))
+        return out
+
+    def inference(self, image: np.ndarray) -> np.ndarray:
+        return self.inference_batch(image[None])[0]
+
+
+class IndexFlatIP:
+    """faiss::IndexFlatIP look-alike: `add(x)`, `search(q, k) -> (D, I)`, `ntotal`."""
+
+    def __init__(self, d: int, capacity: int = 16384):
+        self._lib = _l.load()
+        self.d = d
+        self._h = C.c_void_p()
+        _l.check(self._lib.osb_db_create(C.byref(self._h), d, capacity))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.osb_db_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def ntotal(self) -> int:
+        return int(self._lib.osb_db_size(self._h))
+
+    def add(self, x: np.ndarray) -> int:
+        x = _f32(x).reshape(-1, self.d)
+        first = C.c_int64(-1)
+        _l.check(self._lib.osb_db_add(self._h, x.shape[0], _l.ptr(x), C.byref(first)))
+        return int(first.value)
+
+    def search(self, q: np.ndarray, k: int):
+        q = _f32(q).reshape(-1, self.d)
+        D = np.zeros((q.shape[0], k), np.float32)
+        I = np.zeros((q.shape[0], k), np.int64)
+        _l.check(self._lib.osb_db_search(self._h, q.shape[0], _l.ptr(q), k, _l.ptr(D), _l.ptr(I)))
+        return D, I
+
+    def reset(self):
+        _l.check(self._lib.osb_db_reset(self._h))
+
+
+class BFMatcher:
+    """cv::BFMatcher(cv::NORM_L2, crossCheck=True): `match(query, train) -> (queryIdx, trainIdx, distance)`."""
+
+    def __init__(self, max_pairs: int = 8, max_n: int = 200, dim: int = 64):
+        self._lib = _l.load()
+        self.max_pairs, self.max_n, self.dim = max_pairs, max_n, dim
+        self._h = C.c_void_p()
+        _l.check(self._lib.osb_matcher_create(C.byref(self._h), max_pairs, max_n, dim))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.osb_matcher_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def match_batch(self, queries, trains):
+        P = len(queries)
+        q = np.zeros((P, self.max_n, self.dim), np.float32)
+        t = np.zeros((P, self.max_n, self.dim), np.float32)
+        nq = np.array([len(x) for x in queries], np.int32)
+        nt = np.array([len(x) for x in trains], np.int32)
+        for p in range(P):
+            q[p, :nq[p]] = queries[p]
+            t[p, :nt[p]] = trains[p]
+        qi = np.zeros((P, self.max_n), np.int32); ti = np.zeros((P, self.max_n), np.int32)
+        dist = np.zeros((P, self.max_n), np.float32); n = np.zeros(P, np.int32)
+        _l.check(self._lib.osb_matcher_match(self._h, P, _l.ptr(q), _l.ptr(nq), _l.ptr(t), _l.ptr(nt), _l.ptr(qi),
+                                             _l.ptr(ti), _l.ptr(dist), _l.ptr(n)))
+        return [(qi[p, :n[p]].copy(), ti[p, :n[p]].copy(), dist[p, :n[p]].copy()) for p in range(P)]
+
+    def match(self, query: np.ndarray, train: np.ndarray):
+        return self.match_batch([query], [train])[0]
+
+
+class PoseGraphSolver:
+    """Flat-array form of SwarmLocalizationSolver::solve_once: `solve(graph) -> (poses, summary)`."""
+
+    def __init__(self, max_nodes: int = 4096, max_factors: int = 32768):
+        self._lib = _l.load()
+        self._h = C.c_void_p()
+        _l.check(self._lib.osb_solver_create(C.byref(self._h), max_nodes, max_factors))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.osb_solver_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def default_options(self) -> _l.SolveOptions:
+        o = _l.SolveOptions()
+        self._lib.osb_solve_default_options(C.byref(o))
+        return o
+
+    @staticmethod
+    def _arrays(g):
+        return (np.ascontiguousarray(g["fixed"], np.uint8), np.ascontiguousarray(g["ftype"], np.int32),
+                np.ascontiguousarray(g["ia"], np.int32), np.ascontiguousarray(g["ib"], np.int32),
+                np.ascontiguousarray(g["payload"], np.float64), np.ascontiguousarray(g["huber"], np.uint8))
+
+    def solve(self, g: dict, options: _l.SolveOptions | None = None, init: np.ndarray | None = None):
+        fixed, ftype, ia, ib, payload, huber = self._arrays(g)
+        poses = np.ascontiguousarray(g["init"] if init is None else init, np.float64).copy()
+        opt = options if options is not None else self.default_options()
+        summ = _l.SolveSummary()
+        _l.check(self._lib.osb_solver_solve(self._h, poses.shape[0], _l.ptr(poses), _l.ptr(fixed), len(ftype),
+                                            _l.ptr(ftype), _l.ptr(ia), _l.ptr(ib), _l.ptr(payload), _l.ptr(huber),
+                                            C.byref(opt), C.byref(summ)))
+        return poses, summ
+
+    def linearize(self, g: dict, poses: np.ndarray):
+        _, ftype, ia, ib, payload, _ = self._arrays(g)
+        poses = np.ascontiguousarray(poses, np.float64)
+        m = len(ftype)
+        r = np.zeros((m, 4)); Ja = np.zeros((m, 4, 4)); Jb = np.zeros((m, 4, 4))
+        _l.check(self._lib.osb_solver_linearize(self._h, poses.shape[0], _l.ptr(poses), m, _l.ptr(ftype), _l.ptr(ia),
+                                                _l.ptr(ib), _l.ptr(payload), _l.ptr(r), _l.ptr(Ja), _l.ptr(Jb)))
+        return r, Ja, Jb
+
+
+class KeyframeFrontend:
+    """The per-keyframe pipeline (extract -> ingest -> query) on one GPU."""
+
+    def __init__(self, sp_weights, pca_comp, pca_mean, nv_weights, width=640, height=480, n_dirs=4, max_num=200,
+                 sp_thres=0.015, self_id=0, db_capacity=16384, inner_product_thres=0.3, init_mode_product_thres=0.2,
+                 match_index_dist=5, query_dir=None, zero_bottom_quarter=True, accept_min_3d_pts=10):
+        self._lib = _l.load()
+        cfg = _l.FrontendConfig()
+        cfg.width, cfg.height, cfg.n_dirs, cfg.max_num = width, height, n_dirs, max_num
+        cfg.sp_thres, cfg.self_id, cfg.db_capacity = sp_thres, self_id, db_capacity
+        cfg.inner_product_thres, cfg.init_mode_product_thres = inner_product_thres, init_mode_product_thres
+        cfg.match_index_dist = match_index_dist
+        cfg.query_dir = (1 if n_dirs > 1 else 0) if query_dir is None else query_dir
+        cfg.zero_bottom_quarter = int(zero_bottom_quarter)
+        cfg.accept_min_3d_pts = accept_min_3d_pts
+        self.cfg = cfg
+        spw, nvw = _f32(sp_weights).reshape(-1), _f32(nv_weights).reshape(-1)
+        pc, pm = _f32(pca_comp), _f32(pca_mean)
+        self._h = C.c_void_p()
+        _l.check(self._lib.osb_frontend_create(C.byref(self._h), C.byref(cfg), _l.ptr(spw), spw.size, _l.ptr(pc),
+                                               _l.ptr(pm), _l.ptr(nvw), nvw.size))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.osb_frontend_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def process(self, images_up: np.ndarray, images_down: np.ndarray, msg_id: int):
+        """HOST images [n_dirs,H,W] u8 -> (KeyframeRecord, LoopResult); one synchronisation."""
+        up = np.ascontiguousarray(images_up, np.uint8); down = np.ascontiguousarray(images_down, np.uint8)
+        rec, res = _l.KeyframeRecord(), _l.LoopResult()
+        _l.check(self._lib.osb_frontend_process(self._h, _l.ptr(up), _l.ptr(down), msg_id, C.byref(rec), C.byref(res)))
+        return rec, res
+
+    def process_raw(self, up_ptr: int, down_ptr: int, msg_id: int, rec_ptr: int, res_ptr: int):
+        """same, with raw HOST pointers (pinned buffers owned by the caller)."""
+        _l.check(self._lib.osb_frontend_process(self._h, C.c_void_p(up_ptr), C.c_void_p(down_ptr), msg_id,
+                                                C.c_void_p(rec_ptr), C.c_void_p(res_ptr)))
+
+    def extract(self, up_ptr: int, down_ptr: int, msg_id: int, record_dev: int, stream: int, device_images=False):
+        fn = self._lib.osb_frontend_extract_dev if device_images else self._lib.osb_frontend_extract
+        _l.check(fn(self._h, C.c_void_p(up_ptr), C.c_void_p(down_ptr), msg_id, C.c_void_p(record_dev), C.c_void_p(stream)))
+
+    def ingest(self, records_dev: int, n_records: int, skip: int, stream: int):
+        _l.check(self._lib.osb_frontend_ingest(self._h, C.c_void_p(records_dev), n_records, skip, C.c_void_p(stream)))
+
+    def query(self, record_dev: int, result_dev: int, stream: int, init_mode=False, nonkeyframe=False):
+        _l.check(self._lib.osb_frontend_query(self._h, C.c_void_p(record_dev), int(init_mode), int(nonkeyframe),
+                                              C.c_void_p(result_dev), C.c_void_p(stream)))
+
+    def finish(self, stream: int):
+        _l.check(self._lib.osb_frontend_finish(self._h, C.c_void_p(stream)))
+
+    STAGES = ["superpoint_net", "keypoints_desc", "netvlad", "stereo_pack", "add_to_database", "db_scan",
+              "rule_local_match"]
+
+    def set_profiling(self, enable: bool):
+        _l.check(self._lib.osb_frontend_set_profiling(self._h, int(enable)))
+
+    def stage_ms(self) -> dict:
+        ms = np.zeros(8, np.float32)
+        _l.check(self._lib.osb_frontend_stage_ms(self._h, _l.ptr(ms)))
+        return {k: float(v) for k, v in zip(self.STAGES, ms)}
+
+    def db_size(self, remote=False) -> int:
+        return int(self._lib.osb_frontend_db_size(self._h, int(remote)))
+
+    def db_reset(self):
+        _l.check(self._lib.osb_frontend_db_reset(self._h))
+
+    def db_load(self, global_desc: np.ndarray, local_desc=None, n_kpts=None, remote=False):
+        g = _f32(global_desc)
+        ld = None if local_desc is None else _f32(local_desc)
+        nk = None if n_kpts is None else np.ascontiguousarray(n_kpts, np.int32)
+        _l.check(self._lib.osb_frontend_db_load(self._h, int(remote), g.shape[0], _l.ptr(g), _l.ptr(ld), _l.ptr(nk)))
+
+
+def launch_count() -> int:
+    return int(_l.load().osb_launch_count())

@@ -41,8 +41,8 @@ def superpoint_net(img_u8: np.ndarray, w: dict, num_threads: int | None = None):
     if num_threads is not None:
         torch.set_num_threads(num_threads)
     t = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in w.items()}
-    # cv::Mat::convertTo(CV_32F, 1/255.0): saturate_cast<float>(v * (double)(1/255.0))
-    x = torch.from_numpy((img_u8.astype(np.float64) * (1.0 / 255.0)).astype(np.float32))[None, None]
+    # cv::Mat::convertTo(CV_32F, 1/255.0): OpenCV's cvtScale for 8U->32F computes (float)v * (float)alpha
+    x = torch.from_numpy(img_u8.astype(np.float32) * np.float32(1.0 / 255.0))[None, None]
     relu = F.relu
 
     def conv(x, n, pad):

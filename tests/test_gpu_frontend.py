@@ -1,0 +1,121 @@
+"""GPU: the keyframe pipeline (extract -> add_to_database -> query -> per-direction match) against the oracle
+composed the same way (LoopCam::generate_stereo_image_descriptor + LoopDetector database rule)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from omniswarm_b200 import synth, host, lib
+from oracle import frontend_ref as fr
+
+pytestmark = pytest.mark.gpu
+
+W0, H0 = 96, 64
+
+
+def make_frontend(**kw):
+    comp, mean = synth.pca_matrices(0)
+    args = dict(width=W0, height=H0, n_dirs=4, max_num=200, sp_thres=0.015, self_id=1, db_capacity=256,
+                inner_product_thres=0.3, match_index_dist=2, zero_bottom_quarter=True, accept_min_3d_pts=3)
+    args.update(kw)
+    return host.KeyframeFrontend(synth.flatten_sp_weights(synth.superpoint_weights(0)), comp, mean,
+                                 synth.flatten_nv_weights(synth.netvlad_weights(0)), **args)
+
+
+def frame_images(seed):
+    up = np.stack([synth.image(seed * 10 + d, H0, W0) for d in range(4)])
+    down = np.stack([synth.image(seed * 10 + d + 5, H0, W0) for d in range(4)])
+    return up, down
+
+
+def oracle_record(up, down):
+    comp, mean = synth.pca_matrices(0)
+    w, nvw = synth.superpoint_weights(0), synth.netvlad_weights(0)
+    rec = []
+    for d in range(4):
+        u = up[d].copy(); u[H0 * 3 // 4:] = 0
+        dn = down[d].copy(); dn[H0 * 3 // 4:] = 0
+        ku, du, _, _ = fr.superpoint_inference(u, w, 0.015, 200, comp, mean)
+        kd, dd, _, _ = fr.superpoint_inference(dn, w, 0.015, 200, comp, mean)
+        g = fr.netvlad_net(u, nvw)
+        qi, ti, _ = fr.bf_crosscheck(du, dd) if len(ku) > 3 else (np.zeros(0, int), np.zeros(0, int), None)
+        m = -np.ones(len(ku), int); m[qi] = ti
+        rec.append(dict(kpts=ku, desc=du, n_down=len(kd), g=g, stereo=m))
+    return rec
+
+
+def test_process_record_matches_oracle(gpu):
+    fe = make_frontend()
+    up, down = frame_images(1)
+    rec, res = fe.process(up, down, msg_id=77)
+    ref = oracle_record(up, down)
+    assert rec.drone_id == 1 and rec.msg_id == 77 and rec.n_dirs == 4
+    for d in range(4):
+        n = rec.n_kpts[d]
+        k = np.ctypeslib.as_array(rec.kpts[d])[:n]
+        # small images + margin cases: require the keypoint sets to agree almost everywhere, exact where they do
+        same = {tuple(x) for x in k.tolist()} & {tuple(x) for x in ref[d]["kpts"].tolist()}
+        assert len(same) >= 0.9 * len(ref[d]["kpts"])
+        g = np.ctypeslib.as_array(rec.global_desc[d])
+        assert np.linalg.norm(g - ref[d]["g"]) < 1e-3 and abs(np.linalg.norm(g) - 1) < 1e-5
+        if np.array_equal(k, ref[d]["kpts"]):
+            ld = np.ctypeslib.as_array(rec.local_desc[d])[:n]
+            assert np.linalg.norm(ld - ref[d]["desc"]) / np.linalg.norm(ref[d]["desc"]) < 1e-3
+            assert rec.n_kpts_down[d] == ref[d]["n_down"]
+    assert fe.db_size(False) == sum(1 for d in range(4) if rec.n_kpts[d] > 0) and fe.db_size(True) == 0
+    assert res.accepted == 0                       # database_size() <= MATCH_INDEX_DIST gate / too-new rows
+    fe.close()
+
+
+def test_loop_is_found_on_revisit(gpu):
+    """Revisit an old keyframe: the query returns its row, the per-direction match pairs keypoints with themselves."""
+    fe = make_frontend(match_index_dist=1)
+    frames = [frame_images(s) for s in range(4)]
+    recs = [fe.process(*f, msg_id=i)[0] for i, f in enumerate(frames)]
+    rec, res = fe.process(*frames[0], msg_id=99)               # same images as keyframe 0
+    assert res.accepted == 1 and res.swapped == 0
+    assert res.hit_id == 1 and res.hit_dir == 1               # row of (frame 0, direction 1): rows are frame*4+dir
+    assert abs(res.hit_score - 1.0) < 1e-4
+    assert list(res.dir_new) == [1, 2, 3, 0] and list(res.dir_old) == [1, 2, 3, 0]
+    for slot in range(4):
+        d = res.dir_new[slot]
+        n = res.n_matches[slot]
+        assert n == rec.n_kpts[d] == recs[0].n_kpts[d]
+        assert list(res.match_new[slot][:n]) == list(range(n)) == list(res.match_old[slot][:n])
+    fe.close()
+
+
+def test_query_rule_device_vs_oracle(gpu):
+    """Drive the database through db_load + ingest of synthetic records and compare the acceptance rule with the
+    oracle's LoopDetectorDB for own / remote keyframes, init mode and non-keyframes."""
+    import torch
+    fe = make_frontend(match_index_dist=3, self_id=1)
+    det = fr.LoopDetectorDB(self_id=1, dim=4096, inner_product_thres=0.3, init_mode_product_thres=0.2, match_index_dist=3)
+    db = synth.descriptor_db(40, 4096, 5)
+    fe.db_load(db[:30], remote=False); fe.db_load(db[30:], remote=True)
+    for i in range(30):
+        det.add_frame(i, 1, [db[i]], [10])
+    for i in range(30, 40):
+        det.add_frame(i, 2, [db[i]], [10])
+    assert fe.db_size(False) == 30 and fe.db_size(True) == 10
+    stream = torch.cuda.current_stream().cuda_stream
+    rec_t = torch.zeros(lib.RECORD_BYTES, dtype=torch.uint8, device="cuda")
+    res_t = torch.zeros(lib.RESULT_BYTES, dtype=torch.uint8, device="cuda")
+    cases = [(1, 5, False, False), (1, 29, False, False), (1, 35, False, False), (1, 35, False, True),
+             (2, 12, False, False), (2, 29, True, False), (1, 27, False, False), (1, 26, False, False)]
+    for drone, row, init_mode, nonkf in cases:
+        q = synth.noisy_queries(db, np.array([row]), sigma=0.3)[0]
+        rec = lib.KeyframeRecord()
+        rec.drone_id, rec.n_dirs = drone, 4
+        for d in range(4):
+            rec.n_kpts[d] = 5
+        np.ctypeslib.as_array(rec.global_desc[1])[:] = q
+        rec_t.copy_(torch.frombuffer(bytearray(bytes(rec)), dtype=torch.uint8))
+        fe.query(rec_t.data_ptr(), res_t.data_ptr(), stream, init_mode, nonkf)
+        fe.finish(stream)
+        res = lib.LoopResult.from_buffer_copy(res_t.cpu().numpy().tobytes())
+        rid, rdist = det.query(drone, q, init_mode, nonkf)
+        assert res.hit_id == rid, (drone, row, init_mode, nonkf, res.hit_id, rid)
+        assert abs(res.hit_score - rdist) < 1e-4
+        assert res.accepted == int(rid != -1 and rdist > -1)
+    fe.close()

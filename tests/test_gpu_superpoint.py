@@ -1,0 +1,163 @@
+"""GPU parity of the SuperPoint path (network, keypoints/NMS, descriptors) and NetVLAD against the oracle.
+
+Parity definition (SURVEY.md section 7 hard part 1 / section 8 item 7):
+  * post-processing (threshold, NMS2, top-K, sampling, norm, PCA) given the SAME engine outputs:
+    keypoints and their order bit-exact, descriptors <= 1e-4 relative;
+  * network outputs: semi / desc <= 1e-4 relative to the fp32 oracle;
+  * end to end: keypoints identical except where the oracle heat-map is within a margin of a decision boundary
+    (threshold or a neighbour's confidence), which is reported and bounded.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from omniswarm_b200 import synth, host
+from oracle import frontend_ref as fr
+
+pytestmark = pytest.mark.gpu
+
+W0, H0 = 96, 64
+
+
+@pytest.fixture(scope="module")
+def small_sp(gpu):
+    comp, mean = synth.pca_matrices(0)
+    sp = host.SuperPoint(synth.flatten_sp_weights(synth.superpoint_weights(0)), comp, mean, W0, H0, 0.015, 50, max_batch=3)
+    yield sp
+    sp.close()
+
+
+def rel_err(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def test_postprocess_golden_bit_exact(small_sp):
+    z = np.load(os.path.join(GOLDEN, "postproc.npz"))
+    semi = np.stack([z[f"{n}_semi"] for n in "abc"]); desc = np.stack([z[f"{n}_desc"] for n in "abc"])
+    out = small_sp.postprocess(semi, desc)
+    for i, n in enumerate("abc"):
+        k, d = out[i]
+        assert np.array_equal(k, z[f"{n}_kpts"]), f"case {n}: keypoints / order differ"
+        assert np.array_equal(small_sp.read("conf", i)[:len(k)], z[f"{n}_conf"])
+        ref = z[f"{n}_out"]
+        assert d.shape == ref.shape
+        if len(k):
+            assert rel_err(d, ref) < 1e-4
+        surv = small_sp.read("survivors", i) > 0
+        assert np.array_equal(surv, fr.nms_survivor_mask(z[f"{n}_semi"], 0.015))
+
+
+@pytest.mark.parametrize("kind", ["dense_ties", "all_equal", "empty", "single", "chain"])
+def test_postprocess_edge_cases(small_sp, kind):
+    rng = np.random.default_rng(7)
+    semi = np.zeros((H0, W0), np.float32)
+    if kind == "dense_ties":       # few distinct values -> many equal-confidence neighbours (never suppress each other)
+        semi = rng.choice(np.array([0.0, 0.02, 0.3, 0.3, 0.7], np.float32), (H0, W0))
+    elif kind == "all_equal":      # every pixel a candidate with the same confidence: all survive, raster order
+        semi[:] = 0.5
+    elif kind == "single":
+        semi[H0 - 1, W0 - 1] = 0.4
+    elif kind == "chain":          # strictly decreasing along a row: long dependency chain for the fixpoint loop
+        semi[10, :] = np.linspace(0.9, 0.1, W0).astype(np.float32)
+        semi[30, :] = np.linspace(0.1, 0.9, W0).astype(np.float32)
+    desc = rng.standard_normal((256, H0 // 8, W0 // 8)).astype(np.float32)
+    desc /= np.linalg.norm(desc, axis=0, keepdims=True)
+    (k, d), = small_sp.postprocess(semi, desc)
+    rk, rc = fr.get_keypoints(semi, 0.015, 50)
+    assert np.array_equal(k, rk)
+    comp, mean = synth.pca_matrices(0)
+    rd = fr.compute_descriptors(desc, rk, W0, H0, comp, mean)
+    assert d.shape == rd.shape
+    if len(rk):
+        fin = np.isfinite(rd)
+        assert np.array_equal(np.isfinite(d), fin)
+        assert np.allclose(d[fin], rd[fin], rtol=1e-4, atol=1e-5)
+
+
+def test_u16_index_plane_wrap(gpu):
+    """More than 65535 candidates: the reference's CV_16UC1 index plane wraps (superpoint_tensorrt.cpp:246,260)."""
+    comp, mean = synth.pca_matrices(0)
+    H, W = 256, 320                                    # 81920 pixels, all candidates
+    sp = host.SuperPoint(synth.flatten_sp_weights(synth.superpoint_weights(0)), comp, mean, W, H, 0.015, 200, max_batch=1)
+    rng = np.random.default_rng(3)
+    semi = rng.uniform(0.02, 0.9, (H, W)).astype(np.float32)
+    desc = rng.standard_normal((256, H // 8, W // 8)).astype(np.float32)
+    desc /= np.linalg.norm(desc, axis=0, keepdims=True)
+    (k, d), = sp.postprocess(semi, desc)
+    rk, rc = fr.get_keypoints(semi, 0.015, 200)
+    assert (semi > 0.015).sum() > 65536
+    assert np.array_equal(k, rk)
+    # at least one returned point is displaced by the wrap (its coordinates are not where its confidence lives)
+    conf = sp.read("conf", 0)[:len(k)]
+    assert np.array_equal(conf, rc)
+    assert (semi[k[:, 1].astype(int), k[:, 0].astype(int)] != conf).any()
+    sp.close()
+
+
+def test_network_golden(small_sp):
+    z = np.load(os.path.join(GOLDEN, "superpoint_net.npz"))
+    small_sp.inference(z["img"])
+    semi, desc = small_sp.read("semi"), small_sp.read("desc")
+    assert rel_err(semi, z["semi"]) < 1e-4
+    assert np.abs(semi - z["semi"]).max() < 1e-5
+    assert np.abs(desc - z["desc"].astype(np.float32)).max() < 2e-3      # fixture stored as fp16
+
+
+@pytest.fixture(scope="module")
+def full_sp(gpu):
+    comp, mean = synth.pca_matrices(0)
+    sp = host.SuperPoint(synth.flatten_sp_weights(synth.superpoint_weights(0)), comp, mean, 640, 480, 0.015, 200, max_batch=2)
+    yield sp
+    sp.close()
+
+
+def test_network_full_size_vs_oracle(full_sp):
+    """640x480 (BASELINE config 2): semi / desc within 1e-4 rel of the fp32 oracle; stage-wise keypoint parity
+    bit-exact on the device's own heat-map; end-to-end keypoints equal up to decision-margin cases."""
+    comp, mean = synth.pca_matrices(0)
+    w = synth.superpoint_weights(0)
+    imgs = np.stack([synth.image(0), synth.image(1, zero_bottom_quarter=True)])
+    out = full_sp.inference_batch(imgs)
+    for b in range(2):
+        semi_o, desc_o = fr.superpoint_net(imgs[b], w)
+        semi, desc = full_sp.read("semi", b), full_sp.read("desc", b)
+        assert rel_err(semi, semi_o) < 1e-4 and rel_err(desc, desc_o) < 1e-4
+        assert np.abs(semi - semi_o).max() < 2e-5
+        # stage-wise: oracle post-processing applied to the DEVICE heat-map must agree bit-exactly
+        k, d = out[b]
+        rk, rc = fr.get_keypoints(semi, 0.015, 200)
+        assert np.array_equal(k, rk)
+        rd = fr.compute_descriptors(desc, rk, 640, 480, comp, mean)
+        assert rel_err(d, rd) < 1e-4
+        # end to end vs the oracle's own heat-map: identical set except margin cases
+        ok, oc = fr.get_keypoints(semi_o, 0.015, 200)
+        same = {tuple(x) for x in k.tolist()} & {tuple(x) for x in ok.tolist()}
+        assert len(same) >= 0.97 * len(ok), f"only {len(same)}/{len(ok)} keypoints agree end to end"
+        assert len(k) == 200
+
+
+def test_superpoint_argument_errors(small_sp):
+    with pytest.raises(AssertionError):
+        small_sp.inference(np.zeros((10, 10), np.uint8))       # reference asserts the size (:122)
+    with pytest.raises(host._l.OsbError):
+        host.SuperPoint(np.zeros(10, np.float32), *synth.pca_matrices(0), W0, H0)   # wrong blob length
+
+
+def test_netvlad_vs_oracle(gpu):
+    nvw = synth.netvlad_weights(0)
+    z = np.load(os.path.join(GOLDEN, "netvlad.npz"))
+    nv = host.NetVLAD(synth.flatten_nv_weights(nvw), W0, H0, max_batch=2)
+    v = nv.inference(z["img"])
+    assert rel_err(v, z["out"]) < 1e-4 and abs(np.linalg.norm(v) - 1) < 1e-5
+    nv.close()
+    nv = host.NetVLAD(synth.flatten_nv_weights(nvw), 640, 480, max_batch=4)
+    imgs = np.stack([synth.image(s) for s in range(3)])
+    out = nv.inference_batch(imgs)
+    for b in range(3):
+        assert rel_err(out[b], fr.netvlad_net(imgs[b], nvw)) < 1e-4
+    # distinct images give distinct descriptors; same image gives the same descriptor regardless of batch slot
+    assert np.abs(out[0] @ out[1]) < 0.999
+    assert np.array_equal(nv.inference(imgs[2]), out[2])
+    nv.close()

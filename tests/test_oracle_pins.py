@@ -1,0 +1,174 @@
+"""CPU: pin the oracle (oracle/*.py) against the third-party arithmetic the reference calls, and against the
+committed fixtures.  Pinned: torch grid_sample (= torch::grid_sampler, superpoint_tensorrt.cpp:209),
+cv2.BFMatcher(NORM_L2, True) (= cv::BFMatcher, loop_cam.cpp:147), Jacobians vs central differences,
+NMS2 vs a literal 2-D re-implementation of the C++ loops."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from omniswarm_b200 import synth
+from oracle import frontend_ref as fr
+from oracle import solver_ref as sr
+
+
+def nms2_literal(prob, thres, max_num, dist=4):
+    """NMS2 as the C++ is written (superpoint_tensorrt.cpp:237-310) with 2-D indexing and explicit flat-address
+    emulation of cv::Mat::at for out-of-row columns; independent of oracle.nms2's vectorised form."""
+    H, W = prob.shape
+    pts = [(x, y) for y in range(H) for x in range(W) if prob[y, x] > np.float32(thres)]
+    grid = np.zeros(H * W, np.int8); inds = np.zeros(H * W, np.uint16); conf = np.zeros(H * W, np.float32)
+    for i, (x, y) in enumerate(pts):
+        grid[y * W + x] = 1; inds[y * W + x] = i & 0xFFFF; conf[y * W + x] = prob[y, x]
+    for (x, y) in pts:
+        if grid[y * W + x] != 1:
+            continue
+        for k in range(-dist, dist + 1):
+            for j in range(-dist, dist + 1):
+                if j == 0 and k == 0:
+                    continue
+                L = (y + k) * W + (x + j)
+                if 0 <= L < H * W and conf[L] < conf[y * W + x]:
+                    grid[L] = 0
+        grid[y * W + x] = 2
+    out = []
+    for v in range(H):
+        for u in range(W):
+            if grid[v * W + u] == 2:
+                out.append((pts[int(inds[v * W + u])], float(conf[v * W + u]), v * W + u))
+    out.sort(key=lambda t: (-t[1], t[2]))
+    out = out[:max_num]
+    return np.array([p for p, _, _ in out], np.float32).reshape(-1, 2), np.array([c for _, c, _ in out], np.float32)
+
+
+@pytest.mark.parametrize("seed,density", [(1, 0.03), (2, 0.2), (3, 0.6)])
+def test_nms2_matches_literal_loops(seed, density):
+    rng = np.random.default_rng(seed)
+    H, W = 24, 40
+    p = rng.uniform(0, 0.014, (H, W)).astype(np.float32)
+    m = rng.uniform(size=(H, W)) < density
+    p[m] = rng.choice(np.linspace(0.02, 0.9, 12).astype(np.float32), m.sum())   # many exact ties
+    k1, c1 = fr.get_keypoints(p, 0.015, 30)
+    k2, c2 = nms2_literal(p, 0.015, 30)
+    assert np.array_equal(k1, k2) and np.array_equal(c1, c2)
+
+
+def test_nms2_is_order_dependent_not_local_max():
+    """A suppressed point never suppresses others (SURVEY.md A.2 consequence i)."""
+    p = np.zeros((16, 32), np.float32)
+    p[5, 5], p[5, 8], p[5, 11] = 0.9, 0.5, 0.3     # 0.9 kills 0.5; 0.5 (dead) does NOT kill 0.3
+    k, c = fr.get_keypoints(p, 0.015, 10)
+    assert {tuple(x) for x in k.tolist()} == {(5.0, 5.0), (11.0, 5.0)}
+    p[5, 5], p[5, 8], p[5, 11] = 0.3, 0.5, 0.9     # raster order reversed: 0.3 active first, later zeroed by 0.5,
+    k, c = fr.get_keypoints(p, 0.015, 10)          # 0.5 zeroed by 0.9 -> only 0.9 survives
+    assert {tuple(x) for x in k.tolist()} == {(11.0, 5.0)}
+
+
+def test_grid_sample_pin():
+    """Restated bilinear formula of SURVEY.md A.3 == torch.grid_sample(align_corners=False, zeros)."""
+    rng = np.random.default_rng(0)
+    H, W = 64, 96
+    desc = rng.standard_normal((256, H // 8, W // 8)).astype(np.float32)
+    kpts = np.stack([rng.integers(0, W, 40), rng.integers(0, H, 40)], 1).astype(np.float32)
+    kpts[:4] = [[0, 0], [W - 1, H - 1], [0, H - 1], [W - 1, 0]]           # corners: taps fall outside -> zeros
+    comp, mean = synth.pca_matrices(0)
+    got = fr.compute_descriptors(desc, kpts, W, H, comp, mean)
+    S = np.zeros((len(kpts), 256), np.float64)
+    Hc, Wc = H // 8, W // 8
+    for n, (x, y) in enumerate(kpts):
+        fx, fy = x / 8 - 0.5, y / 8 - 0.5
+        x0, y0 = int(np.floor(fx)), int(np.floor(fy))
+        for dy in (0, 1):
+            for dx in (0, 1):
+                xx, yy = x0 + dx, y0 + dy
+                if 0 <= xx < Wc and 0 <= yy < Hc:
+                    S[n] += desc[:, yy, xx] * (1 - abs(fx - xx)) * (1 - abs(fy - yy))
+    S /= np.sqrt((S ** 2).sum(0, keepdims=True))      # per-CHANNEL norm over keypoints
+    ref = (S - mean) @ comp.T.astype(np.float64)
+    assert np.abs(got - ref).max() < 2e-5
+
+
+def test_bfmatcher_pin():
+    cv2 = pytest.importorskip("cv2")
+    for seed, (nq, nt) in enumerate([(57, 43), (200, 200), (1, 5), (5, 1)]):
+        a = synth.local_descriptors(nq, 10 + seed)
+        b = synth.local_descriptors(nt, 20 + seed, base=a) if nt <= nq else synth.local_descriptors(nt, 20 + seed)
+        qi, ti, dist = fr.bf_crosscheck(a, b)
+        ms = sorted(cv2.BFMatcher(cv2.NORM_L2, True).match(a, b), key=lambda m: m.queryIdx)
+        assert [m.queryIdx for m in ms] == qi.tolist() and [m.trainIdx for m in ms] == ti.tolist()
+        assert np.allclose([m.distance for m in ms], dist, rtol=1e-5, atol=1e-6)
+
+
+def test_jacobians_vs_central_differences():
+    g = synth.pose_graph(3, 12, n_uwb=20, n_loop=15, n_det=8, n_bearing=9, seed=3)
+    worst = 0.0
+    for f in range(len(g["ftype"])):
+        a, b = g["ia"][f], g["ib"][f]
+        pa, pb = g["init"][a], g["init"][b]
+        _, Ja, Jb = sr.factor_residual_jacobian(int(g["ftype"][f]), pa, pb, g["payload"][f])
+        for which, J in ((0, Ja), (1, Jb)):
+            for j in range(4):
+                h = 1e-6
+                p1, p2 = [pa.copy(), pb.copy()], [pa.copy(), pb.copy()]
+                p1[which][j] += h; p2[which][j] -= h
+                r1 = sr.factor_residual_jacobian(int(g["ftype"][f]), p1[0], p1[1], g["payload"][f])[0]
+                r2 = sr.factor_residual_jacobian(int(g["ftype"][f]), p2[0], p2[1], g["payload"][f])[0]
+                worst = max(worst, np.max(np.abs((r1 - r2) / (2 * h) - J[:, j])) / (1 + np.max(np.abs(J[:, j]))))
+    assert worst < 1e-6
+
+
+def test_create_cov6d_sqrt_information():
+    """RelativePoseFactor4d::CreateCov6d (factors.hpp:255-263): element-wise sqrt(|inv(cov4)|)."""
+    cov6 = np.diag([1e-4, 2e-4, 3e-4, 1.0, 1.0, 5e-5])
+    cov6[0, 1] = cov6[1, 0] = 5e-5
+    S = sr.create_cov6d_sqrt_inf(cov6)
+    cov4 = np.zeros((4, 4)); cov4[:3, :3] = cov6[:3, :3]; cov4[3, 3] = cov6[5, 5]
+    assert np.allclose(S * S, np.abs(np.linalg.inv(cov4)))
+
+
+def test_golden_fixtures_reproduce():
+    """The committed fixtures are what the oracle produces today."""
+    comp, mean = synth.pca_matrices(0)
+    z = np.load(os.path.join(GOLDEN, "postproc.npz"))
+    for n in "abc":
+        k, c = fr.get_keypoints(z[f"{n}_semi"], 0.015, 50)
+        assert np.array_equal(k, z[f"{n}_kpts"]) and np.array_equal(c, z[f"{n}_conf"])
+        d = fr.compute_descriptors(z[f"{n}_desc"], k, 96, 64, comp, mean)
+        assert np.allclose(d, z[f"{n}_out"], atol=1e-6, equal_nan=True)
+    z = np.load(os.path.join(GOLDEN, "matcher.npz"))
+    qi, ti, dist = fr.bf_crosscheck(z["q"], z["t"])
+    assert np.array_equal(qi, z["qi"]) and np.array_equal(ti, z["ti"]) and np.array_equal(dist, z["dist"])
+    z = np.load(os.path.join(GOLDEN, "superpoint_net.npz"))
+    semi, desc = fr.superpoint_net(z["img"], synth.superpoint_weights(0))
+    assert np.allclose(semi, z["semi"], atol=1e-6) and np.allclose(desc, z["desc"].astype(np.float32), atol=2e-3)
+    z = np.load(os.path.join(GOLDEN, "netvlad.npz"))
+    assert np.allclose(fr.netvlad_net(z["img"], synth.netvlad_weights(0)), z["out"], atol=1e-6)
+    z = np.load(os.path.join(GOLDEN, "graph_small.npz"))
+    g = synth.pose_graph(3, 12, n_uwb=20, n_loop=15, n_det=8, n_bearing=9, seed=3)
+    res = sr.solve(g)
+    assert np.allclose(res["poses"], z["poses"], atol=1e-9) and abs(res["final_cost"] - z["final_cost"]) < 1e-9
+
+
+def test_query_rule_quirks():
+    """`<=` on the index test, stale `distance` from the remote search, fall-through id."""
+    dim = 16
+    rng = np.random.default_rng(0)
+    rows = rng.standard_normal((12, dim)).astype(np.float32)
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    det = fr.LoopDetectorDB(self_id=1, dim=dim, inner_product_thres=0.5, match_index_dist=5)
+    for i, r in enumerate(rows[:8]):
+        det.add_frame(i, 1, [r], [10])
+    # query == newest row (7): score 1.0 but label 7 > ntotal - max_index = 3 -> rejected; falls through
+    idq, dist = det.query(1, rows[7], False, False)
+    assert dist == -1.0 and idq != -1              # last valid label returned, distance untouched
+    # query == old row 2: accepted with its score
+    idq, dist = det.query(1, rows[2], False, False)
+    assert idq == 2 and abs(dist - 1.0) < 1e-6
+    # remote hit leaves a stale distance that validates a failing local search
+    det.add_frame(100, 2, [rows[9]], [10])
+    idq, dist = det.query(1, rows[9], False, False)
+    assert abs(dist - 1.0) < 1e-6 and idq < fr.REMOTE_MAGIN_NUMBER     # local id, remote score
+    # remote keyframe queries the LOCAL db with max_index 1
+    idq, dist = det.query(2, rows[7], False, False)
+    assert idq == 7 and abs(dist - 1.0) < 1e-6
