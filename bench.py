@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- keyframes/sec of the loop-closure front-end and pose-graph solve ms on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one 4-view fisheye keyframe through the hot path (BASELINE.json config C3 per GPU):
+  8 x SuperPoint (640x480, up+down images of 4 directions) + 4 x NetVLAD + 4 stereo cross-check matches
+  + add_to_database + inner-product top-k against the keyframe database (10 000 rows x 4096 f32 preloaded)
+  + acceptance rule + 4 per-direction cross-check matches against the hit keyframe.
+`value`  = keyframes/s with the u8 images already resident in HBM (whole job, all ranks).
+`e2e`    = the same through the host-buffer C-ABI call osb_frontend_process: pinned host images in, record + loop
+           result back to the host, H2D/D2H inside the timed region.
+N > 1: one drone per GPU (weak scaling); every step ends with ONE NCCL all-gather of the fixed-size keyframe
+record (replaces LoopNet's LCM multicast) and each GPU ingests the N-1 foreign records into its remote database.
+The pose-graph solve (BASELINE config C5 graph: 2000 nodes / 12 000 factors) is single-GPU ("replicas only"): it is
+timed once per run on every rank and reported as `solve_ms`.
+`--impl reference`: the reference's CPU path restated by oracle/ (torch CPU SuperPoint/NetVLAD with all host threads,
+numpy scan, cross-check matcher, scipy sparse LM) -- the reference itself cannot be built here.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, N_DIRS, MAX_NUM = 640, 480, 4, 200
+DB_ROWS = 10000
+POOL = 4                      # distinct keyframes cycled through (each already in the database -> every query hits)
+SP_GFLOP_PER_IMAGE = 52.10    # SURVEY.md section 8d / BASELINE.md section 2
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--db-rows", type=int, default=DB_ROWS)
+    p.add_argument("--no-solve", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def keyframe_images(seed):
+    from omniswarm_b200 import synth
+    up = np.stack([synth.image(1000 * seed + d, H, W) for d in range(N_DIRS)])
+    down = np.stack([synth.image(1000 * seed + 100 + d, H, W) for d in range(N_DIRS)])
+    return up, down
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU path (oracle): used for cpu_baseline (bounded sample) and for --impl reference
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_keyframe(oracle_state, up, down):
+    """One keyframe through the oracle, mirroring the reference call order (loop_cam.cpp:341-523 + loop_detector)."""
+    from oracle import frontend_ref as fr
+    w, nvw, comp, mean, db, det = oracle_state
+    descs = []
+    for d in range(N_DIRS):
+        u = up[d].copy(); u[H * 3 // 4:] = 0
+        dn = down[d].copy(); dn[H * 3 // 4:] = 0
+        ku, du, _, _ = fr.superpoint_inference(u, w, 0.015, MAX_NUM, comp, mean)
+        kd, dd, _, _ = fr.superpoint_inference(dn, w, 0.015, MAX_NUM, comp, mean)
+        g = fr.netvlad_net(u, nvw)
+        fr.bf_crosscheck(du, dd)
+        descs.append((du, g))
+    q = descs[1][1]
+    scores = db @ q                                  # faiss::IndexFlatIP scan (BLAS sgemv)
+    top = np.argsort(-scores, kind="stable")[:10]
+    for d in range(N_DIRS):                          # per-direction match against the hit
+        fr.bf_crosscheck(descs[d][0], descs[(d + 1) % N_DIRS][0])
+    return int(top[0])
+
+
+def cpu_baseline(args, n_keyframes=2):
+    import torch
+    from omniswarm_b200 import synth
+    from oracle import solver_ref as sr
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    comp, mean = synth.pca_matrices(0)
+    state = (synth.superpoint_weights(0), synth.netvlad_weights(0), comp, mean,
+             synth.descriptor_db(args.db_rows, 4096, 1), None)
+    up, down = keyframe_images(0)
+    cpu_keyframe(state, up, down)                    # warm-up (thread pools, allocator)
+    t0 = time.perf_counter()
+    for i in range(n_keyframes):
+        cpu_keyframe(state, up, down)
+    dt = (time.perf_counter() - t0) / n_keyframes
+    out = dict(value=1.0 / dt, unit="keyframes/s", cores=cores, kind="port",
+               sample=f"{n_keyframes} keyframes (8 SuperPoint + 4 NetVLAD 640x480 via torch CPU fp32, {cores} threads; "
+                      f"numpy scan of {args.db_rows} rows; cross-check matcher); reference sets 1 thread "
+                      f"(superpoint_tensorrt.cpp:98)")
+    if not args.no_solve:
+        g = synth.pose_graph_c5(0)
+        t0 = time.perf_counter()
+        res = sr.solve_fast(g)
+        out["solve_ms"] = (time.perf_counter() - t0) * 1e3
+        out["solve_iterations"] = int(res["iterations"])
+        out["solve_final_cost"] = float(res["final_cost"])
+        out["solve_kind"] = "Ceres stand-in: scipy SuperLU (symmetric mode, MMD) LM, Ceres-default tolerances, 1 thread"
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    import torch
+    from omniswarm_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    comp, mean = synth.pca_matrices(0)
+    state = (synth.superpoint_weights(0), synth.netvlad_weights(0), comp, mean,
+             synth.descriptor_db(args.db_rows, 4096, 1), None)
+    frames = [keyframe_images(s) for s in range(min(POOL, 2))]
+    steps = max(1, min(args.steps, 6))               # bounded sample: a CPU keyframe takes seconds
+    warm = max(1, min(args.warmup, 1))
+    for i in range(warm):
+        cpu_keyframe(state, *frames[i % len(frames)])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        cpu_keyframe(state, *frames[i % len(frames)])
+    dt = (time.perf_counter() - t0) / steps
+    val = 1.0 / dt
+    sample = (f"{steps} keyframes on {cores} host threads (torch CPU fp32 SuperPoint/NetVLAD, numpy scan, cross-check "
+              f"matcher): oracle port of the reference path; TensorRT/Ceres are not installable here")
+    line = {"impl": "reference", "metric": "keyframes/sec (SuperPoint+NetVLAD+match)", "value": val, "unit": "keyframes/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": val, "unit": "keyframes/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "C3: 4-view fisheye keyframe (8x SuperPoint 640x480 + 4x NetVLAD + stereo match + DB add + "
+                        f"IP top-k vs {args.db_rows}-row x 4096 f32 DB + rule + 4 local matches)",
+            "images_per_keyframe": 2 * N_DIRS, "db_rows": args.db_rows, "max_kpts": MAX_NUM, "sp_thres": 0.015,
+            "parallelism": f"drone-per-GPU x{world}" + (" + 1 NCCL all-gather of the keyframe record per step" if world > 1 else ""),
+            "l2_note": "per-step working set (activations ~1.3 GB + DB 164 MB) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from omniswarm_b200 import lib, synth, host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback in the product path)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = lib.load()
+    pk = peaks()
+    comp, mean = synth.pca_matrices(0)
+    spw = synth.flatten_sp_weights(synth.superpoint_weights(0))
+    nvw = synth.flatten_nv_weights(synth.netvlad_weights(0))
+    fe = host.KeyframeFrontend(spw, comp, mean, nvw, width=W, height=H, n_dirs=N_DIRS, max_num=MAX_NUM, sp_thres=0.015,
+                               self_id=rank, db_capacity=args.db_rows + 4096, inner_product_thres=0.3,
+                               match_index_dist=5, zero_bottom_quarter=True, accept_min_3d_pts=10)
+    st = torch.cuda.current_stream().cuda_stream
+
+    # ---- set-up (untimed): image pool in pinned host memory and in HBM; database preload ----
+    frames = [keyframe_images(100 * rank + s) for s in range(POOL)]
+    pin_up = [torch.from_numpy(f[0]).pin_memory() for f in frames]
+    pin_dn = [torch.from_numpy(f[1]).pin_memory() for f in frames]
+    dev_up = [t.cuda() for t in pin_up]
+    dev_dn = [t.cuda() for t in pin_dn]
+    rec_dev = torch.zeros(lib.RECORD_BYTES, dtype=torch.uint8, device="cuda")
+    res_dev = torch.zeros(lib.RESULT_BYTES, dtype=torch.uint8, device="cuda")
+    gathered = torch.zeros(world * lib.RECORD_BYTES, dtype=torch.uint8, device="cuda") if world > 1 else None
+    rec_host = torch.zeros(lib.RECORD_BYTES, dtype=torch.uint8).pin_memory()
+    res_host = torch.zeros(lib.RESULT_BYTES, dtype=torch.uint8).pin_memory()
+    # the pool keyframes go into the database first (so that every timed query is a revisit that hits), then
+    # random unit-norm rows with local descriptors up to db_rows
+    for i in range(POOL):
+        fe.extract(dev_up[i].data_ptr(), dev_dn[i].data_ptr(), 10_000 + i, rec_dev.data_ptr(), st, device_images=True)
+        fe.ingest(rec_dev.data_ptr(), 1, -1, st)
+    fe.finish(st)
+    n_fill = args.db_rows - fe.db_size(False)
+    chunk = 2000
+    for s in range(0, n_fill, chunk):
+        n = min(chunk, n_fill - s)
+        g = synth.descriptor_db(n, 4096, 50 + s + 7919 * rank)
+        ld = np.random.default_rng(s + rank).standard_normal((n, MAX_NUM, 64)).astype(np.float32)
+        fe.db_load(g, ld, np.full(n, MAX_NUM, np.int32), remote=False)
+    db_rows_start = fe.db_size(False)
+
+    def step_resident(i):
+        j = i % POOL
+        fe.extract(dev_up[j].data_ptr(), dev_dn[j].data_ptr(), i, rec_dev.data_ptr(), st, device_images=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rec_dev)
+            fe.ingest(gathered.data_ptr(), world, -1, st)
+        else:
+            fe.ingest(rec_dev.data_ptr(), 1, -1, st)
+        fe.query(rec_dev.data_ptr(), res_dev.data_ptr(), st)
+
+    def step_e2e(i):
+        j = i % POOL
+        if world == 1:
+            fe.process_raw(pin_up[j].data_ptr(), pin_dn[j].data_ptr(), i, rec_host.data_ptr(), res_host.data_ptr())
+        else:
+            fe.extract(pin_up[j].data_ptr(), pin_dn[j].data_ptr(), i, rec_dev.data_ptr(), st)
+            dist.all_gather_into_tensor(gathered, rec_dev)
+            fe.ingest(gathered.data_ptr(), world, -1, st)
+            fe.query(rec_dev.data_ptr(), res_dev.data_ptr(), st)
+            rec_host.copy_(rec_dev, non_blocking=True); res_host.copy_(res_dev, non_blocking=True)
+            fe.finish(st)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, base):
+        for i in range(warmup):
+            fn(base + i)
+        fe.finish(st)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = host.launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(base + warmup + i)
+        e1.record()
+        fe.finish(st)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = host.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    # ---- timed region 1: images resident in HBM ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total, launches = timed(step_resident, args.steps, args.warmup, 0)
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = world * 1e3 / ms_step
+
+    # ---- timed region 2: end to end through the host-buffer call (wall clock == device time: sync on both sides) ----
+    barrier()
+    for i in range(args.warmup):
+        step_e2e(50_000 + i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(60_000 + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * args.steps / e2e_s
+    res = lib.LoopResult.from_buffer_copy(res_host.numpy().tobytes())
+    rec = lib.KeyframeRecord.from_buffer_copy(rec_host.numpy().tobytes())
+
+    # ---- stage breakdown (CUDA events inside the library, one extra profiled pass; not part of `value`) ----
+    fe.set_profiling(True)
+    stage_acc = {}
+    for i in range(5):
+        step_resident(70_000 + i)
+        fe.finish(st)
+        for k, v in fe.stage_ms().items():
+            stage_acc.setdefault(k, []).append(v)
+    fe.set_profiling(False)
+    stages = {k: float(np.median(v)) for k, v in stage_acc.items()}
+    db_rows_now = fe.db_size(False)
+    db_rows_remote = fe.db_size(True)
+
+    # ---- rooflines ----
+    conv_ms = stages["superpoint_net"]
+    conv_tflops = 2 * N_DIRS * SP_GFLOP_PER_IMAGE / conv_ms  # GFLOP / ms = TFLOP/s
+    scan_ms = stages["db_scan"]
+    scan_bytes = (db_rows_now + db_rows_remote) * 4096 * 4.0        # local + remote database, each row read once
+    scan_gbs = scan_bytes / scan_ms / 1e6
+    roofline = {"kernel": "conv_ffma_kernel<3> (SuperPoint conv stack, fp32 CUDA-core implicit GEMM; tcgen05 path: see DESIGN.md)",
+                "bound": "tensor", "achieved": conv_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": conv_tflops / pk["bf16_tflops_sustained"], "traffic": None,
+                "algorithmic": f"{2 * N_DIRS} images x {SP_GFLOP_PER_IMAGE} GFLOP", "ms_per_launch_group": conv_ms,
+                "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)"}
+    roofline_match = {"kernel": "db_scan_kernel<1,4>", "bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm_gbs"],
+                      "unit": "GB/s", "frac": scan_gbs / pk["hbm_gbs"], "traffic": None,
+                      "algorithmic": f"({db_rows_now} local + {db_rows_remote} remote) rows x 16384 B", "ms": scan_ms, "peak_source": pk["source"],
+                      "note": "ms includes the remote-DB scan launch and both merge kernels"}
+
+    # ---- pose-graph solve (single GPU; replicas only) ----
+    solve = None
+    if not args.no_solve:
+        g = synth.pose_graph_c5(0)
+        solver = host.PoseGraphSolver(2048, 12288)
+        solver.solve(g)                                         # warm-up
+        times, summ = [], None
+        for _ in range(5):
+            poses, summ = solver.solve(g)
+            times.append(summ.solve_ms)
+        lin_bytes = 12000 * (2 * 32 + 8 + 160 + 36 * 8)
+        solve = {"solve_ms": float(np.median(times)), "iterations": int(summ.iterations),
+                 "pcg_iterations": int(summ.pcg_iterations), "final_cost": float(summ.final_cost),
+                 "termination": int(summ.termination), "graph": "C5: 2000 nodes / 12000 factors, Ceres-default tolerances",
+                 "max_err_vs_gt_m": float(np.abs(poses[:, :3] - g["gt"][:, :3]).max()),
+                 "us_per_pcg_iteration": float(np.median(times)) * 1e3 / max(1, summ.pcg_iterations),
+                 "note": "latency bound: 3 grid synchronisations per PCG iteration; whole problem lives in L2",
+                 "approx_bytes_per_linearisation": lin_bytes}
+
+    if rank == 0:
+        line = {"metric": "keyframes/sec (SuperPoint+NetVLAD+match)", "value": value, "unit": "keyframes/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, world), "gpu_launches": int(launches),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "keyframes/s",
+                        "h2d_bytes_per_step": 2 * N_DIRS * W * H, "d2h_bytes_per_step": lib.RECORD_BYTES + lib.RESULT_BYTES,
+                        "ms_per_step": e2e_s * 1e3 / args.steps},
+                "roofline": roofline, "roofline_match": roofline_match, "stage_ms": stages,
+                "loop_check": {"accepted": int(res.accepted), "hit_id": int(res.hit_id), "hit_score": float(res.hit_score),
+                               "n_kpts": list(rec.n_kpts), "n_matches": list(res.n_matches)},
+                "db_rows": int(db_rows_now), "db_rows_start": int(db_rows_start)}
+        if solve:
+            line["solve"] = solve
+            line["solve_ms"] = solve["solve_ms"]
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

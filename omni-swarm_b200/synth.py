@@ -219,7 +219,7 @@ def pose_graph(n_drones: int = 5, n_frames: int = 100, n_uwb: int | None = None,
     period 50 s, drones offset on a grid), plus a slow yaw so that yaw is exercised.
     Node index = frame * n_drones + drone.  Factor mix: ego-motion
     edges between consecutive frames of each drone (no loss), UWB distances between drones in the
-    same frame (Huber), loop edges between random frames of random drones within 8 m (Huber) and
+    same frame (Huber), loop edges from a keyframe to one of its 4 nearest stored keyframes (Huber) and
     detections-as-relative-pose between drones in the same frame (Huber).
     Noise model: simulator.launch:33-62 / swarm_local_sim.cpp:532-550,349-353.
     """
@@ -277,19 +277,21 @@ def pose_graph(n_drones: int = 5, n_frames: int = 100, n_uwb: int | None = None,
     # loops: relative pose with sqrt-information diag(1/sigma) (swarm_local_sim.cpp:459-465)
     loop_cov_pos, loop_cov_yaw = 0.003, 5.2e-4
     S_loop = np.diag([1 / math.sqrt(loop_cov_pos)] * 3 + [1 / math.sqrt(loop_cov_yaw)])
-    cnt = 0
-    guard = 0
-    while cnt < n_loop and guard < 100 * n_loop + 1000:
-        guard += 1
-        a, b = int(rng.integers(0, n_nodes)), int(rng.integers(0, n_nodes))
-        if a == b or np.linalg.norm(gt[a, :3] - gt[b, :3]) > 8.0:
-            continue
+    # as the simulator does (swarm_local_sim.cpp:474-529): a keyframe is linked to one of its nearest stored
+    # keyframe positions (any drone), excluding its own temporal neighbours
+    frame_of = np.arange(n_nodes) // nd
+    drone_of = np.arange(n_nodes) % nd
+    for _ in range(n_loop):
+        a = int(rng.integers(0, n_nodes))
+        dist = np.linalg.norm(gt[:, :3] - gt[a, :3], axis=1)
+        dist[(drone_of == drone_of[a]) & (np.abs(frame_of - frame_of[a]) <= 3)] = np.inf
+        near = np.argsort(dist, kind="stable")[:4]
+        b = int(near[int(rng.integers(0, 4))])
         meas = _delta_pose(gt[a], gt[b]) + rng.standard_normal(4) * np.sqrt([loop_cov_pos] * 3 + [loop_cov_yaw])
         if rng.uniform() < outlier_frac:
             meas[:3] += rng.uniform(-3, 3, 3)
         meas[3] = _wrap(meas[3])
         add(FACTOR_RELPOSE, a, b, np.concatenate([meas, S_loop.reshape(-1)]), 1)
-        cnt += 1
     # detections-as-relative-pose (solver.cpp:542-551): same frame, two drones
     det_cov_pos, det_cov_yaw = 0.01, 0.01
     S_det = np.diag([1 / math.sqrt(det_cov_pos)] * 3 + [1 / math.sqrt(det_cov_yaw)])

@@ -146,6 +146,13 @@ def num_residuals(g: dict) -> int:
     return n
 
 
+def _spd_solve(A, b):
+    """Sparse direct solve of the SPD normal equations (stand-in for Ceres' SPARSE_NORMAL_CHOLESKY,
+    solver.cpp:1698): SuperLU in symmetric mode with a minimum-degree ordering on A^T + A."""
+    import scipy.sparse.linalg as spla
+    return spla.splu(A, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True)).solve(b)
+
+
 def solve(g: dict, max_iters: int = 200, function_tol: float = 1e-14, gradient_tol: float = 1e-11,
           param_tol: float = 1e-12, verbose: bool = False):
     """Levenberg-Marquardt (Ceres-style step control) with a sparse direct solve.
@@ -189,7 +196,7 @@ def solve(g: dict, max_iters: int = 200, function_tol: float = 1e-14, gradient_t
         diag = np.clip(H.diagonal(), 1e-6, 1e32)
         while True:
             A = H + sp.diags(diag / radius)
-            delta = spla.splu(A.tocsc()).solve(-grad)
+            delta = _spd_solve(A.tocsc(), -grad)
             xn = x.copy()
             xn[free] += delta.reshape(-1, 4)
             new_cost = cost_only(g, xn)
@@ -228,3 +235,111 @@ def create_cov6d_sqrt_inf(cov6: np.ndarray) -> np.ndarray:
     cov4[:3, :3] = cov6[:3, :3]
     cov4[3, 3] = cov6[5, 5]
     return np.sqrt(np.abs(np.linalg.inv(cov4)))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Vectorised evaluation (same arithmetic as factor_residual_jacobian, batched with numpy) so that the CPU
+# baseline of bench.py is a fair "Ceres stand-in" rather than a Python-loop artefact.  DETECTION factors (rare)
+# fall back to the scalar routine.  tests/test_oracle_pins.py checks it against the scalar path.
+# --------------------------------------------------------------------------------------------------------------
+def evaluate_vec(g: dict, x: np.ndarray, want_jac: bool = True):
+    """-> cost, r [m,4], Ja [m,4,4], Jb [m,4,4] (robustified, rows beyond the factor's residual count zero)."""
+    ft, ia, ib, pl = g["ftype"], g["ia"], g["ib"], g["payload"]
+    m = len(ft)
+    r = np.zeros((m, 4)); Ja = np.zeros((m, 4, 4)); Jb = np.zeros((m, 4, 4))
+    pa, pb = x[ia], x[ib]
+    d_idx = np.nonzero(ft == FACTOR_DISTANCE)[0]
+    if len(d_idx):
+        d = pa[d_idx, :3] - pb[d_idx, :3]
+        nrm = np.sqrt((d * d).sum(1))
+        si = pl[d_idx, 1]
+        r[d_idx, 0] = (nrm - pl[d_idx, 0]) * si
+        if want_jac:
+            Ja[d_idx, 0, :3] = d * (si / nrm)[:, None]
+            Jb[d_idx, 0, :3] = -d * (si / nrm)[:, None]
+    p_idx = np.nonzero(ft == FACTOR_RELPOSE)[0]
+    if len(p_idx):
+        A, B, P = pa[p_idx], pb[p_idx], pl[p_idx]
+        c, s = np.cos(A[:, 3]), np.sin(A[:, 3])
+        d = B[:, :3] - A[:, :3]
+        est = np.stack([c * d[:, 0] + s * d[:, 1], -s * d[:, 0] + c * d[:, 1], d[:, 2],
+                        normalize_angle(B[:, 3] - A[:, 3])], 1)
+        e = P[:, 0:4] - est
+        e[:, 3] = normalize_angle(e[:, 3])
+        S = P[:, 4:20].reshape(-1, 4, 4)
+        r[p_idx] = np.einsum("nij,nj->ni", S, e)
+        if want_jac:
+            n = len(p_idx)
+            Ea = np.zeros((n, 4, 4)); Eb = np.zeros((n, 4, 4))
+            Eb[:, 0, 0] = c; Eb[:, 0, 1] = s; Eb[:, 1, 0] = -s; Eb[:, 1, 1] = c; Eb[:, 2, 2] = 1; Eb[:, 3, 3] = 1
+            Ea[:, :3, :3] = -Eb[:, :3, :3]
+            Ea[:, 0, 3] = -s * d[:, 0] + c * d[:, 1]
+            Ea[:, 1, 3] = -c * d[:, 0] - s * d[:, 1]
+            Ea[:, 3, 3] = -1
+            Ja[p_idx] = -np.einsum("nij,njk->nik", S, Ea)
+            Jb[p_idx] = -np.einsum("nij,njk->nik", S, Eb)
+    for f in np.nonzero(ft == FACTOR_DETECTION)[0]:
+        rr, ja, jb = factor_residual_jacobian(FACTOR_DETECTION, pa[f], pb[f], pl[f])
+        r[f, :len(rr)] = rr; Ja[f, :len(rr)] = ja; Jb[f, :len(rr)] = jb
+    s2 = (r * r).sum(1)
+    hub = (g["huber"] != 0) & (s2 > 1.0)
+    cost = 0.5 * s2[~hub].sum() + 0.5 * (2.0 * np.sqrt(s2[hub]) - 1.0).sum()
+    w = np.ones(m); w[hub] = 1.0 / np.sqrt(np.sqrt(s2[hub]))
+    r = r * w[:, None]
+    if want_jac:
+        Ja *= w[:, None, None]; Jb *= w[:, None, None]
+    return cost, r, Ja, Jb
+
+
+def solve_fast(g: dict, max_iters: int = 200, function_tol: float = 1e-6, gradient_tol: float = 1e-10,
+               param_tol: float = 1e-8, num_threads: int | None = None):
+    """Same LM as solve(), vectorised; default tolerances = Ceres defaults (the configuration the reference runs,
+    solver.cpp:1695-1706)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    x = g["init"].astype(np.float64).copy()
+    n = x.shape[0]
+    m = len(g["ftype"])
+    free = np.nonzero(g["fixed"] == 0)[0]
+    col_of = -np.ones(n, np.int64); col_of[free] = np.arange(len(free))
+    nv = 4 * len(free)
+    ia, ib = g["ia"], g["ib"]
+    rows = (np.arange(m)[:, None, None] * 4 + np.arange(4)[None, :, None]) + np.zeros((1, 1, 4), np.int64)
+    ca = (col_of[ia][:, None, None] * 4 + np.arange(4)[None, None, :]) + np.zeros((1, 4, 1), np.int64)
+    cb = (col_of[ib][:, None, None] * 4 + np.arange(4)[None, None, :]) + np.zeros((1, 4, 1), np.int64)
+    ma = np.broadcast_to((col_of[ia] >= 0)[:, None, None], (m, 4, 4))
+    mb = np.broadcast_to((col_of[ib] >= 0)[:, None, None], (m, 4, 4))
+    R = np.concatenate([rows[ma], rows[mb]]); Cc = np.concatenate([ca[ma], cb[mb]])
+    radius, decrease = 1e4, 2.0
+    cost, r, Ja, Jb = evaluate_vec(g, x)
+    initial_cost = cost
+    it = 0
+    for it in range(1, max_iters + 1):
+        J = sp.csr_matrix((np.concatenate([Ja[ma], Jb[mb]]), (R, Cc)), shape=(4 * m, nv))
+        rv = r.reshape(-1)
+        grad = J.T @ rv
+        if np.max(np.abs(grad)) < gradient_tol:
+            break
+        H = (J.T @ J).tocsc()
+        diag = np.clip(H.diagonal(), 1e-6, 1e32)
+        ok = False
+        while radius > 1e-32:
+            delta = _spd_solve((H + sp.diags(diag / radius)).tocsc(), -grad)
+            xn = x.copy(); xn[free] += delta.reshape(-1, 4)
+            new_cost = evaluate_vec(g, xn, want_jac=False)[0]
+            model = -(grad @ delta) - 0.5 * (delta @ (H @ delta))
+            rho = (cost - new_cost) / model if model > 0 else -1.0
+            if rho > 1e-3:
+                radius = min(radius / max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3), 1e16); decrease = 2.0
+                ok = True
+                break
+            radius /= decrease; decrease *= 2.0
+        if not ok:
+            break
+        dcost, step = cost - new_cost, np.linalg.norm(delta)
+        x = xn
+        old = cost
+        cost, r, Ja, Jb = evaluate_vec(g, x)
+        if abs(dcost) < function_tol * old or step < param_tol * (np.linalg.norm(x[free]) + param_tol):
+            break
+    return dict(poses=x, final_cost=cost, initial_cost=initial_cost, iterations=it, n_residuals=num_residuals(g))

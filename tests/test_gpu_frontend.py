@@ -45,7 +45,7 @@ def oracle_record(up, down):
 
 
 def test_process_record_matches_oracle(gpu):
-    fe = make_frontend()
+    fe = make_frontend(match_index_dist=5)      # reference default: the 4 rows a keyframe just added are skipped
     up, down = frame_images(1)
     rec, res = fe.process(up, down, msg_id=77)
     ref = oracle_record(up, down)
