@@ -203,7 +203,7 @@ def workload_config(args, world):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from omniswarm_b200 import lib, synth, host
+    from omniswarm_b200 import lib, synth, host, swarm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -252,7 +252,7 @@ def run_ours(args):
         j = i % POOL
         fe.extract(dev_up[j].data_ptr(), dev_dn[j].data_ptr(), i, rec_dev.data_ptr(), st, device_images=True)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, rec_dev)
+            swarm.exchange_records(rec_dev, gathered)          # the ONE collective of the path (NCCL all-gather)
             fe.ingest(gathered.data_ptr(), world, -1, st)
         else:
             fe.ingest(rec_dev.data_ptr(), 1, -1, st)
@@ -264,7 +264,7 @@ def run_ours(args):
             fe.process_raw(pin_up[j].data_ptr(), pin_dn[j].data_ptr(), i, rec_host.data_ptr(), res_host.data_ptr())
         else:
             fe.extract(pin_up[j].data_ptr(), pin_dn[j].data_ptr(), i, rec_dev.data_ptr(), st)
-            dist.all_gather_into_tensor(gathered, rec_dev)
+            swarm.exchange_records(rec_dev, gathered)
             fe.ingest(gathered.data_ptr(), world, -1, st)
             fe.query(rec_dev.data_ptr(), res_dev.data_ptr(), st)
             rec_host.copy_(rec_dev, non_blocking=True); res_host.copy_(res_dev, non_blocking=True)

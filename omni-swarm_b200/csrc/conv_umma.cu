@@ -1,0 +1,481 @@
+// conv_umma.cu -- SuperPoint convolutions on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+// Layers: swarm_loop/superpoint.ipynb:143-158 of the reference (3x3 pad 1 and 1x1 convolutions, NHWC here).
+//
+// Implicit GEMM, one CTA tile = 8 x 16 output pixels (M = 128) x all output channels (N = Cout, 64..256):
+//   * A operand: for every filter tap (ky,kx) and every 64-channel slab, ONE TMA box {64 ch, 16 x, 8 y, 1 image}
+//     fetched at the tap-shifted coordinate; out-of-image elements are zero-filled by the TMA unit, which is the
+//     convolution's zero padding.  The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle,
+//     i.e. exactly the canonical K-major SWIZZLE_128B UMMA layout (im2col staging is done by the copy engine).
+//   * B operand: the weight slab [N][64] of the same tap, K-major SWIZZLE_128B, by TMA.
+//   * D: fp32 accumulators in TMEM (128 lanes x N columns), double buffered so the epilogue of tile t overlaps
+//     the MMAs of tile t+1.
+// Precision: parity with the fp32 oracle needs ~1e-6 relative error, which fp16/bf16 operands cannot give.  Every
+// fp32 operand x is carried as TWO fp16 planes  hi = fp16(s*x), lo = fp16(s*x - hi)  (s a power of two, exact), and
+// each K step issues three MMAs  hi*hi + lo*hi + hi*lo  into the same accumulator (the dropped lo*lo term is 2^-22
+// relative).  Both planes together are 4 bytes per element -- the same HBM/L2 footprint as fp32 activations -- and
+// the three fp16 MMAs cost 1.5x one TF32 MMA.  Measured against the oracle: see tests/test_gpu_superpoint.py.
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane each), warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (tcgen05.ld -> bias/ReLU -> re-split -> NHWC stores).  Persistent over tiles.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "kernels.cuh"
+#include "conv_umma.cuh"
+
+namespace osb {
+
+constexpr int UM_TH = 8, UM_TW = 16;            // output tile (pixels)
+constexpr int UM_KC = 64;                       // fp16 channels per K slab (= 128 bytes = one swizzle row)
+constexpr int UM_A_BYTES = UM_TH * UM_TW * 128; // 16 KB per plane per stage
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    // a pipeline bug must surface as a launch failure, never as a hung GPU (try_wait itself blocks for a while)
+    if (!done && ++spins > (1u << 24)) __trap();
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(16B units)=1 <<16 |
+// SBO = 1024 B (8 rows x 128 B) <<32 | version 1 <<46 | layout SWIZZLE_128B (2) <<61
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int N>
+struct UmmaCfg {
+  static constexpr int B_BYTES = N * 128;                        // one weight plane per stage
+  static constexpr int STAGE_BYTES = 2 * UM_A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (N <= 64) ? 4 : (N <= 128) ? 3 : 2;
+  static constexpr int TMEM_COLS = (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+struct UmmaArgs {
+  const float* bias;       // [N]
+  __half* out_hi;          // NHWC planes of the next layer (or null)
+  __half* out_lo;
+  float* out_f32;          // fp32 output [pixels][out_cstride] (or null)
+  int H, W, B;
+  int ks;                  // 1 or 3
+  int cin_slabs;           // Cin / 64
+  int out_c;               // channels stored per pixel (<= N)
+  int out_cstride;         // channel stride of the destination
+  float inv_scale;         // 1 / (act_scale * w_scale)
+  float out_scale;         // scale of the stored fp16 planes
+  int relu;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, UmmaArgs P) {
+  using Cfg = UmmaCfg<N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;     // 8-byte barriers
+  // barrier map: full[s] = bar_base + 8 s ; empty[s] = + 8 (STAGES + s) ; tmem_full[a] ; tmem_empty[a]
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = (P.W + UM_TW - 1) / UM_TW, tiles_y = (P.H + UM_TH - 1) / UM_TH;
+  const int n_tiles = P.B * tiles_x * tiles_y;
+  const int taps = P.ks * P.ks, halo = P.ks / 2;
+  const int k_steps = taps * P.cin_slabs;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+      const int x0 = tx * UM_TW, y0 = ty * UM_TH;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int ky = tap / P.ks, kx = tap % P.ks;
+        for (int cs = 0; cs < P.cin_slabs; ++cs) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          tma_load_4d(sa, &tm_a_hi, full_bar(stage), cs * UM_KC, x0 + kx - halo, y0 + ky - halo, b);
+          tma_load_4d(sa + UM_A_BYTES, &tm_a_lo, full_bar(stage), cs * UM_KC, x0 + kx - halo, y0 + ky - halo, b);
+          tma_load_3d(sa + 2 * UM_A_BYTES, &tm_w_hi, full_bar(stage), cs * UM_KC, 0, tap);
+          tma_load_3d(sa + 2 * UM_A_BYTES + Cfg::B_BYTES, &tm_w_lo, full_bar(stage), cs * UM_KC, 0, tap);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = f16 (0), K-major both,
+    // N >> 3 at bit 17, M >> 4 at bit 24
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+      for (int ks = 0; ks < k_steps; ++ks) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+        const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + UM_A_BYTES);
+        const uint64_t b_hi = umma_desc_sw128(sa + 2 * UM_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * UM_A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < UM_KC / 16; ++k) {
+          const uint64_t adv = (uint64_t)(k * 32 >> 4);       // advance 16 fp16 = 32 bytes inside the swizzle row
+          umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, (ks | k) ? 1u : 0u);
+          umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+          umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+        }
+        umma_commit(empty_bar(stage));                         // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull_bar(acc));                             // accumulator complete -> epilogue
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                                    // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;                               // output pixel within the tile
+    const int r = m / UM_TW, c = m % UM_TW;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+      const int y = ty * UM_TH + r, x = tx * UM_TW + c;
+      const bool inside = (y < P.H) && (x < P.W);
+      const size_t pix = ((size_t)b * P.H + y) * P.W + x;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
+#pragma unroll 1
+      for (int n0 = 0; n0 < N; n0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + n0, v);
+        if (!inside || n0 >= P.out_c) continue;
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a = fmaf(__uint_as_float(v[i]), P.inv_scale, __ldg(P.bias + n0 + i));
+          if (P.relu) a = fmaxf(a, 0.f);
+          f[i] = a;
+        }
+        if (P.out_f32) {
+          float4* dst = reinterpret_cast<float4*>(P.out_f32 + pix * P.out_cstride + n0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        } else {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float s0 = f[2 * i] * P.out_scale, s1 = f[2 * i + 1] * P.out_scale;
+            const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
+            const __half l0 = __float2half_rn(s0 - __half2float(h0)), l1 = __float2half_rn(s1 - __half2float(h1));
+            hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          }
+          uint4* dh = reinterpret_cast<uint4*>(P.out_hi + pix * P.out_cstride + n0);
+          uint4* dl = reinterpret_cast<uint4*>(P.out_lo + pix * P.out_cstride + n0);
+          dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));              // 4 epilogue warps -> count 4
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// first layer (Cin = 1) and 2x2 max-pool on split planes, re-split after the fp32 op
+// --------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_store8(__half* hi, __half* lo, const float* f, float scale) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float s0 = f[2 * i] * scale, s1 = f[2 * i + 1] * scale;
+    const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
+    const __half l0 = __float2half_rn(s0 - __half2float(h0)), l1 = __float2half_rn(s1 - __half2float(h1));
+    h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  }
+  *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(128)
+conv_first_split_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ lut,
+                        const uint8_t* __restrict__ img, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                        int H, int W, float out_scale) {
+  __shared__ __align__(16) float sw[9][64];
+  __shared__ __align__(16) float sb[64];
+  __shared__ float slut[256];
+  for (int e = threadIdx.x; e < 9 * 64; e += blockDim.x) (&sw[0][0])[e] = w[e];
+  for (int e = threadIdx.x; e < 64; e += blockDim.x) sb[e] = bias[e];
+  for (int e = threadIdx.x; e < 256; e += blockDim.x) slut[e] = lut[e];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  const int oy = p / W, ox = p % W;
+  const uint8_t* ib = img + (size_t)b * H * W;
+  float in[9];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int gy = oy + ky - 1, gx = ox + kx - 1;
+      in[ky * 3 + kx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? slut[ib[(size_t)gy * W + gx]] : 0.f;
+    }
+  __half* dh = out_hi + ((size_t)b * H * W + p) * 64;
+  __half* dl = out_lo + ((size_t)b * H * W + p) * 64;
+#pragma unroll 2
+  for (int o8 = 0; o8 < 8; ++o8) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) a = fmaf(in[t], sw[t][8 * o8 + j], a);
+      r[j] = fmaxf(a + sb[8 * o8 + j], 0.f);
+    }
+    split_store8(dh + 8 * o8, dl + 8 * o8, r, out_scale);
+  }
+}
+
+// one thread per (output pixel, 8 channels)
+__global__ void maxpool_split_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int C8,
+                                     int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int Ho = H / 2, Wo = W / 2;
+  const int c = (int)(i % C8);
+  int64_t p = i / C8;
+  const int ox = (int)(p % Wo); p /= Wo;
+  const int oy = (int)(p % Ho);
+  const int b = (int)(p / Ho);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const size_t off = ((((size_t)b * H + 2 * oy + dy) * W + 2 * ox + dx) * C8 + c) * 8;
+      const uint4 h = *reinterpret_cast<const uint4*>(in_hi + off);
+      const uint4 l = *reinterpret_cast<const uint4*>(in_lo + off);
+      const uint32_t hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a0 = __half2float(__ushort_as_half((unsigned short)(hv[j] & 0xffff))) +
+                         __half2float(__ushort_as_half((unsigned short)(lv[j] & 0xffff)));
+        const float a1 = __half2float(__ushort_as_half((unsigned short)(hv[j] >> 16))) +
+                         __half2float(__ushort_as_half((unsigned short)(lv[j] >> 16)));
+        m[2 * j] = fmaxf(m[2 * j], a0); m[2 * j + 1] = fmaxf(m[2 * j + 1], a1);
+      }
+    }
+  // the planes already carry the scale: max commutes with the positive scale, re-split with scale 1
+  split_store8(out_hi + (size_t)i * 8, out_lo + (size_t)i * 8, m, 1.0f);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+static osb_status make_tmap(CUtensorMap* tm, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("conv_umma", "cuTensorMapEncodeTiled entry point not available"); return OSB_ERR_CUDA; }
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    set_error("conv_umma", buf);
+    return OSB_ERR_CUDA;
+  }
+  return OSB_OK;
+}
+
+osb_status umma_layer_upload(UmmaLayer* L, const float* w_oihw, const float* bias, int cin, int cout, int ks,
+                             float w_scale) {
+  L->cin = cin; L->cout = cout; L->ks = ks; L->taps = ks * ks; L->w_scale = w_scale;
+  L->n_pad = (cout <= 64) ? 64 : (cout <= 80) ? 80 : (cout <= 128) ? 128 : 256;
+  OSB_REQUIRE(cin % UM_KC == 0 && cout <= 256, "tcgen05 conv: Cin must be a multiple of 64 and Cout <= 256");
+  const size_t n = (size_t)L->taps * L->n_pad * cin;
+  std::vector<__half> hi(n, __float2half(0.f)), lo(n, __float2half(0.f));
+  std::vector<float> bp(L->n_pad, 0.f);
+  for (int o = 0; o < cout; ++o) {
+    bp[o] = bias[o];
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < L->taps; ++t) {
+        const float s = w_oihw[((size_t)o * cin + c) * L->taps + t] * w_scale;
+        const __half h = __float2half_rn(s);
+        const size_t idx = ((size_t)t * L->n_pad + o) * cin + c;
+        hi[idx] = h;
+        lo[idx] = __float2half_rn(s - __half2float(h));
+      }
+  }
+  OSB_CUDA(cudaMalloc(&L->w_hi, n * sizeof(__half)));
+  OSB_CUDA(cudaMalloc(&L->w_lo, n * sizeof(__half)));
+  OSB_CUDA(cudaMalloc(&L->bias, L->n_pad * sizeof(float)));
+  OSB_CUDA(cudaMemcpy(L->w_hi, hi.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+  OSB_CUDA(cudaMemcpy(L->w_lo, lo.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+  OSB_CUDA(cudaMemcpy(L->bias, bp.data(), L->n_pad * sizeof(float), cudaMemcpyHostToDevice));
+  const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)L->n_pad, (uint64_t)L->taps};
+  const uint64_t strides[2] = {(uint64_t)cin * 2, (uint64_t)cin * L->n_pad * 2};
+  const uint32_t box[3] = {UM_KC, (uint32_t)L->n_pad, 1};
+  osb_status s;
+  if ((s = make_tmap(&L->tm_hi, L->w_hi, 3, dims, strides, box)) != OSB_OK) return s;
+  return make_tmap(&L->tm_lo, L->w_lo, 3, dims, strides, box);
+}
+
+void umma_layer_free(UmmaLayer* L) {
+  cudaFree(L->w_hi); cudaFree(L->w_lo); cudaFree(L->bias);
+  L->w_hi = L->w_lo = nullptr; L->bias = nullptr;
+}
+
+osb_status umma_act_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half* p_lo, int B, int H, int W, int C) {
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  const uint32_t box[4] = {UM_KC, UM_TW, UM_TH, 1};
+  osb_status s;
+  if ((s = make_tmap(hi, p_hi, 4, dims, strides, box)) != OSB_OK) return s;
+  return make_tmap(lo, p_lo, 4, dims, strides, box);
+}
+
+template <int N>
+static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const UmmaLayer& L, const UmmaArgs& P,
+                              cudaStream_t st) {
+  using Cfg = UmmaCfg<N>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    OSB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles = P.B * cdiv(P.W, UM_TW) * cdiv(P.H, UM_TH);
+  const int grid = std::min(tiles, num_sms());
+  OSB_LAUNCH((conv_umma_kernel<N>), grid, 256, Cfg::SMEM_BYTES, st, a_hi, a_lo, L.tm_hi, L.tm_lo, P);
+  OSB_CHECK_LAUNCH();
+  return OSB_OK;
+}
+
+osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int B, int H, int W,
+                             float act_scale, __half* out_hi, __half* out_lo, float* out_f32, int out_c, int out_cstride,
+                             float out_scale, int relu, cudaStream_t st) {
+  UmmaArgs P;
+  P.bias = L.bias; P.out_hi = out_hi; P.out_lo = out_lo; P.out_f32 = out_f32;
+  P.H = H; P.W = W; P.B = B; P.ks = L.ks; P.cin_slabs = L.cin / UM_KC;
+  P.out_c = out_c; P.out_cstride = out_cstride;
+  P.inv_scale = 1.0f / (act_scale * L.w_scale); P.out_scale = out_scale; P.relu = relu;
+  OSB_REQUIRE(out_c % 16 == 0 && out_c <= L.n_pad && out_cstride % 8 == 0, "tcgen05 conv: bad output channel layout");
+  switch (L.n_pad) {
+    case 64: return launch_umma<64>(a_hi, a_lo, L, P, st);
+    case 80: return launch_umma<80>(a_hi, a_lo, L, P, st);
+    case 128: return launch_umma<128>(a_hi, a_lo, L, P, st);
+    case 256: return launch_umma<256>(a_hi, a_lo, L, P, st);
+  }
+  set_error("umma_conv_forward", "unsupported N");
+  return OSB_ERR_INVALID;
+}
+
+osb_status umma_first_forward(const float* w_tap_cout, const float* bias, const float* lut, const uint8_t* img,
+                              __half* out_hi, __half* out_lo, int B, int H, int W, float out_scale, cudaStream_t st) {
+  dim3 grid(cdiv(H * W, 128), B);
+  OSB_LAUNCH(conv_first_split_kernel, grid, 128, 0, st, w_tap_cout, bias, lut, img, out_hi, out_lo, H, W, out_scale);
+  OSB_CHECK_LAUNCH();
+  return OSB_OK;
+}
+
+osb_status umma_maxpool_forward(const __half* in_hi, const __half* in_lo, __half* out_hi, __half* out_lo, int B, int H,
+                                int W, int C, cudaStream_t st) {
+  const int64_t total = (int64_t)B * (H / 2) * (W / 2) * (C / 8);
+  OSB_LAUNCH(maxpool_split_kernel, (unsigned)cdiv64(total, 256), 256, 0, st, in_hi, in_lo, out_hi, out_lo, H, W, C / 8, total);
+  OSB_CHECK_LAUNCH();
+  return OSB_OK;
+}
+
+}  // namespace osb

@@ -105,27 +105,44 @@ db_scan_kernel(const float* __restrict__ db, int64_t n_val, const int64_t* __res
   }
 }
 
-// merge: one CTA per query ranks the grid*k candidates (valid ones only) and writes the global top-k.
+// merge: one CTA per query ranks the grid*k candidates (valid ones only) and writes the global top-k.  Candidates are
+// staged in shared memory in chunks, so the inner rank-counting loop reads broadcast shared-memory words.
+constexpr int MERGE_CHUNK = 2048;
 __global__ void __launch_bounds__(1024)
 db_merge_kernel(const float* __restrict__ part_scores, const int64_t* __restrict__ part_ids, int ncand, int k,
                 float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  __shared__ float cs[MERGE_CHUNK];
+  __shared__ int64_t ci[MERGE_CHUNK];
   const int qq = blockIdx.x;
   const float* ps = part_scores + (size_t)qq * ncand;
   const int64_t* pi = part_ids + (size_t)qq * ncand;
   for (int i = threadIdx.x; i < k; i += blockDim.x) { out_scores[qq * k + i] = -INFINITY; out_ids[qq * k + i] = -1; }
-  __syncthreads();
-  for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
-    const int64_t idi = pi[i];
-    if (idi < 0) continue;
-    const float si = ps[i];
-    int rank = 0;
-    for (int j = 0; j < ncand; ++j) {
-      const int64_t idj = __ldg(pi + j);
-      const float sj = __ldg(ps + j);
-      rank += (idj >= 0) && ((sj > si) || (sj == si && idj < idi));
-    }
-    if (rank < k) { out_scores[qq * k + rank] = si; out_ids[qq * k + rank] = idi; }
+  // every thread owns up to PER candidates (ncand <= PER * blockDim.x is guaranteed by the launcher)
+  constexpr int PER = 8;
+  float my_s[PER]; int64_t my_i[PER]; int rank[PER];
+#pragma unroll
+  for (int t = 0; t < PER; ++t) {
+    const int i = threadIdx.x + t * blockDim.x;
+    my_i[t] = (i < ncand) ? pi[i] : -1;
+    my_s[t] = (i < ncand) ? ps[i] : -INFINITY;
+    rank[t] = 0;
   }
+  for (int c0 = 0; c0 < ncand; c0 += MERGE_CHUNK) {
+    const int cn = min(MERGE_CHUNK, ncand - c0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cn; j += blockDim.x) { cs[j] = ps[c0 + j]; ci[j] = pi[c0 + j]; }
+    __syncthreads();
+    for (int j = 0; j < cn; ++j) {
+      const float sj = cs[j];
+      const int64_t idj = ci[j];
+      if (idj < 0) continue;
+#pragma unroll
+      for (int t = 0; t < PER; ++t) rank[t] += (sj > my_s[t]) || (sj == my_s[t] && idj < my_i[t]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < PER; ++t)
+    if (my_i[t] >= 0 && rank[t] < k) { out_scores[qq * k + rank[t]] = my_s[t]; out_ids[qq * k + rank[t]] = my_i[t]; }
 }
 
 template <int Q>
@@ -169,6 +186,7 @@ osb_status db_search_device(const float* rows, int64_t n, const int64_t* n_dev, 
     else if (nb <= 4) s = launch_scan<4>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, st);
     else s = launch_scan<8>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, st);
     if (s != OSB_OK) return s;
+    if (grid * k > 8 * 1024) { set_error("db_search", "too many partial candidates for the merge kernel"); return OSB_ERR_CAPACITY; }
     OSB_LAUNCH(db_merge_kernel, nb, 1024, 0, st, part_scores, part_ids, grid * k, k, scores_dev + (size_t)q0 * k,
                ids_dev + (size_t)q0 * k);
     OSB_CHECK_LAUNCH();

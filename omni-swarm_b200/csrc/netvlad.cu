@@ -3,7 +3,7 @@
 // The reference only fixes the I/O contract (HxW float 0..255 in, 4096 floats out); the hfnet MobileNetVLAD
 // architecture is not in the repository.  The stand-in pinned here (and in oracle/frontend_ref.py::netvlad_net):
 //   conv0 3x3 s2 1->32 ReLU6 | 7 x [depthwise 3x3 (s) ReLU6 + pointwise 1x1 ReLU6] -> 512 ch at 1/16 resolution |
-//   1x1 projection to D=128, per-location L2 norm | NetVLAD K=32: soft-assign (1x1 conv + softmax),
+//   1x1 projection to D=128, per-image centring (x - mean over locations), per-location L2 norm | NetVLAD K=32: soft-assign (1x1 conv + softmax),
 //   residual aggregation, intra-normalisation, flatten (K*D = 4096), L2 norm.
 #include "superpoint.cuh"
 
@@ -37,22 +37,74 @@ __global__ void nv_softmax_kernel(float* __restrict__ a, int64_t locs) {
   for (int k = 0; k < NV_K; ++k) p[k] = v[k] / s;
 }
 
-// VLAD aggregation + intra-norm + final L2: one CTA (1024 threads) per image; warp = cluster k, lane = 4 dims
+// per-image, per-channel mean of the projected features over all locations (instance centring): thread = channel
+__global__ void __launch_bounds__(NV_D)
+nv_colmean_kernel(const float* __restrict__ x, int P, float* __restrict__ mu) {
+  const int b = blockIdx.x, ch = threadIdx.x;
+  const float* xb = x + (size_t)b * P * NV_D;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int p = 0;
+  for (; p + 3 < P; p += 4) {
+    s0 += xb[(size_t)p * NV_D + ch]; s1 += xb[(size_t)(p + 1) * NV_D + ch];
+    s2 += xb[(size_t)(p + 2) * NV_D + ch]; s3 += xb[(size_t)(p + 3) * NV_D + ch];
+  }
+  for (; p < P; ++p) s0 += xb[(size_t)p * NV_D + ch];
+  mu[b * NV_D + ch] = ((s0 + s1) + (s2 + s3)) / (float)P;
+}
+
+// x <- (x - mu[image]) / ||x - mu[image]||_2 per location; one warp per location, lane = 4 channels
+__global__ void nv_center_norm_kernel(float* __restrict__ x, const float* __restrict__ mu, int P, int64_t locs) {
+  const int64_t loc = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (loc >= locs) return;
+  const int b = (int)(loc / P);
+  float4 v = reinterpret_cast<float4*>(x + (size_t)loc * NV_D)[lane];
+  const float4 m = reinterpret_cast<const float4*>(mu + (size_t)b * NV_D)[lane];
+  v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
+  float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  s = warp_sum(s);
+  const float n = sqrtf(s);
+  v.x /= n; v.y /= n; v.z /= n; v.w /= n;
+  reinterpret_cast<float4*>(x + (size_t)loc * NV_D)[lane] = v;
+}
+
+// VLAD aggregation, stage 1: grid (image, slice); warp = cluster k, lane = 4 dims; partial sums over a slice of the
+// locations (fixed partition -> deterministic), written to part[b][slice][k][d] and psum[b][slice][k]
+constexpr int NV_SLICES = 8;
 __global__ void __launch_bounds__(1024)
-nv_vlad_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ cent, int P,
-               float* __restrict__ out) {
-  __shared__ float red[32];
-  const int b = blockIdx.x, k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+nv_vlad_partial_kernel(const float* __restrict__ x, const float* __restrict__ a, int P, float* __restrict__ part,
+                       float* __restrict__ psum) {
+  const int b = blockIdx.x, sl = blockIdx.y, k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = (P + NV_SLICES - 1) / NV_SLICES;
+  const int p0 = sl * per, p1 = min(P, p0 + per);
   const float* xb = x + (size_t)b * P * NV_D;
   const float* ab = a + (size_t)b * P * NV_K;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float asum = 0.f;
-  for (int p = 0; p < P; ++p) {
+#pragma unroll 4
+  for (int p = p0; p < p1; ++p) {
     const float w = __ldg(ab + (size_t)p * NV_K + k);
     const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)p * NV_D) + lane);
     acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
     acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
     asum += w;
+  }
+  reinterpret_cast<float4*>(part + (((size_t)b * NV_SLICES + sl) * NV_K + k) * NV_D)[lane] = acc;
+  if (lane == 0) psum[((size_t)b * NV_SLICES + sl) * NV_K + k] = asum;
+}
+
+// stage 2: sum the slices, subtract asum * centroid, intra-normalise, flatten, L2-normalise; one CTA per image
+__global__ void __launch_bounds__(1024)
+nv_vlad_final_kernel(const float* __restrict__ part, const float* __restrict__ psum, const float* __restrict__ cent,
+                     float* __restrict__ out) {
+  __shared__ float red[32];
+  const int b = blockIdx.x, k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float asum = 0.f;
+  for (int sl = 0; sl < NV_SLICES; ++sl) {
+    const float4 v = reinterpret_cast<const float4*>(part + (((size_t)b * NV_SLICES + sl) * NV_K + k) * NV_D)[lane];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    asum += psum[((size_t)b * NV_SLICES + sl) * NV_K + k];
   }
   const float4 c = reinterpret_cast<const float4*>(cent + (size_t)k * NV_D)[lane];
   acc.x -= asum * c.x; acc.y -= asum * c.y; acc.z -= asum * c.z; acc.w -= asum * c.w;
@@ -126,6 +178,9 @@ osb_status NetVLAD::init(const float* weights, size_t n_weights, int width, int 
   OSB_CUDA(cudaMalloc(&actB, act * sizeof(float)));
   OSB_CUDA(cudaMalloc(&d_assign, B * (H / 16) * (W / 16) * NV_K * sizeof(float)));
   OSB_CUDA(cudaMalloc(&d_out, B * NV_K * NV_D * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&d_mu, B * NV_D * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&d_part, B * NV_SLICES * NV_K * NV_D * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&d_psum, B * NV_SLICES * NV_K * sizeof(float)));
   return OSB_OK;
 }
 
@@ -134,6 +189,7 @@ void NetVLAD::release() {
   for (int i = 0; i < 7; ++i) { cudaFree(blk[i].dw); cudaFree(blk[i].dwb); conv_layer_free(&blk[i].pw); }
   conv_layer_free(&proj); conv_layer_free(&assign);
   cudaFree(d_img); cudaFree(actA); cudaFree(actB); cudaFree(d_assign); cudaFree(d_out);
+  cudaFree(d_mu); cudaFree(d_part); cudaFree(d_psum);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -149,12 +205,17 @@ osb_status NetVLAD::infer_dev(const uint8_t* img_dev, int B, float* out_dev, cud
     RUN(conv_forward(blk[i].pw, actB, actA, B, h, w, blk[i].cout, ACT_RELU6, st));
   }
   RUN(conv_forward(proj, actA, actB, B, h, w, NV_D, ACT_NONE, st));
-  RUN(l2norm_cells(actB, (int64_t)B * h * w, NV_D, st));
-  RUN(conv_forward(assign, actB, d_assign, B, h, w, NV_K, ACT_NONE, st));
   const int64_t locs = (int64_t)B * h * w;
+  OSB_LAUNCH(nv_colmean_kernel, B, NV_D, 0, st, actB, h * w, d_mu);
+  OSB_CHECK_LAUNCH();
+  OSB_LAUNCH(nv_center_norm_kernel, (unsigned)cdiv64(locs * 32, 256), 256, 0, st, actB, d_mu, h * w, locs);
+  OSB_CHECK_LAUNCH();
+  RUN(conv_forward(assign, actB, d_assign, B, h, w, NV_K, ACT_NONE, st));
   OSB_LAUNCH(nv_softmax_kernel, (unsigned)cdiv64(locs, 128), 128, 0, st, d_assign, locs);
   OSB_CHECK_LAUNCH();
-  OSB_LAUNCH(nv_vlad_kernel, B, 1024, 0, st, actB, d_assign, centroids, h * w, out_dev);
+  OSB_LAUNCH(nv_vlad_partial_kernel, dim3(B, NV_SLICES), 1024, 0, st, actB, d_assign, h * w, d_part, d_psum);
+  OSB_CHECK_LAUNCH();
+  OSB_LAUNCH(nv_vlad_final_kernel, B, 1024, 0, st, d_part, d_psum, centroids, out_dev);
   OSB_CHECK_LAUNCH();
 #undef RUN
   return OSB_OK;

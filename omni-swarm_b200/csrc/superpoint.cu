@@ -4,12 +4,16 @@
 // stays in HBM; the reference copied 1.2 MB + 4.9 MB per image back to the host and post-processed on the CPU
 // (swarm_loop/src/tensorrt_generic.cpp:58-75).
 #include "superpoint.cuh"
+#include <stdlib.h>
 
 namespace osb {
 
 static const int SP_CIN[12] = {1, 64, 64, 64, 64, 128, 128, 128, 128, 256, 128, 256};
 static const int SP_COUT[12] = {64, 64, 64, 64, 128, 128, 128, 128, 256, 65, 256, 256};
 static const int SP_KS[12] = {3, 3, 3, 3, 3, 3, 3, 3, 3, 1, 3, 1};
+// power-of-two scales of the split-fp16 planes (exact): activations (post-ReLU, O(1)) x 16, weights (O(0.05)) x 1024
+constexpr float SP_ACT_SCALE = 16.f;
+constexpr float SP_W_SCALE = 1024.f;
 
 size_t sp_expected_weights() {
   size_t n = 0;
@@ -39,10 +43,19 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
     OSB_CUDA(cudaMemcpy(b1a, p + 64 * 9, 64 * sizeof(float), cudaMemcpyHostToDevice));
     p += 64 * 9 + 64;
   }
+  {
+    // OSB_SP_CONV=ffma selects the fp32 CUDA-core convolutions (debug / A-B parity); default = tcgen05 path
+    const char* e = getenv("OSB_SP_CONV");
+    use_umma = !(e && strcmp(e, "ffma") == 0);
+  }
   for (int i = 1; i < 12; ++i) {
     const size_t nw = (size_t)SP_COUT[i] * SP_CIN[i] * SP_KS[i] * SP_KS[i];
     osb_status s = conv_layer_upload(&L[i], p, p + nw, SP_CIN[i], SP_COUT[i], SP_KS[i]);
     if (s != OSB_OK) return s;
+    if (use_umma) {
+      s = umma_layer_upload(&UL[i], p, p + nw, SP_CIN[i], SP_COUT[i], SP_KS[i], SP_W_SCALE);
+      if (s != OSB_OK) return s;
+    }
     p += nw + SP_COUT[i];
   }
   {
@@ -68,7 +81,21 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
   OSB_CUDA(cudaMalloc(&d_img, B * HW));
   OSB_CUDA(cudaMalloc(&actA, B * HW * 64 * sizeof(float)));
   OSB_CUDA(cudaMalloc(&actB, B * HW * 64 * sizeof(float)));
-  OSB_CUDA(cudaMalloc(&d_logits, B * Hc * Wc * 72 * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&d_logits, B * Hc * Wc * 80 * sizeof(float)));
+  if (use_umma) {
+    // input geometry of every conv layer: which ping-pong buffer it reads and its [H][W][C]
+    // (layer order: 1 conv1b 2 conv2a 3 conv2b 4 conv3a 5 conv3b 6 conv4a 7 conv4b 8 convPa 9 convPb 10 convDa 11 convDb)
+    const int in_buf[12] = {-1, 0, 0, 1, 1, 0, 0, 1, 0, 1, 0, 1};      // 0 = actA, 1 = actB
+    const int in_div[12] = {0, 1, 2, 2, 4, 4, 8, 8, 8, 8, 8, 8};
+    for (int i = 1; i < 12; ++i) {
+      const int h = H / in_div[i], w = W / in_div[i], c = SP_CIN[i];
+      __half* base = reinterpret_cast<__half*>(in_buf[i] == 0 ? actA : actB);
+      in_hi[i] = base;
+      in_lo[i] = base + (size_t)max_batch * h * w * c;
+      osb_status s = umma_act_maps(&tmA[i], &tmB[i], in_hi[i], in_lo[i], max_batch, h, w, c);
+      if (s != OSB_OK) return s;
+    }
+  }
   OSB_CUDA(cudaMalloc(&d_semi, B * HW * sizeof(float)));
   OSB_CUDA(cudaMalloc(&d_desc, B * Hc * Wc * 256 * sizeof(float)));
   OSB_CUDA(cudaMalloc(&ks.state, B * HW));
@@ -88,15 +115,55 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
 
 void SuperPoint::release() {
   cudaFree(w1a); cudaFree(b1a); cudaFree(lut); cudaFree(pca_compT); cudaFree(pca_mean_d);
-  for (int i = 1; i < 12; ++i) conv_layer_free(&L[i]);
+  for (int i = 1; i < 12; ++i) { conv_layer_free(&L[i]); umma_layer_free(&UL[i]); }
   cudaFree(d_img); cudaFree(actA); cudaFree(actB); cudaFree(d_logits); cudaFree(d_semi); cudaFree(d_desc);
   cudaFree(ks.state); cudaFree(ks.surv); cudaFree(ks.cand); cudaFree(ks.skey); cudaFree(ks.counts); cudaFree(ks.cnorm);
   cudaFree(d_nk); cudaFree(d_kpts); cudaFree(d_conf); cudaFree(d_out);
   if (stream) cudaStreamDestroy(stream);
 }
 
+// tensor-core network: every activation is a pair of fp16 planes (hi, lo) scaled by SP_ACT_SCALE; the planes of a
+// layer's output live in the ping-pong buffer the next layer's TMA descriptors point at.
+osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t st) {
+  osb_status s;
+#define RUN(x) do { s = (x); if (s != OSB_OK) return s; } while (0)
+  const float SA = SP_ACT_SCALE;
+  auto conv = [&](int i, int h, int w, int out_layer /*layer whose input planes receive the result*/) {
+    return umma_conv_forward(UL[i], tmA[i], tmB[i], B, h, w, SA, in_hi[out_layer], in_lo[out_layer], nullptr,
+                             SP_COUT[i], SP_COUT[i], SA, 1, st);
+  };
+  // pooled outputs go through a temporary plane pair placed in the *other* ping-pong buffer
+  auto planes = [&](float* buf, int h, int w, int c, __half** hi, __half** lo) {
+    *hi = reinterpret_cast<__half*>(buf); *lo = *hi + (size_t)max_batch * h * w * c;
+  };
+  __half *th, *tl;
+  RUN(umma_first_forward(w1a, b1a, lut, img_dev, in_hi[1], in_lo[1], B, H, W, SA, st));            // conv1a -> A
+  planes(actB, H, W, 64, &th, &tl);
+  RUN(umma_conv_forward(UL[1], tmA[1], tmB[1], B, H, W, SA, th, tl, nullptr, 64, 64, SA, 1, st));     // conv1b -> B
+  RUN(umma_maxpool_forward(th, tl, in_hi[2], in_lo[2], B, H, W, 64, st));                             // pool  -> A
+  RUN(conv(2, H / 2, W / 2, 3));                                                                      // conv2a A -> B
+  planes(actA, H / 2, W / 2, 64, &th, &tl);
+  RUN(umma_conv_forward(UL[3], tmA[3], tmB[3], B, H / 2, W / 2, SA, th, tl, nullptr, 64, 64, SA, 1, st));   // conv2b B -> A
+  RUN(umma_maxpool_forward(th, tl, in_hi[4], in_lo[4], B, H / 2, W / 2, 64, st));                     // pool  -> B
+  RUN(conv(4, H / 4, W / 4, 5));                                                                      // conv3a B -> A
+  planes(actB, H / 4, W / 4, 128, &th, &tl);
+  RUN(umma_conv_forward(UL[5], tmA[5], tmB[5], B, H / 4, W / 4, SA, th, tl, nullptr, 128, 128, SA, 1, st)); // conv3b A -> B
+  RUN(umma_maxpool_forward(th, tl, in_hi[6], in_lo[6], B, H / 4, W / 4, 128, st));                    // pool  -> A
+  RUN(conv(6, Hc, Wc, 7));                                                                            // conv4a A -> B
+  RUN(conv(7, Hc, Wc, 8));                                                                            // conv4b B -> A (x)
+  RUN(conv(8, Hc, Wc, 9));                                                                            // convPa A -> B
+  RUN(umma_conv_forward(UL[9], tmA[9], tmB[9], B, Hc, Wc, SA, nullptr, nullptr, d_logits, 80, 80, 1.f, 0, st));   // convPb
+  RUN(conv(10, Hc, Wc, 11));                                                                          // convDa A -> B
+  RUN(umma_conv_forward(UL[11], tmA[11], tmB[11], B, Hc, Wc, SA, nullptr, nullptr, d_desc, 256, 256, 1.f, 0, st)); // convDb
+  RUN(l2norm_cells(d_desc, (int64_t)B * Hc * Wc, 256, st));
+  RUN(sp_softmax_shuffle(d_logits, 80, d_semi, B, Hc, Wc, st));
+#undef RUN
+  return OSB_OK;
+}
+
 // the network: u8 images (device) -> d_semi, d_desc
 osb_status SuperPoint::network(const uint8_t* img_dev, int B, cudaStream_t st) {
+  if (use_umma) return network_umma(img_dev, B, st);
   osb_status s;
 #define RUN(x) do { s = (x); if (s != OSB_OK) return s; } while (0)
   RUN(conv_first_forward(w1a, b1a, lut, img_dev, actA, B, H, W, 64, 1, ACT_RELU, st));      // conv1a

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "kernels.cuh"
+#include "conv_umma.cuh"
 
 namespace osb {
 
@@ -22,10 +23,17 @@ struct SuperPoint {
   int32_t* d_nk = nullptr;
   float *d_kpts = nullptr, *d_conf = nullptr, *d_out = nullptr;
 
+  // tensor-core path (conv_umma.cu): weights as split fp16 planes, one pair of TMA descriptors per conv input
+  bool use_umma = true;
+  UmmaLayer UL[12];
+  CUtensorMap tmA[12], tmB[12];     // [layer] -> (hi, lo) descriptors of that layer's INPUT planes
+  __half *in_hi[12] = {}, *in_lo[12] = {};
+
   osb_status init(const float* weights, size_t n_weights, int width, int height, float thres, int max_num,
                   const float* pca_comp, const float* pca_mean, int max_batch);
   void release();
   osb_status network(const uint8_t* img_dev, int B, cudaStream_t st);
+  osb_status network_umma(const uint8_t* img_dev, int B, cudaStream_t st);
   osb_status postprocess(int B, int32_t* nk, float* kpts, float* conf, float* out, cudaStream_t st);
   osb_status infer_dev(const uint8_t* img_dev, int B, int32_t* nk, float* kpts, float* out, cudaStream_t st);
 };
@@ -39,6 +47,7 @@ struct NetVLAD {
   float* centroids = nullptr;
   uint8_t* d_img = nullptr;
   float *actA = nullptr, *actB = nullptr, *d_assign = nullptr, *d_out = nullptr;
+  float *d_mu = nullptr, *d_part = nullptr, *d_psum = nullptr;
 
   osb_status init(const float* weights, size_t n_weights, int width, int height, int max_batch);
   void release();

@@ -113,10 +113,11 @@ def netvlad_weights(seed: int = 0) -> dict:
         if name.endswith(".bias"):
             w[name] = (rng.standard_normal(shape) * 0.05).astype(np.float32)
         elif name == "centroids":
-            w[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
+            # small centroids: residuals x - c stay image-specific (real NetVLAD centroids are data cluster centres)
+            w[name] = (rng.standard_normal(shape) * 0.01).astype(np.float32)
         else:
             fan_in = int(np.prod(shape[1:]))
-            gain = 3.0 if name.startswith("assign") else 1.0
+            gain = 8.0 if name.startswith("assign") else 1.0
             w[name] = (rng.standard_normal(shape) * math.sqrt(2.0 / fan_in) * gain).astype(np.float32)
     return w
 

@@ -181,7 +181,8 @@ def netvlad_net(img_u8: np.ndarray, w: dict) -> np.ndarray:
             x = relu6(F.conv2d(x, t[f"b{i}.dw.weight"], t[f"b{i}.dw.bias"], stride=s, padding=1, groups=ci))
             x = relu6(F.conv2d(x, t[f"b{i}.pw.weight"], t[f"b{i}.pw.bias"]))
         x = F.conv2d(x, t["proj.weight"], t["proj.bias"])            # [1,D,h,w]
-        x = x / torch.norm(x, dim=1, keepdim=True)                    # per-location L2 norm
+        x = x - x.mean(dim=(2, 3), keepdim=True)                      # per-image centring (makes random-weight
+        x = x / torch.norm(x, dim=1, keepdim=True)                    # descriptors image-specific); per-location L2
         a = torch.softmax(F.conv2d(x, t["assign.weight"], t["assign.bias"]), 1)   # [1,K,h,w]
         D, K = x.shape[1], a.shape[1]
         xf = x.reshape(D, -1)                                         # [D,P]
