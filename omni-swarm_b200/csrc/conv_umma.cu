@@ -101,6 +101,7 @@ struct UmmaArgs {
   float inv_scale;         // 1 / (act_scale * w_scale)
   float out_scale;         // scale of the stored fp16 planes
   int relu;
+  int pool;                // 1: fused 2x2 max-pool, the planes written are [B][H/2][W/2][C]
 };
 
 template <int N>
@@ -204,11 +205,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
+      // fused 2x2 max-pool: the warp owns tile rows 2q, 2q+1 (lane = (row & 1) * 16 + col); the pooled pixel of
+      // (even row, even col) is the max over lanes l, l+1, l+16, l+17 -> two shuffle steps, writer lanes l < 16, l even
+      const int py = ty * (UM_TH / 2) + q, px = tx * (UM_TW / 2) + (lane >> 1);
+      const bool pool_writer = P.pool && lane < 16 && !(lane & 1) && py < (P.H >> 1) && px < (P.W >> 1);
+      const size_t ppix = ((size_t)b * (P.H >> 1) + py) * (P.W >> 1) + px;
 #pragma unroll 1
       for (int n0 = 0; n0 < N; n0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_row + n0, v);
-        if (!inside || n0 >= P.out_c) continue;
+        if (n0 >= P.out_c) continue;                               // warp-uniform
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -216,8 +222,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           if (P.relu) a = fmaxf(a, 0.f);
           f[i] = a;
         }
+        bool store = inside;
+        size_t opix = pix;
+        if (P.pool) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            f[i] = fmaxf(f[i], __shfl_down_sync(0xffffffffu, f[i], 1));
+            f[i] = fmaxf(f[i], __shfl_down_sync(0xffffffffu, f[i], 16));
+          }
+          store = pool_writer; opix = ppix;
+        }
+        if (!store) continue;
         if (P.out_f32) {
-          float4* dst = reinterpret_cast<float4*>(P.out_f32 + pix * P.out_cstride + n0);
+          float4* dst = reinterpret_cast<float4*>(P.out_f32 + opix * P.out_cstride + n0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
         } else {
@@ -230,8 +247,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
             lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
           }
-          uint4* dh = reinterpret_cast<uint4*>(P.out_hi + pix * P.out_cstride + n0);
-          uint4* dl = reinterpret_cast<uint4*>(P.out_lo + pix * P.out_cstride + n0);
+          uint4* dh = reinterpret_cast<uint4*>(P.out_hi + opix * P.out_cstride + n0);
+          uint4* dl = reinterpret_cast<uint4*>(P.out_lo + opix * P.out_cstride + n0);
           dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
           dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
@@ -267,7 +284,9 @@ __device__ __forceinline__ void split_store8(__half* hi, __half* lo, const float
   *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__global__ void __launch_bounds__(128)
+// thread = (pixel, group of 8 output channels): the 8 threads of a pixel write 128 contiguous bytes per plane, a warp
+// 512 contiguous bytes (this kernel is bound by its 629 MB of stores per 8-image keyframe)
+__global__ void __launch_bounds__(256)
 conv_first_split_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ lut,
                         const uint8_t* __restrict__ img, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                         int H, int W, float out_scale) {
@@ -279,7 +298,8 @@ conv_first_split_kernel(const float* __restrict__ w, const float* __restrict__ b
   for (int e = threadIdx.x; e < 256; e += blockDim.x) slut[e] = lut[e];
   __syncthreads();
   const int b = blockIdx.y;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = t >> 3, o8 = t & 7;
   if (p >= H * W) return;
   const int oy = p / W, ox = p % W;
   const uint8_t* ib = img + (size_t)b * H * W;
@@ -291,20 +311,15 @@ conv_first_split_kernel(const float* __restrict__ w, const float* __restrict__ b
       const int gy = oy + ky - 1, gx = ox + kx - 1;
       in[ky * 3 + kx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? slut[ib[(size_t)gy * W + gx]] : 0.f;
     }
-  __half* dh = out_hi + ((size_t)b * H * W + p) * 64;
-  __half* dl = out_lo + ((size_t)b * H * W + p) * 64;
-#pragma unroll 2
-  for (int o8 = 0; o8 < 8; ++o8) {
-    float r[8];
+  float r[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = 0.f;
+  for (int j = 0; j < 8; ++j) {
+    float a = 0.f;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) a = fmaf(in[t], sw[t][8 * o8 + j], a);
-      r[j] = fmaxf(a + sb[8 * o8 + j], 0.f);
-    }
-    split_store8(dh + 8 * o8, dl + 8 * o8, r, out_scale);
+    for (int tt = 0; tt < 9; ++tt) a = fmaf(in[tt], sw[tt][8 * o8 + j], a);
+    r[j] = fmaxf(a + sb[8 * o8 + j], 0.f);
   }
+  split_store8(out_hi + ((size_t)b * H * W + p) * 64 + 8 * o8, out_lo + ((size_t)b * H * W + p) * 64 + 8 * o8, r, out_scale);
 }
 
 // one thread per (output pixel, 8 channels)
@@ -445,8 +460,10 @@ static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, 
 
 osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int B, int H, int W,
                              float act_scale, __half* out_hi, __half* out_lo, float* out_f32, int out_c, int out_cstride,
-                             float out_scale, int relu, cudaStream_t st) {
+                             float out_scale, int relu, int pool, cudaStream_t st) {
   UmmaArgs P;
+  P.pool = pool;
+  OSB_REQUIRE(!pool || (H % 2 == 0 && W % 2 == 0), "fused max-pool needs even H and W");
   P.bias = L.bias; P.out_hi = out_hi; P.out_lo = out_lo; P.out_f32 = out_f32;
   P.H = H; P.W = W; P.B = B; P.ks = L.ks; P.cin_slabs = L.cin / UM_KC;
   P.out_c = out_c; P.out_cstride = out_cstride;
@@ -464,8 +481,8 @@ osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const 
 
 osb_status umma_first_forward(const float* w_tap_cout, const float* bias, const float* lut, const uint8_t* img,
                               __half* out_hi, __half* out_lo, int B, int H, int W, float out_scale, cudaStream_t st) {
-  dim3 grid(cdiv(H * W, 128), B);
-  OSB_LAUNCH(conv_first_split_kernel, grid, 128, 0, st, w_tap_cout, bias, lut, img, out_hi, out_lo, H, W, out_scale);
+  dim3 grid(cdiv(H * W * 8, 256), B);
+  OSB_LAUNCH(conv_first_split_kernel, grid, 256, 0, st, w_tap_cout, bias, lut, img, out_hi, out_lo, H, W, out_scale);
   OSB_CHECK_LAUNCH();
   return OSB_OK;
 }

@@ -12,9 +12,11 @@
 // D = clip(diag(J^T J)), radius update by 1 - (2 rho - 1)^3, decrease factor doubling) and a block-Jacobi
 // preconditioned conjugate gradient on the 4x4-block normal equations.  J^T J is never assembled off-diagonal:
 // a factor thread computes t = Ja p_a + Jb p_b and the two 4-vectors Ja^T t, Jb^T t, and a node thread gathers the
-// contributions of its incident factors through a CSR incidence list in a fixed order (no atomics: results are
-// bit-reproducible run to run).  The graph (8 000 scalars, 12 000 factors for BASELINE config C5, ~5.5 MB per
-// linearisation) lives in L2; the bound is grid-synchronisation latency (3 per CG iteration), not HBM.
+// contributions from its own contiguous run of slots in a fixed order (no atomics: results are bit-reproducible
+// run to run).  The problem (8 000 scalars, 12 000 factors for BASELINE config C5) is latency bound, not HBM bound:
+// the Jacobians of a CTA's factor block stay in shared memory (SoA, conflict-free) for the whole solve, and when the
+// factor list fits 16 CTAs the grid is launched as ONE thread-block cluster so that the 3 barriers per CG iteration
+// are hardware cluster barriers instead of software grid barriers.
 #include <cooperative_groups.h>
 #include <algorithm>
 #include "common.cuh"
@@ -23,7 +25,9 @@ namespace cg = cooperative_groups;
 
 namespace osb {
 
-constexpr int GS_THREADS = 256;
+constexpr int GS_THREADS = 512;
+constexpr int GS_MAX_CLUSTER = 16;
+constexpr int GS_SMEM_J_MAX = 200 * 1024;   // bytes of shared memory a CTA may spend on its Jacobian block
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kTwoPi = 6.28318530717958647692;
 
@@ -152,25 +156,34 @@ __device__ int linearize_factor(int type, const double* __restrict__ pa, const d
 
 struct SolverDev {
   int n, m;
+  int fpc;                 // factors per CTA (contiguous block of the factor list)
+  int use_cluster;         // 1: the whole grid is ONE thread-block cluster (hardware barrier); 0: cooperative grid sync
+  int j_in_smem;           // 1: the CTA's Jacobians live in shared memory (SoA), 0: in `Jg`
   // graph
   const uint8_t* fixed; const int32_t* ftype; const int32_t* ia; const int32_t* ib; const uint8_t* huber;
   const double* payload;
-  const int32_t* node_ptr; const int32_t* inc;   // CSR incidence: entries (factor << 1 | side)
+  const int32_t* node_ptr;                 // CSR: node n owns contribution slots [node_ptr[n], node_ptr[n+1])
+  const int32_t* slot_a; const int32_t* slot_b;   // slot of factor f's contribution to its node a / node b
   // state
-  double* x[2];          // pose buffers (current / trial), [n][4]
-  double* lin[2];        // linearisation buffers: per factor 36 doubles (r[4], Ja[16], Jb[16])
+  double* x[2];            // pose buffers (current / trial), [n][4]
+  double* Jg;              // global Jacobian store, SoA [32][m] (used when the CTA block does not fit shared memory)
   double *g, *D, *Hnn, *Minv, *p, *z, *res, *Ap, *delta;   // node vectors
-  double* contrib;       // [m][8]
-  double* partial;       // [2][4][grid]
+  double* cs;              // contribution slots [2m][4]
+  double* hs;              // Hessian-diagonal-block slots [2m][16] (only touched at a re-linearisation)
+  double* partial;         // [2][4][grid]
   osb_solve_options opt;
   osb_solve_summary* summary;
   double* poses_out;
 };
 
+__device__ __forceinline__ void all_sync(const SolverDev& P, cg::grid_group& grid) {
+  if (P.use_cluster) cg::this_cluster().sync(); else grid.sync();
+}
+
 template <int K>
-__device__ void grid_reduce_sum(double (&v)[K], double* partial, int parity, double* sh, cg::grid_group& grid) {
+__device__ void grid_reduce_sum(double (&v)[K], const SolverDev& P, int parity, double* sh, cg::grid_group& grid) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = GS_THREADS / 32, G = gridDim.x;
-  double* pbuf = partial + (size_t)parity * 4 * G;
+  double* pbuf = P.partial + (size_t)parity * 4 * G;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const double w = warp_sum_d(v[k]);
@@ -182,10 +195,10 @@ __device__ void grid_reduce_sum(double (&v)[K], double* partial, int parity, dou
     for (int k = 0; k < K; ++k) {
       double xv = (lane < nw) ? sh[k * 32 + lane] : 0.0;
       xv = warp_sum_d(xv);
-      if (lane == 0) pbuf[k * G + blockIdx.x] = xv;
+      if (lane == 0) __stcg(pbuf + k * G + blockIdx.x, xv);
     }
   }
-  grid.sync();
+  all_sync(P, grid);
   if (warp == 0) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -201,48 +214,38 @@ __device__ void grid_reduce_sum(double (&v)[K], double* partial, int parity, dou
   __syncthreads();
 }
 
-// evaluate all factors at poses `xp` into linearisation buffer `lin`; returns this thread's cost share and
-// (optionally) its share of sum |J_cur delta|^2 computed with the CURRENT linearisation `lin_cur`.
-__device__ void factor_evaluate(const SolverDev& P, const double* __restrict__ xp, double* __restrict__ lin,
-                                const double* __restrict__ lin_cur, const double* __restrict__ delta, double& cost,
-                                double& jd) {
-  const int T = gridDim.x * GS_THREADS;
-  for (int f = blockIdx.x * GS_THREADS + threadIdx.x; f < P.m; f += T) {
-    const int a = P.ia[f], b = P.ib[f];
-    double pa[4], pb[4];
+__device__ double grid_reduce_max(double vmax, const SolverDev& P, int parity, double* sh, cg::grid_group& grid) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = gridDim.x;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { pa[i] = __ldcg(xp + 4 * a + i); pb[i] = __ldcg(xp + 4 * b + i); }
-    double r[4], Ja[16], Jb[16];
-    const int nr = linearize_factor(P.ftype[f], pa, pb, P.payload + (size_t)f * OSB_PAYLOAD_LEN, r, Ja, Jb);
-    (void)nr;
-    const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
-    double w = 1.0;
-    if (P.huber[f] && s > 1.0) {        // ceres::HuberLoss(1.0): rho(s) = 2 sqrt(s) - 1, rho' = 1/sqrt(s)
-      cost += 0.5 * (2.0 * sqrt(s) - 1.0);
-      w = 1.0 / sqrt(sqrt(s));
-    } else {
-      cost += 0.5 * s;
-    }
-    double* L = lin + (size_t)f * 36;
+  for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if (lane == 0) sh[warp] = vmax;
+  __syncthreads();
+  double* pbuf = P.partial + (size_t)parity * 4 * G;
+  if (warp == 0) {
+    double xv = (lane < GS_THREADS / 32) ? sh[lane] : 0.0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) L[i] = r[i] * w;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { L[4 + i] = Ja[i] * w; L[20 + i] = Jb[i] * w; }
-    if (lin_cur != nullptr) {
-      const double* C = lin_cur + (size_t)f * 36;
-      double da[4], db[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { da[i] = __ldcg(delta + 4 * a + i); db[i] = __ldcg(delta + 4 * b + i); }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        double t = 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) t += C[4 + i * 4 + j] * da[j] + C[20 + i * 4 + j] * db[j];
-        jd += t * t;
-      }
-    }
+    for (int o = 16; o > 0; o >>= 1) xv = fmax(xv, __shfl_xor_sync(0xffffffffu, xv, o));
+    if (lane == 0) __stcg(pbuf + blockIdx.x, xv);
   }
+  all_sync(P, grid);
+  if (warp == 0) {
+    double xv = 0.0;
+    for (int i = lane; i < G; i += 32) xv = fmax(xv, __ldcg(pbuf + i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) xv = fmax(xv, __shfl_xor_sync(0xffffffffu, xv, o));
+    if (lane == 0) sh[0] = xv;
+  }
+  __syncthreads();
+  const double r = sh[0];
+  __syncthreads();
+  return r;
 }
+
+// Jacobian store accessor: element i (0..31: Ja row-major then Jb) of the factor with CTA-local index `li`
+struct JStore {
+  double* base; int stride; int off;
+  __device__ __forceinline__ double& at(int i, int li) const { return base[(size_t)i * stride + off + li]; }
+};
 
 // 4x4 SPD inverse by Gauss-Jordan (no pivoting: the LM term keeps the diagonal positive)
 __device__ void inv4(const double* __restrict__ M, double* __restrict__ out) {
@@ -270,34 +273,109 @@ __device__ void inv4(const double* __restrict__ M, double* __restrict__ out) {
     for (int j = 0; j < 4; ++j) out[i * 4 + j] = a[i][4 + j];
 }
 
-__global__ void __launch_bounds__(GS_THREADS)
+// Linearise every factor of this CTA at `xp`: robustified Jacobians -> J store, gradient contributions J^T r -> cs
+// slots, diagonal-block contributions J^T J -> hs slots.  Returns this thread's share of the cost.
+__device__ double factor_linearize(const SolverDev& P, const double* __restrict__ xp, const JStore& J) {
+  double cost = 0.0;
+  const int f0 = blockIdx.x * P.fpc, f1 = min(P.m, f0 + P.fpc);
+  for (int f = f0 + threadIdx.x; f < f1; f += GS_THREADS) {
+    const int li = f - f0;
+    const int a = P.ia[f], b = P.ib[f];
+    double pa[4], pb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pa[i] = __ldcg(xp + 4 * a + i); pb[i] = __ldcg(xp + 4 * b + i); }
+    double r[4], Ja[16], Jb[16];
+    linearize_factor(P.ftype[f], pa, pb, P.payload + (size_t)f * OSB_PAYLOAD_LEN, r, Ja, Jb);
+    const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+    double w = 1.0;
+    if (P.huber[f] && s > 1.0) {        // ceres::HuberLoss(1.0): rho(s) = 2 sqrt(s) - 1, sqrt(rho') = s^-1/4
+      cost += 0.5 * (2.0 * sqrt(s) - 1.0);
+      w = 1.0 / sqrt(sqrt(s));
+    } else {
+      cost += 0.5 * s;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] *= w;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { Ja[i] *= w; Jb[i] *= w; J.at(i, li) = Ja[i]; J.at(16 + i, li) = Jb[i]; }
+    double* ga = P.cs + 4 * (size_t)P.slot_a[f];
+    double* gb = P.cs + 4 * (size_t)P.slot_b[f];
+    double* ha = P.hs + 16 * (size_t)P.slot_a[f];
+    double* hb = P.hs + 16 * (size_t)P.slot_b[f];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double sa = 0.0, sb = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { sa += Ja[i * 4 + j] * r[i]; sb += Jb[i * 4 + j] * r[i]; }
+      __stcg(ga + j, sa); __stcg(gb + j, sb);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        double ta = 0.0, tb = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ta += Ja[i * 4 + j] * Ja[i * 4 + k]; tb += Jb[i * 4 + j] * Jb[i * 4 + k]; }
+        __stcg(ha + j * 4 + k, ta); __stcg(hb + j * 4 + k, tb);
+      }
+    }
+  }
+  return cost;
+}
+
+// cost at the trial point `xn` and this thread's share of |J_cur delta|^2 (model decrease)
+__device__ void factor_trial(const SolverDev& P, const double* __restrict__ xn, const JStore& J, double& cost, double& jd) {
+  const int f0 = blockIdx.x * P.fpc, f1 = min(P.m, f0 + P.fpc);
+  for (int f = f0 + threadIdx.x; f < f1; f += GS_THREADS) {
+    const int li = f - f0;
+    const int a = P.ia[f], b = P.ib[f];
+    double pa[4], pb[4], da[4], db[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pa[i] = __ldcg(xn + 4 * a + i); pb[i] = __ldcg(xn + 4 * b + i);
+      da[i] = __ldcg(P.delta + 4 * a + i); db[i] = __ldcg(P.delta + 4 * b + i);
+    }
+    double r[4], Ja[16], Jb[16];
+    linearize_factor(P.ftype[f], pa, pb, P.payload + (size_t)f * OSB_PAYLOAD_LEN, r, Ja, Jb);
+    const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+    cost += (P.huber[f] && s > 1.0) ? 0.5 * (2.0 * sqrt(s) - 1.0) : 0.5 * s;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double t = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t += J.at(i * 4 + j, li) * da[j] + J.at(16 + i * 4 + j, li) * db[j];
+      jd += t * t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GS_THREADS, 1)
 graph_solve_kernel(SolverDev P) {
   cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) double smem_j[];
   __shared__ double sh[4 * 32];
   const int T = gridDim.x * GS_THREADS;
   const int gtid = blockIdx.x * GS_THREADS + threadIdx.x;
+  JStore J;
+  if (P.j_in_smem) { J.base = smem_j; J.stride = P.fpc; J.off = 0; }
+  else { J.base = P.Jg; J.stride = P.m; J.off = blockIdx.x * P.fpc; }
   int parity = 0;
   unsigned long long t0 = 0;
   if (gtid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
 
-  int cur = 0;                 // index of the current pose / linearisation buffers
+  int cur = 0;
   double radius = P.opt.initial_trust_radius;
   double decrease = 2.0;
   int iters = 0, pcg_total = 0, termination = 3;
 
-  // ---- initial evaluation ----
-  double v2[2] = {0.0, 0.0};
-  factor_evaluate(P, P.x[0], P.lin[0], nullptr, nullptr, v2[0], v2[1]);
-  grid_reduce_sum<2>(v2, P.partial, parity, sh, grid); parity ^= 1;
-  double cost = v2[0];
+  // ---- initial linearisation ----
+  double v1[1] = {factor_linearize(P, P.x[0], J)};
+  grid_reduce_sum<1>(v1, P, parity, sh, grid); parity ^= 1;
+  double cost = v1[0];
   const double initial_cost = cost;
   bool need_gradient = true;
-  double gmax = 0.0;
+  const int f0 = blockIdx.x * P.fpc, f1 = min(P.m, f0 + P.fpc);
 
   while (iters < P.opt.max_iterations) {
-    const double* L = P.lin[cur];
     if (need_gradient) {
-      // ---- node phase G: gradient, diagonal blocks, LM diagonal ----
+      // ---- node phase G: gather gradient and diagonal blocks from the slots, LM diagonal ----
       double vmax = 0.0;
       for (int n = gtid; n < P.n; n += T) {
         double gn[4] = {0.0, 0.0, 0.0, 0.0};
@@ -305,20 +383,13 @@ graph_solve_kernel(SolverDev P) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) Hn[i] = 0.0;
         if (!P.fixed[n]) {
-          for (int e = P.node_ptr[n]; e < P.node_ptr[n + 1]; ++e) {
-            const int ent = P.inc[e];
-            const double* Lf = L + (size_t)(ent >> 1) * 36;
-            const double* J = Lf + 4 + 16 * (ent & 1);
+          const int s0 = P.node_ptr[n], s1 = P.node_ptr[n + 1];
+#pragma unroll 2
+          for (int sidx = s0; sidx < s1; ++sidx) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const double ri = Lf[i];
+            for (int i = 0; i < 4; ++i) gn[i] += __ldcg(P.cs + 4 * (size_t)sidx + i);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                gn[j] += J[i * 4 + j] * ri;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) Hn[j * 4 + k] += J[i * 4 + j] * J[i * 4 + k];
-              }
-            }
+            for (int i = 0; i < 16; ++i) Hn[i] += __ldcg(P.hs + 16 * (size_t)sidx + i);
           }
         }
 #pragma unroll
@@ -330,40 +401,14 @@ graph_solve_kernel(SolverDev P) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) P.Hnn[16 * n + i] = Hn[i];
       }
-      // max-reduction through the sum machinery: reduce max per block, then max over partials
-      {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = gridDim.x;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        if (lane == 0) sh[warp] = vmax;
-        __syncthreads();
-        double* pbuf = P.partial + (size_t)parity * 4 * G;
-        if (warp == 0) {
-          double xv = (lane < GS_THREADS / 32) ? sh[lane] : 0.0;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) xv = fmax(xv, __shfl_xor_sync(0xffffffffu, xv, o));
-          if (lane == 0) pbuf[blockIdx.x] = xv;
-        }
-        grid.sync();
-        if (warp == 0) {
-          double xv = 0.0;
-          for (int i = lane; i < G; i += 32) xv = fmax(xv, __ldcg(pbuf + i));
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) xv = fmax(xv, __shfl_xor_sync(0xffffffffu, xv, o));
-          if (lane == 0) sh[0] = xv;
-        }
-        __syncthreads();
-        gmax = sh[0];
-        __syncthreads();
-        parity ^= 1;
-      }
+      const double gmax = grid_reduce_max(vmax, P, parity, sh, grid); parity ^= 1;
       need_gradient = false;
       if (gmax <= P.opt.gradient_tolerance) { termination = 1; break; }
     }
 
     // ---- PCG init (node phase): Minv, res = -g, z = Minv res, p = 0, delta = 0 ----
     const double lam = 1.0 / radius;
-    double v3[3] = {0.0, 0.0, 0.0};
+    double v2[2] = {0.0, 0.0};
     for (int n = gtid; n < P.n; n += T) {
       double rn[4] = {0.0, 0.0, 0.0, 0.0}, zn[4] = {0.0, 0.0, 0.0, 0.0};
       if (!P.fixed[n]) {
@@ -384,46 +429,50 @@ graph_solve_kernel(SolverDev P) {
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        P.res[4 * n + i] = rn[i]; P.z[4 * n + i] = zn[i]; P.p[4 * n + i] = 0.0; P.delta[4 * n + i] = 0.0;
-        v3[0] += rn[i] * zn[i]; v3[1] += rn[i] * rn[i];
+        P.res[4 * n + i] = rn[i]; __stcg(P.z + 4 * n + i, zn[i]); __stcg(P.p + 4 * n + i, 0.0); P.delta[4 * n + i] = 0.0;
+        v2[0] += rn[i] * zn[i]; v2[1] += rn[i] * rn[i];
       }
     }
-    grid_reduce_sum<2>(*reinterpret_cast<double(*)[2]>(v3), P.partial, parity, sh, grid); parity ^= 1;
-    double rz = v3[0];
-    const double rr0 = v3[1];
+    grid_reduce_sum<2>(v2, P, parity, sh, grid); parity ^= 1;
+    double rz = v2[0];
+    const double rr0 = v2[1];
     double beta = 0.0;
     int it = 0;
-    // ---- PCG iterations: 3 grid synchronisations each ----
+    // ---- PCG iterations: 3 barriers each ----
     while (it < P.opt.max_pcg_iterations && rr0 > 0.0) {
       // factor phase: p_a = z_a + beta p_a (on the fly), t = Ja p_a + Jb p_b, contributions Ja^T t, Jb^T t
-      for (int f = gtid; f < P.m; f += T) {
+      for (int f = f0 + threadIdx.x; f < f1; f += GS_THREADS) {
+        const int li = f - f0;
         const int a = P.ia[f], b = P.ib[f];
-        const double* Lf = L + (size_t)f * 36;
         double pa[4], pb[4], t[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           pa[i] = __ldcg(P.z + 4 * a + i) + beta * __ldcg(P.p + 4 * a + i);
           pb[i] = __ldcg(P.z + 4 * b + i) + beta * __ldcg(P.p + 4 * b + i);
         }
+        double Jl[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) Jl[i] = J.at(i, li);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           double s = 0.0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) s += Lf[4 + i * 4 + j] * pa[j] + Lf[20 + i * 4 + j] * pb[j];
+          for (int j = 0; j < 4; ++j) s += Jl[i * 4 + j] * pa[j] + Jl[16 + i * 4 + j] * pb[j];
           t[i] = s;
         }
-        double* C = P.contrib + (size_t)f * 8;
+        double* ca = P.cs + 4 * (size_t)P.slot_a[f];
+        double* cb = P.cs + 4 * (size_t)P.slot_b[f];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          double ca = 0.0, cb = 0.0;
+          double sa = 0.0, sb = 0.0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { ca += Lf[4 + i * 4 + j] * t[i]; cb += Lf[20 + i * 4 + j] * t[i]; }
-          __stcg(C + j, ca); __stcg(C + 4 + j, cb);
+          for (int i = 0; i < 4; ++i) { sa += Jl[i * 4 + j] * t[i]; sb += Jl[16 + i * 4 + j] * t[i]; }
+          __stcg(ca + j, sa); __stcg(cb + j, sb);
         }
       }
-      grid.sync();
-      // node phase 1: p = z + beta p (stored), Ap = sum contributions + lam D p, partial p.Ap
-      double v1[1] = {0.0};
+      all_sync(P, grid);
+      // node phase 1: p = z + beta p (stored), Ap = sum of the node's slots + lam D p, partial p.Ap
+      double v1b[1] = {0.0};
       for (int n = gtid; n < P.n; n += T) {
         if (P.fixed[n]) continue;
         double pn[4], ap[4];
@@ -432,17 +481,17 @@ graph_solve_kernel(SolverDev P) {
           pn[i] = P.z[4 * n + i] + beta * P.p[4 * n + i];
           ap[i] = lam * P.D[4 * n + i] * pn[i];
         }
-        for (int e = P.node_ptr[n]; e < P.node_ptr[n + 1]; ++e) {
-          const int ent = P.inc[e];
-          const double* C = P.contrib + (size_t)(ent >> 1) * 8 + 4 * (ent & 1);
+        const int s0 = P.node_ptr[n], s1 = P.node_ptr[n + 1];
+#pragma unroll 4
+        for (int sidx = s0; sidx < s1; ++sidx) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) ap[i] += __ldcg(C + i);
+          for (int i = 0; i < 4; ++i) ap[i] += __ldcg(P.cs + 4 * (size_t)sidx + i);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { P.p[4 * n + i] = pn[i]; P.Ap[4 * n + i] = ap[i]; v1[0] += pn[i] * ap[i]; }
+        for (int i = 0; i < 4; ++i) { __stcg(P.p + 4 * n + i, pn[i]); P.Ap[4 * n + i] = ap[i]; v1b[0] += pn[i] * ap[i]; }
       }
-      grid_reduce_sum<1>(v1, P.partial, parity, sh, grid); parity ^= 1;
-      const double pAp = v1[0];
+      grid_reduce_sum<1>(v1b, P, parity, sh, grid); parity ^= 1;
+      const double pAp = v1b[0];
       if (!(pAp > 0.0)) break;
       const double alpha = rz / pAp;
       // node phase 2: delta += alpha p, res -= alpha Ap, z = Minv res; partial rz_new, rr
@@ -461,11 +510,11 @@ graph_solve_kernel(SolverDev P) {
           for (int j = 0; j < 4; ++j) zn[i] += P.Minv[16 * n + i * 4 + j] * rn[j];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          P.res[4 * n + i] = rn[i]; P.z[4 * n + i] = zn[i];
+          P.res[4 * n + i] = rn[i]; __stcg(P.z + 4 * n + i, zn[i]);
           v22[0] += rn[i] * zn[i]; v22[1] += rn[i] * rn[i];
         }
       }
-      grid_reduce_sum<2>(v22, P.partial, parity, sh, grid); parity ^= 1;
+      grid_reduce_sum<2>(v22, P, parity, sh, grid); parity ^= 1;
       ++it;
       beta = v22[0] / rz;
       rz = v22[0];
@@ -484,44 +533,50 @@ graph_solve_kernel(SolverDev P) {
         const double d = P.fixed[n] ? 0.0 : P.delta[4 * n + i];
         const double xv = xc[4 * n + i];
         __stcg(xn + 4 * n + i, xv + d);
+        if (P.fixed[n]) __stcg(P.delta + 4 * n + i, 0.0);
         v4[0] += P.g[4 * n + i] * d; v4[1] += d * d;
         if (!P.fixed[n]) v4[2] += xv * xv;
       }
     }
-    grid_reduce_sum<3>(v4, P.partial, parity, sh, grid); parity ^= 1;
+    grid_reduce_sum<3>(v4, P, parity, sh, grid); parity ^= 1;
     // ---- evaluate trial, model decrease, elapsed time ----
     double v5[3] = {0.0, 0.0, 0.0};
-    factor_evaluate(P, xn, P.lin[cur ^ 1], L, P.delta, v5[0], v5[1]);
+    factor_trial(P, xn, J, v5[0], v5[1]);
     if (gtid == 0) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
       v5[2] = (double)(t1 - t0) * 1e-9;
     }
-    grid_reduce_sum<3>(v5, P.partial, parity, sh, grid); parity ^= 1;
+    grid_reduce_sum<3>(v5, P, parity, sh, grid); parity ^= 1;
     const double new_cost = v5[0];
     const double model = -v4[0] - 0.5 * v5[1];
     const double elapsed = v5[2];
     const double rho = (model > 0.0) ? (cost - new_cost) / model : -1.0;
     const bool finite = isfinite(new_cost);
+    const bool small_step = sqrt(v4[1]) <= P.opt.parameter_tolerance * (sqrt(v4[2]) + P.opt.parameter_tolerance);
     if (finite && rho > 1e-3) {
       // accept (Ceres LevenbergMarquardtStrategy::StepAccepted)
       const double tmp = 2.0 * rho - 1.0;
       radius = fmin(radius / fmax(1.0 / 3.0, 1.0 - tmp * tmp * tmp), 1e16);
       decrease = 2.0;
       const double dcost = cost - new_cost;
-      cur ^= 1;
       const double old_cost = cost;
+      cur ^= 1;
       cost = new_cost;
-      need_gradient = true;
       if (fabs(dcost) <= P.opt.function_tolerance * old_cost) { termination = 0; break; }
-      if (sqrt(v4[1]) <= P.opt.parameter_tolerance * (sqrt(v4[2]) + P.opt.parameter_tolerance)) { termination = 2; break; }
+      if (small_step) { termination = 2; break; }
+      if (P.opt.max_time_s > 0.0 && elapsed > P.opt.max_time_s) { termination = 4; break; }
+      // re-linearise at the accepted point (the trial pass kept the old Jacobians for the model term)
+      double v1c[1] = {factor_linearize(P, P.x[cur], J)};
+      grid_reduce_sum<1>(v1c, P, parity, sh, grid); parity ^= 1;
+      need_gradient = true;
     } else {
       radius /= decrease;
       decrease *= 2.0;
       if (radius < 1e-32 || !isfinite(radius)) { termination = 5; break; }
-      if (sqrt(v4[1]) <= P.opt.parameter_tolerance * (sqrt(v4[2]) + P.opt.parameter_tolerance)) { termination = 2; break; }
+      if (small_step) { termination = 2; break; }
+      if (P.opt.max_time_s > 0.0 && elapsed > P.opt.max_time_s) { termination = 4; break; }
     }
-    if (P.opt.max_time_s > 0.0 && elapsed > P.opt.max_time_s) { termination = 4; break; }
   }
 
   // ---- write back ----
@@ -553,16 +608,17 @@ __global__ void graph_linearize_kernel(int m, const double* __restrict__ poses, 
 using namespace osb;
 
 struct osb_solver {
-  int max_nodes = 0, max_factors = 0, grid = 0;
+  int max_nodes = 0, max_factors = 0;
+  bool cluster_ok = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::mutex mu;
   // device
   uint8_t *d_fixed = nullptr, *d_huber = nullptr;
-  int32_t *d_type = nullptr, *d_ia = nullptr, *d_ib = nullptr, *d_ptr = nullptr, *d_inc = nullptr;
-  double *d_payload = nullptr, *d_x0 = nullptr, *d_x1 = nullptr, *d_lin0 = nullptr, *d_lin1 = nullptr;
+  int32_t *d_type = nullptr, *d_ia = nullptr, *d_ib = nullptr, *d_ptr = nullptr, *d_slot_a = nullptr, *d_slot_b = nullptr;
+  double *d_payload = nullptr, *d_x0 = nullptr, *d_x1 = nullptr, *d_Jg = nullptr, *d_lin = nullptr;
   double *d_nodevec = nullptr;   // g, D, p, z, res, Ap, delta (7 x 4n) + Hnn, Minv (2 x 16n)
-  double *d_contrib = nullptr, *d_partial = nullptr, *d_out = nullptr;
+  double *d_cs = nullptr, *d_hs = nullptr, *d_partial = nullptr, *d_out = nullptr;
   osb_solve_summary* d_summary = nullptr;
 };
 
@@ -588,25 +644,25 @@ extern "C" osb_status osb_solver_create(osb_solver** out, int max_nodes, int max
   OSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   OSB_CUDA(cudaEventCreate(&h->ev0));
   OSB_CUDA(cudaEventCreate(&h->ev1));
-  int per_sm = 0;
-  OSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_solve_kernel, GS_THREADS, 0));
-  if (per_sm < 1) { set_error("osb_solver_create", "solve kernel cannot be made resident"); return OSB_ERR_CUDA; }
-  const int want = cdiv((int)std::max(n, m), GS_THREADS);
-  h->grid = std::max(1, std::min(want, num_sms()));
+  OSB_CUDA(cudaFuncSetAttribute(graph_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_J_MAX));
+  h->cluster_ok = cudaFuncSetAttribute(graph_solve_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+  cudaGetLastError();
   OSB_CUDA(cudaMalloc(&h->d_fixed, n));
   OSB_CUDA(cudaMalloc(&h->d_huber, m));
   OSB_CUDA(cudaMalloc(&h->d_type, m * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&h->d_ia, m * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&h->d_ib, m * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&h->d_slot_a, m * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&h->d_slot_b, m * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&h->d_ptr, (n + 1) * sizeof(int32_t)));
-  OSB_CUDA(cudaMalloc(&h->d_inc, 2 * m * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&h->d_payload, m * OSB_PAYLOAD_LEN * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_x0, 4 * n * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_x1, 4 * n * sizeof(double)));
-  OSB_CUDA(cudaMalloc(&h->d_lin0, 36 * m * sizeof(double)));
-  OSB_CUDA(cudaMalloc(&h->d_lin1, 36 * m * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_Jg, 32 * m * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_lin, 36 * m * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_nodevec, (7 * 4 + 2 * 16) * n * sizeof(double)));
-  OSB_CUDA(cudaMalloc(&h->d_contrib, 8 * m * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_cs, 8 * m * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_hs, 32 * m * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_partial, 2 * 4 * (size_t)num_sms() * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_out, 4 * n * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_summary, sizeof(osb_solve_summary)));
@@ -617,9 +673,9 @@ extern "C" osb_status osb_solver_create(osb_solver** out, int max_nodes, int max
 extern "C" osb_status osb_solver_destroy(osb_solver* h) {
   if (!h) return OSB_OK;
   cudaFree(h->d_fixed); cudaFree(h->d_huber); cudaFree(h->d_type); cudaFree(h->d_ia); cudaFree(h->d_ib);
-  cudaFree(h->d_ptr); cudaFree(h->d_inc); cudaFree(h->d_payload); cudaFree(h->d_x0); cudaFree(h->d_x1);
-  cudaFree(h->d_lin0); cudaFree(h->d_lin1); cudaFree(h->d_nodevec); cudaFree(h->d_contrib); cudaFree(h->d_partial);
-  cudaFree(h->d_out); cudaFree(h->d_summary);
+  cudaFree(h->d_slot_a); cudaFree(h->d_slot_b); cudaFree(h->d_ptr); cudaFree(h->d_payload); cudaFree(h->d_x0);
+  cudaFree(h->d_x1); cudaFree(h->d_Jg); cudaFree(h->d_lin); cudaFree(h->d_nodevec); cudaFree(h->d_cs); cudaFree(h->d_hs);
+  cudaFree(h->d_partial); cudaFree(h->d_out); cudaFree(h->d_summary);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -649,17 +705,15 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
   std::lock_guard<std::mutex> lk(h->mu);
   osb_solve_options o;
   if (opt) o = *opt; else osb_solve_default_options(&o);
-  // CSR incidence (deterministic: factors in index order within a node)
+  // CSR of contribution slots: node n owns slots [ptr[n], ptr[n+1]); factors in index order within a node, so the
+  // gather order -- and therefore every floating-point sum -- is fixed.
   const size_t n = n_nodes, m = n_factors;
-  std::vector<int32_t> ptr(n + 1, 0), inc(2 * m);
+  std::vector<int32_t> ptr(n + 1, 0), slot_a(m), slot_b(m);
   for (size_t f = 0; f < m; ++f) { ptr[ia[f] + 1]++; ptr[ib[f] + 1]++; }
   for (size_t i = 0; i < n; ++i) ptr[i + 1] += ptr[i];
   {
     std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
-    for (size_t f = 0; f < m; ++f) {
-      inc[fill[ia[f]]++] = (int32_t)(f << 1);
-      inc[fill[ib[f]]++] = (int32_t)((f << 1) | 1);
-    }
+    for (size_t f = 0; f < m; ++f) { slot_a[f] = fill[ia[f]]++; slot_b[f] = fill[ib[f]]++; }
   }
   int n_res = 0;
   for (size_t f = 0; f < m; ++f)
@@ -672,25 +726,59 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
   OSB_CUDA(cudaMemcpyAsync(h->d_ia, ia, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_ib, ib, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_ptr, ptr.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  OSB_CUDA(cudaMemcpyAsync(h->d_inc, inc.data(), 2 * m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_slot_a, slot_a.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(h->d_slot_b, slot_b.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_payload, payload, m * OSB_PAYLOAD_LEN * sizeof(double), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_x0, poses, 4 * n * sizeof(double), cudaMemcpyHostToDevice, st));
 
   SolverDev P;
   P.n = n_nodes; P.m = n_factors;
   P.fixed = h->d_fixed; P.ftype = h->d_type; P.ia = h->d_ia; P.ib = h->d_ib; P.huber = h->d_huber;
-  P.payload = h->d_payload; P.node_ptr = h->d_ptr; P.inc = h->d_inc;
-  P.x[0] = h->d_x0; P.x[1] = h->d_x1; P.lin[0] = h->d_lin0; P.lin[1] = h->d_lin1;
+  P.payload = h->d_payload; P.node_ptr = h->d_ptr; P.slot_a = h->d_slot_a; P.slot_b = h->d_slot_b;
+  P.x[0] = h->d_x0; P.x[1] = h->d_x1; P.Jg = h->d_Jg;
   double* nv = h->d_nodevec;
   const size_t N4 = 4 * (size_t)h->max_nodes, N16 = 16 * (size_t)h->max_nodes;
   P.g = nv; P.D = nv + N4; P.p = nv + 2 * N4; P.z = nv + 3 * N4; P.res = nv + 4 * N4; P.Ap = nv + 5 * N4;
   P.delta = nv + 6 * N4; P.Hnn = nv + 7 * N4; P.Minv = nv + 7 * N4 + N16;
-  P.contrib = h->d_contrib; P.partial = h->d_partial; P.opt = o; P.summary = h->d_summary; P.poses_out = h->d_out;
-  const int want = cdiv(std::max(n_nodes, n_factors), GS_THREADS);
-  const int grid = std::max(1, std::min(want, h->grid));
-  void* args[] = {&P};
+  P.cs = h->d_cs; P.hs = h->d_hs; P.partial = h->d_partial; P.opt = o; P.summary = h->d_summary; P.poses_out = h->d_out;
+
+  // launch shape: ONE thread-block cluster (hardware barrier, ~0.2 us) when the factor list fits 16 CTAs with their
+  // Jacobians in shared memory; otherwise a cooperative grid (software grid barrier).
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(GS_THREADS); cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+  bool launched_cluster = false;
+  {
+    const int G = std::max(1, std::min(GS_MAX_CLUSTER, cdiv(std::max(n_nodes, n_factors), GS_THREADS)));
+    const int fpc = cdiv(n_factors, G);
+    if (h->cluster_ok && (size_t)fpc * 256 <= (size_t)GS_SMEM_J_MAX && cdiv(n_nodes, GS_THREADS) <= 4 * G) {
+      cfg.gridDim = dim3(G); cfg.dynamicSmemBytes = (size_t)fpc * 256;
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, graph_solve_kernel, &cfg) == cudaSuccess && nclusters >= 1) {
+        P.fpc = fpc; P.use_cluster = 1; P.j_in_smem = 1;
+        launched_cluster = true;
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
+  if (!launched_cluster) {
+    int per_sm = 0;
+    const int G0 = std::max(1, std::min(num_sms(), cdiv(std::max(n_nodes, n_factors), GS_THREADS)));
+    int fpc = cdiv(n_factors, G0);
+    P.j_in_smem = ((size_t)fpc * 256 <= (size_t)GS_SMEM_J_MAX) ? 1 : 0;
+    const size_t smem = P.j_in_smem ? (size_t)fpc * 256 : 0;
+    OSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_solve_kernel, GS_THREADS, smem));
+    if (per_sm < 1) { set_error("osb_solver_solve", "solve kernel cannot be made resident"); return OSB_ERR_CUDA; }
+    P.fpc = fpc; P.use_cluster = 0;
+    cfg.gridDim = dim3(G0); cfg.dynamicSmemBytes = smem;
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+  }
   OSB_CUDA(cudaEventRecord(h->ev0, st));
-  OSB_CUDA(cudaLaunchCooperativeKernel((void*)graph_solve_kernel, dim3(grid), dim3(GS_THREADS), args, 0, st));
+  OSB_CUDA(cudaLaunchKernelEx(&cfg, graph_solve_kernel, P));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   OSB_CUDA(cudaEventRecord(h->ev1, st));
   OSB_CUDA(cudaMemcpyAsync(poses, h->d_out, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -719,9 +807,9 @@ extern "C" osb_status osb_solver_linearize(osb_solver* h, int n_nodes, const dou
   OSB_CUDA(cudaMemcpyAsync(h->d_ib, ib, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_payload, payload, m * OSB_PAYLOAD_LEN * sizeof(double), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_x0, poses, 4 * n * sizeof(double), cudaMemcpyHostToDevice, st));
-  double* d_r = h->d_lin0;            // [m][4]
-  double* d_ja = h->d_lin0 + 4 * m;   // [m][16]
-  double* d_jb = h->d_lin1;           // [m][16]
+  double* d_r = h->d_lin;             // [m][4]
+  double* d_ja = h->d_lin + 4 * m;    // [m][16]
+  double* d_jb = h->d_lin + 20 * m;   // [m][16]
   OSB_LAUNCH(graph_linearize_kernel, cdiv(n_factors, 128), 128, 0, st, n_factors, h->d_x0, h->d_type, h->d_ia, h->d_ib,
              h->d_payload, d_r, d_ja, d_jb);
   OSB_CHECK_LAUNCH();

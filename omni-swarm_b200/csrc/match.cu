@@ -25,7 +25,9 @@ template <int Q, int R>
 __global__ void __launch_bounds__(DB_THREADS)
 db_scan_kernel(const float* __restrict__ db, int64_t n_val, const int64_t* __restrict__ n_dev, int dim,
                const float* __restrict__ q, int nq, int k, float* __restrict__ part_scores,
-               int64_t* __restrict__ part_ids) {
+               int64_t* __restrict__ part_ids, float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  if (blockIdx.x == 0)   // final rows start as "no result" (faiss: -inf / -1); the merge kernel overwrites the hits
+    for (int i = threadIdx.x; i < nq * k; i += DB_THREADS) { out_scores[i] = -INFINITY; out_ids[i] = -1; }
   // the row count may live on the device (keyframe front-end: rows are appended without a host round trip);
   // the launch grid was sized for an upper bound, the chunk is derived from the true count.
   const int64_t n = n_dev ? *n_dev : n_val;
@@ -105,49 +107,36 @@ db_scan_kernel(const float* __restrict__ db, int64_t n_val, const int64_t* __res
   }
 }
 
-// merge: one CTA per query ranks the grid*k candidates (valid ones only) and writes the global top-k.  Candidates are
-// staged in shared memory in chunks, so the inner rank-counting loop reads broadcast shared-memory words.
-constexpr int MERGE_CHUNK = 2048;
+// merge: rank counting over the grid*k partial candidates, spread over many CTAs: CTA (x, q) ranks candidates
+// [32x, 32x+32) of query q -- one candidate per warp, the 32 lanes split the comparison range and a shuffle reduction
+// adds the partial counts.  A candidate whose rank is < k writes itself to its final slot (ranks are unique: ids are).
+// The output rows are pre-filled with (-inf, -1) by block 0 of the scan kernel.
 __global__ void __launch_bounds__(1024)
 db_merge_kernel(const float* __restrict__ part_scores, const int64_t* __restrict__ part_ids, int ncand, int k,
                 float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
-  __shared__ float cs[MERGE_CHUNK];
-  __shared__ int64_t ci[MERGE_CHUNK];
-  const int qq = blockIdx.x;
+  const int qq = blockIdx.y;
   const float* ps = part_scores + (size_t)qq * ncand;
   const int64_t* pi = part_ids + (size_t)qq * ncand;
-  for (int i = threadIdx.x; i < k; i += blockDim.x) { out_scores[qq * k + i] = -INFINITY; out_ids[qq * k + i] = -1; }
-  // every thread owns up to PER candidates (ncand <= PER * blockDim.x is guaranteed by the launcher)
-  constexpr int PER = 8;
-  float my_s[PER]; int64_t my_i[PER]; int rank[PER];
-#pragma unroll
-  for (int t = 0; t < PER; ++t) {
-    const int i = threadIdx.x + t * blockDim.x;
-    my_i[t] = (i < ncand) ? pi[i] : -1;
-    my_s[t] = (i < ncand) ? ps[i] : -INFINITY;
-    rank[t] = 0;
-  }
-  for (int c0 = 0; c0 < ncand; c0 += MERGE_CHUNK) {
-    const int cn = min(MERGE_CHUNK, ncand - c0);
-    __syncthreads();
-    for (int j = threadIdx.x; j < cn; j += blockDim.x) { cs[j] = ps[c0 + j]; ci[j] = pi[c0 + j]; }
-    __syncthreads();
-    for (int j = 0; j < cn; ++j) {
-      const float sj = cs[j];
-      const int64_t idj = ci[j];
-      if (idj < 0) continue;
-#pragma unroll
-      for (int t = 0; t < PER; ++t) rank[t] += (sj > my_s[t]) || (sj == my_s[t] && idj < my_i[t]);
-    }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + warp;
+  if (i >= ncand) return;
+  const int64_t idi = __ldg(pi + i);
+  if (idi < 0) return;                       // warp-uniform
+  const float si = __ldg(ps + i);
+  int rank = 0;
+  for (int j = lane; j < ncand; j += 32) {
+    const int64_t idj = __ldg(pi + j);
+    const float sj = __ldg(ps + j);
+    rank += (idj >= 0) && ((sj > si) || (sj == si && idj < idi));
   }
 #pragma unroll
-  for (int t = 0; t < PER; ++t)
-    if (my_i[t] >= 0 && rank[t] < k) { out_scores[qq * k + rank[t]] = my_s[t]; out_ids[qq * k + rank[t]] = my_i[t]; }
+  for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+  if (lane == 0 && rank < k) { out_scores[qq * k + rank] = si; out_ids[qq * k + rank] = idi; }
 }
 
 template <int Q>
 static osb_status launch_scan(const float* db, int64_t n, const int64_t* n_dev, int dim, const float* q, int nq,
-                              int k, int grid, float* ps, int64_t* pi, cudaStream_t st) {
+                              int k, int grid, float* ps, int64_t* pi, float* os, int64_t* oi, cudaStream_t st) {
   constexpr int R = 4;
   size_t smem = ((size_t)Q * dim + (size_t)Q * DB_CHUNK_MAX) * sizeof(float);
   static bool attr_done = false;
@@ -155,7 +144,7 @@ static osb_status launch_scan(const float* db, int64_t n, const int64_t* n_dev, 
     OSB_CUDA(cudaFuncSetAttribute(db_scan_kernel<Q, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
-  OSB_LAUNCH((db_scan_kernel<Q, R>), grid, DB_THREADS, smem, st, db, n, n_dev, dim, q, nq, k, ps, pi);
+  OSB_LAUNCH((db_scan_kernel<Q, R>), grid, DB_THREADS, smem, st, db, n, n_dev, dim, q, nq, k, ps, pi, os, oi);
   OSB_CHECK_LAUNCH();
   return OSB_OK;
 }
@@ -181,13 +170,16 @@ osb_status db_search_device(const float* rows, int64_t n, const int64_t* n_dev, 
     const int nb = min(8, nq - q0);
     const float* qp = q_dev + (size_t)q0 * dim;
     osb_status s;
-    if (nb == 1) s = launch_scan<1>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, st);
-    else if (nb == 2) s = launch_scan<2>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, st);
-    else if (nb <= 4) s = launch_scan<4>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, st);
-    else s = launch_scan<8>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, st);
+    if (nb == 1) s = launch_scan<1>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, scores_dev + (size_t)q0 * k,
+                            ids_dev + (size_t)q0 * k, st);
+    else if (nb == 2) s = launch_scan<2>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, scores_dev + (size_t)q0 * k,
+                            ids_dev + (size_t)q0 * k, st);
+    else if (nb <= 4) s = launch_scan<4>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, scores_dev + (size_t)q0 * k,
+                            ids_dev + (size_t)q0 * k, st);
+    else s = launch_scan<8>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, scores_dev + (size_t)q0 * k,
+                            ids_dev + (size_t)q0 * k, st);
     if (s != OSB_OK) return s;
-    if (grid * k > 8 * 1024) { set_error("db_search", "too many partial candidates for the merge kernel"); return OSB_ERR_CAPACITY; }
-    OSB_LAUNCH(db_merge_kernel, nb, 1024, 0, st, part_scores, part_ids, grid * k, k, scores_dev + (size_t)q0 * k,
+    OSB_LAUNCH(db_merge_kernel, dim3(cdiv(grid * k, 32), nb), 1024, 0, st, part_scores, part_ids, grid * k, k, scores_dev + (size_t)q0 * k,
                ids_dev + (size_t)q0 * k);
     OSB_CHECK_LAUNCH();
   }

@@ -84,6 +84,7 @@ osb_status l2norm_cells(float* x, int64_t cells, int C, cudaStream_t st) {
 // -------------------------------------------------------------------------------------------------------------
 constexpr int KP_THREADS = 1024;
 constexpr int KP_SORT_CAP = 8192;  // survivors sortable in shared memory (64 KB of keys)
+constexpr int KP_RANK_CAP = 4096;  // up to here the order comes from rank counting (no sort); needs 2*CAP key slots
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -128,18 +129,38 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
   int32_t* cand = cand_ + (size_t)b * HW;
   unsigned long long* skey = skey_ + (size_t)b * HW;
 
-  // ---- phase 1: ordered compaction, 4 consecutive pixels per thread per pass (HW is a multiple of 4) ----
-  int base = 0;
-  for (int p0 = 0; p0 < HW; p0 += KP_THREADS * 4) {
-    const int p = p0 + tid * 4;
+  // ---- phase 1: ordered compaction.  Warp w owns the contiguous pixel range [w*seg, (w+1)*seg): pass A counts its
+  // candidates, one block scan turns the 32 warp totals into offsets, pass B rescans and writes cand[] in raster
+  // order with a shuffle scan per 128-pixel row of lanes (no block barrier inside the loops).
+  const int lane = tid & 31, warp = tid >> 5;
+  const int seg = ((HW / 4 + 31) / 32) * 4;          // pixels per warp, multiple of 4
+  const int wp0 = warp * seg, wp1 = min(HW, wp0 + seg);
+  int wcount = 0;
+  for (int p = wp0 + lane * 4; p < wp1; p += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(prob + p);
+    wcount += (v.x > thres) + (v.y > thres) + (v.z > thres) + (v.w > thres);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wcount += __shfl_xor_sync(0xffffffffu, wcount, o);
+  const int wbase = block_exclusive_scan(lane == 0 ? wcount : 0, warp_sums, &s_total);
+  // (only lane 0 contributed, so the exclusive prefix seen by lane 0 of warp w is the sum of earlier warps)
+  int base = __shfl_sync(0xffffffffu, wbase, 0);
+  const int M = s_total;
+  for (int p0 = wp0; p0 < wp1; p0 += 128) {
+    const int p = p0 + lane * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p < HW) v = *reinterpret_cast<const float4*>(prob + p);
-    const int f0 = (p < HW) && (v.x > thres), f1 = (p + 1 < HW) && (v.y > thres);
-    const int f2 = (p + 2 < HW) && (v.z > thres), f3 = (p + 3 < HW) && (v.w > thres);
+    if (p < wp1) v = *reinterpret_cast<const float4*>(prob + p);
+    const int f0 = (p < wp1) && (v.x > thres), f1 = (p < wp1) && (v.y > thres);
+    const int f2 = (p < wp1) && (v.z > thres), f3 = (p < wp1) && (v.w > thres);
     const int cnt = f0 + f1 + f2 + f3;
-    const int off = base + block_exclusive_scan(cnt, warp_sums, &s_total);
-    if (p < HW) {
-      int o = off;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (p < wp1) {
+      int o = base + inc - cnt;
       if (f0) cand[o++] = p;
       if (f1) cand[o++] = p + 1;
       if (f2) cand[o++] = p + 2;
@@ -147,10 +168,8 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
       *reinterpret_cast<uchar4*>(state + p) = make_uchar4(f0, f1, f2, f3);
       *reinterpret_cast<uchar4*>(surv + p) = make_uchar4(0, 0, 0, 0);
     }
-    base += s_total;
-    __syncthreads();
+    base += __shfl_sync(0xffffffffu, inc, 31);
   }
-  const int M = base;
   __syncthreads();
 
   // ---- phase 2: resolve ACTIVE by dependency order ----
@@ -215,7 +234,18 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
   const int n_out = min(S, max_num);
 
   // ---- phase 4: order by (conf desc, raster asc), keep the first max_num ----
-  if (S <= KP_SORT_CAP) {
+  if (S <= KP_RANK_CAP) {
+    // rank counting over the keys in shared memory: the key's rank IS its output slot (keys are unique)
+    for (int i = tid; i < S; i += KP_THREADS) skeys[KP_RANK_CAP + i] = skey[i];
+    __syncthreads();
+    for (int i = tid; i < S; i += KP_THREADS) {
+      const unsigned long long ki = skeys[KP_RANK_CAP + i];
+      int rank = 0;
+      for (int j = 0; j < S; ++j) rank += skeys[KP_RANK_CAP + j] < ki;
+      if (rank < n_out) skeys[rank] = ki;
+    }
+    __syncthreads();
+  } else if (S <= KP_SORT_CAP) {
     int n2 = 32;
     while (n2 < S) n2 <<= 1;
     for (int i = tid; i < n2; i += KP_THREADS) skeys[i] = (i < S) ? skey[i] : ~0ull;
@@ -325,21 +355,26 @@ __device__ __forceinline__ float sample_channel(const float* __restrict__ d, con
   return r;
 }
 
-// per-channel L2 norm over the keypoints of an image (torch::norm(desc, 2, 1) on [256,N], :214); thread = channel
-__global__ void __launch_bounds__(256)
+// per-channel L2 norm over the keypoints of an image (torch::norm(desc, 2, 1) on [256,N], :214).
+// 1024 threads = 4 keypoint groups x 256 channels; group g sums keypoints g, g+4, ... and the four partial sums are
+// combined in a fixed order.
+__global__ void __launch_bounds__(1024)
 sp_desc_norm_kernel(const float* __restrict__ desc, int H, int W, const int32_t* __restrict__ n_kpts,
                     const float* __restrict__ kpts, int max_num, float* __restrict__ cnorm) {
-  const int b = blockIdx.x, ch = threadIdx.x;
+  __shared__ float part[4][256];
+  const int b = blockIdx.x, ch = threadIdx.x & 255, g = threadIdx.x >> 8;
   const int Hc = H / 8, Wc = W / 8;
   const float* d = desc + (size_t)b * Hc * Wc * 256;
   const int N = n_kpts[b];
   float s = 0.f;
-  for (int n = 0; n < N; ++n) {
+  for (int n = g; n < N; n += 4) {
     const Taps t = bilinear_taps(kpts[((size_t)b * max_num + n) * 2], kpts[((size_t)b * max_num + n) * 2 + 1], W, H, Wc, Hc);
     const float v = sample_channel(d, t, Wc, Hc, ch);
     s = fmaf(v, v, s);
   }
-  cnorm[b * 256 + ch] = sqrtf(s);
+  part[g][ch] = s;
+  __syncthreads();
+  if (g == 0) cnorm[b * 256 + ch] = sqrtf((part[0][ch] + part[1][ch]) + (part[2][ch] + part[3][ch]));
 }
 
 // (S^T / cnorm - mean) @ comp^T  (:215-221).  CTA = 8 keypoints of one image, 256 threads.
@@ -380,7 +415,7 @@ sp_desc_pca_kernel(const float* __restrict__ desc, int H, int W, const int32_t* 
 osb_status sp_descriptors(const float* desc_nhwc, int B, int H, int W, const int32_t* n_kpts, const float* kpts,
                           int max_num, const float* pca_compT, const float* pca_mean, float* cnorm, float* out,
                           cudaStream_t st) {
-  OSB_LAUNCH(sp_desc_norm_kernel, B, 256, 0, st, desc_nhwc, H, W, n_kpts, kpts, max_num, cnorm);
+  OSB_LAUNCH(sp_desc_norm_kernel, B, 1024, 0, st, desc_nhwc, H, W, n_kpts, kpts, max_num, cnorm);
   OSB_CHECK_LAUNCH();
   dim3 grid(cdiv(max_num, DP_KP), B);
   OSB_LAUNCH(sp_desc_pca_kernel, grid, 256, 0, st, desc_nhwc, H, W, n_kpts, kpts, max_num, cnorm, pca_compT, pca_mean, out);

@@ -85,7 +85,9 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
   if (use_umma) {
     // input geometry of every conv layer: which ping-pong buffer it reads and its [H][W][C]
     // (layer order: 1 conv1b 2 conv2a 3 conv2b 4 conv3a 5 conv3b 6 conv4a 7 conv4b 8 convPa 9 convPb 10 convDa 11 convDb)
-    const int in_buf[12] = {-1, 0, 0, 1, 1, 0, 0, 1, 0, 1, 0, 1};      // 0 = actA, 1 = actB
+    // with the pools fused into the conv epilogues the layers simply alternate between the two buffers;
+    // conv4b's output x (layer 8 input) stays in B while convPa writes A, so convDa (10) reads B, convDb (11) reads A
+    const int in_buf[12] = {-1, 0, 1, 0, 1, 0, 1, 0, 1, 0, 1, 0};      // 0 = actA, 1 = actB
     const int in_div[12] = {0, 1, 2, 2, 4, 4, 8, 8, 8, 8, 8, 8};
     for (int i = 1; i < 12; ++i) {
       const int h = H / in_div[i], w = W / in_div[i], c = SP_CIN[i];
@@ -128,33 +130,24 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
   osb_status s;
 #define RUN(x) do { s = (x); if (s != OSB_OK) return s; } while (0)
   const float SA = SP_ACT_SCALE;
-  auto conv = [&](int i, int h, int w, int out_layer /*layer whose input planes receive the result*/) {
+  // conv layer i at resolution h x w; its output (optionally 2x2 max-pooled in the epilogue) becomes the input planes
+  // of layer `out_layer`
+  auto conv = [&](int i, int h, int w, int out_layer, int pool) {
     return umma_conv_forward(UL[i], tmA[i], tmB[i], B, h, w, SA, in_hi[out_layer], in_lo[out_layer], nullptr,
-                             SP_COUT[i], SP_COUT[i], SA, 1, st);
+                             SP_COUT[i], SP_COUT[i], SA, 1, pool, st);
   };
-  // pooled outputs go through a temporary plane pair placed in the *other* ping-pong buffer
-  auto planes = [&](float* buf, int h, int w, int c, __half** hi, __half** lo) {
-    *hi = reinterpret_cast<__half*>(buf); *lo = *hi + (size_t)max_batch * h * w * c;
-  };
-  __half *th, *tl;
-  RUN(umma_first_forward(w1a, b1a, lut, img_dev, in_hi[1], in_lo[1], B, H, W, SA, st));            // conv1a -> A
-  planes(actB, H, W, 64, &th, &tl);
-  RUN(umma_conv_forward(UL[1], tmA[1], tmB[1], B, H, W, SA, th, tl, nullptr, 64, 64, SA, 1, st));     // conv1b -> B
-  RUN(umma_maxpool_forward(th, tl, in_hi[2], in_lo[2], B, H, W, 64, st));                             // pool  -> A
-  RUN(conv(2, H / 2, W / 2, 3));                                                                      // conv2a A -> B
-  planes(actA, H / 2, W / 2, 64, &th, &tl);
-  RUN(umma_conv_forward(UL[3], tmA[3], tmB[3], B, H / 2, W / 2, SA, th, tl, nullptr, 64, 64, SA, 1, st));   // conv2b B -> A
-  RUN(umma_maxpool_forward(th, tl, in_hi[4], in_lo[4], B, H / 2, W / 2, 64, st));                     // pool  -> B
-  RUN(conv(4, H / 4, W / 4, 5));                                                                      // conv3a B -> A
-  planes(actB, H / 4, W / 4, 128, &th, &tl);
-  RUN(umma_conv_forward(UL[5], tmA[5], tmB[5], B, H / 4, W / 4, SA, th, tl, nullptr, 128, 128, SA, 1, st)); // conv3b A -> B
-  RUN(umma_maxpool_forward(th, tl, in_hi[6], in_lo[6], B, H / 4, W / 4, 128, st));                    // pool  -> A
-  RUN(conv(6, Hc, Wc, 7));                                                                            // conv4a A -> B
-  RUN(conv(7, Hc, Wc, 8));                                                                            // conv4b B -> A (x)
-  RUN(conv(8, Hc, Wc, 9));                                                                            // convPa A -> B
-  RUN(umma_conv_forward(UL[9], tmA[9], tmB[9], B, Hc, Wc, SA, nullptr, nullptr, d_logits, 80, 80, 1.f, 0, st));   // convPb
-  RUN(conv(10, Hc, Wc, 11));                                                                          // convDa A -> B
-  RUN(umma_conv_forward(UL[11], tmA[11], tmB[11], B, Hc, Wc, SA, nullptr, nullptr, d_desc, 256, 256, 1.f, 0, st)); // convDb
+  RUN(umma_first_forward(w1a, b1a, lut, img_dev, in_hi[1], in_lo[1], B, H, W, SA, st));   // conv1a            -> A
+  RUN(conv(1, H, W, 2, 1));                                                               // conv1b + pool     -> B
+  RUN(conv(2, H / 2, W / 2, 3, 0));                                                       // conv2a            -> A
+  RUN(conv(3, H / 2, W / 2, 4, 1));                                                       // conv2b + pool     -> B
+  RUN(conv(4, H / 4, W / 4, 5, 0));                                                       // conv3a            -> A
+  RUN(conv(5, H / 4, W / 4, 6, 1));                                                       // conv3b + pool     -> B
+  RUN(conv(6, Hc, Wc, 7, 0));                                                             // conv4a            -> A
+  RUN(conv(7, Hc, Wc, 8, 0));                                                             // conv4b            -> B (x)
+  RUN(conv(8, Hc, Wc, 9, 0));                                                             // convPa            -> A
+  RUN(umma_conv_forward(UL[9], tmA[9], tmB[9], B, Hc, Wc, SA, nullptr, nullptr, d_logits, 80, 80, 1.f, 0, 0, st));   // convPb
+  RUN(conv(10, Hc, Wc, 11, 0));                                                           // convDa (reads B)  -> A
+  RUN(umma_conv_forward(UL[11], tmA[11], tmB[11], B, Hc, Wc, SA, nullptr, nullptr, d_desc, 256, 256, 1.f, 0, 0, st)); // convDb
   RUN(l2norm_cells(d_desc, (int64_t)B * Hc * Wc, 256, st));
   RUN(sp_softmax_shuffle(d_logits, 80, d_semi, B, Hc, Wc, st));
 #undef RUN
