@@ -79,6 +79,11 @@ osb_status osb_superpoint_infer_dev(osb_superpoint* h, const uint8_t* images_dev
 osb_status osb_superpoint_postprocess(osb_superpoint* h, const float* semi, const float* desc_nchw, int batch,
                                       int32_t* n_kpts, float* kpts, float* desc);
 osb_status osb_superpoint_read(osb_superpoint* h, int what, int image, float* out, size_t n_floats);
+/* per-layer device time of the last infer() (bench / profiling aid; tensor-core path only): enable, run infer(), then
+ * layer_ms fills ms[0..11] = conv1a, conv1b(+pool), conv2a, conv2b(+pool), conv3a, conv3b(+pool), conv4a, conv4b, convPa,
+ * convPb, convDa, convDb in milliseconds (CUDA events on the handle's stream). */
+osb_status osb_superpoint_set_profiling(osb_superpoint* h, int enable);
+osb_status osb_superpoint_layer_ms(osb_superpoint* h, float* ms, int n);
 
 /* ------------------------------------------------------------------------------------------------------------
  * NetVLAD global descriptor -- replaces class MobileNetVLADTensorRT
@@ -178,6 +183,11 @@ osb_status osb_solver_destroy(osb_solver* h);
 osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses, const uint8_t* fixed, int n_factors,
                             const int32_t* type, const int32_t* ia, const int32_t* ib, const double* payload,
                             const uint8_t* huber, const osb_solve_options* opt, osb_solve_summary* summary);
+/* profiling aid: SM-clock cycles block 0 spent in the phases of the LAST solve, summed over its CG iterations:
+ * out[0] factor phase, [1] barrier after it, [2] node phase 1, [3] reduction 1, [4] node phase 2, [5] reduction 2,
+ * [6] number of CG iterations, [7] whole kernel; [8] CTAs, [9] 1 = one thread-block cluster (hardware barrier) /
+ * 0 = cooperative grid, [10] 1 = Jacobians in shared memory, [11] threads per CTA. */
+osb_status osb_solver_phase_cycles(osb_solver* h, double* out12);
 /* residual + analytic Jacobian of every factor at `poses` (parity hook for the factor kernels):
  * r [n_factors][4], Ja/Jb [n_factors][4][4] (rows >= the factor's residual count are zero), un-robustified. */
 osb_status osb_solver_linearize(osb_solver* h, int n_nodes, const double* poses, int n_factors,

@@ -27,7 +27,6 @@ namespace osb {
 
 constexpr int UM_TH = 8, UM_TW = 16;            // output tile (pixels)
 constexpr int UM_KC = 64;                       // fp16 channels per K slab (= 128 bytes = one swizzle row)
-constexpr int UM_A_BYTES = UM_TH * UM_TW * 128; // 16 KB per plane per stage
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -79,13 +78,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Shared-memory plan.  For a 3x3 layer ONE A box per (kx, 64-channel slab) carries 10 rows (tile + vertical halo):
+// the three vertical taps ky = 0,1,2 read it at row offsets ky*16 rows = ky*2048 bytes -- a multiple of the 1024-byte
+// swizzle atom, so the same SWIZZLE_128B descriptor applies with only the start address moved.  That cuts the
+// activation traffic from 9 to 3.75 tile-loads per tile (L2 -> shared memory is what bounds this kernel).
+// The weights of each tap stream through their own ring.
+constexpr int UM_A_SLOT = (UM_TH + 2) * UM_TW * 128;   // 20 KB per plane: 10 rows x 16 px x 128 B
+constexpr int UM_A_SLOTS = 2;
 template <int N>
 struct UmmaCfg {
-  static constexpr int B_BYTES = N * 128;                        // one weight plane per stage
-  static constexpr int STAGE_BYTES = 2 * UM_A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (N <= 64) ? 4 : (N <= 128) ? 3 : 2;
+  static constexpr int B_BYTES = N * 128;                        // one weight plane of one tap / slab
+  static constexpr int B_SLOT = 2 * B_BYTES;                     // hi + lo
+  static constexpr int B_SLOTS = (N <= 64) ? 6 : (N <= 80) ? 5 : (N <= 128) ? 4 : 2;
+  static constexpr int A_RING = UM_A_SLOTS * 2 * UM_A_SLOT;      // 80 KB
   static constexpr int TMEM_COLS = (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = A_RING + B_SLOTS * B_SLOT + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
 struct UmmaArgs {
@@ -100,7 +107,8 @@ struct UmmaArgs {
   int out_cstride;         // channel stride of the destination
   float inv_scale;         // 1 / (act_scale * w_scale)
   float out_scale;         // scale of the stored fp16 planes
-  int relu;
+  int relu;                // 0 none, 1 ReLU, 2 ReLU6
+  int n_off;               // first output channel of this launch (Cout > 256 runs as several N <= 256 passes)
   int pool;                // 1: fused 2x2 max-pool, the planes written are [B][H/2][W/2][C]
 };
 
@@ -109,25 +117,28 @@ __global__ void __launch_bounds__(256, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, UmmaArgs P) {
   using Cfg = UmmaCfg<N>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int AS = UM_A_SLOTS, BS = Cfg::B_SLOTS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;     // 8-byte barriers
-  // barrier map: full[s] = bar_base + 8 s ; empty[s] = + 8 (STAGES + s) ; tmem_full[a] ; tmem_empty[a]
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t b_base = smem_base + Cfg::A_RING;
+  const uint32_t bar_base = b_base + BS * Cfg::B_SLOT;                   // 8-byte barriers
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (AS + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * AS + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * AS + BS + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * AS + 2 * BS + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * AS + 2 * BS + 2 + a); };
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_x = (P.W + UM_TW - 1) / UM_TW, tiles_y = (P.H + UM_TH - 1) / UM_TH;
   const int n_tiles = P.B * tiles_x * tiles_y;
-  const int taps = P.ks * P.ks, halo = P.ks / 2;
-  const int k_steps = taps * P.cin_slabs;
+  const int halo = P.ks / 2;
+  const uint32_t a_box_bytes = (uint32_t)(UM_TH + 2 * halo) * UM_TW * 128;   // bytes of one A plane box
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < AS; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -143,21 +154,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aph = 0;
+    int bs = 0; uint32_t bph = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
       const int x0 = tx * UM_TW, y0 = ty * UM_TH;
-      for (int tap = 0; tap < taps; ++tap) {
-        const int ky = tap / P.ks, kx = tap % P.ks;
+      for (int kx = 0; kx < P.ks; ++kx) {
         for (int cs = 0; cs < P.cin_slabs; ++cs) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          tma_load_4d(sa, &tm_a_hi, full_bar(stage), cs * UM_KC, x0 + kx - halo, y0 + ky - halo, b);
-          tma_load_4d(sa + UM_A_BYTES, &tm_a_lo, full_bar(stage), cs * UM_KC, x0 + kx - halo, y0 + ky - halo, b);
-          tma_load_3d(sa + 2 * UM_A_BYTES, &tm_w_hi, full_bar(stage), cs * UM_KC, 0, tap);
-          tma_load_3d(sa + 2 * UM_A_BYTES + Cfg::B_BYTES, &tm_w_lo, full_bar(stage), cs * UM_KC, 0, tap);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          // activation box: tile rows + vertical halo at the kx-shifted column, shared by the ks vertical taps
+          mbar_wait(a_empty(as), aph ^ 1);
+          const uint32_t sa = smem_base + as * (2 * UM_A_SLOT);
+          mbar_expect_tx(a_full(as), 2 * a_box_bytes);
+          tma_load_4d(sa, &tm_a_hi, a_full(as), cs * UM_KC, x0 + kx - halo, y0 - halo, b);
+          tma_load_4d(sa + UM_A_SLOT, &tm_a_lo, a_full(as), cs * UM_KC, x0 + kx - halo, y0 - halo, b);
+          if (++as == AS) { as = 0; aph ^= 1; }
+          for (int ky = 0; ky < P.ks; ++ky) {
+            mbar_wait(b_empty(bs), bph ^ 1);
+            const uint32_t sb = b_base + bs * Cfg::B_SLOT;
+            mbar_expect_tx(b_full(bs), Cfg::B_SLOT);
+            tma_load_3d(sb, &tm_w_hi, b_full(bs), cs * UM_KC, P.n_off, ky * P.ks + kx);
+            tma_load_3d(sb + Cfg::B_BYTES, &tm_w_lo, b_full(bs), cs * UM_KC, P.n_off, ky * P.ks + kx);
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
         }
       }
     }
@@ -166,29 +184,43 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = f16 (0), K-major both,
     // N >> 3 at bit 17, M >> 4 at bit 24
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aph = 0;
+    int bs = 0; uint32_t bph = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
-      for (int ks = 0; ks < k_steps; ++ks) {
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-        const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + UM_A_BYTES);
-        const uint64_t b_hi = umma_desc_sw128(sa + 2 * UM_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * UM_A_BYTES + Cfg::B_BYTES);
+      uint32_t first = 1;
+      for (int kx = 0; kx < P.ks; ++kx) {
+        for (int cs = 0; cs < P.cin_slabs; ++cs) {
+          mbar_wait(a_full(as), aph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + as * (2 * UM_A_SLOT);
+          for (int ky = 0; ky < P.ks; ++ky) {
+            mbar_wait(b_full(bs), bph);
+            tc_fence_after();
+            const uint32_t sb = b_base + bs * Cfg::B_SLOT;
+            // vertical tap ky reads the box from tile row ky on: + ky * 16 px * 128 B = ky * 2048 B (2 swizzle atoms)
+            const uint64_t a_hi = umma_desc_sw128(sa + ky * (UM_TW * 128));
+            const uint64_t a_lo = umma_desc_sw128(sa + UM_A_SLOT + ky * (UM_TW * 128));
+            const uint64_t b_hi = umma_desc_sw128(sb), b_lo = umma_desc_sw128(sb + Cfg::B_BYTES);
 #pragma unroll
-        for (int k = 0; k < UM_KC / 16; ++k) {
-          const uint64_t adv = (uint64_t)(k * 32 >> 4);       // advance 16 fp16 = 32 bytes inside the swizzle row
-          umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, (ks | k) ? 1u : 0u);
-          umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-          umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+            for (int k = 0; k < UM_KC / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);     // advance 16 fp16 = 32 bytes inside the swizzle row
+              umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+              umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+            }
+            first = 0;
+            umma_commit(b_empty(bs));                            // weight slot free when these MMAs retire
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
+          umma_commit(a_empty(as));                              // activation box free after its last vertical tap
+          if (++as == AS) { as = 0; aph ^= 1; }
         }
-        umma_commit(empty_bar(stage));                         // frees the smem slot when these MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull_bar(acc));                             // accumulator complete -> epilogue
+      umma_commit(tfull_bar(acc));                               // accumulator complete -> epilogue
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -218,8 +250,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float a = fmaf(__uint_as_float(v[i]), P.inv_scale, __ldg(P.bias + n0 + i));
+          float a = fmaf(__uint_as_float(v[i]), P.inv_scale, __ldg(P.bias + P.n_off + n0 + i));
           if (P.relu) a = fmaxf(a, 0.f);
+          if (P.relu == 2) a = fminf(a, 6.f);
           f[i] = a;
         }
         bool store = inside;
@@ -234,7 +267,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
         if (!store) continue;
         if (P.out_f32) {
-          float4* dst = reinterpret_cast<float4*>(P.out_f32 + opix * P.out_cstride + n0);
+          float4* dst = reinterpret_cast<float4*>(P.out_f32 + opix * P.out_cstride + P.n_off + n0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
         } else {
@@ -247,8 +280,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
             lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
           }
-          uint4* dh = reinterpret_cast<uint4*>(P.out_hi + opix * P.out_cstride + n0);
-          uint4* dl = reinterpret_cast<uint4*>(P.out_lo + opix * P.out_cstride + n0);
+          uint4* dh = reinterpret_cast<uint4*>(P.out_hi + opix * P.out_cstride + P.n_off + n0);
+          uint4* dl = reinterpret_cast<uint4*>(P.out_lo + opix * P.out_cstride + P.n_off + n0);
           dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
           dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
@@ -284,42 +317,66 @@ __device__ __forceinline__ void split_store8(__half* hi, __half* lo, const float
   *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// thread = (pixel, group of 8 output channels): the 8 threads of a pixel write 128 contiguous bytes per plane, a warp
-// 512 contiguous bytes (this kernel is bound by its 629 MB of stores per 8-image keyframe)
-__global__ void __launch_bounds__(256)
+// One thread per pixel computes all 64 channels (9 LUT loads, 576 FMAs); the 128 pixels of a CTA are contiguous in the
+// NHWC planes, so each plane's 16 KB tile is staged in shared memory (16-byte chunks XOR-swizzled by the pixel index)
+// and written out with fully coalesced 16-byte stores.  The kernel is bound by its 629 MB of stores per keyframe.
+__global__ void __launch_bounds__(128)
 conv_first_split_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ lut,
                         const uint8_t* __restrict__ img, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                         int H, int W, float out_scale) {
   __shared__ __align__(16) float sw[9][64];
   __shared__ __align__(16) float sb[64];
   __shared__ float slut[256];
+  __shared__ uint4 tile_hi[128 * 8], tile_lo[128 * 8];       // [pixel][16-byte chunk ^ (pixel & 7)]
   for (int e = threadIdx.x; e < 9 * 64; e += blockDim.x) (&sw[0][0])[e] = w[e];
   for (int e = threadIdx.x; e < 64; e += blockDim.x) sb[e] = bias[e];
   for (int e = threadIdx.x; e < 256; e += blockDim.x) slut[e] = lut[e];
   __syncthreads();
-  const int b = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int p = t >> 3, o8 = t & 7;
-  if (p >= H * W) return;
-  const int oy = p / W, ox = p % W;
-  const uint8_t* ib = img + (size_t)b * H * W;
-  float in[9];
+  const int b = blockIdx.y, t = threadIdx.x;
+  const int p0 = blockIdx.x * 128;
+  const int p = p0 + t;
+  const int HW = H * W;
+  if (p < HW) {
+    const int oy = p / W, ox = p % W;
+    const uint8_t* ib = img + (size_t)b * HW;
+    float in[9];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int gy = oy + ky - 1, gx = ox + kx - 1;
-      in[ky * 3 + kx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? slut[ib[(size_t)gy * W + gx]] : 0.f;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int gy = oy + ky - 1, gx = ox + kx - 1;
+        in[ky * 3 + kx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? slut[ib[(size_t)gy * W + gx]] : 0.f;
+      }
+#pragma unroll 2
+    for (int o8 = 0; o8 < 8; ++o8) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int tt = 0; tt < 9; ++tt) {
+          a0 = fmaf(in[tt], sw[tt][8 * o8 + 2 * j2], a0);
+          a1 = fmaf(in[tt], sw[tt][8 * o8 + 2 * j2 + 1], a1);
+        }
+        const float s0 = fmaxf(a0 + sb[8 * o8 + 2 * j2], 0.f) * out_scale, s1 = fmaxf(a1 + sb[8 * o8 + 2 * j2 + 1], 0.f) * out_scale;
+        const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
+        const __half l0 = __float2half_rn(s0 - __half2float(h0)), l1 = __float2half_rn(s1 - __half2float(h1));
+        h[j2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        l[j2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+      tile_hi[t * 8 + (o8 ^ (t & 7))] = make_uint4(h[0], h[1], h[2], h[3]);
+      tile_lo[t * 8 + (o8 ^ (t & 7))] = make_uint4(l[0], l[1], l[2], l[3]);
     }
-  float r[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float a = 0.f;
-#pragma unroll
-    for (int tt = 0; tt < 9; ++tt) a = fmaf(in[tt], sw[tt][8 * o8 + j], a);
-    r[j] = fmaxf(a + sb[8 * o8 + j], 0.f);
   }
-  split_store8(out_hi + ((size_t)b * H * W + p) * 64 + 8 * o8, out_lo + ((size_t)b * H * W + p) * 64 + 8 * o8, r, out_scale);
+  __syncthreads();
+  const int npx = min(128, HW - p0);
+  uint4* gh = reinterpret_cast<uint4*>(out_hi + ((size_t)b * HW + p0) * 64);
+  uint4* gl = reinterpret_cast<uint4*>(out_lo + ((size_t)b * HW + p0) * 64);
+  for (int i = t; i < npx * 8; i += 128) {
+    const int px = i >> 3, ch = i & 7;
+    gh[i] = tile_hi[px * 8 + (ch ^ (px & 7))];
+    gl[i] = tile_lo[px * 8 + (ch ^ (px & 7))];
+  }
 }
 
 // one thread per (output pixel, 8 channels)
@@ -398,8 +455,8 @@ static osb_status make_tmap(CUtensorMap* tm, void* base, int rank, const uint64_
 osb_status umma_layer_upload(UmmaLayer* L, const float* w_oihw, const float* bias, int cin, int cout, int ks,
                              float w_scale) {
   L->cin = cin; L->cout = cout; L->ks = ks; L->taps = ks * ks; L->w_scale = w_scale;
-  L->n_pad = (cout <= 64) ? 64 : (cout <= 80) ? 80 : (cout <= 128) ? 128 : 256;
-  OSB_REQUIRE(cin % UM_KC == 0 && cout <= 256, "tcgen05 conv: Cin must be a multiple of 64 and Cout <= 256");
+  L->n_pad = (cout <= 64) ? 64 : (cout <= 80) ? 80 : (cout <= 128) ? 128 : (cout <= 256) ? 256 : 512;
+  OSB_REQUIRE(cin % UM_KC == 0 && cout <= 512, "tcgen05 conv: Cin must be a multiple of 64 and Cout <= 512");
   const size_t n = (size_t)L->taps * L->n_pad * cin;
   std::vector<__half> hi(n, __float2half(0.f)), lo(n, __float2half(0.f));
   std::vector<float> bp(L->n_pad, 0.f);
@@ -422,7 +479,7 @@ osb_status umma_layer_upload(UmmaLayer* L, const float* w_oihw, const float* bia
   OSB_CUDA(cudaMemcpy(L->bias, bp.data(), L->n_pad * sizeof(float), cudaMemcpyHostToDevice));
   const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)L->n_pad, (uint64_t)L->taps};
   const uint64_t strides[2] = {(uint64_t)cin * 2, (uint64_t)cin * L->n_pad * 2};
-  const uint32_t box[3] = {UM_KC, (uint32_t)L->n_pad, 1};
+  const uint32_t box[3] = {UM_KC, (uint32_t)std::min(L->n_pad, 256), 1};
   osb_status s;
   if ((s = make_tmap(&L->tm_hi, L->w_hi, 3, dims, strides, box)) != OSB_OK) return s;
   return make_tmap(&L->tm_lo, L->w_lo, 3, dims, strides, box);
@@ -433,10 +490,12 @@ void umma_layer_free(UmmaLayer* L) {
   L->w_hi = L->w_lo = nullptr; L->bias = nullptr;
 }
 
-osb_status umma_act_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half* p_lo, int B, int H, int W, int C) {
+osb_status umma_act_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half* p_lo, int B, int H, int W, int C,
+                         int ks) {
   const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-  const uint32_t box[4] = {UM_KC, UM_TW, UM_TH, 1};
+  // the box carries the vertical halo of the layer that READS these planes (ks x ks filter)
+  const uint32_t box[4] = {UM_KC, UM_TW, (uint32_t)(UM_TH + 2 * (ks / 2)), 1};
   osb_status s;
   if ((s = make_tmap(hi, p_hi, 4, dims, strides, box)) != OSB_OK) return s;
   return make_tmap(lo, p_lo, 4, dims, strides, box);
@@ -469,20 +528,72 @@ osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const 
   P.out_c = out_c; P.out_cstride = out_cstride;
   P.inv_scale = 1.0f / (act_scale * L.w_scale); P.out_scale = out_scale; P.relu = relu;
   OSB_REQUIRE(out_c % 16 == 0 && out_c <= L.n_pad && out_cstride % 8 == 0, "tcgen05 conv: bad output channel layout");
+  P.n_off = 0;
   switch (L.n_pad) {
     case 64: return launch_umma<64>(a_hi, a_lo, L, P, st);
     case 80: return launch_umma<80>(a_hi, a_lo, L, P, st);
     case 128: return launch_umma<128>(a_hi, a_lo, L, P, st);
     case 256: return launch_umma<256>(a_hi, a_lo, L, P, st);
+    case 512: {                                   // two N = 256 passes over the same activations
+      P.out_c = 256;
+      osb_status s = launch_umma<256>(a_hi, a_lo, L, P, st);
+      if (s != OSB_OK) return s;
+      P.n_off = 256;
+      return launch_umma<256>(a_hi, a_lo, L, P, st);
+    }
   }
   set_error("umma_conv_forward", "unsupported N");
   return OSB_ERR_INVALID;
 }
 
+// depthwise 3x3 (pad 1, stride s) + bias + ReLU6 on fp32 NHWC input, output as split fp16 planes for the pointwise
+// tcgen05 conv that follows; one thread per (output pixel, 8 channels)
+__global__ void dwconv3x3_split_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                       const float* __restrict__ x, __half* __restrict__ out_hi,
+                                       __half* __restrict__ out_lo, int H, int W, int Ho, int Wo, int C, int stride,
+                                       float out_scale, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int C8 = C >> 3;
+  const int c = (int)(i % C8) * 8;
+  int64_t p = i / C8;
+  const int ox = (int)(p % Wo); p /= Wo;
+  const int oy = (int)(p % Ho);
+  const int b = (int)(p / Ho);
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int gy = oy * stride + ky - 1, gx = ox * stride + kx - 1;
+      if (gy < 0 || gy >= H || gx < 0 || gx >= W) continue;
+      const float4* xp = reinterpret_cast<const float4*>(x + (((size_t)b * H + gy) * W + gx) * C + c);
+      const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(ky * 3 + kx) * C + c);
+      const float4 v0 = xp[0], v1 = xp[1], w0 = wp[0], w1 = wp[1];
+      a[0] = fmaf(v0.x, w0.x, a[0]); a[1] = fmaf(v0.y, w0.y, a[1]); a[2] = fmaf(v0.z, w0.z, a[2]); a[3] = fmaf(v0.w, w0.w, a[3]);
+      a[4] = fmaf(v1.x, w1.x, a[4]); a[5] = fmaf(v1.y, w1.y, a[5]); a[6] = fmaf(v1.z, w1.z, a[6]); a[7] = fmaf(v1.w, w1.w, a[7]);
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = fminf(fmaxf(a[j] + bias[c + j], 0.f), 6.f);
+  split_store8(out_hi + (size_t)i * 8, out_lo + (size_t)i * 8, a, out_scale);
+}
+
+osb_status umma_dwconv_forward(const float* w_tap_c, const float* bias, const float* x, __half* out_hi, __half* out_lo,
+                               int B, int H, int W, int C, int stride, float out_scale, cudaStream_t st) {
+  const int Ho = H / stride, Wo = W / stride;
+  const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
+  OSB_LAUNCH(dwconv3x3_split_kernel, (unsigned)cdiv64(total, 256), 256, 0, st, w_tap_c, bias, x, out_hi, out_lo, H, W,
+             Ho, Wo, C, stride, out_scale, total);
+  OSB_CHECK_LAUNCH();
+  return OSB_OK;
+}
+
 osb_status umma_first_forward(const float* w_tap_cout, const float* bias, const float* lut, const uint8_t* img,
                               __half* out_hi, __half* out_lo, int B, int H, int W, float out_scale, cudaStream_t st) {
-  dim3 grid(cdiv(H * W * 8, 256), B);
-  OSB_LAUNCH(conv_first_split_kernel, grid, 256, 0, st, w_tap_cout, bias, lut, img, out_hi, out_lo, H, W, out_scale);
+  dim3 grid(cdiv(H * W, 128), B);
+  OSB_LAUNCH(conv_first_split_kernel, grid, 128, 0, st, w_tap_cout, bias, lut, img, out_hi, out_lo, H, W, out_scale);
   OSB_CHECK_LAUNCH();
   return OSB_OK;
 }

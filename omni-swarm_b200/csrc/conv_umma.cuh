@@ -19,14 +19,18 @@ osb_status umma_layer_upload(UmmaLayer* L, const float* w_oihw, const float* bia
                              float w_scale);
 void umma_layer_free(UmmaLayer* L);
 // TMA descriptors of an activation tensor stored as two fp16 NHWC planes [B][H][W][C]
-osb_status umma_act_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half* p_lo, int B, int H, int W, int C);
-// y = act(conv(x) + b), optionally followed by a fused 2x2 max-pool (pool = 1: output is [B][H/2][W/2][C]);
+osb_status umma_act_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half* p_lo, int B, int H, int W, int C,
+                         int ks);
+// relu: 0 none, 1 ReLU, 2 ReLU6.  y = act(conv(x) + b), optionally followed by a fused 2x2 max-pool (pool = 1: output is [B][H/2][W/2][C]);
 // output either as split fp16 planes (out_hi/out_lo, scaled by out_scale) or as fp32
 osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int B, int H, int W,
                              float act_scale, __half* out_hi, __half* out_lo, float* out_f32, int out_c, int out_cstride,
                              float out_scale, int relu, int pool, cudaStream_t st);
 osb_status umma_first_forward(const float* w_tap_cout, const float* bias, const float* lut, const uint8_t* img,
                               __half* out_hi, __half* out_lo, int B, int H, int W, float out_scale, cudaStream_t st);
+// depthwise 3x3 + bias + ReLU6, fp32 NHWC in, split fp16 planes out (feeds a pointwise tcgen05 conv)
+osb_status umma_dwconv_forward(const float* w_tap_c, const float* bias, const float* x, __half* out_hi, __half* out_lo,
+                               int B, int H, int W, int C, int stride, float out_scale, cudaStream_t st);
 osb_status umma_maxpool_forward(const __half* in_hi, const __half* in_lo, __half* out_hi, __half* out_lo, int B, int H,
                                 int W, int C, cudaStream_t st);
 

@@ -174,6 +174,7 @@ struct SolverDev {
   osb_solve_options opt;
   osb_solve_summary* summary;
   double* poses_out;
+  long long* dbg;          // [8] cycle counters of block 0 / thread 0 (profiling aid, see osb_solver_phase_cycles)
 };
 
 __device__ __forceinline__ void all_sync(const SolverDev& P, cg::grid_group& grid) {
@@ -358,7 +359,11 @@ graph_solve_kernel(SolverDev P) {
   else { J.base = P.Jg; J.stride = P.m; J.off = blockIdx.x * P.fpc; }
   int parity = 0;
   unsigned long long t0 = 0;
-  if (gtid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  const long long k0 = clock64();
+  if (gtid == 0) {
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (int i = 0; i < 8; ++i) P.dbg[i] = 0;
+  }
 
   int cur = 0;
   double radius = P.opt.initial_trust_radius;
@@ -440,6 +445,7 @@ graph_solve_kernel(SolverDev P) {
     int it = 0;
     // ---- PCG iterations: 3 barriers each ----
     while (it < P.opt.max_pcg_iterations && rr0 > 0.0) {
+      long long c0 = clock64();
       // factor phase: p_a = z_a + beta p_a (on the fly), t = Ja p_a + Jb p_b, contributions Ja^T t, Jb^T t
       for (int f = f0 + threadIdx.x; f < f1; f += GS_THREADS) {
         const int li = f - f0;
@@ -470,7 +476,9 @@ graph_solve_kernel(SolverDev P) {
           __stcg(ca + j, sa); __stcg(cb + j, sb);
         }
       }
+      long long c1 = clock64();
       all_sync(P, grid);
+      long long c2 = clock64();
       // node phase 1: p = z + beta p (stored), Ap = sum of the node's slots + lam D p, partial p.Ap
       double v1b[1] = {0.0};
       for (int n = gtid; n < P.n; n += T) {
@@ -490,7 +498,9 @@ graph_solve_kernel(SolverDev P) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) { __stcg(P.p + 4 * n + i, pn[i]); P.Ap[4 * n + i] = ap[i]; v1b[0] += pn[i] * ap[i]; }
       }
+      long long c3 = clock64();
       grid_reduce_sum<1>(v1b, P, parity, sh, grid); parity ^= 1;
+      long long c4 = clock64();
       const double pAp = v1b[0];
       if (!(pAp > 0.0)) break;
       const double alpha = rz / pAp;
@@ -514,7 +524,13 @@ graph_solve_kernel(SolverDev P) {
           v22[0] += rn[i] * zn[i]; v22[1] += rn[i] * rn[i];
         }
       }
+      long long c5 = clock64();
       grid_reduce_sum<2>(v22, P, parity, sh, grid); parity ^= 1;
+      if (gtid == 0) {
+        const long long c6 = clock64();
+        P.dbg[0] += c1 - c0; P.dbg[1] += c2 - c1; P.dbg[2] += c3 - c2; P.dbg[3] += c4 - c3; P.dbg[4] += c5 - c4;
+        P.dbg[5] += c6 - c5; P.dbg[6] += 1;
+      }
       ++it;
       beta = v22[0] / rz;
       rz = v22[0];
@@ -588,6 +604,7 @@ graph_solve_kernel(SolverDev P) {
     P.summary->iterations = iters;
     P.summary->pcg_iterations = pcg_total;
     P.summary->termination = termination;
+    P.dbg[7] = clock64() - k0;
   }
 }
 
@@ -620,6 +637,8 @@ struct osb_solver {
   double *d_nodevec = nullptr;   // g, D, p, z, res, Ap, delta (7 x 4n) + Hnn, Minv (2 x 16n)
   double *d_cs = nullptr, *d_hs = nullptr, *d_partial = nullptr, *d_out = nullptr;
   osb_solve_summary* d_summary = nullptr;
+  long long* d_dbg = nullptr;
+  int last_grid = 0, last_cluster = 0, last_jsmem = 0;
 };
 
 extern "C" void osb_solve_default_options(osb_solve_options* o) {
@@ -666,6 +685,8 @@ extern "C" osb_status osb_solver_create(osb_solver** out, int max_nodes, int max
   OSB_CUDA(cudaMalloc(&h->d_partial, 2 * 4 * (size_t)num_sms() * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_out, 4 * n * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_summary, sizeof(osb_solve_summary)));
+  OSB_CUDA(cudaMalloc(&h->d_dbg, 8 * sizeof(long long)));
+  OSB_CUDA(cudaMemset(h->d_dbg, 0, 8 * sizeof(long long)));
   *out = h;
   return OSB_OK;
 }
@@ -675,7 +696,7 @@ extern "C" osb_status osb_solver_destroy(osb_solver* h) {
   cudaFree(h->d_fixed); cudaFree(h->d_huber); cudaFree(h->d_type); cudaFree(h->d_ia); cudaFree(h->d_ib);
   cudaFree(h->d_slot_a); cudaFree(h->d_slot_b); cudaFree(h->d_ptr); cudaFree(h->d_payload); cudaFree(h->d_x0);
   cudaFree(h->d_x1); cudaFree(h->d_Jg); cudaFree(h->d_lin); cudaFree(h->d_nodevec); cudaFree(h->d_cs); cudaFree(h->d_hs);
-  cudaFree(h->d_partial); cudaFree(h->d_out); cudaFree(h->d_summary);
+  cudaFree(h->d_partial); cudaFree(h->d_out); cudaFree(h->d_summary); cudaFree(h->d_dbg);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -740,7 +761,7 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
   const size_t N4 = 4 * (size_t)h->max_nodes, N16 = 16 * (size_t)h->max_nodes;
   P.g = nv; P.D = nv + N4; P.p = nv + 2 * N4; P.z = nv + 3 * N4; P.res = nv + 4 * N4; P.Ap = nv + 5 * N4;
   P.delta = nv + 6 * N4; P.Hnn = nv + 7 * N4; P.Minv = nv + 7 * N4 + N16;
-  P.cs = h->d_cs; P.hs = h->d_hs; P.partial = h->d_partial; P.opt = o; P.summary = h->d_summary; P.poses_out = h->d_out;
+  P.cs = h->d_cs; P.hs = h->d_hs; P.partial = h->d_partial; P.opt = o; P.summary = h->d_summary; P.poses_out = h->d_out; P.dbg = h->d_dbg;
 
   // launch shape: ONE thread-block cluster (hardware barrier, ~0.2 us) when the factor list fits 16 CTAs with their
   // Jacobians in shared memory; otherwise a cooperative grid (software grid barrier).
@@ -777,6 +798,7 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
   }
+  h->last_grid = (int)cfg.gridDim.x; h->last_cluster = P.use_cluster; h->last_jsmem = P.j_in_smem;
   OSB_CUDA(cudaEventRecord(h->ev0, st));
   OSB_CUDA(cudaLaunchKernelEx(&cfg, graph_solve_kernel, P));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -788,6 +810,16 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
   OSB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   summary->solve_ms = ms;
   summary->n_residuals = n_res;
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_solver_phase_cycles(osb_solver* h, double* out12) {
+  OSB_REQUIRE(h != nullptr && out12 != nullptr, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  long long c[8];
+  OSB_CUDA(cudaMemcpy(c, h->d_dbg, sizeof(c), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8; ++i) out12[i] = (double)c[i];
+  out12[8] = h->last_grid; out12[9] = h->last_cluster; out12[10] = h->last_jsmem; out12[11] = GS_THREADS;
   return OSB_OK;
 }
 

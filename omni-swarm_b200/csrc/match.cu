@@ -150,7 +150,9 @@ static osb_status launch_scan(const float* db, int64_t n, const int64_t* n_dev, 
 }
 
 int db_scan_grid(int64_t n, int64_t* chunk_out) {
-  int grid = num_sms();
+  // two CTAs (2 x 16 warps) per SM: with 4 rows per warp pass a 10 k-row database is ONE balanced pass for every
+  // warp (ncu, r01: with one CTA per SM the 17th row group of each CTA ran alone while 15 warps sat at the barrier)
+  int grid = 2 * num_sms();
   int64_t chunk = cdiv64(n > 0 ? n : 1, grid);
   if (chunk > DB_CHUNK_MAX) {
     chunk = DB_CHUNK_MAX;

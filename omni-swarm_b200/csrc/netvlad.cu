@@ -6,8 +6,12 @@
 //   1x1 projection to D=128, per-image centring (x - mean over locations), per-location L2 norm | NetVLAD K=32: soft-assign (1x1 conv + softmax),
 //   residual aggregation, intra-normalisation, flatten (K*D = 4096), L2 norm.
 #include "superpoint.cuh"
+#include <stdlib.h>
 
 namespace osb {
+
+constexpr float NV_ACT_SCALE = 16.f;     // ReLU6 activations (<= 6) as split fp16 planes
+constexpr float NV_W_SCALE = 1024.f;
 
 static const int NVB_CIN[7] = {32, 64, 128, 128, 256, 256, 512};
 static const int NVB_COUT[7] = {64, 128, 128, 256, 256, 512, 512};
@@ -135,6 +139,10 @@ osb_status NetVLAD::init(const float* weights, size_t n_weights, int width, int 
   OSB_REQUIRE(width % 16 == 0 && height % 16 == 0 && width > 0 && height > 0, "width/height must be multiples of 16");
   W = width; H = height; max_batch = max_batch_;
   OSB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  {
+    const char* e = getenv("OSB_SP_CONV");      // same debug switch as SuperPoint: ffma = fp32 CUDA-core pointwise convs
+    use_umma = !(e && strcmp(e, "ffma") == 0);
+  }
   const float* p = weights;
   osb_status s;
   {
@@ -156,9 +164,11 @@ osb_status NetVLAD::init(const float* weights, size_t n_weights, int width, int 
     if ((s = upload(&blk[i].dwb, p, ci)) != OSB_OK) return s;
     p += ci;
     if ((s = conv_layer_upload(&blk[i].pw, p, p + (size_t)co * ci, ci, co, 1)) != OSB_OK) return s;
+    if (use_umma && i >= 1 && (s = umma_layer_upload(&upw[i], p, p + (size_t)co * ci, ci, co, 1, NV_W_SCALE)) != OSB_OK) return s;
     p += (size_t)co * ci + co;
   }
   if ((s = conv_layer_upload(&proj, p, p + (size_t)NV_D * 512, 512, NV_D, 1)) != OSB_OK) return s;
+  if (use_umma && (s = umma_layer_upload(&uproj, p, p + (size_t)NV_D * 512, 512, NV_D, 1, NV_W_SCALE)) != OSB_OK) return s;
   p += (size_t)NV_D * 512 + NV_D;
   if ((s = conv_layer_upload(&assign, p, p + (size_t)NV_K * NV_D, NV_D, NV_K, 1)) != OSB_OK) return s;
   p += (size_t)NV_K * NV_D + NV_K;
@@ -181,6 +191,26 @@ osb_status NetVLAD::init(const float* weights, size_t n_weights, int width, int 
   OSB_CUDA(cudaMalloc(&d_mu, B * NV_D * sizeof(float)));
   OSB_CUDA(cudaMalloc(&d_part, B * NV_SLICES * NV_K * NV_D * sizeof(float)));
   OSB_CUDA(cudaMalloc(&d_psum, B * NV_SLICES * NV_K * sizeof(float)));
+  if (use_umma) {
+    // planes of the pointwise inputs: blocks 1..6 (depthwise outputs) and the projection (block 6 output); all share
+    // one buffer sized for the largest (they are live one at a time, except block 6 -> projection: two halves)
+    size_t maxe = 0;
+    int h = H / 2, w = W / 2;
+    int gh[8], gw[8], gc[8];
+    for (int i = 0; i < 7; ++i) {
+      h /= blk[i].stride; w /= blk[i].stride;
+      gh[i] = h; gw[i] = w; gc[i] = blk[i].cin;
+      if (i >= 1) maxe = std::max(maxe, (size_t)B * h * w * blk[i].cin);
+    }
+    gh[7] = h; gw[7] = w; gc[7] = 512;
+    maxe = std::max(maxe, (size_t)B * h * w * 512);
+    OSB_CUDA(cudaMalloc(&planes, 4 * maxe * sizeof(__half)));          // two regions of (hi, lo)
+    for (int i = 1; i < 8; ++i) {
+      __half* base = planes + ((i & 1) ? 0 : 2 * maxe);                 // alternate regions: block 6 (even) vs proj (7, odd)
+      pl_hi[i] = base; pl_lo[i] = base + (size_t)B * gh[i] * gw[i] * gc[i];
+      if ((s = umma_act_maps(&tmA[i], &tmB[i], pl_hi[i], pl_lo[i], (int)B, gh[i], gw[i], gc[i], 1)) != OSB_OK) return s;
+    }
+  }
   return OSB_OK;
 }
 
@@ -189,7 +219,9 @@ void NetVLAD::release() {
   for (int i = 0; i < 7; ++i) { cudaFree(blk[i].dw); cudaFree(blk[i].dwb); conv_layer_free(&blk[i].pw); }
   conv_layer_free(&proj); conv_layer_free(&assign);
   cudaFree(d_img); cudaFree(actA); cudaFree(actB); cudaFree(d_assign); cudaFree(d_out);
-  cudaFree(d_mu); cudaFree(d_part); cudaFree(d_psum);
+  cudaFree(d_mu); cudaFree(d_part); cudaFree(d_psum); cudaFree(planes);
+  for (int i = 0; i < 7; ++i) umma_layer_free(&upw[i]);
+  umma_layer_free(&uproj);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -200,11 +232,27 @@ osb_status NetVLAD::infer_dev(const uint8_t* img_dev, int B, float* out_dev, cud
   int h = H / 2, w = W / 2;
   RUN(conv_first_forward(w0, b0, lut, img_dev, actA, B, H, W, 32, 2, ACT_RELU6, st));
   for (int i = 0; i < 7; ++i) {
-    RUN(dwconv3x3_forward(blk[i].dw, blk[i].dwb, actA, actB, B, h, w, blk[i].cin, blk[i].stride, ACT_RELU6, st));
-    h /= blk[i].stride; w /= blk[i].stride;
-    RUN(conv_forward(blk[i].pw, actB, actA, B, h, w, blk[i].cout, ACT_RELU6, st));
+    if (use_umma && i >= 1) {
+      // depthwise (fp32 -> split planes) then pointwise on the tensor cores (planes -> fp32, or planes for the projection)
+      RUN(umma_dwconv_forward(blk[i].dw, blk[i].dwb, actA, pl_hi[i], pl_lo[i], B, h, w, blk[i].cin, blk[i].stride,
+                              NV_ACT_SCALE, st));
+      h /= blk[i].stride; w /= blk[i].stride;
+      if (i < 6)
+        RUN(umma_conv_forward(upw[i], tmA[i], tmB[i], B, h, w, NV_ACT_SCALE, nullptr, nullptr, actA, blk[i].cout,
+                              blk[i].cout, 1.f, 2, 0, st));
+      else
+        RUN(umma_conv_forward(upw[i], tmA[i], tmB[i], B, h, w, NV_ACT_SCALE, pl_hi[7], pl_lo[7], nullptr, blk[i].cout,
+                              blk[i].cout, NV_ACT_SCALE, 2, 0, st));
+    } else {
+      RUN(dwconv3x3_forward(blk[i].dw, blk[i].dwb, actA, actB, B, h, w, blk[i].cin, blk[i].stride, ACT_RELU6, st));
+      h /= blk[i].stride; w /= blk[i].stride;
+      RUN(conv_forward(blk[i].pw, actB, actA, B, h, w, blk[i].cout, ACT_RELU6, st));
+    }
   }
-  RUN(conv_forward(proj, actA, actB, B, h, w, NV_D, ACT_NONE, st));
+  if (use_umma)
+    RUN(umma_conv_forward(uproj, tmA[7], tmB[7], B, h, w, NV_ACT_SCALE, nullptr, nullptr, actB, NV_D, NV_D, 1.f, 0, 0, st));
+  else
+    RUN(conv_forward(proj, actA, actB, B, h, w, NV_D, ACT_NONE, st));
   const int64_t locs = (int64_t)B * h * w;
   OSB_LAUNCH(nv_colmean_kernel, B, NV_D, 0, st, actB, h * w, d_mu);
   OSB_CHECK_LAUNCH();

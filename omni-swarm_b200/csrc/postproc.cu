@@ -86,6 +86,20 @@ constexpr int KP_THREADS = 1024;
 constexpr int KP_SORT_CAP = 8192;  // survivors sortable in shared memory (64 KB of keys)
 constexpr int KP_RANK_CAP = 4096;  // up to here the order comes from rank counting (no sort); needs 2*CAP key slots
 
+// 9 consecutive state bytes starting at flat address `start` (may be negative / beyond the plane: those read as 0,
+// "not a candidate") through two aligned 64-bit L2 loads
+__device__ __forceinline__ void load_state9(const uint8_t* __restrict__ state, int start, int HW, uint8_t (&out)[9]) {
+  const int a0 = (start >> 3) << 3;                      // floor to a multiple of 8 (arithmetic shift: works below 0)
+  const unsigned long long lo = (a0 >= 0 && a0 + 8 <= HW) ? __ldcg(reinterpret_cast<const unsigned long long*>(state + a0)) : 0ull;
+  const unsigned long long hi = (a0 + 8 >= 0 && a0 + 16 <= HW) ? __ldcg(reinterpret_cast<const unsigned long long*>(state + a0 + 8)) : 0ull;
+  const int sh = start - a0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const int bpos = i + sh;
+    out[i] = (uint8_t)((bpos < 8 ? (lo >> (8 * bpos)) : (hi >> (8 * (bpos - 8)))) & 0xff);
+  }
+}
+
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int inc = v;
@@ -183,19 +197,25 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
       if (__ldcg(state + L) != 1) continue;
       const float c = prob[L];
       bool suppressed = false, pending = false;
-      for (int k = -4; k <= 0 && !suppressed; ++k) {
-        const int jmax = (k == 0) ? -1 : 4;
-        for (int j = -4; j <= jmax; ++j) {
-          const int Ln = L + k * W + j;
-          if (Ln < 0) continue;
-          const uint8_t s = __ldcg(state + Ln);
-          if (s == 0 || s == 3) continue;
+      // the 40 earlier-visited window positions: rows k = -4..-1 (9 wide) and the 4 pixels to the left in row 0;
+      // all five rows' state bytes are fetched up front (10 independent 64-bit loads), confidences only where needed
+      uint8_t st[5][9];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) load_state9(state, L + (k - 4) * W - 4, HW, st[k]);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          if (k == 4 && j >= 4) continue;                 // same row: only the pixels to the left
+          const uint8_t sv = st[k][j];
+          if (sv == 0 || sv == 3) continue;
+          const int Ln = L + (k - 4) * W + (j - 4);
           if (prob[Ln] > c) {
-            if (s == 2) { suppressed = true; break; }
-            pending = true;
+            if (sv == 2) suppressed = true; else pending = true;
           }
         }
       }
+      if (suppressed) pending = false;
       if (suppressed) __stcg(state + L, (uint8_t)3);
       else if (!pending) __stcg(state + L, (uint8_t)2);
       else local_undecided = 1;
@@ -216,11 +236,16 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
     if (__ldcg(state + L) != 2) continue;
     const float c = prob[L];
     bool alive = true;
-    for (int k = 0; k <= 4 && alive; ++k) {
-      for (int j = (k == 0) ? 1 : -4; j <= 4; ++j) {
-        const int Ln = L + k * W + j;
-        if (Ln >= HW) continue;
-        if (__ldcg(state + Ln) == 2 && prob[Ln] > c) { alive = false; break; }
+    uint8_t st[5][9];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) load_state9(state, L + k * W - 4, HW, st[k]);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        if (k == 0 && j <= 4) continue;                   // same row: only the pixels to the right
+        if (st[k][j] != 2) continue;
+        if (prob[L + k * W + (j - 4)] > c) alive = false;
       }
     }
     if (alive) {
@@ -308,7 +333,7 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
 
 osb_status sp_keypoints(const float* semi, int B, int H, int W, float thres, int max_num, KeypointScratch& ks,
                         int32_t* n_kpts, float* kpts, float* conf, cudaStream_t st) {
-  OSB_REQUIRE((H * W) % 4 == 0, "H*W must be a multiple of 4");
+  OSB_REQUIRE((H * W) % 8 == 0, "H*W must be a multiple of 8");
   static bool attr_done = false;
   const size_t smem = (size_t)KP_SORT_CAP * sizeof(unsigned long long);
   if (!attr_done) {

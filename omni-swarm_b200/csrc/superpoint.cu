@@ -94,7 +94,7 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
       __half* base = reinterpret_cast<__half*>(in_buf[i] == 0 ? actA : actB);
       in_hi[i] = base;
       in_lo[i] = base + (size_t)max_batch * h * w * c;
-      osb_status s = umma_act_maps(&tmA[i], &tmB[i], in_hi[i], in_lo[i], max_batch, h, w, c);
+      osb_status s = umma_act_maps(&tmA[i], &tmB[i], in_hi[i], in_lo[i], max_batch, h, w, c, SP_KS[i]);
       if (s != OSB_OK) return s;
     }
   }
@@ -118,6 +118,7 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
 void SuperPoint::release() {
   cudaFree(w1a); cudaFree(b1a); cudaFree(lut); cudaFree(pca_compT); cudaFree(pca_mean_d);
   for (int i = 1; i < 12; ++i) { conv_layer_free(&L[i]); umma_layer_free(&UL[i]); }
+  for (int i = 0; i < 20; ++i) if (lev[i]) cudaEventDestroy(lev[i]);
   cudaFree(d_img); cudaFree(actA); cudaFree(actB); cudaFree(d_logits); cudaFree(d_semi); cudaFree(d_desc);
   cudaFree(ks.state); cudaFree(ks.surv); cudaFree(ks.cand); cudaFree(ks.skey); cudaFree(ks.counts); cudaFree(ks.cnorm);
   cudaFree(d_nk); cudaFree(d_kpts); cudaFree(d_conf); cudaFree(d_out);
@@ -130,6 +131,8 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
   osb_status s;
 #define RUN(x) do { s = (x); if (s != OSB_OK) return s; } while (0)
   const float SA = SP_ACT_SCALE;
+  n_lev = 0;
+  mark(st);
   // conv layer i at resolution h x w; its output (optionally 2x2 max-pooled in the epilogue) becomes the input planes
   // of layer `out_layer`
   auto conv = [&](int i, int h, int w, int out_layer, int pool) {
@@ -137,17 +140,29 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
                              SP_COUT[i], SP_COUT[i], SA, 1, pool, st);
   };
   RUN(umma_first_forward(w1a, b1a, lut, img_dev, in_hi[1], in_lo[1], B, H, W, SA, st));   // conv1a            -> A
+  mark(st);
   RUN(conv(1, H, W, 2, 1));                                                               // conv1b + pool     -> B
+  mark(st);
   RUN(conv(2, H / 2, W / 2, 3, 0));                                                       // conv2a            -> A
+  mark(st);
   RUN(conv(3, H / 2, W / 2, 4, 1));                                                       // conv2b + pool     -> B
+  mark(st);
   RUN(conv(4, H / 4, W / 4, 5, 0));                                                       // conv3a            -> A
+  mark(st);
   RUN(conv(5, H / 4, W / 4, 6, 1));                                                       // conv3b + pool     -> B
+  mark(st);
   RUN(conv(6, Hc, Wc, 7, 0));                                                             // conv4a            -> A
+  mark(st);
   RUN(conv(7, Hc, Wc, 8, 0));                                                             // conv4b            -> B (x)
+  mark(st);
   RUN(conv(8, Hc, Wc, 9, 0));                                                             // convPa            -> A
+  mark(st);
   RUN(umma_conv_forward(UL[9], tmA[9], tmB[9], B, Hc, Wc, SA, nullptr, nullptr, d_logits, 80, 80, 1.f, 0, 0, st));   // convPb
+  mark(st);
   RUN(conv(10, Hc, Wc, 11, 0));                                                           // convDa (reads B)  -> A
+  mark(st);
   RUN(umma_conv_forward(UL[11], tmA[11], tmB[11], B, Hc, Wc, SA, nullptr, nullptr, d_desc, 256, 256, 1.f, 0, 0, st)); // convDb
+  mark(st);
   RUN(l2norm_cells(d_desc, (int64_t)B * Hc * Wc, 256, st));
   RUN(sp_softmax_shuffle(d_logits, 80, d_semi, B, Hc, Wc, st));
 #undef RUN
@@ -267,6 +282,27 @@ extern "C" osb_status osb_superpoint_postprocess(osb_superpoint* h, const float*
   s = sp.postprocess(batch, sp.d_nk, sp.d_kpts, sp.d_conf, sp.d_out, st);
   if (s != OSB_OK) return s;
   return sp_copy_out(sp, batch, n_kpts, kpts, desc, st);
+}
+
+extern "C" osb_status osb_superpoint_set_profiling(osb_superpoint* h, int enable) {
+  OSB_REQUIRE(h != nullptr, "null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->sp.layer_prof = enable != 0;
+  h->sp.n_lev = 0;
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_superpoint_layer_ms(osb_superpoint* h, float* ms, int n) {
+  OSB_REQUIRE(h != nullptr && ms != nullptr && n >= 12, "need room for 12 layer times");
+  std::lock_guard<std::mutex> lk(h->mu);
+  SuperPoint& sp = h->sp;
+  OSB_CUDA(cudaStreamSynchronize(sp.stream));
+  for (int i = 0; i < n; ++i) ms[i] = 0.f;
+  for (int i = 0; i + 1 < sp.n_lev && i < n; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, sp.lev[i], sp.lev[i + 1]) == cudaSuccess) ms[i] = t; else cudaGetLastError();
+  }
+  return OSB_OK;
 }
 
 extern "C" osb_status osb_superpoint_read(osb_superpoint* h, int what, int image, float* out, size_t n_floats) {

@@ -28,6 +28,11 @@ struct SuperPoint {
   UmmaLayer UL[12];
   CUtensorMap tmA[12], tmB[12];     // [layer] -> (hi, lo) descriptors of that layer's INPUT planes
   __half *in_hi[12] = {}, *in_lo[12] = {};
+  // per-layer timing (debug / bench): ev[i] is recorded after launch i of the network when `layer_prof` is set
+  bool layer_prof = false;
+  cudaEvent_t lev[20] = {};
+  int n_lev = 0;
+  void mark(cudaStream_t st) { if (layer_prof && n_lev < 20) { if (!lev[n_lev]) cudaEventCreate(&lev[n_lev]); cudaEventRecord(lev[n_lev++], st); } }
 
   osb_status init(const float* weights, size_t n_weights, int width, int height, float thres, int max_num,
                   const float* pca_comp, const float* pca_mean, int max_batch);
@@ -48,6 +53,12 @@ struct NetVLAD {
   uint8_t* d_img = nullptr;
   float *actA = nullptr, *actB = nullptr, *d_assign = nullptr, *d_out = nullptr;
   float *d_mu = nullptr, *d_part = nullptr, *d_psum = nullptr;
+  // tensor-core pointwise path: blocks 1..6 and the projection read split fp16 planes written by the depthwise kernel
+  bool use_umma = true;
+  UmmaLayer upw[7], uproj;
+  CUtensorMap tmA[8], tmB[8];           // [block] (7 = projection) descriptors of the pointwise conv's input planes
+  __half *pl_hi[8] = {}, *pl_lo[8] = {};
+  __half* planes = nullptr;
 
   osb_status init(const float* weights, size_t n_weights, int width, int height, int max_batch);
   void release();

@@ -70,6 +70,18 @@ class SuperPoint:
                                                       _l.ptr(k), _l.ptr(d)))
         return [(k[b, :n[b]].copy(), d[b, :n[b]].copy()) for b in range(B)]
 
+    LAYERS = ["conv1a", "conv1b+pool", "conv2a", "conv2b+pool", "conv3a", "conv3b+pool", "conv4a", "conv4b", "convPa",
+              "convPb", "convDa", "convDb"]
+
+    def layer_ms(self, images: np.ndarray) -> dict:
+        """device time of every network layer for one batch (tensor-core path)."""
+        _l.check(self._lib.osb_superpoint_set_profiling(self._h, 1))
+        self.inference_batch(images)
+        ms = np.zeros(12, np.float32)
+        _l.check(self._lib.osb_superpoint_layer_ms(self._h, _l.ptr(ms), 12))
+        _l.check(self._lib.osb_superpoint_set_profiling(self._h, 0))
+        return {k: float(v) for k, v in zip(self.LAYERS, ms)}
+
     def read(self, what: str, image: int = 0) -> np.ndarray:
         H, W = self.height, self.width
         shapes = {"semi": (0, (H, W)), "desc": (1, (256, H // 8, W // 8)), "conf": (2, (self.max_num,)),
@@ -215,6 +227,13 @@ class PoseGraphSolver:
                                             _l.ptr(ftype), _l.ptr(ia), _l.ptr(ib), _l.ptr(payload), _l.ptr(huber),
                                             C.byref(opt), C.byref(summ)))
         return poses, summ
+
+    def phase_cycles(self) -> dict:
+        c = np.zeros(12, np.float64)
+        _l.check(self._lib.osb_solver_phase_cycles(self._h, _l.ptr(c)))
+        names = ["factor", "barrier", "node1", "reduce1", "node2", "reduce2", "cg_iterations", "kernel", "ctas",
+                 "cluster", "j_in_smem", "threads"]
+        return dict(zip(names, c.tolist()))
 
     def linearize(self, g: dict, poses: np.ndarray):
         _, ftype, ia, ib, payload, _ = self._arrays(g)

@@ -77,6 +77,8 @@ _SIG = {
     "osb_superpoint_infer_dev": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
     "osb_superpoint_postprocess": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P]),
     "osb_superpoint_read": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_size_t]),
+    "osb_superpoint_set_profiling": (C.c_int, [_P, C.c_int]),
+    "osb_superpoint_layer_ms": (C.c_int, [_P, _P, C.c_int]),
     "osb_netvlad_create": (C.c_int, [C.POINTER(_P), _P, C.c_size_t, C.c_int, C.c_int, C.c_int]),
     "osb_netvlad_destroy": (C.c_int, [_P]),
     "osb_netvlad_infer": (C.c_int, [_P, _P, C.c_int, _P]),
@@ -97,6 +99,7 @@ _SIG = {
     "osb_solver_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
     "osb_solver_destroy": (C.c_int, [_P]),
     "osb_solver_solve": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]),
+    "osb_solver_phase_cycles": (C.c_int, [_P, _P]),
     "osb_solver_linearize": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "osb_frontend_create": (C.c_int, [C.POINTER(_P), C.POINTER(FrontendConfig), _P, C.c_size_t, _P, _P, _P, C.c_size_t]),
     "osb_frontend_destroy": (C.c_int, [_P]),
