@@ -85,13 +85,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // The weights of each tap stream through their own ring.
 constexpr int UM_A_SLOT = (UM_TH + 2) * UM_TW * 128;   // 20 KB per plane: 10 rows x 16 px x 128 B
 constexpr int UM_A_SLOTS = 2;
-template <int N>
+// RES = true (64 -> 64 channel 3x3 layers: conv1b, conv2a, conv2b = 65 % of the network's FLOPs): the 9 taps' weight
+// planes (144 KB) stay resident in shared memory for the CTA's whole life instead of streaming through a ring, which
+// removes more than half of the remaining L2 -> shared-memory traffic.
+template <int N, bool RES>
 struct UmmaCfg {
   static constexpr int B_BYTES = N * 128;                        // one weight plane of one tap / slab
   static constexpr int B_SLOT = 2 * B_BYTES;                     // hi + lo
-  static constexpr int B_SLOTS = (N <= 64) ? 6 : (N <= 80) ? 5 : (N <= 128) ? 4 : 2;
+  static constexpr int B_SLOTS = RES ? 9 : (N <= 64) ? 6 : (N <= 80) ? 5 : (N <= 128) ? 4 : 2;
   static constexpr int A_RING = UM_A_SLOTS * 2 * UM_A_SLOT;      // 80 KB
-  static constexpr int TMEM_COLS = (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
+  // two fp32 accumulators per tile (see the precision note in the kernel): 2N TMEM columns per buffer
+  static constexpr int NBUF = (4 * N <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = (2 * N * NBUF <= 128) ? 128 : (2 * N * NBUF <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = A_RING + B_SLOTS * B_SLOT + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
@@ -112,12 +117,12 @@ struct UmmaArgs {
   int pool;                // 1: fused 2x2 max-pool, the planes written are [B][H/2][W/2][C]
 };
 
-template <int N>
+template <int N, bool RES>
 __global__ void __launch_bounds__(256, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, UmmaArgs P) {
-  using Cfg = UmmaCfg<N>;
-  constexpr int AS = UM_A_SLOTS, BS = Cfg::B_SLOTS;
+  using Cfg = UmmaCfg<N, RES>;
+  constexpr int AS = UM_A_SLOTS, BS = Cfg::B_SLOTS, NBUF = Cfg::NBUF;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + Cfg::A_RING;
@@ -140,6 +145,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     for (int s = 0; s < AS; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    // (with NBUF == 1 only index 0 is used; with RES the b_full barriers are filled once and b_empty stays unused)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -156,6 +162,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     // ===================== TMA producer =====================
     int as = 0; uint32_t aph = 0;
     int bs = 0; uint32_t bph = 0;
+    if (RES) {
+      // all 9 taps (one 64-channel slab) once: slot t holds tap t
+      for (int t = 0; t < 9; ++t) {
+        const uint32_t sb = b_base + t * Cfg::B_SLOT;
+        mbar_expect_tx(b_full(t), Cfg::B_SLOT);
+        tma_load_3d(sb, &tm_w_hi, b_full(t), 0, P.n_off, t);
+        tma_load_3d(sb + Cfg::B_BYTES, &tm_w_lo, b_full(t), 0, P.n_off, t);
+      }
+    }
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
       const int x0 = tx * UM_TW, y0 = ty * UM_TH;
@@ -168,7 +183,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           tma_load_4d(sa, &tm_a_hi, a_full(as), cs * UM_KC, x0 + kx - halo, y0 - halo, b);
           tma_load_4d(sa + UM_A_SLOT, &tm_a_lo, a_full(as), cs * UM_KC, x0 + kx - halo, y0 - halo, b);
           if (++as == AS) { as = 0; aph ^= 1; }
-          for (int ky = 0; ky < P.ks; ++ky) {
+          for (int ky = 0; ky < P.ks && !RES; ++ky) {
             mbar_wait(b_empty(bs), bph ^ 1);
             const uint32_t sb = b_base + bs * Cfg::B_SLOT;
             mbar_expect_tx(b_full(bs), Cfg::B_SLOT);
@@ -184,13 +199,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = f16 (0), K-major both,
     // N >> 3 at bit 17, M >> 4 at bit 24
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // Precision: the tensor core TRUNCATES its fp32 accumulator after every MMA (measured: ~1e-5 relative per layer when
+    // all three products of the split share one accumulator).  The exact-in-fp32 hi*hi products therefore go to a MAIN
+    // accumulator (one truncation per K=16 step) and the two small cross products lo*hi, hi*lo to a second, CROSS
+    // accumulator whose magnitude -- and truncation error -- is 2^-11 of the main one; the epilogue adds them in fp32.
     int as = 0; uint32_t aph = 0;
     int bs = 0; uint32_t bph = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    if (RES)
+      for (int t = 0; t < 9; ++t) mbar_wait(b_full(t), 0);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+      const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * N);
+      const uint32_t d_cross = d_main + (uint32_t)N;
       uint32_t first = 1;
       for (int kx = 0; kx < P.ks; ++kx) {
         for (int cs = 0; cs < P.cin_slabs; ++cs) {
@@ -198,9 +220,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           tc_fence_after();
           const uint32_t sa = smem_base + as * (2 * UM_A_SLOT);
           for (int ky = 0; ky < P.ks; ++ky) {
-            mbar_wait(b_full(bs), bph);
-            tc_fence_after();
-            const uint32_t sb = b_base + bs * Cfg::B_SLOT;
+            uint32_t sb;
+            if (RES) {
+              sb = b_base + (ky * 3 + kx) * Cfg::B_SLOT;
+            } else {
+              mbar_wait(b_full(bs), bph);
+              tc_fence_after();
+              sb = b_base + bs * Cfg::B_SLOT;
+            }
             // vertical tap ky reads the box from tile row ky on: + ky * 16 px * 128 B = ky * 2048 B (2 swizzle atoms)
             const uint64_t a_hi = umma_desc_sw128(sa + ky * (UM_TW * 128));
             const uint64_t a_lo = umma_desc_sw128(sa + UM_A_SLOT + ky * (UM_TW * 128));
@@ -208,20 +235,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 #pragma unroll
             for (int k = 0; k < UM_KC / 16; ++k) {
               const uint64_t adv = (uint64_t)(k * 32 >> 4);     // advance 16 fp16 = 32 bytes inside the swizzle row
-              umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
-              umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-              umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              const uint32_t accum = (first && k == 0) ? 0u : 1u;
+              umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, accum);
+              umma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, accum);
+              umma_f16(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
             }
             first = 0;
-            umma_commit(b_empty(bs));                            // weight slot free when these MMAs retire
-            if (++bs == BS) { bs = 0; bph ^= 1; }
+            if (!RES) {
+              umma_commit(b_empty(bs));                          // weight slot free when these MMAs retire
+              if (++bs == BS) { bs = 0; bph ^= 1; }
+            }
           }
           umma_commit(a_empty(as));                              // activation box free after its last vertical tap
           if (++as == AS) { as = 0; aph ^= 1; }
         }
       }
-      umma_commit(tfull_bar(acc));                               // accumulator complete -> epilogue
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      umma_commit(tfull_bar(acc));                               // accumulators complete -> epilogue
+      if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -236,7 +266,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       const size_t pix = ((size_t)b * P.H + y) * P.W + x;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * N);
       // fused 2x2 max-pool: the warp owns tile rows 2q, 2q+1 (lane = (row & 1) * 16 + col); the pooled pixel of
       // (even row, even col) is the max over lanes l, l+1, l+16, l+17 -> two shuffle steps, writer lanes l < 16, l even
       const int py = ty * (UM_TH / 2) + q, px = tx * (UM_TW / 2) + (lane >> 1);
@@ -244,13 +274,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       const size_t ppix = ((size_t)b * (P.H >> 1) + py) * (P.W >> 1) + px;
 #pragma unroll 1
       for (int n0 = 0; n0 < N; n0 += 16) {
-        uint32_t v[16];
+        uint32_t v[16], vc[16];
         tmem_ld16(t_row + n0, v);
+        tmem_ld16(t_row + N + n0, vc);
         if (n0 >= P.out_c) continue;                               // warp-uniform
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float a = fmaf(__uint_as_float(v[i]), P.inv_scale, __ldg(P.bias + P.n_off + n0 + i));
+          float a = fmaf(__uint_as_float(v[i]) + __uint_as_float(vc[i]), P.inv_scale, __ldg(P.bias + P.n_off + n0 + i));
           if (P.relu) a = fmaxf(a, 0.f);
           if (P.relu == 2) a = fminf(a, 6.f);
           f[i] = a;
@@ -289,7 +320,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));              // 4 epilogue warps -> count 4
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();
@@ -501,18 +532,18 @@ osb_status umma_act_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half*
   return make_tmap(lo, p_lo, 4, dims, strides, box);
 }
 
-template <int N>
+template <int N, bool RES>
 static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const UmmaLayer& L, const UmmaArgs& P,
                               cudaStream_t st) {
-  using Cfg = UmmaCfg<N>;
+  using Cfg = UmmaCfg<N, RES>;
   static bool attr_done = false;
   if (!attr_done) {
-    OSB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    OSB_CUDA(cudaFuncSetAttribute((conv_umma_kernel<N, RES>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
   const int tiles = P.B * cdiv(P.W, UM_TW) * cdiv(P.H, UM_TH);
   const int grid = std::min(tiles, num_sms());
-  OSB_LAUNCH((conv_umma_kernel<N>), grid, 256, Cfg::SMEM_BYTES, st, a_hi, a_lo, L.tm_hi, L.tm_lo, P);
+  OSB_LAUNCH((conv_umma_kernel<N, RES>), grid, 256, Cfg::SMEM_BYTES, st, a_hi, a_lo, L.tm_hi, L.tm_lo, P);
   OSB_CHECK_LAUNCH();
   return OSB_OK;
 }
@@ -530,16 +561,18 @@ osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const 
   OSB_REQUIRE(out_c % 16 == 0 && out_c <= L.n_pad && out_cstride % 8 == 0, "tcgen05 conv: bad output channel layout");
   P.n_off = 0;
   switch (L.n_pad) {
-    case 64: return launch_umma<64>(a_hi, a_lo, L, P, st);
-    case 80: return launch_umma<80>(a_hi, a_lo, L, P, st);
-    case 128: return launch_umma<128>(a_hi, a_lo, L, P, st);
-    case 256: return launch_umma<256>(a_hi, a_lo, L, P, st);
+    case 64:
+      if (L.ks == 3 && L.cin == UM_KC) return launch_umma<64, true>(a_hi, a_lo, L, P, st);   // weights resident
+      return launch_umma<64, false>(a_hi, a_lo, L, P, st);
+    case 80: return launch_umma<80, false>(a_hi, a_lo, L, P, st);
+    case 128: return launch_umma<128, false>(a_hi, a_lo, L, P, st);
+    case 256: return launch_umma<256, false>(a_hi, a_lo, L, P, st);
     case 512: {                                   // two N = 256 passes over the same activations
       P.out_c = 256;
-      osb_status s = launch_umma<256>(a_hi, a_lo, L, P, st);
+      osb_status s = launch_umma<256, false>(a_hi, a_lo, L, P, st);
       if (s != OSB_OK) return s;
       P.n_off = 256;
-      return launch_umma<256>(a_hi, a_lo, L, P, st);
+      return launch_umma<256, false>(a_hi, a_lo, L, P, st);
     }
   }
   set_error("umma_conv_forward", "unsupported N");

@@ -377,6 +377,17 @@ graph_solve_kernel(SolverDev P) {
   const double initial_cost = cost;
   bool need_gradient = true;
   const int f0 = blockIdx.x * P.fpc, f1 = min(P.m, f0 + P.fpc);
+  // static per-thread data of the fast CG path
+  const bool fast = (P.fpc <= 2 * GS_THREADS) && (P.n <= T);
+  int fa[2] = {0, 0}, fb[2] = {0, 0}, fsa[2] = {0, 0}, fsb[2] = {0, 0};
+  bool fvalid[2] = {false, false};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int f = f0 + threadIdx.x + k * GS_THREADS;
+    if (fast && f < f1) { fvalid[k] = true; fa[k] = P.ia[f]; fb[k] = P.ib[f]; fsa[k] = P.slot_a[f]; fsb[k] = P.slot_b[f]; }
+  }
+  const bool is_node = fast && gtid < P.n && !P.fixed[gtid];
+  const int ns0 = is_node ? P.node_ptr[gtid] : 0, ns1 = is_node ? P.node_ptr[gtid + 1] : 0;
 
   while (iters < P.opt.max_iterations) {
     if (need_gradient) {
@@ -412,30 +423,36 @@ graph_solve_kernel(SolverDev P) {
     }
 
     // ---- PCG init (node phase): Minv, res = -g, z = Minv res, p = 0, delta = 0 ----
+    // Fast path (every node has its own thread, <= 2 factors per thread): the node's Minv, D, res, z, p, delta stay in
+    // REGISTERS for the whole CG solve and the factor's indices are preloaded, so a CG iteration touches global memory
+    // only for what crosses threads: z/p gathers by the factor threads and the contribution slots.
     const double lam = 1.0 / radius;
     double v2[2] = {0.0, 0.0};
+    double Mi[16], Dn[4], rn[4] = {0.0, 0.0, 0.0, 0.0}, zn[4] = {0.0, 0.0, 0.0, 0.0}, pn[4] = {0.0, 0.0, 0.0, 0.0};
+    double dn[4] = {0.0, 0.0, 0.0, 0.0};
     for (int n = gtid; n < P.n; n += T) {
-      double rn[4] = {0.0, 0.0, 0.0, 0.0}, zn[4] = {0.0, 0.0, 0.0, 0.0};
+      double rl[4] = {0.0, 0.0, 0.0, 0.0}, zl[4] = {0.0, 0.0, 0.0, 0.0};
       if (!P.fixed[n]) {
-        double M[16], Mi[16];
+        double M[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) M[i] = P.Hnn[16 * n + i];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) M[i * 5] += lam * P.D[4 * n + i];
+        for (int i = 0; i < 4; ++i) { Dn[i] = P.D[4 * n + i]; M[i * 5] += lam * Dn[i]; }
         inv4(M, Mi);
 #pragma unroll
         for (int i = 0; i < 16; ++i) P.Minv[16 * n + i] = Mi[i];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rn[i] = -P.g[4 * n + i];
+        for (int i = 0; i < 4; ++i) rl[i] = -P.g[4 * n + i];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) zn[i] += Mi[i * 4 + j] * rn[j];
+          for (int j = 0; j < 4; ++j) zl[i] += Mi[i * 4 + j] * rl[j];
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        P.res[4 * n + i] = rn[i]; __stcg(P.z + 4 * n + i, zn[i]); __stcg(P.p + 4 * n + i, 0.0); P.delta[4 * n + i] = 0.0;
-        v2[0] += rn[i] * zn[i]; v2[1] += rn[i] * rn[i];
+        P.res[4 * n + i] = rl[i]; __stcg(P.z + 4 * n + i, zl[i]); __stcg(P.p + 4 * n + i, 0.0); P.delta[4 * n + i] = 0.0;
+        v2[0] += rl[i] * zl[i]; v2[1] += rl[i] * rl[i];
+        rn[i] = rl[i]; zn[i] = zl[i];                       // (fast path: the only iteration of this loop)
       }
     }
     grid_reduce_sum<2>(v2, P, parity, sh, grid); parity ^= 1;
@@ -447,6 +464,43 @@ graph_solve_kernel(SolverDev P) {
     while (it < P.opt.max_pcg_iterations && rr0 > 0.0) {
       long long c0 = clock64();
       // factor phase: p_a = z_a + beta p_a (on the fly), t = Ja p_a + Jb p_b, contributions Ja^T t, Jb^T t
+      if (fast) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (!fvalid[k]) continue;
+          const int li = threadIdx.x + k * GS_THREADS;
+          const double2 za0 = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fa[k]));
+          const double2 za1 = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fa[k] + 2));
+          const double2 pa0 = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fa[k]));
+          const double2 pa1 = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fa[k] + 2));
+          const double2 zb0 = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fb[k]));
+          const double2 zb1 = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fb[k] + 2));
+          const double2 pb0 = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fb[k]));
+          const double2 pb1 = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fb[k] + 2));
+          const double pa[4] = {za0.x + beta * pa0.x, za0.y + beta * pa0.y, za1.x + beta * pa1.x, za1.y + beta * pa1.y};
+          const double pb[4] = {zb0.x + beta * pb0.x, zb0.y + beta * pb0.y, zb1.x + beta * pb1.x, zb1.y + beta * pb1.y};
+          double t[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc += J.at(i * 4 + j, li) * pa[j] + J.at(16 + i * 4 + j, li) * pb[j];
+            t[i] = acc;
+          }
+          double ca[4], cb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double sa = 0.0, sb = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sa += J.at(i * 4 + j, li) * t[i]; sb += J.at(16 + i * 4 + j, li) * t[i]; }
+            ca[j] = sa; cb[j] = sb;
+          }
+          __stcg(reinterpret_cast<double2*>(P.cs + 4 * (size_t)fsa[k]), make_double2(ca[0], ca[1]));
+          __stcg(reinterpret_cast<double2*>(P.cs + 4 * (size_t)fsa[k] + 2), make_double2(ca[2], ca[3]));
+          __stcg(reinterpret_cast<double2*>(P.cs + 4 * (size_t)fsb[k]), make_double2(cb[0], cb[1]));
+          __stcg(reinterpret_cast<double2*>(P.cs + 4 * (size_t)fsb[k] + 2), make_double2(cb[2], cb[3]));
+        }
+      } else {
       for (int f = f0 + threadIdx.x; f < f1; f += GS_THREADS) {
         const int li = f - f0;
         const int a = P.ia[f], b = P.ib[f];
@@ -456,15 +510,12 @@ graph_solve_kernel(SolverDev P) {
           pa[i] = __ldcg(P.z + 4 * a + i) + beta * __ldcg(P.p + 4 * a + i);
           pb[i] = __ldcg(P.z + 4 * b + i) + beta * __ldcg(P.p + 4 * b + i);
         }
-        double Jl[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) Jl[i] = J.at(i, li);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          double s = 0.0;
+          double acc = 0.0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) s += Jl[i * 4 + j] * pa[j] + Jl[16 + i * 4 + j] * pb[j];
-          t[i] = s;
+          for (int j = 0; j < 4; ++j) acc += J.at(i * 4 + j, li) * pa[j] + J.at(16 + i * 4 + j, li) * pb[j];
+          t[i] = acc;
         }
         double* ca = P.cs + 4 * (size_t)P.slot_a[f];
         double* cb = P.cs + 4 * (size_t)P.slot_b[f];
@@ -472,22 +523,46 @@ graph_solve_kernel(SolverDev P) {
         for (int j = 0; j < 4; ++j) {
           double sa = 0.0, sb = 0.0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { sa += Jl[i * 4 + j] * t[i]; sb += Jl[16 + i * 4 + j] * t[i]; }
+          for (int i = 0; i < 4; ++i) { sa += J.at(i * 4 + j, li) * t[i]; sb += J.at(16 + i * 4 + j, li) * t[i]; }
           __stcg(ca + j, sa); __stcg(cb + j, sb);
         }
+      }
       }
       long long c1 = clock64();
       all_sync(P, grid);
       long long c2 = clock64();
-      // node phase 1: p = z + beta p (stored), Ap = sum of the node's slots + lam D p, partial p.Ap
+      // node phase 1: p = z + beta p, Ap = sum of the node's slots + lam D p, partial p.Ap
       double v1b[1] = {0.0};
+      double apn[4] = {0.0, 0.0, 0.0, 0.0};
+      if (fast) {
+        if (is_node) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { pn[i] = zn[i] + beta * pn[i]; apn[i] = lam * Dn[i] * pn[i]; }
+          __stcg(reinterpret_cast<double2*>(P.p + 4 * gtid), make_double2(pn[0], pn[1]));
+          __stcg(reinterpret_cast<double2*>(P.p + 4 * gtid + 2), make_double2(pn[2], pn[3]));
+          for (int s0 = ns0; s0 < ns1; s0 += 8) {          // 16 independent 16-byte loads in flight per batch
+            double2 c[8][2];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int si = min(s0 + k, ns1 - 1);
+              c[k][0] = __ldcg(reinterpret_cast<const double2*>(P.cs + 4 * (size_t)si));
+              c[k][1] = __ldcg(reinterpret_cast<const double2*>(P.cs + 4 * (size_t)si + 2));
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (s0 + k < ns1) { apn[0] += c[k][0].x; apn[1] += c[k][0].y; apn[2] += c[k][1].x; apn[3] += c[k][1].y; }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v1b[0] += pn[i] * apn[i];
+        }
+      } else {
       for (int n = gtid; n < P.n; n += T) {
         if (P.fixed[n]) continue;
-        double pn[4], ap[4];
+        double pl[4], ap[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          pn[i] = P.z[4 * n + i] + beta * P.p[4 * n + i];
-          ap[i] = lam * P.D[4 * n + i] * pn[i];
+          pl[i] = P.z[4 * n + i] + beta * P.p[4 * n + i];
+          ap[i] = lam * P.D[4 * n + i] * pl[i];
         }
         const int s0 = P.node_ptr[n], s1 = P.node_ptr[n + 1];
 #pragma unroll 4
@@ -496,7 +571,8 @@ graph_solve_kernel(SolverDev P) {
           for (int i = 0; i < 4; ++i) ap[i] += __ldcg(P.cs + 4 * (size_t)sidx + i);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { __stcg(P.p + 4 * n + i, pn[i]); P.Ap[4 * n + i] = ap[i]; v1b[0] += pn[i] * ap[i]; }
+        for (int i = 0; i < 4; ++i) { __stcg(P.p + 4 * n + i, pl[i]); P.Ap[4 * n + i] = ap[i]; v1b[0] += pl[i] * ap[i]; }
+      }
       }
       long long c3 = clock64();
       grid_reduce_sum<1>(v1b, P, parity, sh, grid); parity ^= 1;
@@ -506,23 +582,41 @@ graph_solve_kernel(SolverDev P) {
       const double alpha = rz / pAp;
       // node phase 2: delta += alpha p, res -= alpha Ap, z = Minv res; partial rz_new, rr
       double v22[2] = {0.0, 0.0};
+      if (fast) {
+        if (is_node) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { dn[i] += alpha * pn[i]; rn[i] -= alpha * apn[i]; }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc += Mi[i * 4 + j] * rn[j];
+            zn[i] = acc;
+          }
+          __stcg(reinterpret_cast<double2*>(P.z + 4 * gtid), make_double2(zn[0], zn[1]));
+          __stcg(reinterpret_cast<double2*>(P.z + 4 * gtid + 2), make_double2(zn[2], zn[3]));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { v22[0] += rn[i] * zn[i]; v22[1] += rn[i] * rn[i]; }
+        }
+      } else {
       for (int n = gtid; n < P.n; n += T) {
         if (P.fixed[n]) continue;
-        double rn[4], zn[4] = {0.0, 0.0, 0.0, 0.0};
+        double rl[4], zl[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           P.delta[4 * n + i] += alpha * P.p[4 * n + i];
-          rn[i] = P.res[4 * n + i] - alpha * P.Ap[4 * n + i];
+          rl[i] = P.res[4 * n + i] - alpha * P.Ap[4 * n + i];
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) zn[i] += P.Minv[16 * n + i * 4 + j] * rn[j];
+          for (int j = 0; j < 4; ++j) zl[i] += P.Minv[16 * n + i * 4 + j] * rl[j];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          P.res[4 * n + i] = rn[i]; __stcg(P.z + 4 * n + i, zn[i]);
-          v22[0] += rn[i] * zn[i]; v22[1] += rn[i] * rn[i];
+          P.res[4 * n + i] = rl[i]; __stcg(P.z + 4 * n + i, zl[i]);
+          v22[0] += rl[i] * zl[i]; v22[1] += rl[i] * rl[i];
         }
+      }
       }
       long long c5 = clock64();
       grid_reduce_sum<2>(v22, P, parity, sh, grid); parity ^= 1;
@@ -535,6 +629,10 @@ graph_solve_kernel(SolverDev P) {
       beta = v22[0] / rz;
       rz = v22[0];
       if (v22[1] <= P.opt.pcg_tolerance * P.opt.pcg_tolerance * rr0) break;
+    }
+    if (fast && is_node) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) P.delta[4 * gtid + i] = dn[i];
     }
     pcg_total += it;
     ++iters;
