@@ -378,6 +378,7 @@ def run_ours(args):
     sp_prof.layer_ms(imgs8)
     runs = [sp_prof.layer_ms(imgs8) for _ in range(5)]
     layer_ms = {k: float(np.median([r[k] for r in runs])) for k in runs[0]}
+    kp_counts = dict(zip(["candidates", "survivors", "nms_rounds"], sp_prof.read("counts")[:3].tolist()))
     sp_prof.close()
     layer_tflops = {k: (2 * GMAC[k] * 2 * N_DIRS / v if v > 0 else None) for k, v in layer_ms.items()}
     conv_ms = stages["superpoint_net"]
@@ -402,7 +403,7 @@ def run_ours(args):
                 "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)"}
     roofline_stack = {"what": "whole SuperPoint conv stack (12 launches + 2 head epilogues)", "achieved": conv_tflops,
                       "unit": "TFLOP/s", "frac": conv_tflops / pk["bf16_tflops_sustained"], "ms": conv_ms,
-                      "layer_ms": layer_ms, "layer_tflops": layer_tflops}
+                      "layer_ms": layer_ms, "layer_tflops": layer_tflops, "keypoint_counts_image0": kp_counts}
     roofline_match = {"kernel": "db_scan_kernel<1,4>", "bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm_gbs"],
                       "unit": "GB/s", "frac": scan_gbs / pk["hbm_gbs"],
                       "traffic": (traffic or {}).get("db_scan_dram_bytes_per_launch"),

@@ -285,7 +285,8 @@ osb_status osb_frontend_db_load(osb_frontend* h, int remote, int64_t n, const fl
                                 const float* local_desc, const int32_t* n_kpts);
 /* stage timing (CUDA events on the caller's stream, recorded only while enabled).  After a synchronising call
  * (process / finish) stage_ms returns the device time of the LAST extract+ingest+query sequence:
- * [0] SuperPoint network  [1] keypoints + descriptors  [2] NetVLAD  [3] stereo match + record pack
+ * [0] SuperPoint network  [1] keypoints + descriptors (NetVLAD runs concurrently on a second stream)
+ * [2] NetVLAD remainder not hidden behind [1]  [3] stereo match + record pack
  * [4] add_to_database  [5] database scans (remote + local)  [6] acceptance rule + per-direction match  [7] unused */
 osb_status osb_frontend_set_profiling(osb_frontend* h, int enable);
 osb_status osb_frontend_stage_ms(osb_frontend* h, float* ms8);

@@ -25,7 +25,8 @@ namespace cg = cooperative_groups;
 
 namespace osb {
 
-constexpr int GS_THREADS = 512;
+constexpr int GS_THREADS = 256;           // 255 registers per thread: the CG fast path keeps ~50 doubles live per thread
+constexpr int GS_KF = 3;                  // factors per thread on the fast path (16 CTAs x 256 threads x 3 >= 12 288 factors)
 constexpr int GS_MAX_CLUSTER = 16;
 constexpr int GS_SMEM_J_MAX = 200 * 1024;   // bytes of shared memory a CTA may spend on its Jacobian block
 constexpr double kPi = 3.14159265358979323846;
@@ -378,11 +379,12 @@ graph_solve_kernel(SolverDev P) {
   bool need_gradient = true;
   const int f0 = blockIdx.x * P.fpc, f1 = min(P.m, f0 + P.fpc);
   // static per-thread data of the fast CG path
-  const bool fast = (P.fpc <= 2 * GS_THREADS) && (P.n <= T);
-  int fa[2] = {0, 0}, fb[2] = {0, 0}, fsa[2] = {0, 0}, fsb[2] = {0, 0};
-  bool fvalid[2] = {false, false};
+  const bool fast = (P.fpc <= GS_KF * GS_THREADS) && (P.n <= T);
+  int fa[GS_KF], fb[GS_KF], fsa[GS_KF], fsb[GS_KF];
+  bool fvalid[GS_KF];
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < GS_KF; ++k) {
+    fvalid[k] = false; fa[k] = fb[k] = fsa[k] = fsb[k] = 0;
     const int f = f0 + threadIdx.x + k * GS_THREADS;
     if (fast && f < f1) { fvalid[k] = true; fa[k] = P.ia[f]; fb[k] = P.ib[f]; fsa[k] = P.slot_a[f]; fsb[k] = P.slot_b[f]; }
   }
@@ -465,20 +467,27 @@ graph_solve_kernel(SolverDev P) {
       long long c0 = clock64();
       // factor phase: p_a = z_a + beta p_a (on the fly), t = Ja p_a + Jb p_b, contributions Ja^T t, Jb^T t
       if (fast) {
+        // all gathers of this thread's (up to 3) factors are issued before any arithmetic: one L2 round trip
+        double2 zq[GS_KF][4], pq[GS_KF][4];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < GS_KF; ++k) {
+          zq[k][0] = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fa[k]));
+          zq[k][1] = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fa[k] + 2));
+          zq[k][2] = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fb[k]));
+          zq[k][3] = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fb[k] + 2));
+          pq[k][0] = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fa[k]));
+          pq[k][1] = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fa[k] + 2));
+          pq[k][2] = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fb[k]));
+          pq[k][3] = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fb[k] + 2));
+        }
+#pragma unroll
+        for (int k = 0; k < GS_KF; ++k) {
           if (!fvalid[k]) continue;
           const int li = threadIdx.x + k * GS_THREADS;
-          const double2 za0 = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fa[k]));
-          const double2 za1 = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fa[k] + 2));
-          const double2 pa0 = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fa[k]));
-          const double2 pa1 = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fa[k] + 2));
-          const double2 zb0 = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fb[k]));
-          const double2 zb1 = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fb[k] + 2));
-          const double2 pb0 = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fb[k]));
-          const double2 pb1 = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fb[k] + 2));
-          const double pa[4] = {za0.x + beta * pa0.x, za0.y + beta * pa0.y, za1.x + beta * pa1.x, za1.y + beta * pa1.y};
-          const double pb[4] = {zb0.x + beta * pb0.x, zb0.y + beta * pb0.y, zb1.x + beta * pb1.x, zb1.y + beta * pb1.y};
+          const double pa[4] = {zq[k][0].x + beta * pq[k][0].x, zq[k][0].y + beta * pq[k][0].y,
+                                zq[k][1].x + beta * pq[k][1].x, zq[k][1].y + beta * pq[k][1].y};
+          const double pb[4] = {zq[k][2].x + beta * pq[k][2].x, zq[k][2].y + beta * pq[k][2].y,
+                                zq[k][3].x + beta * pq[k][3].x, zq[k][3].y + beta * pq[k][3].y};
           double t[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {

@@ -264,6 +264,8 @@ struct osb_frontend {
   osb_keyframe_record* d_record = nullptr;   // used by process()
   osb_loop_result* d_result = nullptr;
   // stage profiling: ev[i] marks the START of stage i, ev[8] the end of the last one
+  cudaStream_t stream2 = nullptr;                 // NetVLAD runs here, overlapped with the keypoint kernels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool profiling = false;
   cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid[9] = {false, false, false, false, false, false, false, false, false};
@@ -319,6 +321,9 @@ extern "C" osb_status osb_frontend_create(osb_frontend** out, const osb_frontend
 #define FE_TRY(x) do { s = (x); if (s != OSB_OK) { osb_frontend_destroy(h); return s; } } while (0)
 #define FE_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error("osb_frontend_create", cudaGetErrorString(e_)); osb_frontend_destroy(h); return OSB_ERR_CUDA; } } while (0)
   FE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  FE_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  FE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  FE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   FE_TRY(h->sp.init(sp_weights, n_sp_weights, cfg->width, cfg->height, cfg->sp_thres, mn, pca_comp, pca_mean, 2 * nd));
   FE_TRY(h->nv.init(nv_weights, n_nv_weights, cfg->width, cfg->height, nd));
   FE_TRY(dbstore_alloc(h->db[0], cfg->db_capacity, mn));
@@ -366,6 +371,9 @@ extern "C" osb_status osb_frontend_destroy(osb_frontend* h) {
   cudaFree(h->d_q_dist); cudaFree(h->d_dist_scratch); cudaFree(h->d_q_nq); cudaFree(h->d_q_nt); cudaFree(h->d_assign);
   cudaFree(h->d_record); cudaFree(h->d_result);
   for (int i = 0; i < 9; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return OSB_OK;
@@ -384,10 +392,16 @@ static osb_status fe_extract_dev(osb_frontend* h, const uint8_t* img_dev /*[2*nd
   if ((s = h->sp.network(img_dev, 2 * nd, st)) != OSB_OK) return s;
   h->sp.last_batch = 2 * nd;
   fe_mark(h, 1, st);
+  // fork: the keypoint / descriptor kernels run one CTA per image (8 CTAs); NetVLAD (independent of SuperPoint, it only
+  // reads the images) fills the other 140 SMs from a second stream and joins before the record is packed.
+  OSB_CUDA(cudaEventRecord(h->ev_fork, st));
+  OSB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+  // NetVLAD on the up images writes straight into the record (image_desc, loop_cam.cpp:553-556)
+  if ((s = h->nv.infer_dev(img_dev, nd, &record_dev->global_desc[0][0], h->stream2)) != OSB_OK) return s;
+  OSB_CUDA(cudaEventRecord(h->ev_join, h->stream2));
   if ((s = h->sp.postprocess(2 * nd, h->sp.d_nk, h->sp.d_kpts, h->sp.d_conf, h->sp.d_out, st)) != OSB_OK) return s;
   fe_mark(h, 2, st);
-  // NetVLAD on the up images writes straight into the record (image_desc, loop_cam.cpp:553-556)
-  if ((s = h->nv.infer_dev(img_dev, nd, &record_dev->global_desc[0][0], st)) != OSB_OK) return s;
+  OSB_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));      // join (stage 2 = the part of NetVLAD that was not hidden)
   fe_mark(h, 3, st);
   // stereo match up[d] <-> down[d] (loop_cam.cpp:388)
   if ((s = bf_match_device(nd, mn, mn, h->d_st_q, h->sp.d_nk, h->d_st_t, h->sp.d_nk + nd, h->d_dist_scratch,

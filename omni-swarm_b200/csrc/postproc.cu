@@ -150,7 +150,8 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
   const int seg = ((HW / 4 + 31) / 32) * 4;          // pixels per warp, multiple of 4
   const int wp0 = warp * seg, wp1 = min(HW, wp0 + seg);
   int wcount = 0;
-  for (int p = wp0 + lane * 4; p < wp1; p += 128) {
+#pragma unroll 8
+  for (int p = wp0 + lane * 4; p < wp1; p += 128) {      // 8 independent 16-byte loads in flight per lane
     const float4 v = *reinterpret_cast<const float4*>(prob + p);
     wcount += (v.x > thres) + (v.y > thres) + (v.z > thres) + (v.w > thres);
   }
@@ -160,29 +161,37 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
   // (only lane 0 contributed, so the exclusive prefix seen by lane 0 of warp w is the sum of earlier warps)
   int base = __shfl_sync(0xffffffffu, wbase, 0);
   const int M = s_total;
-  for (int p0 = wp0; p0 < wp1; p0 += 128) {
-    const int p = p0 + lane * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p < wp1) v = *reinterpret_cast<const float4*>(prob + p);
-    const int f0 = (p < wp1) && (v.x > thres), f1 = (p < wp1) && (v.y > thres);
-    const int f2 = (p < wp1) && (v.z > thres), f3 = (p < wp1) && (v.w > thres);
-    const int cnt = f0 + f1 + f2 + f3;
-    int inc = cnt;
+  for (int q0 = wp0; q0 < wp1; q0 += 4 * 128) {           // batches of 4 rows of 128 pixels: loads first, scans after
+    float4 vv[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int n = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += n;
+    for (int u = 0; u < 4; ++u) {
+      const int p = q0 + u * 128 + lane * 4;
+      vv[u] = (p < wp1) ? *reinterpret_cast<const float4*>(prob + p) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (p < wp1) {
-      int o = base + inc - cnt;
-      if (f0) cand[o++] = p;
-      if (f1) cand[o++] = p + 1;
-      if (f2) cand[o++] = p + 2;
-      if (f3) cand[o++] = p + 3;
-      *reinterpret_cast<uchar4*>(state + p) = make_uchar4(f0, f1, f2, f3);
-      *reinterpret_cast<uchar4*>(surv + p) = make_uchar4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = q0 + u * 128 + lane * 4;
+      const float4 v = vv[u];
+      const int f0 = (p < wp1) && (v.x > thres), f1 = (p < wp1) && (v.y > thres);
+      const int f2 = (p < wp1) && (v.z > thres), f3 = (p < wp1) && (v.w > thres);
+      const int cnt = f0 + f1 + f2 + f3;
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      if (p < wp1) {
+        int o = base + inc - cnt;
+        if (f0) cand[o++] = p;
+        if (f1) cand[o++] = p + 1;
+        if (f2) cand[o++] = p + 2;
+        if (f3) cand[o++] = p + 3;
+        *reinterpret_cast<uchar4*>(state + p) = make_uchar4(f0, f1, f2, f3);
+        *reinterpret_cast<uchar4*>(surv + p) = make_uchar4(0, 0, 0, 0);
+      }
+      base += __shfl_sync(0xffffffffu, inc, 31);
     }
-    base += __shfl_sync(0xffffffffu, inc, 31);
   }
   __syncthreads();
 
