@@ -378,7 +378,8 @@ def run_ours(args):
     sp_prof.layer_ms(imgs8)
     runs = [sp_prof.layer_ms(imgs8) for _ in range(5)]
     layer_ms = {k: float(np.median([r[k] for r in runs])) for k in runs[0]}
-    kp_counts = dict(zip(["candidates", "survivors", "nms_rounds"], sp_prof.read("counts")[:3].tolist()))
+    _c = sp_prof.read("counts").tolist()
+    kp_counts = {"candidates": _c[0], "survivors": _c[1], "nms_rounds": _c[2], "phase_cycles": _c[4:8]}
     sp_prof.close()
     layer_tflops = {k: (2 * GMAC[k] * 2 * N_DIRS / v if v > 0 else None) for k, v in layer_ms.items()}
     conv_ms = stages["superpoint_net"]

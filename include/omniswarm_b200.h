@@ -75,7 +75,8 @@ osb_status osb_superpoint_infer_dev(osb_superpoint* h, const uint8_t* images_dev
  *  set_heatmap: upload a caller-supplied `semi` [batch][H][W] and `desc` [batch][256][H/8][W/8] (the two engine
  *               outputs, superpoint_tensorrt.cpp:139-140) and run ONLY getKeyPoints+NMS2+computeDescriptors.
  *  read:        copy an intermediate of the last infer() back: what = 0 semi [H][W], 1 desc [256][H/8][W/8],
- *               2 confidences of the returned keypoints [max_num], 3 NMS survivor plane as float [H][W]. */
+ *               2 confidences of the returned keypoints [max_num], 3 NMS survivor plane as float [H][W],
+ *               4 keypoint kernel counters [8]: candidates, survivors, NMS rounds, 0, SM cycles of its 4 phases. */
 osb_status osb_superpoint_postprocess(osb_superpoint* h, const float* semi, const float* desc_nchw, int batch,
                                       int32_t* n_kpts, float* kpts, float* desc);
 osb_status osb_superpoint_read(osb_superpoint* h, int what, int image, float* out, size_t n_floats);

@@ -549,16 +549,16 @@ graph_solve_kernel(SolverDev P) {
           for (int i = 0; i < 4; ++i) { pn[i] = zn[i] + beta * pn[i]; apn[i] = lam * Dn[i] * pn[i]; }
           __stcg(reinterpret_cast<double2*>(P.p + 4 * gtid), make_double2(pn[0], pn[1]));
           __stcg(reinterpret_cast<double2*>(P.p + 4 * gtid + 2), make_double2(pn[2], pn[3]));
-          for (int s0 = ns0; s0 < ns1; s0 += 8) {          // 16 independent 16-byte loads in flight per batch
-            double2 c[8][2];
+          for (int s0 = ns0; s0 < ns1; s0 += 16) {         // 32 independent 16-byte loads in flight per batch: one L2
+            double2 c[16][2];                              // round trip covers every node of degree <= 16
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 16; ++k) {
               const int si = min(s0 + k, ns1 - 1);
               c[k][0] = __ldcg(reinterpret_cast<const double2*>(P.cs + 4 * (size_t)si));
               c[k][1] = __ldcg(reinterpret_cast<const double2*>(P.cs + 4 * (size_t)si + 2));
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < 16; ++k)
               if (s0 + k < ns1) { apn[0] += c[k][0].x; apn[1] += c[k][0].y; apn[2] += c[k][1].x; apn[3] += c[k][1].y; }
           }
 #pragma unroll

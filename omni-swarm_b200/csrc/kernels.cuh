@@ -52,7 +52,7 @@ struct KeypointScratch {   // per handle, sized for max_batch images
   uint8_t* surv = nullptr;      // [B][H*W]
   int32_t* cand = nullptr;      // [B][H*W]
   unsigned long long* skey = nullptr;  // [B][H*W]
-  int32_t* counts = nullptr;    // [B][4]: M candidates, S survivors, rounds, reserved
+  int32_t* counts = nullptr;    // [B][8]: M candidates, S survivors, rounds, reserved, SM cycles of phases 1..4
   float* cnorm = nullptr;       // [B][256]
 };
 osb_status sp_keypoints(const float* semi, int B, int H, int W, float thres, int max_num, KeypointScratch& ks,

@@ -388,17 +388,19 @@ static osb_status fe_extract_dev(osb_frontend* h, const uint8_t* img_dev /*[2*nd
     OSB_LAUNCH(fe_blank_kernel, 256, 256, 0, st, const_cast<uint8_t*>(img_dev), c.height, c.width, 2 * nd);
     OSB_CHECK_LAUNCH();
   }
-  fe_mark(h, 0, st);
-  if ((s = h->sp.network(img_dev, 2 * nd, st)) != OSB_OK) return s;
-  h->sp.last_batch = 2 * nd;
-  fe_mark(h, 1, st);
-  // fork: the keypoint / descriptor kernels run one CTA per image (8 CTAs); NetVLAD (independent of SuperPoint, it only
-  // reads the images) fills the other 140 SMs from a second stream and joins before the record is packed.
+  // fork: NetVLAD is independent of SuperPoint (it only reads the images).  It runs on a second stream for the whole
+  // SuperPoint phase: its element-wise / depthwise kernels co-reside with the persistent convolution CTAs, its
+  // tensor-core launches fill the wave tails, and while the keypoint kernels run (one CTA per image) it owns the
+  // other 140 SMs.  It joins before the record is packed.
   OSB_CUDA(cudaEventRecord(h->ev_fork, st));
   OSB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
   // NetVLAD on the up images writes straight into the record (image_desc, loop_cam.cpp:553-556)
   if ((s = h->nv.infer_dev(img_dev, nd, &record_dev->global_desc[0][0], h->stream2)) != OSB_OK) return s;
   OSB_CUDA(cudaEventRecord(h->ev_join, h->stream2));
+  fe_mark(h, 0, st);
+  if ((s = h->sp.network(img_dev, 2 * nd, st)) != OSB_OK) return s;
+  h->sp.last_batch = 2 * nd;
+  fe_mark(h, 1, st);
   if ((s = h->sp.postprocess(2 * nd, h->sp.d_nk, h->sp.d_kpts, h->sp.d_conf, h->sp.d_out, st)) != OSB_OK) return s;
   fe_mark(h, 2, st);
   OSB_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));      // join (stage 2 = the part of NetVLAD that was not hidden)

@@ -67,7 +67,7 @@ __global__ void nv_center_norm_kernel(float* __restrict__ x, const float* __rest
   v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
   float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   s = warp_sum(s);
-  const float n = sqrtf(s);
+  const float n = fmaxf(sqrtf(s), 1e-12f);       // eps as in F.normalize: a blank image centres to exactly zero
   v.x /= n; v.y /= n; v.z /= n; v.w /= n;
   reinterpret_cast<float4*>(x + (size_t)loc * NV_D)[lane] = v;
 }
@@ -114,7 +114,7 @@ nv_vlad_final_kernel(const float* __restrict__ part, const float* __restrict__ p
   acc.x -= asum * c.x; acc.y -= asum * c.y; acc.z -= asum * c.z; acc.w -= asum * c.w;
   float s = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
   s = warp_sum(s);
-  const float n = sqrtf(s);
+  const float n = fmaxf(sqrtf(s), 1e-12f);
   acc.x /= n; acc.y /= n; acc.z /= n; acc.w /= n;                  // intra-normalisation
   float t = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
   t = warp_sum(t);
@@ -122,7 +122,7 @@ nv_vlad_final_kernel(const float* __restrict__ part, const float* __restrict__ p
   __syncthreads();
   float tot = red[lane];
   tot = warp_sum(tot);
-  const float g = sqrtf(tot);
+  const float g = fmaxf(sqrtf(tot), 1e-12f);
   acc.x /= g; acc.y /= g; acc.z /= g; acc.w /= g;
   reinterpret_cast<float4*>(out + (size_t)b * NV_K * NV_D + (size_t)k * NV_D)[lane] = acc;
 }

@@ -143,6 +143,7 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
   int32_t* cand = cand_ + (size_t)b * HW;
   unsigned long long* skey = skey_ + (size_t)b * HW;
 
+  const long long t_start = clock64();
   // ---- phase 1: ordered compaction.  Warp w owns the contiguous pixel range [w*seg, (w+1)*seg): pass A counts its
   // candidates, one block scan turns the 32 warp totals into offsets, pass B rescans and writes cand[] in raster
   // order with a shuffle scan per 128-pixel row of lanes (no block barrier inside the loops).
@@ -195,6 +196,7 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
   }
   __syncthreads();
 
+  const long long t_p1 = clock64();
   // ---- phase 2: resolve ACTIVE by dependency order ----
   int rounds = 0;
   while (true) {
@@ -237,6 +239,7 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
     if (!u) break;
   }
 
+  const long long t_p2 = clock64();
   // ---- phase 3: survivors ----
   if (tid == 0) s_nsurv = 0;
   __syncthreads();
@@ -267,6 +270,7 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
   const int S = s_nsurv;
   const int n_out = min(S, max_num);
 
+  const long long t_p3 = clock64();
   // ---- phase 4: order by (conf desc, raster asc), keep the first max_num ----
   if (S <= KP_RANK_CAP) {
     // rank counting over the keys in shared memory: the key's rank IS its output slot (keys are unique)
@@ -336,7 +340,10 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
   }
   if (tid == 0) {
     n_kpts[b] = n_out;
-    counts[b * 4 + 0] = M; counts[b * 4 + 1] = S; counts[b * 4 + 2] = rounds; counts[b * 4 + 3] = 0;
+    const long long t_end = clock64();
+    counts[b * 8 + 0] = M; counts[b * 8 + 1] = S; counts[b * 8 + 2] = rounds; counts[b * 8 + 3] = 0;
+    counts[b * 8 + 4] = (int)(t_p1 - t_start); counts[b * 8 + 5] = (int)(t_p2 - t_p1);   // SM cycles per phase
+    counts[b * 8 + 6] = (int)(t_p3 - t_p2); counts[b * 8 + 7] = (int)(t_end - t_p3);
   }
 }
 

@@ -104,7 +104,7 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
   OSB_CUDA(cudaMalloc(&ks.surv, B * HW));
   OSB_CUDA(cudaMalloc(&ks.cand, B * HW * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&ks.skey, B * HW * sizeof(unsigned long long)));
-  OSB_CUDA(cudaMalloc(&ks.counts, B * 4 * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&ks.counts, B * 8 * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&ks.cnorm, B * 256 * sizeof(float)));
   OSB_CUDA(cudaMalloc(&d_nk, B * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&d_kpts, B * max_num * 2 * sizeof(float)));
@@ -332,11 +332,11 @@ extern "C" osb_status osb_superpoint_read(osb_superpoint* h, int what, int image
     for (size_t i = 0; i < HW; ++i) out[i] = (float)tmp[i];
     return OSB_OK;
   } else if (what == 4) {
-    OSB_REQUIRE(n_floats == 4, "counts needs 4 floats");
-    int32_t c[4];
-    OSB_CUDA(cudaMemcpyAsync(c, sp.ks.counts + image * 4, sizeof(c), cudaMemcpyDeviceToHost, st));
+    OSB_REQUIRE(n_floats == 8, "counts needs 8 floats");
+    int32_t c[8];
+    OSB_CUDA(cudaMemcpyAsync(c, sp.ks.counts + image * 8, sizeof(c), cudaMemcpyDeviceToHost, st));
     OSB_CUDA(cudaStreamSynchronize(st));
-    for (int i = 0; i < 4; ++i) out[i] = (float)c[i];
+    for (int i = 0; i < 8; ++i) out[i] = (float)c[i];
     return OSB_OK;
   } else {
     set_error("osb_superpoint_read", "unknown `what`");

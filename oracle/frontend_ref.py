@@ -182,15 +182,15 @@ def netvlad_net(img_u8: np.ndarray, w: dict) -> np.ndarray:
             x = relu6(F.conv2d(x, t[f"b{i}.pw.weight"], t[f"b{i}.pw.bias"]))
         x = F.conv2d(x, t["proj.weight"], t["proj.bias"])            # [1,D,h,w]
         x = x - x.mean(dim=(2, 3), keepdim=True)                      # per-image centring (makes random-weight
-        x = x / torch.norm(x, dim=1, keepdim=True)                    # descriptors image-specific); per-location L2
+        x = x / torch.clamp(torch.norm(x, dim=1, keepdim=True), min=1e-12)   # descriptors image-specific); per-location L2
         a = torch.softmax(F.conv2d(x, t["assign.weight"], t["assign.bias"]), 1)   # [1,K,h,w]
         D, K = x.shape[1], a.shape[1]
         xf = x.reshape(D, -1)                                         # [D,P]
         af = a.reshape(K, -1)                                         # [K,P]
         vlad = af @ xf.t() - af.sum(1, keepdim=True) * t["centroids"]  # [K,D]
-        vlad = vlad / torch.norm(vlad, dim=1, keepdim=True)           # intra-normalisation
+        vlad = vlad / torch.clamp(torch.norm(vlad, dim=1, keepdim=True), min=1e-12)   # intra-normalisation
         v = vlad.reshape(-1)
-        v = v / torch.norm(v)
+        v = v / torch.clamp(torch.norm(v), min=1e-12)              # (eps as F.normalize: blank images give 0, not NaN)
     return v.numpy().copy()
 
 
