@@ -52,6 +52,8 @@ struct KeypointScratch {   // per handle, sized for max_batch images
   uint8_t* surv = nullptr;      // [B][H*W]
   int32_t* cand = nullptr;      // [B][H*W]
   unsigned long long* skey = nullptr;  // [B][H*W]
+  unsigned long long* cmask = nullptr; // [B][2][H*W] earlier / later stronger-neighbour bit masks per candidate
+  bool write_surv = true;              // maintain the survivor plane (parity hook `read(3)`); off in the front-end
   int32_t* counts = nullptr;    // [B][8]: M candidates, S survivors, rounds, reserved, SM cycles of phases 1..4
   float* cnorm = nullptr;       // [B][256]
 };

@@ -325,6 +325,7 @@ extern "C" osb_status osb_frontend_create(osb_frontend** out, const osb_frontend
   FE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   FE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   FE_TRY(h->sp.init(sp_weights, n_sp_weights, cfg->width, cfg->height, cfg->sp_thres, mn, pca_comp, pca_mean, 2 * nd));
+  h->sp.ks.write_surv = false;       // the survivor plane is only a parity hook of the standalone SuperPoint handle
   FE_TRY(h->nv.init(nv_weights, n_nv_weights, cfg->width, cfg->height, nd));
   FE_TRY(dbstore_alloc(h->db[0], cfg->db_capacity, mn));
   FE_TRY(dbstore_alloc(h->db[1], cfg->db_capacity, mn));

@@ -84,7 +84,7 @@ osb_status l2norm_cells(float* x, int64_t cells, int C, cudaStream_t st) {
 // -------------------------------------------------------------------------------------------------------------
 constexpr int KP_THREADS = 1024;
 constexpr int KP_SORT_CAP = 8192;  // survivors sortable in shared memory (64 KB of keys)
-constexpr int KP_RANK_CAP = 4096;  // up to here the order comes from rank counting (no sort); needs 2*CAP key slots
+constexpr int KP_RANK_CAP = 128;   // tiny survivor sets: rank counting (no barriers); otherwise bitonic sort in smem
 
 // 9 consecutive state bytes starting at flat address `start` (may be negative / beyond the plane: those read as 0,
 // "not a candidate") through two aligned 64-bit L2 loads
@@ -98,6 +98,25 @@ __device__ __forceinline__ void load_state9(const uint8_t* __restrict__ state, i
     const int bpos = i + sh;
     out[i] = (uint8_t)((bpos < 8 ? (lo >> (8 * bpos)) : (hi >> (8 * (bpos - 8)))) & 0xff);
   }
+}
+
+// the same 9-byte window kept packed: bytes 0..7 in `w`, byte 8 in `b8` (no per-byte arrays -> no local memory)
+__device__ __forceinline__ void load_state9p(const uint8_t* __restrict__ state, int start, int HW, unsigned long long& w,
+                                             unsigned& b8) {
+  const int a0 = (start >> 3) << 3;
+  const unsigned long long lo = (a0 >= 0 && a0 + 8 <= HW) ? __ldcg(reinterpret_cast<const unsigned long long*>(state + a0)) : 0ull;
+  const unsigned long long hi = (a0 + 8 >= 0 && a0 + 16 <= HW) ? __ldcg(reinterpret_cast<const unsigned long long*>(state + a0 + 8)) : 0ull;
+  const int sh = 8 * (start - a0);
+  w = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+  b8 = (unsigned)((hi >> sh) & 0xffull);
+}
+// 9-bit mask of the window positions whose state byte equals `val`
+__device__ __forceinline__ unsigned window_eq(unsigned long long w, unsigned b8, unsigned val) {
+  unsigned m = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m |= (unsigned)(((w >> (8 * j)) & 0xffull) == val) << j;
+  m |= (unsigned)(b8 == val) << 8;
+  return m;
 }
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
@@ -130,7 +149,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
 __global__ void __launch_bounds__(KP_THREADS)
 sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, int max_num, uint8_t* __restrict__ state_,
                     uint8_t* __restrict__ surv_, int32_t* __restrict__ cand_, unsigned long long* __restrict__ skey_,
-                    int32_t* __restrict__ counts, int32_t* __restrict__ n_kpts, float* __restrict__ kpts,
+                    unsigned long long* __restrict__ cmask_, int write_surv, int32_t* __restrict__ counts, int32_t* __restrict__ n_kpts, float* __restrict__ kpts,
                     float* __restrict__ conf) {
   extern __shared__ __align__(16) unsigned long long skeys[];  // KP_SORT_CAP keys
   __shared__ int warp_sums[32];
@@ -142,6 +161,7 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
   uint8_t* surv = surv_ + (size_t)b * HW;
   int32_t* cand = cand_ + (size_t)b * HW;
   unsigned long long* skey = skey_ + (size_t)b * HW;
+  unsigned long long* cmask = cmask_ + (size_t)b * 2 * HW;
 
   const long long t_start = clock64();
   // ---- phase 1: ordered compaction.  Warp w owns the contiguous pixel range [w*seg, (w+1)*seg): pass A counts its
@@ -151,10 +171,16 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
   const int seg = ((HW / 4 + 31) / 32) * 4;          // pixels per warp, multiple of 4
   const int wp0 = warp * seg, wp1 = min(HW, wp0 + seg);
   int wcount = 0;
-#pragma unroll 8
-  for (int p = wp0 + lane * 4; p < wp1; p += 128) {      // 8 independent 16-byte loads in flight per lane
-    const float4 v = *reinterpret_cast<const float4*>(prob + p);
-    wcount += (v.x > thres) + (v.y > thres) + (v.z > thres) + (v.w > thres);
+  for (int q0 = wp0; q0 < wp1; q0 += 8 * 128) {           // 8 guarded, independent 16-byte loads in flight per lane
+    float4 vv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int p = q0 + u * 128 + lane * 4;
+      vv[u] = (p < wp1) ? *reinterpret_cast<const float4*>(prob + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      wcount += (vv[u].x > thres) + (vv[u].y > thres) + (vv[u].z > thres) + (vv[u].w > thres);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wcount += __shfl_xor_sync(0xffffffffu, wcount, o);
@@ -189,7 +215,7 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
         if (f2) cand[o++] = p + 2;
         if (f3) cand[o++] = p + 3;
         *reinterpret_cast<uchar4*>(state + p) = make_uchar4(f0, f1, f2, f3);
-        *reinterpret_cast<uchar4*>(surv + p) = make_uchar4(0, 0, 0, 0);
+        if (write_surv) *reinterpret_cast<uchar4*>(surv + p) = make_uchar4(0, 0, 0, 0);
       }
       base += __shfl_sync(0xffffffffu, inc, 31);
     }
@@ -197,6 +223,33 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
   __syncthreads();
 
   const long long t_p1 = clock64();
+  // ---- phase 2a: per candidate, WHICH of the 40 earlier-visited / 40 later-visited window positions hold a candidate
+  // with strictly larger confidence (bit q = row*9 + col of the 5x9 window).  Confidences are compared once, here;
+  // the fixpoint rounds below then only look at state bytes.
+  for (int i = tid; i < M; i += KP_THREADS) {
+    const int L = cand[i];
+    const float c = prob[L];
+    unsigned long long we[5], wl[5];
+    unsigned be[5], bl[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      load_state9p(state, L + (k - 4) * W - 4, HW, we[k], be[k]);
+      load_state9p(state, L + k * W - 4, HW, wl[k], bl[k]);
+    }
+    unsigned long long me = 0ull, ml = 0ull;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      // candidate positions (state != 0) of the row, restricted to the earlier / later half of the window
+      unsigned ce = 0x1ffu & ~window_eq(we[k], be[k], 0u), cl = 0x1ffu & ~window_eq(wl[k], bl[k], 0u);
+      if (k == 4) ce &= 0x00fu;                       // row of L itself: only the 4 pixels to the left are earlier
+      if (k == 0) cl &= 0x1e0u;                       // ... and only the 4 pixels to the right are later
+      while (ce) { const int j = __ffs(ce) - 1; ce &= ce - 1; if (prob[L + (k - 4) * W + (j - 4)] > c) me |= 1ull << (k * 9 + j); }
+      while (cl) { const int j = __ffs(cl) - 1; cl &= cl - 1; if (prob[L + k * W + (j - 4)] > c) ml |= 1ull << (k * 9 + j); }
+    }
+    cmask[i] = me;
+    cmask[HW + i] = ml;
+  }
+  __syncthreads();
   // ---- phase 2: resolve ACTIVE by dependency order ----
   int rounds = 0;
   while (true) {
@@ -206,29 +259,17 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
     for (int i = tid; i < M; i += KP_THREADS) {
       const int L = cand[i];
       if (__ldcg(state + L) != 1) continue;
-      const float c = prob[L];
-      bool suppressed = false, pending = false;
-      // the 40 earlier-visited window positions: rows k = -4..-1 (9 wide) and the 4 pixels to the left in row 0;
-      // all five rows' state bytes are fetched up front (10 independent 64-bit loads), confidences only where needed
-      uint8_t st[5][9];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) load_state9(state, L + (k - 4) * W - 4, HW, st[k]);
+      const unsigned long long me = cmask[i];
+      unsigned long long act = 0ull, und = 0ull;             // positions whose candidate is ACTIVE / still undecided
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-#pragma unroll
-        for (int j = 0; j < 9; ++j) {
-          if (k == 4 && j >= 4) continue;                 // same row: only the pixels to the left
-          const uint8_t sv = st[k][j];
-          if (sv == 0 || sv == 3) continue;
-          const int Ln = L + (k - 4) * W + (j - 4);
-          if (prob[Ln] > c) {
-            if (sv == 2) suppressed = true; else pending = true;
-          }
-        }
+        unsigned long long w; unsigned b8;
+        load_state9p(state, L + (k - 4) * W - 4, HW, w, b8);
+        act |= (unsigned long long)window_eq(w, b8, 2u) << (k * 9);
+        und |= (unsigned long long)window_eq(w, b8, 1u) << (k * 9);
       }
-      if (suppressed) pending = false;
-      if (suppressed) __stcg(state + L, (uint8_t)3);
-      else if (!pending) __stcg(state + L, (uint8_t)2);
+      if (me & act) __stcg(state + L, (uint8_t)3);           // an earlier, stronger, active neighbour zeroed it
+      else if (!(me & und)) __stcg(state + L, (uint8_t)2);   // every earlier stronger neighbour is decided inactive
       else local_undecided = 1;
     }
     if (local_undecided) atomicOr(&s_undecided, 1);
@@ -246,24 +287,18 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
   for (int i = tid; i < M; i += KP_THREADS) {
     const int L = cand[i];
     if (__ldcg(state + L) != 2) continue;
-    const float c = prob[L];
-    bool alive = true;
-    uint8_t st[5][9];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) load_state9(state, L + k * W - 4, HW, st[k]);
+    const unsigned long long ml = cmask[HW + i];
+    unsigned long long act = 0ull;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        if (k == 0 && j <= 4) continue;                   // same row: only the pixels to the right
-        if (st[k][j] != 2) continue;
-        if (prob[L + k * W + (j - 4)] > c) alive = false;
-      }
+      unsigned long long w; unsigned b8;
+      load_state9p(state, L + k * W - 4, HW, w, b8);
+      act |= (unsigned long long)window_eq(w, b8, 2u) << (k * 9);
     }
-    if (alive) {
-      surv[L] = 1;
+    if (!(ml & act)) {                                       // no later, stronger, active neighbour overwrote its 2
+      if (write_surv) surv[L] = 1;
       const int pos = atomicAdd(&s_nsurv, 1);
-      skey[pos] = ((unsigned long long)(~__float_as_uint(c)) << 32) | (unsigned)L;
+      skey[pos] = ((unsigned long long)(~__float_as_uint(prob[L])) << 32) | (unsigned)L;
     }
   }
   __syncthreads();
@@ -357,7 +392,7 @@ osb_status sp_keypoints(const float* semi, int B, int H, int W, float thres, int
     attr_done = true;
   }
   OSB_LAUNCH(sp_keypoints_kernel, B, KP_THREADS, smem, st, semi, H, W, thres, max_num, ks.state, ks.surv, ks.cand,
-             ks.skey, ks.counts, n_kpts, kpts, conf);
+             ks.skey, ks.cmask, ks.write_surv ? 1 : 0, ks.counts, n_kpts, kpts, conf);
   OSB_CHECK_LAUNCH();
   return OSB_OK;
 }

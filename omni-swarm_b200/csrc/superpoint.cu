@@ -104,6 +104,7 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
   OSB_CUDA(cudaMalloc(&ks.surv, B * HW));
   OSB_CUDA(cudaMalloc(&ks.cand, B * HW * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&ks.skey, B * HW * sizeof(unsigned long long)));
+  OSB_CUDA(cudaMalloc(&ks.cmask, B * 2 * HW * sizeof(unsigned long long)));
   OSB_CUDA(cudaMalloc(&ks.counts, B * 8 * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&ks.cnorm, B * 256 * sizeof(float)));
   OSB_CUDA(cudaMalloc(&d_nk, B * sizeof(int32_t)));
@@ -120,7 +121,7 @@ void SuperPoint::release() {
   for (int i = 1; i < 12; ++i) { conv_layer_free(&L[i]); umma_layer_free(&UL[i]); }
   for (int i = 0; i < 20; ++i) if (lev[i]) cudaEventDestroy(lev[i]);
   cudaFree(d_img); cudaFree(actA); cudaFree(actB); cudaFree(d_logits); cudaFree(d_semi); cudaFree(d_desc);
-  cudaFree(ks.state); cudaFree(ks.surv); cudaFree(ks.cand); cudaFree(ks.skey); cudaFree(ks.counts); cudaFree(ks.cnorm);
+  cudaFree(ks.state); cudaFree(ks.surv); cudaFree(ks.cand); cudaFree(ks.skey); cudaFree(ks.cmask); cudaFree(ks.counts); cudaFree(ks.cnorm);
   cudaFree(d_nk); cudaFree(d_kpts); cudaFree(d_conf); cudaFree(d_out);
   if (stream) cudaStreamDestroy(stream);
 }

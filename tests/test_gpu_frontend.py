@@ -119,3 +119,22 @@ def test_query_rule_device_vs_oracle(gpu):
         assert abs(res.hit_score - rdist) < 1e-4
         assert res.accepted == int(rid != -1 and rdist > -1)
     fe.close()
+
+
+def test_blank_keyframe_adds_nothing(gpu):
+    """Empty input (no keypoints anywhere): landmark_num == 0 for every direction, so add_to_database adds no row
+    (loop_detector.cpp:153), the query is skipped (:262) and nothing is NaN."""
+    fe = make_frontend(match_index_dist=5)
+    z = np.zeros((4, H0, W0), np.uint8)
+    rec, res = fe.process(z, z, msg_id=1)
+    assert list(rec.n_kpts) == [0, 0, 0, 0] and list(rec.n_kpts_down) == [0, 0, 0, 0]
+    assert fe.db_size(False) == 0 and fe.db_size(True) == 0
+    assert res.accepted == 0 and res.hit_id == -1 and list(res.n_matches) == [0, 0, 0, 0]
+    g = np.ctypeslib.as_array(rec.global_desc)
+    assert np.isfinite(g).all()
+    assert (np.ctypeslib.as_array(rec.stereo_match) == -1).all()
+    # a normal keyframe afterwards still works
+    up, down = frame_images(2)
+    rec2, _ = fe.process(up, down, msg_id=2)
+    assert sum(rec2.n_kpts) > 0 and fe.db_size(False) == sum(1 for d in range(4) if rec2.n_kpts[d] > 0)
+    fe.close()
