@@ -153,6 +153,16 @@ class IndexFlatIP:
         _l.check(self._lib.osb_db_search(self._h, q.shape[0], _l.ptr(q), k, _l.ptr(D), _l.ptr(I)))
         return D, I
 
+    def search_dev(self, q_ptr: int, nq: int, k: int, scores_ptr: int, ids_ptr: int, stream: int):
+        """device pointers in / out, no synchronisation (osb_db_search_dev)."""
+        _l.check(self._lib.osb_db_search_dev(self._h, nq, C.c_void_p(q_ptr), k, C.c_void_p(scores_ptr),
+                                             C.c_void_p(ids_ptr), C.c_void_p(stream)))
+
+    def add_dev(self, x_ptr: int, n: int, stream: int) -> int:
+        first = C.c_int64(-1)
+        _l.check(self._lib.osb_db_add_dev(self._h, n, C.c_void_p(x_ptr), C.byref(first), C.c_void_p(stream)))
+        return int(first.value)
+
     def reset(self):
         _l.check(self._lib.osb_db_reset(self._h))
 
