@@ -116,6 +116,13 @@ osb_status osb_db_search_dev(osb_db* h, int64_t nq, const float* q_dev, int k, f
                              int64_t* ids_dev, void* stream);
 int64_t osb_db_size(osb_db* h);
 osb_status osb_db_reset(osb_db* h);        /* ntotal = 0 (rows stay allocated) */
+/* Row-sharded search (alternative for the 50 k-row sweep): each GPU scans its shard with
+ * osb_db_search_dev, the per-shard top-k lists are all-gathered, and this call merges n_lists lists of k candidates per
+ * query (cand_* are [nq][n_lists][k], ids < 0 = padding) into the global top-k with faiss::IndexFlatIP's order
+ * (loop_detector.cpp:213): score descending, ties by ascending id.  id_offset_dev[l] (may be null) is added IN PLACE to the
+ * ids of list l (shard-local row -> global row). */
+osb_status osb_topk_merge_dev(int nq, int n_lists, int k, const float* cand_scores_dev, int64_t* cand_ids_dev,
+                              const int64_t* id_offset_dev, float* scores_dev, int64_t* ids_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Local descriptor matcher -- replaces cv::BFMatcher(cv::NORM_L2, crossCheck = true).match(query, train)

@@ -199,6 +199,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = f16 (0), K-major both,
     // N >> 3 at bit 17, M >> 4 at bit 24
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr bool WIDE = (2 * N <= 256);
+    constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // Precision: the tensor core TRUNCATES its fp32 accumulator after every MMA (measured: ~1e-5 relative per layer when
     // all three products of the split share one accumulator).  The exact-in-fp32 hi*hi products therefore go to a MAIN
     // accumulator (one truncation per K=16 step) and the two small cross products lo*hi, hi*lo to a second, CROSS
@@ -236,9 +238,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             for (int k = 0; k < UM_KC / 16; ++k) {
               const uint64_t adv = (uint64_t)(k * 32 >> 4);     // advance 16 fp16 = 32 bytes inside the swizzle row
               const uint32_t accum = (first && k == 0) ? 0u : 1u;
-              umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, accum);
-              umma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, accum);
-              umma_f16(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+              if (WIDE) {
+                // the weight slot is [W_hi (N rows) | W_lo (N rows)] and the accumulators are [main (N cols) | cross (N cols)]:
+                // ONE MMA of width 2N computes hi*hi -> main and hi*lo -> cross, fetching the activation operand once
+                // (at N = 64 the instruction is bound by shared-memory operand bandwidth, not by the tensor pipe)
+                umma_f16(d_main, a_hi + adv, b_hi + adv, idesc2, accum);
+                umma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+              } else {
+                umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, accum);
+                umma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, accum);
+                umma_f16(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+              }
             }
             first = 0;
             if (!RES) {
@@ -534,7 +544,7 @@ osb_status umma_act_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half*
 
 template <int N, bool RES>
 static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const UmmaLayer& L, const UmmaArgs& P,
-                              cudaStream_t st) {
+                              cudaStream_t st, int max_ctas) {
   using Cfg = UmmaCfg<N, RES>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -542,7 +552,8 @@ static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, 
     attr_done = true;
   }
   const int tiles = P.B * cdiv(P.W, UM_TW) * cdiv(P.H, UM_TH);
-  const int grid = std::min(tiles, num_sms());
+  // persistent CTAs, one per SM; `max_ctas` leaves SMs free for a kernel running beside this one on another stream
+  const int grid = std::min(tiles, max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms());
   OSB_LAUNCH((conv_umma_kernel<N, RES>), grid, 256, Cfg::SMEM_BYTES, st, a_hi, a_lo, L.tm_hi, L.tm_lo, P);
   OSB_CHECK_LAUNCH();
   return OSB_OK;
@@ -550,7 +561,7 @@ static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, 
 
 osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int B, int H, int W,
                              float act_scale, __half* out_hi, __half* out_lo, float* out_f32, int out_c, int out_cstride,
-                             float out_scale, int relu, int pool, cudaStream_t st) {
+                             float out_scale, int relu, int pool, cudaStream_t st, int max_ctas) {
   UmmaArgs P;
   P.pool = pool;
   OSB_REQUIRE(!pool || (H % 2 == 0 && W % 2 == 0), "fused max-pool needs even H and W");
@@ -562,17 +573,17 @@ osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const 
   P.n_off = 0;
   switch (L.n_pad) {
     case 64:
-      if (L.ks == 3 && L.cin == UM_KC) return launch_umma<64, true>(a_hi, a_lo, L, P, st);   // weights resident
-      return launch_umma<64, false>(a_hi, a_lo, L, P, st);
-    case 80: return launch_umma<80, false>(a_hi, a_lo, L, P, st);
-    case 128: return launch_umma<128, false>(a_hi, a_lo, L, P, st);
-    case 256: return launch_umma<256, false>(a_hi, a_lo, L, P, st);
+      if (L.ks == 3 && L.cin == UM_KC) return launch_umma<64, true>(a_hi, a_lo, L, P, st, max_ctas);   // weights resident
+      return launch_umma<64, false>(a_hi, a_lo, L, P, st, max_ctas);
+    case 80: return launch_umma<80, false>(a_hi, a_lo, L, P, st, max_ctas);
+    case 128: return launch_umma<128, false>(a_hi, a_lo, L, P, st, max_ctas);
+    case 256: return launch_umma<256, false>(a_hi, a_lo, L, P, st, max_ctas);
     case 512: {                                   // two N = 256 passes over the same activations
       P.out_c = 256;
-      osb_status s = launch_umma<256, false>(a_hi, a_lo, L, P, st);
+      osb_status s = launch_umma<256, false>(a_hi, a_lo, L, P, st, max_ctas);
       if (s != OSB_OK) return s;
       P.n_off = 256;
-      return launch_umma<256, false>(a_hi, a_lo, L, P, st);
+      return launch_umma<256, false>(a_hi, a_lo, L, P, st, max_ctas);
     }
   }
   set_error("umma_conv_forward", "unsupported N");

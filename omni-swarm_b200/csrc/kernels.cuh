@@ -8,7 +8,7 @@ namespace osb {
 int db_scan_grid(int64_t n, int64_t* chunk_out);
 // n_dev (optional): true row count in device memory, n is then an upper bound used to size the grid
 osb_status db_search_device(const float* rows, int64_t n, const int64_t* n_dev, int dim, const float* q_dev, int nq,
-                            int k, float* part_scores, int64_t* part_ids, float* scores_dev, int64_t* ids_dev,
+                            int k, float* part_scores, int64_t* part_ids, unsigned int* done, float* scores_dev, int64_t* ids_dev,
                             cudaStream_t st);
 // q/t: device tables of n_pairs pointers to [<=max_n][64] descriptor blocks
 // outputs (qi/ti/dout/map_out) are [n_pairs][out_stride]

@@ -34,6 +34,7 @@ struct DbStore {
   int32_t* frame_msg = nullptr;   // [cap]
   float* part_scores = nullptr;
   int64_t* part_ids = nullptr;
+  unsigned int* done = nullptr;
   float* top_scores = nullptr;    // [KMAX]
   int64_t* top_ids = nullptr;     // [KMAX]
 };
@@ -293,6 +294,8 @@ static osb_status dbstore_alloc(DbStore& s, int64_t cap, int max_num) {
   const int gmax = db_scan_grid(cap, &chunk);
   OSB_CUDA(cudaMalloc(&s.part_scores, (size_t)8 * gmax * FE_KMAX * sizeof(float)));
   OSB_CUDA(cudaMalloc(&s.part_ids, (size_t)8 * gmax * FE_KMAX * sizeof(int64_t)));
+  OSB_CUDA(cudaMalloc(&s.done, sizeof(unsigned int)));
+  OSB_CUDA(cudaMemset(s.done, 0, sizeof(unsigned int)));
   OSB_CUDA(cudaMalloc(&s.top_scores, FE_KMAX * sizeof(float)));
   OSB_CUDA(cudaMalloc(&s.top_ids, FE_KMAX * sizeof(int64_t)));
   return OSB_OK;
@@ -300,7 +303,7 @@ static osb_status dbstore_alloc(DbStore& s, int64_t cap, int max_num) {
 
 static void dbstore_free(DbStore& s) {
   cudaFree(s.dev); cudaFree(s.rows); cudaFree(s.ldesc); cudaFree(s.nk); cudaFree(s.row_frame); cudaFree(s.row_dir);
-  cudaFree(s.frame_rows); cudaFree(s.frame_msg); cudaFree(s.part_scores); cudaFree(s.part_ids);
+  cudaFree(s.frame_rows); cudaFree(s.frame_msg); cudaFree(s.part_scores); cudaFree(s.part_ids); cudaFree(s.done);
   cudaFree(s.top_scores); cudaFree(s.top_ids);
 }
 
@@ -399,10 +402,12 @@ static osb_status fe_extract_dev(osb_frontend* h, const uint8_t* img_dev /*[2*nd
   if ((s = h->nv.infer_dev(img_dev, nd, &record_dev->global_desc[0][0], h->stream2)) != OSB_OK) return s;
   OSB_CUDA(cudaEventRecord(h->ev_join, h->stream2));
   fe_mark(h, 0, st);
-  if ((s = h->sp.network(img_dev, 2 * nd, st)) != OSB_OK) return s;
+  // network; the keypoint kernel is forked beside the descriptor head inside (superpoint.cu) and joined before return
+  const SuperPoint::KpJob kp{h->sp.d_nk, h->sp.d_kpts, h->sp.d_conf};
+  if ((s = h->sp.network(img_dev, 2 * nd, st, &kp)) != OSB_OK) return s;
   h->sp.last_batch = 2 * nd;
   fe_mark(h, 1, st);
-  if ((s = h->sp.postprocess(2 * nd, h->sp.d_nk, h->sp.d_kpts, h->sp.d_conf, h->sp.d_out, st)) != OSB_OK) return s;
+  if ((s = h->sp.descriptors(2 * nd, kp, h->sp.d_out, st)) != OSB_OK) return s;
   fe_mark(h, 2, st);
   OSB_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));      // join (stage 2 = the part of NetVLAD that was not hidden)
   fe_mark(h, 3, st);
@@ -485,9 +490,9 @@ static osb_status fe_query(osb_frontend* h, const osb_keyframe_record* rec, int 
   osb_status s;
   fe_mark(h, 5, st);
   if ((s = db_search_device(R.rows, std::min(R.upper, R.cap), &R.dev->ntotal, OSB_DEEP_DESC_SIZE, q, 1, k_remote,
-                            R.part_scores, R.part_ids, R.top_scores, R.top_ids, st)) != OSB_OK) return s;
+                            R.part_scores, R.part_ids, R.done, R.top_scores, R.top_ids, st)) != OSB_OK) return s;
   if ((s = db_search_device(L.rows, std::min(L.upper, L.cap), &L.dev->ntotal, OSB_DEEP_DESC_SIZE, q, 1, k_local,
-                            L.part_scores, L.part_ids, L.top_scores, L.top_ids, st)) != OSB_OK) return s;
+                            L.part_scores, L.part_ids, L.done, L.top_scores, L.top_ids, st)) != OSB_OK) return s;
   fe_mark(h, 6, st);
   QueryParams qp;
   qp.self_id = c.self_id; qp.n_dirs = c.n_dirs; qp.query_dir = c.query_dir; qp.match_index_dist = c.match_index_dist;

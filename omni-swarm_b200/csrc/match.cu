@@ -12,21 +12,177 @@
 
 namespace osb {
 
+constexpr int DB_THREADS = 512;
+constexpr int DB_CHUNK_MAX = 512;  // rows per CTA
+
+// ---- shared tail of the scan kernels ----------------------------------------------------------------------------
+// (1) the CTA emits the top-k of its own rows by rank counting (score desc, row id asc);
+// (2) fused merge: the LAST CTA to finish (ticket counter) sorts the grid*k candidates of each query in shared memory
+//     (bitonic, 64-bit keys = inverted order-preserving score bits : row id) and writes the final k results -- no second
+//     launch, which at 10 k rows was a third of the search time.  Used when grid*k <= DB_MERGE_MAX; otherwise the host
+//     launches db_merge_kernel.
+constexpr int DB_MERGE_MAX = 4096;
+
+__device__ __forceinline__ unsigned long long db_key(float s, int64_t id) {
+  if (id < 0) return ~0ull;
+  s += 0.0f;                                                   // -0 -> +0 (they tie as floats)
+  unsigned u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);              // ascending unsigned order == ascending float order
+  return ((unsigned long long)(~u) << 32) | (unsigned long long)(unsigned)id;   // ascending key: score desc, id asc
+}
+__device__ __forceinline__ float db_key_score(unsigned long long key) {
+  const unsigned o = ~(unsigned)(key >> 32);
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+__device__ void db_emit_and_merge(const float* ss, int ss_stride, int nrows, int64_t row0, int nq, int k,
+                                  float* __restrict__ part_scores, int64_t* __restrict__ part_ids,
+                                  float* __restrict__ out_scores, int64_t* __restrict__ out_ids, unsigned int* done,
+                                  int fuse, unsigned long long* keys) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int qq = 0; qq < nq; ++qq) {
+    const float* s = ss + qq * ss_stride;
+    float* ps = part_scores + ((size_t)qq * gridDim.x + blockIdx.x) * k;
+    int64_t* pi = part_ids + ((size_t)qq * gridDim.x + blockIdx.x) * k;
+    for (int i = tid; i < k; i += nthr)
+      if (i >= nrows) { ps[i] = -INFINITY; pi[i] = -1; }
+    for (int i = tid; i < nrows; i += nthr) {
+      const float si = s[i];
+      int rank = 0;
+      for (int j = 0; j < nrows; ++j) {
+        const float sj = s[j];
+        rank += (sj > si) || (sj == si && j < i);
+      }
+      if (rank < k) { ps[rank] = si; pi[rank] = row0 + i; }
+    }
+  }
+  if (!fuse) return;
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int ncand = gridDim.x * k;
+  int n2 = 64;
+  while (n2 < ncand) n2 <<= 1;
+  for (int qq = 0; qq < nq; ++qq) {
+    const float* ps = part_scores + (size_t)qq * ncand;
+    const int64_t* pi = part_ids + (size_t)qq * ncand;
+    __syncthreads();
+    for (int i = tid; i < n2; i += nthr) keys[i] = (i < ncand) ? db_key(__ldcg(ps + i), __ldcg(pi + i)) : ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = tid; t < (n2 >> 1); t += nthr) {
+          const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+          const unsigned long long a = keys[lo], b = keys[hi];
+          if ((a > b) == ((lo & size) == 0)) { keys[lo] = b; keys[hi] = a; }
+        }
+        __syncthreads();
+      }
+    for (int i = tid; i < k; i += nthr) {
+      const unsigned long long key = keys[i];
+      const bool ok = key != ~0ull;
+      out_scores[qq * k + i] = ok ? db_key_score(key) : -INFINITY;
+      out_ids[qq * k + i] = ok ? (int64_t)(unsigned)(key & 0xffffffffull) : -1;
+    }
+  }
+  if (tid == 0) *done = 0;                                     // ready for the next search on this scratch
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// db_scan_coop_kernel<Q>: small databases (<= DB_COOP_CHUNK rows per CTA, i.e. <= ~19 k rows; dim = 4096).  With few
+// rows per CTA the warp-per-row scheme leaves half the warps idle (10 k rows / 296 CTAs = 34 rows = 9 groups of 4 for
+// 16 warps) and too few bytes in flight.  Here ALL 16 warps share every row: warp w owns float4 columns
+// [64w, 64w+64) -- its slice of the queries lives in registers (no shared-memory query copy at all), each lane has
+// R x 2 independent 16-byte streaming loads in flight, and the 16 partial sums per row are added in fixed warp order
+// (deterministic).
+// -------------------------------------------------------------------------------------------------------------
+constexpr int DB_COOP_CHUNK = 64;
+constexpr int DB_COOP_DIM = 4096;
+
+template <int Q>
+__global__ void __launch_bounds__(DB_THREADS, (Q <= 2) ? 2 : 1)
+db_scan_coop_kernel(const float* __restrict__ db, int64_t n_val, const int64_t* __restrict__ n_dev,
+                    const float* __restrict__ q, int nq, int k, float* __restrict__ part_scores,
+                    int64_t* __restrict__ part_ids, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                    unsigned int* done, int fuse) {
+  constexpr int DIM4 = DB_COOP_DIM / 4, NW = DB_THREADS / 32, C = DIM4 / (NW * 32), R = 4, CH = DB_COOP_CHUNK;
+  static_assert(C == 2, "column slice");
+  extern __shared__ __align__(16) float smem[];
+  float* partial = smem;                        // [NW][CH][Q]
+  float* ss = smem + NW * CH * Q;               // [Q][CH]
+  if (!fuse && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < nq * k; i += DB_THREADS) { out_scores[i] = -INFINITY; out_ids[i] = -1; }
+  const int64_t n = n_dev ? *n_dev : n_val;
+  const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;         // <= CH: the grid was sized for an upper bound of n
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * chunk;
+  const int64_t row1 = min(n, row0 + chunk);
+  const int nrows = (int)max((int64_t)0, row1 - row0);
+  const int col = warp * (C * 32) + lane;
+  float4 wq[Q][C];
+#pragma unroll
+  for (int qq = 0; qq < Q; ++qq)
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      wq[qq][c] = (qq < nq) ? __ldg(reinterpret_cast<const float4*>(q) + (size_t)qq * DIM4 + col + c * 32)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* base = reinterpret_cast<const float4*>(db) + row0 * DIM4 + col;
+#pragma unroll 2
+  for (int r0 = 0; r0 < nrows; r0 += R) {
+    float4 v[R][C];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = min(r0 + r, nrows - 1);                      // clamped: the surplus loads hit a valid row
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[r][c] = ld_stream_f4(base + (size_t)row * DIM4 + c * 32);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int qq = 0; qq < Q; ++qq) {
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          a = fmaf(v[r][c].x, wq[qq][c].x, a);
+          a = fmaf(v[r][c].y, wq[qq][c].y, a);
+          a = fmaf(v[r][c].z, wq[qq][c].z, a);
+          a = fmaf(v[r][c].w, wq[qq][c].w, a);
+        }
+        a = warp_sum(a);
+        if (lane == 0 && r0 + r < nrows) partial[(warp * CH + r0 + r) * Q + qq] = a;
+      }
+  }
+  __syncthreads();
+  for (int i = tid; i < nrows * Q; i += DB_THREADS) {
+    const int row = i / Q, qq = i % Q;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) a += partial[(w * CH + row) * Q + qq];
+    ss[qq * CH + row] = a;
+  }
+  __syncthreads();
+  db_emit_and_merge(ss, CH, nrows, row0, nq, k, part_scores, part_ids, out_scores, out_ids, done, fuse,
+                    reinterpret_cast<unsigned long long*>(smem));
+}
+
 // -------------------------------------------------------------------------------------------------------------
 // db_scan_kernel<Q,R>: each warp owns R consecutive rows at a time and dots them with Q queries held in shared
 // memory; a lane streams float4 columns lane, lane+32, ... of all R rows (R independent 16-byte loads in flight,
 // 512 contiguous bytes per row per warp instruction).  Scores of the CTA's row chunk are parked in shared memory
 // and the CTA emits its own top-k by rank counting (score desc, row id asc: the library's documented tie rule).
 // -------------------------------------------------------------------------------------------------------------
-constexpr int DB_THREADS = 512;
-constexpr int DB_CHUNK_MAX = 512;  // rows per CTA
 
 template <int Q, int R>
 __global__ void __launch_bounds__(DB_THREADS)
 db_scan_kernel(const float* __restrict__ db, int64_t n_val, const int64_t* __restrict__ n_dev, int dim,
                const float* __restrict__ q, int nq, int k, float* __restrict__ part_scores,
-               int64_t* __restrict__ part_ids, float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
-  if (blockIdx.x == 0)   // final rows start as "no result" (faiss: -inf / -1); the merge kernel overwrites the hits
+               int64_t* __restrict__ part_ids, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+               unsigned int* done, int fuse) {
+  if (!fuse && blockIdx.x == 0)   // final rows start as "no result" (faiss: -inf / -1); the merge kernel overwrites the hits
     for (int i = threadIdx.x; i < nq * k; i += DB_THREADS) { out_scores[i] = -INFINITY; out_ids[i] = -1; }
   // the row count may live on the device (keyframe front-end: rows are appended without a host round trip);
   // the launch grid was sized for an upper bound, the chunk is derived from the true count.
@@ -88,23 +244,8 @@ db_scan_kernel(const float* __restrict__ db, int64_t n_val, const int64_t* __res
       }
   }
   __syncthreads();
-  // per-CTA top-k by rank counting
-  for (int qq = 0; qq < nq; ++qq) {
-    const float* s = ss + qq * DB_CHUNK_MAX;
-    float* ps = part_scores + ((size_t)qq * gridDim.x + blockIdx.x) * k;
-    int64_t* pi = part_ids + ((size_t)qq * gridDim.x + blockIdx.x) * k;
-    for (int i = tid; i < k; i += DB_THREADS)
-      if (i >= nrows) { ps[i] = -INFINITY; pi[i] = -1; }
-    for (int i = tid; i < nrows; i += DB_THREADS) {
-      const float si = s[i];
-      int rank = 0;
-      for (int j = 0; j < nrows; ++j) {
-        const float sj = s[j];
-        rank += (sj > si) || (sj == si && j < i);
-      }
-      if (rank < k) { ps[rank] = si; pi[rank] = row0 + i; }
-    }
-  }
+  db_emit_and_merge(ss, DB_CHUNK_MAX, nrows, row0, nq, k, part_scores, part_ids, out_scores, out_ids, done, fuse,
+                    reinterpret_cast<unsigned long long*>(smem));
 }
 
 // merge: rank counting over the grid*k partial candidates, spread over many CTAs: CTA (x, q) ranks candidates
@@ -136,22 +277,35 @@ db_merge_kernel(const float* __restrict__ part_scores, const int64_t* __restrict
 
 template <int Q>
 static osb_status launch_scan(const float* db, int64_t n, const int64_t* n_dev, int dim, const float* q, int nq,
-                              int k, int grid, float* ps, int64_t* pi, float* os, int64_t* oi, cudaStream_t st) {
+                              int k, int grid, bool coop, float* ps, int64_t* pi, float* os, int64_t* oi,
+                              unsigned int* done, int fuse, cudaStream_t st) {
   constexpr int R = 4;
-  size_t smem = ((size_t)Q * dim + (size_t)Q * DB_CHUNK_MAX) * sizeof(float);
+  const size_t merge_bytes = fuse ? (size_t)DB_MERGE_MAX * sizeof(unsigned long long) : 0;
+  if (coop) {
+    const size_t smem = std::max(merge_bytes, (size_t)(DB_THREADS / 32 + 1) * DB_COOP_CHUNK * Q * sizeof(float));
+    static bool attr_done = false;
+    if (!attr_done) {
+      OSB_CUDA(cudaFuncSetAttribute(db_scan_coop_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr_done = true;
+    }
+    OSB_LAUNCH((db_scan_coop_kernel<Q>), grid, DB_THREADS, smem, st, db, n, n_dev, q, nq, k, ps, pi, os, oi, done, fuse);
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+  }
+  const size_t smem = std::max(merge_bytes, ((size_t)Q * dim + (size_t)Q * DB_CHUNK_MAX) * sizeof(float));
   static bool attr_done = false;
   if (!attr_done) {
     OSB_CUDA(cudaFuncSetAttribute(db_scan_kernel<Q, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
-  OSB_LAUNCH((db_scan_kernel<Q, R>), grid, DB_THREADS, smem, st, db, n, n_dev, dim, q, nq, k, ps, pi, os, oi);
+  OSB_LAUNCH((db_scan_kernel<Q, R>), grid, DB_THREADS, smem, st, db, n, n_dev, dim, q, nq, k, ps, pi, os, oi, done, fuse);
   OSB_CHECK_LAUNCH();
   return OSB_OK;
 }
 
+// largest grid any search over <= n rows uses (scratch sizing)
 int db_scan_grid(int64_t n, int64_t* chunk_out) {
-  // two CTAs (2 x 16 warps) per SM: with 4 rows per warp pass a 10 k-row database is ONE balanced pass for every
-  // warp (ncu, r01: with one CTA per SM the 17th row group of each CTA ran alone while 15 warps sat at the barrier)
+  // two CTAs (2 x 16 warps) per SM
   int grid = 2 * num_sms();
   int64_t chunk = cdiv64(n > 0 ? n : 1, grid);
   if (chunk > DB_CHUNK_MAX) {
@@ -162,28 +316,32 @@ int db_scan_grid(int64_t n, int64_t* chunk_out) {
   return grid;
 }
 
-// device-side search of up to 8 queries; scratch must hold 8*grid_max*k floats / int64
+// device-side search of up to 8 queries per pass; the scratch holds 8*grid_max*k floats / int64 and one ticket counter
+// (zero between searches).  n is an upper bound of *n_dev when n_dev is given.
 osb_status db_search_device(const float* rows, int64_t n, const int64_t* n_dev, int dim, const float* q_dev, int nq,
-                            int k, float* part_scores, int64_t* part_ids, float* scores_dev, int64_t* ids_dev,
-                            cudaStream_t st) {
+                            int k, float* part_scores, int64_t* part_ids, unsigned int* done, float* scores_dev,
+                            int64_t* ids_dev, cudaStream_t st) {
   int64_t chunk;
-  const int grid = db_scan_grid(n, &chunk);   // n is an upper bound of *n_dev when n_dev is given
+  int grid = db_scan_grid(n, &chunk);
+  // small databases: every warp of a CTA shares each row (db_scan_coop_kernel); a CTA never gets more than 64 rows
+  const bool coop = (dim == DB_COOP_DIM) && chunk <= DB_COOP_CHUNK;
+  if (coop) grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, n));
+  const int fuse = (done != nullptr && (int64_t)grid * k <= DB_MERGE_MAX) ? 1 : 0;
   for (int q0 = 0; q0 < nq; q0 += 8) {
     const int nb = min(8, nq - q0);
     const float* qp = q_dev + (size_t)q0 * dim;
+    float* os = scores_dev + (size_t)q0 * k;
+    int64_t* oi = ids_dev + (size_t)q0 * k;
     osb_status s;
-    if (nb == 1) s = launch_scan<1>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, scores_dev + (size_t)q0 * k,
-                            ids_dev + (size_t)q0 * k, st);
-    else if (nb == 2) s = launch_scan<2>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, scores_dev + (size_t)q0 * k,
-                            ids_dev + (size_t)q0 * k, st);
-    else if (nb <= 4) s = launch_scan<4>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, scores_dev + (size_t)q0 * k,
-                            ids_dev + (size_t)q0 * k, st);
-    else s = launch_scan<8>(rows, n, n_dev, dim, qp, nb, k, grid, part_scores, part_ids, scores_dev + (size_t)q0 * k,
-                            ids_dev + (size_t)q0 * k, st);
+    if (nb == 1) s = launch_scan<1>(rows, n, n_dev, dim, qp, nb, k, grid, coop, part_scores, part_ids, os, oi, done, fuse, st);
+    else if (nb == 2) s = launch_scan<2>(rows, n, n_dev, dim, qp, nb, k, grid, coop, part_scores, part_ids, os, oi, done, fuse, st);
+    else if (nb <= 4) s = launch_scan<4>(rows, n, n_dev, dim, qp, nb, k, grid, coop, part_scores, part_ids, os, oi, done, fuse, st);
+    else s = launch_scan<8>(rows, n, n_dev, dim, qp, nb, k, grid, coop, part_scores, part_ids, os, oi, done, fuse, st);
     if (s != OSB_OK) return s;
-    OSB_LAUNCH(db_merge_kernel, dim3(cdiv(grid * k, 32), nb), 1024, 0, st, part_scores, part_ids, grid * k, k, scores_dev + (size_t)q0 * k,
-               ids_dev + (size_t)q0 * k);
-    OSB_CHECK_LAUNCH();
+    if (!fuse) {
+      OSB_LAUNCH(db_merge_kernel, dim3(cdiv(grid * k, 32), nb), 1024, 0, st, part_scores, part_ids, grid * k, k, os, oi);
+      OSB_CHECK_LAUNCH();
+    }
   }
   return OSB_OK;
 }
@@ -317,6 +475,7 @@ struct osb_db {
   float* rows = nullptr;
   float* part_scores = nullptr;
   int64_t* part_ids = nullptr;
+  unsigned int* done = nullptr;     // ticket counter of the fused merge
   float *d_q = nullptr, *d_scores = nullptr;
   int64_t* d_ids = nullptr;
   int kmax = 64, qmax = 64;
@@ -337,6 +496,8 @@ extern "C" osb_status osb_db_create(osb_db** out, int dim, int64_t capacity) {
   OSB_CUDA(cudaMalloc(&h->rows, (size_t)capacity * dim * sizeof(float)));
   OSB_CUDA(cudaMalloc(&h->part_scores, (size_t)8 * h->grid_max * h->kmax * sizeof(float)));
   OSB_CUDA(cudaMalloc(&h->part_ids, (size_t)8 * h->grid_max * h->kmax * sizeof(int64_t)));
+  OSB_CUDA(cudaMalloc(&h->done, sizeof(unsigned int)));
+  OSB_CUDA(cudaMemset(h->done, 0, sizeof(unsigned int)));
   OSB_CUDA(cudaMalloc(&h->d_q, (size_t)h->qmax * dim * sizeof(float)));
   OSB_CUDA(cudaMalloc(&h->d_scores, (size_t)h->qmax * h->kmax * sizeof(float)));
   OSB_CUDA(cudaMalloc(&h->d_ids, (size_t)h->qmax * h->kmax * sizeof(int64_t)));
@@ -346,7 +507,7 @@ extern "C" osb_status osb_db_create(osb_db** out, int dim, int64_t capacity) {
 
 extern "C" osb_status osb_db_destroy(osb_db* h) {
   if (!h) return OSB_OK;
-  cudaFree(h->rows); cudaFree(h->part_scores); cudaFree(h->part_ids);
+  cudaFree(h->rows); cudaFree(h->part_scores); cudaFree(h->part_ids); cudaFree(h->done);
   cudaFree(h->d_q); cudaFree(h->d_scores); cudaFree(h->d_ids);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -390,8 +551,42 @@ extern "C" osb_status osb_db_search_dev(osb_db* h, int64_t nq, const float* q_de
   OSB_REQUIRE(h != nullptr && q_dev && scores_dev && ids_dev, "null argument");
   OSB_REQUIRE(k > 0 && k <= h->kmax && nq > 0, "k must be in 1..64 and nq > 0");
   std::lock_guard<std::mutex> lk(h->mu);
-  return db_search_device(h->rows, h->ntotal, nullptr, h->dim, q_dev, (int)nq, k, h->part_scores, h->part_ids, scores_dev,
+  return db_search_device(h->rows, h->ntotal, nullptr, h->dim, q_dev, (int)nq, k, h->part_scores, h->part_ids, h->done, scores_dev,
                           ids_dev, (cudaStream_t)stream);
+}
+
+// candidate lists of several database shards -> global top-k (same order rule as the scan: score descending, ties by
+// ascending id).  Used by the row-sharded search: every rank scans its shard, the k candidates
+// per query are all-gathered, and each rank merges world*k candidates.  id_offset[l] is added to the ids of list l
+// (shard-local row -> global row); ids < 0 are padding.
+__global__ void topk_fill_offset_kernel(float* __restrict__ out_scores, int64_t* __restrict__ out_ids, int n_out,
+                                        int64_t* __restrict__ cand_ids, int64_t n_cand_total, int ncand, int list_len,
+                                        const int64_t* __restrict__ id_offset) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_out) { out_scores[i] = -INFINITY; out_ids[i] = -1; }
+  if (i < n_cand_total && id_offset) {
+    const int64_t id = cand_ids[i];
+    if (id >= 0) cand_ids[i] = id + id_offset[(i % ncand) / list_len];
+  }
+}
+
+extern "C" osb_status osb_topk_merge_dev(int nq, int n_lists, int k, const float* cand_scores_dev, int64_t* cand_ids_dev,
+                                         const int64_t* id_offset_dev, float* scores_dev, int64_t* ids_dev,
+                                         void* stream) {
+  OSB_REQUIRE(cand_scores_dev && cand_ids_dev && scores_dev && ids_dev, "null argument");
+  OSB_REQUIRE(nq > 0 && n_lists > 0 && k > 0 && k <= 64, "bad nq / n_lists / k");
+  osb_status s = require_device();
+  if (s != OSB_OK) return s;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ncand = n_lists * k;
+  const int64_t total = (int64_t)nq * ncand;
+  OSB_LAUNCH(topk_fill_offset_kernel, (unsigned)cdiv64(total, 256), 256, 0, st, scores_dev, ids_dev, nq * k, cand_ids_dev,
+             total, ncand, k, id_offset_dev);
+  OSB_CHECK_LAUNCH();
+  OSB_LAUNCH(db_merge_kernel, dim3(cdiv(ncand, 32), nq), 1024, 0, st, cand_scores_dev, cand_ids_dev, ncand, k,
+             scores_dev, ids_dev);
+  OSB_CHECK_LAUNCH();
+  return OSB_OK;
 }
 
 extern "C" osb_status osb_db_search(osb_db* h, int64_t nq, const float* q, int k, float* scores, int64_t* ids) {
@@ -402,7 +597,7 @@ extern "C" osb_status osb_db_search(osb_db* h, int64_t nq, const float* q, int k
     const int nb = (int)std::min<int64_t>(h->qmax, nq - q0);
     OSB_CUDA(cudaMemcpyAsync(h->d_q, q + (size_t)q0 * h->dim, (size_t)nb * h->dim * sizeof(float),
                              cudaMemcpyHostToDevice, h->stream));
-    osb_status s = db_search_device(h->rows, h->ntotal, nullptr, h->dim, h->d_q, nb, k, h->part_scores, h->part_ids,
+    osb_status s = db_search_device(h->rows, h->ntotal, nullptr, h->dim, h->d_q, nb, k, h->part_scores, h->part_ids, h->done,
                                     h->d_scores, h->d_ids, h->stream);
     if (s != OSB_OK) return s;
     OSB_CUDA(cudaMemcpyAsync(scores + (size_t)q0 * k, h->d_scores, (size_t)nb * k * sizeof(float),

@@ -30,6 +30,10 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
   W = width; H = height; thres = thres_; max_num = max_num_; max_batch = max_batch_;
   Hc = H / 8; Wc = W / 8;
   OSB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  OSB_CUDA(cudaStreamCreateWithFlags(&kp_stream, cudaStreamNonBlocking));
+  OSB_CUDA(cudaEventCreateWithFlags(&ev_semi, cudaEventDisableTiming));
+  OSB_CUDA(cudaEventCreateWithFlags(&ev_kp, cudaEventDisableTiming));
+  if (const char* e = getenv("OSB_SP_OVERLAP")) overlap_kp = atoi(e) != 0;
   // ---- weights ----
   const float* p = weights;
   {
@@ -124,11 +128,14 @@ void SuperPoint::release() {
   cudaFree(ks.state); cudaFree(ks.surv); cudaFree(ks.cand); cudaFree(ks.skey); cudaFree(ks.cmask); cudaFree(ks.counts); cudaFree(ks.cnorm);
   cudaFree(d_nk); cudaFree(d_kpts); cudaFree(d_conf); cudaFree(d_out);
   if (stream) cudaStreamDestroy(stream);
+  if (kp_stream) cudaStreamDestroy(kp_stream);
+  if (ev_semi) cudaEventDestroy(ev_semi);
+  if (ev_kp) cudaEventDestroy(ev_kp);
 }
 
 // tensor-core network: every activation is a pair of fp16 planes (hi, lo) scaled by SP_ACT_SCALE; the planes of a
 // layer's output live in the ping-pong buffer the next layer's TMA descriptors point at.
-osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t st) {
+osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t st, const KpJob* kp) {
   osb_status s;
 #define RUN(x) do { s = (x); if (s != OSB_OK) return s; } while (0)
   const float SA = SP_ACT_SCALE;
@@ -160,19 +167,33 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
   mark(st);
   RUN(umma_conv_forward(UL[9], tmA[9], tmB[9], B, Hc, Wc, SA, nullptr, nullptr, d_logits, 80, 80, 1.f, 0, 0, st));   // convPb
   mark(st);
-  RUN(conv(10, Hc, Wc, 11, 0));                                                           // convDa (reads B)  -> A
+  RUN(sp_softmax_shuffle(d_logits, 80, d_semi, B, Hc, Wc, st));
+  // the keypoint kernel (one CTA per image, latency-bound) runs beside the descriptor head, which leaves it B SMs
+  const bool fork = kp && overlap_kp && !layer_prof && kp_stream;
+  int head_ctas = 0;
+  if (fork) {
+    OSB_CUDA(cudaEventRecord(ev_semi, st));
+    OSB_CUDA(cudaStreamWaitEvent(kp_stream, ev_semi, 0));
+    RUN(keypoints(B, *kp, kp_stream));
+    OSB_CUDA(cudaEventRecord(ev_kp, kp_stream));
+    head_ctas = std::max(1, num_sms() - B);
+  }
+  RUN(umma_conv_forward(UL[10], tmA[10], tmB[10], B, Hc, Wc, SA, in_hi[11], in_lo[11], nullptr, SP_COUT[10], SP_COUT[10],
+                        SA, 1, 0, st, head_ctas));                                        // convDa (reads B)  -> A
   mark(st);
-  RUN(umma_conv_forward(UL[11], tmA[11], tmB[11], B, Hc, Wc, SA, nullptr, nullptr, d_desc, 256, 256, 1.f, 0, 0, st)); // convDb
+  RUN(umma_conv_forward(UL[11], tmA[11], tmB[11], B, Hc, Wc, SA, nullptr, nullptr, d_desc, 256, 256, 1.f, 0, 0, st,
+                        head_ctas));                                                      // convDb
   mark(st);
   RUN(l2norm_cells(d_desc, (int64_t)B * Hc * Wc, 256, st));
-  RUN(sp_softmax_shuffle(d_logits, 80, d_semi, B, Hc, Wc, st));
+  if (fork) OSB_CUDA(cudaStreamWaitEvent(st, ev_kp, 0));
+  else if (kp) RUN(keypoints(B, *kp, st));
 #undef RUN
   return OSB_OK;
 }
 
 // the network: u8 images (device) -> d_semi, d_desc
-osb_status SuperPoint::network(const uint8_t* img_dev, int B, cudaStream_t st) {
-  if (use_umma) return network_umma(img_dev, B, st);
+osb_status SuperPoint::network(const uint8_t* img_dev, int B, cudaStream_t st, const KpJob* kp) {
+  if (use_umma) return network_umma(img_dev, B, st, kp);
   osb_status s;
 #define RUN(x) do { s = (x); if (s != OSB_OK) return s; } while (0)
   RUN(conv_first_forward(w1a, b1a, lut, img_dev, actA, B, H, W, 64, 1, ACT_RELU, st));      // conv1a
@@ -192,22 +213,38 @@ osb_status SuperPoint::network(const uint8_t* img_dev, int B, cudaStream_t st) {
   RUN(conv_forward(L[11], actB, d_desc, B, Hc, Wc, 256, ACT_NONE, st));                      // convDb
   RUN(l2norm_cells(d_desc, (int64_t)B * Hc * Wc, 256, st));
   RUN(sp_softmax_shuffle(d_logits, 72, d_semi, B, Hc, Wc, st));
+  if (kp) RUN(keypoints(B, *kp, st));
 #undef RUN
   return OSB_OK;
 }
 
+osb_status SuperPoint::keypoints(int B, const KpJob& kp, cudaStream_t st) {
+  return sp_keypoints(d_semi, B, H, W, thres, max_num, ks, kp.nk, kp.kpts, kp.conf, st);
+}
+
+osb_status SuperPoint::descriptors(int B, const KpJob& kp, float* out, cudaStream_t st) {
+  return sp_descriptors(d_desc, B, H, W, kp.nk, kp.kpts, max_num, pca_compT, pca_mean_d, ks.cnorm, out, st);
+}
+
 osb_status SuperPoint::postprocess(int B, int32_t* nk, float* kpts, float* conf, float* out, cudaStream_t st) {
-  osb_status s = sp_keypoints(d_semi, B, H, W, thres, max_num, ks, nk, kpts, conf, st);
+  const KpJob kp{nk, kpts, conf};
+  osb_status s = keypoints(B, kp, st);
   if (s != OSB_OK) return s;
-  return sp_descriptors(d_desc, B, H, W, nk, kpts, max_num, pca_compT, pca_mean_d, ks.cnorm, out, st);
+  return descriptors(B, kp, out, st);
+}
+
+osb_status SuperPoint::forward(const uint8_t* img_dev, int B, int32_t* nk, float* kpts, float* conf, float* out,
+                               cudaStream_t st) {
+  OSB_REQUIRE(B > 0 && B <= max_batch, "batch out of range");
+  const KpJob kp{nk, kpts, conf};
+  osb_status s = network(img_dev, B, st, &kp);
+  if (s != OSB_OK) return s;
+  last_batch = B;
+  return descriptors(B, kp, out, st);
 }
 
 osb_status SuperPoint::infer_dev(const uint8_t* img_dev, int B, int32_t* nk, float* kpts, float* out, cudaStream_t st) {
-  OSB_REQUIRE(B > 0 && B <= max_batch, "batch out of range");
-  osb_status s = network(img_dev, B, st);
-  if (s != OSB_OK) return s;
-  last_batch = B;
-  return postprocess(B, nk, kpts, d_conf, out, st);
+  return forward(img_dev, B, nk, kpts, d_conf, out, st);
 }
 
 }  // namespace osb

@@ -37,8 +37,18 @@ struct SuperPoint {
   osb_status init(const float* weights, size_t n_weights, int width, int height, float thres, int max_num,
                   const float* pca_comp, const float* pca_mean, int max_batch);
   void release();
-  osb_status network(const uint8_t* img_dev, int B, cudaStream_t st);
-  osb_status network_umma(const uint8_t* img_dev, int B, cudaStream_t st);
+  // keypoint extraction needs only the detector head: when a KpJob is passed, the network launches it on `kp_stream`
+  // as soon as the heat map exists and runs the descriptor head beside it (on B fewer SMs); `st` re-joins before return
+  struct KpJob { int32_t* nk; float* kpts; float* conf; };
+  cudaStream_t kp_stream = nullptr;
+  cudaEvent_t ev_semi = nullptr, ev_kp = nullptr;
+  bool overlap_kp = true;
+  osb_status network(const uint8_t* img_dev, int B, cudaStream_t st, const KpJob* kp = nullptr);
+  osb_status network_umma(const uint8_t* img_dev, int B, cudaStream_t st, const KpJob* kp);
+  osb_status keypoints(int B, const KpJob& kp, cudaStream_t st);
+  osb_status descriptors(int B, const KpJob& kp, float* out, cudaStream_t st);
+  // network + keypoints + descriptors (what inference() is)
+  osb_status forward(const uint8_t* img_dev, int B, int32_t* nk, float* kpts, float* conf, float* out, cudaStream_t st);
   osb_status postprocess(int B, int32_t* nk, float* kpts, float* conf, float* out, cudaStream_t st);
   osb_status infer_dev(const uint8_t* img_dev, int B, int32_t* nk, float* kpts, float* out, cudaStream_t st);
 };

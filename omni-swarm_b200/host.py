@@ -310,7 +310,7 @@ class KeyframeFrontend:
     def finish(self, stream: int):
         _l.check(self._lib.osb_frontend_finish(self._h, C.c_void_p(stream)))
 
-    STAGES = ["superpoint_net", "keypoints_desc(+netvlad overlapped)", "netvlad_unhidden", "stereo_pack", "add_to_database", "db_scan",
+    STAGES = ["superpoint_net(+keypoints beside descriptor head)", "descriptors", "netvlad_unhidden", "stereo_pack", "add_to_database", "db_scan",
               "rule_local_match"]
 
     def set_profiling(self, enable: bool):

@@ -89,6 +89,7 @@ _SIG = {
     "osb_db_add_dev": (C.c_int, [_P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
     "osb_db_search": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P]),
     "osb_db_search_dev": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P, _P]),
+    "osb_topk_merge_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "osb_db_size": (C.c_int64, [_P]),
     "osb_db_reset": (C.c_int, [_P]),
     "osb_matcher_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int]),

@@ -44,3 +44,91 @@ def routing(gathered_host: torch.Tensor, self_id: int):
         dirs = [d for d in range(min(rec.n_dirs, _l.MAX_DIRS)) if rec.n_kpts[d] > 0]      # loop_detector.cpp:153
         out.append((r, rec.drone_id, rec.msg_id, "local" if rec.drone_id == self_id else "remote", dirs))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Row-sharded keyframe database (the alternative layout for the 50 k-row sweep)
+# ---------------------------------------------------------------------------------------------------------------
+def shard_rows(n_rows: int, rank: int, world: int) -> tuple[int, int]:
+    """contiguous balanced split of the database rows: the first n_rows % world ranks hold one extra row."""
+    base, extra = divmod(n_rows, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+class RowShardedIndex:
+    """faiss::IndexFlatIP semantics (loop_detector.h:27-29, loop_detector.cpp:213) over a database whose ROWS are split
+    across the ranks: two exchange steps per search -- all-gather the queries (world x dim floats), every rank scans its
+    own shard for all of them (one pass over the shard, up to 8 queries per pass), all-gather the k candidates per
+    (shard, query), and each rank merges world x k candidates for its own query.  Global row ids = shard-local row +
+    the shard's first row; order = score descending, ties by ascending global id, -1 / -inf padding.
+
+    `shard` is this rank's rows [n_local, dim] (float32 numpy, or a CUDA tensor); `n_rows_total` fixes every rank's
+    row range.
+    """
+
+    def __init__(self, shard, n_rows_total: int, dim: int = 4096, group=None, device=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dim, self.n_total = dim, n_rows_total
+        self.starts = [shard_rows(n_rows_total, r, self.world)[0] for r in range(self.world)]
+        a, b = shard_rows(n_rows_total, self.rank, self.world)
+        assert tuple(shard.shape) == (b - a, dim), (shard.shape, a, b)
+        self.device = device
+        self._open(shard)
+
+    # -- the three device steps (overridden by the CPU/gloo test with host stand-ins) --
+    def _open(self, shard):
+        from . import host
+        self._index = host.IndexFlatIP(self.dim, capacity=max(1, shard.shape[0]))
+        if shard.shape[0]:
+            if isinstance(shard, torch.Tensor):                      # rows already in HBM
+                assert shard.is_cuda and shard.dtype == torch.float32 and shard.is_contiguous()
+                self._index.add_dev(shard.data_ptr(), shard.shape[0], torch.cuda.current_stream().cuda_stream)
+                torch.cuda.current_stream().synchronize()
+            else:
+                self._index.add(shard)
+        self._lib = _l.load()
+        self._offs = torch.tensor(self.starts, dtype=torch.int64, device=self.device)
+
+    def _local_search(self, queries: torch.Tensor, k: int):
+        nq = queries.shape[0]
+        sc = torch.empty(nq, k, dtype=torch.float32, device=queries.device)
+        ids = torch.empty(nq, k, dtype=torch.int64, device=queries.device)
+        st = torch.cuda.current_stream().cuda_stream
+        self._index.search_dev(queries.data_ptr(), nq, k, sc.data_ptr(), ids.data_ptr(), st)
+        return sc, ids
+
+    def _merge(self, cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int):
+        """cand_* [n_lists, k] (ids shard-local) -> global top-k of ONE query"""
+        import ctypes as C
+        out_s = torch.empty(k, dtype=torch.float32, device=cand_scores.device)
+        out_i = torch.empty(k, dtype=torch.int64, device=cand_scores.device)
+        st = torch.cuda.current_stream().cuda_stream
+        _l.check(self._lib.osb_topk_merge_dev(1, cand_scores.shape[0], k, C.c_void_p(cand_scores.data_ptr()),
+                                              C.c_void_p(cand_ids.data_ptr()), C.c_void_p(self._offs.data_ptr()),
+                                              C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()), C.c_void_p(st)))
+        return out_s, out_i
+
+    def search(self, query: torch.Tensor, k: int):
+        """query: this rank's [dim] float32 tensor -> (scores [k], global ids [k]) for THIS rank's query."""
+        w = self.world
+        q_all = torch.empty(w, self.dim, dtype=torch.float32, device=query.device)
+        if w > 1:
+            dist.all_gather_into_tensor(q_all, query.reshape(1, self.dim).contiguous(), group=self.group)
+        else:
+            q_all.copy_(query.reshape(1, self.dim))
+        sc, ids = self._local_search(q_all, k)                       # [w queries, k] over my shard
+        if w > 1:
+            sc_all = torch.empty(w, w, k, dtype=torch.float32, device=query.device)     # [shard, query, k]
+            id_all = torch.empty(w, w, k, dtype=torch.int64, device=query.device)
+            dist.all_gather_into_tensor(sc_all.view(w * w, k), sc.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(id_all.view(w * w, k), ids.contiguous(), group=self.group)
+            sc, ids = sc_all[:, self.rank, :].contiguous(), id_all[:, self.rank, :].contiguous()
+        return self._merge(sc, ids, k)
+
+    def close(self):
+        if getattr(self, "_index", None) is not None:
+            self._index.close()
+            self._index = None

@@ -63,6 +63,69 @@ def test_db_full_size_property(gpu):
     assert (np.diff(D, axis=1) <= 0).all()                     # descending
 
 
+def test_db_streaming_path_with_ties(gpu):
+    """> 64 rows per CTA: the warp-per-row streaming kernel (the 50 k-row sweep's path), fused and unfused merge; exact
+    duplicates far apart must come back in ascending row order."""
+    n = 24000
+    db = synth.descriptor_db(n, 4096, 3)
+    db[23000] = db[5]; db[12000] = db[5]
+    idx = host.IndexFlatIP(4096, capacity=n); idx.add(db)
+    ref = fr.IndexFlatIP(4096); ref.add(db)
+    q = synth.noisy_queries(db, np.array([5, 9000, 23999]))
+    for k in (6, 10, 40):                                      # 296 CTAs x 40 candidates > 4096: separate merge kernel
+        D, I = idx.search(q, k)
+        Dr, Ir = ref.search(q, k)
+        assert np.array_equal(I, Ir), f"ids differ at k={k}"
+        assert np.allclose(D, Dr, rtol=1e-5, atol=1e-6)
+    assert idx.search(db[5][None], 3)[1][0].tolist() == [5, 12000, 23000]
+
+
+def test_db_repeated_searches_reuse_the_ticket(gpu):
+    """the fused merge's ticket counter must be back at zero after every search (same handle, many searches)."""
+    db = synth.descriptor_db(2000, 4096, 4)
+    idx = host.IndexFlatIP(4096, capacity=2048); idx.add(db)
+    ref = fr.IndexFlatIP(4096); ref.add(db)
+    for i in range(6):
+        q = synth.noisy_queries(db, np.array([i * 300, i * 300 + 1]))
+        assert np.array_equal(idx.search(q, 7)[1], ref.search(q, 7)[1])
+
+
+def test_row_sharded_merge(gpu):
+    """SURVEY 8e alternative: three shards scanned separately, candidates merged by osb_topk_merge_dev == unsharded."""
+    import ctypes as C
+    import torch
+    from omniswarm_b200 import swarm, lib
+    n, k = 1000, 8
+    db = synth.descriptor_db(n, 4096, 6)
+    db[900] = db[10]                                           # tie across shards
+    ref = fr.IndexFlatIP(4096); ref.add(db)
+    q = np.concatenate([synth.noisy_queries(db, np.array([10, 500])), db[900][None]])
+    Dr, Ir = ref.search(q, k)
+    spans = [swarm.shard_rows(n, r, 3) for r in range(3)]
+    cs, ci = [], []
+    for a, b in spans:
+        sh = host.IndexFlatIP(4096, capacity=b - a); sh.add(db[a:b])
+        D, I = sh.search(q, k)
+        cs.append(D); ci.append(I); sh.close()
+    cand_s = torch.from_numpy(np.stack(cs, 1).copy()).cuda()    # [nq][n_lists][k]
+    cand_i = torch.from_numpy(np.stack(ci, 1).copy()).cuda()
+    offs = torch.tensor([a for a, _ in spans], dtype=torch.int64).cuda()
+    out_s = torch.empty(3, k, dtype=torch.float32, device="cuda"); out_i = torch.empty(3, k, dtype=torch.int64, device="cuda")
+    L = lib.load()
+    lib.check(L.osb_topk_merge_dev(3, 3, k, C.c_void_p(cand_s.data_ptr()), C.c_void_p(cand_i.data_ptr()),
+                                   C.c_void_p(offs.data_ptr()), C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()),
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert np.array_equal(out_i.cpu().numpy(), Ir) and np.allclose(out_s.cpu().numpy(), Dr, rtol=1e-5, atol=1e-6)
+    assert out_i[2, :2].tolist() == [10, 900]
+    # the single-rank RowShardedIndex is the same machinery with one list
+    rs = swarm.RowShardedIndex(db, n, device="cuda")
+    s1, i1 = rs.search(torch.from_numpy(q[0]).cuda(), k)
+    torch.cuda.synchronize()
+    assert np.array_equal(i1.cpu().numpy(), Ir[0])
+    rs.close()
+
+
 def test_matcher_matches_oracle_and_cv2(gpu):
     m = host.BFMatcher(max_pairs=8, max_n=200)
     qs, ts = [], []
