@@ -171,7 +171,12 @@ typedef struct {
   double parameter_tolerance;    /* Ceres default 1e-8 */
   double pcg_tolerance;          /* relative residual of the inner solve */
   double initial_trust_radius;   /* Ceres default 1e4 */
+  int32_t preconditioner;        /* OSB_PRECOND_AUTO (chain block-tridiagonal when the graph fits the one-cluster fast
+                                    path, else block-Jacobi) or OSB_PRECOND_BLOCK_JACOBI */
+  int32_t reserved;
 } osb_solve_options;
+#define OSB_PRECOND_AUTO 0
+#define OSB_PRECOND_BLOCK_JACOBI 1
 
 typedef struct {
   double initial_cost;           /* 1/2 sum rho(|r|^2), as ceres Summary::initial_cost */
@@ -194,8 +199,14 @@ osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses, const uin
 /* profiling aid: SM-clock cycles block 0 spent in the phases of the LAST solve, summed over its CG iterations:
  * out[0] factor phase, [1] barrier after it, [2] node phase 1, [3] reduction 1, [4] node phase 2, [5] reduction 2,
  * [6] number of CG iterations, [7] whole kernel; [8] CTAs, [9] 1 = one thread-block cluster (hardware barrier) /
- * 0 = cooperative grid, [10] 1 = Jacobians in shared memory, [11] threads per CTA. */
+ * 0 = cooperative grid, [10] bit 0 = Jacobians in shared memory, bit 1 = chain preconditioner, [11] threads per CTA. */
 osb_status osb_solver_phase_cycles(osb_solver* h, double* out12);
+/* host-only (no GPU needed): the node numbering the solver uses for its chain preconditioner -- a greedy maximum-weight
+ * path cover of the factor graph (on a swarm graph: every drone's odometry chain).  order_out[i] = caller's node id of
+ * internal node i; link_out[i] = 1 iff internal node i-1 precedes i on its path and i % 16 != 0. */
+osb_status osb_solver_chain_plan(int n_nodes, const uint8_t* fixed, int n_factors, const int32_t* type,
+                                 const int32_t* ia, const int32_t* ib, const double* payload, int32_t* order_out,
+                                 uint8_t* link_out);
 /* residual + analytic Jacobian of every factor at `poses` (parity hook for the factor kernels):
  * r [n_factors][4], Ja/Jb [n_factors][4][4] (rows >= the factor's residual count are zero), un-robustified. */
 osb_status osb_solver_linearize(osb_solver* h, int n_nodes, const double* poses, int n_factors,

@@ -17,11 +17,12 @@ constexpr int DB_CHUNK_MAX = 512;  // rows per CTA
 
 // ---- shared tail of the scan kernels ----------------------------------------------------------------------------
 // (1) the CTA emits the top-k of its own rows by rank counting (score desc, row id asc);
-// (2) fused merge: the LAST CTA to finish (ticket counter) sorts the grid*k candidates of each query in shared memory
-//     (bitonic, 64-bit keys = inverted order-preserving score bits : row id) and writes the final k results -- no second
-//     launch, which at 10 k rows was a third of the search time.  Used when grid*k <= DB_MERGE_MAX; otherwise the host
-//     launches db_merge_kernel.
-constexpr int DB_MERGE_MAX = 4096;
+// (2) fused merge: the LAST CTA to finish (ticket counter) merges the per-CTA lists of each query in shared memory
+//     (64-bit keys = inverted order-preserving score bits : row id) and writes the final k results -- no second
+//     launch, which at 10 k rows was a third of the search time.  Used when k <= DB_FUSE_KMAX and grid <= DB_MERGE_MAX;
+//     otherwise the host launches db_merge_kernel.
+constexpr int DB_MERGE_MAX = 3584;       // heads + k*k candidate keys must fit the 32 KB key buffer
+constexpr int DB_FUSE_KMAX = 16;
 
 __device__ __forceinline__ unsigned long long db_key(float s, int64_t id) {
   if (id < 0) return ~0ull;
@@ -64,29 +65,45 @@ __device__ void db_emit_and_merge(const float* ss, int ss_stride, int nrows, int
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const int ncand = gridDim.x * k;
-  int n2 = 64;
-  while (n2 < ncand) n2 <<= 1;
+  // Every CTA's list is already in final order, so the global top-k can only come from the lists whose HEAD is among
+  // the k best heads: rank the G heads (G^2 / 512 comparisons per thread, shared-memory broadcasts), pull those <= k
+  // lists (k^2 candidates) and rank them.  Keys are unique (row ids are), so ranks are slots.
+  const int G = gridDim.x;
+  unsigned long long* heads = keys;                 // [G]
+  unsigned long long* cand = keys + G;              // [k*k]
+  __shared__ int s_sel[DB_FUSE_KMAX];
+  __shared__ int s_nsel;
   for (int qq = 0; qq < nq; ++qq) {
-    const float* ps = part_scores + (size_t)qq * ncand;
-    const int64_t* pi = part_ids + (size_t)qq * ncand;
+    const float* ps = part_scores + (size_t)qq * G * k;
+    const int64_t* pi = part_ids + (size_t)qq * G * k;
     __syncthreads();
-    for (int i = tid; i < n2; i += nthr) keys[i] = (i < ncand) ? db_key(__ldcg(ps + i), __ldcg(pi + i)) : ~0ull;
+    if (tid == 0) s_nsel = 0;
+    for (int b = tid; b < G; b += nthr) heads[b] = db_key(__ldcg(ps + (size_t)b * k), __ldcg(pi + (size_t)b * k));
     __syncthreads();
-    for (int size = 2; size <= n2; size <<= 1)
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int t = tid; t < (n2 >> 1); t += nthr) {
-          const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-          const unsigned long long a = keys[lo], b = keys[hi];
-          if ((a > b) == ((lo & size) == 0)) { keys[lo] = b; keys[hi] = a; }
-        }
-        __syncthreads();
+    for (int b = tid; b < G; b += nthr) {
+      const unsigned long long kb = heads[b];
+      if (kb == ~0ull) continue;
+      int rank = 0;
+      for (int j = 0; j < G; ++j) rank += heads[j] < kb;
+      if (rank < k) { s_sel[rank] = b; atomicMax(&s_nsel, rank + 1); }
+    }
+    __syncthreads();
+    const int nsel = s_nsel, nc = nsel * k;
+    for (int i = tid; i < nc; i += nthr) {
+      const size_t src = (size_t)s_sel[i / k] * k + (i % k);
+      cand[i] = db_key(__ldcg(ps + src), __ldcg(pi + src));
+    }
+    for (int i = tid; i < k; i += nthr) { out_scores[qq * k + i] = -INFINITY; out_ids[qq * k + i] = -1; }
+    __syncthreads();
+    for (int i = tid; i < nc; i += nthr) {
+      const unsigned long long ki = cand[i];
+      if (ki == ~0ull) continue;
+      int rank = 0;
+      for (int j = 0; j < nc; ++j) rank += cand[j] < ki;
+      if (rank < k) {
+        out_scores[qq * k + rank] = db_key_score(ki);
+        out_ids[qq * k + rank] = (int64_t)(unsigned)(ki & 0xffffffffull);
       }
-    for (int i = tid; i < k; i += nthr) {
-      const unsigned long long key = keys[i];
-      const bool ok = key != ~0ull;
-      out_scores[qq * k + i] = ok ? db_key_score(key) : -INFINITY;
-      out_ids[qq * k + i] = ok ? (int64_t)(unsigned)(key & 0xffffffffull) : -1;
     }
   }
   if (tid == 0) *done = 0;                                     // ready for the next search on this scratch
@@ -280,7 +297,7 @@ static osb_status launch_scan(const float* db, int64_t n, const int64_t* n_dev, 
                               int k, int grid, bool coop, float* ps, int64_t* pi, float* os, int64_t* oi,
                               unsigned int* done, int fuse, cudaStream_t st) {
   constexpr int R = 4;
-  const size_t merge_bytes = fuse ? (size_t)DB_MERGE_MAX * sizeof(unsigned long long) : 0;
+  const size_t merge_bytes = fuse ? (size_t)(DB_MERGE_MAX + DB_FUSE_KMAX * DB_FUSE_KMAX) * sizeof(unsigned long long) : 0;
   if (coop) {
     const size_t smem = std::max(merge_bytes, (size_t)(DB_THREADS / 32 + 1) * DB_COOP_CHUNK * Q * sizeof(float));
     static bool attr_done = false;
@@ -326,7 +343,7 @@ osb_status db_search_device(const float* rows, int64_t n, const int64_t* n_dev, 
   // small databases: every warp of a CTA shares each row (db_scan_coop_kernel); a CTA never gets more than 64 rows
   const bool coop = (dim == DB_COOP_DIM) && chunk <= DB_COOP_CHUNK;
   if (coop) grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, n));
-  const int fuse = (done != nullptr && (int64_t)grid * k <= DB_MERGE_MAX) ? 1 : 0;
+  const int fuse = (done != nullptr && k <= DB_FUSE_KMAX && grid <= DB_MERGE_MAX) ? 1 : 0;
   for (int q0 = 0; q0 < nq; q0 += 8) {
     const int nb = min(8, nq - q0);
     const float* qp = q_dev + (size_t)q0 * dim;

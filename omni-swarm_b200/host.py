@@ -243,7 +243,25 @@ class PoseGraphSolver:
         _l.check(self._lib.osb_solver_phase_cycles(self._h, _l.ptr(c)))
         names = ["factor", "barrier", "node1", "reduce1", "node2", "reduce2", "cg_iterations", "kernel", "ctas",
                  "cluster", "j_in_smem", "threads"]
-        return dict(zip(names, c.tolist()))
+        d = dict(zip(names, c.tolist()))
+        d["chain_preconditioner"] = float(int(d["j_in_smem"]) >> 1)
+        d["j_in_smem"] = float(int(d["j_in_smem"]) & 1)
+        return d
+
+    @staticmethod
+    def chain_plan(g: dict):
+        """Host-only: the solver's internal node numbering (greedy maximum-weight path cover) ->
+        (order [n] internal -> caller's node id, link [n] uint8)."""
+        lib = _l.load()
+        fixed = np.ascontiguousarray(g["fixed"], np.uint8)
+        ftype = np.ascontiguousarray(g["ftype"], np.int32)
+        ia = np.ascontiguousarray(g["ia"], np.int32); ib = np.ascontiguousarray(g["ib"], np.int32)
+        payload = np.ascontiguousarray(g["payload"], np.float64)
+        n = fixed.shape[0]
+        order = np.zeros(n, np.int32); link = np.zeros(n, np.uint8)
+        _l.check(lib.osb_solver_chain_plan(n, _l.ptr(fixed), len(ftype), _l.ptr(ftype), _l.ptr(ia), _l.ptr(ib),
+                                           _l.ptr(payload), _l.ptr(order), _l.ptr(link)))
+        return order, link
 
     def linearize(self, g: dict, poses: np.ndarray):
         _, ftype, ia, ib, payload, _ = self._arrays(g)

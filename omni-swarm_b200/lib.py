@@ -29,7 +29,7 @@ class SolveOptions(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("max_pcg_iterations", C.c_int32), ("max_time_s", C.c_double),
                 ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
                 ("parameter_tolerance", C.c_double), ("pcg_tolerance", C.c_double),
-                ("initial_trust_radius", C.c_double)]
+                ("initial_trust_radius", C.c_double), ("preconditioner", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SolveSummary(C.Structure):
@@ -101,6 +101,7 @@ _SIG = {
     "osb_solver_destroy": (C.c_int, [_P]),
     "osb_solver_solve": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]),
     "osb_solver_phase_cycles": (C.c_int, [_P, _P]),
+    "osb_solver_chain_plan": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P]),
     "osb_solver_linearize": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "osb_frontend_create": (C.c_int, [C.POINTER(_P), C.POINTER(FrontendConfig), _P, C.c_size_t, _P, _P, _P, C.c_size_t]),
     "osb_frontend_destroy": (C.c_int, [_P]),

@@ -92,3 +92,34 @@ def test_solve_c5_full_size_properties(solver):
     assert np.abs(poses[:, :3] - g["gt"][:, :3]).max() < 0.5
     p2, s2 = solver.solve(g, init=poses)
     assert s2.iterations <= 3 and np.abs(p2 - poses).max() < 1e-3
+
+
+def test_chain_preconditioner_same_answer_fewer_iterations(solver):
+    """The chain (block-tridiagonal path) preconditioner and block-Jacobi solve the same normal equations: converged
+    poses agree, the inner iteration count drops several-fold, and node ids in arbitrary order (the path cover has to find
+    the chains) change nothing."""
+    g = synth.pose_graph_c5(0)
+    o_bj = solver.default_options(); o_bj.preconditioner = 1
+    p_bj, s_bj = solver.solve(g, o_bj)
+    assert solver.phase_cycles()["chain_preconditioner"] == 0.0
+    p_ch, s_ch = solver.solve(g)
+    assert solver.phase_cycles()["chain_preconditioner"] == 1.0
+    assert s_ch.termination in (0, 1, 2)
+    assert abs(s_ch.final_cost - s_bj.final_cost) < 1e-5 * s_bj.final_cost
+    assert np.abs(p_ch - p_bj).max() < 2e-2                   # both stopped by the Ceres-default function tolerance
+    assert s_ch.pcg_iterations * 3 < s_bj.pcg_iterations, (s_ch.pcg_iterations, s_bj.pcg_iterations)
+    # tight solves agree to parity tolerance
+    pt_ch, st_ch = solver.solve(g, tight(solver))
+    ot = tight(solver); ot.preconditioner = 1
+    pt_bj, st_bj = solver.solve(g, ot)
+    assert np.abs(pt_ch - pt_bj).max() < 1e-5 and abs(st_ch.final_cost - st_bj.final_cost) < 1e-8 * st_bj.final_cost
+    # shuffled node numbering
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(g["n_nodes"])
+    g2 = dict(g)
+    g2["ia"] = perm[g["ia"]].astype(np.int32); g2["ib"] = perm[g["ib"]].astype(np.int32)
+    for key in ("init", "gt", "fixed"):
+        arr = np.empty_like(g[key]); arr[perm] = g[key]; g2[key] = arr
+    p2, s2 = solver.solve(g2, tight(solver))
+    assert np.abs(p2[perm] - pt_ch).max() < 1e-5
+    assert s2.pcg_iterations < 2 * st_ch.pcg_iterations + 50

@@ -27,3 +27,35 @@ def test_descriptor_db_unit_norm():
     assert np.allclose(np.linalg.norm(db, axis=1), 1.0, atol=1e-5)
     q = synth.noisy_queries(db, np.array([5, 6]))
     assert ((db @ q.T).argmax(0) == [5, 6]).all() and (db[[5, 6]] * q).sum(1).min() > 0.8
+
+
+def test_solver_chain_plan_recovers_odometry_chains():
+    """Host logic of the chain preconditioner (no GPU): the greedy path cover must be a permutation, every link must be
+    backed by a factor between the two nodes, links never cross a 16-node boundary, fixed nodes come last, and on the
+    swarm graph the odometry chains are recovered (almost every free node is linked to its predecessor)."""
+    from omniswarm_b200 import host, synth
+    g = synth.pose_graph(5, 40, seed=3)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(g["n_nodes"])                       # caller's node ids in arbitrary order
+    g2 = dict(g)
+    g2["ia"] = perm[g["ia"]].astype(np.int32); g2["ib"] = perm[g["ib"]].astype(np.int32)
+    fixed = np.zeros_like(g["fixed"]); fixed[perm[np.nonzero(g["fixed"])[0]]] = 1
+    g2["fixed"] = fixed
+    order, link = host.PoseGraphSolver.chain_plan(g2)
+    n = g["n_nodes"]
+    assert sorted(order.tolist()) == list(range(n))
+    n_fixed = int(fixed.sum())
+    assert fixed[order[n - n_fixed:]].all() and not fixed[order[:n - n_fixed]].any()
+    pairs = {(int(a), int(b)) for a, b in zip(g2["ia"], g2["ib"])} | {(int(b), int(a)) for a, b in zip(g2["ia"], g2["ib"])}
+    for i in np.nonzero(link)[0]:
+        assert i % 16 != 0
+        assert (int(order[i - 1]), int(order[i])) in pairs
+    free = n - n_fixed
+    # 5 chains of 40 (one starts at the fixed node): all but the path starts and the 16-boundaries are linked
+    assert link.sum() >= free - 5 - free // 16 - 1
+    # the links follow ego-motion edges: consecutive frames of the same drone in the ORIGINAL numbering
+    inv = np.argsort(perm)
+    orig = inv[order]
+    lk = np.nonzero(link)[0]
+    same_drone = (orig[lk] % 5) == (orig[lk - 1] % 5)
+    assert same_drone.mean() > 0.95 and (np.abs(orig[lk] // 5 - orig[lk - 1] // 5)[same_drone] == 1).all()
