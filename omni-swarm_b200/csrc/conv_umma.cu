@@ -157,20 +157,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  // programmatic dependent launch: the next layer's CTAs may be scheduled as ours retire (they still wait for this whole
+  // grid in their own griddepcontrol.wait before touching activations)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int as = 0; uint32_t aph = 0;
     int bs = 0; uint32_t bph = 0;
     if (RES) {
-      // all 9 taps (one 64-channel slab) once: slot t holds tap t
-      for (int t = 0; t < 9; ++t) {
-        const uint32_t sb = b_base + t * Cfg::B_SLOT;
-        mbar_expect_tx(b_full(t), Cfg::B_SLOT);
-        tma_load_3d(sb, &tm_w_hi, b_full(t), 0, P.n_off, t);
-        tma_load_3d(sb + Cfg::B_BYTES, &tm_w_lo, b_full(t), 0, P.n_off, t);
-      }
+      // all 9 taps (one 64-channel slab) once: slot t holds tap t.  Issued in the order the MMA warp first needs them
+      // (kx outer, ky inner) and BEFORE the dependency wait: weights are constants, so with programmatic dependent launch
+      // they stream in while the previous layer is still draining.
+      for (int kx = 0; kx < 3; ++kx)
+        for (int ky = 0; ky < 3; ++ky) {
+          const int t = ky * 3 + kx;
+          const uint32_t sb = b_base + t * Cfg::B_SLOT;
+          mbar_expect_tx(b_full(t), Cfg::B_SLOT);
+          tma_load_3d(sb, &tm_w_hi, b_full(t), 0, P.n_off, t);
+          tma_load_3d(sb + Cfg::B_BYTES, &tm_w_lo, b_full(t), 0, P.n_off, t);
+        }
     }
+    // the activations are the previous kernel's output: wait for the whole grid we depend on (no-op without PDL)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
       const int x0 = tx * UM_TW, y0 = ty * UM_TH;
@@ -208,8 +217,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     int as = 0; uint32_t aph = 0;
     int bs = 0; uint32_t bph = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    if (RES)
-      for (int t = 0; t < 9; ++t) mbar_wait(b_full(t), 0);
+    bool first_tile = true;                                    // RES: a tap's weights are awaited the first time it is used
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
@@ -224,6 +232,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           for (int ky = 0; ky < P.ks; ++ky) {
             uint32_t sb;
             if (RES) {
+              if (first_tile) { mbar_wait(b_full(ky * 3 + kx), 0); tc_fence_after(); }
               sb = b_base + (ky * 3 + kx) * Cfg::B_SLOT;
             } else {
               mbar_wait(b_full(bs), bph);
@@ -261,6 +270,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
       }
       umma_commit(tfull_bar(acc));                               // accumulators complete -> epilogue
+      first_tile = false;
       if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -542,6 +552,9 @@ osb_status umma_act_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half*
   return make_tmap(lo, p_lo, 4, dims, strides, box);
 }
 
+// OSB_CONV_PDL=0 launches the convolutions without programmatic dependent launch (A/B switch)
+static const bool g_conv_pdl = [] { const char* e = getenv("OSB_CONV_PDL"); return !(e && atoi(e) == 0); }();
+
 template <int N, bool RES>
 static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const UmmaLayer& L, const UmmaArgs& P,
                               cudaStream_t st, int max_ctas) {
@@ -554,8 +567,14 @@ static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, 
   const int tiles = P.B * cdiv(P.W, UM_TW) * cdiv(P.H, UM_TH);
   // persistent CTAs, one per SM; `max_ctas` leaves SMs free for a kernel running beside this one on another stream
   const int grid = std::min(tiles, max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms());
-  OSB_LAUNCH((conv_umma_kernel<N, RES>), grid, 256, Cfg::SMEM_BYTES, st, a_hi, a_lo, L.tm_hi, L.tm_lo, P);
-  OSB_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_conv_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<N, RES>, a_hi, a_lo, L.tm_hi, L.tm_lo, P));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return OSB_OK;
 }
 

@@ -310,30 +310,34 @@ __device__ __forceinline__ void mat4_mul(const double* A, const double* B, doubl
 // Warp-collective: every lane of the warp must call it.
 __device__ __forceinline__ void chain_apply(const double (&Si)[16], const double (&L)[16], bool link, int sl,
                                             const double (&r)[4], double (&z)[4]) {
+  // Branch-free on purpose: a divergent `if` between two shuffles sends the warp through the compiler's
+  // WARPSYNC.COLLECTIVE slow path for every following shuffle (measured: 50 k cycles per application instead of 2 k).
+  // The active lane of a step is selected by a 0/1 multiplier; L is zero on lanes without a predecessor link.
+  __syncwarp();
   double y[4] = {r[0], r[1], r[2], r[3]};
+#pragma unroll
   for (int s = 1; s < 16; ++s) {                       // forward: y_i = r_i - L_i y_{i-1}
     double yp[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) yp[k] = __shfl_up_sync(0xffffffffu, y[k], 1);
-    if (sl == s && link) {
+    const double m = (sl == s && link) ? 1.0 : 0.0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) y[i] -= L[i * 4] * yp[0] + L[i * 4 + 1] * yp[1] + L[i * 4 + 2] * yp[2] + L[i * 4 + 3] * yp[3];
-    }
+    for (int i = 0; i < 4; ++i)
+      y[i] -= m * (L[i * 4] * yp[0] + L[i * 4 + 1] * yp[1] + L[i * 4 + 2] * yp[2] + L[i * 4 + 3] * yp[3]);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) z[i] = Si[i * 4] * y[0] + Si[i * 4 + 1] * y[1] + Si[i * 4 + 2] * y[2] + Si[i * 4 + 3] * y[3];
-  for (int s = 14; s >= 0; --s) {                      // backward: z_i = S_i^-1 y_i - L_{i+1}^T z_{i+1}
-    double u[4] = {0.0, 0.0, 0.0, 0.0};
-    if (sl == s + 1 && link) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) u[j] = L[j] * z[0] + L[4 + j] * z[1] + L[8 + j] * z[2] + L[12 + j] * z[3];
-    }
+  for (int s = 14; s >= 0; --s) {                      // backward: z_i = S_i^-1 y_i - L_{i+1}^T z_{i+1}
+    const double m = (sl == s + 1 && link) ? 1.0 : 0.0;
+    double u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = m * (L[j] * z[0] + L[4 + j] * z[1] + L[8 + j] * z[2] + L[12 + j] * z[3]);
 #pragma unroll
     for (int k = 0; k < 4; ++k) u[k] = __shfl_down_sync(0xffffffffu, u[k], 1);
-    if (sl == s) {
+    const double mz = (sl == s) ? 1.0 : 0.0;           // (lane 15 receives lane 16's u, which is zero: sl = 0 there)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) z[k] -= u[k];
-    }
+    for (int k = 0; k < 4; ++k) z[k] -= mz * u[k];
   }
 }
 
@@ -546,6 +550,7 @@ graph_solve_kernel(SolverDev P) {
       for (int i = 0; i < 16; ++i) Lr[i] = 0.0;
       for (int s = 0; s < 16; ++s) {
         double Sp[16];
+        __syncwarp();                                              // converge after the previous step's divergent block
 #pragma unroll
         for (int i = 0; i < 16; ++i) Sp[i] = __shfl_up_sync(0xffffffffu, Mi[i], 1);
         if (sl == s) {
