@@ -173,10 +173,16 @@ typedef struct {
   double initial_trust_radius;   /* Ceres default 1e4 */
   int32_t preconditioner;        /* OSB_PRECOND_AUTO (chain block-tridiagonal when the graph fits the one-cluster fast
                                     path, else block-Jacobi) or OSB_PRECOND_BLOCK_JACOBI */
-  int32_t reserved;
+  int32_t inner_precision;       /* arithmetic INSIDE the PCG (Jacobian blocks, direction/residual vectors, preconditioner):
+                                    OSB_INNER_AUTO = fp32 when pcg_tolerance >= 1e-4 (LM only needs an inexact step; fp64
+                                    FMA issues ~50x slower than fp32 on this GPU), else fp64.  Residuals, costs, gradient,
+                                    poses and all LM decisions are always fp64. */
 } osb_solve_options;
 #define OSB_PRECOND_AUTO 0
 #define OSB_PRECOND_BLOCK_JACOBI 1
+#define OSB_INNER_AUTO 0
+#define OSB_INNER_FP64 1
+#define OSB_INNER_FP32 2
 
 typedef struct {
   double initial_cost;           /* 1/2 sum rho(|r|^2), as ceres Summary::initial_cost */
@@ -199,7 +205,8 @@ osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses, const uin
 /* profiling aid: SM-clock cycles block 0 spent in the phases of the LAST solve, summed over its CG iterations:
  * out[0] factor phase, [1] barrier after it, [2] node phase 1, [3] reduction 1, [4] node phase 2, [5] reduction 2,
  * [6] number of CG iterations, [7] whole kernel; [8] CTAs, [9] 1 = one thread-block cluster (hardware barrier) /
- * 0 = cooperative grid, [10] bit 0 = Jacobians in shared memory, bit 1 = chain preconditioner, [11] threads per CTA. */
+ * 0 = cooperative grid, [10] bit 0 = Jacobians in shared memory, bit 1 = chain preconditioner, bit 2 = fp32 inner
+ * arithmetic, [11] threads per CTA. */
 osb_status osb_solver_phase_cycles(osb_solver* h, double* out12);
 /* host-only (no GPU needed): the node numbering the solver uses for its chain preconditioner -- a greedy maximum-weight
  * path cover of the factor graph (on a swarm graph: every drone's odometry chain).  order_out[i] = caller's node id of

@@ -166,17 +166,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     int as = 0; uint32_t aph = 0;
     int bs = 0; uint32_t bph = 0;
     if (RES) {
-      // all 9 taps (one 64-channel slab) once: slot t holds tap t.  Issued in the order the MMA warp first needs them
-      // (kx outer, ky inner) and BEFORE the dependency wait: weights are constants, so with programmatic dependent launch
-      // they stream in while the previous layer is still draining.
-      for (int kx = 0; kx < 3; ++kx)
-        for (int ky = 0; ky < 3; ++ky) {
-          const int t = ky * 3 + kx;
-          const uint32_t sb = b_base + t * Cfg::B_SLOT;
-          mbar_expect_tx(b_full(t), Cfg::B_SLOT);
-          tma_load_3d(sb, &tm_w_hi, b_full(t), 0, P.n_off, t);
-          tma_load_3d(sb + Cfg::B_BYTES, &tm_w_lo, b_full(t), 0, P.n_off, t);
-        }
+      // all 9 taps (one 64-channel slab) once: slot t holds tap t.  Issued BEFORE the dependency wait: weights are
+      // constants, so under programmatic dependent launch they stream in while the previous layer is still draining.
+      for (int t = 0; t < 9; ++t) {
+        const uint32_t sb = b_base + t * Cfg::B_SLOT;
+        mbar_expect_tx(b_full(t), Cfg::B_SLOT);
+        tma_load_3d(sb, &tm_w_hi, b_full(t), 0, P.n_off, t);
+        tma_load_3d(sb + Cfg::B_BYTES, &tm_w_lo, b_full(t), 0, P.n_off, t);
+      }
     }
     // the activations are the previous kernel's output: wait for the whole grid we depend on (no-op without PDL)
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -217,7 +214,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     int as = 0; uint32_t aph = 0;
     int bs = 0; uint32_t bph = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    bool first_tile = true;                                    // RES: a tap's weights are awaited the first time it is used
+    if (RES)
+      for (int t = 0; t < 9; ++t) mbar_wait(b_full(t), 0);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
@@ -232,7 +230,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           for (int ky = 0; ky < P.ks; ++ky) {
             uint32_t sb;
             if (RES) {
-              if (first_tile) { mbar_wait(b_full(ky * 3 + kx), 0); tc_fence_after(); }
               sb = b_base + (ky * 3 + kx) * Cfg::B_SLOT;
             } else {
               mbar_wait(b_full(bs), bph);
@@ -270,7 +267,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
       }
       umma_commit(tfull_bar(acc));                               // accumulators complete -> epilogue
-      first_tile = false;
       if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -552,8 +548,10 @@ osb_status umma_act_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half*
   return make_tmap(lo, p_lo, 4, dims, strides, box);
 }
 
-// OSB_CONV_PDL=0 launches the convolutions without programmatic dependent launch (A/B switch)
-static const bool g_conv_pdl = [] { const char* e = getenv("OSB_CONV_PDL"); return !(e && atoi(e) == 0); }();
+// OSB_CONV_PDL=1 launches the convolutions with programmatic dependent launch.  Off by default: measured (r01f) it
+// costs throughput here -- the dependent layer's CTAs take the SMs the concurrent NetVLAD stream was filling
+// (2.10 ms per keyframe with it, 1.93 ms without).
+static const bool g_conv_pdl = [] { const char* e = getenv("OSB_CONV_PDL"); return e && atoi(e) != 0; }();
 
 template <int N, bool RES>
 static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const UmmaLayer& L, const UmmaArgs& P,

@@ -29,7 +29,6 @@ constexpr int GS_THREADS = 256;           // 255 registers per thread: the CG fa
 constexpr int GS_KF = 3;                  // factors per thread on the fast path (16 CTAs x 256 threads x 3 >= 12 288 factors)
 constexpr int GS_MAX_CLUSTER = 16;
 constexpr int GS_SMEM_J_MAX = 200 * 1024;   // bytes of shared memory a CTA may spend on its Jacobian block
-constexpr int GS_SMEM_CHAIN = 16 * GS_THREADS * 8;   // L_i of the chain preconditioner, [16][GS_THREADS] doubles
 constexpr int GS_SMEM_DYN_MAX = 227 * 1024 - 2048;  // opt-in limit minus the kernel's static shared memory
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kTwoPi = 6.28318530717958647692;
@@ -38,11 +37,15 @@ __device__ __forceinline__ double normalize_angle(double a) {   // factors.hpp:3
   return a - kTwoPi * floor((a + kPi) / kTwoPi);
 }
 
-// residual (nr rows) and 4x4 Jacobian blocks (row-major, rows >= nr zero) of one factor, un-robustified
-__device__ int linearize_factor(int type, const double* __restrict__ pa, const double* __restrict__ pb,
-                                const double* __restrict__ pl, double r[4], double Ja[16], double Jb[16]) {
+// residual (nr rows) and 4x4 Jacobian blocks (row-major, rows >= nr zero) of one factor, un-robustified.
+// JAC = false: residual only (trial-point cost; identical arithmetic for r).
+template <bool JAC>
+__device__ __forceinline__ int linearize_factor_t(int type, const double* __restrict__ pa, const double* __restrict__ pb,
+                                                  const double* __restrict__ pl, double r[4], double Ja[16], double Jb[16]) {
+  if (JAC) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { Ja[i] = 0.0; Jb[i] = 0.0; }
+    for (int i = 0; i < 16; ++i) { Ja[i] = 0.0; Jb[i] = 0.0; }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) r[i] = 0.0;
   if (type == OSB_FACTOR_DISTANCE) {
@@ -157,6 +160,26 @@ __device__ int linearize_factor(int type, const double* __restrict__ pa, const d
   return nr;
 }
 
+__device__ __forceinline__ int linearize_factor(int type, const double* __restrict__ pa, const double* __restrict__ pb,
+                                                const double* __restrict__ pl, double r[4], double Ja[16], double Jb[16]) {
+  return linearize_factor_t<true>(type, pa, pb, pl, r, Ja, Jb);
+}
+// |r|^2 only (un-robustified): the Jacobian arithmetic of the inlined body is dead code here
+__device__ __forceinline__ double factor_sqnorm(int type, const double* __restrict__ pa, const double* __restrict__ pb,
+                                                const double* __restrict__ pl) {
+  double r[4], Ja[16], Jb[16];
+  linearize_factor_t<false>(type, pa, pb, pl, r, Ja, Jb);
+  return r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+}
+
+// The inner (PCG) arithmetic type.  Measured on this B200 (scripts/microbench/fp64_rate.cu): an SM issues one DFMA
+// warp-instruction every ~12 cycles but ~4 FFMA warp-instructions per cycle, and with the fp64 version of this kernel the
+// CG iteration was bound by exactly that pipe (2300 DFMA warp-instructions per SM per iteration ~ 28 k of 35 k cycles).
+// Levenberg-Marquardt only needs an INEXACT step (relative residual 1e-2), so everything inside the PCG -- Jacobian
+// blocks, direction / residual / preconditioner vectors, the chain factorisation -- runs in fp32 when the requested
+// pcg_tolerance allows (>= 1e-4); residuals, costs, the gradient J^T r, the diagonal, the poses and every LM decision stay
+// fp64.  A numpy emulation of the same loop gives the same iteration counts and poses within 1e-8 of the all-fp64 solve
+// (DESIGN.md).  T = double is kept for tight tolerances (parity tests).
 struct SolverDev {
   int n, m;
   int fpc;                 // factors per CTA (contiguous block of the factor list)
@@ -169,9 +192,11 @@ struct SolverDev {
   const int32_t* slot_a; const int32_t* slot_b;   // slot of factor f's contribution to its node a / node b
   // state
   double* x[2];            // pose buffers (current / trial), [n][4]
-  double* Jg;              // global Jacobian store, SoA [32][m] (used when the CTA block does not fit shared memory)
-  double *g, *D, *Hnn, *Minv, *p, *z, *res, *Ap, *delta;   // node vectors
-  double* cs;              // contribution slots [2m][4]
+  void* Jg;                // global Jacobian store, SoA [32][m] of T (used when the CTA block does not fit shared memory)
+  double *g, *D, *Hnn;     // gradient, LM diagonal, diagonal Hessian blocks (fp64)
+  void *Minv, *p, *z, *res, *Ap, *delta;   // PCG node vectors, element type T
+  double* gs;              // gradient contribution slots [2m][4] (fp64, written at a linearisation)
+  void* cs;                // PCG contribution slots [2m][4] of T
   double* hs;              // Hessian-diagonal-block slots [2m][16] (only touched at a re-linearisation)
   double* partial;         // [2][4][grid]
   osb_solve_options opt;
@@ -191,14 +216,24 @@ __device__ __forceinline__ void all_sync(const SolverDev& P, cg::grid_group& gri
   if (P.use_cluster) cg::this_cluster().sync(); else grid.sync();
 }
 
-template <int K>
-__device__ void grid_reduce_sum(double (&v)[K], const SolverDev& P, int parity, double* sh, cg::grid_group& grid) {
+__device__ __forceinline__ float warp_sum_t(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_t(double v) { return warp_sum_d(v); }
+
+// grid-wide sums of K values.  The warp level runs in T (cheap in fp32), the 8 warp sums, the CTA partials and the final
+// sum are fp64 (a handful of instructions on warp 0 only).
+template <int K, typename T>
+__device__ void grid_reduce_sum(T (&vin)[K], double (&v)[K], const SolverDev& P, int parity, double* sh, cg::grid_group& grid) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = GS_THREADS / 32, G = gridDim.x;
   double* pbuf = P.partial + (size_t)parity * 4 * G;
+  __syncwarp();
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const double w = warp_sum_d(v[k]);
-    if (lane == 0) sh[k * 32 + warp] = w;
+    const T w = warp_sum_t(vin[k]);
+    if (lane == 0) sh[k * 32 + warp] = (double)w;
   }
   __syncthreads();
   if (warp == 0) {
@@ -227,6 +262,7 @@ __device__ void grid_reduce_sum(double (&v)[K], const SolverDev& P, int parity, 
 
 __device__ double grid_reduce_max(double vmax, const SolverDev& P, int parity, double* sh, cg::grid_group& grid) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = gridDim.x;
+  __syncwarp();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
   if (lane == 0) sh[warp] = vmax;
@@ -253,27 +289,46 @@ __device__ double grid_reduce_max(double vmax, const SolverDev& P, int parity, d
 }
 
 // Jacobian store accessor: element i (0..31: Ja row-major then Jb) of the factor with CTA-local index `li`
+template <typename T>
 struct JStore {
-  double* base; int stride; int off;
-  __device__ __forceinline__ double& at(int i, int li) const { return base[(size_t)i * stride + off + li]; }
+  T* base; int stride; int off;
+  __device__ __forceinline__ T& at(int i, int li) const { return base[(size_t)i * stride + off + li]; }
 };
 
+// vector loads / stores of a node's 4-vector (one 16-byte access in fp32, two in fp64), L2-coherent
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
+  const double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+  __stcg(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+}
+__device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
+  __stcg(reinterpret_cast<double2*>(p), make_double2(v[0], v[1]));
+  __stcg(reinterpret_cast<double2*>(p) + 1, make_double2(v[2], v[3]));
+}
+
 // 4x4 SPD inverse by Gauss-Jordan (no pivoting: the LM term keeps the diagonal positive)
-__device__ void inv4(const double* __restrict__ M, double* __restrict__ out) {
-  double a[4][8];
+template <typename T>
+__device__ void inv4(const T* __restrict__ M, T* __restrict__ out) {
+  T a[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { a[i][j] = M[i * 4 + j]; a[i][4 + j] = (i == j) ? 1.0 : 0.0; }
+    for (int j = 0; j < 4; ++j) { a[i][j] = M[i * 4 + j]; a[i][4 + j] = (i == j) ? T(1) : T(0); }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const double piv = 1.0 / a[c][c];
+    const T piv = T(1) / a[c][c];
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[c][j] *= piv;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (i == c) continue;
-      const double f = a[i][c];
+      const T f = a[i][c];
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[i][j] -= f * a[c][j];
     }
@@ -284,7 +339,6 @@ __device__ void inv4(const double* __restrict__ M, double* __restrict__ out) {
     for (int j = 0; j < 4; ++j) out[i * 4 + j] = a[i][4 + j];
 }
 
-
 // ---- chain preconditioner -----------------------------------------------------------------------------------------
 // Block-Jacobi sees only a node's own 4x4 block, and a pose graph is dominated by long odometry chains: C5 needs 1663
 // PCG iterations that way.  The host covers the graph with vertex-disjoint paths (heaviest factors first) and numbers the
@@ -293,13 +347,14 @@ __device__ void inv4(const double* __restrict__ M, double* __restrict__ out) {
 //   M = sum over chain factors (full 8x8 contribution) + sum over the other factors (their two diagonal blocks) + lam D,
 // a sum of PSD terms plus a positive diagonal, hence SPD.  Factorisation M = (I + L) S (I + L)^T by a 16-step sweep over
 // the half-warp (once per PCG solve); application z = M^-1 r = 15 forward + 15 backward steps of 4-vector shuffles.
-// Same CPU emulation as the kernel: 1663 -> 404 PCG iterations on C5.
-__device__ __forceinline__ void mat4_mul(const double* A, const double* B, double* C) {        // C = A B
+// Same CPU emulation as the kernel: 1663 -> 385 PCG iterations on C5.
+template <typename T>
+__device__ __forceinline__ void mat4_mul(const T* A, const T* B, T* C) {        // C = A B
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      double a = 0.0;
+      T a = T(0);
 #pragma unroll
       for (int k = 0; k < 4; ++k) a += A[i * 4 + k] * B[k * 4 + j];
       C[i * 4 + j] = a;
@@ -308,19 +363,18 @@ __device__ __forceinline__ void mat4_mul(const double* A, const double* B, doubl
 
 // z = M^-1 r for the segment this half-warp owns.  Si = S_i^-1, L = L_i (zero when the node has no predecessor link).
 // Warp-collective: every lane of the warp must call it.
-__device__ __forceinline__ void chain_apply(const double (&Si)[16], const double (&L)[16], bool link, int sl,
-                                            const double (&r)[4], double (&z)[4]) {
-  // Branch-free on purpose: a divergent `if` between two shuffles sends the warp through the compiler's
-  // WARPSYNC.COLLECTIVE slow path for every following shuffle (measured: 50 k cycles per application instead of 2 k).
-  // The active lane of a step is selected by a 0/1 multiplier; L is zero on lanes without a predecessor link.
+template <typename T>
+__device__ __forceinline__ void chain_apply(const T (&Si)[16], const T (&L)[16], bool link, int sl, const T (&r)[4], T (&z)[4]) {
+  // Branch-free on purpose (no divergent code between two shuffles): the active lane of a step is selected by a 0/1
+  // multiplier; L is zero on lanes without a predecessor link.
   __syncwarp();
-  double y[4] = {r[0], r[1], r[2], r[3]};
+  T y[4] = {r[0], r[1], r[2], r[3]};
 #pragma unroll
   for (int s = 1; s < 16; ++s) {                       // forward: y_i = r_i - L_i y_{i-1}
-    double yp[4];
+    T yp[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) yp[k] = __shfl_up_sync(0xffffffffu, y[k], 1);
-    const double m = (sl == s && link) ? 1.0 : 0.0;
+    const T m = (sl == s && link) ? T(1) : T(0);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       y[i] -= m * (L[i * 4] * yp[0] + L[i * 4 + 1] * yp[1] + L[i * 4 + 2] * yp[2] + L[i * 4 + 3] * yp[3]);
@@ -329,21 +383,23 @@ __device__ __forceinline__ void chain_apply(const double (&Si)[16], const double
   for (int i = 0; i < 4; ++i) z[i] = Si[i * 4] * y[0] + Si[i * 4 + 1] * y[1] + Si[i * 4 + 2] * y[2] + Si[i * 4 + 3] * y[3];
 #pragma unroll
   for (int s = 14; s >= 0; --s) {                      // backward: z_i = S_i^-1 y_i - L_{i+1}^T z_{i+1}
-    const double m = (sl == s + 1 && link) ? 1.0 : 0.0;
-    double u[4];
+    const T m = (sl == s + 1 && link) ? T(1) : T(0);
+    T u[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) u[j] = m * (L[j] * z[0] + L[4 + j] * z[1] + L[8 + j] * z[2] + L[12 + j] * z[3]);
 #pragma unroll
     for (int k = 0; k < 4; ++k) u[k] = __shfl_down_sync(0xffffffffu, u[k], 1);
-    const double mz = (sl == s) ? 1.0 : 0.0;           // (lane 15 receives lane 16's u, which is zero: sl = 0 there)
+    const T mz = (sl == s) ? T(1) : T(0);              // (lane 15 receives lane 16's u, which is zero: sl = 0 there)
 #pragma unroll
     for (int k = 0; k < 4; ++k) z[k] -= mz * u[k];
   }
 }
 
-// Linearise every factor of this CTA at `xp`: robustified Jacobians -> J store, gradient contributions J^T r -> cs
-// slots, diagonal-block contributions J^T J -> hs slots.  Returns this thread's share of the cost.
-__device__ double factor_linearize(const SolverDev& P, const double* __restrict__ xp, const JStore& J) {
+// Linearise every factor of this CTA at `xp` (fp64): robustified Jacobians -> J store (as T), gradient contributions
+// J^T r -> gs slots, diagonal-block contributions J^T J -> hs slots, chain couplings -> es.  Returns this thread's share
+// of the cost.
+template <typename T>
+__device__ double factor_linearize(const SolverDev& P, const double* __restrict__ xp, const JStore<T>& J) {
   double cost = 0.0;
   const int f0 = blockIdx.x * P.fpc, f1 = min(P.m, f0 + P.fpc);
   for (int f = f0 + threadIdx.x; f < f1; f += GS_THREADS) {
@@ -365,7 +421,7 @@ __device__ double factor_linearize(const SolverDev& P, const double* __restrict_
 #pragma unroll
     for (int i = 0; i < 4; ++i) r[i] *= w;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { Ja[i] *= w; Jb[i] *= w; J.at(i, li) = Ja[i]; J.at(16 + i, li) = Jb[i]; }
+    for (int i = 0; i < 16; ++i) { Ja[i] *= w; Jb[i] *= w; J.at(i, li) = (T)Ja[i]; J.at(16 + i, li) = (T)Jb[i]; }
     if (P.use_chain) {
       const int es = P.es_slot[f];
       if (es >= 0) {                      // E = J_later^T J_earlier (rows: the later node of the pair)
@@ -383,8 +439,8 @@ __device__ double factor_linearize(const SolverDev& P, const double* __restrict_
           }
       }
     }
-    double* ga = P.cs + 4 * (size_t)P.slot_a[f];
-    double* gb = P.cs + 4 * (size_t)P.slot_b[f];
+    double* ga = P.gs + 4 * (size_t)P.slot_a[f];
+    double* gb = P.gs + 4 * (size_t)P.slot_b[f];
     double* ha = P.hs + 16 * (size_t)P.slot_a[f];
     double* hb = P.hs + 16 * (size_t)P.slot_b[f];
 #pragma unroll
@@ -405,43 +461,49 @@ __device__ double factor_linearize(const SolverDev& P, const double* __restrict_
   return cost;
 }
 
-// cost at the trial point `xn` and this thread's share of |J_cur delta|^2 (model decrease)
-__device__ void factor_trial(const SolverDev& P, const double* __restrict__ xn, const JStore& J, double& cost, double& jd) {
+// cost at the trial point `xn` (fp64) and this thread's share of |J_cur delta|^2 (model decrease, in T)
+template <typename T>
+__device__ void factor_trial(const SolverDev& P, const double* __restrict__ xn, const JStore<T>& J, double& cost, double& jd) {
   const int f0 = blockIdx.x * P.fpc, f1 = min(P.m, f0 + P.fpc);
+  const T* delta = static_cast<const T*>(P.delta);
+  T jdt = T(0);
   for (int f = f0 + threadIdx.x; f < f1; f += GS_THREADS) {
     const int li = f - f0;
     const int a = P.ia[f], b = P.ib[f];
-    double pa[4], pb[4], da[4], db[4];
+    double pa[4], pb[4];
+    T da[4], db[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      pa[i] = __ldcg(xn + 4 * a + i); pb[i] = __ldcg(xn + 4 * b + i);
-      da[i] = __ldcg(P.delta + 4 * a + i); db[i] = __ldcg(P.delta + 4 * b + i);
-    }
-    double r[4], Ja[16], Jb[16];
-    linearize_factor(P.ftype[f], pa, pb, P.payload + (size_t)f * OSB_PAYLOAD_LEN, r, Ja, Jb);
-    const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+    for (int i = 0; i < 4; ++i) { pa[i] = __ldcg(xn + 4 * a + i); pb[i] = __ldcg(xn + 4 * b + i); }
+    ld4(delta + 4 * a, da); ld4(delta + 4 * b, db);
+    const double s = factor_sqnorm(P.ftype[f], pa, pb, P.payload + (size_t)f * OSB_PAYLOAD_LEN);
     cost += (P.huber[f] && s > 1.0) ? 0.5 * (2.0 * sqrt(s) - 1.0) : 0.5 * s;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double t = 0.0;
+      T t = T(0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) t += J.at(i * 4 + j, li) * da[j] + J.at(16 + i * 4 + j, li) * db[j];
-      jd += t * t;
+      jdt += t * t;
     }
   }
+  jd += (double)jdt;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(GS_THREADS, 1)
 graph_solve_kernel(SolverDev P) {
   cg::grid_group grid = cg::this_grid();
-  extern __shared__ __align__(16) double smem_j[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* smem_j = reinterpret_cast<T*>(smem_raw);
   __shared__ double sh[4 * 32];
-  const int T = gridDim.x * GS_THREADS;
+  const int T_ = gridDim.x * GS_THREADS;
   const int gtid = blockIdx.x * GS_THREADS + threadIdx.x;
-  JStore J;
+  JStore<T> J;
   if (P.j_in_smem) { J.base = smem_j; J.stride = P.fpc; J.off = 0; }
-  else { J.base = P.Jg; J.stride = P.m; J.off = blockIdx.x * P.fpc; }
-  double* Ls = smem_j + (size_t)32 * P.fpc;      // [16][GS_THREADS]: L_i of the chain preconditioner (use_chain only)
+  else { J.base = static_cast<T*>(P.Jg); J.stride = P.m; J.off = blockIdx.x * P.fpc; }
+  T* Ls = smem_j + (size_t)32 * P.fpc;          // [16][GS_THREADS]: L_i of the chain preconditioner (use_chain only)
+  T* const Pp = static_cast<T*>(P.p); T* const Pz = static_cast<T*>(P.z); T* const Pres = static_cast<T*>(P.res);
+  T* const PAp = static_cast<T*>(P.Ap); T* const Pdelta = static_cast<T*>(P.delta); T* const PMinv = static_cast<T*>(P.Minv);
+  T* const Pcs = static_cast<T*>(P.cs);
   int parity = 0;
   unsigned long long t0 = 0;
   const long long k0 = clock64();
@@ -456,14 +518,14 @@ graph_solve_kernel(SolverDev P) {
   int iters = 0, pcg_total = 0, termination = 3;
 
   // ---- initial linearisation ----
-  double v1[1] = {factor_linearize(P, P.x[0], J)};
-  grid_reduce_sum<1>(v1, P, parity, sh, grid); parity ^= 1;
+  double v1[1], w1[1] = {factor_linearize(P, P.x[0], J)};
+  grid_reduce_sum<1>(w1, v1, P, parity, sh, grid); parity ^= 1;
   double cost = v1[0];
   const double initial_cost = cost;
   bool need_gradient = true;
   const int f0 = blockIdx.x * P.fpc, f1 = min(P.m, f0 + P.fpc);
   // static per-thread data of the fast CG path
-  const bool fast = (P.fpc <= GS_KF * GS_THREADS) && (P.n <= T);
+  const bool fast = (P.fpc <= GS_KF * GS_THREADS) && (P.n <= T_);
   int fa[GS_KF], fb[GS_KF], fsa[GS_KF], fsb[GS_KF];
   bool fvalid[GS_KF];
 #pragma unroll
@@ -474,12 +536,14 @@ graph_solve_kernel(SolverDev P) {
   }
   const bool is_node = fast && gtid < P.n && !P.fixed[gtid];
   const int ns0 = is_node ? P.node_ptr[gtid] : 0, ns1 = is_node ? P.node_ptr[gtid + 1] : 0;
+  const bool chain = fast && P.use_chain;
+  const int sl = threadIdx.x & 15;
 
   while (iters < P.opt.max_iterations) {
     if (need_gradient) {
-      // ---- node phase G: gather gradient and diagonal blocks from the slots, LM diagonal ----
+      // ---- node phase G (fp64): gather gradient and diagonal blocks from the slots, LM diagonal ----
       double vmax = 0.0;
-      for (int n = gtid; n < P.n; n += T) {
+      for (int n = gtid; n < P.n; n += T_) {
         double gn[4] = {0.0, 0.0, 0.0, 0.0};
         double Hn[16];
 #pragma unroll
@@ -489,7 +553,7 @@ graph_solve_kernel(SolverDev P) {
 #pragma unroll 2
           for (int sidx = s0; sidx < s1; ++sidx) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) gn[i] += __ldcg(P.cs + 4 * (size_t)sidx + i);
+            for (int i = 0; i < 4; ++i) gn[i] += __ldcg(P.gs + 4 * (size_t)sidx + i);
 #pragma unroll
             for (int i = 0; i < 16; ++i) Hn[i] += __ldcg(P.hs + 16 * (size_t)sidx + i);
           }
@@ -518,38 +582,39 @@ graph_solve_kernel(SolverDev P) {
       if (gmax <= P.opt.gradient_tolerance) { termination = 1; break; }
     }
 
-    // ---- PCG init (node phase): Minv, res = -g, z = Minv res, p = 0, delta = 0 ----
-    // Fast path (every node has its own thread, <= 2 factors per thread): the node's Minv, D, res, z, p, delta stay in
-    // REGISTERS for the whole CG solve and the factor's indices are preloaded, so a CG iteration touches global memory
-    // only for what crosses threads: z/p gathers by the factor threads and the contribution slots.
+    // ---- PCG init (node phase): preconditioner, res = -g, z = M^-1 res, p = 0, delta = 0 ----
+    // Fast path (every node has its own thread, <= GS_KF factors per thread): the node's preconditioner blocks, D, res,
+    // z, p, delta stay in REGISTERS for the whole CG solve and the factor's indices are preloaded, so a CG iteration
+    // touches global memory only for what crosses threads: z/p gathers by the factor threads and the contribution slots.
     const double lam = 1.0 / radius;
-    double v2[2] = {0.0, 0.0};
-    double Mi[16], Dn[4], rn[4] = {0.0, 0.0, 0.0, 0.0}, zn[4] = {0.0, 0.0, 0.0, 0.0}, pn[4] = {0.0, 0.0, 0.0, 0.0};
-    double dn[4] = {0.0, 0.0, 0.0, 0.0};
-    const bool chain = fast && P.use_chain;
-    const int sl = threadIdx.x & 15;
+    T v2[2] = {T(0), T(0)};
+    T Mi[16], Dl[4] = {T(0), T(0), T(0), T(0)}, rn[4] = {T(0), T(0), T(0), T(0)}, zn[4] = {T(0), T(0), T(0), T(0)};
+    T pn[4] = {T(0), T(0), T(0), T(0)}, dn[4] = {T(0), T(0), T(0), T(0)};     // Dl = lam * D
     bool lk = false;
     if (chain) {
       // factorise the segment's block-tridiagonal M = (I + L) S (I + L)^T: 16 steps over the half-warp, Mi := S_i^-1
-      double M[16], E[16];
+      T M[16], E[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { M[i] = (i % 5 == 0) ? 1.0 : 0.0; E[i] = 0.0; Mi[i] = 0.0; }
+      for (int i = 0; i < 16; ++i) { M[i] = (i % 5 == 0) ? T(1) : T(0); E[i] = T(0); Mi[i] = T(0); }
       if (is_node) {
+        double Md[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) M[i] = P.Hnn[16 * gtid + i];
+        for (int i = 0; i < 16; ++i) Md[i] = P.Hnn[16 * gtid + i];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { Dn[i] = P.D[4 * gtid + i]; M[i * 5] += lam * Dn[i]; }
+        for (int i = 0; i < 4; ++i) { const double ld = lam * P.D[4 * gtid + i]; Dl[i] = (T)ld; Md[i * 5] += ld; }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) M[i] = (T)Md[i];
         lk = P.link[gtid] != 0;
         if (lk) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) E[i] = P.En[16 * gtid + i];
+          for (int i = 0; i < 16; ++i) E[i] = (T)P.En[16 * gtid + i];
         }
       }
-      double Lr[16];
+      T Lr[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) Lr[i] = 0.0;
+      for (int i = 0; i < 16; ++i) Lr[i] = T(0);
       for (int s = 0; s < 16; ++s) {
-        double Sp[16];
+        T Sp[16];
         __syncwarp();                                              // converge after the previous step's divergent block
 #pragma unroll
         for (int i = 0; i < 16; ++i) Sp[i] = __shfl_up_sync(0xffffffffu, Mi[i], 1);
@@ -560,7 +625,7 @@ graph_solve_kernel(SolverDev P) {
             for (int i = 0; i < 4; ++i)
 #pragma unroll
               for (int j = 0; j < 4; ++j) {                        // S_i = M_i - L_i E_i^T
-                double a = 0.0;
+                T a = T(0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) a += Lr[i * 4 + k] * E[j * 4 + k];
                 M[i * 4 + j] -= a;
@@ -571,57 +636,55 @@ graph_solve_kernel(SolverDev P) {
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) Ls[i * GS_THREADS + threadIdx.x] = Lr[i];
-      double zl[4];
       if (is_node) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rn[i] = -P.g[4 * gtid + i];
+        for (int i = 0; i < 4; ++i) rn[i] = (T)(-P.g[4 * gtid + i]);
       }
-      chain_apply(Mi, Lr, lk, sl, rn, zl);
+      chain_apply(Mi, Lr, lk, sl, rn, zn);
+      if (gtid < P.n) {
+        const T zero4[4] = {T(0), T(0), T(0), T(0)};
+        st4(Pres + 4 * gtid, rn); st4(Pz + 4 * gtid, zn); st4(Pp + 4 * gtid, zero4); st4(Pdelta + 4 * gtid, zero4);
+      }
       if (is_node) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          zn[i] = zl[i];
-          P.res[4 * gtid + i] = rn[i]; __stcg(P.z + 4 * gtid + i, zl[i]); __stcg(P.p + 4 * gtid + i, 0.0);
-          P.delta[4 * gtid + i] = 0.0;
-          v2[0] += rn[i] * zl[i]; v2[1] += rn[i] * rn[i];
-        }
-      } else if (gtid < P.n) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          P.res[4 * gtid + i] = 0.0; __stcg(P.z + 4 * gtid + i, 0.0); __stcg(P.p + 4 * gtid + i, 0.0); P.delta[4 * gtid + i] = 0.0;
-        }
+        for (int i = 0; i < 4; ++i) { v2[0] += rn[i] * zn[i]; v2[1] += rn[i] * rn[i]; }
       }
     } else {
-    for (int n = gtid; n < P.n; n += T) {
-      double rl[4] = {0.0, 0.0, 0.0, 0.0}, zl[4] = {0.0, 0.0, 0.0, 0.0};
-      if (!P.fixed[n]) {
-        double M[16];
+      for (int n = gtid; n < P.n; n += T_) {
+        T rl[4] = {T(0), T(0), T(0), T(0)}, zl[4] = {T(0), T(0), T(0), T(0)};
+        if (!P.fixed[n]) {
+          double Md[16];
+          T M[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) M[i] = P.Hnn[16 * n + i];
+          for (int i = 0; i < 16; ++i) Md[i] = P.Hnn[16 * n + i];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { Dn[i] = P.D[4 * n + i]; M[i * 5] += lam * Dn[i]; }
-        inv4(M, Mi);
+          for (int i = 0; i < 4; ++i) { const double ld = lam * P.D[4 * n + i]; Dl[i] = (T)ld; Md[i * 5] += ld; }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) P.Minv[16 * n + i] = Mi[i];
+          for (int i = 0; i < 16; ++i) M[i] = (T)Md[i];
+          inv4(M, Mi);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rl[i] = -P.g[4 * n + i];
+          for (int i = 0; i < 16; ++i) PMinv[16 * n + i] = Mi[i];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 4; ++i) rl[i] = (T)(-P.g[4 * n + i]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) zl[i] += Mi[i * 4 + j] * rl[j];
-      }
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        P.res[4 * n + i] = rl[i]; __stcg(P.z + 4 * n + i, zl[i]); __stcg(P.p + 4 * n + i, 0.0); P.delta[4 * n + i] = 0.0;
-        v2[0] += rl[i] * zl[i]; v2[1] += rl[i] * rl[i];
-        rn[i] = rl[i]; zn[i] = zl[i];                       // (fast path: the only iteration of this loop)
+            for (int j = 0; j < 4; ++j) zl[i] += Mi[i * 4 + j] * rl[j];
+        }
+        const T zero4[4] = {T(0), T(0), T(0), T(0)};
+        st4(Pres + 4 * n, rl); st4(Pz + 4 * n, zl); st4(Pp + 4 * n, zero4); st4(Pdelta + 4 * n, zero4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v2[0] += rl[i] * zl[i]; v2[1] += rl[i] * rl[i];
+          rn[i] = rl[i]; zn[i] = zl[i];                       // (fast path: the only iteration of this loop)
+        }
       }
     }
-    }
-    grid_reduce_sum<2>(v2, P, parity, sh, grid); parity ^= 1;
-    double rz = v2[0];
-    const double rr0 = v2[1];
-    double beta = 0.0;
+    double r2[2];
+    grid_reduce_sum<2>(v2, r2, P, parity, sh, grid); parity ^= 1;
+    double rz = r2[0];
+    const double rr0 = r2[1];
+    T beta = T(0);
     int it = 0;
     // ---- PCG iterations: 3 barriers each ----
     while (it < P.opt.max_pcg_iterations && rr0 > 0.0) {
@@ -629,224 +692,206 @@ graph_solve_kernel(SolverDev P) {
       // factor phase: p_a = z_a + beta p_a (on the fly), t = Ja p_a + Jb p_b, contributions Ja^T t, Jb^T t
       if (fast) {
         // all gathers of this thread's (up to 3) factors are issued before any arithmetic: one L2 round trip
-        double2 zq[GS_KF][4], pq[GS_KF][4];
+        T zq[GS_KF][2][4], pq[GS_KF][2][4];
 #pragma unroll
         for (int k = 0; k < GS_KF; ++k) {
-          zq[k][0] = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fa[k]));
-          zq[k][1] = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fa[k] + 2));
-          zq[k][2] = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fb[k]));
-          zq[k][3] = __ldcg(reinterpret_cast<const double2*>(P.z + 4 * fb[k] + 2));
-          pq[k][0] = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fa[k]));
-          pq[k][1] = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fa[k] + 2));
-          pq[k][2] = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fb[k]));
-          pq[k][3] = __ldcg(reinterpret_cast<const double2*>(P.p + 4 * fb[k] + 2));
+          ld4(Pz + 4 * fa[k], zq[k][0]); ld4(Pz + 4 * fb[k], zq[k][1]);
+          ld4(Pp + 4 * fa[k], pq[k][0]); ld4(Pp + 4 * fb[k], pq[k][1]);
         }
 #pragma unroll
         for (int k = 0; k < GS_KF; ++k) {
           if (!fvalid[k]) continue;
           const int li = threadIdx.x + k * GS_THREADS;
-          const double pa[4] = {zq[k][0].x + beta * pq[k][0].x, zq[k][0].y + beta * pq[k][0].y,
-                                zq[k][1].x + beta * pq[k][1].x, zq[k][1].y + beta * pq[k][1].y};
-          const double pb[4] = {zq[k][2].x + beta * pq[k][2].x, zq[k][2].y + beta * pq[k][2].y,
-                                zq[k][3].x + beta * pq[k][3].x, zq[k][3].y + beta * pq[k][3].y};
-          double t[4];
+          T pa[4], pb[4], t[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { pa[i] = zq[k][0][i] + beta * pq[k][0][i]; pb[i] = zq[k][1][i] + beta * pq[k][1][i]; }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            double acc = 0.0;
+            T acc = T(0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc += J.at(i * 4 + j, li) * pa[j] + J.at(16 + i * 4 + j, li) * pb[j];
             t[i] = acc;
           }
-          double ca[4], cb[4];
+          T ca[4], cb[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            double sa = 0.0, sb = 0.0;
+            T sa = T(0), sb = T(0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) { sa += J.at(i * 4 + j, li) * t[i]; sb += J.at(16 + i * 4 + j, li) * t[i]; }
             ca[j] = sa; cb[j] = sb;
           }
-          __stcg(reinterpret_cast<double2*>(P.cs + 4 * (size_t)fsa[k]), make_double2(ca[0], ca[1]));
-          __stcg(reinterpret_cast<double2*>(P.cs + 4 * (size_t)fsa[k] + 2), make_double2(ca[2], ca[3]));
-          __stcg(reinterpret_cast<double2*>(P.cs + 4 * (size_t)fsb[k]), make_double2(cb[0], cb[1]));
-          __stcg(reinterpret_cast<double2*>(P.cs + 4 * (size_t)fsb[k] + 2), make_double2(cb[2], cb[3]));
+          st4(Pcs + 4 * (size_t)fsa[k], ca);
+          st4(Pcs + 4 * (size_t)fsb[k], cb);
         }
       } else {
-      for (int f = f0 + threadIdx.x; f < f1; f += GS_THREADS) {
-        const int li = f - f0;
-        const int a = P.ia[f], b = P.ib[f];
-        double pa[4], pb[4], t[4];
+        for (int f = f0 + threadIdx.x; f < f1; f += GS_THREADS) {
+          const int li = f - f0;
+          const int a = P.ia[f], b = P.ib[f];
+          T za[4], zb[4], qa[4], qb[4], pa[4], pb[4], t[4];
+          ld4(Pz + 4 * a, za); ld4(Pz + 4 * b, zb); ld4(Pp + 4 * a, qa); ld4(Pp + 4 * b, qb);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          pa[i] = __ldcg(P.z + 4 * a + i) + beta * __ldcg(P.p + 4 * a + i);
-          pb[i] = __ldcg(P.z + 4 * b + i) + beta * __ldcg(P.p + 4 * b + i);
+          for (int i = 0; i < 4; ++i) { pa[i] = za[i] + beta * qa[i]; pb[i] = zb[i] + beta * qb[i]; }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            T acc = T(0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc += J.at(i * 4 + j, li) * pa[j] + J.at(16 + i * 4 + j, li) * pb[j];
+            t[i] = acc;
+          }
+          T ca[4], cb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            T sa = T(0), sb = T(0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sa += J.at(i * 4 + j, li) * t[i]; sb += J.at(16 + i * 4 + j, li) * t[i]; }
+            ca[j] = sa; cb[j] = sb;
+          }
+          st4(Pcs + 4 * (size_t)P.slot_a[f], ca);
+          st4(Pcs + 4 * (size_t)P.slot_b[f], cb);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc += J.at(i * 4 + j, li) * pa[j] + J.at(16 + i * 4 + j, li) * pb[j];
-          t[i] = acc;
-        }
-        double* ca = P.cs + 4 * (size_t)P.slot_a[f];
-        double* cb = P.cs + 4 * (size_t)P.slot_b[f];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          double sa = 0.0, sb = 0.0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { sa += J.at(i * 4 + j, li) * t[i]; sb += J.at(16 + i * 4 + j, li) * t[i]; }
-          __stcg(ca + j, sa); __stcg(cb + j, sb);
-        }
-      }
       }
       long long c1 = clock64();
       all_sync(P, grid);
       long long c2 = clock64();
       // node phase 1: p = z + beta p, Ap = sum of the node's slots + lam D p, partial p.Ap
-      double v1b[1] = {0.0};
-      double apn[4] = {0.0, 0.0, 0.0, 0.0};
+      T v1b[1] = {T(0)};
+      T apn[4] = {T(0), T(0), T(0), T(0)};
       if (fast) {
         if (is_node) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { pn[i] = zn[i] + beta * pn[i]; apn[i] = lam * Dn[i] * pn[i]; }
-          __stcg(reinterpret_cast<double2*>(P.p + 4 * gtid), make_double2(pn[0], pn[1]));
-          __stcg(reinterpret_cast<double2*>(P.p + 4 * gtid + 2), make_double2(pn[2], pn[3]));
-          for (int s0 = ns0; s0 < ns1; s0 += 16) {         // 32 independent 16-byte loads in flight per batch: one L2
-            double2 c[16][2];                              // round trip covers every node of degree <= 16
+          for (int i = 0; i < 4; ++i) { pn[i] = zn[i] + beta * pn[i]; apn[i] = Dl[i] * pn[i]; }
+          st4(Pp + 4 * gtid, pn);
+          for (int s0 = ns0; s0 < ns1; s0 += 16) {         // 16 (fp32) / 32 (fp64) independent 16-byte loads in flight
+            T c[16][4];                                    // per batch: one L2 round trip covers every node of degree <= 16
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const int si = min(s0 + k, ns1 - 1);
-              c[k][0] = __ldcg(reinterpret_cast<const double2*>(P.cs + 4 * (size_t)si));
-              c[k][1] = __ldcg(reinterpret_cast<const double2*>(P.cs + 4 * (size_t)si + 2));
-            }
+            for (int k = 0; k < 16; ++k) ld4(Pcs + 4 * (size_t)min(s0 + k, ns1 - 1), c[k]);
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-              if (s0 + k < ns1) { apn[0] += c[k][0].x; apn[1] += c[k][0].y; apn[2] += c[k][1].x; apn[3] += c[k][1].y; }
+              if (s0 + k < ns1) { apn[0] += c[k][0]; apn[1] += c[k][1]; apn[2] += c[k][2]; apn[3] += c[k][3]; }
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) v1b[0] += pn[i] * apn[i];
         }
       } else {
-      for (int n = gtid; n < P.n; n += T) {
-        if (P.fixed[n]) continue;
-        double pl[4], ap[4];
+        for (int n = gtid; n < P.n; n += T_) {
+          if (P.fixed[n]) continue;
+          T zl[4], ql[4], pl[4], ap[4];
+          ld4(Pz + 4 * n, zl); ld4(Pp + 4 * n, ql);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          pl[i] = P.z[4 * n + i] + beta * P.p[4 * n + i];
-          ap[i] = lam * P.D[4 * n + i] * pl[i];
-        }
-        const int s0 = P.node_ptr[n], s1 = P.node_ptr[n + 1];
+          for (int i = 0; i < 4; ++i) { pl[i] = zl[i] + beta * ql[i]; ap[i] = (T)(lam * P.D[4 * n + i]) * pl[i]; }
+          const int s0 = P.node_ptr[n], s1 = P.node_ptr[n + 1];
 #pragma unroll 4
-        for (int sidx = s0; sidx < s1; ++sidx) {
+          for (int sidx = s0; sidx < s1; ++sidx) {
+            T c[4];
+            ld4(Pcs + 4 * (size_t)sidx, c);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) ap[i] += __ldcg(P.cs + 4 * (size_t)sidx + i);
+            for (int i = 0; i < 4; ++i) ap[i] += c[i];
+          }
+          st4(Pp + 4 * n, pl); st4(PAp + 4 * n, ap);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v1b[0] += pl[i] * ap[i];
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { __stcg(P.p + 4 * n + i, pl[i]); P.Ap[4 * n + i] = ap[i]; v1b[0] += pl[i] * ap[i]; }
-      }
       }
       long long c3 = clock64();
-      grid_reduce_sum<1>(v1b, P, parity, sh, grid); parity ^= 1;
+      double r1[1];
+      grid_reduce_sum<1>(v1b, r1, P, parity, sh, grid); parity ^= 1;
       long long c4 = clock64();
-      const double pAp = v1b[0];
+      const double pAp = r1[0];
       if (!(pAp > 0.0)) break;
-      const double alpha = rz / pAp;
-      // node phase 2: delta += alpha p, res -= alpha Ap, z = Minv res; partial rz_new, rr
-      double v22[2] = {0.0, 0.0};
+      const T alpha = (T)(rz / pAp);
+      // node phase 2: delta += alpha p, res -= alpha Ap, z = M^-1 res; partial rz_new, rr
+      T v22[2] = {T(0), T(0)};
       if (fast) {
         if (is_node) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) { dn[i] += alpha * pn[i]; rn[i] -= alpha * apn[i]; }
         }
         if (chain) {                                          // warp-collective: every lane takes part in the sweeps
-          double Lr[16];
+          T Lr[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) Lr[i] = Ls[i * GS_THREADS + threadIdx.x];
           chain_apply(Mi, Lr, lk, sl, rn, zn);
         } else if (is_node) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            double acc = 0.0;
+            T acc = T(0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc += Mi[i * 4 + j] * rn[j];
             zn[i] = acc;
           }
         }
         if (is_node) {
-          __stcg(reinterpret_cast<double2*>(P.z + 4 * gtid), make_double2(zn[0], zn[1]));
-          __stcg(reinterpret_cast<double2*>(P.z + 4 * gtid + 2), make_double2(zn[2], zn[3]));
+          st4(Pz + 4 * gtid, zn);
 #pragma unroll
           for (int i = 0; i < 4; ++i) { v22[0] += rn[i] * zn[i]; v22[1] += rn[i] * rn[i]; }
         }
       } else {
-      for (int n = gtid; n < P.n; n += T) {
-        if (P.fixed[n]) continue;
-        double rl[4], zl[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int n = gtid; n < P.n; n += T_) {
+          if (P.fixed[n]) continue;
+          T dl[4], pl[4], rl[4], al[4], zl[4] = {T(0), T(0), T(0), T(0)};
+          ld4(Pdelta + 4 * n, dl); ld4(Pp + 4 * n, pl); ld4(Pres + 4 * n, rl); ld4(PAp + 4 * n, al);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          P.delta[4 * n + i] += alpha * P.p[4 * n + i];
-          rl[i] = P.res[4 * n + i] - alpha * P.Ap[4 * n + i];
+          for (int i = 0; i < 4; ++i) { dl[i] += alpha * pl[i]; rl[i] -= alpha * al[i]; }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) zl[i] += PMinv[16 * n + i * 4 + j] * rl[j];
+          st4(Pdelta + 4 * n, dl); st4(Pres + 4 * n, rl); st4(Pz + 4 * n, zl);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { v22[0] += rl[i] * zl[i]; v22[1] += rl[i] * rl[i]; }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) zl[i] += P.Minv[16 * n + i * 4 + j] * rl[j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          P.res[4 * n + i] = rl[i]; __stcg(P.z + 4 * n + i, zl[i]);
-          v22[0] += rl[i] * zl[i]; v22[1] += rl[i] * rl[i];
-        }
-      }
       }
       long long c5 = clock64();
-      grid_reduce_sum<2>(v22, P, parity, sh, grid); parity ^= 1;
+      double r22[2];
+      grid_reduce_sum<2>(v22, r22, P, parity, sh, grid); parity ^= 1;
       if (gtid == 0) {
         const long long c6 = clock64();
         P.dbg[0] += c1 - c0; P.dbg[1] += c2 - c1; P.dbg[2] += c3 - c2; P.dbg[3] += c4 - c3; P.dbg[4] += c5 - c4;
         P.dbg[5] += c6 - c5; P.dbg[6] += 1;
       }
       ++it;
-      beta = v22[0] / rz;
-      rz = v22[0];
-      if (v22[1] <= P.opt.pcg_tolerance * P.opt.pcg_tolerance * rr0) break;
+      beta = (T)(r22[0] / rz);
+      rz = r22[0];
+      if (r22[1] <= P.opt.pcg_tolerance * P.opt.pcg_tolerance * rr0) break;
     }
-    if (fast && is_node) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) P.delta[4 * gtid + i] = dn[i];
-    }
+    if (fast && is_node) st4(Pdelta + 4 * gtid, dn);
     pcg_total += it;
     ++iters;
 
-    // ---- trial point: x_new = x + delta; g.delta, |delta|^2, |x|^2 ----
+    // ---- trial point (fp64): x_new = x + delta; g.delta, |delta|^2, |x|^2 ----
     double* xc = P.x[cur];
     double* xn = P.x[cur ^ 1];
-    double v4[3] = {0.0, 0.0, 0.0};
-    for (int n = gtid; n < P.n; n += T) {
+    double v4[3] = {0.0, 0.0, 0.0}, r4[3];
+    for (int n = gtid; n < P.n; n += T_) {
+      T dl[4];
+      ld4(Pdelta + 4 * n, dl);
+      if (fast && n == gtid && is_node) { dl[0] = dn[0]; dl[1] = dn[1]; dl[2] = dn[2]; dl[3] = dn[3]; }   // (own store)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const double d = P.fixed[n] ? 0.0 : P.delta[4 * n + i];
+        const double d = P.fixed[n] ? 0.0 : (double)dl[i];
         const double xv = xc[4 * n + i];
         __stcg(xn + 4 * n + i, xv + d);
-        if (P.fixed[n]) __stcg(P.delta + 4 * n + i, 0.0);
         v4[0] += P.g[4 * n + i] * d; v4[1] += d * d;
         if (!P.fixed[n]) v4[2] += xv * xv;
       }
+      if (P.fixed[n]) { const T zero4[4] = {T(0), T(0), T(0), T(0)}; st4(Pdelta + 4 * n, zero4); }
     }
-    grid_reduce_sum<3>(v4, P, parity, sh, grid); parity ^= 1;
+    grid_reduce_sum<3>(v4, r4, P, parity, sh, grid); parity ^= 1;
     // ---- evaluate trial, model decrease, elapsed time ----
-    double v5[3] = {0.0, 0.0, 0.0};
+    double v5[3] = {0.0, 0.0, 0.0}, r5[3];
     factor_trial(P, xn, J, v5[0], v5[1]);
     if (gtid == 0) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
       v5[2] = (double)(t1 - t0) * 1e-9;
     }
-    grid_reduce_sum<3>(v5, P, parity, sh, grid); parity ^= 1;
-    const double new_cost = v5[0];
-    const double model = -v4[0] - 0.5 * v5[1];
-    const double elapsed = v5[2];
+    grid_reduce_sum<3>(v5, r5, P, parity, sh, grid); parity ^= 1;
+    const double new_cost = r5[0];
+    const double model = -r4[0] - 0.5 * r5[1];
+    const double elapsed = r5[2];
     const double rho = (model > 0.0) ? (cost - new_cost) / model : -1.0;
     const bool finite = isfinite(new_cost);
-    const bool small_step = sqrt(v4[1]) <= P.opt.parameter_tolerance * (sqrt(v4[2]) + P.opt.parameter_tolerance);
+    const bool small_step = sqrt(r4[1]) <= P.opt.parameter_tolerance * (sqrt(r4[2]) + P.opt.parameter_tolerance);
     if (finite && rho > 1e-3) {
       // accept (Ceres LevenbergMarquardtStrategy::StepAccepted)
       const double tmp = 2.0 * rho - 1.0;
@@ -860,8 +905,8 @@ graph_solve_kernel(SolverDev P) {
       if (small_step) { termination = 2; break; }
       if (P.opt.max_time_s > 0.0 && elapsed > P.opt.max_time_s) { termination = 4; break; }
       // re-linearise at the accepted point (the trial pass kept the old Jacobians for the model term)
-      double v1c[1] = {factor_linearize(P, P.x[cur], J)};
-      grid_reduce_sum<1>(v1c, P, parity, sh, grid); parity ^= 1;
+      double v1c[1], w1c[1] = {factor_linearize(P, P.x[cur], J)};
+      grid_reduce_sum<1>(w1c, v1c, P, parity, sh, grid); parity ^= 1;
       need_gradient = true;
     } else {
       radius /= decrease;
@@ -874,7 +919,7 @@ graph_solve_kernel(SolverDev P) {
 
   // ---- write back ----
   const double* xf = P.x[cur];
-  for (int i = gtid; i < 4 * P.n; i += T) P.poses_out[i] = __ldcg(xf + i);
+  for (int i = gtid; i < 4 * P.n; i += T_) P.poses_out[i] = __ldcg(xf + i);
   if (gtid == 0) {
     P.summary->initial_cost = initial_cost;
     P.summary->final_cost = cost;
@@ -912,13 +957,13 @@ struct osb_solver {
   int32_t *d_type = nullptr, *d_ia = nullptr, *d_ib = nullptr, *d_ptr = nullptr, *d_slot_a = nullptr, *d_slot_b = nullptr;
   double *d_payload = nullptr, *d_x0 = nullptr, *d_x1 = nullptr, *d_Jg = nullptr, *d_lin = nullptr;
   double *d_nodevec = nullptr;   // g, D, p, z, res, Ap, delta (7 x 4n) + Hnn, Minv (2 x 16n)
-  double *d_cs = nullptr, *d_hs = nullptr, *d_partial = nullptr, *d_out = nullptr;
+  double *d_cs = nullptr, *d_gs = nullptr, *d_hs = nullptr, *d_partial = nullptr, *d_out = nullptr;
   osb_solve_summary* d_summary = nullptr;
   long long* d_dbg = nullptr;
   uint8_t* d_link = nullptr;
   int32_t *d_es_ptr = nullptr, *d_es_slot = nullptr;
   double *d_es = nullptr, *d_En = nullptr;
-  int last_grid = 0, last_cluster = 0, last_jsmem = 0, last_chain = 0;
+  int last_grid = 0, last_cluster = 0, last_jsmem = 0, last_chain = 0, last_f32 = 0;
 };
 
 extern "C" void osb_solve_default_options(osb_solve_options* o) {
@@ -931,6 +976,7 @@ extern "C" void osb_solve_default_options(osb_solve_options* o) {
   o->parameter_tolerance = 1e-8;
   o->pcg_tolerance = 1e-2;
   o->preconditioner = OSB_PRECOND_AUTO;
+  o->inner_precision = OSB_INNER_AUTO;
   o->initial_trust_radius = 1e4;
 }
 
@@ -944,8 +990,10 @@ extern "C" osb_status osb_solver_create(osb_solver** out, int max_nodes, int max
   OSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   OSB_CUDA(cudaEventCreate(&h->ev0));
   OSB_CUDA(cudaEventCreate(&h->ev1));
-  OSB_CUDA(cudaFuncSetAttribute(graph_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_DYN_MAX));
-  h->cluster_ok = cudaFuncSetAttribute(graph_solve_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+  OSB_CUDA(cudaFuncSetAttribute(graph_solve_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_DYN_MAX));
+  OSB_CUDA(cudaFuncSetAttribute(graph_solve_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_DYN_MAX));
+  h->cluster_ok = cudaFuncSetAttribute(graph_solve_kernel<float>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                  cudaFuncSetAttribute(graph_solve_kernel<double>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
   cudaGetLastError();
   OSB_CUDA(cudaMalloc(&h->d_fixed, n));
   OSB_CUDA(cudaMalloc(&h->d_huber, m));
@@ -962,6 +1010,7 @@ extern "C" osb_status osb_solver_create(osb_solver** out, int max_nodes, int max
   OSB_CUDA(cudaMalloc(&h->d_lin, 36 * m * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_nodevec, (7 * 4 + 2 * 16) * n * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_cs, 8 * m * sizeof(double)));
+  OSB_CUDA(cudaMalloc(&h->d_gs, 8 * m * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_hs, 32 * m * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_partial, 2 * 4 * (size_t)num_sms() * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_out, 4 * n * sizeof(double)));
@@ -981,7 +1030,7 @@ extern "C" osb_status osb_solver_destroy(osb_solver* h) {
   if (!h) return OSB_OK;
   cudaFree(h->d_fixed); cudaFree(h->d_huber); cudaFree(h->d_type); cudaFree(h->d_ia); cudaFree(h->d_ib);
   cudaFree(h->d_slot_a); cudaFree(h->d_slot_b); cudaFree(h->d_ptr); cudaFree(h->d_payload); cudaFree(h->d_x0);
-  cudaFree(h->d_x1); cudaFree(h->d_Jg); cudaFree(h->d_lin); cudaFree(h->d_nodevec); cudaFree(h->d_cs); cudaFree(h->d_hs);
+  cudaFree(h->d_x1); cudaFree(h->d_Jg); cudaFree(h->d_lin); cudaFree(h->d_nodevec); cudaFree(h->d_cs); cudaFree(h->d_gs); cudaFree(h->d_hs);
   cudaFree(h->d_partial); cudaFree(h->d_out); cudaFree(h->d_summary); cudaFree(h->d_dbg);
   cudaFree(h->d_link); cudaFree(h->d_es_ptr); cudaFree(h->d_es_slot); cudaFree(h->d_es); cudaFree(h->d_En);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1144,9 +1193,13 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
   const size_t N4 = 4 * (size_t)h->max_nodes, N16 = 16 * (size_t)h->max_nodes;
   P.g = nv; P.D = nv + N4; P.p = nv + 2 * N4; P.z = nv + 3 * N4; P.res = nv + 4 * N4; P.Ap = nv + 5 * N4;
   P.delta = nv + 6 * N4; P.Hnn = nv + 7 * N4; P.Minv = nv + 7 * N4 + N16;
-  P.cs = h->d_cs; P.hs = h->d_hs; P.partial = h->d_partial; P.opt = o; P.summary = h->d_summary; P.poses_out = h->d_out; P.dbg = h->d_dbg;
+  P.cs = h->d_cs; P.gs = h->d_gs; P.hs = h->d_hs; P.partial = h->d_partial; P.opt = o; P.summary = h->d_summary; P.poses_out = h->d_out; P.dbg = h->d_dbg;
   P.use_chain = 0; P.link = h->d_link; P.es_ptr = h->d_es_ptr; P.es_slot = h->d_es_slot; P.es = h->d_es; P.En = h->d_En;
 
+  // inner precision: fp32 PCG unless the caller asks for a tighter inner solve than fp32 can deliver
+  const bool f32 = o.inner_precision == OSB_INNER_FP32 || (o.inner_precision == OSB_INNER_AUTO && o.pcg_tolerance >= 1e-4);
+  const size_t tsz = f32 ? sizeof(float) : sizeof(double);
+  const void* kern = f32 ? (const void*)graph_solve_kernel<float> : (const void*)graph_solve_kernel<double>;
   // launch shape: ONE thread-block cluster (hardware barrier, ~0.2 us) when the factor list fits 16 CTAs with their
   // Jacobians in shared memory; otherwise a cooperative grid (software grid barrier).
   cudaLaunchConfig_t cfg = {};
@@ -1156,16 +1209,17 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
   {
     const int G = std::max(1, std::min(GS_MAX_CLUSTER, cdiv(std::max(n_nodes, n_factors), GS_THREADS)));
     const int fpc = cdiv(n_factors, G);
-    if (h->cluster_ok && (size_t)fpc * 256 <= (size_t)GS_SMEM_J_MAX && cdiv(n_nodes, GS_THREADS) <= 4 * G) {
-      // chain preconditioner: needs the fast path (one thread per node, <= GS_KF factors per thread) and 32 KB more
+    const size_t jbytes = (size_t)fpc * 32 * tsz, cbytes = (size_t)16 * GS_THREADS * tsz;
+    if (h->cluster_ok && jbytes <= (size_t)GS_SMEM_J_MAX && cdiv(n_nodes, GS_THREADS) <= 4 * G) {
+      // chain preconditioner: needs the fast path (one thread per node, <= GS_KF factors per thread) and room for L
       const bool chain = o.preconditioner != OSB_PRECOND_BLOCK_JACOBI && fpc <= GS_KF * GS_THREADS &&
-                         n_nodes <= G * GS_THREADS && (size_t)fpc * 256 + GS_SMEM_CHAIN <= (size_t)GS_SMEM_DYN_MAX;
+                         n_nodes <= G * GS_THREADS && jbytes + cbytes <= (size_t)GS_SMEM_DYN_MAX;
       P.use_chain = chain ? 1 : 0;
-      cfg.gridDim = dim3(G); cfg.dynamicSmemBytes = (size_t)fpc * 256 + (chain ? GS_SMEM_CHAIN : 0);
+      cfg.gridDim = dim3(G); cfg.dynamicSmemBytes = jbytes + (chain ? cbytes : 0);
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       int nclusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&nclusters, graph_solve_kernel, &cfg) == cudaSuccess && nclusters >= 1) {
+      if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) == cudaSuccess && nclusters >= 1) {
         P.fpc = fpc; P.use_cluster = 1; P.j_in_smem = 1;
         launched_cluster = true;
       } else {
@@ -1179,9 +1233,10 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
     int per_sm = 0;
     const int G0 = std::max(1, std::min(num_sms(), cdiv(std::max(n_nodes, n_factors), GS_THREADS)));
     int fpc = cdiv(n_factors, G0);
-    P.j_in_smem = ((size_t)fpc * 256 <= (size_t)GS_SMEM_J_MAX) ? 1 : 0;
-    const size_t smem = P.j_in_smem ? (size_t)fpc * 256 : 0;
-    OSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_solve_kernel, GS_THREADS, smem));
+    const size_t jbytes = (size_t)fpc * 32 * tsz;
+    P.j_in_smem = (jbytes <= (size_t)GS_SMEM_J_MAX) ? 1 : 0;
+    const size_t smem = P.j_in_smem ? jbytes : 0;
+    OSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GS_THREADS, smem));
     if (per_sm < 1) { set_error("osb_solver_solve", "solve kernel cannot be made resident"); return OSB_ERR_CUDA; }
     P.fpc = fpc; P.use_cluster = 0;
     cfg.gridDim = dim3(G0); cfg.dynamicSmemBytes = smem;
@@ -1189,8 +1244,12 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
     attr[0].val.cooperative = 1;
   }
   h->last_grid = (int)cfg.gridDim.x; h->last_cluster = P.use_cluster; h->last_jsmem = P.j_in_smem; h->last_chain = P.use_chain;
+  h->last_f32 = f32 ? 1 : 0;
   OSB_CUDA(cudaEventRecord(h->ev0, st));
-  OSB_CUDA(cudaLaunchKernelEx(&cfg, graph_solve_kernel, P));
+  {
+    void* kargs[1] = {&P};
+    OSB_CUDA(cudaLaunchKernelExC(&cfg, kern, kargs));
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   OSB_CUDA(cudaEventRecord(h->ev1, st));
   OSB_CUDA(cudaMemcpyAsync(x_p.data(), h->d_out, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1211,7 +1270,7 @@ extern "C" osb_status osb_solver_phase_cycles(osb_solver* h, double* out12) {
   long long c[8];
   OSB_CUDA(cudaMemcpy(c, h->d_dbg, sizeof(c), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 8; ++i) out12[i] = (double)c[i];
-  out12[8] = h->last_grid; out12[9] = h->last_cluster; out12[10] = h->last_jsmem + 2 * h->last_chain; out12[11] = GS_THREADS;
+  out12[8] = h->last_grid; out12[9] = h->last_cluster; out12[10] = h->last_jsmem + 2 * h->last_chain + 4 * h->last_f32; out12[11] = GS_THREADS;
   return OSB_OK;
 }
 

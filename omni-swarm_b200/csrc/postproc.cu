@@ -432,25 +432,38 @@ __device__ __forceinline__ float sample_channel(const float* __restrict__ d, con
 }
 
 // per-channel L2 norm over the keypoints of an image (torch::norm(desc, 2, 1) on [256,N], :214).
-// 1024 threads = 4 keypoint groups x 256 channels; group g sums keypoints g, g+4, ... and the four partial sums are
-// combined in a fixed order.
-__global__ void __launch_bounds__(1024)
+// The kernel is a chain of dependent L2 round trips (keypoint -> 4 taps), so it is spread wide: CTA = (image, 64-channel
+// slab), 1024 threads = 16 keypoint groups x 64 channels; group g sums keypoints g, g+16, ... (two in flight per
+// iteration) and the 16 partial sums are combined in a fixed order.
+constexpr int DN_GROUPS = 16, DN_CH = 64;
+__global__ void __launch_bounds__(DN_GROUPS * DN_CH)
 sp_desc_norm_kernel(const float* __restrict__ desc, int H, int W, const int32_t* __restrict__ n_kpts,
                     const float* __restrict__ kpts, int max_num, float* __restrict__ cnorm) {
-  __shared__ float part[4][256];
-  const int b = blockIdx.x, ch = threadIdx.x & 255, g = threadIdx.x >> 8;
+  __shared__ float part[DN_GROUPS][DN_CH];
+  const int b = blockIdx.x, c = threadIdx.x % DN_CH, g = threadIdx.x / DN_CH;
+  const int ch = blockIdx.y * DN_CH + c;
   const int Hc = H / 8, Wc = W / 8;
   const float* d = desc + (size_t)b * Hc * Wc * 256;
+  const float* kp = kpts + (size_t)b * max_num * 2;
   const int N = n_kpts[b];
   float s = 0.f;
-  for (int n = g; n < N; n += 4) {
-    const Taps t = bilinear_taps(kpts[((size_t)b * max_num + n) * 2], kpts[((size_t)b * max_num + n) * 2 + 1], W, H, Wc, Hc);
-    const float v = sample_channel(d, t, Wc, Hc, ch);
-    s = fmaf(v, v, s);
+  for (int n = g; n < N; n += 2 * DN_GROUPS) {
+    const int n2 = n + DN_GROUPS;
+    const Taps t0 = bilinear_taps(kp[2 * n], kp[2 * n + 1], W, H, Wc, Hc);
+    const Taps t1 = bilinear_taps(kp[2 * min(n2, N - 1)], kp[2 * min(n2, N - 1) + 1], W, H, Wc, Hc);
+    const float v0 = sample_channel(d, t0, Wc, Hc, ch);
+    const float v1 = sample_channel(d, t1, Wc, Hc, ch);
+    s = fmaf(v0, v0, s);
+    if (n2 < N) s = fmaf(v1, v1, s);
   }
-  part[g][ch] = s;
+  part[g][c] = s;
   __syncthreads();
-  if (g == 0) cnorm[b * 256 + ch] = sqrtf((part[0][ch] + part[1][ch]) + (part[2][ch] + part[3][ch]));
+  if (g == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < DN_GROUPS; ++i) t += part[i][c];
+    cnorm[b * 256 + ch] = sqrtf(t);
+  }
 }
 
 // (S^T / cnorm - mean) @ comp^T  (:215-221).  CTA = 8 keypoints of one image, 256 threads.
@@ -466,7 +479,8 @@ sp_desc_pca_kernel(const float* __restrict__ desc, int H, int W, const int32_t* 
   const int Hc = H / 8, Wc = W / 8;
   const float* d = desc + (size_t)b * Hc * Wc * 256;
   const float cn = cnorm[b * 256 + tid], mu = pca_mean[tid];
-  for (int i = 0; i < DP_KP; ++i) {
+#pragma unroll
+  for (int i = 0; i < DP_KP; ++i) {                       // unrolled: the 8 x 4 tap loads are independent L2 round trips
     const int n = n0 + i;
     float v = 0.f;
     if (n < N) {
@@ -479,6 +493,7 @@ sp_desc_pca_kernel(const float* __restrict__ desc, int H, int W, const int32_t* 
   // 8 keypoints x 64 outputs = 512 dot products of length 256; thread -> (kp = tid/32 .., o = ...)
   const int o = tid & 63, kq = tid >> 6;  // kq in 0..3 -> keypoints kq and kq+4
   float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
   for (int c = 0; c < 256; ++c) {
     const float w = __ldg(pca_compT + c * 64 + o);   // transposed [256][64]: coalesced across o
     a0 = fmaf(sv[kq][c], w, a0);
@@ -491,7 +506,7 @@ sp_desc_pca_kernel(const float* __restrict__ desc, int H, int W, const int32_t* 
 osb_status sp_descriptors(const float* desc_nhwc, int B, int H, int W, const int32_t* n_kpts, const float* kpts,
                           int max_num, const float* pca_compT, const float* pca_mean, float* cnorm, float* out,
                           cudaStream_t st) {
-  OSB_LAUNCH(sp_desc_norm_kernel, B, 1024, 0, st, desc_nhwc, H, W, n_kpts, kpts, max_num, cnorm);
+  OSB_LAUNCH(sp_desc_norm_kernel, dim3(B, 256 / DN_CH), DN_GROUPS * DN_CH, 0, st, desc_nhwc, H, W, n_kpts, kpts, max_num, cnorm);
   OSB_CHECK_LAUNCH();
   dim3 grid(cdiv(max_num, DP_KP), B);
   OSB_LAUNCH(sp_desc_pca_kernel, grid, 256, 0, st, desc_nhwc, H, W, n_kpts, kpts, max_num, cnorm, pca_compT, pca_mean, out);

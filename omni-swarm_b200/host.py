@@ -244,7 +244,8 @@ class PoseGraphSolver:
         names = ["factor", "barrier", "node1", "reduce1", "node2", "reduce2", "cg_iterations", "kernel", "ctas",
                  "cluster", "j_in_smem", "threads"]
         d = dict(zip(names, c.tolist()))
-        d["chain_preconditioner"] = float(int(d["j_in_smem"]) >> 1)
+        d["chain_preconditioner"] = float((int(d["j_in_smem"]) >> 1) & 1)
+        d["inner_fp32"] = float((int(d["j_in_smem"]) >> 2) & 1)
         d["j_in_smem"] = float(int(d["j_in_smem"]) & 1)
         return d
 

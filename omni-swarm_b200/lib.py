@@ -29,7 +29,7 @@ class SolveOptions(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("max_pcg_iterations", C.c_int32), ("max_time_s", C.c_double),
                 ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
                 ("parameter_tolerance", C.c_double), ("pcg_tolerance", C.c_double),
-                ("initial_trust_radius", C.c_double), ("preconditioner", C.c_int32), ("reserved", C.c_int32)]
+                ("initial_trust_radius", C.c_double), ("preconditioner", C.c_int32), ("inner_precision", C.c_int32)]
 
 
 class SolveSummary(C.Structure):

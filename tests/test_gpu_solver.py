@@ -123,3 +123,18 @@ def test_chain_preconditioner_same_answer_fewer_iterations(solver):
     p2, s2 = solver.solve(g2, tight(solver))
     assert np.abs(p2[perm] - pt_ch).max() < 1e-5
     assert s2.pcg_iterations < 2 * st_ch.pcg_iterations + 50
+
+
+def test_fp32_inner_solve_matches_fp64_inner_solve(solver):
+    """Default options run the PCG in fp32 (LM needs an inexact step only); forcing fp64 inside must give the same outer
+    iterations, (almost) the same inner iteration count and the same poses far inside the parity tolerance."""
+    for g in (synth.pose_graph_c5(0), synth.pose_graph(5, 100, seed=1, outlier_frac=0.1)):
+        p32, s32 = solver.solve(g)
+        assert solver.phase_cycles()["inner_fp32"] == 1.0
+        o = solver.default_options(); o.inner_precision = 1
+        p64, s64 = solver.solve(g, o)
+        assert solver.phase_cycles()["inner_fp32"] == 0.0
+        assert s32.iterations == s64.iterations and s32.termination == s64.termination
+        assert abs(s32.pcg_iterations - s64.pcg_iterations) <= max(10, s64.pcg_iterations // 20)
+        assert abs(s32.final_cost - s64.final_cost) < 1e-7 * s64.final_cost
+        assert np.abs(p32 - p64).max() < 1e-5
