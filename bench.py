@@ -438,6 +438,24 @@ def run_ours(args):
                                         + ("164 MB > 126 MB L2" if rows == 10_000 else "819 MB >> L2")})
             idx.close(); del blk
 
+    # ---- config C2: one pinhole stream, the reference's own call pattern (one synchronous inference() per image,
+    #      host buffers in and out) -- SuperPoint + NetVLAD on a single 640x480 frame ----
+    c2 = None
+    if rank == 0:
+        sp1 = host.SuperPoint(spw, comp, mean, W, H, 0.015, MAX_NUM, max_batch=1)
+        nv1 = host.NetVLAD(nvw, W, H, max_batch=1)
+        img1 = np.ascontiguousarray(frames[0][0][0])
+        for _ in range(3):
+            sp1.inference(img1); nv1.inference(img1)
+        reps = 40
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            kp1, _d1 = sp1.inference(img1); nv1.inference(img1)
+        dt = (time.perf_counter() - t0) / reps
+        c2 = {"workload": "C2: single 640x480 pinhole frame, SuperPoint.inference + NetVLAD.inference, host buffers, synchronous",
+              "frames_per_s": 1.0 / dt, "ms_per_frame": dt * 1e3, "n_kpts": int(len(kp1))}
+        sp1.close(); nv1.close()
+
     # ---- SURVEY 8e alternative: the 50 k-row database sharded by rows across the ranks (2 exchange steps per search) ----
     match_sharded = None
     if world > 1:
@@ -482,6 +500,10 @@ def run_ours(args):
         _, s_bj = solver.solve(g, o_bj)
         bj = {"solve_ms": float(s_bj.solve_ms), "pcg_iterations": int(s_bj.pcg_iterations), "iterations": int(s_bj.iterations),
               "final_cost": float(s_bj.final_cost)}
+        o_64 = solver.default_options(); o_64.inner_precision = 1
+        _, s_64 = solver.solve(g, o_64)
+        f64 = {"solve_ms": float(s_64.solve_ms), "pcg_iterations": int(s_64.pcg_iterations), "iterations": int(s_64.iterations),
+               "final_cost": float(s_64.final_cost)}
         poses, summ = solver.solve(g)                           # (phase_cycles below belong to the default solve)
         solve = {"solve_ms": float(np.median(times)), "iterations": int(summ.iterations),
                  "pcg_iterations": int(summ.pcg_iterations), "final_cost": float(summ.final_cost),
@@ -489,9 +511,11 @@ def run_ours(args):
                  "max_err_vs_gt_m": float(np.abs(poses[:, :3] - g["gt"][:, :3]).max()),
                  "us_per_pcg_iteration": float(np.median(times)) * 1e3 / max(1, summ.pcg_iterations),
                  "phase_cycles": solver.phase_cycles(),
+                 "chain_sweep_cycles_per_iteration_by_cta_warp": (solver.chain_cycles() / max(1, summ.pcg_iterations)).round(0).tolist(),
                  "preconditioner": "chain (block-tridiagonal along the path cover, 16-node segments)",
-                 "block_jacobi": bj,
-                 "note": "latency bound: 3 barriers per PCG iteration; whole problem lives in shared memory / L2",
+                 "inner_precision": "fp32 PCG inside fp64 Levenberg-Marquardt",
+                 "block_jacobi": bj, "fp64_inner": f64,
+                 "note": "latency bound: 3 cluster barriers + 2 L2 round trips per PCG iteration; whole problem lives in shared memory / L2",
                  "approx_bytes_per_linearisation": lin_bytes}
 
     if rank == 0:
@@ -504,7 +528,7 @@ def run_ours(args):
                         "h2d_bytes_per_step": 2 * N_DIRS * W * H, "d2h_bytes_per_step": lib.RECORD_BYTES + lib.RESULT_BYTES,
                         "ms_per_step": e2e_s * 1e3 / args.steps},
                 "roofline": roofline, "roofline_conv_stack": roofline_stack, "roofline_match": roofline_match,
-                "match_sweep": match_sweep, "match_sharded": match_sharded,
+                "match_sweep": match_sweep, "match_sharded": match_sharded, "c2_pinhole": c2,
                 "stage_ms": stages,
                 "loop_check": {"accepted": int(res.accepted), "hit_id": int(res.hit_id), "hit_score": float(res.hit_score),
                                "n_kpts": list(rec.n_kpts), "n_matches": list(res.n_matches)},

@@ -174,9 +174,8 @@ typedef struct {
   int32_t preconditioner;        /* OSB_PRECOND_AUTO (chain block-tridiagonal when the graph fits the one-cluster fast
                                     path, else block-Jacobi) or OSB_PRECOND_BLOCK_JACOBI */
   int32_t inner_precision;       /* arithmetic INSIDE the PCG (Jacobian blocks, direction/residual vectors, preconditioner):
-                                    OSB_INNER_AUTO = fp32 when pcg_tolerance >= 1e-4 (LM only needs an inexact step; fp64
-                                    FMA issues ~50x slower than fp32 on this GPU), else fp64.  Residuals, costs, gradient,
-                                    poses and all LM decisions are always fp64. */
+                                    OSB_INNER_AUTO = fp32 when pcg_tolerance >= 1e-4 (LM only needs an inexact step), else
+                                    fp64.  Residuals, costs, gradient, poses and all LM decisions are always fp64. */
 } osb_solve_options;
 #define OSB_PRECOND_AUTO 0
 #define OSB_PRECOND_BLOCK_JACOBI 1
@@ -208,6 +207,8 @@ osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses, const uin
  * 0 = cooperative grid, [10] bit 0 = Jacobians in shared memory, bit 1 = chain preconditioner, bit 2 = fp32 inner
  * arithmetic, [11] threads per CTA. */
 osb_status osb_solver_phase_cycles(osb_solver* h, double* out12);
+/* profiling aid: SM-clock cycles each warp spent in the chain-preconditioner sweeps of the LAST solve, [16 CTAs][8 warps] */
+osb_status osb_solver_chain_cycles(osb_solver* h, double* out128);
 /* host-only (no GPU needed): the node numbering the solver uses for its chain preconditioner -- a greedy maximum-weight
  * path cover of the factor graph (on a swarm graph: every drone's odometry chain).  order_out[i] = caller's node id of
  * internal node i; link_out[i] = 1 iff internal node i-1 precedes i on its path and i % 16 != 0. */

@@ -172,14 +172,15 @@ __device__ __forceinline__ double factor_sqnorm(int type, const double* __restri
   return r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
 }
 
-// The inner (PCG) arithmetic type.  Measured on this B200 (scripts/microbench/fp64_rate.cu): an SM issues one DFMA
-// warp-instruction every ~12 cycles but ~4 FFMA warp-instructions per cycle, and with the fp64 version of this kernel the
-// CG iteration was bound by exactly that pipe (2300 DFMA warp-instructions per SM per iteration ~ 28 k of 35 k cycles).
-// Levenberg-Marquardt only needs an INEXACT step (relative residual 1e-2), so everything inside the PCG -- Jacobian
-// blocks, direction / residual / preconditioner vectors, the chain factorisation -- runs in fp32 when the requested
-// pcg_tolerance allows (>= 1e-4); residuals, costs, the gradient J^T r, the diagonal, the poses and every LM decision stay
-// fp64.  A numpy emulation of the same loop gives the same iteration counts and poses within 1e-8 of the all-fp64 solve
-// (DESIGN.md).  T = double is kept for tight tolerances (parity tests).
+// The inner (PCG) arithmetic type.  Levenberg-Marquardt only needs an INEXACT step (relative residual 1e-2), so
+// everything inside the PCG -- Jacobian blocks, direction / residual / preconditioner vectors, contribution slots, the
+// chain factorisation -- runs in fp32 when the requested pcg_tolerance allows (>= 1e-4); residuals, costs, the gradient
+// J^T r, the diagonal, the poses and every LM decision stay fp64.  fp32 halves what bounds a CG iteration here: the
+// 32-bit shuffles of the preconditioner sweeps, the bytes of every cross-thread gather through L2, the shared-memory
+// footprint of the Jacobians (96 KB instead of 192 KB) and the live registers.  (It is NOT an fp64-throughput issue:
+// scripts/microbench/fp64_rate.cu measures 62 DFMA lanes/clk/SM against 117 FFMA lanes/clk/SM on this B200.)  A numpy
+// emulation of the same loop gives the same iteration counts and poses within 1e-8 of the all-fp64 solve;
+// tests/test_gpu_solver.py checks it on the GPU.  T = double is kept for tight tolerances (parity tests).
 struct SolverDev {
   int n, m;
   int fpc;                 // factors per CTA (contiguous block of the factor list)
@@ -294,6 +295,14 @@ struct JStore {
   T* base; int stride; int off;
   __device__ __forceinline__ T& at(int i, int li) const { return base[(size_t)i * stride + off + li]; }
 };
+
+// clock read that cannot be scheduled before `v` has been computed (phase attribution only)
+__device__ __forceinline__ long long clock_after(float v) {
+  long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) : "f"(v) : "memory"); return c;
+}
+__device__ __forceinline__ long long clock_after(double v) {
+  long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) : "d"(v) : "memory"); return c;
+}
 
 // vector loads / stores of a node's 4-vector (one 16-byte access in fp32, two in fp64), L2-coherent
 __device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
@@ -509,7 +518,7 @@ graph_solve_kernel(SolverDev P) {
   const long long k0 = clock64();
   if (gtid == 0) {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-    for (int i = 0; i < 8; ++i) P.dbg[i] = 0;
+    for (int i = 0; i < 8 + GS_MAX_CLUSTER * (GS_THREADS / 32); ++i) P.dbg[i] = 0;
   }
 
   int cur = 0;
@@ -792,7 +801,7 @@ graph_solve_kernel(SolverDev P) {
           for (int i = 0; i < 4; ++i) v1b[0] += pl[i] * ap[i];
         }
       }
-      long long c3 = clock64();
+      long long c3 = clock_after(v1b[0]);
       double r1[1];
       grid_reduce_sum<1>(v1b, r1, P, parity, sh, grid); parity ^= 1;
       long long c4 = clock64();
@@ -802,15 +811,18 @@ graph_solve_kernel(SolverDev P) {
       // node phase 2: delta += alpha p, res -= alpha Ap, z = M^-1 res; partial rz_new, rr
       T v22[2] = {T(0), T(0)};
       if (fast) {
-        if (is_node) {
+        // (no is_node guard: pn / apn are zero on the other lanes, and a divergent branch here would send the warp
+        //  through the slow collective-shuffle path of chain_apply)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { dn[i] += alpha * pn[i]; rn[i] -= alpha * apn[i]; }
-        }
+        for (int i = 0; i < 4; ++i) { dn[i] += alpha * pn[i]; rn[i] -= alpha * apn[i]; }
         if (chain) {                                          // warp-collective: every lane takes part in the sweeps
           T Lr[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) Lr[i] = Ls[i * GS_THREADS + threadIdx.x];
+          const long long q0 = clock_after(rn[0] + Lr[15]);
           chain_apply(Mi, Lr, lk, sl, rn, zn);
+          const long long q1 = clock_after(zn[0] + zn[3]);
+          if ((threadIdx.x & 31) == 0) P.dbg[8 + blockIdx.x * (GS_THREADS / 32) + (threadIdx.x >> 5)] += q1 - q0;
         } else if (is_node) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -841,7 +853,7 @@ graph_solve_kernel(SolverDev P) {
           for (int i = 0; i < 4; ++i) { v22[0] += rl[i] * zl[i]; v22[1] += rl[i] * rl[i]; }
         }
       }
-      long long c5 = clock64();
+      long long c5 = clock_after(v22[0] + v22[1]);
       double r22[2];
       grid_reduce_sum<2>(v22, r22, P, parity, sh, grid); parity ^= 1;
       if (gtid == 0) {
@@ -1015,8 +1027,8 @@ extern "C" osb_status osb_solver_create(osb_solver** out, int max_nodes, int max
   OSB_CUDA(cudaMalloc(&h->d_partial, 2 * 4 * (size_t)num_sms() * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_out, 4 * n * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_summary, sizeof(osb_solve_summary)));
-  OSB_CUDA(cudaMalloc(&h->d_dbg, 8 * sizeof(long long)));
-  OSB_CUDA(cudaMemset(h->d_dbg, 0, 8 * sizeof(long long)));
+  OSB_CUDA(cudaMalloc(&h->d_dbg, (8 + 128) * sizeof(long long)));
+  OSB_CUDA(cudaMemset(h->d_dbg, 0, (8 + 128) * sizeof(long long)));
   OSB_CUDA(cudaMalloc(&h->d_link, n));
   OSB_CUDA(cudaMalloc(&h->d_es_ptr, (n + 1) * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&h->d_es_slot, m * sizeof(int32_t)));
@@ -1271,6 +1283,16 @@ extern "C" osb_status osb_solver_phase_cycles(osb_solver* h, double* out12) {
   OSB_CUDA(cudaMemcpy(c, h->d_dbg, sizeof(c), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 8; ++i) out12[i] = (double)c[i];
   out12[8] = h->last_grid; out12[9] = h->last_cluster; out12[10] = h->last_jsmem + 2 * h->last_chain + 4 * h->last_f32; out12[11] = GS_THREADS;
+  return OSB_OK;
+}
+
+// profiling aid: per-warp cycles spent in the chain preconditioner sweeps of the last solve, [16 CTAs][8 warps]
+extern "C" osb_status osb_solver_chain_cycles(osb_solver* h, double* out128) {
+  OSB_REQUIRE(h != nullptr && out128 != nullptr, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  long long c[128];
+  OSB_CUDA(cudaMemcpy(c, h->d_dbg + 8, sizeof(c), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 128; ++i) out128[i] = (double)c[i];
   return OSB_OK;
 }
 

@@ -249,6 +249,11 @@ class PoseGraphSolver:
         d["j_in_smem"] = float(int(d["j_in_smem"]) & 1)
         return d
 
+    def chain_cycles(self) -> np.ndarray:
+        c = np.zeros(128, np.float64)
+        _l.check(self._lib.osb_solver_chain_cycles(self._h, _l.ptr(c)))
+        return c.reshape(16, 8)
+
     @staticmethod
     def chain_plan(g: dict):
         """Host-only: the solver's internal node numbering (greedy maximum-weight path cover) ->

@@ -101,6 +101,7 @@ _SIG = {
     "osb_solver_destroy": (C.c_int, [_P]),
     "osb_solver_solve": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]),
     "osb_solver_phase_cycles": (C.c_int, [_P, _P]),
+    "osb_solver_chain_cycles": (C.c_int, [_P, _P]),
     "osb_solver_chain_plan": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P]),
     "osb_solver_linearize": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "osb_frontend_create": (C.c_int, [C.POINTER(_P), C.POINTER(FrontendConfig), _P, C.c_size_t, _P, _P, _P, C.c_size_t]),
