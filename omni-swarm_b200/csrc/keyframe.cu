@@ -266,7 +266,8 @@ struct osb_frontend {
   osb_loop_result* d_result = nullptr;
   // stage profiling: ev[i] marks the START of stage i, ev[8] the end of the last one
   cudaStream_t stream2 = nullptr;                 // NetVLAD runs here, overlapped with the keypoint kernels
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t stream_sp = nullptr;               // SuperPoint runs here at the highest stream priority (null: caller's stream)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sp = nullptr;
   bool profiling = false;
   cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid[9] = {false, false, false, false, false, false, false, false, false};
@@ -325,6 +326,17 @@ extern "C" osb_status osb_frontend_create(osb_frontend** out, const osb_frontend
 #define FE_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error("osb_frontend_create", cudaGetErrorString(e_)); osb_frontend_destroy(h); return OSB_ERR_CUDA; } } while (0)
   FE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   FE_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  {
+    // SuperPoint is the critical path, NetVLAD (stream2, default = lowest priority) only has to finish before the pack:
+    // the convolution CTAs of SuperPoint are dispatched first whenever both streams have work.  OSB_FE_PRIO=0: off.
+    const char* e = getenv("OSB_FE_PRIO");
+    if (!(e && atoi(e) == 0)) {
+      int least = 0, greatest = 0;
+      FE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      FE_CUDA(cudaStreamCreateWithPriority(&h->stream_sp, cudaStreamNonBlocking, greatest));
+    }
+  }
+  FE_CUDA(cudaEventCreateWithFlags(&h->ev_sp, cudaEventDisableTiming));
   FE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   FE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   FE_TRY(h->sp.init(sp_weights, n_sp_weights, cfg->width, cfg->height, cfg->sp_thres, mn, pca_comp, pca_mean, 2 * nd));
@@ -378,6 +390,8 @@ extern "C" osb_status osb_frontend_destroy(osb_frontend* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->stream_sp) cudaStreamDestroy(h->stream_sp);
+  if (h->ev_sp) cudaEventDestroy(h->ev_sp);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return OSB_OK;
@@ -401,14 +415,20 @@ static osb_status fe_extract_dev(osb_frontend* h, const uint8_t* img_dev /*[2*nd
   // NetVLAD on the up images writes straight into the record (image_desc, loop_cam.cpp:553-556)
   if ((s = h->nv.infer_dev(img_dev, nd, &record_dev->global_desc[0][0], h->stream2)) != OSB_OK) return s;
   OSB_CUDA(cudaEventRecord(h->ev_join, h->stream2));
-  fe_mark(h, 0, st);
+  cudaStream_t sps = h->stream_sp ? h->stream_sp : st;
+  if (sps != st) OSB_CUDA(cudaStreamWaitEvent(sps, h->ev_fork, 0));
+  fe_mark(h, 0, sps);
   // network; the keypoint kernel is forked beside the descriptor head inside (superpoint.cu) and joined before return
   const SuperPoint::KpJob kp{h->sp.d_nk, h->sp.d_kpts, h->sp.d_conf};
-  if ((s = h->sp.network(img_dev, 2 * nd, st, &kp)) != OSB_OK) return s;
+  if ((s = h->sp.network(img_dev, 2 * nd, sps, &kp)) != OSB_OK) return s;
   h->sp.last_batch = 2 * nd;
-  fe_mark(h, 1, st);
-  if ((s = h->sp.descriptors(2 * nd, kp, h->sp.d_out, st)) != OSB_OK) return s;
-  fe_mark(h, 2, st);
+  fe_mark(h, 1, sps);
+  if ((s = h->sp.descriptors(2 * nd, kp, h->sp.d_out, sps)) != OSB_OK) return s;
+  fe_mark(h, 2, sps);
+  if (sps != st) {
+    OSB_CUDA(cudaEventRecord(h->ev_sp, sps));
+    OSB_CUDA(cudaStreamWaitEvent(st, h->ev_sp, 0));
+  }
   OSB_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));      // join (stage 2 = the part of NetVLAD that was not hidden)
   fe_mark(h, 3, st);
   // stereo match up[d] <-> down[d] (loop_cam.cpp:388)

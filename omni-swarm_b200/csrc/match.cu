@@ -419,38 +419,70 @@ bf_dist_kernel(const float* const* __restrict__ qptr, const int32_t* __restrict_
 }
 
 // one CTA per pair: forward / backward argmin (first minimum wins), mutual test, ordered compaction.
+// ONE coalesced pass over the distance matrix: warp w owns rows w, w+8, ...; a lane holds columns lane, lane+32, ... of
+// the row.  Row minimum = lane-local scan (ascending j, strict <) + shuffle reduction (ties -> smaller j); column minima
+// accumulate per lane over the warp's rows (ascending i, strict <) and the 8 warps are combined in warp order per row
+// block -- both reproduce "first minimum wins" of the sequential scan exactly.
+constexpr int BF_MAXN = 256;                       // max_n <= 256 (one thread per query row in the compaction)
 __global__ void __launch_bounds__(256)
 bf_crosscheck_kernel(const float* __restrict__ dist, const int32_t* __restrict__ nq, const int32_t* __restrict__ nt,
                      int max_n, int out_stride, int32_t* __restrict__ qi, int32_t* __restrict__ ti,
                      float* __restrict__ dout, int32_t* __restrict__ n_out, int32_t* __restrict__ map_out) {
-  __shared__ int fwd[256], bwd[256];
-  __shared__ float fdist[256];
+  __shared__ int fwd[BF_MAXN], bwd[BF_MAXN];
+  __shared__ float fdist[BF_MAXN];
+  __shared__ float cmin[8][BF_MAXN];
+  __shared__ int cidx[8][BF_MAXN];
   __shared__ int warp_cnt[8];
-  const int pair = blockIdx.x, tid = threadIdx.x;
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_q = nq[pair], n_t = nt[pair];
   const float* dp = dist + (size_t)pair * max_n * max_n;
-  if (tid < n_q && n_t > 0) {
-    float best = dp[(size_t)tid * max_n];
-    int bj = 0;
-    for (int j = 1; j < n_t; ++j) {
-      const float d = dp[(size_t)tid * max_n + j];
-      if (d < best) { best = d; bj = j; }
+  constexpr int CPL = BF_MAXN / 32;               // columns per lane
+  float cbest[CPL];
+  int cbi[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) { cbest[c] = INFINITY; cbi[c] = -1; }
+  for (int i = warp; i < n_q; i += 8) {
+    float v[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int j = lane + 32 * c;
+      v[c] = (j < n_t) ? dp[(size_t)i * max_n + j] : INFINITY;
     }
-    fwd[tid] = bj; fdist[tid] = best;
+    float best = INFINITY;
+    int bj = 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int j = lane + 32 * c;
+      if (j < n_t) {
+        if (v[c] < best || bj == 0x7fffffff) { best = v[c]; bj = j; }
+        if (v[c] < cbest[c] || cbi[c] < 0) { cbest[c] = v[c]; cbi[c] = i; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (oj != 0x7fffffff && (bj == 0x7fffffff || ob < best || (ob == best && oj < bj))) { best = ob; bj = oj; }
+    }
+    if (lane == 0 && n_t > 0) { fwd[i] = bj; fdist[i] = best; }
   }
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) { cmin[warp][lane + 32 * c] = cbest[c]; cidx[warp][lane + 32 * c] = cbi[c]; }
+  __syncthreads();
   if (tid < n_t && n_q > 0) {
-    float best = dp[tid];
-    int bi = 0;
-    for (int i = 1; i < n_q; ++i) {
-      const float d = dp[(size_t)i * max_n + tid];
-      if (d < best) { best = d; bi = i; }
+    // rows of warp w are w, w+8, ...: the sequential scan's winner is the smallest row index among the minima
+    float best = INFINITY;
+    int bi = -1;
+    for (int w = 0; w < 8; ++w) {
+      const float d = cmin[w][tid];
+      const int i = cidx[w][tid];
+      if (i >= 0 && (bi < 0 || d < best || (d == best && i < bi))) { best = d; bi = i; }
     }
     bwd[tid] = bi;
   }
   __syncthreads();
   const bool keep = (tid < n_q) && (n_t > 0) && (bwd[fwd[tid]] == tid);
   const unsigned bal = __ballot_sync(0xffffffffu, keep);
-  const int lane = tid & 31, warp = tid >> 5;
   if (lane == 0) warp_cnt[warp] = __popc(bal);
   __syncthreads();
   int base = 0, total = 0;

@@ -30,7 +30,11 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
   W = width; H = height; thres = thres_; max_num = max_num_; max_batch = max_batch_;
   Hc = H / 8; Wc = W / 8;
   OSB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  OSB_CUDA(cudaStreamCreateWithFlags(&kp_stream, cudaStreamNonBlocking));
+  {
+    int least = 0, greatest = 0;
+    OSB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    OSB_CUDA(cudaStreamCreateWithPriority(&kp_stream, cudaStreamNonBlocking, greatest));
+  }
   OSB_CUDA(cudaEventCreateWithFlags(&ev_semi, cudaEventDisableTiming));
   OSB_CUDA(cudaEventCreateWithFlags(&ev_kp, cudaEventDisableTiming));
   if (const char* e = getenv("OSB_SP_OVERLAP")) overlap_kp = atoi(e) != 0;
