@@ -419,29 +419,32 @@ bf_dist_kernel(const float* const* __restrict__ qptr, const int32_t* __restrict_
 }
 
 // one CTA per pair: forward / backward argmin (first minimum wins), mutual test, ordered compaction.
-// ONE coalesced pass over the distance matrix: warp w owns rows w, w+8, ...; a lane holds columns lane, lane+32, ... of
-// the row.  Row minimum = lane-local scan (ascending j, strict <) + shuffle reduction (ties -> smaller j); column minima
-// accumulate per lane over the warp's rows (ascending i, strict <) and the 8 warps are combined in warp order per row
-// block -- both reproduce "first minimum wins" of the sequential scan exactly.
+// ONE coalesced pass over the distance matrix with 32 warps: warp w owns rows w, w+32, ...; a lane holds columns lane,
+// lane+32, ... of the row.  Row minimum = lane-local scan (ascending j, strict <) + shuffle reduction (ties -> smaller
+// j).  Column minimum = min over 64-bit keys (distance bits : row) -- distances are >= +0, so their bit patterns order
+// like the floats and a tie resolves to the smaller row: per-lane running key, then one shared-memory atomicMin per
+// (warp, column).  Both reproduce "first minimum wins" of the sequential scan exactly.
 constexpr int BF_MAXN = 256;                       // max_n <= 256 (one thread per query row in the compaction)
-__global__ void __launch_bounds__(256)
+constexpr int BF_CC_THREADS = 1024;
+__global__ void __launch_bounds__(BF_CC_THREADS)
 bf_crosscheck_kernel(const float* __restrict__ dist, const int32_t* __restrict__ nq, const int32_t* __restrict__ nt,
                      int max_n, int out_stride, int32_t* __restrict__ qi, int32_t* __restrict__ ti,
                      float* __restrict__ dout, int32_t* __restrict__ n_out, int32_t* __restrict__ map_out) {
-  __shared__ int fwd[BF_MAXN], bwd[BF_MAXN];
+  __shared__ int fwd[BF_MAXN];
   __shared__ float fdist[BF_MAXN];
-  __shared__ float cmin[8][BF_MAXN];
-  __shared__ int cidx[8][BF_MAXN];
+  __shared__ unsigned long long ckey[BF_MAXN];
   __shared__ int warp_cnt[8];
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = BF_CC_THREADS / 32, CPL = BF_MAXN / 32;
   const int n_q = nq[pair], n_t = nt[pair];
   const float* dp = dist + (size_t)pair * max_n * max_n;
-  constexpr int CPL = BF_MAXN / 32;               // columns per lane
-  float cbest[CPL];
-  int cbi[CPL];
+  if (tid < BF_MAXN) ckey[tid] = ~0ull;
+  __syncthreads();
+  unsigned long long cbest[CPL];
 #pragma unroll
-  for (int c = 0; c < CPL; ++c) { cbest[c] = INFINITY; cbi[c] = -1; }
-  for (int i = warp; i < n_q; i += 8) {
+  for (int c = 0; c < CPL; ++c) cbest[c] = ~0ull;
+#pragma unroll 2
+  for (int i = warp; i < n_q; i += NW) {
     float v[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
@@ -455,7 +458,8 @@ bf_crosscheck_kernel(const float* __restrict__ dist, const int32_t* __restrict__
       const int j = lane + 32 * c;
       if (j < n_t) {
         if (v[c] < best || bj == 0x7fffffff) { best = v[c]; bj = j; }
-        if (v[c] < cbest[c] || cbi[c] < 0) { cbest[c] = v[c]; cbi[c] = i; }
+        const unsigned long long key = ((unsigned long long)__float_as_uint(v[c]) << 32) | (unsigned)i;
+        cbest[c] = min(cbest[c], key);
       }
     }
 #pragma unroll
@@ -467,23 +471,12 @@ bf_crosscheck_kernel(const float* __restrict__ dist, const int32_t* __restrict__
     if (lane == 0 && n_t > 0) { fwd[i] = bj; fdist[i] = best; }
   }
 #pragma unroll
-  for (int c = 0; c < CPL; ++c) { cmin[warp][lane + 32 * c] = cbest[c]; cidx[warp][lane + 32 * c] = cbi[c]; }
+  for (int c = 0; c < CPL; ++c)
+    if (cbest[c] != ~0ull) atomicMin(&ckey[lane + 32 * c], cbest[c]);
   __syncthreads();
-  if (tid < n_t && n_q > 0) {
-    // rows of warp w are w, w+8, ...: the sequential scan's winner is the smallest row index among the minima
-    float best = INFINITY;
-    int bi = -1;
-    for (int w = 0; w < 8; ++w) {
-      const float d = cmin[w][tid];
-      const int i = cidx[w][tid];
-      if (i >= 0 && (bi < 0 || d < best || (d == best && i < bi))) { best = d; bi = i; }
-    }
-    bwd[tid] = bi;
-  }
-  __syncthreads();
-  const bool keep = (tid < n_q) && (n_t > 0) && (bwd[fwd[tid]] == tid);
+  const bool keep = (tid < n_q) && (n_t > 0) && ((int)(unsigned)(ckey[fwd[tid]] & 0xffffffffull) == tid);
   const unsigned bal = __ballot_sync(0xffffffffu, keep);
-  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  if (lane == 0 && warp < 8) warp_cnt[warp] = __popc(bal);
   __syncthreads();
   int base = 0, total = 0;
   for (int w = 0; w < 8; ++w) { if (w < warp) base += warp_cnt[w]; total += warp_cnt[w]; }
@@ -505,7 +498,7 @@ osb_status bf_match_device(int n_pairs, int max_n, int out_stride, const float* 
   dim3 g1(cdiv(max_n, BF_ROWS), n_pairs);
   OSB_LAUNCH(bf_dist_kernel, g1, 256, 0, st, q, nq, t, nt, max_n, dist_scratch);
   OSB_CHECK_LAUNCH();
-  OSB_LAUNCH(bf_crosscheck_kernel, n_pairs, 256, 0, st, dist_scratch, nq, nt, max_n, out_stride, qi, ti, dout, n_out,
+  OSB_LAUNCH(bf_crosscheck_kernel, n_pairs, BF_CC_THREADS, 0, st, dist_scratch, nq, nt, max_n, out_stride, qi, ti, dout, n_out,
              map_out);
   OSB_CHECK_LAUNCH();
   return OSB_OK;
