@@ -218,7 +218,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "keyframes/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, world):
@@ -538,13 +538,22 @@ def run_ours(args):
             line["solve_ms"] = solve["solve_ms"]
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else that lands on fd 1 (NCCL prints its
+    version banner there, libraries print progress) was redirected to stderr at start-up."""
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 if __name__ == "__main__":
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
