@@ -364,65 +364,75 @@ __device__ __forceinline__ void split_store8(__half* hi, __half* lo, const float
   *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// One thread per pixel computes all 64 channels (9 LUT loads, 576 FMAs); the 128 pixels of a CTA are contiguous in the
-// NHWC planes, so each plane's 16 KB tile is staged in shared memory (16-byte chunks XOR-swizzled by the pixel index)
-// and written out with fully coalesced 16-byte stores.  The kernel is bound by its 629 MB of stores per keyframe.
-__global__ void __launch_bounds__(128)
+// conv1a (Cin = 1) + bias + ReLU -> split fp16 planes.  Thread = (8 output channels, one pixel column of a 32 x 8 tile):
+// the 72 weights of its channels live in registers for the whole tile, the inputs (after the u8 -> f32 LUT) are staged
+// once per CTA in shared memory and slide down the column through registers (3 broadcast LDS per pixel instead of one
+// LDS per FMA pair), and the 8 threads of a pixel write its 128-byte channel vector as eight adjacent 16-byte chunks --
+// a warp stores 4 pixels x 128 B contiguously per plane, no staging of the output.  The plane scale (a power of two) is
+// folded into weights and bias, and the 9 taps (ky-major) accumulate onto the bias.
+constexpr int CF_TW = 32, CF_TH = 8;
+__global__ void __launch_bounds__(256)
 conv_first_split_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ lut,
                         const uint8_t* __restrict__ img, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                         int H, int W, float out_scale) {
-  __shared__ __align__(16) float sw[9][64];
-  __shared__ __align__(16) float sb[64];
-  __shared__ float slut[256];
-  __shared__ uint4 tile_hi[128 * 8], tile_lo[128 * 8];       // [pixel][16-byte chunk ^ (pixel & 7)]
-  for (int e = threadIdx.x; e < 9 * 64; e += blockDim.x) (&sw[0][0])[e] = w[e];
-  for (int e = threadIdx.x; e < 64; e += blockDim.x) sb[e] = bias[e];
-  for (int e = threadIdx.x; e < 256; e += blockDim.x) slut[e] = lut[e];
+  __shared__ float sin_[CF_TH + 2][CF_TW + 2];
+  const int tid = threadIdx.x, b = blockIdx.z, x0 = blockIdx.x * CF_TW, y0 = blockIdx.y * CF_TH;
+  const uint8_t* ib = img + (size_t)b * H * W;
+  for (int e = tid; e < (CF_TH + 2) * (CF_TW + 2); e += 256) {
+    const int r = e / (CF_TW + 2), c = e % (CF_TW + 2);
+    const int gy = y0 + r - 1, gx = x0 + c - 1;
+    sin_[r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(lut + ib[(size_t)gy * W + gx]) : 0.f;
+  }
+  const int cg = tid & 7, px = tid >> 3;
+  float wr[9][8], br[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + t * 64 + cg * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + t * 64 + cg * 8 + 4));
+    wr[t][0] = w0.x; wr[t][1] = w0.y; wr[t][2] = w0.z; wr[t][3] = w0.w;
+    wr[t][4] = w1.x; wr[t][5] = w1.y; wr[t][6] = w1.z; wr[t][7] = w1.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[t][j] *= out_scale;          // power of two: exact, commutes with every rounding below
+  }
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8 + 4));
+    br[0] = b0.x; br[1] = b0.y; br[2] = b0.z; br[3] = b0.w; br[4] = b1.x; br[5] = b1.y; br[6] = b1.z; br[7] = b1.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) br[j] *= out_scale;
+  }
   __syncthreads();
-  const int b = blockIdx.y, t = threadIdx.x;
-  const int p0 = blockIdx.x * 128;
-  const int p = p0 + t;
-  const int HW = H * W;
-  if (p < HW) {
-    const int oy = p / W, ox = p % W;
-    const uint8_t* ib = img + (size_t)b * HW;
-    float in[9];
+  const int x = x0 + px;
+  float in[3][3];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+  for (int k = 0; k < 3; ++k) { in[0][k] = sin_[0][px + k]; in[1][k] = sin_[1][px + k]; }
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int gy = oy + ky - 1, gx = ox + kx - 1;
-        in[ky * 3 + kx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? slut[ib[(size_t)gy * W + gx]] : 0.f;
-      }
-#pragma unroll 2
-    for (int o8 = 0; o8 < 8; ++o8) {
+  for (int r = 0; r < CF_TH; ++r) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) in[2][k] = sin_[r + 2][px + k];
+    const int y = y0 + r;
+    if (y < H && x < W) {
       uint32_t h[4], l[4];
 #pragma unroll
       for (int j2 = 0; j2 < 4; ++j2) {
-        float a0 = 0.f, a1 = 0.f;
+        float a0 = br[2 * j2], a1 = br[2 * j2 + 1];                // bias first: 9 taps accumulate onto it
 #pragma unroll
-        for (int tt = 0; tt < 9; ++tt) {
-          a0 = fmaf(in[tt], sw[tt][8 * o8 + 2 * j2], a0);
-          a1 = fmaf(in[tt], sw[tt][8 * o8 + 2 * j2 + 1], a1);
+        for (int t = 0; t < 9; ++t) {
+          a0 = fmaf(in[t / 3][t % 3], wr[t][2 * j2], a0);
+          a1 = fmaf(in[t / 3][t % 3], wr[t][2 * j2 + 1], a1);
         }
-        const float s0 = fmaxf(a0 + sb[8 * o8 + 2 * j2], 0.f) * out_scale, s1 = fmaxf(a1 + sb[8 * o8 + 2 * j2 + 1], 0.f) * out_scale;
+        const float s0 = fmaxf(a0, 0.f), s1 = fmaxf(a1, 0.f);
         const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
         const __half l0 = __float2half_rn(s0 - __half2float(h0)), l1 = __float2half_rn(s1 - __half2float(h1));
         h[j2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
         l[j2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
       }
-      tile_hi[t * 8 + (o8 ^ (t & 7))] = make_uint4(h[0], h[1], h[2], h[3]);
-      tile_lo[t * 8 + (o8 ^ (t & 7))] = make_uint4(l[0], l[1], l[2], l[3]);
+      const size_t chunk = (((size_t)b * H + y) * W + x) * 8 + cg;          // 16-byte chunk index inside the plane
+      reinterpret_cast<uint4*>(out_hi)[chunk] = make_uint4(h[0], h[1], h[2], h[3]);
+      reinterpret_cast<uint4*>(out_lo)[chunk] = make_uint4(l[0], l[1], l[2], l[3]);
     }
-  }
-  __syncthreads();
-  const int npx = min(128, HW - p0);
-  uint4* gh = reinterpret_cast<uint4*>(out_hi + ((size_t)b * HW + p0) * 64);
-  uint4* gl = reinterpret_cast<uint4*>(out_lo + ((size_t)b * HW + p0) * 64);
-  for (int i = t; i < npx * 8; i += 128) {
-    const int px = i >> 3, ch = i & 7;
-    gh[i] = tile_hi[px * 8 + (ch ^ (px & 7))];
-    gl[i] = tile_lo[px * 8 + (ch ^ (px & 7))];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { in[0][k] = in[1][k]; in[1][k] = in[2][k]; }
   }
 }
 
@@ -653,8 +663,8 @@ osb_status umma_dwconv_forward(const float* w_tap_c, const float* bias, const fl
 
 osb_status umma_first_forward(const float* w_tap_cout, const float* bias, const float* lut, const uint8_t* img,
                               __half* out_hi, __half* out_lo, int B, int H, int W, float out_scale, cudaStream_t st) {
-  dim3 grid(cdiv(H * W, 128), B);
-  OSB_LAUNCH(conv_first_split_kernel, grid, 128, 0, st, w_tap_cout, bias, lut, img, out_hi, out_lo, H, W, out_scale);
+  dim3 grid(cdiv(W, CF_TW), cdiv(H, CF_TH), B);
+  OSB_LAUNCH(conv_first_split_kernel, grid, 256, 0, st, w_tap_cout, bias, lut, img, out_hi, out_lo, H, W, out_scale);
   OSB_CHECK_LAUNCH();
   return OSB_OK;
 }

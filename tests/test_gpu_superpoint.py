@@ -163,6 +163,32 @@ def test_netvlad_vs_oracle(gpu):
     nv.close()
 
 
+def test_onboard_resolution_400x208(gpu):
+    """The reference's TX2 configuration (400x208 engines, nodelet-sfisheye.launch:45-51; the size loop_tensorrt_test.cpp
+    exercises): pooled maps of 200x104, 100x52 and 50x26 leave ragged 16x8 tiles in both directions."""
+    W, H = 400, 208
+    comp, mean = synth.pca_matrices(0)
+    w = synth.superpoint_weights(0)
+    sp = host.SuperPoint(synth.flatten_sp_weights(w), comp, mean, W, H, 0.015, 200, max_batch=2)
+    imgs = np.stack([synth.image(5, H, W), synth.image(6, H, W, zero_bottom_quarter=True)])
+    out = sp.inference_batch(imgs)
+    for b in range(2):
+        semi_o, desc_o = fr.superpoint_net(imgs[b], w)
+        semi, desc = sp.read("semi", b), sp.read("desc", b)
+        assert rel_err(semi, semi_o) < 1e-4 and rel_err(desc, desc_o) < 1e-4
+        k, d = out[b]
+        rk, _ = fr.get_keypoints(semi, 0.015, 200)
+        assert np.array_equal(k, rk)                      # bit-exact on the device's own heat-map
+        assert rel_err(d, fr.compute_descriptors(desc, rk, W, H, comp, mean)) < 1e-4
+    sp.close()
+    nvw = synth.netvlad_weights(0)
+    nv = host.NetVLAD(synth.flatten_nv_weights(nvw), W, H, max_batch=2)
+    v = nv.inference_batch(imgs)
+    for b in range(2):
+        assert rel_err(v[b], fr.netvlad_net(imgs[b], nvw)) < 1e-4
+    nv.close()
+
+
 def test_tensor_core_path_vs_cuda_core_path(gpu):
     """The tcgen05 convolutions (split-fp16, 3 MMAs per K step) and the fp32 FFMA convolutions are two
     implementations of the same network: both must sit within 1e-4 of the fp32 oracle, and within 1e-5 of each other."""
