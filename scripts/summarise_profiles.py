@@ -118,6 +118,9 @@ def main():
             best = max(out, key=lambda o: bytes_of(o[1]) if "dram__bytes_read.sum" in o[1] else 0)
             traffic[key] = bytes_of(best[1])
             traffic[key + "_kernel"] = best[0][:80]
+    rep = os.path.join(OUT, "prof_solve.ncu-rep")
+    if os.path.exists(rep):
+        ncu_summary(tag, "solve", rep)
     traffic["source"] = f"profiles/{tag}_ncu_*.md (ncu --set full, largest captured launch)"
     json.dump(traffic, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
     b = os.path.join(OUT, "bench.json")
