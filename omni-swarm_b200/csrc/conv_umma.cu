@@ -115,6 +115,7 @@ struct UmmaArgs {
   int relu;                // 0 none, 1 ReLU, 2 ReLU6
   int n_off;               // first output channel of this launch (Cout > 256 runs as several N <= 256 passes)
   int pool;                // 1: fused 2x2 max-pool, the planes written are [B][H/2][W/2][C]
+  int n_split;             // a layer wider than the kernel's N runs as n_split work items per tile (N channels each)
 };
 
 template <int N, bool RES>
@@ -138,6 +139,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_x = (P.W + UM_TW - 1) / UM_TW, tiles_y = (P.H + UM_TH - 1) / UM_TH;
   const int n_tiles = P.B * tiles_x * tiles_y;
+  // work item = (tile, channel block): items of one tile are adjacent, so concurrent CTAs share its activations in L2
+  const int n_items = n_tiles * P.n_split;
   const int halo = P.ks / 2;
   const uint32_t a_box_bytes = (uint32_t)(UM_TH + 2 * halo) * UM_TW * 128;   // bytes of one A plane box
 
@@ -177,7 +180,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     }
     // the activations are the previous kernel's output: wait for the whole grid we depend on (no-op without PDL)
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int tile = item / P.n_split, n_off = P.n_off + (item % P.n_split) * N;
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
       const int x0 = tx * UM_TW, y0 = ty * UM_TH;
       for (int kx = 0; kx < P.ks; ++kx) {
@@ -193,8 +197,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             mbar_wait(b_empty(bs), bph ^ 1);
             const uint32_t sb = b_base + bs * Cfg::B_SLOT;
             mbar_expect_tx(b_full(bs), Cfg::B_SLOT);
-            tma_load_3d(sb, &tm_w_hi, b_full(bs), cs * UM_KC, P.n_off, ky * P.ks + kx);
-            tma_load_3d(sb + Cfg::B_BYTES, &tm_w_lo, b_full(bs), cs * UM_KC, P.n_off, ky * P.ks + kx);
+            tma_load_3d(sb, &tm_w_hi, b_full(bs), cs * UM_KC, n_off, ky * P.ks + kx);
+            tma_load_3d(sb + Cfg::B_BYTES, &tm_w_lo, b_full(bs), cs * UM_KC, n_off, ky * P.ks + kx);
             if (++bs == BS) { bs = 0; bph ^= 1; }
           }
         }
@@ -216,7 +220,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     int acc = 0; uint32_t acc_phase = 0;
     if (RES)
       for (int t = 0; t < 9; ++t) mbar_wait(b_full(t), 0);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * N);
@@ -275,7 +279,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int m = q * 32 + lane;                               // output pixel within the tile
     const int r = m / UM_TW, c = m % UM_TW;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int tile = item / P.n_split, n_off = P.n_off + (item % P.n_split) * N;
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
       const int y = ty * UM_TH + r, x = tx * UM_TW + c;
       const bool inside = (y < P.H) && (x < P.W);
@@ -293,11 +298,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         uint32_t v[16], vc[16];
         tmem_ld16(t_row + n0, v);
         tmem_ld16(t_row + N + n0, vc);
-        if (n0 >= P.out_c) continue;                               // warp-uniform
+        if (n_off - P.n_off + n0 >= P.out_c) continue;              // warp-uniform
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float a = fmaf(__uint_as_float(v[i]) + __uint_as_float(vc[i]), P.inv_scale, __ldg(P.bias + P.n_off + n0 + i));
+          float a = fmaf(__uint_as_float(v[i]) + __uint_as_float(vc[i]), P.inv_scale, __ldg(P.bias + n_off + n0 + i));
           if (P.relu) a = fmaxf(a, 0.f);
           if (P.relu == 2) a = fminf(a, 6.f);
           f[i] = a;
@@ -314,7 +319,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
         if (!store) continue;
         if (P.out_f32) {
-          float4* dst = reinterpret_cast<float4*>(P.out_f32 + opix * P.out_cstride + P.n_off + n0);
+          float4* dst = reinterpret_cast<float4*>(P.out_f32 + opix * P.out_cstride + n_off + n0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
         } else {
@@ -327,8 +332,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
             lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
           }
-          uint4* dh = reinterpret_cast<uint4*>(P.out_hi + opix * P.out_cstride + P.n_off + n0);
-          uint4* dl = reinterpret_cast<uint4*>(P.out_lo + opix * P.out_cstride + P.n_off + n0);
+          uint4* dh = reinterpret_cast<uint4*>(P.out_hi + opix * P.out_cstride + n_off + n0);
+          uint4* dl = reinterpret_cast<uint4*>(P.out_lo + opix * P.out_cstride + n_off + n0);
           dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
           dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
@@ -539,7 +544,13 @@ osb_status umma_layer_upload(UmmaLayer* L, const float* w_oihw, const float* bia
   const uint32_t box[3] = {UM_KC, (uint32_t)std::min(L->n_pad, 256), 1};
   osb_status s;
   if ((s = make_tmap(&L->tm_hi, L->w_hi, 3, dims, strides, box)) != OSB_OK) return s;
-  return make_tmap(&L->tm_lo, L->w_lo, 3, dims, strides, box);
+  if ((s = make_tmap(&L->tm_lo, L->w_lo, 3, dims, strides, box)) != OSB_OK) return s;
+  if (L->n_pad >= 256) {                       // 128-row boxes: the layer as n_pad / 128 work items per tile
+    const uint32_t box128[3] = {UM_KC, 128, 1};
+    if ((s = make_tmap(&L->tm_hi128, L->w_hi, 3, dims, strides, box128)) != OSB_OK) return s;
+    if ((s = make_tmap(&L->tm_lo128, L->w_lo, 3, dims, strides, box128)) != OSB_OK) return s;
+  }
+  return OSB_OK;
 }
 
 void umma_layer_free(UmmaLayer* L) {
@@ -563,16 +574,19 @@ osb_status umma_act_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half*
 // (2.10 ms per keyframe with it, 1.93 ms without).
 static const bool g_conv_pdl = [] { const char* e = getenv("OSB_CONV_PDL"); return e && atoi(e) != 0; }();
 
+// OSB_CONV_NSPLIT=0: layers of 256 / 512 output channels run through the N = 256 kernel (A/B switch)
+static const bool g_conv_nsplit = [] { const char* e = getenv("OSB_CONV_NSPLIT"); return !(e && atoi(e) == 0); }();
+
 template <int N, bool RES>
 static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const UmmaLayer& L, const UmmaArgs& P,
-                              cudaStream_t st, int max_ctas) {
+                              cudaStream_t st, int max_ctas, bool box128 = false) {
   using Cfg = UmmaCfg<N, RES>;
   static bool attr_done = false;
   if (!attr_done) {
     OSB_CUDA(cudaFuncSetAttribute((conv_umma_kernel<N, RES>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  const int tiles = P.B * cdiv(P.W, UM_TW) * cdiv(P.H, UM_TH);
+  const int tiles = P.B * cdiv(P.W, UM_TW) * cdiv(P.H, UM_TH) * P.n_split;
   // persistent CTAs, one per SM; `max_ctas` leaves SMs free for a kernel running beside this one on another stream
   const int grid = std::min(tiles, max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms());
   cudaLaunchConfig_t cfg = {};
@@ -581,7 +595,8 @@ static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = g_conv_pdl ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<N, RES>, a_hi, a_lo, L.tm_hi, L.tm_lo, P));
+  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<N, RES>, a_hi, a_lo, box128 ? L.tm_hi128 : L.tm_hi,
+                              box128 ? L.tm_lo128 : L.tm_lo, P));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return OSB_OK;
 }
@@ -597,15 +612,25 @@ osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const 
   P.out_c = out_c; P.out_cstride = out_cstride;
   P.inv_scale = 1.0f / (act_scale * L.w_scale); P.out_scale = out_scale; P.relu = relu;
   OSB_REQUIRE(out_c % 16 == 0 && out_c <= L.n_pad && out_cstride % 8 == 0, "tcgen05 conv: bad output channel layout");
-  P.n_off = 0;
+  P.n_off = 0; P.n_split = 1;
   switch (L.n_pad) {
     case 64:
       if (L.ks == 3 && L.cin == UM_KC) return launch_umma<64, true>(a_hi, a_lo, L, P, st, max_ctas);   // weights resident
       return launch_umma<64, false>(a_hi, a_lo, L, P, st, max_ctas);
     case 80: return launch_umma<80, false>(a_hi, a_lo, L, P, st, max_ctas);
     case 128: return launch_umma<128, false>(a_hi, a_lo, L, P, st, max_ctas);
-    case 256: return launch_umma<256, false>(a_hi, a_lo, L, P, st, max_ctas);
-    case 512: {                                   // two N = 256 passes over the same activations
+    case 256:
+      if (g_conv_nsplit) {                        // 2 items of 128 channels per tile: TMEM double-buffered (the N = 256
+        P.n_split = 2;                            // kernel is single-buffered), finer work items for the 320-tile layers
+        return launch_umma<128, false>(a_hi, a_lo, L, P, st, max_ctas, true);
+      }
+      return launch_umma<256, false>(a_hi, a_lo, L, P, st, max_ctas);
+    case 512: {
+      if (g_conv_nsplit) {
+        P.n_split = 4;
+        return launch_umma<128, false>(a_hi, a_lo, L, P, st, max_ctas, true);
+      }
+      // two N = 256 passes over the same activations
       P.out_c = 256;
       osb_status s = launch_umma<256, false>(a_hi, a_lo, L, P, st, max_ctas);
       if (s != OSB_OK) return s;

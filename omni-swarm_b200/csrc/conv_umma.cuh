@@ -13,6 +13,7 @@ struct UmmaLayer {
   __half *w_hi = nullptr, *w_lo = nullptr;
   float* bias = nullptr;
   CUtensorMap tm_hi, tm_lo;
+  CUtensorMap tm_hi128, tm_lo128;     // same planes with 128-row boxes (n_pad >= 256 only)
 };
 
 osb_status umma_layer_upload(UmmaLayer* L, const float* w_oihw, const float* bias, int cin, int cout, int ks,

@@ -414,7 +414,10 @@ static osb_status fe_extract_dev(osb_frontend* h, const uint8_t* img_dev /*[2*nd
   OSB_CUDA(cudaEventRecord(h->ev_fork, st));
   OSB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
   // NetVLAD on the up images writes straight into the record (image_desc, loop_cam.cpp:553-556)
-  if ((s = h->nv.infer_dev(img_dev, nd, &record_dev->global_desc[0][0], h->stream2)) != OSB_OK) return s;
+  // (OSB_FE_SKIP_NV=1 is a measurement switch only -- it leaves the global descriptors stale -- used to attribute the
+  //  cost of sharing the GPU with NetVLAD)
+  static const bool skip_nv = [] { const char* e = getenv("OSB_FE_SKIP_NV"); return e && atoi(e) != 0; }();
+  if (!skip_nv && (s = h->nv.infer_dev(img_dev, nd, &record_dev->global_desc[0][0], h->stream2)) != OSB_OK) return s;
   OSB_CUDA(cudaEventRecord(h->ev_join, h->stream2));
   cudaStream_t sps = h->stream_sp ? h->stream_sp : st;
   if (sps != st) OSB_CUDA(cudaStreamWaitEvent(sps, h->ev_fork, 0));
