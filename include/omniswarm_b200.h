@@ -201,6 +201,23 @@ osb_status osb_solver_destroy(osb_solver* h);
 osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses, const uint8_t* fixed, int n_factors,
                             const int32_t* type, const int32_t* ia, const int32_t* ib, const double* payload,
                             const uint8_t* huber, const osb_solve_options* opt, osb_solve_summary* summary);
+/* Resident graph: instead of re-flattening the whole window for every solve (the reference rebuilds its
+ * ceres::Problem each time: setup_problem_with_sferror / _loops_and_detections / _ego_motion,
+ * swarm_localization_solver.cpp:1064-1214), the adapter appends what add_new_swarm_frame / add_new_loop_connection
+ * (swarm_localization_solver.hpp:197-214) bring.  The factor list stays in device memory, only new factors cross PCIe,
+ * and the poses persist between solves like the reference's est_poses.  Node ids are append order; drop_oldest renumbers
+ * (sliding window, solver.cpp:186-202).  osb_solver_solve and the resident graph can be mixed on one handle. */
+osb_status osb_solver_graph_clear(osb_solver* h);
+osb_status osb_solver_graph_add_nodes(osb_solver* h, int n, const double* poses /*[n][4]*/, const uint8_t* fixed /*[n] or NULL*/,
+                                      int32_t* first_id);
+osb_status osb_solver_graph_add_factors(osb_solver* h, int m, const int32_t* type, const int32_t* ia, const int32_t* ib,
+                                        const double* payload, const uint8_t* huber);
+osb_status osb_solver_graph_set_fixed(osb_solver* h, int node, int fixed);
+osb_status osb_solver_graph_set_poses(osb_solver* h, int first, int n, const double* poses);
+osb_status osb_solver_graph_get_poses(osb_solver* h, int first, int n, double* poses);
+osb_status osb_solver_graph_size(osb_solver* h, int32_t* n_nodes, int32_t* n_factors);
+osb_status osb_solver_graph_drop_oldest(osb_solver* h, int n_nodes);
+osb_status osb_solver_solve_resident(osb_solver* h, const osb_solve_options* opt, osb_solve_summary* summary);
 /* profiling aid: SM-clock cycles block 0 spent in the phases of the LAST solve, summed over its CG iterations:
  * out[0] factor phase, [1] barrier after it, [2] node phase 1, [3] reduction 1, [4] node phase 2, [5] reduction 2,
  * [6] number of CG iterations, [7] whole kernel; [8] CTAs, [9] 1 = one thread-block cluster (hardware barrier) /

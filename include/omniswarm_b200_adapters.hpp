@@ -199,4 +199,71 @@ class FlatPoseGraph {
   std::vector<double> payload_;
 };
 
+// Same interface, but the window lives in the solver between solves (osb_solver_graph_*): after a solve
+// only the pose blocks and factors added since (add_new_swarm_frame / add_new_loop_connection,
+// swarm_localization_solver.hpp:197-214) are sent; poses are written back to the caller's double[4] blocks.
+class ResidentPoseGraph {
+ public:
+  explicit ResidentPoseGraph(osb_solver* solver) : solver_(solver) { check(osb_solver_graph_clear(solver_), "osb_solver_graph_clear"); }
+  int node(double* pose) {
+    for (size_t i = 0; i < ptr_.size(); ++i) if (ptr_[i] == pose) return (int)i;
+    ptr_.push_back(pose);
+    new_fixed_.push_back(0);
+    return (int)ptr_.size() - 1;
+  }
+  void set_constant(double* pose) {
+    const int id = node(pose);
+    if (id >= sent_nodes_) new_fixed_[id - sent_nodes_] = 1;
+    else check(osb_solver_graph_set_fixed(solver_, id, 1), "osb_solver_graph_set_fixed");
+  }
+  void add_distance(double* pa, double* pb, double d, double sqrt_inf, bool huber) {
+    if (pa == pb) return;
+    double pl[OSB_PAYLOAD_LEN] = {d, sqrt_inf};
+    push(OSB_FACTOR_DISTANCE, pa, pb, pl, huber);
+  }
+  void add_relative_pose(double* pa, double* pb, const double meas[4], const double S[16], bool huber) {
+    if (pa == pb) return;
+    double pl[OSB_PAYLOAD_LEN] = {0};
+    for (int i = 0; i < 4; ++i) pl[i] = meas[i];
+    for (int i = 0; i < 16; ++i) pl[4 + i] = S[i];
+    push(OSB_FACTOR_RELPOSE, pa, pb, pl, huber);
+  }
+  osb_solve_summary solve(const osb_solve_options* opt = nullptr) {
+    flush();
+    osb_solve_summary s{};
+    check(osb_solver_solve_resident(solver_, opt, &s), "osb_solver_solve_resident");
+    std::vector<double> poses(4 * ptr_.size());
+    check(osb_solver_graph_get_poses(solver_, 0, (int)ptr_.size(), poses.data()), "osb_solver_graph_get_poses");
+    for (size_t i = 0; i < ptr_.size(); ++i) for (int j = 0; j < 4; ++j) ptr_[i][j] = poses[4 * i + j];
+    return s;
+  }
+
+ private:
+  void flush() {                                     // send what was added since the last solve
+    const int n_new = (int)ptr_.size() - sent_nodes_;
+    if (n_new > 0) {
+      std::vector<double> poses(4 * (size_t)n_new);
+      for (int i = 0; i < n_new; ++i) for (int j = 0; j < 4; ++j) poses[4 * i + j] = ptr_[sent_nodes_ + i][j];
+      int32_t first = -1;
+      check(osb_solver_graph_add_nodes(solver_, n_new, poses.data(), new_fixed_.data(), &first), "osb_solver_graph_add_nodes");
+      sent_nodes_ += n_new; new_fixed_.clear();
+    }
+    if (!type_.empty()) {
+      check(osb_solver_graph_add_factors(solver_, (int)type_.size(), type_.data(), ia_.data(), ib_.data(), payload_.data(),
+                                         huber_.data()), "osb_solver_graph_add_factors");
+      type_.clear(); ia_.clear(); ib_.clear(); huber_.clear(); payload_.clear();
+    }
+  }
+  void push(int type, double* pa, double* pb, const double* pl, bool huber) {
+    type_.push_back(type); ia_.push_back(node(pa)); ib_.push_back(node(pb)); huber_.push_back(huber ? 1 : 0);
+    payload_.insert(payload_.end(), pl, pl + OSB_PAYLOAD_LEN);
+  }
+  osb_solver* solver_;
+  int sent_nodes_ = 0;
+  std::vector<double*> ptr_;
+  std::vector<uint8_t> new_fixed_, huber_;
+  std::vector<int32_t> type_, ia_, ib_;
+  std::vector<double> payload_;
+};
+
 }  // namespace osb

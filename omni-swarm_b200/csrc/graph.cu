@@ -976,6 +976,12 @@ struct osb_solver {
   int32_t *d_es_ptr = nullptr, *d_es_slot = nullptr;
   double *d_es = nullptr, *d_En = nullptr;
   int last_grid = 0, last_cluster = 0, last_jsmem = 0, last_chain = 0, last_f32 = 0;
+  // resident graph (osb_solver_graph_*): host mirrors of what is already in device memory
+  std::vector<double> g_poses, g_payload;
+  std::vector<uint8_t> g_fixed, g_huber;
+  std::vector<int32_t> g_type, g_ia, g_ib;
+  size_t g_uploaded = 0;            // factors whose type / huber / payload are already on the device
+  bool g_static_valid = false;      // false after a one-shot osb_solver_solve overwrote the device factor arrays
 };
 
 extern "C" void osb_solve_default_options(osb_solve_options* o) {
@@ -1128,16 +1134,12 @@ static osb_status validate_graph(int n_nodes, int n_factors, const int32_t* type
   return OSB_OK;
 }
 
-extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses, const uint8_t* fixed, int n_factors,
-                                       const int32_t* type, const int32_t* ia, const int32_t* ib,
-                                       const double* payload, const uint8_t* huber, const osb_solve_options* opt,
-                                       osb_solve_summary* summary) {
-  OSB_REQUIRE(h && poses && fixed && type && ia && ib && payload && huber && summary, "null argument");
-  OSB_REQUIRE(n_nodes > 0 && n_nodes <= h->max_nodes && n_factors > 0 && n_factors <= h->max_factors,
-              "graph larger than the solver capacity");
-  osb_status s = validate_graph(n_nodes, n_factors, type, ia, ib);
-  if (s != OSB_OK) return s;
-  std::lock_guard<std::mutex> lk(h->mu);
+// the solve proper.  upload_static: copy type / huber / payload to the device (one-shot entry point); the resident entry
+// point has already appended them.  The caller holds h->mu.
+static osb_status solver_run(osb_solver* h, int n_nodes, double* poses, const uint8_t* fixed, int n_factors,
+                             const int32_t* type, const int32_t* ia, const int32_t* ib, const double* payload,
+                             const uint8_t* huber, bool upload_static, const osb_solve_options* opt,
+                             osb_solve_summary* summary) {
   osb_solve_options o;
   if (opt) o = *opt; else osb_solve_default_options(&o);
   // Internal node numbering: the paths of the chain plan are runs of consecutive ids (fixed nodes last).  Everything on
@@ -1183,14 +1185,16 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
              : (((int)payload[f * OSB_PAYLOAD_LEN + 10] & 1) ? 3 : 2);
   cudaStream_t st = h->stream;
   OSB_CUDA(cudaMemcpyAsync(h->d_fixed, fixed_p.data(), n, cudaMemcpyHostToDevice, st));
-  OSB_CUDA(cudaMemcpyAsync(h->d_huber, huber, m, cudaMemcpyHostToDevice, st));
-  OSB_CUDA(cudaMemcpyAsync(h->d_type, type, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (upload_static) {
+    OSB_CUDA(cudaMemcpyAsync(h->d_huber, huber, m, cudaMemcpyHostToDevice, st));
+    OSB_CUDA(cudaMemcpyAsync(h->d_type, type, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    OSB_CUDA(cudaMemcpyAsync(h->d_payload, payload, m * OSB_PAYLOAD_LEN * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
   OSB_CUDA(cudaMemcpyAsync(h->d_ia, ia_p.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_ib, ib_p.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_ptr, ptr.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_slot_a, slot_a.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_slot_b, slot_b.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  OSB_CUDA(cudaMemcpyAsync(h->d_payload, payload, m * OSB_PAYLOAD_LEN * sizeof(double), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_x0, x_p.data(), 4 * n * sizeof(double), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_link, plan.link.data(), n, cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_es_ptr, es_ptr.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -1274,6 +1278,138 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
   summary->solve_ms = ms;
   summary->n_residuals = n_res;
   return OSB_OK;
+}
+
+extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses, const uint8_t* fixed, int n_factors,
+                                       const int32_t* type, const int32_t* ia, const int32_t* ib,
+                                       const double* payload, const uint8_t* huber, const osb_solve_options* opt,
+                                       osb_solve_summary* summary) {
+  OSB_REQUIRE(h && poses && fixed && type && ia && ib && payload && huber && summary, "null argument");
+  OSB_REQUIRE(n_nodes > 0 && n_nodes <= h->max_nodes && n_factors > 0 && n_factors <= h->max_factors,
+              "graph larger than the solver capacity");
+  osb_status s = validate_graph(n_nodes, n_factors, type, ia, ib);
+  if (s != OSB_OK) return s;
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->g_static_valid = false;              // the device factor arrays now hold this graph, not the resident one
+  return solver_run(h, n_nodes, poses, fixed, n_factors, type, ia, ib, payload, huber, true, opt, summary);
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Resident graph.  The reference re-flattens its whole window into a ceres::Problem on every
+// solve (setup_problem_with_sferror / _loops_and_detections / _ego_motion, swarm_localization_solver.cpp:1064-1214).
+// Here the factor list lives in device memory between solves: add_new_swarm_frame / add_new_loop_connection
+// (swarm_localization_solver.hpp:197-214) append what a frame adds, only the new factors cross PCIe, and the poses
+// stay where the last solve left them (the reference's est_poses persist the same way).
+// -------------------------------------------------------------------------------------------------------------
+extern "C" osb_status osb_solver_graph_clear(osb_solver* h) {
+  OSB_REQUIRE(h != nullptr, "null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->g_poses.clear(); h->g_payload.clear(); h->g_fixed.clear(); h->g_huber.clear();
+  h->g_type.clear(); h->g_ia.clear(); h->g_ib.clear();
+  h->g_uploaded = 0; h->g_static_valid = true;
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_solver_graph_add_nodes(osb_solver* h, int n, const double* poses, const uint8_t* fixed,
+                                                 int32_t* first_id) {
+  OSB_REQUIRE(h != nullptr && n > 0 && poses != nullptr, "bad argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  const size_t have = h->g_fixed.size();
+  if (have + (size_t)n > (size_t)h->max_nodes) { set_error("osb_solver_graph_add_nodes", "node capacity exceeded"); return OSB_ERR_CAPACITY; }
+  if (first_id) *first_id = (int32_t)have;
+  h->g_poses.insert(h->g_poses.end(), poses, poses + 4 * (size_t)n);
+  for (int i = 0; i < n; ++i) h->g_fixed.push_back(fixed ? fixed[i] : 0);
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_solver_graph_add_factors(osb_solver* h, int m, const int32_t* type, const int32_t* ia,
+                                                   const int32_t* ib, const double* payload, const uint8_t* huber) {
+  OSB_REQUIRE(h != nullptr && m > 0 && type && ia && ib && payload && huber, "bad argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  const size_t have = h->g_type.size();
+  if (have + (size_t)m > (size_t)h->max_factors) { set_error("osb_solver_graph_add_factors", "factor capacity exceeded"); return OSB_ERR_CAPACITY; }
+  osb_status s = validate_graph((int)h->g_fixed.size(), m, type, ia, ib);
+  if (s != OSB_OK) return s;
+  h->g_type.insert(h->g_type.end(), type, type + m);
+  h->g_ia.insert(h->g_ia.end(), ia, ia + m);
+  h->g_ib.insert(h->g_ib.end(), ib, ib + m);
+  h->g_huber.insert(h->g_huber.end(), huber, huber + m);
+  h->g_payload.insert(h->g_payload.end(), payload, payload + (size_t)m * OSB_PAYLOAD_LEN);
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_solver_graph_set_fixed(osb_solver* h, int node, int fixed) {
+  OSB_REQUIRE(h != nullptr, "null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  OSB_REQUIRE(node >= 0 && (size_t)node < h->g_fixed.size(), "node out of range");
+  h->g_fixed[node] = fixed ? 1 : 0;
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_solver_graph_set_poses(osb_solver* h, int first, int n, const double* poses) {
+  OSB_REQUIRE(h != nullptr && poses != nullptr, "bad argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  OSB_REQUIRE(first >= 0 && n >= 0 && (size_t)(first + n) <= h->g_fixed.size(), "node range out of bounds");
+  std::copy(poses, poses + 4 * (size_t)n, h->g_poses.begin() + 4 * (size_t)first);
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_solver_graph_get_poses(osb_solver* h, int first, int n, double* poses) {
+  OSB_REQUIRE(h != nullptr && poses != nullptr, "bad argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  OSB_REQUIRE(first >= 0 && n >= 0 && (size_t)(first + n) <= h->g_fixed.size(), "node range out of bounds");
+  std::copy(h->g_poses.begin() + 4 * (size_t)first, h->g_poses.begin() + 4 * (size_t)(first + n), poses);
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_solver_graph_size(osb_solver* h, int32_t* n_nodes, int32_t* n_factors) {
+  OSB_REQUIRE(h != nullptr, "null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (n_nodes) *n_nodes = (int32_t)h->g_fixed.size();
+  if (n_factors) *n_factors = (int32_t)h->g_type.size();
+  return OSB_OK;
+}
+
+// sliding window (solver.cpp:186-202 trims old keyframes): drop the first `n_nodes` nodes and every factor touching them;
+// the remaining nodes are renumbered (id - n_nodes).  A rare operation: the device factor arrays are rebuilt.
+extern "C" osb_status osb_solver_graph_drop_oldest(osb_solver* h, int n_nodes) {
+  OSB_REQUIRE(h != nullptr && n_nodes >= 0, "bad argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  OSB_REQUIRE((size_t)n_nodes <= h->g_fixed.size(), "cannot drop more nodes than the graph holds");
+  if (n_nodes == 0) return OSB_OK;
+  h->g_poses.erase(h->g_poses.begin(), h->g_poses.begin() + 4 * (size_t)n_nodes);
+  h->g_fixed.erase(h->g_fixed.begin(), h->g_fixed.begin() + n_nodes);
+  size_t w = 0;
+  for (size_t f = 0; f < h->g_type.size(); ++f) {
+    if (h->g_ia[f] < n_nodes || h->g_ib[f] < n_nodes) continue;
+    h->g_type[w] = h->g_type[f]; h->g_ia[w] = h->g_ia[f] - n_nodes; h->g_ib[w] = h->g_ib[f] - n_nodes;
+    h->g_huber[w] = h->g_huber[f];
+    if (w != f) std::copy(h->g_payload.begin() + f * OSB_PAYLOAD_LEN, h->g_payload.begin() + (f + 1) * OSB_PAYLOAD_LEN,
+                          h->g_payload.begin() + w * OSB_PAYLOAD_LEN);
+    ++w;
+  }
+  h->g_type.resize(w); h->g_ia.resize(w); h->g_ib.resize(w); h->g_huber.resize(w); h->g_payload.resize(w * OSB_PAYLOAD_LEN);
+  h->g_uploaded = 0;                       // factor positions moved: re-send on the next solve
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_solver_solve_resident(osb_solver* h, const osb_solve_options* opt, osb_solve_summary* summary) {
+  OSB_REQUIRE(h != nullptr && summary != nullptr, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  const size_t n = h->g_fixed.size(), m = h->g_type.size();
+  OSB_REQUIRE(n > 0 && m > 0, "the resident graph is empty");
+  if (!h->g_static_valid) { h->g_uploaded = 0; h->g_static_valid = true; }
+  if (h->g_uploaded < m) {                 // only the factors added since the last solve cross PCIe
+    const size_t f0 = h->g_uploaded, k = m - f0;
+    cudaStream_t st = h->stream;
+    OSB_CUDA(cudaMemcpyAsync(h->d_huber + f0, h->g_huber.data() + f0, k, cudaMemcpyHostToDevice, st));
+    OSB_CUDA(cudaMemcpyAsync(h->d_type + f0, h->g_type.data() + f0, k * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    OSB_CUDA(cudaMemcpyAsync(h->d_payload + f0 * OSB_PAYLOAD_LEN, h->g_payload.data() + f0 * OSB_PAYLOAD_LEN,
+                             k * OSB_PAYLOAD_LEN * sizeof(double), cudaMemcpyHostToDevice, st));
+    h->g_uploaded = m;
+  }
+  return solver_run(h, (int)n, h->g_poses.data(), h->g_fixed.data(), (int)m, h->g_type.data(), h->g_ia.data(),
+                    h->g_ib.data(), h->g_payload.data(), h->g_huber.data(), false, opt, summary);
 }
 
 extern "C" osb_status osb_solver_phase_cycles(osb_solver* h, double* out12) {

@@ -238,6 +238,53 @@ class PoseGraphSolver:
                                             C.byref(opt), C.byref(summ)))
         return poses, summ
 
+    # ---- resident graph: the factor list stays on the device between solves ----
+    def graph_clear(self):
+        _l.check(self._lib.osb_solver_graph_clear(self._h))
+
+    def graph_add_nodes(self, poses: np.ndarray, fixed: np.ndarray | None = None) -> int:
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 4)
+        fx = None if fixed is None else np.ascontiguousarray(fixed, np.uint8)
+        first = C.c_int32(-1)
+        _l.check(self._lib.osb_solver_graph_add_nodes(self._h, poses.shape[0], _l.ptr(poses),
+                                                      None if fx is None else _l.ptr(fx), C.byref(first)))
+        return int(first.value)
+
+    def graph_add_factors(self, ftype, ia, ib, payload, huber):
+        ftype = np.ascontiguousarray(ftype, np.int32); ia = np.ascontiguousarray(ia, np.int32)
+        ib = np.ascontiguousarray(ib, np.int32); huber = np.ascontiguousarray(huber, np.uint8)
+        payload = np.ascontiguousarray(payload, np.float64)
+        _l.check(self._lib.osb_solver_graph_add_factors(self._h, len(ftype), _l.ptr(ftype), _l.ptr(ia), _l.ptr(ib),
+                                                        _l.ptr(payload), _l.ptr(huber)))
+
+    def graph_set_fixed(self, node: int, fixed: bool = True):
+        _l.check(self._lib.osb_solver_graph_set_fixed(self._h, node, int(fixed)))
+
+    def graph_set_poses(self, first: int, poses: np.ndarray):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 4)
+        _l.check(self._lib.osb_solver_graph_set_poses(self._h, first, poses.shape[0], _l.ptr(poses)))
+
+    def graph_get_poses(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        if n is None:
+            n = self.graph_size()[0] - first
+        out = np.zeros((n, 4), np.float64)
+        _l.check(self._lib.osb_solver_graph_get_poses(self._h, first, n, _l.ptr(out)))
+        return out
+
+    def graph_size(self) -> tuple[int, int]:
+        a, b = C.c_int32(0), C.c_int32(0)
+        _l.check(self._lib.osb_solver_graph_size(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def graph_drop_oldest(self, n_nodes: int):
+        _l.check(self._lib.osb_solver_graph_drop_oldest(self._h, n_nodes))
+
+    def solve_resident(self, options: _l.SolveOptions | None = None) -> _l.SolveSummary:
+        opt = options if options is not None else self.default_options()
+        summ = _l.SolveSummary()
+        _l.check(self._lib.osb_solver_solve_resident(self._h, C.byref(opt), C.byref(summ)))
+        return summ
+
     def phase_cycles(self) -> dict:
         c = np.zeros(12, np.float64)
         _l.check(self._lib.osb_solver_phase_cycles(self._h, _l.ptr(c)))

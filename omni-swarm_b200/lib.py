@@ -100,6 +100,15 @@ _SIG = {
     "osb_solver_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
     "osb_solver_destroy": (C.c_int, [_P]),
     "osb_solver_solve": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]),
+    "osb_solver_graph_clear": (C.c_int, [_P]),
+    "osb_solver_graph_add_nodes": (C.c_int, [_P, C.c_int, _P, _P, C.POINTER(C.c_int32)]),
+    "osb_solver_graph_add_factors": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
+    "osb_solver_graph_set_fixed": (C.c_int, [_P, C.c_int, C.c_int]),
+    "osb_solver_graph_set_poses": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "osb_solver_graph_get_poses": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "osb_solver_graph_size": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "osb_solver_graph_drop_oldest": (C.c_int, [_P, C.c_int]),
+    "osb_solver_solve_resident": (C.c_int, [_P, _P, _P]),
     "osb_solver_phase_cycles": (C.c_int, [_P, _P]),
     "osb_solver_chain_cycles": (C.c_int, [_P, _P]),
     "osb_solver_chain_plan": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P]),

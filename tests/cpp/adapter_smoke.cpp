@@ -36,6 +36,21 @@ int main() {
   g.add_relative_pose(a, b, meas, S, false);
   g.set_constant(a);
   osb_solve_summary s = g.solve(solver);
+  {
+    // resident variant: two poses first, a third pose and its edge appended after the first solve
+    double c0[4] = {0, 0, 0, 0}, c1[4] = {0.9, 0.1, 0, 0.05}, c2[4] = {2.2, 0, 0, 0.25};
+    osb::ResidentPoseGraph rg(solver);
+    rg.add_relative_pose(c0, c1, meas, S, false);
+    rg.set_constant(c0);
+    rg.solve();
+    rg.add_relative_pose(c1, c2, meas, S, false);
+    osb_solve_summary rs = rg.solve();
+    const double ex = 1.0 + std::cos(0.1), ey = std::sin(0.1);
+    if (std::fabs(c1[0] - 1.0) > 1e-6 || std::fabs(c2[0] - ex) > 1e-6 || std::fabs(c2[1] - ey) > 1e-6 || std::fabs(c2[3] - 0.2) > 1e-6) {
+      std::printf("resident solve wrong: %f %f | %f %f %f cost %g\n", c1[0], c1[3], c2[0], c2[1], c2[3], rs.final_cost);
+      return 5;
+    }
+  }
   osb_solver_destroy(solver);
   if (std::fabs(b[0] - 1.0) > 1e-6 || std::fabs(b[3] - 0.1) > 1e-6 || a[0] != 0.0) {
     std::printf("solve wrong: %f %f %f %f cost %g\n", b[0], b[1], b[2], b[3], s.final_cost);

@@ -138,3 +138,66 @@ def test_fp32_inner_solve_matches_fp64_inner_solve(solver):
         assert abs(s32.pcg_iterations - s64.pcg_iterations) <= max(10, s64.pcg_iterations // 20)
         assert abs(s32.final_cost - s64.final_cost) < 1e-7 * s64.final_cost
         assert np.abs(p32 - p64).max() < 1e-5
+
+
+def _frames_of(g, n_drones):
+    return (np.maximum(g["ia"], g["ib"]) // n_drones)
+
+
+def test_resident_graph_incremental_equals_one_shot(solver):
+    """nodes and factors appended frame by frame (as add_new_swarm_frame / add_new_loop_connection would)
+    give bit-for-bit the one-shot solve of the same arrays; poses persist; the one-shot entry point can be mixed in."""
+    nd = 5
+    g = synth.pose_graph(nd, 60, seed=4)
+    # stream the graph in 4 chunks of frames; a factor is added once both of its nodes exist (factor order is kept)
+    fr_of = _frames_of(g, nd)
+    order = np.argsort(fr_of, kind="stable")
+    g2 = dict(g)
+    for k in ("ftype", "ia", "ib", "huber"):
+        g2[k] = g[k][order]
+    g2["payload"] = g["payload"][order]
+    ref_poses, ref_s = solver.solve(g2)
+    solver.graph_clear()
+    bounds = [0, 15, 30, 45, 60]
+    fr2 = fr_of[order]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        first = solver.graph_add_nodes(g["init"][a * nd:b * nd], g["fixed"][a * nd:b * nd])
+        assert first == a * nd
+        sel = (fr2 >= a) & (fr2 < b)
+        solver.graph_add_factors(g2["ftype"][sel], g2["ia"][sel], g2["ib"][sel], g2["payload"][sel], g2["huber"][sel])
+    assert solver.graph_size() == (g["n_nodes"], len(g["ftype"]))
+    s = solver.solve_resident()
+    poses = solver.graph_get_poses()
+    assert np.array_equal(poses, ref_poses) and s.final_cost == ref_s.final_cost and s.pcg_iterations == ref_s.pcg_iterations
+    # poses persist: a second solve starts from the solution and stops at once
+    s2 = solver.solve_resident()
+    assert s2.iterations <= 2 and np.abs(solver.graph_get_poses() - poses).max() < 1e-3
+    # a one-shot solve on the same handle in between must not corrupt the resident factor arrays
+    other = synth.pose_graph(3, 12, n_uwb=20, n_loop=15, n_det=8, seed=3)
+    solver.solve(other)
+    solver.graph_set_poses(0, g["init"])
+    s3 = solver.solve_resident()
+    assert np.array_equal(solver.graph_get_poses(), ref_poses) and s3.final_cost == ref_s.final_cost
+
+
+def test_resident_graph_sliding_window(solver):
+    """drop_oldest (solver.cpp:186-202 trims the window) == solving the sub-graph of the remaining frames"""
+    nd = 5
+    g = synth.pose_graph(nd, 40, seed=6)
+    solver.graph_clear()
+    solver.graph_add_nodes(g["init"], g["fixed"])
+    solver.graph_add_factors(g["ftype"], g["ia"], g["ib"], g["payload"], g["huber"])
+    drop = 10 * nd
+    solver.graph_drop_oldest(drop)
+    keep = (g["ia"] >= drop) & (g["ib"] >= drop)
+    sub = dict(n_nodes=g["n_nodes"] - drop, init=g["init"][drop:].copy(), gt=g["gt"][drop:], fixed=g["fixed"][drop:].copy(),
+               ftype=g["ftype"][keep], ia=g["ia"][keep] - drop, ib=g["ib"][keep] - drop, huber=g["huber"][keep],
+               payload=g["payload"][keep])
+    sub["fixed"][0] = 1                                    # the new oldest pose of drone 0 anchors the gauge
+    solver.graph_set_fixed(0, True)
+    assert solver.graph_size() == (sub["n_nodes"], int(keep.sum()))
+    s = solver.solve_resident()
+    ref_poses, ref_s = solver.solve(sub)
+    assert np.array_equal(solver.graph_get_poses(), ref_poses) and s.final_cost == ref_s.final_cost
+    with pytest.raises(host._l.OsbError):
+        solver.graph_add_factors(sub["ftype"][:1], np.array([10 ** 6], np.int32), sub["ib"][:1], sub["payload"][:1], sub["huber"][:1])
