@@ -19,6 +19,7 @@
 // are hardware cluster barriers instead of software grid barriers.
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cstring>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -1078,14 +1079,21 @@ static double factor_weight(int type, const double* pl) {
 
 static void build_chain_plan(int n, const uint8_t* fixed, int m, const int32_t* type, const int32_t* ia, const int32_t* ib,
                              const double* payload, ChainPlan& pl) {
-  std::vector<double> w(m);
-  std::vector<int32_t> idx(m);
-  for (int f = 0; f < m; ++f) { w[f] = factor_weight(type[f], payload + (size_t)f * OSB_PAYLOAD_LEN); idx[f] = f; }
-  std::sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) { return w[x] != w[y] ? w[x] > w[y] : x < y; });
+  // sort key: (inverted bits of the weight as a non-negative float) : factor index -> ascending u64 order is weight
+  // descending, ties by index (weights only need float resolution here)
+  std::vector<uint64_t> keys(m);
+  for (int f = 0; f < m; ++f) {
+    const float wf = (float)factor_weight(type[f], payload + (size_t)f * OSB_PAYLOAD_LEN);
+    uint32_t bits;
+    std::memcpy(&bits, &wf, sizeof(bits));
+    keys[f] = ((uint64_t)(~bits) << 32) | (uint32_t)f;
+  }
+  std::sort(keys.begin(), keys.end());
   std::vector<int32_t> parent(n), nb0(n, -1), nb1(n, -1);
   for (int i = 0; i < n; ++i) parent[i] = i;
   auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
-  for (int32_t f : idx) {
+  for (uint64_t key : keys) {
+    const int32_t f = (int32_t)(key & 0xffffffffu);
     const int a = ia[f], b = ib[f];
     if (fixed[a] || fixed[b] || nb1[a] >= 0 || nb1[b] >= 0) continue;
     const int ra = find(a), rb = find(b);
