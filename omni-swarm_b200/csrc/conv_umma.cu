@@ -676,9 +676,84 @@ __global__ void dwconv3x3_split_kernel(const float* __restrict__ w, const float*
   split_store8(out_hi + (size_t)i * 8, out_lo + (size_t)i * 8, a, out_scale);
 }
 
+// stride-1 variant: one thread per (4 consecutive output pixels of a row, 8 channels).  The 3 x 6 input window is read
+// once (36 float4 instead of 72 for four single-pixel threads) and the 9 x 8 weights once per thread; same tap order per
+// output as the kernel above, so the planes are bit-identical.
+__global__ void dwconv3x3_split_s1x4_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                            const float* __restrict__ x, __half* __restrict__ out_hi,
+                                            __half* __restrict__ out_lo, int H, int W, int C, float out_scale,
+                                            int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int C8 = C >> 3, Wg = (W + 3) >> 2;
+  const int c = (int)(i % C8) * 8;
+  int64_t p = i / C8;
+  const int ox0 = (int)(p % Wg) * 4; p /= Wg;
+  const int oy = (int)(p % H);
+  const int b = (int)(p / H);
+  float4 wv[9][2];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4* wp = reinterpret_cast<const float4*>(w + (size_t)t * C + c);
+    wv[t][0] = __ldg(wp); wv[t][1] = __ldg(wp + 1);
+  }
+  float a[4][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[q][j] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int gy = oy + ky - 1;
+    if (gy < 0 || gy >= H) continue;
+    float4 v[6][2];
+#pragma unroll
+    for (int cx = 0; cx < 6; ++cx) {
+      const int gx = ox0 + cx - 1;
+      if (gx >= 0 && gx < W) {
+        const float4* xp = reinterpret_cast<const float4*>(x + (((size_t)b * H + gy) * W + gx) * C + c);
+        v[cx][0] = xp[0]; v[cx][1] = xp[1];
+      } else {
+        v[cx][0] = v[cx][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int gx = ox0 + q + kx - 1;
+        if (gx < 0 || gx >= W) continue;              // (skipped like the single-pixel kernel: no +0 added)
+        const float4 v0 = v[q + kx][0], v1 = v[q + kx][1], w0 = wv[ky * 3 + kx][0], w1 = wv[ky * 3 + kx][1];
+        a[q][0] = fmaf(v0.x, w0.x, a[q][0]); a[q][1] = fmaf(v0.y, w0.y, a[q][1]);
+        a[q][2] = fmaf(v0.z, w0.z, a[q][2]); a[q][3] = fmaf(v0.w, w0.w, a[q][3]);
+        a[q][4] = fmaf(v1.x, w1.x, a[q][4]); a[q][5] = fmaf(v1.y, w1.y, a[q][5]);
+        a[q][6] = fmaf(v1.z, w1.z, a[q][6]); a[q][7] = fmaf(v1.w, w1.w, a[q][7]);
+      }
+  }
+  float bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bb[j] = __ldg(bias + c + j);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int ox = ox0 + q;
+    if (ox >= W) break;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[q][j] = fminf(fmaxf(a[q][j] + bb[j], 0.f), 6.f);
+    const size_t o = ((((size_t)b * H + oy) * W + ox) * C8 + (c >> 3)) * 8;
+    split_store8(out_hi + o, out_lo + o, a[q], out_scale);
+  }
+}
+
 osb_status umma_dwconv_forward(const float* w_tap_c, const float* bias, const float* x, __half* out_hi, __half* out_lo,
                                int B, int H, int W, int C, int stride, float out_scale, cudaStream_t st) {
   const int Ho = H / stride, Wo = W / stride;
+  if (stride == 1) {
+    const int64_t total4 = (int64_t)B * H * ((W + 3) / 4) * (C / 8);
+    OSB_LAUNCH(dwconv3x3_split_s1x4_kernel, (unsigned)cdiv64(total4, 128), 128, 0, st, w_tap_c, bias, x, out_hi, out_lo,
+               H, W, C, out_scale, total4);
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+  }
   const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
   OSB_LAUNCH(dwconv3x3_split_kernel, (unsigned)cdiv64(total, 256), 256, 0, st, w_tap_c, bias, x, out_hi, out_lo, H, W,
              Ho, Wo, C, stride, out_scale, total);

@@ -127,6 +127,90 @@ nv_vlad_final_kernel(const float* __restrict__ part, const float* __restrict__ p
   reinterpret_cast<float4*>(out + (size_t)b * NV_K * NV_D + (size_t)k * NV_D)[lane] = acc;
 }
 
+// Block 0 fused: depthwise 3x3 (32 ch, stride 1) + ReLU6 -> pointwise 32 -> 64 + ReLU6, fp32 in / fp32 out.
+// The pointwise layer has K = 32, half a tensor-core slab, and as a generic tiled GEMM it was the slowest launch of the
+// network (75 us for 1.3 GFLOP); fused, the depthwise output never leaves shared memory.  CTA = 8 x 16 pixels:
+// (1) input tile + halo -> shared memory, (2) depthwise: thread = (4 channels, pixel), its 9 x 4 weights in registers,
+// (3) pointwise: thread = 4 pixels x 8 output channels, K = 32 from shared memory (padded rows, broadcast reads).
+constexpr int F0_TW = 16, F0_TH = 8, F0_C = 32, F0_OC = 64, F0_PX = F0_TW * F0_TH;
+constexpr int F0_SMEM = ((F0_TH + 2) * (F0_TW + 2) * F0_C + F0_PX * (F0_C + 1) + F0_C * F0_OC) * (int)sizeof(float);
+__global__ void __launch_bounds__(256)
+nv_block0_fused_kernel(const float* __restrict__ x, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                       const float* __restrict__ pw_kc, const float* __restrict__ pw_b, float* __restrict__ y, int H,
+                       int W) {
+  extern __shared__ __align__(16) float f0_smem[];
+  float* s_in = f0_smem;                                               // [TH+2][TW+2][32]
+  float* s_dw = s_in + (F0_TH + 2) * (F0_TW + 2) * F0_C;               // [128][33]
+  float* s_w = s_dw + F0_PX * (F0_C + 1);                              // [32][64]
+  const int tid = threadIdx.x, b = blockIdx.z, x0 = blockIdx.x * F0_TW, y0 = blockIdx.y * F0_TH;
+  const float* xb = x + (size_t)b * H * W * F0_C;
+  for (int e = tid; e < (F0_TH + 2) * (F0_TW + 2) * (F0_C / 4); e += 256) {
+    const int c4 = e % (F0_C / 4), pc = (e / (F0_C / 4)) % (F0_TW + 2), pr = e / ((F0_C / 4) * (F0_TW + 2));
+    const int gy = y0 + pr - 1, gx = x0 + pc - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)gy * W + gx) * F0_C) + c4);
+    reinterpret_cast<float4*>(s_in)[e] = v;
+  }
+  for (int e = tid; e < F0_C * F0_OC / 4; e += 256) reinterpret_cast<float4*>(s_w)[e] = __ldg(reinterpret_cast<const float4*>(pw_kc) + e);
+  // depthwise weights of this thread's 4 channels
+  const int cg = tid & 7, slot = tid >> 3;
+  float4 wd[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wd[t] = __ldg(reinterpret_cast<const float4*>(dw_w + t * F0_C) + cg);
+  const float4 bd = __ldg(reinterpret_cast<const float4*>(dw_b) + cg);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < F0_PX / 32; ++j) {
+    const int px = slot + 32 * j, r = px / F0_TW, c = px % F0_TW;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 v = reinterpret_cast<const float4*>(s_in + ((r + ky) * (F0_TW + 2) + c + kx) * F0_C)[cg];
+        const float4 ww = wd[ky * 3 + kx];
+        a.x = fmaf(v.x, ww.x, a.x); a.y = fmaf(v.y, ww.y, a.y); a.z = fmaf(v.z, ww.z, a.z); a.w = fmaf(v.w, ww.w, a.w);
+      }
+    float* d = s_dw + px * (F0_C + 1) + cg * 4;
+    d[0] = fminf(fmaxf(a.x + bd.x, 0.f), 6.f); d[1] = fminf(fmaxf(a.y + bd.y, 0.f), 6.f);
+    d[2] = fminf(fmaxf(a.z + bd.z, 0.f), 6.f); d[3] = fminf(fmaxf(a.w + bd.w, 0.f), 6.f);
+  }
+  __syncthreads();
+  // pointwise: 4 pixels x 8 output channels per thread
+  const int ocg = tid & 7, pxg = tid >> 3;
+  float acc[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[j][o] = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < F0_C; ++k) {
+    const float4 w0 = reinterpret_cast<const float4*>(s_w + k * F0_OC + ocg * 8)[0];
+    const float4 w1 = reinterpret_cast<const float4*>(s_w + k * F0_OC + ocg * 8)[1];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float av = s_dw[(pxg * 4 + j) * (F0_C + 1) + k];
+      acc[j][0] = fmaf(av, w0.x, acc[j][0]); acc[j][1] = fmaf(av, w0.y, acc[j][1]);
+      acc[j][2] = fmaf(av, w0.z, acc[j][2]); acc[j][3] = fmaf(av, w0.w, acc[j][3]);
+      acc[j][4] = fmaf(av, w1.x, acc[j][4]); acc[j][5] = fmaf(av, w1.y, acc[j][5]);
+      acc[j][6] = fmaf(av, w1.z, acc[j][6]); acc[j][7] = fmaf(av, w1.w, acc[j][7]);
+    }
+  }
+  const float4 b0v = __ldg(reinterpret_cast<const float4*>(pw_b + ocg * 8)), b1v = __ldg(reinterpret_cast<const float4*>(pw_b + ocg * 8) + 1);
+  const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int px = pxg * 4 + j, gy = y0 + px / F0_TW, gx = x0 + px % F0_TW;
+    if (gy >= H || gx >= W) continue;
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = fminf(fmaxf(acc[j][q] + bb[q], 0.f), 6.f);
+    float4* dst = reinterpret_cast<float4*>(y + (((size_t)b * H + gy) * W + gx) * F0_OC + ocg * 8);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
 static osb_status upload(float** dst, const float* src, size_t n) {
   OSB_CUDA(cudaMalloc(dst, n * sizeof(float)));
   OSB_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
@@ -164,6 +248,14 @@ osb_status NetVLAD::init(const float* weights, size_t n_weights, int width, int 
     if ((s = upload(&blk[i].dwb, p, ci)) != OSB_OK) return s;
     p += ci;
     if ((s = conv_layer_upload(&blk[i].pw, p, p + (size_t)co * ci, ci, co, 1)) != OSB_OK) return s;
+    if (i == 0) {                                  // block 0 fused kernel: pointwise weights as [k][oc]
+      std::vector<float> kc((size_t)ci * co);
+      for (int o = 0; o < co; ++o)
+        for (int k = 0; k < ci; ++k) kc[(size_t)k * co + o] = p[(size_t)o * ci + k];
+      if ((s = upload(&pw0_kc, kc.data(), kc.size())) != OSB_OK) return s;
+      if ((s = upload(&pw0_b, p + (size_t)co * ci, co)) != OSB_OK) return s;
+      OSB_CUDA(cudaFuncSetAttribute(nv_block0_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F0_SMEM));
+    }
     if (use_umma && i >= 1 && (s = umma_layer_upload(&upw[i], p, p + (size_t)co * ci, ci, co, 1, NV_W_SCALE)) != OSB_OK) return s;
     p += (size_t)co * ci + co;
   }
@@ -215,7 +307,7 @@ osb_status NetVLAD::init(const float* weights, size_t n_weights, int width, int 
 }
 
 void NetVLAD::release() {
-  cudaFree(w0); cudaFree(b0); cudaFree(lut); cudaFree(centroids);
+  cudaFree(w0); cudaFree(b0); cudaFree(lut); cudaFree(centroids); cudaFree(pw0_kc); cudaFree(pw0_b);
   for (int i = 0; i < 7; ++i) { cudaFree(blk[i].dw); cudaFree(blk[i].dwb); conv_layer_free(&blk[i].pw); }
   conv_layer_free(&proj); conv_layer_free(&assign);
   cudaFree(d_img); cudaFree(actA); cudaFree(actB); cudaFree(d_assign); cudaFree(d_out);
@@ -231,18 +323,26 @@ osb_status NetVLAD::infer_dev(const uint8_t* img_dev, int B, float* out_dev, cud
 #define RUN(x) do { s = (x); if (s != OSB_OK) return s; } while (0)
   int h = H / 2, w = W / 2;
   RUN(conv_first_forward(w0, b0, lut, img_dev, actA, B, H, W, 32, 2, ACT_RELU6, st));
+  float* cur = actA;                 // fp32 activations of the previous block
   for (int i = 0; i < 7; ++i) {
-    if (use_umma && i >= 1) {
+    if (use_umma && i == 0) {
+      dim3 grid(cdiv(w, F0_TW), cdiv(h, F0_TH), B);
+      OSB_LAUNCH(nv_block0_fused_kernel, grid, 256, F0_SMEM, st, cur, blk[0].dw, blk[0].dwb, pw0_kc, pw0_b, actB, h, w);
+      OSB_CHECK_LAUNCH();
+      cur = actB;
+    } else if (use_umma) {
       // depthwise (fp32 -> split planes) then pointwise on the tensor cores (planes -> fp32, or planes for the projection)
-      RUN(umma_dwconv_forward(blk[i].dw, blk[i].dwb, actA, pl_hi[i], pl_lo[i], B, h, w, blk[i].cin, blk[i].stride,
+      RUN(umma_dwconv_forward(blk[i].dw, blk[i].dwb, cur, pl_hi[i], pl_lo[i], B, h, w, blk[i].cin, blk[i].stride,
                               NV_ACT_SCALE, st));
       h /= blk[i].stride; w /= blk[i].stride;
-      if (i < 6)
+      if (i < 6) {
         RUN(umma_conv_forward(upw[i], tmA[i], tmB[i], B, h, w, NV_ACT_SCALE, nullptr, nullptr, actA, blk[i].cout,
                               blk[i].cout, 1.f, 2, 0, st));
-      else
+        cur = actA;
+      } else {
         RUN(umma_conv_forward(upw[i], tmA[i], tmB[i], B, h, w, NV_ACT_SCALE, pl_hi[7], pl_lo[7], nullptr, blk[i].cout,
                               blk[i].cout, NV_ACT_SCALE, 2, 0, st));
+      }
     } else {
       RUN(dwconv3x3_forward(blk[i].dw, blk[i].dwb, actA, actB, B, h, w, blk[i].cin, blk[i].stride, ACT_RELU6, st));
       h /= blk[i].stride; w /= blk[i].stride;

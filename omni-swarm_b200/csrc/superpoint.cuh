@@ -56,7 +56,7 @@ struct SuperPoint {
 struct NetVLAD {
   int W = 0, H = 0, max_batch = 0;
   cudaStream_t stream = nullptr;
-  float *w0 = nullptr, *b0 = nullptr, *lut = nullptr;
+  float *w0 = nullptr, *b0 = nullptr, *lut = nullptr, *pw0_kc = nullptr, *pw0_b = nullptr;
   struct Block { float *dw = nullptr, *dwb = nullptr; ConvLayer pw; int cin = 0, cout = 0, stride = 1; } blk[7];
   ConvLayer proj, assign;
   float* centroids = nullptr;
