@@ -70,19 +70,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// asynchronous TMEM load (no wait) + the wait as a separate step, so that the loads of the next 16 columns are in flight
-// while the current ones are converted and stored; tmem_regs_ready pins the register reads behind the wait.
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-               : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_regs_ready(uint32_t (&v)[16]) {
-  asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                    "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -306,9 +293,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       const int py = ty * (UM_TH / 2) + q, px = tx * (UM_TW / 2) + (lane >> 1);
       const bool pool_writer = P.pool && lane < 16 && !(lane & 1) && py < (P.H >> 1) && px < (P.W >> 1);
       const size_t ppix = ((size_t)b * (P.H >> 1) + py) * (P.W >> 1) + px;
-      // two register buffers: the TMEM loads of chunk n0 + 16 are issued before chunk n0 is converted and stored
-      auto process = [&](int n0, uint32_t (&v)[16], uint32_t (&vc)[16]) {
-        if (n_off - P.n_off + n0 >= P.out_c) return;              // warp-uniform
+#pragma unroll 1
+      for (int n0 = 0; n0 < N; n0 += 16) {
+        uint32_t v[16], vc[16];
+        tmem_ld16(t_row + n0, v);
+        tmem_ld16(t_row + N + n0, vc);
+        if (n_off - P.n_off + n0 >= P.out_c) continue;              // warp-uniform
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -327,7 +317,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           }
           store = pool_writer; opix = ppix;
         }
-        if (!store) return;
+        if (!store) continue;
         if (P.out_f32) {
           float4* dst = reinterpret_cast<float4*>(P.out_f32 + opix * P.out_cstride + n_off + n0);
 #pragma unroll
@@ -346,21 +336,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           uint4* dl = reinterpret_cast<uint4*>(P.out_lo + opix * P.out_cstride + n_off + n0);
           dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
           dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-        }
-      };
-      uint32_t va[16], vca[16], vb[16], vcb[16];
-      tmem_ld16_issue(t_row, va); tmem_ld16_issue(t_row + N, vca);
-      // fully unrolled: registers with a load in flight must not cross a loop back-edge (a phi copy would read them
-      // before tcgen05.wait::ld)
-#pragma unroll
-      for (int n0 = 0; n0 < N; n0 += 32) {
-        tmem_ld_wait(); tmem_regs_ready(va); tmem_regs_ready(vca);
-        if (n0 + 16 < N) { tmem_ld16_issue(t_row + n0 + 16, vb); tmem_ld16_issue(t_row + N + n0 + 16, vcb); }
-        process(n0, va, vca);
-        if (n0 + 16 < N) {
-          tmem_ld_wait(); tmem_regs_ready(vb); tmem_regs_ready(vcb);
-          if (n0 + 32 < N) { tmem_ld16_issue(t_row + n0 + 32, va); tmem_ld16_issue(t_row + N + n0 + 32, vca); }
-          process(n0 + 16, vb, vcb);
         }
       }
       tc_fence_before();
