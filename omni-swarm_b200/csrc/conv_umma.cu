@@ -118,7 +118,7 @@ struct UmmaArgs {
   int n_split;             // a layer wider than the kernel's N runs as n_split work items per tile (N channels each)
 };
 
-template <int N, bool RES>
+template <int N, bool RES, bool SPLIT>
 __global__ void __launch_bounds__(256, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, UmmaArgs P) {
@@ -140,7 +140,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   const int tiles_x = (P.W + UM_TW - 1) / UM_TW, tiles_y = (P.H + UM_TH - 1) / UM_TH;
   const int n_tiles = P.B * tiles_x * tiles_y;
   // work item = (tile, channel block): items of one tile are adjacent, so concurrent CTAs share its activations in L2
-  const int n_items = n_tiles * P.n_split;
+  const int n_split = SPLIT ? P.n_split : 1;          // compile-time 1 for ordinary layers: no div / mod per item
+  const int n_items = n_tiles * n_split;
   const int halo = P.ks / 2;
   const uint32_t a_box_bytes = (uint32_t)(UM_TH + 2 * halo) * UM_TW * 128;   // bytes of one A plane box
 
@@ -181,7 +182,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     // the activations are the previous kernel's output: wait for the whole grid we depend on (no-op without PDL)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int tile = item / P.n_split, n_off = P.n_off + (item % P.n_split) * N;
+      const int tile = SPLIT ? item / n_split : item, n_off = SPLIT ? P.n_off + (item % n_split) * N : P.n_off;
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
       const int x0 = tx * UM_TW, y0 = ty * UM_TH;
       for (int kx = 0; kx < P.ks; ++kx) {
@@ -280,7 +281,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int r = m / UM_TW, c = m % UM_TW;
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int tile = item / P.n_split, n_off = P.n_off + (item % P.n_split) * N;
+      const int tile = SPLIT ? item / n_split : item, n_off = SPLIT ? P.n_off + (item % n_split) * N : P.n_off;
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
       const int y = ty * UM_TH + r, x = tx * UM_TW + c;
       const bool inside = (y < P.H) && (x < P.W);
@@ -577,13 +578,13 @@ static const bool g_conv_pdl = [] { const char* e = getenv("OSB_CONV_PDL"); retu
 // OSB_CONV_NSPLIT=0: layers of 256 / 512 output channels run through the N = 256 kernel (A/B switch)
 static const bool g_conv_nsplit = [] { const char* e = getenv("OSB_CONV_NSPLIT"); return !(e && atoi(e) == 0); }();
 
-template <int N, bool RES>
+template <int N, bool RES, bool SPLIT = false>
 static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const UmmaLayer& L, const UmmaArgs& P,
                               cudaStream_t st, int max_ctas, bool box128 = false) {
   using Cfg = UmmaCfg<N, RES>;
   static bool attr_done = false;
   if (!attr_done) {
-    OSB_CUDA(cudaFuncSetAttribute((conv_umma_kernel<N, RES>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    OSB_CUDA(cudaFuncSetAttribute((conv_umma_kernel<N, RES, SPLIT>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
   const int tiles = P.B * cdiv(P.W, UM_TW) * cdiv(P.H, UM_TH) * P.n_split;
@@ -595,7 +596,7 @@ static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = g_conv_pdl ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<N, RES>, a_hi, a_lo, box128 ? L.tm_hi128 : L.tm_hi,
+  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<N, RES, SPLIT>, a_hi, a_lo, box128 ? L.tm_hi128 : L.tm_hi,
                               box128 ? L.tm_lo128 : L.tm_lo, P));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return OSB_OK;
@@ -622,13 +623,13 @@ osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const 
     case 256:
       if (g_conv_nsplit) {                        // 2 items of 128 channels per tile: TMEM double-buffered (the N = 256
         P.n_split = 2;                            // kernel is single-buffered), finer work items for the 320-tile layers
-        return launch_umma<128, false>(a_hi, a_lo, L, P, st, max_ctas, true);
+        return launch_umma<128, false, true>(a_hi, a_lo, L, P, st, max_ctas, true);
       }
       return launch_umma<256, false>(a_hi, a_lo, L, P, st, max_ctas);
     case 512: {
       if (g_conv_nsplit) {
         P.n_split = 4;
-        return launch_umma<128, false>(a_hi, a_lo, L, P, st, max_ctas, true);
+        return launch_umma<128, false, true>(a_hi, a_lo, L, P, st, max_ctas, true);
       }
       // two N = 256 passes over the same activations
       P.out_c = 256;

@@ -10,7 +10,7 @@ if [ "$1" = "full" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-solve --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
 tail -3 gpurun_out/bench_ncu.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:db_scan -s 2 -c 4 -o gpurun_out/prof_dbscan -f python bench.py --steps 2 --warmup 1 --no-solve --no-cpu-baseline > gpurun_out/ncu_dbscan.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:conv_umma_kernel<\(int\)64, \(bool\)1>'  -s 3 -c 3 -o gpurun_out/prof_conv -f python bench.py --steps 2 --warmup 1 --no-solve --no-cpu-baseline > gpurun_out/ncu_conv.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:conv_umma_kernel<\(int\)64, \(bool\)1,'  -s 3 -c 3 -o gpurun_out/prof_conv -f python bench.py --steps 2 --warmup 1 --no-solve --no-cpu-baseline > gpurun_out/ncu_conv.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:graph_solve -s 1 -c 1 -o gpurun_out/prof_solve -f python -c "
 import sys; sys.path.insert(0, '.')
 from omniswarm_b200 import host, synth
