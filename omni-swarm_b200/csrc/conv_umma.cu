@@ -70,6 +70,13 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// 256-bit global store (STG.256, sm_100): the epilogue's stores have one lane per pixel, so every store instruction
+// touches 32 different lines whatever its width -- 32 bytes per lane halves the instruction (and LSU line) count
+__device__ __forceinline__ void st_global_256(void* p, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4,
+                                              uint32_t r5, uint32_t r6, uint32_t r7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4),
+               "r"(r5), "r"(r6), "r"(r7) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -320,9 +327,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
         if (!store) continue;
         if (P.out_f32) {
-          float4* dst = reinterpret_cast<float4*>(P.out_f32 + opix * P.out_cstride + n_off + n0);
+          float* dst = P.out_f32 + opix * P.out_cstride + n_off + n0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          for (int i = 0; i < 2; ++i)
+            st_global_256(dst + 8 * i, __float_as_uint(f[8 * i]), __float_as_uint(f[8 * i + 1]), __float_as_uint(f[8 * i + 2]),
+                          __float_as_uint(f[8 * i + 3]), __float_as_uint(f[8 * i + 4]), __float_as_uint(f[8 * i + 5]),
+                          __float_as_uint(f[8 * i + 6]), __float_as_uint(f[8 * i + 7]));
         } else {
           uint32_t hi[8], lo[8];
 #pragma unroll
@@ -333,10 +343,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
             lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
           }
-          uint4* dh = reinterpret_cast<uint4*>(P.out_hi + opix * P.out_cstride + n_off + n0);
-          uint4* dl = reinterpret_cast<uint4*>(P.out_lo + opix * P.out_cstride + n_off + n0);
-          dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          st_global_256(P.out_hi + opix * P.out_cstride + n_off + n0, hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7]);
+          st_global_256(P.out_lo + opix * P.out_cstride + n_off + n0, lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7]);
         }
       }
       tc_fence_before();
