@@ -222,7 +222,7 @@ osb_status osb_solver_solve_resident(osb_solver* h, const osb_solve_options* opt
  * out[0] factor phase, [1] barrier after it, [2] node phase 1, [3] reduction 1, [4] node phase 2, [5] reduction 2,
  * [6] number of CG iterations, [7] whole kernel; [8] CTAs, [9] 1 = one thread-block cluster (hardware barrier) /
  * 0 = cooperative grid, [10] bit 0 = Jacobians in shared memory, bit 1 = chain preconditioner, bit 2 = fp32 inner
- * arithmetic, bit 3 = distributed-shared-memory exchange, [11] threads per CTA. */
+ * arithmetic, [11] threads per CTA. */
 osb_status osb_solver_phase_cycles(osb_solver* h, double* out12);
 /* profiling aid: SM-clock cycles each warp spent in the chain-preconditioner sweeps of the LAST solve, [16 CTAs][8 warps] */
 osb_status osb_solver_chain_cycles(osb_solver* h, double* out128);

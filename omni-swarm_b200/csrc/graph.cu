@@ -205,10 +205,6 @@ struct SolverDev {
   osb_solve_summary* summary;
   double* poses_out;
   long long* dbg;          // [8] cycle counters of block 0 / thread 0 (profiling aid, see osb_solver_phase_cycles)
-  // distributed-shared-memory exchange (fast path, fp32 only; see the kernel)
-  int use_dsmem;
-  int slot_cap;            // contribution slots a CTA's nodes own at most
-  int n_rep;               // nodes in the z / p replicas (n rounded up to a multiple of the CTA size)
   // chain preconditioner (fast path only; see chain_apply)
   int use_chain;
   const uint8_t* link;     // [n] 1: node i-1 is node i's predecessor on a path of the cover (never set when i % 16 == 0)
@@ -324,29 +320,6 @@ __device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
 __device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
   __stcg(reinterpret_cast<double2*>(p), make_double2(v[0], v[1]));
   __stcg(reinterpret_cast<double2*>(p) + 1, make_double2(v[2], v[3]));
-}
-
-__device__ __forceinline__ void st4s(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
-__device__ __forceinline__ void st4s(double* p, const double (&v)[4]) {
-  reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]); reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
-}
-__device__ __forceinline__ void ld4s(const float* p, float (&v)[4]) {
-  const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-}
-__device__ __forceinline__ void ld4s(const double* p, double (&v)[4]) {
-  const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-}
-
-// Distributed shared memory (fast path, fp32).  What crosses threads in a CG iteration -- z and p of every node (read
-// by the factor threads of any CTA) and the per-factor contributions (read by the node's thread) -- does not need L2:
-// a node thread stores its z / p into the replica every CTA keeps in shared memory (16 remote 16-byte stores), a factor
-// thread stores its two contributions into the slot array of the CTA that owns the node, and all reads are local
-// shared-memory loads.  The cluster barriers that already separate the phases order the remote stores.
-template <typename T>
-__device__ __forceinline__ void dsm_broadcast4(cg::cluster_group& cl, T* local_slot, const T (&v)[4]) {
-  const unsigned G = cl.num_blocks();
-  for (unsigned r = 0; r < G; ++r) st4s(cl.map_shared_rank(local_slot, r), v);
 }
 
 // 4x4 SPD inverse by Gauss-Jordan (no pivoting: the LM term keeps the diagonal positive)
@@ -538,14 +511,6 @@ graph_solve_kernel(SolverDev P) {
   if (P.j_in_smem) { J.base = smem_j; J.stride = P.fpc; J.off = 0; }
   else { J.base = static_cast<T*>(P.Jg); J.stride = P.m; J.off = blockIdx.x * P.fpc; }
   T* Ls = smem_j + (size_t)32 * P.fpc;          // [16][GS_THREADS]: L_i of the chain preconditioner (use_chain only)
-  // distributed-shared-memory exchange buffers (use_dsmem only): replicas of every node's z and p, and the
-  // contribution slots of the nodes this CTA owns
-  const bool dsm = P.use_dsmem != 0;
-  const int n_rep = P.n_rep;
-  T* zall = Ls + 16 * GS_THREADS;               // [n_rep][4]
-  T* pall = zall + (size_t)4 * n_rep;           // [n_rep][4]
-  T* cloc = pall + (size_t)4 * n_rep;           // [slot_cap][4]
-  cg::cluster_group cluster = cg::this_cluster();
   T* const Pp = static_cast<T*>(P.p); T* const Pz = static_cast<T*>(P.z); T* const Pres = static_cast<T*>(P.res);
   T* const PAp = static_cast<T*>(P.Ap); T* const Pdelta = static_cast<T*>(P.delta); T* const PMinv = static_cast<T*>(P.Minv);
   T* const Pcs = static_cast<T*>(P.cs);
@@ -579,18 +544,6 @@ graph_solve_kernel(SolverDev P) {
     const int f = f0 + threadIdx.x + k * GS_THREADS;
     if (fast && f < f1) { fvalid[k] = true; fa[k] = P.ia[f]; fb[k] = P.ib[f]; fsa[k] = P.slot_a[f]; fsb[k] = P.slot_b[f]; }
   }
-  // DSMEM routing of this thread's factors: owner CTA of each end node and the slot index inside the owner's array
-  int foa[GS_KF], fob[GS_KF], fla[GS_KF], flb[GS_KF];
-#pragma unroll
-  for (int k = 0; k < GS_KF; ++k) {
-    foa[k] = fob[k] = fla[k] = flb[k] = 0;
-    if (dsm && fvalid[k]) {
-      foa[k] = fa[k] / GS_THREADS; fob[k] = fb[k] / GS_THREADS;
-      fla[k] = fsa[k] - P.node_ptr[min(foa[k] * GS_THREADS, P.n)];
-      flb[k] = fsb[k] - P.node_ptr[min(fob[k] * GS_THREADS, P.n)];
-    }
-  }
-  const int slot_base = dsm ? P.node_ptr[min((int)blockIdx.x * GS_THREADS, P.n)] : 0;
   const bool is_node = fast && gtid < P.n && !P.fixed[gtid];
   const int ns0 = is_node ? P.node_ptr[gtid] : 0, ns1 = is_node ? P.node_ptr[gtid + 1] : 0;
   const bool chain = fast && P.use_chain;
@@ -701,7 +654,6 @@ graph_solve_kernel(SolverDev P) {
       if (gtid < P.n) {
         const T zero4[4] = {T(0), T(0), T(0), T(0)};
         st4(Pres + 4 * gtid, rn); st4(Pz + 4 * gtid, zn); st4(Pp + 4 * gtid, zero4); st4(Pdelta + 4 * gtid, zero4);
-        if (dsm) { dsm_broadcast4(cluster, zall + 4 * gtid, zn); dsm_broadcast4(cluster, pall + 4 * gtid, zero4); }
       }
       if (is_node) {
 #pragma unroll
@@ -731,7 +683,6 @@ graph_solve_kernel(SolverDev P) {
         }
         const T zero4[4] = {T(0), T(0), T(0), T(0)};
         st4(Pres + 4 * n, rl); st4(Pz + 4 * n, zl); st4(Pp + 4 * n, zero4); st4(Pdelta + 4 * n, zero4);
-        if (dsm) { dsm_broadcast4(cluster, zall + 4 * n, zl); dsm_broadcast4(cluster, pall + 4 * n, zero4); }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           v2[0] += rl[i] * zl[i]; v2[1] += rl[i] * rl[i];
@@ -754,13 +705,8 @@ graph_solve_kernel(SolverDev P) {
         T zq[GS_KF][2][4], pq[GS_KF][2][4];
 #pragma unroll
         for (int k = 0; k < GS_KF; ++k) {
-          if (dsm) {
-            ld4s(zall + 4 * fa[k], zq[k][0]); ld4s(zall + 4 * fb[k], zq[k][1]);
-            ld4s(pall + 4 * fa[k], pq[k][0]); ld4s(pall + 4 * fb[k], pq[k][1]);
-          } else {
-            ld4(Pz + 4 * fa[k], zq[k][0]); ld4(Pz + 4 * fb[k], zq[k][1]);
-            ld4(Pp + 4 * fa[k], pq[k][0]); ld4(Pp + 4 * fb[k], pq[k][1]);
-          }
+          ld4(Pz + 4 * fa[k], zq[k][0]); ld4(Pz + 4 * fb[k], zq[k][1]);
+          ld4(Pp + 4 * fa[k], pq[k][0]); ld4(Pp + 4 * fb[k], pq[k][1]);
         }
 #pragma unroll
         for (int k = 0; k < GS_KF; ++k) {
@@ -784,13 +730,8 @@ graph_solve_kernel(SolverDev P) {
             for (int i = 0; i < 4; ++i) { sa += J.at(i * 4 + j, li) * t[i]; sb += J.at(16 + i * 4 + j, li) * t[i]; }
             ca[j] = sa; cb[j] = sb;
           }
-          if (dsm) {
-            st4s(cluster.map_shared_rank(cloc + 4 * fla[k], foa[k]), ca);
-            st4s(cluster.map_shared_rank(cloc + 4 * flb[k], fob[k]), cb);
-          } else {
-            st4(Pcs + 4 * (size_t)fsa[k], ca);
-            st4(Pcs + 4 * (size_t)fsb[k], cb);
-          }
+          st4(Pcs + 4 * (size_t)fsa[k], ca);
+          st4(Pcs + 4 * (size_t)fsb[k], cb);
         }
       } else {
         for (int f = f0 + threadIdx.x; f < f1; f += GS_THREADS) {
@@ -829,14 +770,6 @@ graph_solve_kernel(SolverDev P) {
         if (is_node) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) { pn[i] = zn[i] + beta * pn[i]; apn[i] = Dl[i] * pn[i]; }
-          if (dsm) {
-            dsm_broadcast4(cluster, pall + 4 * gtid, pn);
-            for (int si = ns0; si < ns1; ++si) {             // local shared memory: no batching needed
-              T c4[4];
-              ld4s(cloc + 4 * (si - slot_base), c4);
-              apn[0] += c4[0]; apn[1] += c4[1]; apn[2] += c4[2]; apn[3] += c4[3];
-            }
-          } else {
           st4(Pp + 4 * gtid, pn);
           for (int s0 = ns0; s0 < ns1; s0 += 16) {         // 16 (fp32) / 32 (fp64) independent 16-byte loads in flight
             T c[16][4];                                    // per batch: one L2 round trip covers every node of degree <= 16
@@ -845,7 +778,6 @@ graph_solve_kernel(SolverDev P) {
 #pragma unroll
             for (int k = 0; k < 16; ++k)
               if (s0 + k < ns1) { apn[0] += c[k][0]; apn[1] += c[k][1]; apn[2] += c[k][2]; apn[3] += c[k][3]; }
-          }
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) v1b[0] += pn[i] * apn[i];
@@ -902,7 +834,7 @@ graph_solve_kernel(SolverDev P) {
           }
         }
         if (is_node) {
-          if (dsm) dsm_broadcast4(cluster, zall + 4 * gtid, zn); else st4(Pz + 4 * gtid, zn);
+          st4(Pz + 4 * gtid, zn);
 #pragma unroll
           for (int i = 0; i < 4; ++i) { v22[0] += rn[i] * zn[i]; v22[1] += rn[i] * rn[i]; }
         }
@@ -1044,7 +976,7 @@ struct osb_solver {
   uint8_t* d_link = nullptr;
   int32_t *d_es_ptr = nullptr, *d_es_slot = nullptr;
   double *d_es = nullptr, *d_En = nullptr;
-  int last_grid = 0, last_cluster = 0, last_jsmem = 0, last_chain = 0, last_f32 = 0, last_dsmem = 0;
+  int last_grid = 0, last_cluster = 0, last_jsmem = 0, last_chain = 0, last_f32 = 0;
   // resident graph (osb_solver_graph_*): host mirrors of what is already in device memory
   std::vector<double> g_poses, g_payload;
   std::vector<uint8_t> g_fixed, g_huber;
@@ -1286,7 +1218,7 @@ static osb_status solver_run(osb_solver* h, int n_nodes, double* poses, const ui
   P.g = nv; P.D = nv + N4; P.p = nv + 2 * N4; P.z = nv + 3 * N4; P.res = nv + 4 * N4; P.Ap = nv + 5 * N4;
   P.delta = nv + 6 * N4; P.Hnn = nv + 7 * N4; P.Minv = nv + 7 * N4 + N16;
   P.cs = h->d_cs; P.gs = h->d_gs; P.hs = h->d_hs; P.partial = h->d_partial; P.opt = o; P.summary = h->d_summary; P.poses_out = h->d_out; P.dbg = h->d_dbg;
-  P.use_chain = 0; P.use_dsmem = 0; P.slot_cap = 0; P.n_rep = 0; P.link = h->d_link; P.es_ptr = h->d_es_ptr; P.es_slot = h->d_es_slot; P.es = h->d_es; P.En = h->d_En;
+  P.use_chain = 0; P.link = h->d_link; P.es_ptr = h->d_es_ptr; P.es_slot = h->d_es_slot; P.es = h->d_es; P.En = h->d_En;
 
   // inner precision: fp32 PCG unless the caller asks for a tighter inner solve than fp32 can deliver
   const bool f32 = o.inner_precision == OSB_INNER_FP32 || (o.inner_precision == OSB_INNER_AUTO && o.pcg_tolerance >= 1e-4);
@@ -1307,18 +1239,7 @@ static osb_status solver_run(osb_solver* h, int n_nodes, double* poses, const ui
       const bool chain = o.preconditioner != OSB_PRECOND_BLOCK_JACOBI && fpc <= GS_KF * GS_THREADS &&
                          n_nodes <= G * GS_THREADS && jbytes + cbytes <= (size_t)GS_SMEM_DYN_MAX;
       P.use_chain = chain ? 1 : 0;
-      // distributed-shared-memory exchange: fp32 fast path with room for the z / p replicas and the slot array
-      int slot_cap = 0;
-      for (int c = 0; c < G; ++c) {
-        const int n0 = std::min(c * GS_THREADS, n_nodes), n1 = std::min((c + 1) * GS_THREADS, n_nodes);
-        slot_cap = std::max(slot_cap, ptr[n1] - ptr[n0]);
-      }
-      const int n_rep = cdiv(n_nodes, GS_THREADS) * GS_THREADS;
-      const size_t dbytes = ((size_t)8 * n_rep + (size_t)4 * slot_cap) * tsz;
-      static const bool dsm_env = [] { const char* e = getenv("OSB_SOLVER_DSMEM"); return !(e && atoi(e) == 0); }();
-      const bool dsm = dsm_env && f32 && chain && jbytes + cbytes + dbytes <= (size_t)GS_SMEM_DYN_MAX;
-      P.use_dsmem = dsm ? 1 : 0; P.slot_cap = slot_cap; P.n_rep = n_rep;
-      cfg.gridDim = dim3(G); cfg.dynamicSmemBytes = jbytes + (chain ? cbytes : 0) + (dsm ? dbytes : 0);
+      cfg.gridDim = dim3(G); cfg.dynamicSmemBytes = jbytes + (chain ? cbytes : 0);
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       int nclusters = 0;
@@ -1327,12 +1248,12 @@ static osb_status solver_run(osb_solver* h, int n_nodes, double* poses, const ui
         launched_cluster = true;
       } else {
         cudaGetLastError();
-        P.use_chain = 0; P.use_dsmem = 0;
+        P.use_chain = 0;
       }
     }
   }
   if (!launched_cluster) {
-    P.use_chain = 0; P.use_dsmem = 0;
+    P.use_chain = 0;
     int per_sm = 0;
     const int G0 = std::max(1, std::min(num_sms(), cdiv(std::max(n_nodes, n_factors), GS_THREADS)));
     int fpc = cdiv(n_factors, G0);
@@ -1347,7 +1268,7 @@ static osb_status solver_run(osb_solver* h, int n_nodes, double* poses, const ui
     attr[0].val.cooperative = 1;
   }
   h->last_grid = (int)cfg.gridDim.x; h->last_cluster = P.use_cluster; h->last_jsmem = P.j_in_smem; h->last_chain = P.use_chain;
-  h->last_f32 = f32 ? 1 : 0; h->last_dsmem = P.use_dsmem;
+  h->last_f32 = f32 ? 1 : 0;
   OSB_CUDA(cudaEventRecord(h->ev0, st));
   {
     void* kargs[1] = {&P};
@@ -1505,7 +1426,7 @@ extern "C" osb_status osb_solver_phase_cycles(osb_solver* h, double* out12) {
   long long c[8];
   OSB_CUDA(cudaMemcpy(c, h->d_dbg, sizeof(c), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 8; ++i) out12[i] = (double)c[i];
-  out12[8] = h->last_grid; out12[9] = h->last_cluster; out12[10] = h->last_jsmem + 2 * h->last_chain + 4 * h->last_f32 + 8 * h->last_dsmem; out12[11] = GS_THREADS;
+  out12[8] = h->last_grid; out12[9] = h->last_cluster; out12[10] = h->last_jsmem + 2 * h->last_chain + 4 * h->last_f32; out12[11] = GS_THREADS;
   return OSB_OK;
 }
 

@@ -293,7 +293,6 @@ class PoseGraphSolver:
         d = dict(zip(names, c.tolist()))
         d["chain_preconditioner"] = float((int(d["j_in_smem"]) >> 1) & 1)
         d["inner_fp32"] = float((int(d["j_in_smem"]) >> 2) & 1)
-        d["dsmem_exchange"] = float((int(d["j_in_smem"]) >> 3) & 1)
         d["j_in_smem"] = float(int(d["j_in_smem"]) & 1)
         return d
 
