@@ -511,7 +511,7 @@ graph_solve_kernel(SolverDev P) {
   if (P.j_in_smem) { J.base = smem_j; J.stride = P.fpc; J.off = 0; }
   else { J.base = static_cast<T*>(P.Jg); J.stride = P.m; J.off = blockIdx.x * P.fpc; }
   T* Ls = smem_j + (size_t)32 * P.fpc;          // [16][GS_THREADS]: L_i of the chain preconditioner (use_chain only)
-  T* Pp = static_cast<T*>(P.p); T* const Pz = static_cast<T*>(P.z); T* const Pres = static_cast<T*>(P.res);
+  T* const Pp = static_cast<T*>(P.p); T* const Pz = static_cast<T*>(P.z); T* const Pres = static_cast<T*>(P.res);
   T* const PAp = static_cast<T*>(P.Ap); T* const Pdelta = static_cast<T*>(P.delta); T* const PMinv = static_cast<T*>(P.Minv);
   T* const Pcs = static_cast<T*>(P.cs);
   int parity = 0;
@@ -548,9 +548,6 @@ graph_solve_kernel(SolverDev P) {
   const int ns0 = is_node ? P.node_ptr[gtid] : 0, ns1 = is_node ? P.node_ptr[gtid + 1] : 0;
   const bool chain = fast && P.use_chain;
   const int sl = threadIdx.x & 15;
-  int deg_warp = ns1 - ns0;                      // largest slot count among this warp's nodes (uniform loop bound)
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) deg_warp = max(deg_warp, __shfl_xor_sync(0xffffffffu, deg_warp, o));
 
   while (iters < P.opt.max_iterations) {
     if (need_gradient) {
@@ -699,17 +696,9 @@ graph_solve_kernel(SolverDev P) {
     const double rr0 = r2[1];
     T beta = T(0);
     int it = 0;
-    // ---- PCG iterations ----
-    // Fast path: TWO barriers per iteration.  p^T A p = |J p|^2 + lam p^T D p, and both terms are known in the factor
-    // phase (the factor threads form t = J p anyway; a node thread can update its own p = z + beta p there), so the
-    // reduction of p^T A p rides on the barrier that publishes the contribution slots.  The new p goes to the other of
-    // two p buffers, because factor threads of other CTAs are still reading the old one.
-    // Generic path: three barriers (factor | node 1 + reduce | node 2 + reduce).
-    // (Ap is not materialised on the fast path: its buffer is the second p)
-    T* Pp_next = fast ? ((Pp == PAp) ? static_cast<T*>(P.p) : PAp) : Pp;
+    // ---- PCG iterations: 3 barriers each ----
     while (it < P.opt.max_pcg_iterations && rr0 > 0.0) {
       long long c0 = clock64();
-      T vpap[1] = {T(0)};
       // factor phase: p_a = z_a + beta p_a (on the fly), t = Ja p_a + Jb p_b, contributions Ja^T t, Jb^T t
       if (fast) {
         // all gathers of this thread's (up to 3) factors are issued before any arithmetic: one L2 round trip
@@ -733,7 +722,6 @@ graph_solve_kernel(SolverDev P) {
             for (int j = 0; j < 4; ++j) acc += J.at(i * 4 + j, li) * pa[j] + J.at(16 + i * 4 + j, li) * pb[j];
             t[i] = acc;
           }
-          vpap[0] += t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + t[3] * t[3];
           T ca[4], cb[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -745,10 +733,6 @@ graph_solve_kernel(SolverDev P) {
           st4(Pcs + 4 * (size_t)fsa[k], ca);
           st4(Pcs + 4 * (size_t)fsb[k], cb);
         }
-        // this thread's own node: p = z + beta p, lam p^T D p (zeros on lanes without a node: no branch around the math)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { pn[i] = zn[i] + beta * pn[i]; vpap[0] += Dl[i] * pn[i] * pn[i]; }
-        if (is_node) st4(Pp_next + 4 * gtid, pn);
       } else {
         for (int f = f0 + threadIdx.x; f < f1; f += GS_THREADS) {
           const int li = f - f0;
@@ -776,34 +760,29 @@ graph_solve_kernel(SolverDev P) {
           st4(Pcs + 4 * (size_t)P.slot_b[f], cb);
         }
       }
-      long long c1 = clock_after(vpap[0]);
-      double r1[1];
+      long long c1 = clock64();
+      all_sync(P, grid);
+      long long c2 = clock64();
+      // node phase 1: p = z + beta p, Ap = sum of the node's slots + lam D p, partial p.Ap
       T v1b[1] = {T(0)};
       T apn[4] = {T(0), T(0), T(0), T(0)};
-      long long c2, c3, c4;
       if (fast) {
-        grid_reduce_sum<1>(vpap, r1, P, parity, sh, grid); parity ^= 1;      // barrier 1 + p^T A p
-        c2 = clock64();
-        // Ap = sum of the node's slots + lam D p.  Warp-uniform trip count and no is_node branch: this code runs straight
-        // into the shuffles of chain_apply, and a warp that is divergent there pays ~240 cycles per shuffle.
+        if (is_node) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) apn[i] = Dl[i] * pn[i];
-        for (int s0 = 0; s0 < deg_warp; s0 += 16) {        // 16 (fp32) / 32 (fp64) independent 16-byte loads in flight
-          T c[16][4];                                      // per batch: one L2 round trip covers every node of degree <= 16
+          for (int i = 0; i < 4; ++i) { pn[i] = zn[i] + beta * pn[i]; apn[i] = Dl[i] * pn[i]; }
+          st4(Pp + 4 * gtid, pn);
+          for (int s0 = ns0; s0 < ns1; s0 += 16) {         // 16 (fp32) / 32 (fp64) independent 16-byte loads in flight
+            T c[16][4];                                    // per batch: one L2 round trip covers every node of degree <= 16
 #pragma unroll
-          for (int k = 0; k < 16; ++k) ld4(Pcs + 4 * (size_t)max(0, min(ns0 + s0 + k, ns1 - 1)), c[k]);
+            for (int k = 0; k < 16; ++k) ld4(Pcs + 4 * (size_t)min(s0 + k, ns1 - 1), c[k]);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const T m = (ns0 + s0 + k < ns1) ? T(1) : T(0);
-            apn[0] += m * c[k][0]; apn[1] += m * c[k][1]; apn[2] += m * c[k][2]; apn[3] += m * c[k][3];
+            for (int k = 0; k < 16; ++k)
+              if (s0 + k < ns1) { apn[0] += c[k][0]; apn[1] += c[k][1]; apn[2] += c[k][2]; apn[3] += c[k][3]; }
           }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v1b[0] += pn[i] * apn[i];
         }
-        c3 = clock_after(apn[0] + apn[3]);
-        c4 = c3;
       } else {
-        all_sync(P, grid);
-        c2 = clock64();
-        // node phase 1: p = z + beta p, Ap = sum of the node's slots + lam D p, partial p.Ap
         for (int n = gtid; n < P.n; n += T_) {
           if (P.fixed[n]) continue;
           T zl[4], ql[4], pl[4], ap[4];
@@ -822,10 +801,11 @@ graph_solve_kernel(SolverDev P) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) v1b[0] += pl[i] * ap[i];
         }
-        c3 = clock_after(v1b[0]);
-        grid_reduce_sum<1>(v1b, r1, P, parity, sh, grid); parity ^= 1;
-        c4 = clock64();
       }
+      long long c3 = clock_after(v1b[0]);
+      double r1[1];
+      grid_reduce_sum<1>(v1b, r1, P, parity, sh, grid); parity ^= 1;
+      long long c4 = clock64();
       const double pAp = r1[0];
       if (!(pAp > 0.0)) break;
       const T alpha = (T)(rz / pAp);
@@ -883,7 +863,6 @@ graph_solve_kernel(SolverDev P) {
         P.dbg[5] += c6 - c5; P.dbg[6] += 1;
       }
       ++it;
-      if (fast) { T* tmp = Pp; Pp = Pp_next; Pp_next = tmp; }       // the p just written is the one the next factor phase reads
       beta = (T)(r22[0] / rz);
       rz = r22[0];
       if (r22[1] <= P.opt.pcg_tolerance * P.opt.pcg_tolerance * rr0) break;
