@@ -392,8 +392,8 @@ def run_ours(args):
     scan_ms = stages["db_scan"]
     scan_bytes = (db_rows_now + db_rows_remote) * 4096 * 4.0        # local + remote database, each row read once
     scan_gbs = scan_bytes / scan_ms / 1e6
-    roofline = {"kernel": "conv_umma_kernel<64> (conv1b 64->64 3x3 @640x480 + fused 2x2 max-pool; tcgen05 + TMA, split-fp16 "
-                          "3 MMAs per K step)",
+    roofline = {"kernel": "conv_umma_kernel<64,RES> (conv1b 64->64 3x3 @640x480 + fused 2x2 max-pool; tcgen05 + TMA, split-fp16: "
+                          "hi*hi + hi*lo as one MMA of width 2N, lo*hi as one of width N per K step)",
                 "bound": "tensor", "achieved": layer_tflops[dom], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": layer_tflops[dom] / pk["bf16_tflops_sustained"],
                 "traffic": (traffic or {}).get("conv1b_dram_bytes_per_launch"),

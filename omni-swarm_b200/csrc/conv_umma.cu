@@ -12,9 +12,11 @@
 //     the MMAs of tile t+1.
 // Precision: parity with the fp32 oracle needs ~1e-6 relative error, which fp16/bf16 operands cannot give.  Every
 // fp32 operand x is carried as TWO fp16 planes  hi = fp16(s*x), lo = fp16(s*x - hi)  (s a power of two, exact), and
-// each K step issues three MMAs  hi*hi + lo*hi + hi*lo  into the same accumulator (the dropped lo*lo term is 2^-22
-// relative).  Both planes together are 4 bytes per element -- the same HBM/L2 footprint as fp32 activations -- and
-// the three fp16 MMAs cost 1.5x one TF32 MMA.  Measured against the oracle: see tests/test_gpu_superpoint.py.
+// each K step computes the three products  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is 2^-22 relative): hi*hi goes
+// to a MAIN accumulator, the two cross products to a CROSS accumulator (see the truncation note at the MMA issuer), and
+// for 2N <= 256 one MMA of width 2N covers hi*hi and hi*lo at once.  Both planes together are 4 bytes per element -- the
+// same HBM/L2 footprint as fp32 activations -- and the fp16 MACs cost 1.5x one TF32 MMA.  Measured against the oracle:
+// see tests/test_gpu_superpoint.py.
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane each), warp 2 = TMEM
 // allocator, warps 4-7 = epilogue (tcgen05.ld -> bias/ReLU -> re-split -> NHWC stores).  Persistent over tiles.
 #include <cuda.h>
