@@ -239,6 +239,21 @@ osb_status osb_solver_linearize(osb_solver* h, int n_nodes, const double* poses,
                                 double* r, double* Ja, double* Jb);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Geometric filter of the loop matcher (first half) -- the inlier mask of
+ *   cv::findHomography(old_2d, new_2d, CV_RANSAC, 3, mask)            swarm_loop/src/loop_detector.cpp:589-598
+ * for n_pairs correspondence sets at once.  src = old_2d, dst = new_2d, [n_pairs][max_n][2] floats, n[pair] points each
+ * (max_n <= 256).  mask [n_pairs][max_n] (1 = inlier), n_inliers [n_pairs], winner [n_pairs] (hypothesis index, -1 if
+ * none; may be NULL in the host variant).  Fewer than 4 points: empty mask (the reference rejects the pair, :598-600).
+ * OpenCV's RANSAC is randomised; this one is deterministic in (points, seed): 512 hypotheses drawn by a counter-based
+ * hash, same 4-point model / error / threshold rule, first best hypothesis wins (oracle/geometry_ref.py, pinned against
+ * cv2 on well-separated data). */
+osb_status osb_homography_ransac(const float* src, const float* dst, const int32_t* n, int n_pairs, int max_n,
+                                 float thresh, uint32_t seed, uint8_t* mask, int32_t* n_inliers, int32_t* winner);
+osb_status osb_homography_ransac_dev(const float* src_dev, const float* dst_dev, const int32_t* n_dev, int n_pairs,
+                                     int max_n, float thresh, uint32_t seed, uint8_t* mask_dev, int32_t* n_inliers_dev,
+                                     int32_t* winner_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Keyframe front-end -- the per-keyframe pipeline of LoopCam::on_flattened_images (loop_cam.cpp:178-229 ->
  *   generate_stereo_image_descriptor :341-523) followed by LoopDetector::on_image_recv's database work
  *   (loop_detector.cpp:89-104,150-287) and compute_correspond_features' matcher (loop_detector.cpp:539-587),

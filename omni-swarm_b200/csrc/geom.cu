@@ -1,0 +1,177 @@
+// geom.cu -- geometric filter of the loop matcher: homography-RANSAC inlier mask.
+//
+// Replaces cv::findHomography(old_2d, new_2d, CV_RANSAC, 3, mask) in LoopDetector::compute_correspond_features
+// (swarm_loop/src/loop_detector.cpp:589-598) for the direction pairs of one keyframe.  OpenCV's RANSAC samples from cv::RNG
+// and is not reproducible; the library defines a deterministic RANSAC with the same model (4-point homography), error
+// (|new - H old|^2) and threshold (err <= thresh^2, the winner is the first hypothesis with the most inliers), stated in
+// oracle/geometry_ref.py and pinned there against cv2.  This file is bit-exact against that statement: every floating-point
+// operation is an explicitly rounded IEEE double operation (no fused multiply-add).
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace osb {
+
+constexpr int HG_HYP = 512;            // hypotheses per pair
+constexpr int HG_THREADS = 256;
+constexpr int HG_MAXN = 256;           // matches per pair (<= OSB_MAX_KPTS)
+
+__host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+
+// 4 distinct match indices for hypothesis h (oracle: draw4)
+__device__ bool hg_draw4(uint32_t seed, int h, int n, int (&idx)[4]) {
+  for (int slot = 0; slot < 4; ++slot) {
+    bool ok = false;
+    for (int t = 0; t < 16 && !ok; ++t) {
+      const int v = (int)(lowbias32(seed ^ lowbias32((uint32_t)((h * 4 + slot) * 16 + t) + 0x9E3779B9u)) % (uint32_t)n);
+      bool dup = false;
+      for (int j = 0; j < slot; ++j) dup |= (idx[j] == v);
+      if (!dup) { idx[slot] = v; ok = true; }
+    }
+    if (!ok) return false;
+  }
+  return true;
+}
+
+// H (h33 = 1) from 4 correspondences: Gaussian elimination with partial pivoting, separately rounded operations
+__device__ bool hg_solve(const float2* __restrict__ src, const float2* __restrict__ dst, const int (&idx)[4], double (&h)[9]) {
+  double A[8][9];
+  for (int i = 0; i < 4; ++i) {
+    const double x = src[idx[i]].x, y = src[idx[i]].y, u = dst[idx[i]].x, v = dst[idx[i]].y;
+    double* r0 = A[2 * i];
+    double* r1 = A[2 * i + 1];
+    r0[0] = x; r0[1] = y; r0[2] = 1.0; r0[3] = 0.0; r0[4] = 0.0; r0[5] = 0.0; r0[6] = -__dmul_rn(u, x); r0[7] = -__dmul_rn(u, y); r0[8] = u;
+    r1[0] = 0.0; r1[1] = 0.0; r1[2] = 0.0; r1[3] = x; r1[4] = y; r1[5] = 1.0; r1[6] = -__dmul_rn(v, x); r1[7] = -__dmul_rn(v, y); r1[8] = v;
+  }
+  for (int c = 0; c < 8; ++c) {
+    int p = c;
+    double best = fabs(A[c][c]);
+    for (int r = c + 1; r < 8; ++r)
+      if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); p = r; }
+    if (!(best > 1e-9)) return false;
+    if (p != c)
+      for (int k = 0; k < 9; ++k) { const double t = A[c][k]; A[c][k] = A[p][k]; A[p][k] = t; }
+    const double inv = __ddiv_rn(1.0, A[c][c]);
+    for (int r = c + 1; r < 8; ++r) {
+      const double f = __dmul_rn(A[r][c], inv);
+      for (int k = c; k < 9; ++k) A[r][k] = __dsub_rn(A[r][k], __dmul_rn(f, A[c][k]));
+    }
+  }
+  h[8] = 1.0;
+  for (int c = 7; c >= 0; --c) {
+    double s = A[c][8];
+    for (int k = c + 1; k < 8; ++k) s = __dsub_rn(s, __dmul_rn(A[c][k], h[k]));
+    h[c] = __ddiv_rn(s, A[c][c]);
+  }
+  return true;
+}
+
+__device__ __forceinline__ bool hg_inlier(const double (&h)[9], float2 s, float2 d, double t2) {
+  const double x = s.x, y = s.y;
+  const double w = __dadd_rn(__dadd_rn(__dmul_rn(h[6], x), __dmul_rn(h[7], y)), 1.0);
+  const double px = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(h[0], x), __dmul_rn(h[1], y)), h[2]), w);
+  const double py = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(h[3], x), __dmul_rn(h[4], y)), h[5]), w);
+  const double dx = __dsub_rn((double)d.x, px), dy = __dsub_rn((double)d.y, py);
+  return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= t2;      // NaN (w = 0) compares false, as in the oracle
+}
+
+// one CTA per pair.  src / dst: [n_pairs][max_n] float2 (old_2d / new_2d of the flagged matches, in match order)
+__global__ void __launch_bounds__(HG_THREADS)
+homography_ransac_kernel(const float2* __restrict__ src, const float2* __restrict__ dst, const int32_t* __restrict__ n_pts,
+                         int max_n, float thresh, uint32_t seed, uint8_t* __restrict__ mask, int32_t* __restrict__ n_inl,
+                         int32_t* __restrict__ winner) {
+  __shared__ float2 s_src[HG_MAXN], s_dst[HG_MAXN];
+  __shared__ unsigned int s_best;
+  __shared__ double s_h[9];
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  const int n = min(n_pts[pair], min(max_n, HG_MAXN));
+  uint8_t* mk = mask + (size_t)pair * max_n;
+  for (int i = tid; i < max_n; i += HG_THREADS) mk[i] = 0;
+  if (tid == 0) { s_best = 0u; n_inl[pair] = 0; winner[pair] = -1; }
+  if (n < 4) return;                                   // the reference rejects the pair (loop_detector.cpp:598-600)
+  for (int i = tid; i < n; i += HG_THREADS) { s_src[i] = src[(size_t)pair * max_n + i]; s_dst[i] = dst[(size_t)pair * max_n + i]; }
+  __syncthreads();
+  const double t2 = __dmul_rn((double)thresh, (double)thresh);
+  for (int hyp = tid; hyp < HG_HYP; hyp += HG_THREADS) {
+    int idx[4];
+    double h[9];
+    if (!hg_draw4(seed, hyp, n, idx) || !hg_solve(s_src, s_dst, idx, h)) continue;
+    int c = 0;
+    for (int i = 0; i < n; ++i) c += hg_inlier(h, s_src[i], s_dst[i], t2) ? 1 : 0;
+    // most inliers, then the smaller hypothesis index: key = (count + 1) << 16 | (0xFFFF - hyp)
+    atomicMax(&s_best, ((unsigned)(c + 1) << 16) | (unsigned)(0xFFFF - hyp));
+  }
+  __syncthreads();
+  const unsigned best = s_best;
+  if (best == 0u) return;                              // every hypothesis degenerate
+  const int hw = 0xFFFF - (int)(best & 0xFFFFu);
+  if (tid == (hw % HG_THREADS)) {                      // its owner recomputes the model (identical arithmetic)
+    int idx[4];
+    double h[9];
+    hg_draw4(seed, hw, n, idx);
+    hg_solve(s_src, s_dst, idx, h);
+    for (int k = 0; k < 9; ++k) s_h[k] = h[k];
+  }
+  __syncthreads();
+  double h[9];
+  for (int k = 0; k < 9; ++k) h[k] = s_h[k];
+  for (int i = tid; i < n; i += HG_THREADS) mk[i] = hg_inlier(h, s_src[i], s_dst[i], t2) ? 1 : 0;
+  if (tid == 0) { n_inl[pair] = (int)(best >> 16) - 1; winner[pair] = hw; }
+}
+
+osb_status homography_ransac_device(const float* src_dev, const float* dst_dev, const int32_t* n_dev, int n_pairs, int max_n,
+                                    float thresh, uint32_t seed, uint8_t* mask_dev, int32_t* n_inl_dev, int32_t* winner_dev,
+                                    cudaStream_t st) {
+  if (n_pairs <= 0) return OSB_OK;
+  OSB_REQUIRE(max_n > 0 && max_n <= HG_MAXN, "homography: max_n out of range (1..256)");
+  OSB_LAUNCH(homography_ransac_kernel, n_pairs, HG_THREADS, 0, st, reinterpret_cast<const float2*>(src_dev),
+             reinterpret_cast<const float2*>(dst_dev), n_dev, max_n, thresh, seed, mask_dev, n_inl_dev, winner_dev);
+  OSB_CHECK_LAUNCH();
+  return OSB_OK;
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" osb_status osb_homography_ransac_dev(const float* src_dev, const float* dst_dev, const int32_t* n_dev,
+                                                int n_pairs, int max_n, float thresh, uint32_t seed, uint8_t* mask_dev,
+                                                int32_t* n_inliers_dev, int32_t* winner_dev, void* stream) {
+  OSB_REQUIRE(src_dev && dst_dev && n_dev && mask_dev && n_inliers_dev && winner_dev, "null argument");
+  osb_status s = require_device();
+  if (s != OSB_OK) return s;
+  return homography_ransac_device(src_dev, dst_dev, n_dev, n_pairs, max_n, thresh, seed, mask_dev, n_inliers_dev, winner_dev,
+                                  (cudaStream_t)stream);
+}
+
+// host buffers in / out (allocates its scratch per call: a convenience for tests and small callers)
+extern "C" osb_status osb_homography_ransac(const float* src, const float* dst, const int32_t* n, int n_pairs, int max_n,
+                                            float thresh, uint32_t seed, uint8_t* mask, int32_t* n_inliers,
+                                            int32_t* winner) {
+  OSB_REQUIRE(src && dst && n && mask && n_inliers && n_pairs > 0 && max_n > 0, "bad argument");
+  osb_status s = require_device();
+  if (s != OSB_OK) return s;
+  const size_t pts = (size_t)n_pairs * max_n;
+  float *d_src = nullptr, *d_dst = nullptr;
+  int32_t *d_n = nullptr, *d_inl = nullptr, *d_win = nullptr;
+  uint8_t* d_mask = nullptr;
+  OSB_CUDA(cudaMalloc(&d_src, pts * 2 * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&d_dst, pts * 2 * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&d_n, n_pairs * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&d_inl, n_pairs * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&d_win, n_pairs * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&d_mask, pts));
+  OSB_CUDA(cudaMemcpy(d_src, src, pts * 2 * sizeof(float), cudaMemcpyHostToDevice));
+  OSB_CUDA(cudaMemcpy(d_dst, dst, pts * 2 * sizeof(float), cudaMemcpyHostToDevice));
+  OSB_CUDA(cudaMemcpy(d_n, n, n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice));
+  s = homography_ransac_device(d_src, d_dst, d_n, n_pairs, max_n, thresh, seed, d_mask, d_inl, d_win, nullptr);
+  if (s == OSB_OK) {
+    OSB_CUDA(cudaMemcpy(mask, d_mask, pts, cudaMemcpyDeviceToHost));
+    OSB_CUDA(cudaMemcpy(n_inliers, d_inl, n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (winner) OSB_CUDA(cudaMemcpy(winner, d_win, n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_src); cudaFree(d_dst); cudaFree(d_n); cudaFree(d_inl); cudaFree(d_win); cudaFree(d_mask);
+  return s;
+}

@@ -202,6 +202,25 @@ class BFMatcher:
         return self.match_batch([query], [train])[0]
 
 
+def homography_ransac(src_list, dst_list, thresh: float = 3.0, seed: int = 0):
+    """cv::findHomography(old_2d, new_2d, CV_RANSAC, 3, mask) for several correspondence sets at once
+    (loop_detector.cpp:589-598): src_list[i] = old_2d, dst_list[i] = new_2d, [n_i, 2] float32 ->
+    list of (mask uint8 [n_i], n_inliers, winning hypothesis)."""
+    lib = _l.load()
+    n_pairs = len(src_list)
+    max_n = max(1, max(len(a) for a in src_list))
+    src = np.zeros((n_pairs, max_n, 2), np.float32); dst = np.zeros((n_pairs, max_n, 2), np.float32)
+    n = np.zeros(n_pairs, np.int32)
+    for i, (a, b) in enumerate(zip(src_list, dst_list)):
+        n[i] = len(a)
+        if len(a):
+            src[i, :len(a)] = a; dst[i, :len(a)] = b
+    mask = np.zeros((n_pairs, max_n), np.uint8); ninl = np.zeros(n_pairs, np.int32); win = np.zeros(n_pairs, np.int32)
+    _l.check(lib.osb_homography_ransac(_l.ptr(src), _l.ptr(dst), _l.ptr(n), n_pairs, max_n, float(thresh), int(seed),
+                                       _l.ptr(mask), _l.ptr(ninl), _l.ptr(win)))
+    return [(mask[i, :n[i]].copy(), int(ninl[i]), int(win[i])) for i in range(n_pairs)]
+
+
 class PoseGraphSolver:
     """Flat-array form of SwarmLocalizationSolver::solve_once: `solve(graph) -> (poses, summary)`."""
 

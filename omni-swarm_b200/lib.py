@@ -92,6 +92,8 @@ _SIG = {
     "osb_topk_merge_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "osb_db_size": (C.c_int64, [_P]),
     "osb_db_reset": (C.c_int, [_P]),
+    "osb_homography_ransac": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_uint32, _P, _P, _P]),
+    "osb_homography_ransac_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_uint32, _P, _P, _P, _P]),
     "osb_matcher_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int]),
     "osb_matcher_destroy": (C.c_int, [_P]),
     "osb_matcher_match": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),

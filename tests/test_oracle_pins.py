@@ -172,3 +172,48 @@ def test_query_rule_quirks():
     # remote keyframe queries the LOCAL db with max_index 1
     idq, dist = det.query(2, rows[7], False, False)
     assert idq == 7 and abs(dist - 1.0) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# geometric filter: the deterministic homography RANSAC pinned against the real OpenCV
+# ---------------------------------------------------------------------------------------------------------------
+def _homography_case(seed, n=200, n_out=60, noise=0.3):
+    rng = np.random.default_rng(seed)
+    src = rng.uniform(0, 640, (n, 2)).astype(np.float32); src[:, 1] *= 0.75
+    H = np.array([[1.0 + rng.normal(0, 0.03), rng.normal(0, 0.03), rng.normal(0, 15)],
+                  [rng.normal(0, 0.03), 1.0 + rng.normal(0, 0.03), rng.normal(0, 15)],
+                  [rng.normal(0, 2e-5), rng.normal(0, 2e-5), 1.0]])
+    p = np.c_[src, np.ones(n)] @ H.T
+    dst = (p[:, :2] / p[:, 2:]).astype(np.float32) + rng.normal(0, noise, (n, 2)).astype(np.float32)
+    out = rng.choice(n, n_out, replace=False)
+    dst[out] += (rng.uniform(25, 80, (n_out, 2)) * rng.choice([-1, 1], (n_out, 2))).astype(np.float32)
+    truth = np.ones(n, np.uint8); truth[out] = 0
+    return src, dst, truth
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_homography_mask_equals_opencv_on_separated_data(seed):
+    """cv::findHomography(old_2d, new_2d, CV_RANSAC, 3, mask) (loop_detector.cpp:590) through the Python binding of the
+    same OpenCV function: inliers with 0.3 px noise, outliers 25-80 px away -> the masks must be identical."""
+    import cv2
+    from oracle import geometry_ref as gr
+    src, dst, truth = _homography_case(seed)
+    m, c, h = gr.homography_ransac_mask(src, dst, 3.0, seed=seed)
+    _, mc = cv2.findHomography(src, dst, cv2.RANSAC, 3.0)
+    assert np.array_equal(m, mc.ravel()) and np.array_equal(m, truth) and c == int(truth.sum()) and h >= 0
+
+
+def test_homography_edge_cases_and_pair_filter():
+    from oracle import geometry_ref as gr
+    src, dst, truth = _homography_case(5, n=40, n_out=10)
+    assert gr.homography_ransac_mask(src[:3], dst[:3])[1] == 0              # fewer than 4 points: nothing passes
+    m4 = gr.homography_ransac_mask(src[truth == 1][:4], dst[truth == 1][:4])
+    assert m4[1] == 4                                                       # exactly 4: the model fits them
+    same = np.repeat(src[:1], 10, 0)
+    assert gr.homography_ransac_mask(same, same)[2] == -1                   # all points identical: every sample degenerate
+    # the reference's filter: matches whose NEW landmark has no 3-D flag are dropped first (loop_detector.cpp:572-586)
+    n = len(src)
+    flags = np.ones(n, np.uint8); flags[::5] = 0
+    qn, qo = gr.loop_pair_filter(list(range(n)), list(range(n)), flags, dst, src)
+    assert set(qn.tolist()) == {i for i in range(n) if flags[i] and truth[i]} and np.array_equal(qn, qo)
+    assert gr.loop_pair_filter([0, 1, 2], [0, 1, 2], flags, dst, src) is None
