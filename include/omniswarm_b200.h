@@ -294,6 +294,14 @@ typedef struct {
   int32_t n_matches[OSB_MAX_DIRS];                 /* cross-check matches new-vs-old per direction pair */
   int32_t match_new[OSB_MAX_DIRS][OSB_MAX_KPTS];   /* queryIdx */
   int32_t match_old[OSB_MAX_DIRS][OSB_MAX_KPTS];   /* trainIdx */
+  /* geometric filter (osb_frontend_config::geometric_filter; loop_detector.cpp:569-598): per direction pair, the
+   * matches whose NEW landmark has a 3-D flag (stereo_match >= 0) and that pass the homography-RANSAC mask of
+   * findHomography(old_2d, new_2d, RANSAC, 3).  geo_valid = 0 when fewer than 4 flagged matches remained (the reference
+   * returns false for the pair).  Untouched (zero) when the filter is off. */
+  int32_t geo_valid[OSB_MAX_DIRS];
+  int32_t n_geo[OSB_MAX_DIRS];
+  int32_t geo_new[OSB_MAX_DIRS][OSB_MAX_KPTS];
+  int32_t geo_old[OSB_MAX_DIRS][OSB_MAX_KPTS];
 } osb_loop_result;
 
 typedef struct osb_frontend osb_frontend;
@@ -308,6 +316,8 @@ typedef struct {
   int32_t query_dir;             /* direction queried: 1 for STEREO_FISHEYE, 0 for pinhole (loop_detector.cpp:249-257) */
   int32_t zero_bottom_quarter;   /* 1 for STEREO_FISHEYE: blank rows [3H/4, H) of every image (loop_cam.cpp:535-538) */
   int32_t accept_min_3d_pts;     /* ACCEPT_MIN_3D_PTS: stereo match skipped when n_kpts <= this (loop_cam.cpp:385-391) */
+  int32_t geometric_filter;      /* 1: run the 3-D-flag + homography-RANSAC filter of loop_detector.cpp:569-598 in query */
+  int32_t ransac_seed;           /* seed of the deterministic RANSAC (osb_homography_ransac) */
 } osb_frontend_config;
 
 osb_status osb_frontend_create(osb_frontend** out, const osb_frontend_config* cfg, const float* sp_weights,
@@ -342,6 +352,10 @@ osb_status osb_frontend_db_reset(osb_frontend* h);
  * [n][4096] and optional local descriptors [n][max_num][64] + counts [n] (HOST). */
 osb_status osb_frontend_db_load(osb_frontend* h, int remote, int64_t n, const float* global_desc,
                                 const float* local_desc, const int32_t* n_kpts);
+/* landmarks_2d [n][max_num][2] and stereo_match [n][max_num] (>= 0 <=> landmarks_flag) of rows loaded with
+ * osb_frontend_db_load -- what the geometric filter reads when such a row is the loop hit */
+osb_status osb_frontend_db_set_geometry(osb_frontend* h, int remote, int64_t first_row, int64_t n, const float* kpts,
+                                        const int32_t* stereo_match);
 /* stage timing (CUDA events on the caller's stream, recorded only while enabled).  After a synchronising call
  * (process / finish) stage_ms returns the device time of the LAST extract+ingest+query sequence:
  * [0] SuperPoint network  [1] keypoints + descriptors (NetVLAD runs concurrently on a second stream)

@@ -27,6 +27,8 @@ struct DbStore {
   DbDev* dev = nullptr;
   float* rows = nullptr;       // [cap][4096]
   float* ldesc = nullptr;      // [cap][max_num][64]
+  float* kpts = nullptr;       // [cap][max_num][2]   landmarks_2d of the row (geometric filter)
+  int32_t* smatch = nullptr;   // [cap][max_num]      stereo_match of the row: >= 0 <=> landmarks_flag
   int32_t* nk = nullptr;       // [cap]
   int32_t* row_frame = nullptr;// [cap]
   int32_t* row_dir = nullptr;  // [cap]
@@ -118,7 +120,8 @@ __global__ void fe_assign_kernel(const osb_keyframe_record* __restrict__ recs, i
 __global__ void fe_copy_rows_kernel(const osb_keyframe_record* __restrict__ recs, const int32_t* __restrict__ assign,
                                     int max_num, float* __restrict__ l_rows, float* __restrict__ l_ldesc,
                                     int32_t* __restrict__ l_nk, float* __restrict__ r_rows, float* __restrict__ r_ldesc,
-                                    int32_t* __restrict__ r_nk) {
+                                    int32_t* __restrict__ r_nk, float* __restrict__ l_kpts, int32_t* __restrict__ l_sm,
+                                    float* __restrict__ r_kpts, int32_t* __restrict__ r_sm) {
   const int r = blockIdx.x / OSB_MAX_DIRS, d = blockIdx.x % OSB_MAX_DIRS;
   const int a = assign[blockIdx.x];
   if (a < 0) return;
@@ -135,6 +138,12 @@ __global__ void fe_copy_rows_kernel(const osb_keyframe_record* __restrict__ recs
   const float4* l = reinterpret_cast<const float4*>(&rec->local_desc[d][0][0]);
   float4* ld = reinterpret_cast<float4*>(ldesc + (size_t)row * max_num * OSB_FEATURE_DESC_SIZE);
   for (int i = threadIdx.x; i < n * OSB_FEATURE_DESC_SIZE / 4; i += blockDim.x) ld[i] = l[i];
+  float* kp = (is_remote ? r_kpts : l_kpts) + (size_t)row * max_num * 2;
+  int32_t* sm = (is_remote ? r_sm : l_sm) + (size_t)row * max_num;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    kp[2 * i] = rec->kpts[d][i][0]; kp[2 * i + 1] = rec->kpts[d][i][1];
+    sm[i] = rec->stereo_match[d][i];
+  }
   if (threadIdx.x == 0) nk[row] = n;
 }
 
@@ -173,7 +182,11 @@ __global__ void fe_query_rule_kernel(QueryParams qp, const osb_keyframe_record* 
                                      const int32_t* __restrict__ r_frame_rows, const int32_t* __restrict__ r_nk,
                                      const float* __restrict__ r_ldesc,
                                      osb_loop_result* __restrict__ res, const float** __restrict__ qptr,
-                                     const float** __restrict__ tptr, int32_t* __restrict__ nq, int32_t* __restrict__ nt) {
+                                     const float** __restrict__ tptr, int32_t* __restrict__ nq, int32_t* __restrict__ nt,
+                                     const float* __restrict__ l_kpts, const int32_t* __restrict__ l_sm,
+                                     const float* __restrict__ r_kpts, const int32_t* __restrict__ r_sm,
+                                     const float** __restrict__ g_qk, const float** __restrict__ g_tk,
+                                     const int32_t** __restrict__ g_qflag) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const bool own = rec->drone_id == qp.self_id;
   const double thres = qp.init_mode ? qp.init_mode_product_thres : qp.inner_product_thres;
@@ -200,6 +213,7 @@ __global__ void fe_query_rule_kernel(QueryParams qp, const osb_keyframe_record* 
   res->swapped = 0;
   for (int j = 0; j < OSB_MAX_DIRS; ++j) {
     nq[j] = 0; nt[j] = 0; qptr[j] = nullptr; tptr[j] = nullptr;
+    g_qk[j] = nullptr; g_tk[j] = nullptr; g_qflag[j] = nullptr;
     res->dir_new[j] = -1; res->dir_old[j] = -1;
   }
   if (!accepted) return;
@@ -236,8 +250,71 @@ __global__ void fe_query_rule_kernel(QueryParams qp, const osb_keyframe_record* 
     res->dir_new[slot] = dir_new; res->dir_old[slot] = dir_old;
     if (swapped) { qptr[slot] = p_db; nq[slot] = n_db; tptr[slot] = p_rec; nt[slot] = n_rec; }
     else { qptr[slot] = p_rec; nq[slot] = n_rec; tptr[slot] = p_db; nt[slot] = n_db; }
+    {   // 2-D landmarks and 3-D flags of the two sides, for the geometric filter (loop_detector.cpp:569-598)
+      const float* k_rec = &rec->kpts[dir_rec][0][0];
+      const int32_t* f_rec = &rec->stereo_match[dir_rec][0];
+      const float* k_db = (hit_remote ? r_kpts : l_kpts) + (size_t)row_db * qp.max_num * 2;
+      const int32_t* f_db = (hit_remote ? r_sm : l_sm) + (size_t)row_db * qp.max_num;
+      g_qk[slot] = swapped ? k_db : k_rec; g_tk[slot] = swapped ? k_rec : k_db; g_qflag[slot] = swapped ? f_db : f_rec;
+    }
     ++slot;
   }
+}
+
+// geometric filter, step 1 (loop_detector.cpp:569-586): keep, in match order, the matches whose NEW (query-side) landmark
+// has a 3-D flag; gather old_2d / new_2d of the kept matches.  One CTA per direction-pair slot; ordered compaction by
+// ballot prefix.
+__global__ void __launch_bounds__(256)
+fe_geo_gather_kernel(const osb_loop_result* __restrict__ res, const float* const* __restrict__ g_qk,
+                     const float* const* __restrict__ g_tk, const int32_t* const* __restrict__ g_qflag,
+                     float2* __restrict__ src, float2* __restrict__ dst, int32_t* __restrict__ kept,
+                     int32_t* __restrict__ n_kept) {
+  __shared__ int warp_cnt[8];
+  const int slot = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = (res->dir_new[slot] >= 0) ? res->n_matches[slot] : 0;
+  bool keep = false;
+  int qi = 0, ti = 0;
+  if (tid < n) {
+    qi = res->match_new[slot][tid]; ti = res->match_old[slot][tid];
+    keep = g_qflag[slot][qi] >= 0;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int w = 0; w < 8; ++w) { if (w < warp) base += warp_cnt[w]; total += warp_cnt[w]; }
+  if (keep) {
+    const int pos = base + __popc(bal & ((1u << lane) - 1u));
+    const float* tk = g_tk[slot];
+    const float* qk = g_qk[slot];
+    src[slot * OSB_MAX_KPTS + pos] = make_float2(tk[2 * ti], tk[2 * ti + 1]);      // old_2d
+    dst[slot * OSB_MAX_KPTS + pos] = make_float2(qk[2 * qi], qk[2 * qi + 1]);      // new_2d
+    kept[slot * OSB_MAX_KPTS + pos] = tid;
+  }
+  if (tid == 0) n_kept[slot] = total;
+}
+
+// step 3 (:590-597): reduceVector by the RANSAC mask
+__global__ void __launch_bounds__(256)
+fe_geo_apply_kernel(osb_loop_result* __restrict__ res, const int32_t* __restrict__ kept, const int32_t* __restrict__ n_kept,
+                    const uint8_t* __restrict__ mask) {
+  __shared__ int warp_cnt[8];
+  const int slot = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = n_kept[slot];
+  const bool valid = n >= 4;                                  // else the reference returns false (:598-600)
+  const bool keep = valid && tid < n && mask[slot * OSB_MAX_KPTS + tid] != 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int w = 0; w < 8; ++w) { if (w < warp) base += warp_cnt[w]; total += warp_cnt[w]; }
+  if (keep) {
+    const int pos = base + __popc(bal & ((1u << lane) - 1u));
+    const int m = kept[slot * OSB_MAX_KPTS + tid];
+    res->geo_new[slot][pos] = res->match_new[slot][m];
+    res->geo_old[slot][pos] = res->match_old[slot][m];
+  }
+  if (tid == 0) { res->n_geo[slot] = total; res->geo_valid[slot] = (res->dir_new[slot] >= 0 && valid) ? 1 : 0; }
 }
 
 }  // namespace osb
@@ -260,6 +337,11 @@ struct osb_frontend {
   const float** d_q_q = nullptr; const float** d_q_t = nullptr;
   int32_t *d_q_nq = nullptr, *d_q_nt = nullptr;
   float* d_q_dist = nullptr;
+  // geometric filter scratch (cfg.geometric_filter)
+  const float** d_g_qk = nullptr; const float** d_g_tk = nullptr; const int32_t** d_g_qflag = nullptr;
+  float *d_g_src = nullptr, *d_g_dst = nullptr;
+  int32_t *d_g_kept = nullptr, *d_g_nkept = nullptr, *d_g_ninl = nullptr, *d_g_win = nullptr;
+  uint8_t* d_g_mask = nullptr;
   int32_t* d_assign = nullptr;   // [max_records][4]
   int max_records = 64;
   osb_keyframe_record* d_record = nullptr;   // used by process()
@@ -286,6 +368,10 @@ static osb_status dbstore_alloc(DbStore& s, int64_t cap, int max_num) {
   OSB_CUDA(cudaMemset(s.dev, 0, sizeof(DbDev)));
   OSB_CUDA(cudaMalloc(&s.rows, (size_t)cap * OSB_DEEP_DESC_SIZE * sizeof(float)));
   OSB_CUDA(cudaMalloc(&s.ldesc, (size_t)cap * max_num * OSB_FEATURE_DESC_SIZE * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&s.kpts, (size_t)cap * max_num * 2 * sizeof(float)));
+  OSB_CUDA(cudaMalloc(&s.smatch, (size_t)cap * max_num * sizeof(int32_t)));
+  OSB_CUDA(cudaMemset(s.kpts, 0, (size_t)cap * max_num * 2 * sizeof(float)));
+  OSB_CUDA(cudaMemset(s.smatch, 0, (size_t)cap * max_num * sizeof(int32_t)));   // rows loaded without geometry: every landmark flagged
   OSB_CUDA(cudaMalloc(&s.nk, cap * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&s.row_frame, cap * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&s.row_dir, cap * sizeof(int32_t)));
@@ -303,7 +389,7 @@ static osb_status dbstore_alloc(DbStore& s, int64_t cap, int max_num) {
 }
 
 static void dbstore_free(DbStore& s) {
-  cudaFree(s.dev); cudaFree(s.rows); cudaFree(s.ldesc); cudaFree(s.nk); cudaFree(s.row_frame); cudaFree(s.row_dir);
+  cudaFree(s.dev); cudaFree(s.rows); cudaFree(s.ldesc); cudaFree(s.kpts); cudaFree(s.smatch); cudaFree(s.nk); cudaFree(s.row_frame); cudaFree(s.row_dir);
   cudaFree(s.frame_rows); cudaFree(s.frame_msg); cudaFree(s.part_scores); cudaFree(s.part_ids); cudaFree(s.done);
   cudaFree(s.top_scores); cudaFree(s.top_ids);
 }
@@ -357,6 +443,16 @@ extern "C" osb_status osb_frontend_create(osb_frontend** out, const osb_frontend
   FE_CUDA(cudaMalloc(&h->d_st_n, OSB_MAX_DIRS * sizeof(int32_t)));
   FE_CUDA(cudaMalloc(&h->d_st_dist, OSB_MAX_DIRS * mn * sizeof(float)));
   FE_CUDA(cudaMalloc(&h->d_q_dist, OSB_MAX_DIRS * OSB_MAX_KPTS * sizeof(float)));
+  FE_CUDA(cudaMalloc(&h->d_g_qk, OSB_MAX_DIRS * sizeof(float*)));
+  FE_CUDA(cudaMalloc(&h->d_g_tk, OSB_MAX_DIRS * sizeof(float*)));
+  FE_CUDA(cudaMalloc(&h->d_g_qflag, OSB_MAX_DIRS * sizeof(int32_t*)));
+  FE_CUDA(cudaMalloc(&h->d_g_src, OSB_MAX_DIRS * OSB_MAX_KPTS * 2 * sizeof(float)));
+  FE_CUDA(cudaMalloc(&h->d_g_dst, OSB_MAX_DIRS * OSB_MAX_KPTS * 2 * sizeof(float)));
+  FE_CUDA(cudaMalloc(&h->d_g_kept, OSB_MAX_DIRS * OSB_MAX_KPTS * sizeof(int32_t)));
+  FE_CUDA(cudaMalloc(&h->d_g_nkept, OSB_MAX_DIRS * sizeof(int32_t)));
+  FE_CUDA(cudaMalloc(&h->d_g_ninl, OSB_MAX_DIRS * sizeof(int32_t)));
+  FE_CUDA(cudaMalloc(&h->d_g_win, OSB_MAX_DIRS * sizeof(int32_t)));
+  FE_CUDA(cudaMalloc(&h->d_g_mask, OSB_MAX_DIRS * OSB_MAX_KPTS));
   FE_CUDA(cudaMalloc(&h->d_dist_scratch, (size_t)OSB_MAX_DIRS * mn * mn * sizeof(float)));
   FE_CUDA(cudaMalloc(&h->d_q_nq, OSB_MAX_DIRS * sizeof(int32_t)));
   FE_CUDA(cudaMalloc(&h->d_q_nt, OSB_MAX_DIRS * sizeof(int32_t)));
@@ -385,6 +481,8 @@ extern "C" osb_status osb_frontend_destroy(osb_frontend* h) {
   dbstore_free(h->db[0]); dbstore_free(h->db[1]);
   cudaFree(h->d_img); cudaFree(h->d_st_q); cudaFree(h->d_st_t); cudaFree(h->d_q_q); cudaFree(h->d_q_t);
   cudaFree(h->d_st_qi); cudaFree(h->d_st_ti); cudaFree(h->d_st_map); cudaFree(h->d_st_n); cudaFree(h->d_st_dist);
+  cudaFree(h->d_g_qk); cudaFree(h->d_g_tk); cudaFree(h->d_g_qflag); cudaFree(h->d_g_src); cudaFree(h->d_g_dst);
+  cudaFree(h->d_g_kept); cudaFree(h->d_g_nkept); cudaFree(h->d_g_ninl); cudaFree(h->d_g_win); cudaFree(h->d_g_mask);
   cudaFree(h->d_q_dist); cudaFree(h->d_dist_scratch); cudaFree(h->d_q_nq); cudaFree(h->d_q_nt); cudaFree(h->d_assign);
   cudaFree(h->d_record); cudaFree(h->d_result);
   for (int i = 0; i < 9; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -490,7 +588,7 @@ static osb_status fe_ingest(osb_frontend* h, const osb_keyframe_record* recs, in
              h->d_assign);
   OSB_CHECK_LAUNCH();
   OSB_LAUNCH(fe_copy_rows_kernel, n_records * OSB_MAX_DIRS, 256, 0, st, recs, h->d_assign, h->cfg.max_num, L.rows,
-             L.ldesc, L.nk, R.rows, R.ldesc, R.nk);
+             L.ldesc, L.nk, R.rows, R.ldesc, R.nk, L.kpts, L.smatch, R.kpts, R.smatch);
   OSB_CHECK_LAUNCH();
   L.upper += (int64_t)n_records * OSB_MAX_DIRS;
   R.upper += (int64_t)n_records * OSB_MAX_DIRS;
@@ -525,14 +623,26 @@ static osb_status fe_query(osb_frontend* h, const osb_keyframe_record* rec, int 
   qp.inner_product_thres = c.inner_product_thres; qp.init_mode_product_thres = c.init_mode_product_thres;
   OSB_LAUNCH(fe_query_rule_kernel, 1, 32, 0, st, qp, rec, L.dev, R.dev, L.top_scores, L.top_ids, R.top_scores, R.top_ids,
              L.row_frame, L.row_dir, L.frame_rows, L.nk, L.ldesc, R.row_frame, R.row_dir, R.frame_rows, R.nk, R.ldesc,
-             res, h->d_q_q, h->d_q_t, h->d_q_nq, h->d_q_nt);
+             res, h->d_q_q, h->d_q_t, h->d_q_nq, h->d_q_nt, L.kpts, L.smatch, R.kpts, R.smatch, h->d_g_qk, h->d_g_tk,
+             h->d_g_qflag);
   OSB_CHECK_LAUNCH();
   // per-direction cross-check match new vs old (loop_detector.cpp:564-567); empty pairs produce n = 0
   s = bf_match_device(OSB_MAX_DIRS, c.max_num, OSB_MAX_KPTS, h->d_q_q, h->d_q_nq, h->d_q_t, h->d_q_nt,
                       h->d_dist_scratch, &res->match_new[0][0], &res->match_old[0][0], h->d_q_dist,
                       &res->n_matches[0], nullptr, st);
+  if (s != OSB_OK) return s;
+  if (c.geometric_filter) {
+    // loop_detector.cpp:569-598: 3-D-flag filter, homography RANSAC mask, reduceVector -- all direction pairs at once
+    OSB_LAUNCH(fe_geo_gather_kernel, OSB_MAX_DIRS, 256, 0, st, res, h->d_g_qk, h->d_g_tk, h->d_g_qflag,
+               reinterpret_cast<float2*>(h->d_g_src), reinterpret_cast<float2*>(h->d_g_dst), h->d_g_kept, h->d_g_nkept);
+    OSB_CHECK_LAUNCH();
+    if ((s = homography_ransac_device(h->d_g_src, h->d_g_dst, h->d_g_nkept, OSB_MAX_DIRS, OSB_MAX_KPTS, 3.0f,
+                                      (uint32_t)c.ransac_seed, h->d_g_mask, h->d_g_ninl, h->d_g_win, st)) != OSB_OK) return s;
+    OSB_LAUNCH(fe_geo_apply_kernel, OSB_MAX_DIRS, 256, 0, st, res, h->d_g_kept, h->d_g_nkept, h->d_g_mask);
+    OSB_CHECK_LAUNCH();
+  }
   fe_mark(h, 7, st);
-  return s;
+  return OSB_OK;
 }
 
 extern "C" osb_status osb_frontend_query(osb_frontend* h, const osb_keyframe_record* record_dev, int init_mode,
@@ -614,6 +724,25 @@ extern "C" osb_status osb_frontend_db_reset(osb_frontend* h) {
   return OSB_OK;
 }
 
+// landmarks_2d and stereo_match (>= 0 <=> landmarks_flag) of rows [first_row, first_row + n) that were put in with
+// osb_frontend_db_load: the inputs of the geometric filter when such a row is the loop hit
+extern "C" osb_status osb_frontend_db_set_geometry(osb_frontend* h, int remote, int64_t first_row, int64_t n,
+                                                   const float* kpts, const int32_t* stereo_match) {
+  OSB_REQUIRE(h && kpts && stereo_match && n >= 0 && first_row >= 0, "bad arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  cudaStream_t st = h->stream;
+  if (fe_refresh_counts(h, st) != OSB_OK) return OSB_ERR_CUDA;
+  DbStore& S = h->db[remote ? 1 : 0];
+  OSB_REQUIRE(first_row + n <= S.upper, "rows out of range");
+  const int mn = h->cfg.max_num;
+  OSB_CUDA(cudaMemcpyAsync(S.kpts + (size_t)first_row * mn * 2, kpts, (size_t)n * mn * 2 * sizeof(float),
+                           cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaMemcpyAsync(S.smatch + (size_t)first_row * mn, stereo_match, (size_t)n * mn * sizeof(int32_t),
+                           cudaMemcpyHostToDevice, st));
+  OSB_CUDA(cudaStreamSynchronize(st));
+  return OSB_OK;
+}
+
 extern "C" osb_status osb_frontend_db_load(osb_frontend* h, int remote, int64_t n, const float* global_desc,
                                            const float* local_desc, const int32_t* n_kpts) {
   OSB_REQUIRE(h && global_desc && n >= 0, "bad arguments");
@@ -637,6 +766,9 @@ extern "C" osb_status osb_frontend_db_load(osb_frontend* h, int remote, int64_t 
   if (local_desc)
     OSB_CUDA(cudaMemcpyAsync(S.ldesc + (size_t)base * mn * OSB_FEATURE_DESC_SIZE, local_desc,
                              (size_t)n * mn * OSB_FEATURE_DESC_SIZE * sizeof(float), cudaMemcpyHostToDevice, st));
+  // rows loaded without geometry: landmarks at the origin, every landmark flagged (osb_frontend_db_set_geometry fills them)
+  OSB_CUDA(cudaMemsetAsync(S.kpts + (size_t)base * mn * 2, 0, (size_t)n * mn * 2 * sizeof(float), st));
+  OSB_CUDA(cudaMemsetAsync(S.smatch + (size_t)base * mn, 0, (size_t)n * mn * sizeof(int32_t), st));
   OSB_CUDA(cudaMemcpyAsync(S.nk + base, nk.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(S.row_frame + base, rf.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(S.row_dir + base, rd.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));

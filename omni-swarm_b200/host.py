@@ -350,7 +350,8 @@ class KeyframeFrontend:
 
     def __init__(self, sp_weights, pca_comp, pca_mean, nv_weights, width=640, height=480, n_dirs=4, max_num=200,
                  sp_thres=0.015, self_id=0, db_capacity=16384, inner_product_thres=0.3, init_mode_product_thres=0.2,
-                 match_index_dist=5, query_dir=None, zero_bottom_quarter=True, accept_min_3d_pts=10):
+                 match_index_dist=5, query_dir=None, zero_bottom_quarter=True, accept_min_3d_pts=10,
+                 geometric_filter=False, ransac_seed=0):
         self._lib = _l.load()
         cfg = _l.FrontendConfig()
         cfg.width, cfg.height, cfg.n_dirs, cfg.max_num = width, height, n_dirs, max_num
@@ -360,6 +361,7 @@ class KeyframeFrontend:
         cfg.query_dir = (1 if n_dirs > 1 else 0) if query_dir is None else query_dir
         cfg.zero_bottom_quarter = int(zero_bottom_quarter)
         cfg.accept_min_3d_pts = accept_min_3d_pts
+        cfg.geometric_filter, cfg.ransac_seed = int(geometric_filter), int(ransac_seed)
         self.cfg = cfg
         spw, nvw = _f32(sp_weights).reshape(-1), _f32(nv_weights).reshape(-1)
         pc, pm = _f32(pca_comp), _f32(pca_mean)
@@ -422,6 +424,11 @@ class KeyframeFrontend:
         ld = None if local_desc is None else _f32(local_desc)
         nk = None if n_kpts is None else np.ascontiguousarray(n_kpts, np.int32)
         _l.check(self._lib.osb_frontend_db_load(self._h, int(remote), g.shape[0], _l.ptr(g), _l.ptr(ld), _l.ptr(nk)))
+
+    def db_set_geometry(self, first_row: int, kpts: np.ndarray, stereo_match: np.ndarray, remote=False):
+        """landmarks_2d [n][max_num][2] and stereo_match [n][max_num] of rows put in with db_load"""
+        k = _f32(kpts); sm = np.ascontiguousarray(stereo_match, np.int32)
+        _l.check(self._lib.osb_frontend_db_set_geometry(self._h, int(remote), first_row, k.shape[0], _l.ptr(k), _l.ptr(sm)))
 
 
 def launch_count() -> int:

@@ -51,7 +51,9 @@ class LoopResult(C.Structure):
     _fields_ = [("hit_id", C.c_int32), ("hit_dir", C.c_int32), ("hit_score", C.c_float), ("accepted", C.c_int32),
                 ("swapped", C.c_int32), ("dir_new", C.c_int32 * MAX_DIRS), ("dir_old", C.c_int32 * MAX_DIRS),
                 ("n_matches", C.c_int32 * MAX_DIRS), ("match_new", (C.c_int32 * MAX_KPTS) * MAX_DIRS),
-                ("match_old", (C.c_int32 * MAX_KPTS) * MAX_DIRS)]
+                ("match_old", (C.c_int32 * MAX_KPTS) * MAX_DIRS),
+                ("geo_valid", C.c_int32 * MAX_DIRS), ("n_geo", C.c_int32 * MAX_DIRS),
+                ("geo_new", (C.c_int32 * MAX_KPTS) * MAX_DIRS), ("geo_old", (C.c_int32 * MAX_KPTS) * MAX_DIRS)]
 
 
 class FrontendConfig(C.Structure):
@@ -59,7 +61,7 @@ class FrontendConfig(C.Structure):
                 ("sp_thres", C.c_float), ("self_id", C.c_int32), ("db_capacity", C.c_int32),
                 ("inner_product_thres", C.c_double), ("init_mode_product_thres", C.c_double),
                 ("match_index_dist", C.c_int32), ("query_dir", C.c_int32), ("zero_bottom_quarter", C.c_int32),
-                ("accept_min_3d_pts", C.c_int32)]
+                ("accept_min_3d_pts", C.c_int32), ("geometric_filter", C.c_int32), ("ransac_seed", C.c_int32)]
 
 
 RECORD_BYTES = C.sizeof(KeyframeRecord)
@@ -128,6 +130,7 @@ _SIG = {
     "osb_frontend_db_size": (C.c_int64, [_P, C.c_int]),
     "osb_frontend_db_reset": (C.c_int, [_P]),
     "osb_frontend_db_load": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P]),
+    "osb_frontend_db_set_geometry": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, _P]),
 }
 
 _lib = None

@@ -138,3 +138,39 @@ def test_blank_keyframe_adds_nothing(gpu):
     rec2, _ = fe.process(up, down, msg_id=2)
     assert sum(rec2.n_kpts) > 0 and fe.db_size(False) == sum(1 for d in range(4) if rec2.n_kpts[d] > 0)
     fe.close()
+
+
+def test_geometric_filter_in_query(gpu):
+    """loop_detector.cpp:569-598 on the device: the query's matches are reduced to those whose NEW landmark has a 3-D flag
+    and that pass the homography-RANSAC mask; compared with the oracle filter applied to the same matches and geometry."""
+    from oracle import geometry_ref as gr
+    fe = make_frontend(match_index_dist=1, geometric_filter=True, ransac_seed=3)
+    frames = [frame_images(s) for s in range(4)]
+    recs = [fe.process(*f, msg_id=i)[0] for i, f in enumerate(frames)]
+    rec, res = fe.process(*frames[0], msg_id=99)               # revisit keyframe 0: identical landmarks on both sides
+    assert res.accepted == 1 and res.swapped == 0
+    for slot in range(4):
+        d_new, d_old = res.dir_new[slot], res.dir_old[slot]
+        n = res.n_matches[slot]
+        mn = list(res.match_new[slot][:n]); mo = list(res.match_old[slot][:n])
+        flags = (np.ctypeslib.as_array(rec.stereo_match[d_new]) >= 0).astype(np.uint8)
+        k_new = np.ctypeslib.as_array(rec.kpts[d_new]).copy()
+        k_old = np.ctypeslib.as_array(recs[0].kpts[d_old]).copy()
+        ref = gr.loop_pair_filter(mn, mo, flags, k_new, k_old, 3.0, seed=3)
+        if ref is None:
+            assert res.geo_valid[slot] == 0 and res.n_geo[slot] == 0
+            continue
+        qn, qo = ref
+        g = res.n_geo[slot]
+        assert res.geo_valid[slot] == 1 and g == len(qn)
+        assert list(res.geo_new[slot][:g]) == qn.tolist() and list(res.geo_old[slot][:g]) == qo.tolist()
+        # identical frames: every flagged match is an exact inlier of the identity homography
+        assert g == int(sum(flags[q] for q in mn))
+    fe.close()
+    # filter off (default): the geometry fields stay zero
+    fe = make_frontend(match_index_dist=1)
+    for i, f in enumerate(frames):
+        fe.process(*f, msg_id=i)
+    _, res = fe.process(*frames[0], msg_id=99)
+    assert list(res.geo_valid) == [0, 0, 0, 0] and list(res.n_geo) == [0, 0, 0, 0]
+    fe.close()
