@@ -456,6 +456,34 @@ def run_ours(args):
               "frames_per_s": 1.0 / dt, "ms_per_frame": dt * 1e3, "n_kpts": int(len(kp1))}
         sp1.close(); nv1.close()
 
+    # ---- geometric filter: homography-RANSAC masks of the 4 direction pairs of a keyframe, 200 matches each ----
+    geometry = None
+    if rank == 0:
+        rng = np.random.default_rng(3)
+        src = rng.uniform(0, 640, (4, 200, 2)).astype(np.float32); src[..., 1] *= 0.75
+        dst = src + rng.normal(0, 0.3, src.shape).astype(np.float32) + np.float32(5.0)
+        dst[:, ::4] += np.float32(40.0)                                     # 25 % outliers
+        t_src, t_dst = torch.from_numpy(src).cuda(), torch.from_numpy(dst).cuda()
+        t_n = torch.full((4,), 200, dtype=torch.int32, device="cuda")
+        t_mask = torch.zeros(4, 200, dtype=torch.uint8, device="cuda")
+        t_inl = torch.zeros(4, dtype=torch.int32, device="cuda"); t_win = torch.zeros(4, dtype=torch.int32, device="cuda")
+
+        def _geo():
+            lib.check(L.osb_homography_ransac_dev(C.c_void_p(t_src.data_ptr()), C.c_void_p(t_dst.data_ptr()),
+                                                  C.c_void_p(t_n.data_ptr()), 4, 200, C.c_float(3.0), 0,
+                                                  C.c_void_p(t_mask.data_ptr()), C.c_void_p(t_inl.data_ptr()),
+                                                  C.c_void_p(t_win.data_ptr()), C.c_void_p(st)))
+        for _ in range(3):
+            _geo()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            _geo()
+        e1.record(); torch.cuda.synchronize()
+        geometry = {"what": "osb_homography_ransac_dev: 4 direction pairs x 200 matches, 512 hypotheses each (fp64, "
+                            "bit-exact against oracle/geometry_ref.py)", "us_per_keyframe": e0.elapsed_time(e1) / 50 * 1e3,
+                    "inliers": t_inl.cpu().tolist()}
+
     # ---- SURVEY 8e alternative: the 50 k-row database sharded by rows across the ranks (2 exchange steps per search) ----
     match_sharded = None
     if world > 1:
@@ -545,7 +573,7 @@ def run_ours(args):
                         "h2d_bytes_per_step": 2 * N_DIRS * W * H, "d2h_bytes_per_step": lib.RECORD_BYTES + lib.RESULT_BYTES,
                         "ms_per_step": e2e_s * 1e3 / args.steps},
                 "roofline": roofline, "roofline_conv_stack": roofline_stack, "roofline_match": roofline_match,
-                "match_sweep": match_sweep, "match_sharded": match_sharded, "c2_pinhole": c2,
+                "match_sweep": match_sweep, "match_sharded": match_sharded, "c2_pinhole": c2, "geometry": geometry,
                 "stage_ms": stages,
                 "loop_check": {"accepted": int(res.accepted), "hit_id": int(res.hit_id), "hit_score": float(res.hit_score),
                                "n_kpts": list(rec.n_kpts), "n_matches": list(res.n_matches)},
