@@ -12,7 +12,7 @@
 namespace osb {
 
 constexpr int HG_HYP = 512;            // hypotheses per pair
-constexpr int HG_THREADS = 256;
+constexpr int HG_THREADS = 512;
 constexpr int HG_MAXN = 256;           // matches per pair (<= OSB_MAX_KPTS)
 
 __host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
@@ -68,24 +68,30 @@ __device__ bool hg_solve(const float2* __restrict__ src, const float2* __restric
   return true;
 }
 
+// |new - H old|^2 <= thresh^2 written without the division: with (px, py, w) = H (x, y, 1),
+//   (u w - px)^2 + (v w - py)^2 <= thresh^2 w^2        (w = 0 makes the right side 0: such a point is never an inlier
+// unless it maps exactly, as in the divided form)
 __device__ __forceinline__ bool hg_inlier(const double (&h)[9], float2 s, float2 d, double t2) {
   const double x = s.x, y = s.y;
   const double w = __dadd_rn(__dadd_rn(__dmul_rn(h[6], x), __dmul_rn(h[7], y)), 1.0);
-  const double px = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(h[0], x), __dmul_rn(h[1], y)), h[2]), w);
-  const double py = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(h[3], x), __dmul_rn(h[4], y)), h[5]), w);
-  const double dx = __dsub_rn((double)d.x, px), dy = __dsub_rn((double)d.y, py);
-  return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= t2;      // NaN (w = 0) compares false, as in the oracle
+  const double px = __dadd_rn(__dadd_rn(__dmul_rn(h[0], x), __dmul_rn(h[1], y)), h[2]);
+  const double py = __dadd_rn(__dadd_rn(__dmul_rn(h[3], x), __dmul_rn(h[4], y)), h[5]);
+  const double ex = __dsub_rn(__dmul_rn((double)d.x, w), px), ey = __dsub_rn(__dmul_rn((double)d.y, w), py);
+  return __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)) <= __dmul_rn(t2, __dmul_rn(w, w));
 }
 
-// one CTA per pair.  src / dst: [n_pairs][max_n] float2 (old_2d / new_2d of the flagged matches, in match order)
+// one CTA per pair.  src / dst: [n_pairs][max_n] float2 (old_2d / new_2d of the flagged matches, in match order).
+// Phase A: thread h solves hypothesis h (model -> shared memory).  Phase B: a warp scores one hypothesis at a time, its
+// lanes splitting the matches; the count goes into an atomicMax key (inliers, -hypothesis).  Phase C: the winner's mask.
 __global__ void __launch_bounds__(HG_THREADS)
 homography_ransac_kernel(const float2* __restrict__ src, const float2* __restrict__ dst, const int32_t* __restrict__ n_pts,
                          int max_n, float thresh, uint32_t seed, uint8_t* __restrict__ mask, int32_t* __restrict__ n_inl,
                          int32_t* __restrict__ winner) {
   __shared__ float2 s_src[HG_MAXN], s_dst[HG_MAXN];
+  __shared__ double s_h[HG_HYP][9];
+  __shared__ unsigned char s_ok[HG_HYP];
   __shared__ unsigned int s_best;
-  __shared__ double s_h[9];
-  const int pair = blockIdx.x, tid = threadIdx.x;
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = min(n_pts[pair], min(max_n, HG_MAXN));
   uint8_t* mk = mask + (size_t)pair * max_n;
   for (int i = tid; i < max_n; i += HG_THREADS) mk[i] = 0;
@@ -97,26 +103,31 @@ homography_ransac_kernel(const float2* __restrict__ src, const float2* __restric
   for (int hyp = tid; hyp < HG_HYP; hyp += HG_THREADS) {
     int idx[4];
     double h[9];
-    if (!hg_draw4(seed, hyp, n, idx) || !hg_solve(s_src, s_dst, idx, h)) continue;
+    const bool ok = hg_draw4(seed, hyp, n, idx) && hg_solve(s_src, s_dst, idx, h);
+    s_ok[hyp] = ok ? 1 : 0;
+    if (ok)
+      for (int k = 0; k < 9; ++k) s_h[hyp][k] = h[k];
+  }
+  __syncthreads();
+  for (int hyp = warp; hyp < HG_HYP; hyp += HG_THREADS / 32) {
+    if (!s_ok[hyp]) continue;                          // warp-uniform
+    double h[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) h[k] = s_h[hyp][k];
     int c = 0;
-    for (int i = 0; i < n; ++i) c += hg_inlier(h, s_src[i], s_dst[i], t2) ? 1 : 0;
+    for (int i = lane; i < n; i += 32) c += hg_inlier(h, s_src[i], s_dst[i], t2) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     // most inliers, then the smaller hypothesis index: key = (count + 1) << 16 | (0xFFFF - hyp)
-    atomicMax(&s_best, ((unsigned)(c + 1) << 16) | (unsigned)(0xFFFF - hyp));
+    if (lane == 0) atomicMax(&s_best, ((unsigned)(c + 1) << 16) | (unsigned)(0xFFFF - hyp));
   }
   __syncthreads();
   const unsigned best = s_best;
   if (best == 0u) return;                              // every hypothesis degenerate
   const int hw = 0xFFFF - (int)(best & 0xFFFFu);
-  if (tid == (hw % HG_THREADS)) {                      // its owner recomputes the model (identical arithmetic)
-    int idx[4];
-    double h[9];
-    hg_draw4(seed, hw, n, idx);
-    hg_solve(s_src, s_dst, idx, h);
-    for (int k = 0; k < 9; ++k) s_h[k] = h[k];
-  }
-  __syncthreads();
   double h[9];
-  for (int k = 0; k < 9; ++k) h[k] = s_h[k];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) h[k] = s_h[hw][k];
   for (int i = tid; i < n; i += HG_THREADS) mk[i] = hg_inlier(h, s_src[i], s_dst[i], t2) ? 1 : 0;
   if (tid == 0) { n_inl[pair] = (int)(best >> 16) - 1; winner[pair] = hw; }
 }

@@ -11,7 +11,8 @@ bit-exact against it:
 
   * hypothesis h = 0..n_hyp-1 draws 4 distinct match indices from a counter-based hash (lowbias32 of seed, h, slot, try);
   * H maps old -> new (h33 = 1): 8x8 linear system, Gaussian elimination with partial pivoting; singular -> skipped;
-  * a match is an inlier iff |new - H old|^2 <= thresh^2 (OpenCV: findInliers, err <= thresh*thresh);
+  * a match is an inlier iff |new - H old|^2 <= thresh^2 (OpenCV: findInliers, err <= thresh*thresh), evaluated in the
+    division-free form (u w - px)^2 + (v w - py)^2 <= thresh^2 w^2;
   * the winner has the most inliers, ties to the smaller h (OpenCV keeps the first best); mask = its inliers.
 
 Pinned against the real OpenCV (cv2.findHomography(..., cv2.RANSAC, 3.0)) in tests/test_oracle_pins.py: on correspondences
@@ -86,13 +87,16 @@ def solve_h(src4: np.ndarray, dst4: np.ndarray):
 
 
 def inliers(h: np.ndarray, src: np.ndarray, dst: np.ndarray, thresh: float) -> np.ndarray:
+    """|new - H old|^2 <= thresh^2, stated without the division: with (px, py, w) = H (x, y, 1),
+    (u w - px)^2 + (v w - py)^2 <= thresh^2 w^2."""
     x = src[:, 0].astype(np.float64); y = src[:, 1].astype(np.float64)
     w = (h[6] * x + h[7] * y) + 1.0
-    px = ((h[0] * x + h[1] * y) + h[2]) / w
-    py = ((h[3] * x + h[4] * y) + h[5]) / w
-    dx = dst[:, 0].astype(np.float64) - px
-    dy = dst[:, 1].astype(np.float64) - py
-    return (dx * dx + dy * dy) <= np.float64(thresh) * np.float64(thresh)
+    px = (h[0] * x + h[1] * y) + h[2]
+    py = (h[3] * x + h[4] * y) + h[5]
+    ex = dst[:, 0].astype(np.float64) * w - px
+    ey = dst[:, 1].astype(np.float64) * w - py
+    t2 = np.float64(thresh) * np.float64(thresh)
+    return (ex * ex + ey * ey) <= t2 * (w * w)
 
 
 def homography_ransac_mask(src: np.ndarray, dst: np.ndarray, thresh: float = 3.0, seed: int = 0, n_hyp: int = N_HYP):
