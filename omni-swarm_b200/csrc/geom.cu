@@ -5,7 +5,8 @@
 // and is not reproducible; the library defines a deterministic RANSAC with the same model (4-point homography), error
 // (|new - H old|^2) and threshold (err <= thresh^2, the winner is the first hypothesis with the most inliers), stated in
 // oracle/geometry_ref.py and pinned there against cv2.  This file is bit-exact against that statement: every floating-point
-// operation is an explicitly rounded IEEE double operation (no fused multiply-add).
+// operation is an explicitly rounded IEEE double operation (no fused multiply-add).  The 4-point model is built in
+// closed form (projective basis), so a hypothesis costs ~150 register-resident flops.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -35,36 +36,50 @@ __device__ bool hg_draw4(uint32_t seed, int h, int n, int (&idx)[4]) {
   return true;
 }
 
-// H (h33 = 1) from 4 correspondences: Gaussian elimination with partial pivoting, separately rounded operations
+// Projective-basis construction of the 4-point homography (closed form, branch-free, registers only):
+//   frame(p1..p4) = [p1 p2 p3] diag(v),  v = adj([p1 p2 p3]) p4   (p_i homogeneous; any scale of v serves)
+//   H = frame(dst) adj(frame(src))       (unnormalised: the inlier test is homogeneous in H)
+// A sample is degenerate when one of the four triangles of a quadruple has twice-area <= 1 px^2.
+struct HgFrame { double m[9]; bool ok; };
+
+__device__ __forceinline__ HgFrame hg_frame(float2 q1, float2 q2, float2 q3, float2 q4) {
+  const double x1 = q1.x, y1 = q1.y, x2 = q2.x, y2 = q2.y, x3 = q3.x, y3 = q3.y, x4 = q4.x, y4 = q4.y;
+  const double a00 = __dsub_rn(y2, y3), a01 = __dsub_rn(x3, x2), a02 = __dsub_rn(__dmul_rn(x2, y3), __dmul_rn(x3, y2));
+  const double a10 = __dsub_rn(y3, y1), a11 = __dsub_rn(x1, x3), a12 = __dsub_rn(__dmul_rn(x3, y1), __dmul_rn(x1, y3));
+  const double a20 = __dsub_rn(y1, y2), a21 = __dsub_rn(x2, x1), a22 = __dsub_rn(__dmul_rn(x1, y2), __dmul_rn(x2, y1));
+  const double det = __dadd_rn(__dadd_rn(a02, a12), a22);
+  const double v0 = __dadd_rn(__dadd_rn(__dmul_rn(a00, x4), __dmul_rn(a01, y4)), a02);
+  const double v1 = __dadd_rn(__dadd_rn(__dmul_rn(a10, x4), __dmul_rn(a11, y4)), a12);
+  const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(a20, x4), __dmul_rn(a21, y4)), a22);
+  HgFrame f;
+  f.ok = fabs(det) > 1.0 && fabs(v0) > 1.0 && fabs(v1) > 1.0 && fabs(v2) > 1.0;
+  f.m[0] = __dmul_rn(x1, v0); f.m[1] = __dmul_rn(x2, v1); f.m[2] = __dmul_rn(x3, v2);
+  f.m[3] = __dmul_rn(y1, v0); f.m[4] = __dmul_rn(y2, v1); f.m[5] = __dmul_rn(y3, v2);
+  f.m[6] = v0; f.m[7] = v1; f.m[8] = v2;
+  return f;
+}
+
 __device__ bool hg_solve(const float2* __restrict__ src, const float2* __restrict__ dst, const int (&idx)[4], double (&h)[9]) {
-  double A[8][9];
-  for (int i = 0; i < 4; ++i) {
-    const double x = src[idx[i]].x, y = src[idx[i]].y, u = dst[idx[i]].x, v = dst[idx[i]].y;
-    double* r0 = A[2 * i];
-    double* r1 = A[2 * i + 1];
-    r0[0] = x; r0[1] = y; r0[2] = 1.0; r0[3] = 0.0; r0[4] = 0.0; r0[5] = 0.0; r0[6] = -__dmul_rn(u, x); r0[7] = -__dmul_rn(u, y); r0[8] = u;
-    r1[0] = 0.0; r1[1] = 0.0; r1[2] = 0.0; r1[3] = x; r1[4] = y; r1[5] = 1.0; r1[6] = -__dmul_rn(v, x); r1[7] = -__dmul_rn(v, y); r1[8] = v;
-  }
-  for (int c = 0; c < 8; ++c) {
-    int p = c;
-    double best = fabs(A[c][c]);
-    for (int r = c + 1; r < 8; ++r)
-      if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); p = r; }
-    if (!(best > 1e-9)) return false;
-    if (p != c)
-      for (int k = 0; k < 9; ++k) { const double t = A[c][k]; A[c][k] = A[p][k]; A[p][k] = t; }
-    const double inv = __ddiv_rn(1.0, A[c][c]);
-    for (int r = c + 1; r < 8; ++r) {
-      const double f = __dmul_rn(A[r][c], inv);
-      for (int k = c; k < 9; ++k) A[r][k] = __dsub_rn(A[r][k], __dmul_rn(f, A[c][k]));
-    }
-  }
-  h[8] = 1.0;
-  for (int c = 7; c >= 0; --c) {
-    double s = A[c][8];
-    for (int k = c + 1; k < 8; ++k) s = __dsub_rn(s, __dmul_rn(A[c][k], h[k]));
-    h[c] = __ddiv_rn(s, A[c][c]);
-  }
+  const HgFrame A = hg_frame(src[idx[0]], src[idx[1]], src[idx[2]], src[idx[3]]);
+  const HgFrame B = hg_frame(dst[idx[0]], dst[idx[1]], dst[idx[2]], dst[idx[3]]);
+  if (!(A.ok && B.ok)) return false;
+  const double* a = A.m;
+  double c[9];                                         // adj(A), row-major
+  c[0] = __dsub_rn(__dmul_rn(a[4], a[8]), __dmul_rn(a[5], a[7]));
+  c[1] = __dsub_rn(__dmul_rn(a[2], a[7]), __dmul_rn(a[1], a[8]));
+  c[2] = __dsub_rn(__dmul_rn(a[1], a[5]), __dmul_rn(a[2], a[4]));
+  c[3] = __dsub_rn(__dmul_rn(a[5], a[6]), __dmul_rn(a[3], a[8]));
+  c[4] = __dsub_rn(__dmul_rn(a[0], a[8]), __dmul_rn(a[2], a[6]));
+  c[5] = __dsub_rn(__dmul_rn(a[2], a[3]), __dmul_rn(a[0], a[5]));
+  c[6] = __dsub_rn(__dmul_rn(a[3], a[7]), __dmul_rn(a[4], a[6]));
+  c[7] = __dsub_rn(__dmul_rn(a[1], a[6]), __dmul_rn(a[0], a[7]));
+  c[8] = __dsub_rn(__dmul_rn(a[0], a[4]), __dmul_rn(a[1], a[3]));
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      h[i * 3 + j] = __dadd_rn(__dadd_rn(__dmul_rn(B.m[i * 3], c[j]), __dmul_rn(B.m[i * 3 + 1], c[3 + j])),
+                               __dmul_rn(B.m[i * 3 + 2], c[6 + j]));
   return true;
 }
 
@@ -73,7 +88,7 @@ __device__ bool hg_solve(const float2* __restrict__ src, const float2* __restric
 // unless it maps exactly, as in the divided form)
 __device__ __forceinline__ bool hg_inlier(const double (&h)[9], float2 s, float2 d, double t2) {
   const double x = s.x, y = s.y;
-  const double w = __dadd_rn(__dadd_rn(__dmul_rn(h[6], x), __dmul_rn(h[7], y)), 1.0);
+  const double w = __dadd_rn(__dadd_rn(__dmul_rn(h[6], x), __dmul_rn(h[7], y)), h[8]);
   const double px = __dadd_rn(__dadd_rn(__dmul_rn(h[0], x), __dmul_rn(h[1], y)), h[2]);
   const double py = __dadd_rn(__dadd_rn(__dmul_rn(h[3], x), __dmul_rn(h[4], y)), h[5]);
   const double ex = __dsub_rn(__dmul_rn((double)d.x, w), px), ey = __dsub_rn(__dmul_rn((double)d.y, w), py);

@@ -10,7 +10,8 @@ error and threshold, restated here operation by operation (IEEE double, no fused
 bit-exact against it:
 
   * hypothesis h = 0..n_hyp-1 draws 4 distinct match indices from a counter-based hash (lowbias32 of seed, h, slot, try);
-  * H maps old -> new (h33 = 1): 8x8 linear system, Gaussian elimination with partial pivoting; singular -> skipped;
+  * H maps old -> new: closed-form projective-basis construction H = frame(new) adj(frame(old)), unnormalised (the inlier
+    test is homogeneous in H); a sample with a triangle of twice-area <= 1 px^2 is degenerate and skipped;
   * a match is an inlier iff |new - H old|^2 <= thresh^2 (OpenCV: findInliers, err <= thresh*thresh), evaluated in the
     division-free form (u w - px)^2 + (v w - py)^2 <= thresh^2 w^2;
   * the winner has the most inliers, ties to the smaller h (OpenCV keeps the first best); mask = its inliers.
@@ -53,36 +54,36 @@ def draw4(seed: int, h: int, n: int):
     return idx
 
 
+def _frame(p: np.ndarray):
+    """[p1 p2 p3] diag(adj([p1 p2 p3]) p4) for 4 points (homogeneous, unnormalised) -> (3x3 row-major list, ok)."""
+    f = np.float64
+    x1, y1, x2, y2, x3, y3, x4, y4 = (f(p[0, 0]), f(p[0, 1]), f(p[1, 0]), f(p[1, 1]), f(p[2, 0]), f(p[2, 1]), f(p[3, 0]),
+                                      f(p[3, 1]))
+    a00 = y2 - y3; a01 = x3 - x2; a02 = x2 * y3 - x3 * y2
+    a10 = y3 - y1; a11 = x1 - x3; a12 = x3 * y1 - x1 * y3
+    a20 = y1 - y2; a21 = x2 - x1; a22 = x1 * y2 - x2 * y1
+    det = (a02 + a12) + a22
+    v0 = (a00 * x4 + a01 * y4) + a02
+    v1 = (a10 * x4 + a11 * y4) + a12
+    v2 = (a20 * x4 + a21 * y4) + a22
+    ok = abs(det) > 1.0 and abs(v0) > 1.0 and abs(v1) > 1.0 and abs(v2) > 1.0     # no triangle of twice-area <= 1 px^2
+    return [x1 * v0, x2 * v1, x3 * v2, y1 * v0, y2 * v1, y3 * v2, v0, v1, v2], ok
+
+
 def solve_h(src4: np.ndarray, dst4: np.ndarray):
-    """H (9 doubles, h33 = 1) with dst ~ H src from 4 correspondences; None if singular."""
-    A = np.zeros((8, 9), np.float64)
-    for i in range(4):
-        x, y = np.float64(src4[i, 0]), np.float64(src4[i, 1])
-        u, v = np.float64(dst4[i, 0]), np.float64(dst4[i, 1])
-        A[2 * i] = [x, y, 1.0, 0.0, 0.0, 0.0, -(u * x), -(u * y), u]
-        A[2 * i + 1] = [0.0, 0.0, 0.0, x, y, 1.0, -(v * x), -(v * y), v]
-    for c in range(8):
-        p = c
-        best = abs(A[c, c])
-        for r in range(c + 1, 8):
-            if abs(A[r, c]) > best:
-                best = abs(A[r, c]); p = r
-        if not best > 1e-9:
-            return None
-        if p != c:
-            A[[c, p]] = A[[p, c]]
-        inv = np.float64(1.0) / A[c, c]
-        for r in range(c + 1, 8):
-            f = A[r, c] * inv
-            for k in range(c, 9):
-                A[r, k] = A[r, k] - f * A[c, k]
+    """H (9 doubles, row-major, UNNORMALISED) with dst ~ H src from 4 correspondences by the projective-basis
+    construction H = frame(dst) adj(frame(src)); None for a degenerate sample."""
+    a, oka = _frame(src4)
+    b, okb = _frame(dst4)
+    if not (oka and okb):
+        return None
+    c = [a[4] * a[8] - a[5] * a[7], a[2] * a[7] - a[1] * a[8], a[1] * a[5] - a[2] * a[4],
+         a[5] * a[6] - a[3] * a[8], a[0] * a[8] - a[2] * a[6], a[2] * a[3] - a[0] * a[5],
+         a[3] * a[7] - a[4] * a[6], a[1] * a[6] - a[0] * a[7], a[0] * a[4] - a[1] * a[3]]
     h = np.zeros(9, np.float64)
-    h[8] = 1.0
-    for c in range(7, -1, -1):
-        s = A[c, 8]
-        for k in range(c + 1, 8):
-            s = s - A[c, k] * h[k]
-        h[c] = s / A[c, c]
+    for i in range(3):
+        for j in range(3):
+            h[i * 3 + j] = (b[i * 3] * c[j] + b[i * 3 + 1] * c[3 + j]) + b[i * 3 + 2] * c[6 + j]
     return h
 
 
@@ -90,7 +91,7 @@ def inliers(h: np.ndarray, src: np.ndarray, dst: np.ndarray, thresh: float) -> n
     """|new - H old|^2 <= thresh^2, stated without the division: with (px, py, w) = H (x, y, 1),
     (u w - px)^2 + (v w - py)^2 <= thresh^2 w^2."""
     x = src[:, 0].astype(np.float64); y = src[:, 1].astype(np.float64)
-    w = (h[6] * x + h[7] * y) + 1.0
+    w = (h[6] * x + h[7] * y) + h[8]
     px = (h[0] * x + h[1] * y) + h[2]
     py = (h[3] * x + h[4] * y) + h[5]
     ex = dst[:, 0].astype(np.float64) * w - px
