@@ -246,7 +246,8 @@ osb_status osb_solver_linearize(osb_solver* h, int n_nodes, const double* poses,
  * none; may be NULL in the host variant).  Fewer than 4 points: empty mask (the reference rejects the pair, :598-600).
  * OpenCV's RANSAC is randomised; this one is deterministic in (points, seed): 512 hypotheses drawn by a counter-based
  * hash, same 4-point model / error / threshold rule, first best hypothesis wins (oracle/geometry_ref.py, pinned against
- * cv2 on well-separated data). */
+ * cv2 on well-separated data).  The two stand-alone entry points share one process-wide scratch buffer: calls on
+ * different streams must not overlap (the front-end owns its own). */
 osb_status osb_homography_ransac(const float* src, const float* dst, const int32_t* n, int n_pairs, int max_n,
                                  float thresh, uint32_t seed, uint8_t* mask, int32_t* n_inliers, int32_t* winner);
 osb_status osb_homography_ransac_dev(const float* src_dev, const float* dst_dev, const int32_t* n_dev, int n_pairs,

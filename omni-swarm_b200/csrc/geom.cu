@@ -7,13 +7,15 @@
 // oracle/geometry_ref.py and pinned there against cv2.  This file is bit-exact against that statement: every floating-point
 // operation is an explicitly rounded IEEE double operation (no fused multiply-add).  The 4-point model is built in
 // closed form (projective basis), so a hypothesis costs ~150 register-resident flops.
+#include <mutex>
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace osb {
 
 constexpr int HG_HYP = 512;            // hypotheses per pair
-constexpr int HG_THREADS = 512;
+constexpr int HG_THREADS = 256;
 constexpr int HG_MAXN = 256;           // matches per pair (<= OSB_MAX_KPTS)
 
 __host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
@@ -95,65 +97,104 @@ __device__ __forceinline__ bool hg_inlier(const double (&h)[9], float2 s, float2
   return __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)) <= __dmul_rn(t2, __dmul_rn(w, w));
 }
 
-// one CTA per pair.  src / dst: [n_pairs][max_n] float2 (old_2d / new_2d of the flagged matches, in match order).
-// Phase A: thread h solves hypothesis h (model -> shared memory).  Phase B: a warp scores one hypothesis at a time, its
-// lanes splitting the matches; the count goes into an atomicMax key (inliers, -hypothesis).  Phase C: the winner's mask.
+// HG_SPLIT CTAs per pair (fp64 scoring is bound by one SM's fp64 pipe: 512 x 200 inlier tests).  src / dst:
+// [n_pairs][max_n] float2 (old_2d / new_2d of the flagged matches, in match order).
+// Phase A: the CTA's 64 hypotheses are solved by its first 64 threads (model -> shared memory).  Phase B: a warp scores
+// one hypothesis at a time, its lanes splitting the matches; the count goes into the pair's global atomicMax key
+// (inliers, -hypothesis).  Phase C: the last CTA of the pair to finish (ticket) rebuilds the winner and writes the mask.
+constexpr int HG_SPLIT = 8;
+constexpr int HG_PER_CTA = HG_HYP / HG_SPLIT;
 __global__ void __launch_bounds__(HG_THREADS)
 homography_ransac_kernel(const float2* __restrict__ src, const float2* __restrict__ dst, const int32_t* __restrict__ n_pts,
                          int max_n, float thresh, uint32_t seed, uint8_t* __restrict__ mask, int32_t* __restrict__ n_inl,
-                         int32_t* __restrict__ winner) {
+                         int32_t* __restrict__ winner, unsigned int* __restrict__ g_key, unsigned int* __restrict__ g_ticket) {
   __shared__ float2 s_src[HG_MAXN], s_dst[HG_MAXN];
-  __shared__ double s_h[HG_HYP][9];
-  __shared__ unsigned char s_ok[HG_HYP];
-  __shared__ unsigned int s_best;
-  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double s_h[HG_PER_CTA][9];
+  __shared__ unsigned char s_ok[HG_PER_CTA];
+  __shared__ int s_last;
+  const int pair = blockIdx.x, part = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = min(n_pts[pair], min(max_n, HG_MAXN));
   uint8_t* mk = mask + (size_t)pair * max_n;
-  for (int i = tid; i < max_n; i += HG_THREADS) mk[i] = 0;
-  if (tid == 0) { s_best = 0u; n_inl[pair] = 0; winner[pair] = -1; }
-  if (n < 4) return;                                   // the reference rejects the pair (loop_detector.cpp:598-600)
+  if (n < 4) {                                         // the reference rejects the pair (loop_detector.cpp:598-600)
+    if (part == 0) {
+      for (int i = tid; i < max_n; i += HG_THREADS) mk[i] = 0;
+      if (tid == 0) { n_inl[pair] = 0; winner[pair] = -1; }
+    }
+    return;
+  }
   for (int i = tid; i < n; i += HG_THREADS) { s_src[i] = src[(size_t)pair * max_n + i]; s_dst[i] = dst[(size_t)pair * max_n + i]; }
   __syncthreads();
   const double t2 = __dmul_rn((double)thresh, (double)thresh);
-  for (int hyp = tid; hyp < HG_HYP; hyp += HG_THREADS) {
+  const int h0 = part * HG_PER_CTA;
+  if (tid < HG_PER_CTA) {
     int idx[4];
     double h[9];
-    const bool ok = hg_draw4(seed, hyp, n, idx) && hg_solve(s_src, s_dst, idx, h);
-    s_ok[hyp] = ok ? 1 : 0;
+    const bool ok = hg_draw4(seed, h0 + tid, n, idx) && hg_solve(s_src, s_dst, idx, h);
+    s_ok[tid] = ok ? 1 : 0;
     if (ok)
-      for (int k = 0; k < 9; ++k) s_h[hyp][k] = h[k];
+      for (int k = 0; k < 9; ++k) s_h[tid][k] = h[k];
   }
   __syncthreads();
-  for (int hyp = warp; hyp < HG_HYP; hyp += HG_THREADS / 32) {
-    if (!s_ok[hyp]) continue;                          // warp-uniform
+  for (int j = warp; j < HG_PER_CTA; j += HG_THREADS / 32) {
+    if (!s_ok[j]) continue;                            // warp-uniform
     double h[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) h[k] = s_h[hyp][k];
+    for (int k = 0; k < 9; ++k) h[k] = s_h[j][k];
     int c = 0;
     for (int i = lane; i < n; i += 32) c += hg_inlier(h, s_src[i], s_dst[i], t2) ? 1 : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     // most inliers, then the smaller hypothesis index: key = (count + 1) << 16 | (0xFFFF - hyp)
-    if (lane == 0) atomicMax(&s_best, ((unsigned)(c + 1) << 16) | (unsigned)(0xFFFF - hyp));
+    if (lane == 0) atomicMax(&g_key[pair], ((unsigned)(c + 1) << 16) | (unsigned)(0xFFFF - (h0 + j)));
   }
+  __threadfence();
   __syncthreads();
-  const unsigned best = s_best;
-  if (best == 0u) return;                              // every hypothesis degenerate
+  if (tid == 0) s_last = (atomicAdd(&g_ticket[pair], 1u) == HG_SPLIT - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const unsigned best = *reinterpret_cast<volatile unsigned int*>(&g_key[pair]);
+  __syncthreads();
+  if (tid == 0) { g_key[pair] = 0u; g_ticket[pair] = 0u; }      // ready for the next launch on this scratch
+  if (best == 0u) {                                    // every hypothesis degenerate
+    for (int i = tid; i < max_n; i += HG_THREADS) mk[i] = 0;
+    if (tid == 0) { n_inl[pair] = 0; winner[pair] = -1; }
+    return;
+  }
   const int hw = 0xFFFF - (int)(best & 0xFFFFu);
+  int idx[4];
   double h[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) h[k] = s_h[hw][k];
-  for (int i = tid; i < n; i += HG_THREADS) mk[i] = hg_inlier(h, s_src[i], s_dst[i], t2) ? 1 : 0;
+  hg_draw4(seed, hw, n, idx);                          // identical arithmetic: every thread rebuilds the winner
+  hg_solve(s_src, s_dst, idx, h);
+  for (int i = tid; i < max_n; i += HG_THREADS) mk[i] = (i < n && hg_inlier(h, s_src[i], s_dst[i], t2)) ? 1 : 0;
   if (tid == 0) { n_inl[pair] = (int)(best >> 16) - 1; winner[pair] = hw; }
+}
+
+// per-pair scratch of the kernel (key + ticket), zero between launches
+static unsigned int* hg_scratch(int n_pairs) {
+  static unsigned int* buf = nullptr;
+  static int cap = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (n_pairs > cap) {
+    unsigned int* nb = nullptr;
+    const int ncap = std::max(64, n_pairs);
+    if (cudaMalloc(&nb, 2 * (size_t)ncap * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    cudaMemset(nb, 0, 2 * (size_t)ncap * sizeof(unsigned int));
+    buf = nb; cap = ncap;                              // (an outgrown buffer is left to the context: launches may still use it)
+  }
+  return buf;
 }
 
 osb_status homography_ransac_device(const float* src_dev, const float* dst_dev, const int32_t* n_dev, int n_pairs, int max_n,
                                     float thresh, uint32_t seed, uint8_t* mask_dev, int32_t* n_inl_dev, int32_t* winner_dev,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, unsigned int* scratch) {
   if (n_pairs <= 0) return OSB_OK;
   OSB_REQUIRE(max_n > 0 && max_n <= HG_MAXN, "homography: max_n out of range (1..256)");
-  OSB_LAUNCH(homography_ransac_kernel, n_pairs, HG_THREADS, 0, st, reinterpret_cast<const float2*>(src_dev),
-             reinterpret_cast<const float2*>(dst_dev), n_dev, max_n, thresh, seed, mask_dev, n_inl_dev, winner_dev);
+  OSB_REQUIRE(scratch != nullptr, "homography: no scratch");
+  OSB_LAUNCH(homography_ransac_kernel, dim3(n_pairs, HG_SPLIT), HG_THREADS, 0, st, reinterpret_cast<const float2*>(src_dev),
+             reinterpret_cast<const float2*>(dst_dev), n_dev, max_n, thresh, seed, mask_dev, n_inl_dev, winner_dev, scratch,
+             scratch + n_pairs);
   OSB_CHECK_LAUNCH();
   return OSB_OK;
 }
@@ -168,8 +209,9 @@ extern "C" osb_status osb_homography_ransac_dev(const float* src_dev, const floa
   OSB_REQUIRE(src_dev && dst_dev && n_dev && mask_dev && n_inliers_dev && winner_dev, "null argument");
   osb_status s = require_device();
   if (s != OSB_OK) return s;
+  // (shared process-wide scratch: concurrent callers on different streams must serialise, as documented in the header)
   return homography_ransac_device(src_dev, dst_dev, n_dev, n_pairs, max_n, thresh, seed, mask_dev, n_inliers_dev, winner_dev,
-                                  (cudaStream_t)stream);
+                                  (cudaStream_t)stream, hg_scratch(n_pairs));
 }
 
 // host buffers in / out (allocates its scratch per call: a convenience for tests and small callers)
@@ -192,7 +234,7 @@ extern "C" osb_status osb_homography_ransac(const float* src, const float* dst, 
   OSB_CUDA(cudaMemcpy(d_src, src, pts * 2 * sizeof(float), cudaMemcpyHostToDevice));
   OSB_CUDA(cudaMemcpy(d_dst, dst, pts * 2 * sizeof(float), cudaMemcpyHostToDevice));
   OSB_CUDA(cudaMemcpy(d_n, n, n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice));
-  s = homography_ransac_device(d_src, d_dst, d_n, n_pairs, max_n, thresh, seed, d_mask, d_inl, d_win, nullptr);
+  s = homography_ransac_device(d_src, d_dst, d_n, n_pairs, max_n, thresh, seed, d_mask, d_inl, d_win, nullptr, hg_scratch(n_pairs));
   if (s == OSB_OK) {
     OSB_CUDA(cudaMemcpy(mask, d_mask, pts, cudaMemcpyDeviceToHost));
     OSB_CUDA(cudaMemcpy(n_inliers, d_inl, n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost));

@@ -71,6 +71,6 @@ osb_status nhwc_to_nchw(const float* in, float* out, int B, int C, int h, int w,
 // homography-RANSAC inlier masks of n_pairs correspondence sets ([n_pairs][max_n] float2 old / new points)
 osb_status homography_ransac_device(const float* src_dev, const float* dst_dev, const int32_t* n_dev, int n_pairs, int max_n,
                                     float thresh, uint32_t seed, uint8_t* mask_dev, int32_t* n_inl_dev, int32_t* winner_dev,
-                                    cudaStream_t st);
+                                    cudaStream_t st, unsigned int* scratch /* 2 * n_pairs words, zero between launches */);
 
 }  // namespace osb

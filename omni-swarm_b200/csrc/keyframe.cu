@@ -342,6 +342,7 @@ struct osb_frontend {
   float *d_g_src = nullptr, *d_g_dst = nullptr;
   int32_t *d_g_kept = nullptr, *d_g_nkept = nullptr, *d_g_ninl = nullptr, *d_g_win = nullptr;
   uint8_t* d_g_mask = nullptr;
+  unsigned int* d_g_scratch = nullptr;
   int32_t* d_assign = nullptr;   // [max_records][4]
   int max_records = 64;
   osb_keyframe_record* d_record = nullptr;   // used by process()
@@ -453,6 +454,8 @@ extern "C" osb_status osb_frontend_create(osb_frontend** out, const osb_frontend
   FE_CUDA(cudaMalloc(&h->d_g_ninl, OSB_MAX_DIRS * sizeof(int32_t)));
   FE_CUDA(cudaMalloc(&h->d_g_win, OSB_MAX_DIRS * sizeof(int32_t)));
   FE_CUDA(cudaMalloc(&h->d_g_mask, OSB_MAX_DIRS * OSB_MAX_KPTS));
+  FE_CUDA(cudaMalloc(&h->d_g_scratch, 2 * OSB_MAX_DIRS * sizeof(unsigned int)));
+  FE_CUDA(cudaMemset(h->d_g_scratch, 0, 2 * OSB_MAX_DIRS * sizeof(unsigned int)));
   FE_CUDA(cudaMalloc(&h->d_dist_scratch, (size_t)OSB_MAX_DIRS * mn * mn * sizeof(float)));
   FE_CUDA(cudaMalloc(&h->d_q_nq, OSB_MAX_DIRS * sizeof(int32_t)));
   FE_CUDA(cudaMalloc(&h->d_q_nt, OSB_MAX_DIRS * sizeof(int32_t)));
@@ -482,7 +485,7 @@ extern "C" osb_status osb_frontend_destroy(osb_frontend* h) {
   cudaFree(h->d_img); cudaFree(h->d_st_q); cudaFree(h->d_st_t); cudaFree(h->d_q_q); cudaFree(h->d_q_t);
   cudaFree(h->d_st_qi); cudaFree(h->d_st_ti); cudaFree(h->d_st_map); cudaFree(h->d_st_n); cudaFree(h->d_st_dist);
   cudaFree(h->d_g_qk); cudaFree(h->d_g_tk); cudaFree(h->d_g_qflag); cudaFree(h->d_g_src); cudaFree(h->d_g_dst);
-  cudaFree(h->d_g_kept); cudaFree(h->d_g_nkept); cudaFree(h->d_g_ninl); cudaFree(h->d_g_win); cudaFree(h->d_g_mask);
+  cudaFree(h->d_g_kept); cudaFree(h->d_g_nkept); cudaFree(h->d_g_ninl); cudaFree(h->d_g_win); cudaFree(h->d_g_mask); cudaFree(h->d_g_scratch);
   cudaFree(h->d_q_dist); cudaFree(h->d_dist_scratch); cudaFree(h->d_q_nq); cudaFree(h->d_q_nt); cudaFree(h->d_assign);
   cudaFree(h->d_record); cudaFree(h->d_result);
   for (int i = 0; i < 9; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -637,7 +640,7 @@ static osb_status fe_query(osb_frontend* h, const osb_keyframe_record* rec, int 
                reinterpret_cast<float2*>(h->d_g_src), reinterpret_cast<float2*>(h->d_g_dst), h->d_g_kept, h->d_g_nkept);
     OSB_CHECK_LAUNCH();
     if ((s = homography_ransac_device(h->d_g_src, h->d_g_dst, h->d_g_nkept, OSB_MAX_DIRS, OSB_MAX_KPTS, 3.0f,
-                                      (uint32_t)c.ransac_seed, h->d_g_mask, h->d_g_ninl, h->d_g_win, st)) != OSB_OK) return s;
+                                      (uint32_t)c.ransac_seed, h->d_g_mask, h->d_g_ninl, h->d_g_win, st, h->d_g_scratch)) != OSB_OK) return s;
     OSB_LAUNCH(fe_geo_apply_kernel, OSB_MAX_DIRS, 256, 0, st, res, h->d_g_kept, h->d_g_nkept, h->d_g_mask);
     OSB_CHECK_LAUNCH();
   }
