@@ -125,6 +125,8 @@ struct UmmaArgs {
   int n_off;               // first output channel of this launch (Cout > 256 runs as several N <= 256 passes)
   int pool;                // 1: fused 2x2 max-pool, the planes written are [B][H/2][W/2][C]
   int n_split;             // a layer wider than the kernel's N runs as n_split work items per tile (N channels each)
+  int epi;                 // 0: bias/act/pool + store; 1: detector head -- softmax over 65 logits, drop the dustbin,
+                           //    8x8 pixel shuffle straight into the heat map `out_f32` ([B][8H][8W])
 };
 
 template <int N, bool RES, bool SPLIT>
@@ -303,6 +305,52 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       const int py = ty * (UM_TH / 2) + q, px = tx * (UM_TW / 2) + (lane >> 1);
       const bool pool_writer = P.pool && lane < 16 && !(lane & 1) && py < (P.H >> 1) && px < (P.W >> 1);
       const size_t ppix = ((size_t)b * (P.H >> 1) + py) * (P.W >> 1) + px;
+      if (P.epi == 1) {
+        // fused detector head (superpoint.ipynb:190-198): the thread holds one cell's 65 logits in TMEM.  Three passes over
+        // the columns (max, sum in channel order, normalise + pixel shuffle) -- the arithmetic of sp_softmax_shuffle_kernel,
+        // so the heat map is bit-identical to the two-kernel path.
+        auto logit = [&](uint32_t a, uint32_t c, int ch) {
+          return fmaf(__uint_as_float(a) + __uint_as_float(c), P.inv_scale, __ldg(P.bias + ch));
+        };
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int n0 = 0; n0 < 80; n0 += 16) {
+          uint32_t v[16], vc[16];
+          tmem_ld16(t_row + n0, v);
+          tmem_ld16(t_row + N + n0, vc);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n0 + i < 65) mx = fmaxf(mx, logit(v[i], vc[i], n0 + i));
+        }
+        float sum = 0.f;
+#pragma unroll 1
+        for (int n0 = 0; n0 < 80; n0 += 16) {
+          uint32_t v[16], vc[16];
+          tmem_ld16(t_row + n0, v);
+          tmem_ld16(t_row + N + n0, vc);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n0 + i < 65) sum += expf(logit(v[i], vc[i], n0 + i) - mx);
+        }
+        const int W8 = P.W * 8;
+        float* out = P.out_f32 + ((size_t)b * P.H * 8 + (size_t)y * 8) * W8 + (size_t)x * 8;
+#pragma unroll 1
+        for (int n0 = 0; n0 < 64; n0 += 16) {
+          uint32_t v[16], vc[16];
+          tmem_ld16(t_row + n0, v);
+          tmem_ld16(t_row + N + n0, vc);
+          if (!inside) continue;
+          float e[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) e[i] = expf(logit(v[i], vc[i], n0 + i) - mx) / sum;
+#pragma unroll
+          for (int r2 = 0; r2 < 2; ++r2) {
+            float4* dst = reinterpret_cast<float4*>(out + (size_t)(n0 / 8 + r2) * W8);
+            dst[0] = make_float4(e[8 * r2], e[8 * r2 + 1], e[8 * r2 + 2], e[8 * r2 + 3]);
+            dst[1] = make_float4(e[8 * r2 + 4], e[8 * r2 + 5], e[8 * r2 + 6], e[8 * r2 + 7]);
+          }
+        }
+      } else
 #pragma unroll 1
       for (int n0 = 0; n0 < N; n0 += 16) {
         uint32_t v[16], vc[16];
@@ -623,7 +671,7 @@ osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const 
   P.out_c = out_c; P.out_cstride = out_cstride;
   P.inv_scale = 1.0f / (act_scale * L.w_scale); P.out_scale = out_scale; P.relu = relu;
   OSB_REQUIRE(out_c % 16 == 0 && out_c <= L.n_pad && out_cstride % 8 == 0, "tcgen05 conv: bad output channel layout");
-  P.n_off = 0; P.n_split = 1;
+  P.n_off = 0; P.n_split = 1; P.epi = 0;
   switch (L.n_pad) {
     case 64:
       if (L.ks == 3 && L.cin == UM_KC) return launch_umma<64, true>(a_hi, a_lo, L, P, st, max_ctas);   // weights resident
@@ -651,6 +699,20 @@ osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const 
   }
   set_error("umma_conv_forward", "unsupported N");
   return OSB_ERR_INVALID;
+}
+
+// detector head: convPb (256 -> 65, 1x1) with the softmax + 8x8 pixel shuffle fused into the epilogue; `semi` is the heat
+// map [B][8H][8W]
+osb_status umma_conv_softmax_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int B, int H, int W,
+                                     float act_scale, float* semi, cudaStream_t st, int max_ctas) {
+  OSB_REQUIRE(L.n_pad == 80 && L.cout == 65 && L.ks == 1, "fused detector head expects the 65-logit 1x1 layer");
+  UmmaArgs P;
+  P.pool = 0; P.bias = L.bias; P.out_hi = nullptr; P.out_lo = nullptr; P.out_f32 = semi;
+  P.H = H; P.W = W; P.B = B; P.ks = L.ks; P.cin_slabs = L.cin / UM_KC;
+  P.out_c = 80; P.out_cstride = 80;
+  P.inv_scale = 1.0f / (act_scale * L.w_scale); P.out_scale = 1.f; P.relu = 0;
+  P.n_off = 0; P.n_split = 1; P.epi = 1;
+  return launch_umma<80, false>(a_hi, a_lo, L, P, st, max_ctas);
 }
 
 // depthwise 3x3 (pad 1, stride s) + bias + ReLU6 on fp32 NHWC input, output as split fp16 planes for the pointwise

@@ -27,6 +27,8 @@ osb_status umma_act_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half*
 osb_status umma_conv_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int B, int H, int W,
                              float act_scale, __half* out_hi, __half* out_lo, float* out_f32, int out_c, int out_cstride,
                              float out_scale, int relu, int pool, cudaStream_t st, int max_ctas = 0);
+osb_status umma_conv_softmax_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int B, int H, int W,
+                                     float act_scale, float* semi, cudaStream_t st, int max_ctas = 0);
 osb_status umma_first_forward(const float* w_tap_cout, const float* bias, const float* lut, const uint8_t* img,
                               __half* out_hi, __half* out_lo, int B, int H, int W, float out_scale, cudaStream_t st);
 // depthwise 3x3 + bias + ReLU6, fp32 NHWC in, split fp16 planes out (feeds a pointwise tcgen05 conv)

@@ -38,6 +38,7 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
   OSB_CUDA(cudaEventCreateWithFlags(&ev_semi, cudaEventDisableTiming));
   OSB_CUDA(cudaEventCreateWithFlags(&ev_kp, cudaEventDisableTiming));
   if (const char* e = getenv("OSB_SP_OVERLAP")) overlap_kp = atoi(e) != 0;
+  if (const char* e = getenv("OSB_SP_FUSED_SOFTMAX")) fused_softmax = atoi(e) != 0;
   // ---- weights ----
   const float* p = weights;
   {
@@ -169,9 +170,14 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
   mark(st);
   RUN(conv(8, Hc, Wc, 9, 0));                                                             // convPa            -> A
   mark(st);
-  RUN(umma_conv_forward(UL[9], tmA[9], tmB[9], B, Hc, Wc, SA, nullptr, nullptr, d_logits, 80, 80, 1.f, 0, 0, st));   // convPb
-  mark(st);
-  RUN(sp_softmax_shuffle(d_logits, 80, d_semi, B, Hc, Wc, st));
+  if (fused_softmax) {
+    RUN(umma_conv_softmax_forward(UL[9], tmA[9], tmB[9], B, Hc, Wc, SA, d_semi, st));      // convPb + softmax + pixel shuffle
+    mark(st);
+  } else {
+    RUN(umma_conv_forward(UL[9], tmA[9], tmB[9], B, Hc, Wc, SA, nullptr, nullptr, d_logits, 80, 80, 1.f, 0, 0, st));   // convPb
+    mark(st);
+    RUN(sp_softmax_shuffle(d_logits, 80, d_semi, B, Hc, Wc, st));
+  }
   // the keypoint kernel (one CTA per image, latency-bound) runs beside the descriptor head, which leaves it B SMs
   const bool fork = kp && overlap_kp && !layer_prof && kp_stream;
   int head_ctas = 0;

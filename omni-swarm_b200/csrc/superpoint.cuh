@@ -43,6 +43,7 @@ struct SuperPoint {
   cudaStream_t kp_stream = nullptr;
   cudaEvent_t ev_semi = nullptr, ev_kp = nullptr;
   bool overlap_kp = true;
+  bool fused_softmax = true;       // detector-head softmax + pixel shuffle in convPb's epilogue (OSB_SP_FUSED_SOFTMAX=0: two kernels)
   osb_status network(const uint8_t* img_dev, int B, cudaStream_t st, const KpJob* kp = nullptr);
   osb_status network_umma(const uint8_t* img_dev, int B, cudaStream_t st, const KpJob* kp);
   osb_status keypoints(int B, const KpJob& kp, cudaStream_t st);
