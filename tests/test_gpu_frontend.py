@@ -174,3 +174,46 @@ def test_geometric_filter_in_query(gpu):
     _, res = fe.process(*frames[0], msg_id=99)
     assert list(res.geo_valid) == [0, 0, 0, 0] and list(res.n_geo) == [0, 0, 0, 0]
     fe.close()
+
+
+def test_geometric_filter_on_loaded_rows(gpu):
+    """Rows put in with db_load get their landmarks_2d / stereo_match through db_set_geometry; a query that hits such a
+    row runs the geometric filter on them (and treats every landmark as flagged when no geometry was set)."""
+    import torch
+    from oracle import geometry_ref as gr
+    fe = make_frontend(match_index_dist=1, geometric_filter=True, ransac_seed=0)
+    rng = np.random.default_rng(2)
+    n_rows, mn = 12, 200
+    g = synth.descriptor_db(n_rows, 4096, 9)
+    ld = synth.local_descriptors(mn, 77)[None].repeat(n_rows, 0).copy()          # same 200 local descriptors in every row
+    nk = np.full(n_rows, 150, np.int32)
+    fe.db_load(g, ld, nk, remote=False)
+    k_old = np.zeros((n_rows, mn, 2), np.float32)
+    k_old[:, :150] = rng.uniform(0, 90, (n_rows, 150, 2)).astype(np.float32)
+    sm = np.zeros((n_rows, mn), np.int32)
+    fe.db_set_geometry(0, k_old, sm, remote=False)
+    # query record: direction 1 carries row 3's descriptors; its landmarks are row 3's shifted by (5, -2), 30 of them moved far
+    rec = lib.KeyframeRecord()
+    rec.drone_id, rec.msg_id, rec.n_dirs = 1, 500, 4
+    rec.n_kpts[1] = 150
+    np.ctypeslib.as_array(rec.global_desc[1])[:] = g[3]
+    np.ctypeslib.as_array(rec.local_desc[1])[:150] = ld[3, :150]
+    k_new = k_old[3].copy(); k_new[:150] += np.float32([5.0, -2.0]); k_new[:30] += np.float32(40.0)
+    np.ctypeslib.as_array(rec.kpts[1])[:] = k_new
+    smn = np.zeros(mn, np.int32); smn[100:120] = -1                              # 20 new landmarks without a 3-D flag
+    np.ctypeslib.as_array(rec.stereo_match[1])[:] = smn
+    stream = torch.cuda.current_stream().cuda_stream
+    rec_t = torch.frombuffer(bytearray(bytes(rec)), dtype=torch.uint8).cuda()
+    res_t = torch.zeros(lib.RESULT_BYTES, dtype=torch.uint8, device="cuda")
+    fe.query(rec_t.data_ptr(), res_t.data_ptr(), stream)
+    fe.finish(stream)
+    res = lib.LoopResult.from_buffer_copy(res_t.cpu().numpy().tobytes())
+    assert res.accepted == 1 and res.hit_id == 3 and res.dir_new[0] == 1
+    n = res.n_matches[0]
+    mnw = list(res.match_new[0][:n]); mo = list(res.match_old[0][:n])
+    assert mnw == list(range(150)) == mo                                         # identical descriptors: identity match
+    qn, qo = gr.loop_pair_filter(mnw, mo, (smn >= 0).astype(np.uint8), k_new, k_old[3], 3.0, seed=0)
+    gcount = res.n_geo[0]
+    assert res.geo_valid[0] == 1 and gcount == len(qn) == 150 - 30 - 20
+    assert list(res.geo_new[0][:gcount]) == qn.tolist() and list(res.geo_old[0][:gcount]) == qo.tolist()
+    fe.close()
