@@ -500,42 +500,6 @@ conv_first_split_kernel(const float* __restrict__ w, const float* __restrict__ b
   }
 }
 
-// one thread per (output pixel, 8 channels)
-__global__ void maxpool_split_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
-                                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int C8,
-                                     int64_t total) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int Ho = H / 2, Wo = W / 2;
-  const int c = (int)(i % C8);
-  int64_t p = i / C8;
-  const int ox = (int)(p % Wo); p /= Wo;
-  const int oy = (int)(p % Ho);
-  const int b = (int)(p / Ho);
-  float m[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
-#pragma unroll
-  for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 2; ++dx) {
-      const size_t off = ((((size_t)b * H + 2 * oy + dy) * W + 2 * ox + dx) * C8 + c) * 8;
-      const uint4 h = *reinterpret_cast<const uint4*>(in_hi + off);
-      const uint4 l = *reinterpret_cast<const uint4*>(in_lo + off);
-      const uint32_t hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a0 = __half2float(__ushort_as_half((unsigned short)(hv[j] & 0xffff))) +
-                         __half2float(__ushort_as_half((unsigned short)(lv[j] & 0xffff)));
-        const float a1 = __half2float(__ushort_as_half((unsigned short)(hv[j] >> 16))) +
-                         __half2float(__ushort_as_half((unsigned short)(lv[j] >> 16)));
-        m[2 * j] = fmaxf(m[2 * j], a0); m[2 * j + 1] = fmaxf(m[2 * j + 1], a1);
-      }
-    }
-  // the planes already carry the scale: max commutes with the positive scale, re-split with scale 1
-  split_store8(out_hi + (size_t)i * 8, out_lo + (size_t)i * 8, m, 1.0f);
-}
-
 // --------------------------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------------------------
@@ -838,14 +802,6 @@ osb_status umma_first_forward(const float* w_tap_cout, const float* bias, const 
                               __half* out_hi, __half* out_lo, int B, int H, int W, float out_scale, cudaStream_t st) {
   dim3 grid(cdiv(W, CF_TW), cdiv(H, CF_TH), B);
   OSB_LAUNCH(conv_first_split_kernel, grid, 256, 0, st, w_tap_cout, bias, lut, img, out_hi, out_lo, H, W, out_scale);
-  OSB_CHECK_LAUNCH();
-  return OSB_OK;
-}
-
-osb_status umma_maxpool_forward(const __half* in_hi, const __half* in_lo, __half* out_hi, __half* out_lo, int B, int H,
-                                int W, int C, cudaStream_t st) {
-  const int64_t total = (int64_t)B * (H / 2) * (W / 2) * (C / 8);
-  OSB_LAUNCH(maxpool_split_kernel, (unsigned)cdiv64(total, 256), 256, 0, st, in_hi, in_lo, out_hi, out_lo, H, W, C / 8, total);
   OSB_CHECK_LAUNCH();
   return OSB_OK;
 }

@@ -34,7 +34,4 @@ osb_status umma_first_forward(const float* w_tap_cout, const float* bias, const 
 // depthwise 3x3 + bias + ReLU6, fp32 NHWC in, split fp16 planes out (feeds a pointwise tcgen05 conv)
 osb_status umma_dwconv_forward(const float* w_tap_c, const float* bias, const float* x, __half* out_hi, __half* out_lo,
                                int B, int H, int W, int C, int stride, float out_scale, cudaStream_t st);
-osb_status umma_maxpool_forward(const __half* in_hi, const __half* in_lo, __half* out_hi, __half* out_lo, int B, int H,
-                                int W, int C, cudaStream_t st);
-
 }  // namespace osb
