@@ -76,7 +76,9 @@ osb_status osb_superpoint_infer_dev(osb_superpoint* h, const uint8_t* images_dev
  *               outputs, superpoint_tensorrt.cpp:139-140) and run ONLY getKeyPoints+NMS2+computeDescriptors.
  *  read:        copy an intermediate of the last infer() back: what = 0 semi [H][W], 1 desc [256][H/8][W/8],
  *               2 confidences of the returned keypoints [max_num], 3 NMS survivor plane as float [H][W],
- *               4 keypoint kernel counters [8]: candidates, survivors, NMS rounds, 0, SM cycles of its 4 phases. */
+ *               4 keypoint kernel counters [8]: candidates, survivors, NMS rounds, 0, SM cycles of its 4 phases,
+ *               5 cycle counters [16] of the fused conv1a+conv1b kernel's CTA 0 from the last infer() with profiling on
+ *                 (producer wait / compute / wait, loop total, MMA wait TMEM / wait tile / issue, epilogue wait / work, tiles). */
 osb_status osb_superpoint_postprocess(osb_superpoint* h, const float* semi, const float* desc_nchw, int batch,
                                       int32_t* n_kpts, float* kpts, float* desc);
 osb_status osb_superpoint_read(osb_superpoint* h, int what, int image, float* out, size_t n_floats);
@@ -246,8 +248,8 @@ osb_status osb_solver_linearize(osb_solver* h, int n_nodes, const double* poses,
  * none; may be NULL in the host variant).  Fewer than 4 points: empty mask (the reference rejects the pair, :598-600).
  * OpenCV's RANSAC is randomised; this one is deterministic in (points, seed): 512 hypotheses drawn by a counter-based
  * hash, same 4-point model / error / threshold rule, first best hypothesis wins (oracle/geometry_ref.py, pinned against
- * cv2 on well-separated data).  The two stand-alone entry points share one process-wide scratch buffer: calls on
- * different streams must not overlap (the front-end owns its own). */
+ * cv2 on well-separated data).  No process-wide state: the _dev entry point takes its scratch from the stream-ordered
+ * allocator of `stream`, so concurrent callers on different streams are safe. */
 osb_status osb_homography_ransac(const float* src, const float* dst, const int32_t* n, int n_pairs, int max_n,
                                  float thresh, uint32_t seed, uint8_t* mask, int32_t* n_inliers, int32_t* winner);
 osb_status osb_homography_ransac_dev(const float* src_dev, const float* dst_dev, const int32_t* n_dev, int n_pairs,
@@ -290,6 +292,10 @@ typedef struct {
   int32_t swapped;               /* 1 when the hit is a remote keyframe and the query keyframe is our own: the reference
                                     then calls compute_loop(old, new) (loop_detector.cpp:113-118), i.e. the DATABASE
                                     frame is the matcher's query side ("new") and the current keyframe the train side */
+  int32_t hit_msg_id;            /* msg_id of the matched keyframe = imgid2fisheye[best_image_id], the key of
+                                    fisheyeframe_database (loop_detector.cpp:272-275,105-111); -1 without a hit, and for rows
+                                    put in with osb_frontend_db_load */
+  int32_t hit_drone_id;          /* drone_id of the matched keyframe (fisheyeframe_database[msg_id].drone_id); -1 without a hit */
   int32_t dir_new[OSB_MAX_DIRS]; /* direction pairing of compute_correspond_features (loop_detector.cpp:455-465), */
   int32_t dir_old[OSB_MAX_DIRS]; /* one slot per pair with landmarks on both sides, -1 = unused slot */
   int32_t n_matches[OSB_MAX_DIRS];                 /* cross-check matches new-vs-old per direction pair */

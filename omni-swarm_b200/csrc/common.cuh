@@ -47,13 +47,37 @@ inline void set_error(const char* where, const char* what) {
 
 #define OSB_CHECK_LAUNCH() OSB_CUDA(cudaGetLastError())
 
+// Per-DEVICE (not per-process) state: a host process may open handles on several GPUs (one nodelet per drone on the
+// 8-GPU box), so "done once" flags and cached device attributes are keyed by the current device.
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < 64) ? dev : 0;
+}
+struct PerDeviceOnce {                     // first(dev) is true exactly once per device, thread-safe
+  std::atomic<unsigned long long> mask{0};
+  bool first(int dev) { return !((mask.fetch_or(1ull << dev, std::memory_order_acq_rel) >> dev) & 1ull); }
+  void reset(int dev) { mask.fetch_and(~(1ull << dev), std::memory_order_acq_rel); }
+};
+// opt a kernel into > 48 KB of dynamic shared memory on the CURRENT device, once per device
+#define OSB_SMEM_OPT_IN(kernel, bytes)                                                                      \
+  do {                                                                                                      \
+    static osb::PerDeviceOnce _once;                                                                        \
+    const int _dev = osb::current_device();                                                                 \
+    if (_once.first(_dev)) {                                                                                \
+      cudaError_t _oe = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+      if (_oe != cudaSuccess) { _once.reset(_dev); OSB_CUDA(_oe); }                                           \
+    }                                                                                                       \
+  } while (0)
+
 inline int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  const int dev = current_device();
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }

@@ -1,0 +1,365 @@
+// conv1_fused.cu -- SuperPoint's first two layers as ONE kernel: conv1a (1 -> 64, 3x3, ReLU) is computed inside the SM and
+// feeds conv1b (64 -> 64, 3x3, ReLU, fused 2x2 max-pool) on the tensor cores without ever leaving shared memory.
+// (swarm_loop/superpoint.ipynb:143-146,165-167 of the reference)
+//
+// Unfused, conv1a wrote its output as split-fp16 planes (629 MB per 8-image keyframe) that conv1b immediately re-read:
+// a 0.17 ms kernel plus 4.8x avoidable HBM traffic in the dominant layer.  Here the only HBM traffic of the pair is the u8
+// image in and the pooled conv1b planes out.
+//
+// Tile = 16 rows x 8 pixels of conv1b output (M = 128, GEMM row m = r*8 + c).  Its conv1a halo tile is 18 rows x 10 pixels
+// x 64 channels, kept ONCE in shared memory as two fp16 planes (hi, lo), pixel pitch 128 B, row pitch 1280 B, each pixel's
+// eight 16-byte channel chunks XOR-swizzled with bits [7,10) of their absolute shared-memory address -- the K-major
+// SWIZZLE_128B pattern.  All nine filter taps are views of that one copy: tap (ky,kx) is the UMMA descriptor whose start
+// address is moved by (ky*10 + kx)*128 bytes, with SBO = 1280 B between the 8-pixel row groups.  That the tensor core
+// derives its XOR phase from the absolute address (so that a start address inside a 1024-byte swizzle atom and an SBO that
+// is not a multiple of 1024 read the right bytes) was measured on the B200 with scripts/microbench/umma_swizzle_probe.cu
+// (profiles/r02_umma_swizzle_probe.txt: variant 0 exact for all nine taps).
+//
+// Shared memory (227 KB): conv1b weights resident, 9 taps x [W_hi | W_lo] = 144 KB; halo rows: 33 rows x 1280 B x 2 planes
+// = 82.5 KB -- not the 36 rows two independent tiles would need.  Tiles therefore alternate between window 0 = rows
+// [0,18) and window 1 = rows [15,33): 15 of a tile's 18 halo rows can be produced while the previous tile's MMAs are
+// still reading theirs, the 3 overlapping rows are computed early, held in registers and stored as soon as those MMAs
+// have retired.
+//
+// Warp roles (448 threads = 14 warps): warp 13 weight TMA + MMA issuer (one lane; the scheduler arbitrates
+// highest-warp-id-first, so the issuer is never starved by the producers it shares a scheduler with), warp 12 TMEM
+// allocator, warps 4-7 epilogue (TMEM -> bias/ReLU -> 2x2 max-pool by shuffles -> re-split -> NHWC planes of conv2a's
+// input), warps 0-3 and 8-11 conv1a producers: two per scheduler, the u8 input patch of a tile (20 x 12 bytes) staged in
+// shared memory one tile ahead (thread = 8 output channels of one halo pixel column, 72 weights in registers, fp32 FMAs in the order of
+// conv_first_split_kernel, so the fused and unfused paths are bit-identical).
+#include "conv_umma.cuh"
+#include "umma_ptx.cuh"
+
+namespace osb {
+
+constexpr int F1_TH = 16, F1_TW = 8;                    // conv1b output tile
+constexpr int F1_HR = F1_TH + 2, F1_HC = F1_TW + 2;     // conv1a halo tile: 18 x 10 pixels
+constexpr int F1_PITCH = F1_HC * 128;                   // bytes per halo row per plane
+constexpr int F1_ROWS = 33;                             // window 0 = rows [0,18), window 1 = rows [15,33)
+constexpr int F1_WIN1 = F1_ROWS - F1_HR;                // 15: first row of window 1
+constexpr int F1_PLANE = F1_ROWS * F1_PITCH;            // 42 240 B
+constexpr int F1_W_SLOT = 2 * 64 * 128;                 // one tap: [W_hi (64 rows) | W_lo (64 rows)] x 128 B
+constexpr int F1_W_BYTES = 9 * F1_W_SLOT;               // 147 456 B
+constexpr int F1_NPROD = 8;                             // producer warps: 8 x 4 pixel slots per step
+constexpr int F1_THREADS = 14 * 32;                     // 448 (register allocation rounds to 16 warps: 128 registers)
+constexpr int F1_BAR_OFF = F1_W_BYTES + 2 * F1_PLANE;
+constexpr int F1_PR = F1_HR + 2, F1_PC = F1_HC + 2;     // u8 input patch of a tile: 20 rows x 12 columns
+constexpr int F1_PATCH_OFF = F1_BAR_OFF + 80;           // 9 mbarriers + the TMEM base slot, then the patch
+constexpr int F1_SMEM = F1_PATCH_OFF + F1_PR * F1_PC;
+static_assert(F1_SMEM <= 227 * 1024, "shared memory plan exceeds 227 KB");
+static_assert(F1_PR * F1_PC <= F1_NPROD * 32, "one patch byte per producer thread");
+
+struct Fused1Args {
+  const uint8_t* img;      // [B][H][W]
+  const float* w1a;        // conv1a weights [tap][64]
+  const float* b1a;        // conv1a bias [64]
+  const float* bias;       // conv1b bias [64]
+  __half* out_hi;          // pooled conv1b output planes [B][H/2][W/2][64]
+  __half* out_lo;
+  int H, W, B;
+  float alpha;             // (float)(1/255): u8 -> f32 as cv::Mat::convertTo does (superpoint_tensorrt.cpp:127)
+  float act_scale;         // scale of the conv1a planes (power of two)
+  float inv_scale;         // 1 / (act_scale * w_scale)
+  float out_scale;         // scale of the stored planes
+  unsigned long long* dbg; // optional [16] cycle counters of CTA 0 (null = off): see umma_conv1_fused_forward
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void st_shared_128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(F1_THREADS, 1)
+conv1_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, Fused1Args P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();                              // the plan has no slack for re-aligning
+  const uint32_t a_hi_base = base + F1_W_BYTES, a_lo_base = a_hi_base + F1_PLANE;
+  const uint32_t bar_base = base + F1_BAR_OFF;
+  const uint32_t b_full = bar_base;
+  auto a_full = [&](int w) { return bar_base + 8u * (1 + w); };
+  auto mma_done = [&](int w) { return bar_base + 8u * (3 + w); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (5 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (7 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + F1_BAR_OFF + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = (P.W + F1_TW - 1) / F1_TW, tiles_y = (P.H + F1_TH - 1) / F1_TH;
+  const int n_tiles = P.B * tiles_x * tiles_y;
+
+  if (threadIdx.x == 0) {
+    mbar_init(b_full, 1);
+    for (int w = 0; w < 2; ++w) { mbar_init(a_full(w), F1_NPROD); mbar_init(mma_done(w), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(bar_base + 72u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == 13 && lane == 0) {
+    // ===================== conv1b weights: all 9 taps once, resident for the CTA's life =====================
+    mbar_expect_tx(b_full, F1_W_BYTES);
+    for (int t = 0; t < 9; ++t) {
+      const uint32_t sb = base + t * F1_W_SLOT;
+      tma_load_3d(sb, &tm_w_hi, b_full, 0, 0, t);
+      tma_load_3d(sb + F1_W_SLOT / 2, &tm_w_lo, b_full, 0, 0, t);
+    }
+    // ===================== MMA issuer (same thread) =====================
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // N = 64
+    constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // N = 128: [main | cross]
+    int acc = 0; uint32_t acc_phase = 0;
+    uint32_t i = 0;
+    mbar_wait(b_full, 0);
+    const bool prof = P.dbg != nullptr && blockIdx.x == 0;
+    long long c_te = 0, c_af = 0, c_is = 0, t0 = 0, t1 = 0, t2 = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+      const int w = i & 1;
+      if (prof) t0 = clock64();
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      if (prof) t1 = clock64();
+      mbar_wait(a_full(w), (i >> 1) & 1);
+      if (prof) t2 = clock64();
+      tc_fence_after();
+      const uint32_t d_main = tmem_base + (uint32_t)(acc * 128), d_cross = d_main + 64;
+      const uint32_t row0 = w ? F1_WIN1 : 0;
+      uint32_t first = 1;
+      // tap order (kx outer, ky inner, K ascending) = the accumulation order of conv_umma_kernel: bit-identical sums
+      for (int kx = 0; kx < 3; ++kx) {
+        for (int ky = 0; ky < 3; ++ky) {
+          const uint32_t off = ((row0 + ky) * F1_HC + kx) * 128;
+          const uint64_t a_hi = umma_desc_sw128_sbo(a_hi_base + off, F1_PITCH);
+          const uint64_t a_lo = umma_desc_sw128_sbo(a_lo_base + off, F1_PITCH);
+          const uint32_t sb = base + (ky * 3 + kx) * F1_W_SLOT;
+          const uint64_t b_hi = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            // one MMA of width 128 over [W_hi | W_lo]: hi*hi -> main, hi*lo -> cross; then lo*hi -> cross
+            umma_f16(d_main, a_hi + adv, b_hi + adv, idesc2, (first && k == 0) ? 0u : 1u);
+            umma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+          }
+          first = 0;
+        }
+      }
+      umma_commit(mma_done(w));                    // the halo window may be overwritten
+      umma_commit(tfull_bar(acc));                 // accumulators complete -> epilogue
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (prof) { c_te += t1 - t0; c_af += t2 - t1; c_is += clock64() - t2; }
+    }
+    if (prof) { P.dbg[4] = c_te; P.dbg[5] = c_af; P.dbg[6] = c_is; P.dbg[9] = i; }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                        // TMEM lane quarter = tile rows 4q .. 4q+3 (lane = (row & 3) * 8 + col)
+    int acc = 0; uint32_t acc_phase = 0;
+    const int Hp = P.H >> 1, Wp = P.W >> 1;
+    const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
+    long long c_wait = 0, c_work = 0, t0 = 0, t1 = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (prof) t0 = clock64();
+      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+      // pooled pixel of (even row, even col): max over lanes l, l+1, l+8, l+9; writer lanes have row and col even
+      const int py = ty * (F1_TH / 2) + 2 * q + (lane >> 4), px = tx * (F1_TW / 2) + ((lane & 7) >> 1);
+      const bool writer = !(lane & 8) && !(lane & 1) && py < Hp && px < Wp;
+      const size_t ppix = ((size_t)b * Hp + py) * Wp + px;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      if (prof) t1 = clock64();
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
+#pragma unroll 1
+      for (int n0 = 0; n0 < 64; n0 += 16) {
+        uint32_t v[16], vc[16];
+        tmem_ld16(t_row + n0, v);
+        tmem_ld16(t_row + 64 + n0, vc);
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = fmaf(__uint_as_float(v[i]) + __uint_as_float(vc[i]), P.inv_scale, __ldg(P.bias + n0 + i));
+          f[i] = fmaxf(a, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          f[i] = fmaxf(f[i], __shfl_down_sync(0xffffffffu, f[i], 1));
+          f[i] = fmaxf(f[i], __shfl_down_sync(0xffffffffu, f[i], 8));
+        }
+        if (!writer) continue;
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float s0 = f[2 * i] * P.out_scale, s1 = f[2 * i + 1] * P.out_scale;
+          const __half2 hp = __floats2half2_rn(s0, s1);
+          const float2 hf = __half22float2(hp);
+          const __half2 lp = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+          hi[i] = *reinterpret_cast<const uint32_t*>(&hp);
+          lo[i] = *reinterpret_cast<const uint32_t*>(&lp);
+        }
+        st_global_256(P.out_hi + ppix * 64 + n0, hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7]);
+        st_global_256(P.out_lo + ppix * 64 + n0, lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (prof) { c_wait += t1 - t0; c_work += clock64() - t1; }
+    }
+    if (prof) { P.dbg[7] = c_wait; P.dbg[8] = c_work; }
+  } else if (warp < 4 || (warp >= 8 && warp < 12)) {
+    // ===================== conv1a producers (8 warps, two per scheduler) =====================
+    // lane = (pixel slot, 8 output channels): the 8 lanes of a pixel are adjacent, so a quarter-warp writes the eight
+    // 16-byte chunks of one 128-byte pixel row -- conflict-free 128-bit shared stores.  32 pixel slots per step: steps
+    // 0..4 take the 150 halo pixels private to this window, step 5 the 30 pixels of the three rows shared with the other
+    // window (computed before, stored after the previous tile's MMAs have retired).
+    const int pw = warp < 4 ? warp : warp - 4;     // 0 .. 7
+    const int slot = pw * 4 + (lane >> 3);         // 0 .. 31
+    const int cg = lane & 7;
+    const int ptid = pw * 32 + lane;               // 0 .. 255: byte of the input patch this thread stages
+    const int pr = ptid / F1_PC, pc = ptid - pr * F1_PC;
+    uint8_t* patch = smem_raw + F1_PATCH_OFF;
+    float wr[9][8], br[8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.w1a + t * 64 + cg * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.w1a + t * 64 + cg * 8 + 4));
+      wr[t][0] = w0.x; wr[t][1] = w0.y; wr[t][2] = w0.z; wr[t][3] = w0.w;
+      wr[t][4] = w1.x; wr[t][5] = w1.y; wr[t][6] = w1.z; wr[t][7] = w1.w;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) wr[t][jj] *= P.act_scale;      // power of two: exact
+    }
+    {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(P.b1a + cg * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(P.b1a + cg * 8 + 4));
+      br[0] = b0.x; br[1] = b0.y; br[2] = b0.z; br[3] = b0.w; br[4] = b1.x; br[5] = b1.y; br[6] = b1.z; br[7] = b1.w;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) br[jj] *= P.act_scale;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // the image is the previous kernel's output (no-op without PDL)
+    // input patch of a tile: rows y0-2 .. y0+17, columns x0-2 .. x0+9 of the u8 image, zero outside (conv1a's padding)
+    auto patch_byte = [&](int tile) -> uint32_t {
+      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+      const int gy = ty * F1_TH - 2 + pr, gx = tx * F1_TW - 2 + pc;
+      const bool in = ptid < F1_PR * F1_PC && gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
+      return in ? (uint32_t)__ldg(P.img + ((size_t)b * P.H + gy) * P.W + gx) : 0u;
+    };
+    int tile = blockIdx.x;
+    if (ptid < F1_PR * F1_PC) patch[ptid] = (uint8_t)(tile < n_tiles ? patch_byte(tile) : 0u);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    uint32_t i = 0;
+    const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
+    long long c_w1 = 0, c_cmp = 0, c_w2 = 0, t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    const long long t_begin = clock64();
+    for (; tile < n_tiles; tile += gridDim.x, ++i) {
+      const int w = i & 1;
+      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y;
+      const int next = tile + gridDim.x;
+      const uint32_t nb = next < n_tiles ? patch_byte(next) : 0u;      // next tile's patch byte: in flight for the whole tile
+      const uint32_t row0 = w ? F1_WIN1 : 0;
+      // conv1a of halo pixel (r, c) -> split fp16 chunks of this thread's 8 channels
+      auto compute = [&](int r, int c, uint32_t (&h)[4], uint32_t (&l)[4]) {
+        const uint8_t* pp = patch + r * F1_PC + c;
+        float in[3][3];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) in[dy][dx] = __fmul_rn(__uint2float_rn((uint32_t)pp[dy * F1_PC + dx]), P.alpha);
+        const int iy = ty * F1_TH - 1 + r, ix = tx * F1_TW - 1 + c;
+        const bool valid = iy >= 0 && iy < P.H && ix >= 0 && ix < P.W;          // outside the image: conv1b's zero padding
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          float a0 = br[2 * j2], a1 = br[2 * j2 + 1];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            a0 = fmaf(in[t / 3][t % 3], wr[t][2 * j2], a0);
+            a1 = fmaf(in[t / 3][t % 3], wr[t][2 * j2 + 1], a1);
+          }
+          const float s0 = fmaxf(a0, 0.f), s1 = fmaxf(a1, 0.f);
+          // one packed conversion per pair (cvt.rn.f16x2.f32: same roundings as two scalar conversions, off the slow pipe)
+          const __half2 hp = __floats2half2_rn(s0, s1);
+          const float2 hf = __half22float2(hp);
+          const __half2 lp = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+          h[j2] = valid ? *reinterpret_cast<const uint32_t*>(&hp) : 0u;
+          l[j2] = valid ? *reinterpret_cast<const uint32_t*>(&lp) : 0u;
+        }
+      };
+      auto store = [&](int r, int c, const uint32_t (&h)[4], const uint32_t (&l)[4]) {
+        const uint32_t off = ((row0 + r) * F1_HC + c) * 128;
+        const uint32_t ah = a_hi_base + off, al = a_lo_base + off;
+        st_shared_128(ah + (((uint32_t)cg ^ ((ah >> 7) & 7u)) << 4), h[0], h[1], h[2], h[3]);
+        st_shared_128(al + (((uint32_t)cg ^ ((al >> 7) & 7u)) << 4), l[0], l[1], l[2], l[3]);
+      };
+      // rows private to this window are free once the tile two back (same window) has retired
+      if (prof) t0 = clock64();
+      if (i >= 2) mbar_wait(mma_done(w), ((i >> 1) - 1) & 1);
+      if (prof) t1 = clock64();
+      // private rows: halo rows 0..14 of window 0, 3..17 of window 1
+#pragma unroll 1
+      for (int step = 0; step < 5; ++step) {
+        const int q = step * 32 + slot;
+        const int qc = min(q, 149);                            // idle slots of the last private step redo pixel 149, unstored
+        const int r = qc / F1_HC, c = qc - r * F1_HC;
+        uint32_t h[4], l[4];
+        compute(r + (w ? 3 : 0), c, h, l);
+        if (q < 150) store(r + (w ? 3 : 0), c, h, l);
+      }
+      {
+        // the three rows shared with the other window (15..17 of window 0 = 0..2 of window 1): computed now, stored only
+        // after the previous tile's MMAs have read them
+        const int qc = min(slot, 29);
+        const int r = qc / F1_HC + (w ? 0 : 15), c = qc % F1_HC;
+        uint32_t h[4], l[4];
+        compute(r, c, h, l);
+        if (prof) t2 = clock64();
+        if (i >= 1) mbar_wait(mma_done(w ^ 1), ((i - 1) >> 1) & 1);
+        if (prof) t3 = clock64();
+        if (slot < 30) store(r, c, h, l);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(w));
+      // hand the patch over to the next tile: everyone has read this one, then everyone sees the next
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ptid < F1_PR * F1_PC) patch[ptid] = (uint8_t)nb;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (prof) { c_w1 += t1 - t0; c_cmp += t2 - t1; c_w2 += t3 - t2; }
+    }
+    if (prof) { P.dbg[0] = c_w1; P.dbg[1] = c_cmp; P.dbg[2] = c_w2; P.dbg[3] = clock64() - t_begin; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// conv1a + ReLU + conv1b + ReLU + 2x2 max-pool: u8 images -> the split planes conv2a reads.  L1b = conv1b's weights
+// (n_pad 64, Cin 64, 3x3) as uploaded by umma_layer_upload; w1a [tap][64], b1a [64] fp32.
+osb_status umma_conv1_fused_forward(const UmmaLayer& L1b, const float* w1a, const float* b1a, const uint8_t* img, int B, int H,
+                                    int W, float act_scale, __half* out_hi, __half* out_lo, float out_scale, cudaStream_t st,
+                                    int max_ctas, unsigned long long* dbg) {
+  OSB_REQUIRE(L1b.n_pad == 64 && L1b.cin == 64 && L1b.ks == 3, "fused first layers expect the 64 -> 64 3x3 layer");
+  OSB_REQUIRE(H % 2 == 0 && W % 2 == 0, "fused max-pool needs even H and W");
+  Fused1Args P;
+  P.img = img; P.w1a = w1a; P.b1a = b1a; P.bias = L1b.bias; P.out_hi = out_hi; P.out_lo = out_lo;
+  P.H = H; P.W = W; P.B = B;
+  P.alpha = (float)(1.0 / 255.0);
+  P.dbg = dbg;
+  P.act_scale = act_scale; P.inv_scale = 1.0f / (act_scale * L1b.w_scale); P.out_scale = out_scale;
+  OSB_SMEM_OPT_IN(conv1_fused_kernel, F1_SMEM);
+  const int tiles = B * cdiv(W, F1_TW) * cdiv(H, F1_TH);
+  const int grid = std::min(tiles, max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(F1_THREADS); cfg.dynamicSmemBytes = F1_SMEM; cfg.stream = st;
+  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv1_fused_kernel, L1b.tm_hi, L1b.tm_lo, P));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return OSB_OK;
+}
+
+}  // namespace osb

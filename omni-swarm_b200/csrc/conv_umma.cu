@@ -24,68 +24,12 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "conv_umma.cuh"
+#include "umma_ptx.cuh"
 
 namespace osb {
 
 constexpr int UM_TH = 8, UM_TW = 16;            // output tile (pixels)
 constexpr int UM_KC = 64;                       // fp16 channels per K slab (= 128 bytes = one swizzle row)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  uint32_t spins = 0;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    // a pipeline bug must surface as a launch failure, never as a hung GPU (try_wait itself blocks for a while)
-    if (!done && ++spins > (1u << 24)) __trap();
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(16B units)=1 <<16 |
-// SBO = 1024 B (8 rows x 128 B) <<32 | version 1 <<46 | layout SWIZZLE_128B (2) <<61
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// 256-bit global store (STG.256, sm_100): the epilogue's stores have one lane per pixel, so every store instruction
-// touches 32 different lines whatever its width -- 32 bytes per lane halves the instruction (and LSU line) count
-__device__ __forceinline__ void st_global_256(void* p, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4,
-                                              uint32_t r5, uint32_t r6, uint32_t r7) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4),
-               "r"(r5), "r"(r6), "r"(r7) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-               : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // Shared-memory plan.  For a 3x3 layer ONE A box per (kx, 64-channel slab) carries 10 rows (tile + vertical halo):
 // the three vertical taps ky = 0,1,2 read it at row offsets ky*16 rows = ky*2048 bytes -- a multiple of the 1024-byte
@@ -604,11 +548,7 @@ template <int N, bool RES, bool SPLIT = false>
 static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const UmmaLayer& L, const UmmaArgs& P,
                               cudaStream_t st, int max_ctas, bool box128 = false) {
   using Cfg = UmmaCfg<N, RES>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    OSB_CUDA(cudaFuncSetAttribute((conv_umma_kernel<N, RES, SPLIT>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  OSB_SMEM_OPT_IN((conv_umma_kernel<N, RES, SPLIT>), Cfg::SMEM_BYTES);
   const int tiles = P.B * cdiv(P.W, UM_TW) * cdiv(P.H, UM_TH) * P.n_split;
   // persistent CTAs, one per SM; `max_ctas` leaves SMs free for a kernel running beside this one on another stream
   const int grid = std::min(tiles, max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms());

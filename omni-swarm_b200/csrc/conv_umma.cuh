@@ -31,6 +31,13 @@ osb_status umma_conv_softmax_forward(const UmmaLayer& L, const CUtensorMap& a_hi
                                      float act_scale, float* semi, cudaStream_t st, int max_ctas = 0);
 osb_status umma_first_forward(const float* w_tap_cout, const float* bias, const float* lut, const uint8_t* img,
                               __half* out_hi, __half* out_lo, int B, int H, int W, float out_scale, cudaStream_t st);
+// conv1a + ReLU + conv1b + ReLU + 2x2 max-pool in one kernel (conv1_fused.cu): u8 images -> pooled split planes
+osb_status umma_conv1_fused_forward(const UmmaLayer& L1b, const float* w1a, const float* b1a, const uint8_t* img, int B, int H,
+                                    int W, float act_scale, __half* out_hi, __half* out_lo, float out_scale, cudaStream_t st,
+                                    int max_ctas = 0, unsigned long long* dbg = nullptr);
+// dbg (optional, [16] device words): SM-clock cycles of CTA 0 summed over its tiles -- [0] producer wait (window free),
+// [1] producer compute + stores, [2] producer wait (shared rows), [3] producer loop total, [4] MMA issuer wait (TMEM free),
+// [5] wait (halo tile full), [6] issue, [7] epilogue wait, [8] epilogue work, [9] tiles of CTA 0
 // depthwise 3x3 + bias + ReLU6, fp32 NHWC in, split fp16 planes out (feeds a pointwise tcgen05 conv)
 osb_status umma_dwconv_forward(const float* w_tap_c, const float* bias, const float* x, __half* out_hi, __half* out_lo,
                                int B, int H, int W, int C, int stride, float out_scale, cudaStream_t st);

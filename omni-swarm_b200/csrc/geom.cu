@@ -170,22 +170,6 @@ homography_ransac_kernel(const float2* __restrict__ src, const float2* __restric
   if (tid == 0) { n_inl[pair] = (int)(best >> 16) - 1; winner[pair] = hw; }
 }
 
-// per-pair scratch of the kernel (key + ticket), zero between launches
-static unsigned int* hg_scratch(int n_pairs) {
-  static unsigned int* buf = nullptr;
-  static int cap = 0;
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lk(mu);
-  if (n_pairs > cap) {
-    unsigned int* nb = nullptr;
-    const int ncap = std::max(64, n_pairs);
-    if (cudaMalloc(&nb, 2 * (size_t)ncap * sizeof(unsigned int)) != cudaSuccess) return nullptr;
-    cudaMemset(nb, 0, 2 * (size_t)ncap * sizeof(unsigned int));
-    buf = nb; cap = ncap;                              // (an outgrown buffer is left to the context: launches may still use it)
-  }
-  return buf;
-}
-
 osb_status homography_ransac_device(const float* src_dev, const float* dst_dev, const int32_t* n_dev, int n_pairs, int max_n,
                                     float thresh, uint32_t seed, uint8_t* mask_dev, int32_t* n_inl_dev, int32_t* winner_dev,
                                     cudaStream_t st, unsigned int* scratch) {
@@ -209,9 +193,16 @@ extern "C" osb_status osb_homography_ransac_dev(const float* src_dev, const floa
   OSB_REQUIRE(src_dev && dst_dev && n_dev && mask_dev && n_inliers_dev && winner_dev, "null argument");
   osb_status s = require_device();
   if (s != OSB_OK) return s;
-  // (shared process-wide scratch: concurrent callers on different streams must serialise, as documented in the header)
-  return homography_ransac_device(src_dev, dst_dev, n_dev, n_pairs, max_n, thresh, seed, mask_dev, n_inliers_dev, winner_dev,
-                                  (cudaStream_t)stream, hg_scratch(n_pairs));
+  // per-call scratch (key + ticket per pair) from the stream-ordered allocator: no process-wide state, no synchronisation,
+  // safe for concurrent callers on different streams (the reference's nodelet is multi-threaded)
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* scratch = nullptr;
+  OSB_CUDA(cudaMallocAsync(&scratch, 2 * (size_t)n_pairs * sizeof(unsigned int), st));
+  OSB_CUDA(cudaMemsetAsync(scratch, 0, 2 * (size_t)n_pairs * sizeof(unsigned int), st));
+  s = homography_ransac_device(src_dev, dst_dev, n_dev, n_pairs, max_n, thresh, seed, mask_dev, n_inliers_dev, winner_dev, st,
+                               scratch);
+  cudaFreeAsync(scratch, st);
+  return s;
 }
 
 // host buffers in / out (allocates its scratch per call: a convenience for tests and small callers)
@@ -223,6 +214,7 @@ extern "C" osb_status osb_homography_ransac(const float* src, const float* dst, 
   if (s != OSB_OK) return s;
   const size_t pts = (size_t)n_pairs * max_n;
   float *d_src = nullptr, *d_dst = nullptr;
+  unsigned int* d_scratch = nullptr;
   int32_t *d_n = nullptr, *d_inl = nullptr, *d_win = nullptr;
   uint8_t* d_mask = nullptr;
   OSB_CUDA(cudaMalloc(&d_src, pts * 2 * sizeof(float)));
@@ -231,15 +223,17 @@ extern "C" osb_status osb_homography_ransac(const float* src, const float* dst, 
   OSB_CUDA(cudaMalloc(&d_inl, n_pairs * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&d_win, n_pairs * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&d_mask, pts));
+  OSB_CUDA(cudaMalloc(&d_scratch, 2 * (size_t)n_pairs * sizeof(unsigned int)));
+  OSB_CUDA(cudaMemset(d_scratch, 0, 2 * (size_t)n_pairs * sizeof(unsigned int)));
   OSB_CUDA(cudaMemcpy(d_src, src, pts * 2 * sizeof(float), cudaMemcpyHostToDevice));
   OSB_CUDA(cudaMemcpy(d_dst, dst, pts * 2 * sizeof(float), cudaMemcpyHostToDevice));
   OSB_CUDA(cudaMemcpy(d_n, n, n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice));
-  s = homography_ransac_device(d_src, d_dst, d_n, n_pairs, max_n, thresh, seed, d_mask, d_inl, d_win, nullptr, hg_scratch(n_pairs));
+  s = homography_ransac_device(d_src, d_dst, d_n, n_pairs, max_n, thresh, seed, d_mask, d_inl, d_win, nullptr, d_scratch);
   if (s == OSB_OK) {
     OSB_CUDA(cudaMemcpy(mask, d_mask, pts, cudaMemcpyDeviceToHost));
     OSB_CUDA(cudaMemcpy(n_inliers, d_inl, n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (winner) OSB_CUDA(cudaMemcpy(winner, d_win, n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost));
   }
-  cudaFree(d_src); cudaFree(d_dst); cudaFree(d_n); cudaFree(d_inl); cudaFree(d_win); cudaFree(d_mask);
+  cudaFree(d_src); cudaFree(d_dst); cudaFree(d_n); cudaFree(d_inl); cudaFree(d_win); cudaFree(d_mask); cudaFree(d_scratch);
   return s;
 }

@@ -33,7 +33,8 @@ struct DbStore {
   int32_t* row_frame = nullptr;// [cap]
   int32_t* row_dir = nullptr;  // [cap]
   int32_t* frame_rows = nullptr;  // [cap][4]
-  int32_t* frame_msg = nullptr;   // [cap]
+  int32_t* frame_msg = nullptr;   // [cap]   msg_id of the keyframe (imgid2fisheye -> fisheyeframe_database key)
+  int32_t* frame_drone = nullptr; // [cap]   drone_id of the keyframe
   float* part_scores = nullptr;
   int64_t* part_ids = nullptr;
   unsigned int* done = nullptr;
@@ -89,6 +90,7 @@ __global__ void fe_assign_kernel(const osb_keyframe_record* __restrict__ recs, i
                                  int32_t* __restrict__ l_frame_rows, int32_t* __restrict__ l_frame_msg,
                                  int32_t* __restrict__ r_row_frame, int32_t* __restrict__ r_row_dir,
                                  int32_t* __restrict__ r_frame_rows, int32_t* __restrict__ r_frame_msg,
+                                 int32_t* __restrict__ l_frame_drone, int32_t* __restrict__ r_frame_drone,
                                  int32_t* __restrict__ assign /*[n_records][4]: row | (remote<<30), or -1*/) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   for (int r = 0; r < n_records; ++r) {
@@ -101,9 +103,11 @@ __global__ void fe_assign_kernel(const osb_keyframe_record* __restrict__ recs, i
     int32_t* row_dir = is_remote ? r_row_dir : l_row_dir;
     int32_t* frame_rows = is_remote ? r_frame_rows : l_frame_rows;
     int32_t* frame_msg = is_remote ? r_frame_msg : l_frame_msg;
+    int32_t* frame_drone = is_remote ? r_frame_drone : l_frame_drone;
     if (db->nframes >= cap) { db->overflow = 1; continue; }
     const int fs = db->nframes++;
     frame_msg[fs] = rec->msg_id;
+    frame_drone[fs] = rec->drone_id;
     for (int d = 0; d < OSB_MAX_DIRS; ++d) {
       frame_rows[fs * OSB_MAX_DIRS + d] = -1;
       if (d >= rec->n_dirs || rec->n_kpts[d] <= 0) continue;         // landmark_num > 0 (loop_detector.cpp:153)
@@ -186,7 +190,9 @@ __global__ void fe_query_rule_kernel(QueryParams qp, const osb_keyframe_record* 
                                      const float* __restrict__ l_kpts, const int32_t* __restrict__ l_sm,
                                      const float* __restrict__ r_kpts, const int32_t* __restrict__ r_sm,
                                      const float** __restrict__ g_qk, const float** __restrict__ g_tk,
-                                     const int32_t** __restrict__ g_qflag) {
+                                     const int32_t** __restrict__ g_qflag,
+                                     const int32_t* __restrict__ l_frame_msg, const int32_t* __restrict__ l_frame_drone,
+                                     const int32_t* __restrict__ r_frame_msg, const int32_t* __restrict__ r_frame_drone) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const bool own = rec->drone_id == qp.self_id;
   const double thres = qp.init_mode ? qp.init_mode_product_thres : qp.inner_product_thres;
@@ -211,6 +217,8 @@ __global__ void fe_query_rule_kernel(QueryParams qp, const osb_keyframe_record* 
   res->accepted = accepted ? 1 : 0;
   res->hit_dir = -1;
   res->swapped = 0;
+  res->hit_msg_id = -1;
+  res->hit_drone_id = -1;
   for (int j = 0; j < OSB_MAX_DIRS; ++j) {
     nq[j] = 0; nt[j] = 0; qptr[j] = nullptr; tptr[j] = nullptr;
     g_qk[j] = nullptr; g_tk[j] = nullptr; g_qflag[j] = nullptr;
@@ -227,6 +235,10 @@ __global__ void fe_query_rule_kernel(QueryParams qp, const osb_keyframe_record* 
   const int fs = row_frame[row];
   const int direction_old = row_dir[row];                   // imgid2dir (:275)
   res->hit_dir = direction_old;
+  // imgid2fisheye[best_image_id] -> the keyframe's msg_id, fisheyeframe_database[msg_id].drone_id (loop_detector.cpp:272-275):
+  // what the host adapter needs to find the old FisheyeFrameDescriptor_t for compute_loop
+  res->hit_msg_id = (hit_remote ? r_frame_msg : l_frame_msg)[fs];
+  res->hit_drone_id = (hit_remote ? r_frame_drone : l_frame_drone)[fs];
   // compute_loop(new, old) -- or (old, new) when the hit comes from the remote database and the keyframe is ours
   // (loop_detector.cpp:113-118): the first argument plays "new_frame_desc" (the matcher's query side).
   const bool swapped = hit_remote && own;
@@ -351,6 +363,8 @@ struct osb_frontend {
   cudaStream_t stream2 = nullptr;                 // NetVLAD runs here, overlapped with the keypoint kernels
   cudaStream_t stream_sp = nullptr;               // SuperPoint runs here at the highest stream priority (null: caller's stream)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sp = nullptr;
+  cudaEvent_t ev_ingest = nullptr;                // recorded after the last ingest on ITS stream
+  bool ingest_pending = false;
   bool profiling = false;
   cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid[9] = {false, false, false, false, false, false, false, false, false};
@@ -378,6 +392,7 @@ static osb_status dbstore_alloc(DbStore& s, int64_t cap, int max_num) {
   OSB_CUDA(cudaMalloc(&s.row_dir, cap * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&s.frame_rows, cap * OSB_MAX_DIRS * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&s.frame_msg, cap * sizeof(int32_t)));
+  OSB_CUDA(cudaMalloc(&s.frame_drone, cap * sizeof(int32_t)));
   int64_t chunk;
   const int gmax = db_scan_grid(cap, &chunk);
   OSB_CUDA(cudaMalloc(&s.part_scores, (size_t)8 * gmax * FE_KMAX * sizeof(float)));
@@ -391,7 +406,7 @@ static osb_status dbstore_alloc(DbStore& s, int64_t cap, int max_num) {
 
 static void dbstore_free(DbStore& s) {
   cudaFree(s.dev); cudaFree(s.rows); cudaFree(s.ldesc); cudaFree(s.kpts); cudaFree(s.smatch); cudaFree(s.nk); cudaFree(s.row_frame); cudaFree(s.row_dir);
-  cudaFree(s.frame_rows); cudaFree(s.frame_msg); cudaFree(s.part_scores); cudaFree(s.part_ids); cudaFree(s.done);
+  cudaFree(s.frame_rows); cudaFree(s.frame_msg); cudaFree(s.frame_drone); cudaFree(s.part_scores); cudaFree(s.part_ids); cudaFree(s.done);
   cudaFree(s.top_scores); cudaFree(s.top_ids);
 }
 
@@ -427,6 +442,7 @@ extern "C" osb_status osb_frontend_create(osb_frontend** out, const osb_frontend
   FE_CUDA(cudaEventCreateWithFlags(&h->ev_sp, cudaEventDisableTiming));
   FE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   FE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  FE_CUDA(cudaEventCreateWithFlags(&h->ev_ingest, cudaEventDisableTiming));
   FE_TRY(h->sp.init(sp_weights, n_sp_weights, cfg->width, cfg->height, cfg->sp_thres, mn, pca_comp, pca_mean, 2 * nd));
   h->sp.ks.write_surv = false;       // the survivor plane is only a parity hook of the standalone SuperPoint handle
   FE_TRY(h->nv.init(nv_weights, n_nv_weights, cfg->width, cfg->height, nd));
@@ -491,6 +507,7 @@ extern "C" osb_status osb_frontend_destroy(osb_frontend* h) {
   for (int i = 0; i < 9; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_ingest) cudaEventDestroy(h->ev_ingest);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream_sp) cudaStreamDestroy(h->stream_sp);
   if (h->ev_sp) cudaEventDestroy(h->ev_sp);
@@ -569,18 +586,26 @@ extern "C" osb_status osb_frontend_extract(osb_frontend* h, const uint8_t* image
   return fe_extract_dev(h, h->d_img, msg_id, record_dev, st);
 }
 
+static osb_status fe_refresh_counts(osb_frontend* h, cudaStream_t st);
+
 static osb_status fe_ingest(osb_frontend* h, const osb_keyframe_record* recs, int n_records, int skip, cudaStream_t st) {
   OSB_REQUIRE(n_records >= 0 && n_records <= h->max_records, "too many records in one ingest (max 64)");
   if (n_records == 0) return OSB_OK;
   DbStore &L = h->db[0], &R = h->db[1];
   if (L.upper + (int64_t)n_records * OSB_MAX_DIRS > L.cap || R.upper + (int64_t)n_records * OSB_MAX_DIRS > R.cap) {
-    // the upper bounds are conservative: refresh them from the device before giving up
-    DbDev hl, hr;
-    OSB_CUDA(cudaMemcpyAsync(&hl, L.dev, sizeof(DbDev), cudaMemcpyDeviceToHost, st));
-    OSB_CUDA(cudaMemcpyAsync(&hr, R.dev, sizeof(DbDev), cudaMemcpyDeviceToHost, st));
+    // the upper bounds are conservative (every record charged to both databases): make them exact, and count which
+    // database each record of this batch really goes to, before giving up
+    osb_status rs = fe_refresh_counts(h, st);
+    if (rs != OSB_OK) return rs;
+    std::vector<int32_t> hdr((size_t)n_records * 4);
+    OSB_CUDA(cudaMemcpy2DAsync(hdr.data(), 16, recs, sizeof(osb_keyframe_record), 16, n_records, cudaMemcpyDeviceToHost, st));
     OSB_CUDA(cudaStreamSynchronize(st));
-    L.upper = hl.ntotal; R.upper = hr.ntotal;
-    if (L.upper + (int64_t)n_records * OSB_MAX_DIRS > L.cap || R.upper + (int64_t)n_records * OSB_MAX_DIRS > R.cap) {
+    int64_t n_loc = 0, n_rem = 0;
+    for (int r = 0; r < n_records; ++r) {
+      if (r == skip) continue;
+      (hdr[(size_t)r * 4] == h->cfg.self_id ? n_loc : n_rem) += OSB_MAX_DIRS;
+    }
+    if (L.upper + n_loc > L.cap || R.upper + n_rem > R.cap) {
       set_error("osb_frontend_ingest", "database capacity exceeded");
       return OSB_ERR_CAPACITY;
     }
@@ -588,13 +613,15 @@ static osb_status fe_ingest(osb_frontend* h, const osb_keyframe_record* recs, in
   fe_mark(h, 4, st);
   OSB_LAUNCH(fe_assign_kernel, 1, 32, 0, st, recs, n_records, skip, h->cfg.self_id, L.dev, R.dev, (long long)L.cap,
              L.row_frame, L.row_dir, L.frame_rows, L.frame_msg, R.row_frame, R.row_dir, R.frame_rows, R.frame_msg,
-             h->d_assign);
+             L.frame_drone, R.frame_drone, h->d_assign);
   OSB_CHECK_LAUNCH();
   OSB_LAUNCH(fe_copy_rows_kernel, n_records * OSB_MAX_DIRS, 256, 0, st, recs, h->d_assign, h->cfg.max_num, L.rows,
              L.ldesc, L.nk, R.rows, R.ldesc, R.nk, L.kpts, L.smatch, R.kpts, R.smatch);
   OSB_CHECK_LAUNCH();
   L.upper += (int64_t)n_records * OSB_MAX_DIRS;
   R.upper += (int64_t)n_records * OSB_MAX_DIRS;
+  OSB_CUDA(cudaEventRecord(h->ev_ingest, st));
+  h->ingest_pending = true;
   fe_mark(h, 5, st);
   return OSB_OK;
 }
@@ -627,7 +654,7 @@ static osb_status fe_query(osb_frontend* h, const osb_keyframe_record* rec, int 
   OSB_LAUNCH(fe_query_rule_kernel, 1, 32, 0, st, qp, rec, L.dev, R.dev, L.top_scores, L.top_ids, R.top_scores, R.top_ids,
              L.row_frame, L.row_dir, L.frame_rows, L.nk, L.ldesc, R.row_frame, R.row_dir, R.frame_rows, R.nk, R.ldesc,
              res, h->d_q_q, h->d_q_t, h->d_q_nq, h->d_q_nt, L.kpts, L.smatch, R.kpts, R.smatch, h->d_g_qk, h->d_g_tk,
-             h->d_g_qflag);
+             h->d_g_qflag, L.frame_msg, L.frame_drone, R.frame_msg, R.frame_drone);
   OSB_CHECK_LAUNCH();
   // per-direction cross-check match new vs old (loop_detector.cpp:564-567); empty pairs produce n = 0
   s = bf_match_device(OSB_MAX_DIRS, c.max_num, OSB_MAX_KPTS, h->d_q_q, h->d_q_nq, h->d_q_t, h->d_q_nt,
@@ -655,12 +682,17 @@ extern "C" osb_status osb_frontend_query(osb_frontend* h, const osb_keyframe_rec
   return fe_query(h, record_dev, init_mode, nonkeyframe, result_dev, (cudaStream_t)stream);
 }
 
+// exact host-side row counts.  The counts are read on `st`, which need not be the stream that carried the last ingest
+// (streams are non-blocking): wait for that ingest first, or the bound could be lowered below the true count while the
+// rows are still being appended -- the scan grid is sized from it.
 static osb_status fe_refresh_counts(osb_frontend* h, cudaStream_t st) {
+  if (h->ingest_pending) OSB_CUDA(cudaStreamWaitEvent(st, h->ev_ingest, 0));
   DbDev hl, hr;
   OSB_CUDA(cudaMemcpyAsync(&hl, h->db[0].dev, sizeof(DbDev), cudaMemcpyDeviceToHost, st));
   OSB_CUDA(cudaMemcpyAsync(&hr, h->db[1].dev, sizeof(DbDev), cudaMemcpyDeviceToHost, st));
   OSB_CUDA(cudaStreamSynchronize(st));
   h->db[0].upper = hl.ntotal; h->db[1].upper = hr.ntotal;
+  h->ingest_pending = false;
   return OSB_OK;
 }
 
@@ -758,6 +790,8 @@ extern "C" osb_status osb_frontend_db_load(osb_frontend* h, int remote, int64_t 
   const int mn = h->cfg.max_num, qd = h->cfg.query_dir;
   DbDev hd;
   OSB_CUDA(cudaMemcpy(&hd, S.dev, sizeof(DbDev), cudaMemcpyDeviceToHost));
+  // the frame tables are [cap] too, and a keyframe without keypoints adds a frame but no row (nframes may exceed ntotal)
+  if ((int64_t)hd.nframes + n > S.cap) { set_error("osb_frontend_db_load", "frame table capacity exceeded"); return OSB_ERR_CAPACITY; }
   OSB_CUDA(cudaMemcpyAsync(S.rows + (size_t)base * OSB_DEEP_DESC_SIZE, global_desc,
                            (size_t)n * OSB_DEEP_DESC_SIZE * sizeof(float), cudaMemcpyHostToDevice, st));
   std::vector<int32_t> nk(n), rf(n), rd(n), fr((size_t)n * OSB_MAX_DIRS, -1), fm(n, -1);
@@ -778,6 +812,8 @@ extern "C" osb_status osb_frontend_db_load(osb_frontend* h, int remote, int64_t 
   OSB_CUDA(cudaMemcpyAsync(S.frame_rows + (size_t)hd.nframes * OSB_MAX_DIRS, fr.data(), fr.size() * sizeof(int32_t),
                            cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(S.frame_msg + hd.nframes, fm.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  std::vector<int32_t> fd(n, remote ? -1 : h->cfg.self_id);
+  OSB_CUDA(cudaMemcpyAsync(S.frame_drone + hd.nframes, fd.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   hd.ntotal += n; hd.nframes += (int)n;
   OSB_CUDA(cudaMemcpyAsync(S.dev, &hd, sizeof(DbDev), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaStreamSynchronize(st));

@@ -138,7 +138,9 @@ db_scan_coop_kernel(const float* __restrict__ db, int64_t n_val, const int64_t* 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row0 = (int64_t)blockIdx.x * chunk;
   const int64_t row1 = min(n, row0 + chunk);
-  const int nrows = (int)max((int64_t)0, row1 - row0);
+  // the grid was sized from a HOST upper bound of n; should the device count ever exceed it, rows beyond the chunk are
+  // dropped rather than written past the shared arrays (the front-end keeps the bound exact, see fe_refresh_counts)
+  const int nrows = (int)min((int64_t)CH, max((int64_t)0, row1 - row0));
   const int col = warp * (C * 32) + lane;
   float4 wq[Q][C];
 #pragma unroll
@@ -219,7 +221,7 @@ db_scan_kernel(const float* __restrict__ db, int64_t n_val, const int64_t* __res
   __syncthreads();
   const int64_t row0 = (int64_t)blockIdx.x * chunk;
   const int64_t row1 = min(n, row0 + chunk);
-  const int nrows = (int)max((int64_t)0, row1 - row0);
+  const int nrows = (int)min((int64_t)DB_CHUNK_MAX, max((int64_t)0, row1 - row0));   // (same guard as the cooperative kernel)
   const int ngroups = (nrows + R - 1) / R;
   for (int g = warp; g < ngroups; g += nwarps) {
     const int64_t r0 = row0 + (int64_t)g * R;
@@ -227,7 +229,7 @@ db_scan_kernel(const float* __restrict__ db, int64_t n_val, const int64_t* __res
     bool valid[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      valid[r] = (r0 + r) < row1;
+      valid[r] = (r0 + r) < row0 + nrows;
       rp[r] = reinterpret_cast<const float4*>(db + (valid[r] ? (r0 + r) : r0) * (int64_t)dim);
     }
     float acc[R][Q];
@@ -300,21 +302,13 @@ static osb_status launch_scan(const float* db, int64_t n, const int64_t* n_dev, 
   const size_t merge_bytes = fuse ? (size_t)(DB_MERGE_MAX + DB_FUSE_KMAX * DB_FUSE_KMAX) * sizeof(unsigned long long) : 0;
   if (coop) {
     const size_t smem = std::max(merge_bytes, (size_t)(DB_THREADS / 32 + 1) * DB_COOP_CHUNK * Q * sizeof(float));
-    static bool attr_done = false;
-    if (!attr_done) {
-      OSB_CUDA(cudaFuncSetAttribute(db_scan_coop_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr_done = true;
-    }
+    OSB_SMEM_OPT_IN(db_scan_coop_kernel<Q>, 64 * 1024);
     OSB_LAUNCH((db_scan_coop_kernel<Q>), grid, DB_THREADS, smem, st, db, n, n_dev, q, nq, k, ps, pi, os, oi, done, fuse);
     OSB_CHECK_LAUNCH();
     return OSB_OK;
   }
   const size_t smem = std::max(merge_bytes, ((size_t)Q * dim + (size_t)Q * DB_CHUNK_MAX) * sizeof(float));
-  static bool attr_done = false;
-  if (!attr_done) {
-    OSB_CUDA(cudaFuncSetAttribute(db_scan_kernel<Q, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
+  OSB_SMEM_OPT_IN((db_scan_kernel<Q, R>), 200 * 1024);
   OSB_LAUNCH((db_scan_kernel<Q, R>), grid, DB_THREADS, smem, st, db, n, n_dev, dim, q, nq, k, ps, pi, os, oi, done, fuse);
   OSB_CHECK_LAUNCH();
   return OSB_OK;

@@ -385,12 +385,8 @@ sp_keypoints_kernel(const float* __restrict__ semi, int H, int W, float thres, i
 osb_status sp_keypoints(const float* semi, int B, int H, int W, float thres, int max_num, KeypointScratch& ks,
                         int32_t* n_kpts, float* kpts, float* conf, cudaStream_t st) {
   OSB_REQUIRE((H * W) % 8 == 0, "H*W must be a multiple of 8");
-  static bool attr_done = false;
   const size_t smem = (size_t)KP_SORT_CAP * sizeof(unsigned long long);
-  if (!attr_done) {
-    OSB_CUDA(cudaFuncSetAttribute(sp_keypoints_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  OSB_SMEM_OPT_IN(sp_keypoints_kernel, smem);
   OSB_LAUNCH(sp_keypoints_kernel, B, KP_THREADS, smem, st, semi, H, W, thres, max_num, ks.state, ks.surv, ks.cand,
              ks.skey, ks.cmask, ks.write_surv ? 1 : 0, ks.counts, n_kpts, kpts, conf);
   OSB_CHECK_LAUNCH();

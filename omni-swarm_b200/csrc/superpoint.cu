@@ -39,6 +39,7 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
   OSB_CUDA(cudaEventCreateWithFlags(&ev_kp, cudaEventDisableTiming));
   if (const char* e = getenv("OSB_SP_OVERLAP")) overlap_kp = atoi(e) != 0;
   if (const char* e = getenv("OSB_SP_FUSED_SOFTMAX")) fused_softmax = atoi(e) != 0;
+  if (const char* e = getenv("OSB_SP_FUSE1")) fuse_first = atoi(e) != 0;
   // ---- weights ----
   const float* p = weights;
   {
@@ -107,6 +108,8 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
       if (s != OSB_OK) return s;
     }
   }
+  OSB_CUDA(cudaMalloc(&d_f1dbg, 16 * sizeof(unsigned long long)));
+  OSB_CUDA(cudaMemset(d_f1dbg, 0, 16 * sizeof(unsigned long long)));
   OSB_CUDA(cudaMalloc(&d_semi, B * HW * sizeof(float)));
   OSB_CUDA(cudaMalloc(&d_desc, B * Hc * Wc * 256 * sizeof(float)));
   OSB_CUDA(cudaMalloc(&ks.state, B * HW));
@@ -131,7 +134,7 @@ void SuperPoint::release() {
   for (int i = 0; i < 20; ++i) if (lev[i]) cudaEventDestroy(lev[i]);
   cudaFree(d_img); cudaFree(actA); cudaFree(actB); cudaFree(d_logits); cudaFree(d_semi); cudaFree(d_desc);
   cudaFree(ks.state); cudaFree(ks.surv); cudaFree(ks.cand); cudaFree(ks.skey); cudaFree(ks.cmask); cudaFree(ks.counts); cudaFree(ks.cnorm);
-  cudaFree(d_nk); cudaFree(d_kpts); cudaFree(d_conf); cudaFree(d_out);
+  cudaFree(d_nk); cudaFree(d_kpts); cudaFree(d_conf); cudaFree(d_out); cudaFree(d_f1dbg);
   if (stream) cudaStreamDestroy(stream);
   if (kp_stream) cudaStreamDestroy(kp_stream);
   if (ev_semi) cudaEventDestroy(ev_semi);
@@ -152,10 +155,17 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
     return umma_conv_forward(UL[i], tmA[i], tmB[i], B, h, w, SA, in_hi[out_layer], in_lo[out_layer], nullptr,
                              SP_COUT[i], SP_COUT[i], SA, 1, pool, st);
   };
-  RUN(umma_first_forward(w1a, b1a, lut, img_dev, in_hi[1], in_lo[1], B, H, W, SA, st));   // conv1a            -> A
-  mark(st);
-  RUN(conv(1, H, W, 2, 1));                                                               // conv1b + pool     -> B
-  mark(st);
+  if (fuse_first) {
+    mark(st);                                                                             // (conv1a has no launch of its own)
+    RUN(umma_conv1_fused_forward(UL[1], w1a, b1a, img_dev, B, H, W, SA, in_hi[2], in_lo[2], SA, st, 0,
+                                 layer_prof ? d_f1dbg : nullptr));   // conv1a+conv1b+pool -> B
+    mark(st);
+  } else {
+    RUN(umma_first_forward(w1a, b1a, lut, img_dev, in_hi[1], in_lo[1], B, H, W, SA, st)); // conv1a            -> A
+    mark(st);
+    RUN(conv(1, H, W, 2, 1));                                                             // conv1b + pool     -> B
+    mark(st);
+  }
   RUN(conv(2, H / 2, W / 2, 3, 0));                                                       // conv2a            -> A
   mark(st);
   RUN(conv(3, H / 2, W / 2, 4, 1));                                                       // conv2b + pool     -> B
@@ -385,6 +395,13 @@ extern "C" osb_status osb_superpoint_read(osb_superpoint* h, int what, int image
     OSB_CUDA(cudaMemcpyAsync(c, sp.ks.counts + image * 8, sizeof(c), cudaMemcpyDeviceToHost, st));
     OSB_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < 8; ++i) out[i] = (float)c[i];
+    return OSB_OK;
+  } else if (what == 5) {
+    OSB_REQUIRE(n_floats == 16, "fused-kernel counters need 16 floats");
+    unsigned long long c[16];
+    OSB_CUDA(cudaMemcpyAsync(c, sp.d_f1dbg, sizeof(c), cudaMemcpyDeviceToHost, st));
+    OSB_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 16; ++i) out[i] = (float)c[i];
     return OSB_OK;
   } else {
     set_error("osb_superpoint_read", "unknown `what`");

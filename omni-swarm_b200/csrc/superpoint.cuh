@@ -43,6 +43,8 @@ struct SuperPoint {
   cudaStream_t kp_stream = nullptr;
   cudaEvent_t ev_semi = nullptr, ev_kp = nullptr;
   bool overlap_kp = true;
+  unsigned long long* d_f1dbg = nullptr;   // cycle counters of the fused first-layers kernel (filled while layer_prof is on)
+  bool fuse_first = true;          // conv1a computed inside conv1b's kernel (conv1_fused.cu; OSB_SP_FUSE1=0: two kernels)
   bool fused_softmax = true;       // detector-head softmax + pixel shuffle in convPb's epilogue (OSB_SP_FUSED_SOFTMAX=0: two kernels)
   osb_status network(const uint8_t* img_dev, int B, cudaStream_t st, const KpJob* kp = nullptr);
   osb_status network_umma(const uint8_t* img_dev, int B, cudaStream_t st, const KpJob* kp);

@@ -49,7 +49,7 @@ class KeyframeRecord(C.Structure):
 
 class LoopResult(C.Structure):
     _fields_ = [("hit_id", C.c_int32), ("hit_dir", C.c_int32), ("hit_score", C.c_float), ("accepted", C.c_int32),
-                ("swapped", C.c_int32), ("dir_new", C.c_int32 * MAX_DIRS), ("dir_old", C.c_int32 * MAX_DIRS),
+                ("swapped", C.c_int32), ("hit_msg_id", C.c_int32), ("hit_drone_id", C.c_int32), ("dir_new", C.c_int32 * MAX_DIRS), ("dir_old", C.c_int32 * MAX_DIRS),
                 ("n_matches", C.c_int32 * MAX_DIRS), ("match_new", (C.c_int32 * MAX_KPTS) * MAX_DIRS),
                 ("match_old", (C.c_int32 * MAX_KPTS) * MAX_DIRS),
                 ("geo_valid", C.c_int32 * MAX_DIRS), ("n_geo", C.c_int32 * MAX_DIRS),

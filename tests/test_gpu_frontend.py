@@ -217,3 +217,126 @@ def test_geometric_filter_on_loaded_rows(gpu):
     assert res.geo_valid[0] == 1 and gcount == len(qn) == 150 - 30 - 20
     assert list(res.geo_new[0][:gcount]) == qn.tolist() and list(res.geo_old[0][:gcount]) == qo.tolist()
     fe.close()
+
+
+def test_c3_keyframe_record_vs_oracle(gpu):
+    """BASELINE config C3 at full size: one 4-view fisheye keyframe = 8 x 640x480 images through osb_frontend_process,
+    the whole record against the oracle composed as LoopCam::generate_stereo_image_descriptor (loop_cam.cpp:341-523):
+    keypoints bit-exact on the device heat-map of every image, local descriptors and NetVLAD <= 1e-4 relative, heat-map /
+    descriptor map <= 1e-4 relative to the fp32 network, stereo pairs exact given the device descriptors."""
+    W, H, MN = 640, 480, 200
+    comp, mean = synth.pca_matrices(0)
+    w, nvw = synth.superpoint_weights(0), synth.netvlad_weights(0)
+    spw = synth.flatten_sp_weights(w)
+    fe = host.KeyframeFrontend(spw, comp, mean, synth.flatten_nv_weights(nvw), width=W, height=H, n_dirs=4, max_num=MN,
+                               sp_thres=0.015, self_id=3, db_capacity=64, match_index_dist=5, zero_bottom_quarter=True,
+                               accept_min_3d_pts=10)
+    up = np.stack([synth.image(100 + d, H, W) for d in range(4)])
+    down = np.stack([synth.image(200 + d, H, W) for d in range(4)])
+    rec, res = fe.process(up, down, msg_id=4242)
+    assert (rec.drone_id, rec.msg_id, rec.n_dirs) == (3, 4242, 4)
+    imgs = np.concatenate([up, down]).copy()
+    imgs[:, H * 3 // 4:, :] = 0                                   # loop_cam.cpp:535-538
+    sp = host.SuperPoint(spw, comp, mean, W, H, 0.015, MN, max_batch=8)
+    alone = sp.inference_batch(imgs)
+    n_same = n_ref = 0
+    for b in range(8):
+        semi, desc = sp.read("semi", b), sp.read("desc", b)
+        k, dsc = alone[b]
+        semi_o, desc_o = fr.superpoint_net(imgs[b], w)
+        assert np.linalg.norm(semi - semi_o) <= 1e-4 * np.linalg.norm(semi_o) and np.abs(semi - semi_o).max() < 1e-4
+        assert np.linalg.norm(desc - desc_o) <= 1e-4 * np.linalg.norm(desc_o)
+        rk, _ = fr.get_keypoints(semi, 0.015, MN)                 # oracle NMS2 on the DEVICE heat-map: bit-exact
+        assert np.array_equal(k, rk), f"image {b}: keypoints differ from the oracle NMS on the device heat-map"
+        rd = fr.compute_descriptors(desc, rk, W, H, comp, mean)
+        assert np.linalg.norm(dsc - rd) <= 1e-4 * np.linalg.norm(rd)
+        ok, _ = fr.get_keypoints(semi_o, 0.015, MN)               # end to end: margin cases only
+        n_same += len({tuple(x) for x in k.tolist()} & {tuple(x) for x in ok.tolist()}); n_ref += len(ok)
+    assert n_same >= 0.97 * n_ref, f"only {n_same}/{n_ref} keypoints agree end to end"
+    for d in range(4):
+        ku, du = alone[d]; kd, dd = alone[4 + d]
+        n = rec.n_kpts[d]
+        # the front-end's batch of 8 and the stand-alone handle run the same kernels: records are bit-identical
+        assert n == len(ku) and rec.n_kpts_down[d] == len(kd)
+        assert np.array_equal(np.ctypeslib.as_array(rec.kpts[d])[:n], ku)
+        assert np.array_equal(np.ctypeslib.as_array(rec.local_desc[d])[:n], du)
+        g = np.ctypeslib.as_array(rec.global_desc[d])
+        go = fr.netvlad_net(imgs[d], nvw)
+        assert np.linalg.norm(g - go) <= 1e-4 * np.linalg.norm(go) and abs(np.linalg.norm(g) - 1) < 1e-5
+        qi, ti, _ = fr.bf_crosscheck(du, dd)                      # loop_cam.cpp:388 on the device descriptors
+        m = -np.ones(MN, np.int64); m[qi] = ti
+        assert n > 10 and np.array_equal(np.ctypeslib.as_array(rec.stereo_match[d]), m)
+    assert fe.db_size(False) == 4 and res.accepted == 0 and res.hit_msg_id == -1
+    sp.close(); fe.close()
+
+
+def test_remote_hit_swaps_matcher_roles(gpu):
+    """Multi-drone path on one GPU: two keyframes extracted here are re-labelled as a foreign drone's and ingested (they go
+    to the REMOTE database, ids + REMOTE_MAGIN_NUMBER); an own non-keyframe that looks like the first one must hit it, and
+    because the hit is remote and the query keyframe ours the reference calls compute_loop(old, new)
+    (loop_detector.cpp:113-118): the DATABASE frame is the matcher's query side.  Checked against the oracle matcher with
+    the roles exchanged, direction pairing of loop_detector.cpp:455-465 included."""
+    import torch
+    fe = make_frontend(self_id=1, match_index_dist=5, inner_product_thres=0.3)
+    stream = torch.cuda.current_stream().cuda_stream
+    recs_t = torch.zeros(2 * lib.RECORD_BYTES, dtype=torch.uint8, device="cuda")
+    frames = [frame_images(31), frame_images(32)]
+    for i, (up, down) in enumerate(frames):
+        up = np.ascontiguousarray(up); down = np.ascontiguousarray(down)
+        fe.extract(up.ctypes.data, down.ctypes.data, 700 + i, recs_t.data_ptr() + i * lib.RECORD_BYTES, stream)
+        fe.finish(stream)
+    raw = bytearray(recs_t.cpu().numpy().tobytes())
+    foreign = []
+    for i in range(2):
+        r = lib.KeyframeRecord.from_buffer(raw, i * lib.RECORD_BYTES)
+        r.drone_id = 2                                            # a foreign drone's keyframe
+        foreign.append(lib.KeyframeRecord.from_buffer_copy(bytes(raw[i * lib.RECORD_BYTES:(i + 1) * lib.RECORD_BYTES])))
+    recs_t.copy_(torch.frombuffer(raw, dtype=torch.uint8))
+    fe.ingest(recs_t.data_ptr(), 2, -1, stream)
+    fe.finish(stream)
+    n_rows = [sum(1 for d in range(4) if f.n_kpts[d] > 0) for f in foreign]
+    assert fe.db_size(True) == sum(n_rows) and fe.db_size(False) == 0
+    # own keyframe: frame 0 seen again, shifted by two pixels with a little noise (descriptors close, not identical)
+    rng = np.random.default_rng(5)
+    up, down = frames[0]
+    shift = lambda a: np.clip(np.roll(a, 2, axis=2).astype(np.int16) + rng.integers(-3, 4, a.shape), 0, 255).astype(np.uint8)
+    up2, down2 = np.ascontiguousarray(shift(up)), np.ascontiguousarray(shift(down))
+    own_t = torch.zeros(lib.RECORD_BYTES, dtype=torch.uint8, device="cuda")
+    res_t = torch.zeros(lib.RESULT_BYTES, dtype=torch.uint8, device="cuda")
+    fe.extract(up2.ctypes.data, down2.ctypes.data, 900, own_t.data_ptr(), stream)
+    fe.query(own_t.data_ptr(), res_t.data_ptr(), stream, init_mode=False, nonkeyframe=True)
+    fe.finish(stream)
+    own = lib.KeyframeRecord.from_buffer_copy(own_t.cpu().numpy().tobytes())
+    res = lib.LoopResult.from_buffer_copy(res_t.cpu().numpy().tobytes())
+    assert own.drone_id == 1
+    # expected hit: best inner product over the remote rows (max_index = 1: every row is old enough), rows in ingest order
+    rows = [(f, d) for f in range(2) for d in range(4) if foreign[f].n_kpts[d] > 0]
+    q = np.ctypeslib.as_array(own.global_desc[1]).astype(np.float32)
+    scores = np.array([np.ctypeslib.as_array(foreign[f].global_desc[d]) @ q for f, d in rows])
+    best = int(np.argmax(scores))
+    assert scores[best] > 0.3 and np.sort(scores)[-1] - np.sort(scores)[-2] > 1e-4
+    f_hit, d_hit = rows[best]
+    assert f_hit == 0                                             # it is the frame we re-visited
+    assert res.accepted == 1 and res.swapped == 1
+    assert res.hit_id == lib.REMOTE_MAGIN_NUMBER + best and res.hit_dir == d_hit
+    assert res.hit_msg_id == 700 + f_hit and res.hit_drone_id == 2
+    assert abs(res.hit_score - scores[best]) < 1e-4
+    # direction pairing with swapped roles: main_new = direction_old (database), main_old = the queried direction (1)
+    main_new, main_old = d_hit, 1
+    slot = 0
+    for _dn in range(main_new, main_new + 4):
+        dir_new = _dn % 4
+        dir_old = ((main_old - main_new + 4) % 4 + _dn) % 4
+        n_db, n_rec = foreign[f_hit].n_kpts[dir_new], own.n_kpts[dir_old]
+        if n_db <= 0 or n_rec <= 0:
+            continue
+        assert (res.dir_new[slot], res.dir_old[slot]) == (dir_new, dir_old)
+        qd = np.ctypeslib.as_array(foreign[f_hit].local_desc[dir_new])[:n_db]       # "new" = the DATABASE frame
+        td = np.ctypeslib.as_array(own.local_desc[dir_old])[:n_rec]                 # "old" = the current keyframe
+        qi, ti, _ = fr.bf_crosscheck(qd, td)
+        n = res.n_matches[slot]
+        assert n == len(qi) and n > 5
+        assert list(res.match_new[slot][:n]) == qi.tolist() and list(res.match_old[slot][:n]) == ti.tolist()
+        slot += 1
+    assert slot >= 1 and all(res.dir_new[s] == -1 for s in range(slot, 4))
+    fe.close()

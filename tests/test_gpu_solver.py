@@ -94,6 +94,23 @@ def test_solve_c5_full_size_properties(solver):
     assert s2.iterations <= 3 and np.abs(p2 - poses).max() < 1e-3
 
 
+def test_solve_c5_converged_poses_vs_oracle(solver):
+    """The graph the bench times (BASELINE config 5: 2000 pose nodes, 12 000 factors) against the oracle run to the same
+    tight tolerances: converged poses <= 1e-4, final cost <= 1e-8 relative, residual count equal."""
+    g = synth.pose_graph_c5(0)
+    ref = sr.solve_fast(g, max_iters=300, function_tol=1e-14, gradient_tol=1e-11, param_tol=1e-12)
+    poses, s = solver.solve(g, tight(solver))
+    assert s.termination in (0, 1, 2), s.termination
+    assert abs(s.initial_cost - ref["initial_cost"]) < 1e-9 * ref["initial_cost"]
+    assert abs(s.final_cost - ref["final_cost"]) < 1e-8 * ref["final_cost"], (s.final_cost, ref["final_cost"])
+    assert np.abs(poses - ref["poses"]).max() < 1e-4
+    assert s.n_residuals == ref["n_residuals"]
+    # the default (Ceres-tolerance, fp32-inner) solve that the bench reports stops near the same point
+    p_def, s_def = solver.solve(g)
+    assert abs(s_def.final_cost - ref["final_cost"]) < 1e-6 * ref["final_cost"]
+    assert np.abs(p_def - ref["poses"]).max() < 2e-2
+
+
 def test_chain_preconditioner_same_answer_fewer_iterations(solver):
     """The chain (block-tridiagonal path) preconditioner and block-Jacobi solve the same normal equations: converged
     poses agree, the inner iteration count drops several-fold, and node ids in arbitrary order (the path cover has to find
