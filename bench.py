@@ -4,7 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one 4-view fisheye keyframe through the hot path (BASELINE.json config C3 per GPU):
+A "step" is one batch of KF_PER_STEP = 10 four-view fisheye keyframes through the hot path (BASELINE.json config C3 per
+GPU; the default 20 steps time 200 keyframes), each keyframe being
   8 x SuperPoint (640x480, up+down images of 4 directions) + 4 x NetVLAD + 4 stereo cross-check matches
   + add_to_database + inner-product top-k against the keyframe database (10 000 rows x 4096 f32 preloaded)
   + acceptance rule + 4 per-direction cross-check matches against the hit keyframe.
@@ -16,7 +17,11 @@ record (replaces LoopNet's LCM multicast) and each GPU ingests the N-1 foreign r
 The pose-graph solve (BASELINE config C5 graph: 2000 nodes / 12 000 factors) is single-GPU ("replicas only"): it is
 timed once per run on every rank and reported as `solve_ms`.
 `--impl reference`: the reference's CPU path restated by oracle/ (torch CPU SuperPoint/NetVLAD with all host threads,
-numpy scan, cross-check matcher, scipy sparse LM) -- the reference itself cannot be built here.
+numpy scan, cross-check matcher, scipy sparse LM) -- the reference itself cannot be built here.  With
+--gpus N it runs N CPU drones side by side (N processes sharing the host threads), the same weak-scaling workload.
+`trt_like_baseline` (N = 1, in the main line): baseline/trt_like.py, the reference's TensorRT structure with the engines
+replaced by PyTorch/cuDNN fp16 -- batch 1, H2D + enqueue + D2H of every binding + synchronize per image, CPU
+post-processing -- timed on the same GPU and host.
 """
 import argparse
 import ctypes as C
@@ -34,7 +39,9 @@ sys.path.insert(0, ROOT)
 
 W, H, N_DIRS, MAX_NUM = 640, 480, 4, 200
 DB_ROWS = 10000
-POOL = 4                      # distinct keyframes cycled through (each already in the database -> every query hits)
+POOL = 8                      # distinct keyframes cycled through; the first POOL_IN_DB are in the database beforehand (their
+POOL_IN_DB = 4                # queries hit from the start), the others are new the first time and revisits afterwards
+KF_PER_STEP = 10              # keyframes per step: --steps 20 times 200 keyframes
 SP_GFLOP_PER_IMAGE = 52.10    # SURVEY.md section 8d / BASELINE.md section 2
 
 
@@ -47,6 +54,11 @@ def parse():
     p.add_argument("--db-rows", type=int, default=DB_ROWS)
     p.add_argument("--no-solve", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-trt-like", action="store_true")
+    p.add_argument("--blocking-exchange", action="store_true",
+                   help="N > 1: all-gather of round i between extract and ingest of round i (the r01 pipeline), for A/B")
+    p.add_argument("--cpu-drone", type=int, default=-1, help=argparse.SUPPRESS)      # internal: one CPU drone of --impl reference
+    p.add_argument("--cpu-threads", type=int, default=0, help=argparse.SUPPRESS)
     return p.parse_args()
 
 
@@ -187,43 +199,92 @@ def cpu_baseline(args, n_keyframes=2):
     return out
 
 
+def _cpu_drone(args):
+    """one CPU drone of the reference arm: `steps` keyframes on `cpu_threads` torch threads; prints its wall time"""
+    import torch
+    from omniswarm_b200 import synth
+    torch.set_num_threads(max(1, args.cpu_threads))
+    comp, mean = synth.pca_matrices(0)
+    state = (synth.superpoint_weights(0), synth.netvlad_weights(0), comp, mean,
+             synth.descriptor_db(args.db_rows, 4096, 1 + args.cpu_drone), None)
+    frames = [keyframe_images(100 * args.cpu_drone + s) for s in range(2)]
+    for i in range(max(1, args.warmup)):
+        cpu_keyframe(state, *frames[i % len(frames)])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        cpu_keyframe(state, *frames[i % len(frames)])
+    _JSON_OUT.write(json.dumps({"drone": args.cpu_drone, "wall_s": time.perf_counter() - t0, "keyframes": args.steps}) + "\n")
+    _JSON_OUT.flush()
+
+
+def trt_like_baseline(args, frames, n_keyframes=6):
+    """baseline/trt_like.py on the same GPU and host: the reference's TensorRT call structure with cuDNN fp16 engines"""
+    import torch
+    from omniswarm_b200 import synth
+    from baseline.trt_like import TrtLikeFrontend
+    torch.set_num_threads(1)                         # the reference pins libtorch to one thread (superpoint_tensorrt.cpp:98)
+    comp, mean = synth.pca_matrices(0)
+    fe = TrtLikeFrontend(synth.superpoint_weights(0), synth.netvlad_weights(0), comp, mean,
+                         synth.descriptor_db(args.db_rows, 4096, 1), H, W, 0.015, MAX_NUM)
+    for i in range(3):                               # warm-up: cuDNN autotune, allocator
+        fe.keyframe(*frames[i % len(frames)])
+    fe.bytes_h2d = fe.bytes_d2h = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n_keyframes):
+        hit, nk, nm = fe.keyframe(*frames[i % len(frames)])
+    dt = (time.perf_counter() - t0) / n_keyframes
+    return {"value": 1.0 / dt, "unit": "keyframes/s", "ms_per_keyframe": dt * 1e3, "kind": "TRT-like stand-in (PyTorch/cuDNN fp16, "
+            "channels-last, batch 1; H2D + enqueue + D2H of semi/desc + synchronize per image; CPU NMS2 in C, libtorch "
+            "grid_sample/PCA on 1 thread, cv2 BFMatcher, numpy sgemv scan)", "keyframes": n_keyframes,
+            "h2d_bytes_per_keyframe": fe.bytes_h2d // n_keyframes, "d2h_bytes_per_keyframe": fe.bytes_d2h // n_keyframes,
+            "n_kpts": nk, "note": "end to end from host images to host results, like `e2e`; mirrors "
+            "tensorrt_generic.cpp:58-75 + superpoint_tensorrt.cpp:117-230 + loop_cam.cpp:341-523; TensorRT itself is not installable here"}
+
+
 def run_reference(args):
+    if args.cpu_drone >= 0:
+        return _cpu_drone(args)
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t_all = time.perf_counter()
-    import torch
-    from omniswarm_b200 import synth
-    cores, host_cores = best_cpu_threads()
-    comp, mean = synth.pca_matrices(0)
-    state = (synth.superpoint_weights(0), synth.netvlad_weights(0), comp, mean,
-             synth.descriptor_db(args.db_rows, 4096, 1), None)
-    frames = [keyframe_images(s) for s in range(min(POOL, 2))]
+    n = max(1, args.gpus)
+    best, host_cores = best_cpu_threads()
+    threads = max(1, min(best, host_cores // n))
     steps = max(1, min(args.steps, 6))               # bounded sample: a CPU keyframe takes seconds
     warm = max(1, min(args.warmup, 1))
-    for i in range(warm):
-        cpu_keyframe(state, *frames[i % len(frames)])
-    t0 = time.perf_counter()
-    for i in range(steps):
-        cpu_keyframe(state, *frames[i % len(frames)])
-    dt = (time.perf_counter() - t0) / steps
-    val = 1.0 / dt
-    sample = (f"{steps} keyframes on {cores} of {host_cores} host threads (fastest of 8/16/32/64/all; torch CPU fp32 "
-              f"SuperPoint/NetVLAD, numpy scan, cross-check "
-              f"matcher): oracle port of the reference path; TensorRT/Ceres are not installable here")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    env["CUDA_VISIBLE_DEVICES"] = ""                 # the arm must not touch a GPU
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cpu-drone", str(d),
+                               "--cpu-threads", str(threads), "--steps", str(steps), "--warmup", str(warm),
+                               "--db-rows", str(args.db_rows)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
+             for d in range(n)]
+    walls = []
+    for p in procs:
+        out, _ = p.communicate()
+        walls.append(json.loads(out.strip().splitlines()[-1])["wall_s"])
+    dt = max(walls) / steps                          # N drones run side by side: the slowest one bounds the swarm
+    val = n / dt
+    sample = (f"bounded sample: {steps} keyframes per drone (a step of the GPU arm is {KF_PER_STEP} keyframes; ms_per_step is "
+              f"scaled to that), {n} CPU drone process(es) x {threads} torch threads on a {host_cores}-thread host "
+              f"(single-drone optimum: {best} threads, fastest of 8/16/32/64/all); torch CPU fp32 SuperPoint/NetVLAD, numpy "
+              f"scan, cross-check matcher: oracle port of the reference path; TensorRT/Ceres are not installable here")
     line = {"impl": "reference", "metric": "keyframes/sec (SuperPoint+NetVLAD+match)", "value": val, "unit": "keyframes/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * KF_PER_STEP,
+            "keyframes_timed": steps, "ms_per_keyframe": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, 1),
-            "cpu_baseline": {"value": val, "unit": "keyframes/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(args, n),
+            "cpu_baseline": {"value": val, "unit": "keyframes/s", "cores": threads * n, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
+            "gpu_launches": 0, "cpu_drones": n, "wall_s": time.perf_counter() - t_all}
     _emit(line)
 
 
-def workload_config(args, world):
+def workload_config(args, world, keyframes_per_step=KF_PER_STEP):
     return {"workload": "C3: 4-view fisheye keyframe (8x SuperPoint 640x480 + 4x NetVLAD + stereo match + DB add + "
                         f"IP top-k vs {args.db_rows}-row x 4096 f32 DB + rule + 4 local matches)",
+            "keyframes_per_step": keyframes_per_step, "distinct_keyframes": POOL,
             "images_per_keyframe": 2 * N_DIRS, "db_rows": args.db_rows, "max_kpts": MAX_NUM, "sp_thres": 0.015,
             "parallelism": f"drone-per-GPU x{world}" + (" + 1 NCCL all-gather of the keyframe record per step" if world > 1 else ""),
             "l2_note": "per-step working set (activations ~1.3 GB + DB 164 MB) exceeds the 126 MB L2; no explicit flush"}
@@ -261,11 +322,22 @@ def run_ours(args):
     rec_dev = torch.zeros(lib.RECORD_BYTES, dtype=torch.uint8, device="cuda")
     res_dev = torch.zeros(lib.RESULT_BYTES, dtype=torch.uint8, device="cuda")
     gathered = torch.zeros(world * lib.RECORD_BYTES, dtype=torch.uint8, device="cuda") if world > 1 else None
+    # N > 1: the exchange goes through the C ABI (osb_swarm_*: ncclAllGather on the library's own communicator); the
+    # 128-byte communicator id travels over the torch.distributed group that also carries the timing reductions
+    sw, rec2, gath2, pending = None, None, None, [False]
+    if world > 1:
+        uid = torch.zeros(lib.SWARM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(host.Swarm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        sw = host.Swarm(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        rec2 = [torch.zeros(lib.RECORD_BYTES, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        gath2 = [torch.zeros(world * lib.RECORD_BYTES, dtype=torch.uint8, device="cuda") for _ in range(2)]
     rec_host = torch.zeros(lib.RECORD_BYTES, dtype=torch.uint8).pin_memory()
     res_host = torch.zeros(lib.RESULT_BYTES, dtype=torch.uint8).pin_memory()
     # the pool keyframes go into the database first (so that every timed query is a revisit that hits), then
     # random unit-norm rows with local descriptors up to db_rows
-    for i in range(POOL):
+    for i in range(POOL_IN_DB):
         fe.extract(dev_up[i].data_ptr(), dev_dn[i].data_ptr(), 10_000 + i, rec_dev.data_ptr(), st, device_images=True)
         fe.ingest(rec_dev.data_ptr(), 1, -1, st)
     fe.finish(st)
@@ -278,27 +350,54 @@ def run_ours(args):
         fe.db_load(g, ld, np.full(n, MAX_NUM, np.int32), remote=False)
     db_rows_start = fe.db_size(False)
 
-    def step_resident(i):
-        j = i % POOL
-        fe.extract(dev_up[j].data_ptr(), dev_dn[j].data_ptr(), i, rec_dev.data_ptr(), st, device_images=True)
-        if world > 1:
-            swarm.exchange_records(rec_dev, gathered)          # the ONE collective of the path (NCCL all-gather)
+    def swarm_round(i, rec):
+        """after extract of keyframe i into `rec`: database work + the ONE collective of the path.
+        Default (asynchronous, like the reference's LCM thread, loop_net.cpp:142-172): the own keyframe goes to the local
+        database at once, the foreign records of the PREVIOUS round -- whose all-gather ran behind this keyframe's
+        extraction -- go to the remote database, and this round's all-gather starts on the library's side stream."""
+        if args.blocking_exchange:
+            sw.exchange(rec.data_ptr(), gathered.data_ptr(), st)
             fe.ingest(gathered.data_ptr(), world, -1, st)
-        else:
-            fe.ingest(rec_dev.data_ptr(), 1, -1, st)
-        fe.query(rec_dev.data_ptr(), res_dev.data_ptr(), st)
+            return
+        b = i & 1
+        fe.ingest(rec.data_ptr(), 1, -1, st)                                  # add_to_database of the own keyframe
+        if pending[0]:
+            sw.wait(st)
+            fe.ingest(gath2[b ^ 1].data_ptr(), world, rank, st)               # last round's foreign keyframes (own slot skipped)
+        sw.exchange_async(rec.data_ptr(), gath2[b].data_ptr(), st)
+        pending[0] = True
 
-    def step_e2e(i):
+    def keyframe_resident(i):
+        j = i % POOL
+        if world > 1:
+            rec = rec2[i & 1]
+            fe.extract(dev_up[j].data_ptr(), dev_dn[j].data_ptr(), i, rec.data_ptr(), st, device_images=True)
+            swarm_round(i, rec)
+            fe.query(rec.data_ptr(), res_dev.data_ptr(), st)
+        else:
+            fe.extract(dev_up[j].data_ptr(), dev_dn[j].data_ptr(), i, rec_dev.data_ptr(), st, device_images=True)
+            fe.ingest(rec_dev.data_ptr(), 1, -1, st)
+            fe.query(rec_dev.data_ptr(), res_dev.data_ptr(), st)
+
+    def keyframe_e2e(i):
         j = i % POOL
         if world == 1:
             fe.process_raw(pin_up[j].data_ptr(), pin_dn[j].data_ptr(), i, rec_host.data_ptr(), res_host.data_ptr())
         else:
-            fe.extract(pin_up[j].data_ptr(), pin_dn[j].data_ptr(), i, rec_dev.data_ptr(), st)
-            swarm.exchange_records(rec_dev, gathered)
-            fe.ingest(gathered.data_ptr(), world, -1, st)
-            fe.query(rec_dev.data_ptr(), res_dev.data_ptr(), st)
-            rec_host.copy_(rec_dev, non_blocking=True); res_host.copy_(res_dev, non_blocking=True)
+            rec = rec2[i & 1]
+            fe.extract(pin_up[j].data_ptr(), pin_dn[j].data_ptr(), i, rec.data_ptr(), st)
+            swarm_round(i, rec)
+            fe.query(rec.data_ptr(), res_dev.data_ptr(), st)
+            rec_host.copy_(rec, non_blocking=True); res_host.copy_(res_dev, non_blocking=True)
             fe.finish(st)
+
+    def step_resident(i):                 # one step = one batch of KF_PER_STEP keyframes
+        for k in range(KF_PER_STEP):
+            keyframe_resident(i * KF_PER_STEP + k)
+
+    def step_e2e(i):
+        for k in range(KF_PER_STEP):
+            keyframe_e2e(i * KF_PER_STEP + k)
 
     def barrier():
         if world > 1:
@@ -334,23 +433,24 @@ def run_ours(args):
     ms_total, launches = timed(step_resident, args.steps, args.warmup, 0, sampler)
     clocks = sampler.stop()
     ms_step = ms_total / args.steps
-    value = world * 1e3 / ms_step
+    ms_keyframe = ms_step / KF_PER_STEP
+    value = world * 1e3 / ms_keyframe
 
     # ---- timed region 2: end to end through the host-buffer call (wall clock == device time: sync on both sides) ----
     barrier()
     for i in range(args.warmup):
-        step_e2e(50_000 + i)
+        step_e2e(5_000 + i)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        step_e2e(60_000 + i)
+        step_e2e(6_000 + i)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * args.steps / e2e_s
+    e2e_value = world * args.steps * KF_PER_STEP / e2e_s
     res = lib.LoopResult.from_buffer_copy(res_host.numpy().tobytes())
     rec = lib.KeyframeRecord.from_buffer_copy(rec_host.numpy().tobytes())
 
@@ -358,7 +458,7 @@ def run_ours(args):
     fe.set_profiling(True)
     stage_acc = {}
     for i in range(5):
-        step_resident(70_000 + i)
+        keyframe_resident(700_000 + i)
         fe.finish(st)
         for k, v in fe.stage_ms().items():
             stage_acc.setdefault(k, []).append(v)
@@ -366,6 +466,30 @@ def run_ours(args):
     stages = {k: float(np.median(v)) for k, v in stage_acc.items()}
     db_rows_now = fe.db_size(False)
     db_rows_remote = fe.db_size(True)
+
+    # ---- the collective alone: one blocking all-gather of the 286 KB record, CUDA events, max over ranks ----
+    exchange = None
+    if world > 1:
+        sw.wait(st)
+        for _ in range(5):
+            sw.exchange(rec2[0].data_ptr(), gathered.data_ptr(), st)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 50
+        e0.record()
+        for _ in range(reps):
+            sw.exchange(rec2[0].data_ptr(), gathered.data_ptr(), st)
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = float(t.item())
+        exchange = {"exchange_us": us, "bytes_per_rank": lib.RECORD_BYTES,
+                    "recv_gbs_per_gpu": (world - 1) * lib.RECORD_BYTES / us / 1e3,
+                    "frac_of_nvlink_770gbs": (world - 1) * lib.RECORD_BYTES / us / 1e3 / 770.0,
+                    "pipeline": "blocking between extract and ingest" if args.blocking_exchange else
+                                "asynchronous: round i's ncclAllGather (osb_swarm_exchange_async, side stream) runs behind the "
+                                "extraction of keyframe i+1; its foreign records are ingested one round later",
+                    "api": "osb_swarm_* (C ABI, ncclAllGather on the library's communicator)"}
 
     # ---- rooflines ----
     # dominant kernel: the conv1b launch of conv_umma_kernel<64> (43 % of the network's FLOPs).  Its own duration comes
@@ -384,7 +508,9 @@ def run_ours(args):
     layer_tflops = {k: (2 * GMAC[k] * 2 * N_DIRS / v if v > 0 else None) for k, v in layer_ms.items()}
     conv_ms = float(sum(layer_ms.values()))      # the 12 conv launches of a standalone handle (no overlapped work)
     conv_tflops = 2 * N_DIRS * SP_GFLOP_PER_IMAGE / conv_ms  # GFLOP / ms = TFLOP/s
-    dom = "conv1b+pool"
+    dom = "conv1b+pool"        # with the default fused first layers this launch is conv1a + conv1b + pool
+    dom_gmac = GMAC["conv1a"] + GMAC["conv1b+pool"] if layer_ms["conv1a"] < 0.02 else GMAC["conv1b+pool"]
+    dom_tflops = 2 * dom_gmac * 2 * N_DIRS / layer_ms[dom]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -392,25 +518,29 @@ def run_ours(args):
     scan_ms = stages["db_scan"]
     scan_bytes = (db_rows_now + db_rows_remote) * 4096 * 4.0        # local + remote database, each row read once
     scan_gbs = scan_bytes / scan_ms / 1e6
-    roofline = {"kernel": "conv_umma_kernel<64,RES> (conv1b 64->64 3x3 @640x480 + fused 2x2 max-pool; tcgen05 + TMA, split-fp16: "
-                          "hi*hi + hi*lo as one MMA of width 2N, lo*hi as one of width N per K step)",
-                "bound": "tensor", "achieved": layer_tflops[dom], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": layer_tflops[dom] / pk["bf16_tflops_sustained"],
-                "traffic": (traffic or {}).get("conv1b_dram_bytes_per_launch"),
-                "algorithmic": f"{2 * N_DIRS} images x {2 * GMAC[dom]:.3f} GFLOP (fp32-equivalent MACs x 2); the tensor pipes "
-                               "execute 3x this many fp16 MACs for fp32-level accuracy",
-                "ms_per_launch": layer_ms[dom], "mma_tflops_executed": 3 * layer_tflops[dom],
-                "mma_frac_of_peak": 3 * layer_tflops[dom] / pk["bf16_tflops_sustained"],
+    roofline = {"kernel": "conv1_fused_kernel (conv1a 1->64 computed in the SM by 8 producer warps + conv1b 64->64 3x3 @640x480 on "
+                          "tcgen05 from ONE shared-memory halo copy (9 descriptor views) + fused 2x2 max-pool; split-fp16: hi*hi + "
+                          "hi*lo as one MMA of width 128, lo*hi as one of width 64 per K step)",
+                "bound": "tensor", "achieved": dom_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": dom_tflops / pk["bf16_tflops_sustained"],
+                "traffic": (traffic or {}).get("conv1_fused_dram_bytes_per_launch"),
+                "algorithmic": f"{2 * N_DIRS} images x {2 * dom_gmac:.3f} GFLOP (conv1a + conv1b, fp32-equivalent MACs x 2); the "
+                               "tensor pipes execute 3x conv1b's share as fp16 MACs for fp32-level accuracy",
+                "algorithmic_dram_bytes": 2 * N_DIRS * (W * H + (W // 2) * (H // 2) * 64 * 4),
+                "ms_per_launch": layer_ms[dom], "mma_tflops_executed": 3 * 2 * GMAC["conv1b+pool"] * 2 * N_DIRS / layer_ms[dom],
+                "mma_frac_of_peak": 3 * 2 * GMAC["conv1b+pool"] * 2 * N_DIRS / layer_ms[dom] / pk["bf16_tflops_sustained"],
                 "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)"}
     roofline_stack = {"what": "whole SuperPoint conv stack (12 conv launches, per-layer CUDA-event times of a standalone handle)", "achieved": conv_tflops,
                       "unit": "TFLOP/s", "frac": conv_tflops / pk["bf16_tflops_sustained"], "ms": conv_ms,
                       "layer_ms": layer_ms, "layer_tflops": layer_tflops, "keypoint_counts_image0": kp_counts}
-    roofline_match = {"kernel": "db_scan_kernel<1,4>", "bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm_gbs"],
+    scan_kernel = "db_scan_coop_kernel<1>" if db_rows_now <= 2 * 148 * 64 else "db_scan_kernel<1,4>"
+    roofline_match = {"kernel": scan_kernel, "bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm_gbs"],
                       "unit": "GB/s", "frac": scan_gbs / pk["hbm_gbs"],
                       "traffic": (traffic or {}).get("db_scan_dram_bytes_per_launch"),
                       "algorithmic": f"({db_rows_now} local + {db_rows_remote} remote) rows x 16384 B", "ms": scan_ms,
                       "peak_source": pk["source"],
-                      "note": "ms = the db_scan stage of the step: 2 scan launches (remote + local DB) + 2 merge launches"}
+                      "note": "ms = the db_scan stage of a keyframe: the remote-database and the local-database scan launches "
+                              "(the merge is fused into each scan's last CTA)"}
 
     # ---- database scan alone (the HBM-roofline kernel): 10 k rows (config C3) and 50 k rows (config C5) ----
     match_sweep = []
@@ -568,12 +698,14 @@ def run_ours(args):
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world), "gpu_launches": int(launches),
+                "keyframes_timed": args.steps * KF_PER_STEP, "ms_per_keyframe": ms_keyframe,
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "keyframes/s",
-                        "h2d_bytes_per_step": 2 * N_DIRS * W * H, "d2h_bytes_per_step": lib.RECORD_BYTES + lib.RESULT_BYTES,
-                        "ms_per_step": e2e_s * 1e3 / args.steps},
+                        "h2d_bytes_per_step": KF_PER_STEP * 2 * N_DIRS * W * H,
+                        "d2h_bytes_per_step": KF_PER_STEP * (lib.RECORD_BYTES + lib.RESULT_BYTES),
+                        "ms_per_step": e2e_s * 1e3 / args.steps, "ms_per_keyframe": e2e_s * 1e3 / (args.steps * KF_PER_STEP)},
                 "roofline": roofline, "roofline_conv_stack": roofline_stack, "roofline_match": roofline_match,
-                "match_sweep": match_sweep, "match_sharded": match_sharded, "c2_pinhole": c2, "geometry": geometry,
+                "exchange": exchange, "match_sweep": match_sweep, "match_sharded": match_sharded, "c2_pinhole": c2, "geometry": geometry,
                 "stage_ms": stages,
                 "loop_check": {"accepted": int(res.accepted), "hit_id": int(res.hit_id), "hit_score": float(res.hit_score),
                                "n_kpts": list(rec.n_kpts), "n_matches": list(res.n_matches)},
@@ -581,11 +713,16 @@ def run_ours(args):
         if solve:
             line["solve"] = solve
             line["solve_ms"] = solve["solve_ms"]
+        if world == 1 and not args.no_trt_like:
+            line["trt_like_baseline"] = trt_like_baseline(args, frames)
+            line["trt_like_baseline"]["ours_e2e_over_trt_like"] = e2e_value / line["trt_like_baseline"]["value"]
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         _emit(line)
     if world > 1:
+        sw.wait(st); torch.cuda.synchronize()
         dist.barrier()
+        sw.close()
         dist.destroy_process_group()
 
 

@@ -241,6 +241,35 @@ osb_status osb_solver_linearize(osb_solver* h, int n_nodes, const double* poses,
                                 double* r, double* Ja, double* Jb);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * PCM outlier rejection of loop edges -- replaces SwarmLocalOutlierRejection::OutlierRejectionLoopEdgesPCM
+ *   (swarm_localization/src/swarm_outlier_rejection/swarm_outlier_rejection.cpp:173-297), the stage that feeds
+ *   get_good_loops() to the solve: pairwise consistency of the n loop edges of one drone pair
+ *   (err = odom_a * p_edge2 * odom_b^-1 * p_edge1^-1, 6-D log map, squared Mahalanobis distance < pcm_thres, :190-235) and
+ *   FMC::maxCliqueHeu on the consistency graph (third_party/fast_max-clique_finder/src/findCliqueHeu.cpp:120-244, restated
+ *   literally incl. its prunings and candidate order).
+ * osb_loop_edge: what the adapter reads off a Swarm::LoopEdge and the two DroneTrajectory objects (swarm_msgs is not in the
+ *   reference tree, so its arithmetic is defined in oracle/pcm_ref.py): relative_pose as (x y z, qw qx qy qz),
+ *   get_covariance() 6x6 row-major (translation block first), the ego-motion pose of drone id_a at ts_a and of drone id_b at
+ *   ts_b, and the accumulated trajectory length at those stamps.  The odometry between two stamps is pose(ts1)^-1 * pose(ts2)
+ *   with covariance |len2 - len1| * diag(odom_pos_cov_per_m x3, odom_ang_cov_per_m x3).
+ * Edges are in insertion order (all_loops[id_a][id_b]); edges of another drone pair are never consistent.
+ * Outputs: clique [n] = indices of the kept loops in maxCliqueHeu's order (good_loops_set, :291-296), clique_size; optional
+ *   adj [n][n] (1 = consistent) and smd [n][n] (squared Mahalanobis distances, +inf where undefined).  n <= 4096. */
+typedef struct {
+  int32_t id_a, id_b;
+  double rel_pose[7];
+  double cov[36];
+  double odom_a[7];
+  double odom_b[7];
+  double len_a, len_b;
+} osb_loop_edge;
+osb_status osb_pcm(const osb_loop_edge* edges, int n, double pcm_thres, double odom_pos_cov_per_m, double odom_ang_cov_per_m,
+                   int32_t* clique, int32_t* clique_size, uint8_t* adj, double* smd);
+osb_status osb_pcm_dev(const osb_loop_edge* edges_dev, int n, double pcm_thres, double odom_pos_cov_per_m,
+                       double odom_ang_cov_per_m, int32_t* clique_dev, int32_t* clique_size_dev, uint8_t* adj_dev,
+                       double* smd_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Geometric filter of the loop matcher (first half) -- the inlier mask of
  *   cv::findHomography(old_2d, new_2d, CV_RANSAC, 3, mask)            swarm_loop/src/loop_detector.cpp:589-598
  * for n_pairs correspondence sets at once.  src = old_2d, dst = new_2d, [n_pairs][max_n][2] floats, n[pair] points each
@@ -370,6 +399,33 @@ osb_status osb_frontend_db_set_geometry(osb_frontend* h, int remote, int64_t fir
  * [4] add_to_database  [5] database scans (remote + local)  [6] acceptance rule + per-direction match  [7] unused */
 osb_status osb_frontend_set_profiling(osb_frontend* h, int enable);
 osb_status osb_frontend_stage_ms(osb_frontend* h, float* ms8);
+/* ------------------------------------------------------------------------------------------------------------
+ * Swarm-wide keyframe exchange -- replaces LoopNet::broadcast_fisheye_desc / image_desc_callback
+ *   (swarm_loop/src/loop_net.cpp:20-120,142-172; called from swarm_loop/src/swarm_loop.cpp:167): the LCM UDP multicast of
+ *   one header + one message per landmark becomes ONE ncclAllGather of the fixed-size osb_keyframe_record per keyframe
+ *   round (drone = rank; NVLink on the 8-GPU box).  NCCL is opened with dlopen on first use (no link-time dependency).
+ * unique_id: rank 0 creates the 128-byte communicator id and hands it to the other drones over any channel they already
+ *            share (a ROS parameter, a file, the LCM channel); every rank then calls init with the same id.
+ * exchange:  record_dev (this drone's record) -> gathered_dev[world] in rank order, enqueued on `stream`, no
+ *            synchronisation.  osb_frontend_ingest(gathered_dev, world, ...) routes own / foreign records by drone_id.
+ * exchange_async + wait: the reference's exchange is asynchronous (loop_net.cpp:142-172), so the collective may run on
+ *            the handle's own stream behind an event of `stream` while the next keyframe is extracted; osb_swarm_wait
+ *            makes `stream` wait for the LAST exchange_async.  One exchange in flight per handle; the caller
+ *            double-buffers record_dev / gathered_dev.   world == 1: a device copy, no NCCL needed. */
+#define OSB_SWARM_ID_BYTES 128
+typedef struct osb_swarm osb_swarm;
+osb_status osb_swarm_unique_id(uint8_t* id_out /*[OSB_SWARM_ID_BYTES]*/);
+osb_status osb_swarm_init(osb_swarm** out, const uint8_t* id /*[OSB_SWARM_ID_BYTES], may be NULL when world == 1*/, int rank,
+                          int world);
+osb_status osb_swarm_destroy(osb_swarm* h);
+osb_status osb_swarm_exchange(osb_swarm* h, const osb_keyframe_record* record_dev, osb_keyframe_record* gathered_dev,
+                              void* stream);
+osb_status osb_swarm_exchange_async(osb_swarm* h, const osb_keyframe_record* record_dev, osb_keyframe_record* gathered_dev,
+                                    void* stream);
+osb_status osb_swarm_wait(osb_swarm* h, void* stream);
+int osb_swarm_rank(osb_swarm* h);
+int osb_swarm_world(osb_swarm* h);
+
 /* number of kernels launched by this library since it was loaded (all handles), for bench.py's gpu_launches */
 int64_t osb_launch_count(void);
 

@@ -431,5 +431,71 @@ class KeyframeFrontend:
         _l.check(self._lib.osb_frontend_db_set_geometry(self._h, int(remote), first_row, k.shape[0], _l.ptr(k), _l.ptr(sm)))
 
 
+def pcm_outlier_rejection(edges, pcm_thres: float, odom_pos_cov_per_m: float, odom_ang_cov_per_m: float,
+                          want_matrices: bool = False):
+    """SwarmLocalOutlierRejection::OutlierRejectionLoopEdgesPCM (swarm_outlier_rejection.cpp:173-297) for the loop edges of
+    one drone pair: `edges` = list of dicts (id_a, id_b, rel [7], cov [6,6], odom_a [7], odom_b [7], len_a, len_b) in
+    insertion order -> indices of the kept loops in maxCliqueHeu's order (+ adjacency and smd matrices on request)."""
+    lib = _l.load()
+    n = len(edges)
+    arr = (_l.LoopEdge * n)()
+    for i, e in enumerate(edges):
+        a = arr[i]
+        a.id_a, a.id_b, a.len_a, a.len_b = int(e["id_a"]), int(e["id_b"]), float(e["len_a"]), float(e["len_b"])
+        a.rel_pose[:] = [float(x) for x in e["rel"]]
+        a.cov[:] = [float(x) for x in np.asarray(e["cov"], np.float64).reshape(-1)]
+        a.odom_a[:] = [float(x) for x in e["odom_a"]]
+        a.odom_b[:] = [float(x) for x in e["odom_b"]]
+    clique = np.zeros(n, np.int32)
+    size = C.c_int32(0)
+    adj = np.zeros((n, n), np.uint8) if want_matrices else None
+    smd = np.zeros((n, n), np.float64) if want_matrices else None
+    _l.check(lib.osb_pcm(arr, n, float(pcm_thres), float(odom_pos_cov_per_m), float(odom_ang_cov_per_m), _l.ptr(clique),
+                         C.byref(size), _l.ptr(adj), _l.ptr(smd)))
+    out = clique[:size.value].copy()
+    return (out, adj, smd) if want_matrices else out
+
+
+class Swarm:
+    """The swarm-wide keyframe exchange behind the C ABI (osb_swarm_*): one ncclAllGather of the fixed-size keyframe
+    record per round; replaces LoopNet::broadcast_fisheye_desc / image_desc_callback (loop_net.cpp:20-120,142-172).
+    `unique_id()` on rank 0, hand the 128 bytes to the other ranks, then `Swarm(id, rank, world)` everywhere."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * _l.SWARM_ID_BYTES)()
+        _l.check(_l.load().osb_swarm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, uid: bytes | None, rank: int, world: int):
+        self._lib = _l.load()
+        self._h = C.c_void_p()
+        idbuf = None
+        if uid is not None:
+            assert len(uid) == _l.SWARM_ID_BYTES
+            idbuf = (C.c_uint8 * _l.SWARM_ID_BYTES).from_buffer_copy(uid)
+        _l.check(self._lib.osb_swarm_init(C.byref(self._h), idbuf, rank, world))
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.osb_swarm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def exchange(self, record_dev: int, gathered_dev: int, stream: int):
+        """this rank's record -> gathered[world] in rank order, enqueued on `stream` (osb_swarm_exchange)"""
+        _l.check(self._lib.osb_swarm_exchange(self._h, C.c_void_p(record_dev), C.c_void_p(gathered_dev), C.c_void_p(stream)))
+
+    def exchange_async(self, record_dev: int, gathered_dev: int, stream: int):
+        """the same on the handle's own stream, behind an event of `stream` (osb_swarm_exchange_async)"""
+        _l.check(self._lib.osb_swarm_exchange_async(self._h, C.c_void_p(record_dev), C.c_void_p(gathered_dev), C.c_void_p(stream)))
+
+    def wait(self, stream: int):
+        """`stream` waits for the last exchange_async (osb_swarm_wait)"""
+        _l.check(self._lib.osb_swarm_wait(self._h, C.c_void_p(stream)))
+
+
 def launch_count() -> int:
     return int(_l.load().osb_launch_count())

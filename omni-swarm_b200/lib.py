@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(CSRC, "libomniswarm_b200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NO_DEVICE = 0, 1, 2, 3, 4
 MAX_DIRS, MAX_KPTS, FEATURE_DESC_SIZE, DEEP_DESC_SIZE = 4, 200, 64, 4096
 REMOTE_MAGIN_NUMBER = 1000000
+SWARM_ID_BYTES = 128
 PAYLOAD_LEN = 24
 
 
@@ -54,6 +55,11 @@ class LoopResult(C.Structure):
                 ("match_old", (C.c_int32 * MAX_KPTS) * MAX_DIRS),
                 ("geo_valid", C.c_int32 * MAX_DIRS), ("n_geo", C.c_int32 * MAX_DIRS),
                 ("geo_new", (C.c_int32 * MAX_KPTS) * MAX_DIRS), ("geo_old", (C.c_int32 * MAX_KPTS) * MAX_DIRS)]
+
+
+class LoopEdge(C.Structure):
+    _fields_ = [("id_a", C.c_int32), ("id_b", C.c_int32), ("rel_pose", C.c_double * 7), ("cov", C.c_double * 36),
+                ("odom_a", C.c_double * 7), ("odom_b", C.c_double * 7), ("len_a", C.c_double), ("len_b", C.c_double)]
 
 
 class FrontendConfig(C.Structure):
@@ -131,6 +137,16 @@ _SIG = {
     "osb_frontend_db_reset": (C.c_int, [_P]),
     "osb_frontend_db_load": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P]),
     "osb_frontend_db_set_geometry": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, _P]),
+    "osb_pcm": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P]),
+    "osb_pcm_dev": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P, _P]),
+    "osb_swarm_unique_id": (C.c_int, [_P]),
+    "osb_swarm_init": (C.c_int, [C.POINTER(_P), _P, C.c_int, C.c_int]),
+    "osb_swarm_destroy": (C.c_int, [_P]),
+    "osb_swarm_exchange": (C.c_int, [_P, _P, _P, _P]),
+    "osb_swarm_exchange_async": (C.c_int, [_P, _P, _P, _P]),
+    "osb_swarm_wait": (C.c_int, [_P, _P]),
+    "osb_swarm_rank": (C.c_int, [_P]),
+    "osb_swarm_world": (C.c_int, [_P]),
 }
 
 _lib = None

@@ -347,3 +347,82 @@ def pose_graph_c5(seed: int = 0) -> dict:
     """BASELINE.json C5 graph: 5 drones x 400 frames = 2000 nodes, 12 000 factors
     = 1995 ego + 4000 UWB + 4000 loop + 2005 detection-as-relative-pose."""
     return pose_graph(5, 400, n_uwb=4000, n_loop=4000, n_det=2005, seed=seed)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# loop edges of one drone pair for the PCM outlier rejection (SURVEY.md 8f-2)
+# ----------------------------------------------------------------------------------------------------------------
+def _quat_from_rotvec(rv):
+    a = np.linalg.norm(rv)
+    if a < 1e-12:
+        return np.array([1.0, 0.5 * rv[0], 0.5 * rv[1], 0.5 * rv[2]])
+    return np.concatenate([[np.cos(a / 2)], np.sin(a / 2) * rv / a])
+
+
+class _PoseAlgebra:
+    """(t, unit quaternion wxyz) poses: compose / invert (generator-side helper, independent of the oracle)"""
+
+    @staticmethod
+    def q_mul(a, b):
+        aw, ax, ay, az = a; bw, bx, by, bz = b
+        return np.array([aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                         aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw])
+
+    @staticmethod
+    def q_rot(q, v):
+        u = q[1:]
+        c = np.cross(u, v)
+        return v + 2.0 * (q[0] * c + np.cross(u, c))
+
+    @classmethod
+    def pose_mul(cls, a, b):
+        return np.concatenate([a[:3] + cls.q_rot(a[3:], b[:3]), cls.q_mul(a[3:], b[3:])])
+
+    @classmethod
+    def pose_inv(cls, a):
+        qc = np.array([a[3], -a[4], -a[5], -a[6]])
+        return np.concatenate([-cls.q_rot(qc, a[:3]), qc])
+
+
+def pcm_edges(n: int = 60, outlier_frac: float = 0.3, seed: int = 0, flip_frac: float = 0.3, id_a: int = 1, id_b: int = 2,
+              other_pair: int = 0):
+    """n loop edges between drones id_a and id_b flying the circles of swarm_local_sim.cpp (:589-604) with yaw and small
+    roll/pitch: inliers = true relative pose + noise of the labelled covariance, outliers = gross errors; a fraction of
+    the edges is stored b -> a (LoopEdge::same_robot_pair == 2); `other_pair` extra edges belong to another drone pair.
+    Edge dicts as oracle/pcm_ref.py and host.pcm_outlier_rejection take them; e["inlier"] is the ground truth."""
+    rng = np.random.default_rng(seed + 7000)
+    T, R = 50.0, 5.0
+    pr = _PoseAlgebra
+
+    def gt(drone, t):
+        ph = 2 * np.pi * t / T
+        pos = np.array([R * np.sin(ph) + 2.0 * drone, R * (1 - np.cos(ph)) - 1.5 * drone, 2.0 * np.sin(ph) + 0.3 * drone])
+        q = _quat_from_rotvec(np.array([0.03 * np.sin(ph), 0.02 * np.cos(ph), 0.6 * ph + 0.2 * drone]))
+        return np.concatenate([pos, q])
+
+    def path_len(t):                          # arc length of the circle (constant speed), metres
+        return np.hypot(2 * np.pi * R / T, 2 * np.pi * 2.0 / T * 0.7) * t
+
+    sig_p, sig_a = 0.03, 0.01
+    cov = np.diag([sig_p ** 2] * 3 + [sig_a ** 2] * 3)
+    edges = []
+    for i in range(n + other_pair):
+        ta, tb = rng.uniform(0, 40), rng.uniform(0, 40)
+        a, b = (id_a, id_b) if i < n else (id_a, id_b + 5)
+        pa, pb = gt(a, ta), gt(b, tb)
+        rel = pr.pose_mul(pr.pose_inv(pa), pb)
+        inlier = rng.uniform() >= outlier_frac
+        if inlier:
+            noise = np.concatenate([rng.normal(0, sig_p, 3), _quat_from_rotvec(rng.normal(0, sig_a, 3))])
+        else:
+            noise = np.concatenate([rng.uniform(-3, 3, 3), _quat_from_rotvec(rng.uniform(-0.8, 0.8, 3))])
+        rel = pr.pose_mul(rel, noise)
+        rel[3:] /= np.linalg.norm(rel[3:])
+        e = dict(id_a=a, id_b=b, rel=rel, cov=cov * rng.uniform(0.8, 1.3), odom_a=pa, odom_b=pb, len_a=path_len(ta),
+                 len_b=path_len(tb), inlier=bool(inlier) and i < n)
+        if i < n and rng.uniform() < flip_frac:                      # the same loop reported b -> a
+            e = dict(id_a=b, id_b=a, rel=pr.pose_inv(rel), cov=e["cov"], odom_a=pb, odom_b=pa, len_a=e["len_b"],
+                     len_b=e["len_a"], inlier=e["inlier"])
+        edges.append(e)
+    order = rng.permutation(len(edges))
+    return [edges[i] for i in order]

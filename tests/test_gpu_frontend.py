@@ -340,3 +340,28 @@ def test_remote_hit_swaps_matcher_roles(gpu):
         slot += 1
     assert slot >= 1 and all(res.dir_new[s] == -1 for s in range(slot, 4))
     fe.close()
+
+
+def test_swarm_exchange_single_rank_and_ingest(gpu):
+    """osb_swarm_* with world = 1 (no NCCL needed): exchange and exchange_async + wait deliver the record, and the gathered
+    buffer feeds osb_frontend_ingest exactly like the record itself (own drone -> local database)."""
+    import torch
+    fe = make_frontend(self_id=1, match_index_dist=5)
+    sw = host.Swarm(None, 0, 1)
+    stream = torch.cuda.current_stream().cuda_stream
+    rec_t = torch.zeros(lib.RECORD_BYTES, dtype=torch.uint8, device="cuda")
+    g1 = torch.zeros(lib.RECORD_BYTES, dtype=torch.uint8, device="cuda")
+    g2 = torch.zeros(lib.RECORD_BYTES, dtype=torch.uint8, device="cuda")
+    up, down = (np.ascontiguousarray(a) for a in frame_images(41))
+    fe.extract(up.ctypes.data, down.ctypes.data, 5, rec_t.data_ptr(), stream)
+    sw.exchange(rec_t.data_ptr(), g1.data_ptr(), stream)
+    sw.exchange_async(rec_t.data_ptr(), g2.data_ptr(), stream)
+    sw.wait(stream)
+    fe.ingest(g2.data_ptr(), 1, -1, stream)
+    fe.finish(stream)
+    assert torch.equal(rec_t, g1) and torch.equal(rec_t, g2)
+    rec = lib.KeyframeRecord.from_buffer_copy(g2.cpu().numpy().tobytes())
+    assert rec.msg_id == 5 and fe.db_size(False) == sum(1 for d in range(4) if rec.n_kpts[d] > 0) and fe.db_size(True) == 0
+    with pytest.raises(host._l.OsbError):
+        host.Swarm(None, 0, 2)                     # world > 1 needs the unique id
+    sw.close(); fe.close()

@@ -217,3 +217,62 @@ def test_homography_edge_cases_and_pair_filter():
     qn, qo = gr.loop_pair_filter(list(range(n)), list(range(n)), flags, dst, src)
     assert set(qn.tolist()) == {i for i in range(n) if flags[i] and truth[i]} and np.array_equal(qn, qo)
     assert gr.loop_pair_filter([0, 1, 2], [0, 1, 2], flags, dst, src) is None
+
+
+def test_c_restatement_of_nms2_agrees_with_numpy_oracle():
+    """oracle/c/nms2_ref.c (plain C, compiled by __graft_entry__.build) and oracle/frontend_ref.py::nms2 (numpy) are two
+    independent statements of superpoint_tensorrt.cpp:164-189,237-310: golden fixtures, exact ties, the flat-address column
+    wrap at the image edge and the u16 index-plane wrap above 65535 candidates must all agree bit for bit."""
+    from oracle import nms2_c
+    z = np.load(os.path.join(GOLDEN, "postproc.npz"))
+    for n in "abc":
+        k, c = nms2_c.get_keypoints(z[f"{n}_semi"], 0.015, 50)
+        assert np.array_equal(k, z[f"{n}_kpts"]) and np.array_equal(c, z[f"{n}_conf"])
+    rng = np.random.default_rng(11)
+    cases = [rng.choice(np.array([0.0, 0.02, 0.3, 0.3, 0.7], np.float32), (64, 96)),        # dense ties
+             np.full((40, 56), 0.5, np.float32),                                             # all equal
+             np.zeros((32, 32), np.float32),                                                 # empty
+             rng.uniform(0.0, 1.0, (48, 80)).astype(np.float32),
+             rng.uniform(0.02, 0.9, (256, 320)).astype(np.float32)]                          # > 65535 candidates
+    cases[3][:, 0] = 0.95; cases[3][:, -1] = 0.9                                             # strong columns at both edges
+    for prob in cases:
+        for max_num in (7, 200):
+            k, c = nms2_c.get_keypoints(prob, 0.015, max_num)
+            rk, rc = fr.get_keypoints(prob, 0.015, max_num)
+            assert np.array_equal(k, rk) and np.array_equal(c, rc)
+
+
+def test_pcm_oracle_clique_heuristic_and_consistency():
+    """oracle/pcm_ref.py: (a) the restated FMC::maxCliqueHeu returns a clique and, on small random graphs, one as large as
+    the exact maximum clique in most cases (it is a heuristic: never larger, always a clique); (b) the pairwise consistency
+    test separates inliers from gross outliers on the synthetic loop edges, is symmetric under storing a loop b -> a, and
+    never links edges of different drone pairs."""
+    from oracle import pcm_ref as pr
+    rng = np.random.default_rng(0)
+    hits = 0
+    for trial in range(30):
+        n = int(rng.integers(5, 13))
+        a = (rng.uniform(size=(n, n)) < 0.55).astype(np.uint8)
+        a = np.triu(a, 1); a = a + a.T
+        clique, size = pr.max_clique_heu(a)
+        assert size == len(clique) and len(set(clique)) == len(clique)
+        assert all(a[u, v] for i, u in enumerate(clique) for v in clique[i + 1:]), "heuristic returned a non-clique"
+        exact = pr.max_clique_exact(a)
+        assert size <= exact
+        hits += size == exact
+    assert hits >= 20
+    edges = synth.pcm_edges(40, 0.35, 3, other_pair=4)
+    clique, adj, size = pr.pcm(edges, 15.0, 1e-4, 1e-5)
+    inl = np.array([e["inlier"] for e in edges])
+    assert size >= 0.5 * inl.sum() and all(edges[i]["inlier"] for i in clique)
+    pair = np.array([{e["id_a"], e["id_b"]} == {1, 2} for e in edges])
+    assert adj[np.ix_(pair, ~pair)].sum() == 0 and adj[np.ix_(~pair, pair)].sum() == 0    # across drone pairs: never consistent
+    assert np.array_equal(adj, adj.T) and adj.diagonal().sum() == 0
+    # a loop stored b -> a (same_robot_pair == 2, :214-224): with exact data the error pose is the identity in either statement
+    e, other = dict(edges[0]), dict(edges[1])
+    for x in (e, other):
+        x["rel"] = pr.pose_mul(pr.pose_inv(x["odom_a"]), x["odom_b"])
+    flipped = dict(id_a=e["id_b"], id_b=e["id_a"], rel=pr.pose_inv(e["rel"]), cov=e["cov"], odom_a=e["odom_b"],
+                   odom_b=e["odom_a"], len_a=e["len_b"], len_b=e["len_a"])
+    if pr.same_robot_pair(e, other):
+        assert pr.pair_smd(e, other, 1e-4, 1e-5) < 1e-18 and pr.pair_smd(flipped, other, 1e-4, 1e-5) < 1e-18
