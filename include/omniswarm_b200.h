@@ -286,6 +286,55 @@ osb_status osb_homography_ransac_dev(const float* src_dev, const float* dst_dev,
                                      int32_t* winner_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Relative pose of a loop candidate (second half) -- replaces LoopDetector::compute_relative_pose
+ *   (swarm_loop/src/loop_detector.cpp:355-413: cv::solvePnPRansac(matched_3d_now, matched_2d_norm_old, K = I, iterations
+ *   100 / 1000 in init mode, reprojection error 3), PnPRestoCamPose, DeltaPose, RPerror :338-351, pnp_result_verify :317-336)
+ *   and LoopDetector::check_loop_odometry_consistency (:294-315): everything between the matched landmarks and the LoopEdge.
+ * pts3d [n_cand][max_n][3] = matched_3d_now (landmarks in the NEW drone's body frame), pts2d [n_cand][max_n][2] =
+ *   matched_2d_norm_old (normalised coordinates in the OLD camera), n [n_cand] valid counts, max_n <= 1024.
+ * OpenCV's RANSAC is randomised; this one is deterministic in (points, seed, prior): hypothesis h fits 4 hashed
+ *   correspondences by a fixed-schedule Levenberg-Marquardt started from `prior` (the odometry prediction the reference
+ *   computes and leaves unused, initial_old_cam_pose :377-382), the first hypothesis with the most inliers
+ *   (reprojection error^2 <= thresh^2, no cheirality test, as cv::projectPoints) wins, and the pose is the LM minimiser over
+ *   its inliers -- the definition of solvePnPRansac's result (oracle/pnp_ref.py, pinned against cv2.solvePnPRansac).
+ * Poses are 7 doubles (x y z, qw qx qy qz); Swarm::Pose / DeltaPose / quat2eulers are defined in oracle/pnp_ref.py
+ *   (swarm_msgs is not in the reference tree). */
+typedef struct {
+  int32_t iterations;            /* 100, or 1000 in init mode (:385-391) */
+  float reproj_thresh;           /* 3 (:393) */
+  uint32_t seed;
+  int32_t is_4dof;               /* DeltaPose(..., is_4dof) (:403) */
+  int32_t min_loop_num;          /* MIN_LOOP_NUM, or INIT_MODE_MIN_LOOP_NUM in init mode (:328-332) */
+  int32_t same_drone;            /* 1: drone_id_a == drone_id_b, run the odometry-consistency check (:294-298) */
+  double rperr_thres;            /* RPERR_THRES */
+  double accept_loop_yaw_rad;    /* ACCEPT_LOOP_YAW_RAD */
+  double max_loop_dis;           /* MAX_LOOP_DIS */
+  double odometry_consistency_threshold;
+  double prior[7];               /* initial (R, t) guess, x_cam_old = R X_now + t: (drone_pose_now^-1 drone_pose_old extrinsic)^-1 */
+  double extrinsic[7];           /* old camera in the old drone's body frame */
+  double drone_pose_now[7];
+  double drone_pose_old[7];
+  double odom_rel[7];            /* same_drone: ego-motion between the two stamps (get_relative_pose_by_ts) */
+  double odom_edge_cov[36];      /* same_drone: odometry covariance + edge covariance, 6x6 row-major (:303) */
+} osb_pnp_params;
+typedef struct {
+  int32_t pnp_success;           /* a model with >= 4 inliers was found */
+  int32_t n_inliers;
+  int32_t winner;                /* winning hypothesis, -1 if none */
+  int32_t verified;              /* pnp_result_verify (:317-336) */
+  int32_t odometry_consistent;   /* check_loop_odometry_consistency (:294-315); 1 for inter-drone loops */
+  int32_t reserved;
+  double rperr;                  /* RPerror (:338-351) */
+  double md;                     /* squared Mahalanobis distance of the odometry check */
+  double pose_cam[7];            /* (t, q) of the PnP solution: x_cam_old = R X_now + t */
+  double dp_old_to_new[4];       /* DP_old_to_new: x y z yaw -- the LoopEdge's relative pose */
+} osb_pnp_result;
+osb_status osb_pnp_ransac(const float* pts3d, const float* pts2d, const int32_t* n, int n_cand, int max_n,
+                          const osb_pnp_params* params, uint8_t* mask /*[n_cand][max_n]*/, osb_pnp_result* results);
+osb_status osb_pnp_ransac_dev(const float* pts3d_dev, const float* pts2d_dev, const int32_t* n_dev, int n_cand, int max_n,
+                              const osb_pnp_params* params_dev, uint8_t* mask_dev, osb_pnp_result* results_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Keyframe front-end -- the per-keyframe pipeline of LoopCam::on_flattened_images (loop_cam.cpp:178-229 ->
  *   generate_stereo_image_descriptor :341-523) followed by LoopDetector::on_image_recv's database work
  *   (loop_detector.cpp:89-104,150-287) and compute_correspond_features' matcher (loop_detector.cpp:539-587),

@@ -17,48 +17,12 @@
 // reference tree: they are defined in oracle/pcm_ref.py and restated here (covariances and ego-motion poses are inputs).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "pose_algebra.cuh"
 
 namespace osb {
 
 constexpr int PCM_MAX_N = 4096;
 constexpr int PCM_MAX_W = PCM_MAX_N / 32;
-
-struct PoseD { double t[3]; double q[4]; };   // translation, unit quaternion (w, x, y, z)
-
-__device__ __forceinline__ void q_mul(const double* a, const double* b, double* o) {
-  o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
-  o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
-  o[2] = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
-  o[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
-}
-__device__ __forceinline__ void q_rot(const double* q, const double* v, double* o) {    // v + 2 w (u x v) + 2 u x (u x v)
-  const double cx = q[2] * v[2] - q[3] * v[1], cy = q[3] * v[0] - q[1] * v[2], cz = q[1] * v[1] - q[2] * v[0];
-  const double dx = q[2] * cz - q[3] * cy, dy = q[3] * cx - q[1] * cz, dz = q[1] * cy - q[2] * cx;
-  o[0] = v[0] + 2.0 * (q[0] * cx + dx);
-  o[1] = v[1] + 2.0 * (q[0] * cy + dy);
-  o[2] = v[2] + 2.0 * (q[0] * cz + dz);
-}
-__device__ __forceinline__ PoseD pose_mul(const PoseD& a, const PoseD& b) {
-  PoseD o;
-  double r[3];
-  q_rot(a.q, b.t, r);
-  o.t[0] = a.t[0] + r[0]; o.t[1] = a.t[1] + r[1]; o.t[2] = a.t[2] + r[2];
-  q_mul(a.q, b.q, o.q);
-  return o;
-}
-__device__ __forceinline__ PoseD pose_inv(const PoseD& a) {
-  PoseD o;
-  o.q[0] = a.q[0]; o.q[1] = -a.q[1]; o.q[2] = -a.q[2]; o.q[3] = -a.q[3];
-  double r[3];
-  q_rot(o.q, a.t, r);
-  o.t[0] = -r[0]; o.t[1] = -r[1]; o.t[2] = -r[2];
-  return o;
-}
-__device__ __forceinline__ PoseD load_pose(const double* p) {
-  PoseD o;
-  o.t[0] = p[0]; o.t[1] = p[1]; o.t[2] = p[2]; o.q[0] = p[3]; o.q[1] = p[4]; o.q[2] = p[5]; o.q[3] = p[6];
-  return o;
-}
 
 // squared Mahalanobis consistency error of (e1 = the LATER loop, e2 = the earlier one); +inf for another drone pair
 __device__ double pcm_pair_smd(const osb_loop_edge* __restrict__ e1, const osb_loop_edge* __restrict__ e2, double pos_cov,
@@ -78,39 +42,15 @@ __device__ double pcm_pair_smd(const osb_loop_edge* __restrict__ e1, const osb_l
   const PoseD odom_b = pose_mul(pose_inv(load_pose(e1->odom_b)), load_pose(b2));
   const double dl = fabs(la2 - e1->len_a) + fabs(lb2 - e1->len_b);
   const PoseD err = pose_mul(pose_mul(pose_mul(odom_a, p2), pose_inv(odom_b)), pose_inv(load_pose(e1->rel_pose)));   // :227
-  // log map: [translation ; rotation vector]
-  double v[6] = {err.t[0], err.t[1], err.t[2], 0, 0, 0};
-  {
-    const double s = err.q[0] < 0 ? -1.0 : 1.0;
-    const double w = s * err.q[0], x = s * err.q[1], y = s * err.q[2], z = s * err.q[3];
-    const double n = sqrt(x * x + y * y + z * z);
-    const double k = n < 1e-12 ? 2.0 : 2.0 * atan2(n, w) / n;
-    v[3] = k * x; v[4] = k * y; v[5] = k * z;
-  }
+  double v[6];
+  pose_log(err, v);
   // C = cov_1 + cov_2 + (|dlen_a| + |dlen_b|) * diag(pos x3, ang x3); smd = v^T C^-1 v by an unpivoted Cholesky
-  double L[6][6];
+  double C[36];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    double s = e1->cov[j * 6 + j] + e2->cov[j * 6 + j] + dl * (j < 3 ? pos_cov : ang_cov);
-    for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
-    if (!(s > 0.0)) return INFINITY;
-    L[j][j] = sqrt(s);
+  for (int i = 0; i < 36; ++i) C[i] = e1->cov[i] + e2->cov[i];
 #pragma unroll
-    for (int i = j + 1; i < 6; ++i) {
-      double c = e1->cov[i * 6 + j] + e2->cov[i * 6 + j];
-      for (int k = 0; k < j; ++k) c -= L[i][k] * L[j][k];
-      L[i][j] = c / L[j][j];
-    }
-  }
-  double smd = 0.0, y[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    double c = v[i];
-    for (int k = 0; k < i; ++k) c -= L[i][k] * y[k];
-    y[i] = c / L[i][i];
-    smd += y[i] * y[i];
-  }
-  return smd;
+  for (int j = 0; j < 6; ++j) C[j * 6 + j] += dl * (j < 3 ? pos_cov : ang_cov);
+  return smd6(v, C);
 }
 
 // adjacency bit matrix: thread = (row i, word w) -> bits of columns 32w .. 32w+31

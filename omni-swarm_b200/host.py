@@ -431,6 +431,38 @@ class KeyframeFrontend:
         _l.check(self._lib.osb_frontend_db_set_geometry(self._h, int(remote), first_row, k.shape[0], _l.ptr(k), _l.ptr(sm)))
 
 
+def pnp_ransac(cases, max_n: int | None = None):
+    """LoopDetector::compute_relative_pose + check_loop_odometry_consistency (loop_detector.cpp:294-413) for a batch of loop
+    candidates.  cases: list of dicts with X [n,3], uv [n,2] and the osb_pnp_params fields (prior, extrinsic, drone_pose_now,
+    drone_pose_old [7]; iterations, thresh, seed, is_4dof, min_loop_num, rperr_thres, accept_loop_yaw_rad, max_loop_dis;
+    optional same_drone, odom_rel [7], cov [6,6], odometry_consistency_threshold) -> list of (mask uint8 [n], PnpResult)."""
+    lib = _l.load()
+    nc = len(cases)
+    if max_n is None:
+        max_n = max(1, max(len(c["X"]) for c in cases))
+    p3 = np.zeros((nc, max_n, 3), np.float32); p2 = np.zeros((nc, max_n, 2), np.float32)
+    n = np.zeros(nc, np.int32)
+    prm = (_l.PnpParams * nc)()
+    for i, c in enumerate(cases):
+        k = len(c["X"]); n[i] = k
+        if k:
+            p3[i, :k] = c["X"]; p2[i, :k] = c["uv"]
+        p = prm[i]
+        p.iterations, p.reproj_thresh, p.seed = int(c.get("iterations", 100)), float(c.get("thresh", 3.0)), int(c.get("seed", 0))
+        p.is_4dof, p.min_loop_num, p.same_drone = int(c.get("is_4dof", 1)), int(c.get("min_loop_num", 15)), int(c.get("same_drone", 0))
+        p.rperr_thres, p.accept_loop_yaw_rad = float(c.get("rperr_thres", 0.1)), float(c.get("accept_loop_yaw_rad", 0.8))
+        p.max_loop_dis = float(c.get("max_loop_dis", 5.0))
+        p.odometry_consistency_threshold = float(c.get("odometry_consistency_threshold", 10.0))
+        for name in ("prior", "extrinsic", "drone_pose_now", "drone_pose_old"):
+            getattr(p, name)[:] = [float(x) for x in c[name]]
+        p.odom_rel[:] = [float(x) for x in c.get("odom_rel", [0, 0, 0, 1, 0, 0, 0])]
+        p.odom_edge_cov[:] = [float(x) for x in np.asarray(c.get("cov", np.eye(6)), np.float64).reshape(-1)]
+    mask = np.zeros((nc, max_n), np.uint8)
+    res = (_l.PnpResult * nc)()
+    _l.check(lib.osb_pnp_ransac(_l.ptr(p3), _l.ptr(p2), _l.ptr(n), nc, max_n, prm, _l.ptr(mask), res))
+    return [(mask[i, :n[i]].copy(), res[i]) for i in range(nc)]
+
+
 def pcm_outlier_rejection(edges, pcm_thres: float, odom_pos_cov_per_m: float, odom_ang_cov_per_m: float,
                           want_matrices: bool = False):
     """SwarmLocalOutlierRejection::OutlierRejectionLoopEdgesPCM (swarm_outlier_rejection.cpp:173-297) for the loop edges of

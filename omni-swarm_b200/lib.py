@@ -62,6 +62,21 @@ class LoopEdge(C.Structure):
                 ("odom_a", C.c_double * 7), ("odom_b", C.c_double * 7), ("len_a", C.c_double), ("len_b", C.c_double)]
 
 
+class PnpParams(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("reproj_thresh", C.c_float), ("seed", C.c_uint32), ("is_4dof", C.c_int32),
+                ("min_loop_num", C.c_int32), ("same_drone", C.c_int32), ("rperr_thres", C.c_double),
+                ("accept_loop_yaw_rad", C.c_double), ("max_loop_dis", C.c_double),
+                ("odometry_consistency_threshold", C.c_double), ("prior", C.c_double * 7), ("extrinsic", C.c_double * 7),
+                ("drone_pose_now", C.c_double * 7), ("drone_pose_old", C.c_double * 7), ("odom_rel", C.c_double * 7),
+                ("odom_edge_cov", C.c_double * 36)]
+
+
+class PnpResult(C.Structure):
+    _fields_ = [("pnp_success", C.c_int32), ("n_inliers", C.c_int32), ("winner", C.c_int32), ("verified", C.c_int32),
+                ("odometry_consistent", C.c_int32), ("reserved", C.c_int32), ("rperr", C.c_double), ("md", C.c_double),
+                ("pose_cam", C.c_double * 7), ("dp_old_to_new", C.c_double * 4)]
+
+
 class FrontendConfig(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("n_dirs", C.c_int32), ("max_num", C.c_int32),
                 ("sp_thres", C.c_float), ("self_id", C.c_int32), ("db_capacity", C.c_int32),
@@ -137,6 +152,8 @@ _SIG = {
     "osb_frontend_db_reset": (C.c_int, [_P]),
     "osb_frontend_db_load": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P]),
     "osb_frontend_db_set_geometry": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, _P]),
+    "osb_pnp_ransac": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "osb_pnp_ransac_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "osb_pcm": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P]),
     "osb_pcm_dev": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P, _P]),
     "osb_swarm_unique_id": (C.c_int, [_P]),

@@ -426,3 +426,47 @@ def pcm_edges(n: int = 60, outlier_frac: float = 0.3, seed: int = 0, flip_frac: 
         edges.append(e)
     order = rng.permutation(len(edges))
     return [edges[i] for i in order]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# 3-D / 2-D correspondences of one loop candidate for the PnP stage (second half)
+# ----------------------------------------------------------------------------------------------------------------
+def pnp_case(n: int = 200, outlier_frac: float = 0.25, seed: int = 0, noise: float = 0.002, yaw: float = 0.3,
+             prior_error: float = 0.15):
+    """n landmarks in the NEW drone's odometry frame (matched_3d_now) seen by the OLD camera (matched_2d_norm_old, normalised
+    coordinates, K = I): the old drone sits ~1.5 m away with a yaw offset, its camera looks along body +x (extrinsic
+    rotation of the usual camera convention).  Returns dict(X [n,3] f32, uv [n,2] f32, inlier [n] bool, pose_true (t,q) with
+    x_cam_old = R X + t, prior (t,q) = the truth disturbed by `prior_error` (what odometry would predict), extrinsic,
+    drone_pose_now, drone_pose_old)."""
+    pa = _PoseAlgebra
+    rng = np.random.default_rng(seed + 9000)
+    # camera-in-body extrinsic: camera z = body x, camera x = -body y, camera y = -body z
+    Rcb = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
+
+    def quat_from_R(R):
+        w = np.sqrt(max(0.0, 1.0 + R[0, 0] + R[1, 1] + R[2, 2])) / 2.0
+        return np.array([w, (R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w)])
+
+    extrinsic = np.concatenate([[0.05, 0.0, 0.03], quat_from_R(Rcb)])
+    # everything the PnP sees lives in the NEW drone's odometry (world) frame Wn: its own pose, the landmarks
+    # (matched_3d_now) and therefore the solved old-camera pose; the OLD drone reports its pose in its own gravity-aligned
+    # frame Wo, which differs from Wn by a yaw and a translation
+    drone_pose_now = np.concatenate([[2.0, -1.0, 1.2], _quat_from_rotvec(np.array([0.01, -0.02, 0.7]))])
+    d_old_in_new = np.concatenate([[-1.2, 0.6, 0.1], _quat_from_rotvec(np.array([0.0, 0.0, yaw]))])
+    old_in_wn = pa.pose_mul(drone_pose_now, d_old_in_new)
+    wo_from_wn = np.concatenate([[4.0, 2.5, -0.4], _quat_from_rotvec(np.array([0.0, 0.0, -1.1]))])
+    drone_pose_old = pa.pose_mul(wo_from_wn, old_in_wn)
+    cam_old_in_new = pa.pose_mul(old_in_wn, extrinsic)                # old camera pose in Wn
+    pose_true = pa.pose_inv(cam_old_in_new)                            # x_cam_old = R X + t
+    # landmarks in front of the old camera, expressed in Wn
+    Pc = np.stack([rng.uniform(-2.5, 2.5, n), rng.uniform(-1.5, 1.5, n), rng.uniform(2.0, 9.0, n)], 1)
+    X = np.stack([pa.q_rot(cam_old_in_new[3:], p) + cam_old_in_new[:3] for p in Pc])
+    uv = Pc[:, :2] / Pc[:, 2:3] + rng.normal(0, noise, (n, 2))
+    inlier = rng.uniform(size=n) >= outlier_frac
+    uv[~inlier] = rng.uniform(-1.2, 1.2, ((~inlier).sum(), 2))
+    far = np.linalg.norm(uv - Pc[:, :2] / Pc[:, 2:3], axis=1) < 0.2
+    inlier = inlier | far                                              # a random "outlier" that happens to fit is an inlier
+    prior = pa.pose_mul(np.concatenate([rng.normal(0, prior_error, 3), _quat_from_rotvec(rng.normal(0, prior_error * 0.5, 3))]),
+                        pose_true)
+    return dict(X=X.astype(np.float32), uv=uv.astype(np.float32), inlier=inlier, pose_true=pose_true, prior=prior,
+                extrinsic=extrinsic, drone_pose_now=drone_pose_now, drone_pose_old=drone_pose_old)

@@ -276,3 +276,37 @@ def test_pcm_oracle_clique_heuristic_and_consistency():
                    odom_b=e["odom_a"], len_a=e["len_b"], len_b=e["len_a"])
     if pr.same_robot_pair(e, other):
         assert pr.pair_smd(e, other, 1e-4, 1e-5) < 1e-18 and pr.pair_smd(flipped, other, 1e-4, 1e-5) < 1e-18
+
+
+def test_pnp_oracle_pinned_against_opencv():
+    """oracle/pnp_ref.py (deterministic RANSAC + LM, the definition of cv::solvePnPRansac's result) against the real OpenCV
+    on correspondences whose outliers are gross: same inlier set, same pose.  Also the reference's own setting (reprojection
+    error 3 in NORMALISED coordinates, loop_detector.cpp:393): every correspondence is an inlier and the pose is the
+    least-squares fit over all of them -- cv2 agrees on that too."""
+    import cv2
+    from oracle import pnp_ref as pn, pcm_ref as pr
+    for seed, out in ((0, 0.25), (1, 0.4), (2, 0.0)):
+        c = synth.pnp_case(160, out, seed)
+        res = pn.pnp_ransac(c["X"], c["uv"], c["prior"], iterations=100, thresh=0.03, seed=seed)
+        assert res["success"] and np.array_equal(res["mask"].astype(bool), c["inlier"])
+        ok, rvec, tvec, inl = cv2.solvePnPRansac(c["X"].astype(np.float64), c["uv"].astype(np.float64), np.eye(3), None,
+                                                 iterationsCount=100, reprojectionError=0.03, confidence=0.99)
+        m = np.zeros(len(c["X"]), bool); m[inl.ravel()] = True
+        assert ok and np.array_equal(m, res["mask"].astype(bool))
+        R, _ = cv2.Rodrigues(rvec)
+        Ro = np.stack([pr.q_rot(res["pose"][3:], e) for e in np.eye(3)], 1)
+        assert np.abs(R - Ro).max() < 1e-6 and np.abs(tvec.ravel() - res["pose"][:3]).max() < 1e-6
+        assert np.abs(res["pose"][:3] - c["pose_true"][:3]).max() < 0.02
+    c = synth.pnp_case(120, 0.0, 5)
+    res = pn.pnp_ransac(c["X"], c["uv"], c["prior"], iterations=100, thresh=3.0, seed=0)
+    ok, rvec, tvec, inl = cv2.solvePnPRansac(c["X"].astype(np.float64), c["uv"].astype(np.float64), np.eye(3), None,
+                                             iterationsCount=100, reprojectionError=3.0, confidence=0.99)
+    assert res["n_inliers"] == 120 == len(inl) and np.abs(tvec.ravel() - res["pose"][:3]).max() < 1e-6
+    # the acceptance chain on the true geometry: small roll/pitch error, the loop's 4-DoF pose = old drone -> new drone
+    prm = dict(extrinsic=c["extrinsic"], drone_pose_now=c["drone_pose_now"], drone_pose_old=c["drone_pose_old"], is_4dof=1,
+               min_loop_num=15, rperr_thres=0.1, accept_loop_yaw_rad=0.8, max_loop_dis=5.0)
+    v = pn.loop_from_pnp(res, prm)
+    assert v["verified"] and v["rperr"] < 0.01
+    old_in_wn = pr.pose_mul(pr.pose_inv(res["pose"]), pr.pose_inv(c["extrinsic"]))      # old drone in the new drone's frame
+    d = pn.delta_pose(old_in_wn, c["drone_pose_now"], True)
+    assert np.abs(v["dp"][:3] - d[:3]).max() < 1e-9 and abs(v["dp"][3] - 0.3 * -1) < 0.02   # yaw(new) - yaw(old) = -0.3
