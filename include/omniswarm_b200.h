@@ -286,6 +286,30 @@ osb_status osb_homography_ransac_dev(const float* src_dev, const float* dst_dev,
                                      int32_t* winner_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Keypoints -> 3-D landmarks + landmarks_flag -- replaces the per-keypoint loops of
+ *   LoopCam::generate_stereo_image_descriptor (swarm_loop/src/loop_cam.cpp:393-432: liftProjective, triangulatePoint :73-106,
+ *   err <= TRIANGLE_THRES, in front of the up camera) and generate_gray_depth_image_descriptor (:276-302: depth look-up in
+ *   mm, DEPTH_NEAR_THRES < dep < DEPTH_FAR_THRES, lift through pose_cam).  Arrays are [n_dirs][max_n][...]; intrinsics =
+ *   fx fy cx cy of the distortion-free flattened pinhole (HOST pointer in both variants); poses are 7 doubles
+ *   (x y z, qw qx qy qz), already pose_drone * extrinsic; nothing is lifted when a direction has <= accept_min_3d_pts
+ *   keypoints (:385-391, :267).  stereo_match[d][i] = index of the down keypoint matched to up keypoint i, or -1. */
+osb_status osb_stereo_lift(const float* kp_up, const float* kp_down, const int32_t* stereo_match, const int32_t* n_up,
+                           const int32_t* n_down, int n_dirs, int max_n, const double* intrinsics, const double* pose_up,
+                           const double* pose_down, double triangle_thres, int accept_min_3d_pts, float* pts3d,
+                           uint8_t* flag_up, uint8_t* flag_down);
+osb_status osb_stereo_lift_dev(const float* kp_up_dev, const float* kp_down_dev, const int32_t* stereo_match_dev,
+                               const int32_t* n_up_dev, const int32_t* n_down_dev, int n_dirs, int max_n,
+                               const double* intrinsics, const double* pose_up_dev, const double* pose_down_dev,
+                               double triangle_thres, int accept_min_3d_pts, float* pts3d_dev, uint8_t* flag_up_dev,
+                               uint8_t* flag_down_dev, void* stream);
+osb_status osb_depth_lift(const float* kp, const int32_t* n, int n_dirs, int max_n, const uint16_t* depth_mm, int height,
+                          int width, const double* intrinsics, const double* pose_cam, double near_thres, double far_thres,
+                          int accept_min_3d_pts, float* pts3d, uint8_t* flag);
+osb_status osb_depth_lift_dev(const float* kp_dev, const int32_t* n_dev, int n_dirs, int max_n, const uint16_t* depth_mm_dev,
+                              int height, int width, const double* intrinsics, const double* pose_cam_dev, double near_thres,
+                              double far_thres, int accept_min_3d_pts, float* pts3d_dev, uint8_t* flag_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Relative pose of a loop candidate (second half) -- replaces LoopDetector::compute_relative_pose
  *   (swarm_loop/src/loop_detector.cpp:355-413: cv::solvePnPRansac(matched_3d_now, matched_2d_norm_old, K = I, iterations
  *   100 / 1000 in init mode, reprojection error 3), PnPRestoCamPose, DeltaPose, RPerror :338-351, pnp_result_verify :317-336)
@@ -357,9 +381,13 @@ typedef struct {
   float local_desc[OSB_MAX_DIRS][OSB_MAX_KPTS][OSB_FEATURE_DESC_SIZE]; /* feature_descriptor (up image) */
   float kpts[OSB_MAX_DIRS][OSB_MAX_KPTS][2];                           /* landmarks_2d (up image) */
   int32_t stereo_match[OSB_MAX_DIRS][OSB_MAX_KPTS];                    /* down-image keypoint index matched to each
-                                                                          up keypoint by the cross-check matcher, or -1
-                                                                          (input of the host triangulation that sets
-                                                                          landmarks_flag, loop_cam.cpp:405-454) */
+                                                                          up keypoint by the cross-check matcher, or -1 */
+  float landmarks_3d[OSB_MAX_DIRS][OSB_MAX_KPTS][3];                   /* landmarks_3d (loop_cam.cpp:405-432): triangulated
+                                                                          in the drone's odometry frame; zero without flag */
+  int32_t landmarks_flag[OSB_MAX_DIRS][OSB_MAX_KPTS];                  /* landmarks_flag.  With osb_frontend_set_cameras: 1
+                                                                          iff the stereo pair triangulates (err <=
+                                                                          TRIANGLE_THRES, in front of the camera, :423);
+                                                                          without cameras: stereo_match >= 0, a superset */
 } osb_keyframe_record;
 
 typedef struct {
@@ -437,6 +465,14 @@ osb_status osb_frontend_db_reset(osb_frontend* h);
  * [n][4096] and optional local descriptors [n][max_num][64] + counts [n] (HOST). */
 osb_status osb_frontend_db_load(osb_frontend* h, int remote, int64_t n, const float* global_desc,
                                 const float* local_desc, const int32_t* n_kpts);
+/* Stereo triangulation inside extract: with the cameras set, every keyframe's record carries the
+ * reference's landmarks_3d / landmarks_flag (loop_cam.cpp:393-432) -- up/down keypoints lifted through the distortion-free
+ * pinhole of the flattened images (intrinsics fx fy cx cy), triangulated between pose_drone * left_extrinsic[d] and
+ * pose_drone * right_extrinsic[d] (7 doubles each: x y z, qw qx qy qz), kept iff err <= triangle_thres and the point is in
+ * front of the up camera.  set_drone_pose gives the pose_drone of the NEXT extract (msg.pose_drone, :394). */
+osb_status osb_frontend_set_cameras(osb_frontend* h, const double* intrinsics /*[4]*/, const double* left_extrinsics /*[n_dirs][7]*/,
+                                    const double* right_extrinsics /*[n_dirs][7]*/, double triangle_thres);
+osb_status osb_frontend_set_drone_pose(osb_frontend* h, const double* pose_drone /*[7]*/);
 /* landmarks_2d [n][max_num][2] and stereo_match [n][max_num] (>= 0 <=> landmarks_flag) of rows loaded with
  * osb_frontend_db_load -- what the geometric filter reads when such a row is the loop hit */
 osb_status osb_frontend_db_set_geometry(osb_frontend* h, int remote, int64_t first_row, int64_t n, const float* kpts,

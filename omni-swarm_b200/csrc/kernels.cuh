@@ -69,6 +69,11 @@ osb_status nhwc_to_nchw(const float* in, float* out, int B, int C, int h, int w,
 
 // ---- geom.cu ---------------------------------------------------------------------------------------------------
 // homography-RANSAC inlier masks of n_pairs correspondence sets ([n_pairs][max_n] float2 old / new points)
+// stereo triangulation of the matched up/down keypoints of n_dirs directions (lift.cu; loop_cam.cpp:393-432)
+osb_status stereo_lift_device(const float* kp_up, const float* kp_down, const int32_t* match, const int32_t* n_up,
+                              const int32_t* n_down, int n_dirs, int max_n, const double* K, const double* pose_up,
+                              const double* pose_down, double triangle_thres, int min_pts, float* pts3d, uint8_t* flag_up,
+                              uint8_t* flag_down, cudaStream_t st);
 osb_status homography_ransac_device(const float* src_dev, const float* dst_dev, const int32_t* n_dev, int n_pairs, int max_n,
                                     float thresh, uint32_t seed, uint8_t* mask_dev, int32_t* n_inl_dev, int32_t* winner_dev,
                                     cudaStream_t st, unsigned int* scratch /* 2 * n_pairs words, zero between launches */);

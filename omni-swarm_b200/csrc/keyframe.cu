@@ -28,7 +28,7 @@ struct DbStore {
   float* rows = nullptr;       // [cap][4096]
   float* ldesc = nullptr;      // [cap][max_num][64]
   float* kpts = nullptr;       // [cap][max_num][2]   landmarks_2d of the row (geometric filter)
-  int32_t* smatch = nullptr;   // [cap][max_num]      stereo_match of the row: >= 0 <=> landmarks_flag
+  int32_t* smatch = nullptr;   // [cap][max_num]      landmarks_flag of the row (non-zero = the landmark has a 3-D point)
   int32_t* nk = nullptr;       // [cap]
   int32_t* row_frame = nullptr;// [cap]
   int32_t* row_dir = nullptr;  // [cap]
@@ -59,7 +59,8 @@ __global__ void fe_blank_kernel(uint8_t* __restrict__ img, int H, int W, int n_i
 __global__ void fe_pack_kernel(osb_keyframe_record* __restrict__ rec, int drone_id, int msg_id, int n_dirs, int max_num,
                                const int32_t* __restrict__ nk, const float* __restrict__ kpts,
                                const float* __restrict__ desc, const int32_t* __restrict__ stereo_map,
-                               int accept_min_3d_pts) {
+                               int accept_min_3d_pts, const float* __restrict__ l3d /*[n_dirs][max_num][3] or null*/,
+                               const uint8_t* __restrict__ lflag /*[n_dirs][max_num] or null*/) {
   const int d = blockIdx.x;
   const int tid = threadIdx.x;
   if (d >= n_dirs) {          // unused directions: zero counts
@@ -79,7 +80,13 @@ __global__ void fe_pack_kernel(osb_keyframe_record* __restrict__ rec, int drone_
     rec->kpts[d][i][0] = ok ? kpts[((size_t)d * max_num + i) * 2] : 0.f;
     rec->kpts[d][i][1] = ok ? kpts[((size_t)d * max_num + i) * 2 + 1] : 0.f;
     // the stereo match is skipped when landmarks_2d.size() <= ACCEPT_MIN_3D_PTS (loop_cam.cpp:385-391)
-    rec->stereo_match[d][i] = (ok && n > accept_min_3d_pts) ? stereo_map[(size_t)d * max_num + i] : -1;
+    const int sm = (ok && n > accept_min_3d_pts) ? stereo_map[(size_t)d * max_num + i] : -1;
+    rec->stereo_match[d][i] = sm;
+    // landmarks_flag / landmarks_3d (loop_cam.cpp:405-432): triangulated on the device when the cameras are known
+    const bool fl = ok && (lflag ? lflag[(size_t)d * max_num + i] != 0 : sm >= 0);
+    rec->landmarks_flag[d][i] = fl ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rec->landmarks_3d[d][i][k] = (fl && l3d) ? l3d[((size_t)d * max_num + i) * 3 + k] : 0.f;
   }
 }
 
@@ -146,7 +153,7 @@ __global__ void fe_copy_rows_kernel(const osb_keyframe_record* __restrict__ recs
   int32_t* sm = (is_remote ? r_sm : l_sm) + (size_t)row * max_num;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     kp[2 * i] = rec->kpts[d][i][0]; kp[2 * i + 1] = rec->kpts[d][i][1];
-    sm[i] = rec->stereo_match[d][i];
+    sm[i] = rec->landmarks_flag[d][i];
   }
   if (threadIdx.x == 0) nk[row] = n;
 }
@@ -264,7 +271,7 @@ __global__ void fe_query_rule_kernel(QueryParams qp, const osb_keyframe_record* 
     else { qptr[slot] = p_rec; nq[slot] = n_rec; tptr[slot] = p_db; nt[slot] = n_db; }
     {   // 2-D landmarks and 3-D flags of the two sides, for the geometric filter (loop_detector.cpp:569-598)
       const float* k_rec = &rec->kpts[dir_rec][0][0];
-      const int32_t* f_rec = &rec->stereo_match[dir_rec][0];
+      const int32_t* f_rec = &rec->landmarks_flag[dir_rec][0];
       const float* k_db = (hit_remote ? r_kpts : l_kpts) + (size_t)row_db * qp.max_num * 2;
       const int32_t* f_db = (hit_remote ? r_sm : l_sm) + (size_t)row_db * qp.max_num;
       g_qk[slot] = swapped ? k_db : k_rec; g_tk[slot] = swapped ? k_rec : k_db; g_qflag[slot] = swapped ? f_db : f_rec;
@@ -288,7 +295,7 @@ fe_geo_gather_kernel(const osb_loop_result* __restrict__ res, const float* const
   int qi = 0, ti = 0;
   if (tid < n) {
     qi = res->match_new[slot][tid]; ti = res->match_old[slot][tid];
-    keep = g_qflag[slot][qi] >= 0;
+    keep = g_qflag[slot][qi] != 0;
   }
   const unsigned bal = __ballot_sync(0xffffffffu, keep);
   if (lane == 0) warp_cnt[warp] = __popc(bal);
@@ -355,6 +362,13 @@ struct osb_frontend {
   int32_t *d_g_kept = nullptr, *d_g_nkept = nullptr, *d_g_ninl = nullptr, *d_g_win = nullptr;
   uint8_t* d_g_mask = nullptr;
   unsigned int* d_g_scratch = nullptr;
+  // stereo triangulation (osb_frontend_set_cameras)
+  bool have_cameras = false;
+  double K[4] = {0, 0, 0, 0}, triangle_thres = 0.006;
+  double left_ext[OSB_MAX_DIRS][7], right_ext[OSB_MAX_DIRS][7], pose_drone[7] = {0, 0, 0, 1, 0, 0, 0};
+  double* d_cam_pose = nullptr;  // [2][n_dirs][7]: pose_drone * left / right extrinsics of the current keyframe
+  float* d_l3d = nullptr;        // [n_dirs][max_num][3]
+  uint8_t *d_lflag_up = nullptr, *d_lflag_down = nullptr;
   int32_t* d_assign = nullptr;   // [max_records][4]
   int max_records = 64;
   osb_keyframe_record* d_record = nullptr;   // used by process()
@@ -386,7 +400,7 @@ static osb_status dbstore_alloc(DbStore& s, int64_t cap, int max_num) {
   OSB_CUDA(cudaMalloc(&s.kpts, (size_t)cap * max_num * 2 * sizeof(float)));
   OSB_CUDA(cudaMalloc(&s.smatch, (size_t)cap * max_num * sizeof(int32_t)));
   OSB_CUDA(cudaMemset(s.kpts, 0, (size_t)cap * max_num * 2 * sizeof(float)));
-  OSB_CUDA(cudaMemset(s.smatch, 0, (size_t)cap * max_num * sizeof(int32_t)));   // rows loaded without geometry: every landmark flagged
+  OSB_CUDA(cudaMemset(s.smatch, 1, (size_t)cap * max_num * sizeof(int32_t)));   // rows loaded without geometry: every landmark flagged (non-zero)
   OSB_CUDA(cudaMalloc(&s.nk, cap * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&s.row_frame, cap * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&s.row_dir, cap * sizeof(int32_t)));
@@ -476,6 +490,10 @@ extern "C" osb_status osb_frontend_create(osb_frontend** out, const osb_frontend
   FE_CUDA(cudaMalloc(&h->d_q_nq, OSB_MAX_DIRS * sizeof(int32_t)));
   FE_CUDA(cudaMalloc(&h->d_q_nt, OSB_MAX_DIRS * sizeof(int32_t)));
   FE_CUDA(cudaMalloc(&h->d_assign, h->max_records * OSB_MAX_DIRS * sizeof(int32_t)));
+  FE_CUDA(cudaMalloc(&h->d_cam_pose, 2 * OSB_MAX_DIRS * 7 * sizeof(double)));
+  FE_CUDA(cudaMalloc(&h->d_l3d, (size_t)OSB_MAX_DIRS * mn * 3 * sizeof(float)));
+  FE_CUDA(cudaMalloc(&h->d_lflag_up, (size_t)OSB_MAX_DIRS * mn));
+  FE_CUDA(cudaMalloc(&h->d_lflag_down, (size_t)OSB_MAX_DIRS * mn));
   FE_CUDA(cudaMalloc(&h->d_record, sizeof(osb_keyframe_record)));
   FE_CUDA(cudaMalloc(&h->d_result, sizeof(osb_loop_result)));
   {
@@ -504,6 +522,7 @@ extern "C" osb_status osb_frontend_destroy(osb_frontend* h) {
   cudaFree(h->d_g_kept); cudaFree(h->d_g_nkept); cudaFree(h->d_g_ninl); cudaFree(h->d_g_win); cudaFree(h->d_g_mask); cudaFree(h->d_g_scratch);
   cudaFree(h->d_q_dist); cudaFree(h->d_dist_scratch); cudaFree(h->d_q_nq); cudaFree(h->d_q_nt); cudaFree(h->d_assign);
   cudaFree(h->d_record); cudaFree(h->d_result);
+  cudaFree(h->d_cam_pose); cudaFree(h->d_l3d); cudaFree(h->d_lflag_up); cudaFree(h->d_lflag_down);
   for (int i = 0; i < 9; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -514,6 +533,20 @@ extern "C" osb_status osb_frontend_destroy(osb_frontend* h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return OSB_OK;
+}
+
+// a * b for poses (x y z, qw qx qy qz), host side
+static void pose_compose_host(const double* a, const double* b, double* o) {
+  const double w = a[3], x = a[4], y = a[5], z = a[6];
+  const double cx = y * b[2] - z * b[1], cy = z * b[0] - x * b[2], cz = x * b[1] - y * b[0];
+  const double dx = y * cz - z * cy, dy = z * cx - x * cz, dz = x * cy - y * cx;
+  o[0] = a[0] + b[0] + 2.0 * (w * cx + dx);
+  o[1] = a[1] + b[1] + 2.0 * (w * cy + dy);
+  o[2] = a[2] + b[2] + 2.0 * (w * cz + dz);
+  o[3] = w * b[3] - x * b[4] - y * b[5] - z * b[6];
+  o[4] = w * b[4] + x * b[3] + y * b[6] - z * b[5];
+  o[5] = w * b[5] - x * b[6] + y * b[3] + z * b[4];
+  o[6] = w * b[6] + x * b[5] - y * b[4] + z * b[3];
 }
 
 static osb_status fe_extract_dev(osb_frontend* h, const uint8_t* img_dev /*[2*nd][H][W] up then down*/, int32_t msg_id,
@@ -556,8 +589,22 @@ static osb_status fe_extract_dev(osb_frontend* h, const uint8_t* img_dev /*[2*nd
   // stereo match up[d] <-> down[d] (loop_cam.cpp:388)
   if ((s = bf_match_device(nd, mn, mn, h->d_st_q, h->sp.d_nk, h->d_st_t, h->sp.d_nk + nd, h->d_dist_scratch,
                            h->d_st_qi, h->d_st_ti, h->d_st_dist, h->d_st_n, h->d_st_map, st)) != OSB_OK) return s;
+  if (h->have_cameras) {
+    // pose_up / pose_down = pose_drone * extrinsics (loop_cam.cpp:394-396), then the per-keypoint triangulation (:398-432)
+    double cam[2][OSB_MAX_DIRS][7];
+    for (int d = 0; d < nd; ++d) {
+      pose_compose_host(h->pose_drone, h->left_ext[d], cam[0][d]);
+      pose_compose_host(h->pose_drone, h->right_ext[d], cam[1][d]);
+    }
+    OSB_CUDA(cudaMemcpyAsync(h->d_cam_pose, cam[0], (size_t)nd * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
+    OSB_CUDA(cudaMemcpyAsync(h->d_cam_pose + OSB_MAX_DIRS * 7, cam[1], (size_t)nd * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((s = stereo_lift_device(h->sp.d_kpts, h->sp.d_kpts + (size_t)nd * mn * 2, h->d_st_map, h->sp.d_nk, h->sp.d_nk + nd, nd, mn,
+                                h->K, h->d_cam_pose, h->d_cam_pose + OSB_MAX_DIRS * 7, h->triangle_thres, c.accept_min_3d_pts,
+                                h->d_l3d, h->d_lflag_up, h->d_lflag_down, st)) != OSB_OK) return s;
+  }
   OSB_LAUNCH(fe_pack_kernel, OSB_MAX_DIRS, 256, 0, st, record_dev, c.self_id, msg_id, nd, mn, h->sp.d_nk, h->sp.d_kpts,
-             h->sp.d_out, h->d_st_map, c.accept_min_3d_pts);
+             h->sp.d_out, h->d_st_map, c.accept_min_3d_pts, h->have_cameras ? h->d_l3d : nullptr,
+             h->have_cameras ? h->d_lflag_up : nullptr);
   OSB_CHECK_LAUNCH();
   fe_mark(h, 4, st);
   return OSB_OK;
@@ -714,6 +761,26 @@ extern "C" osb_status osb_frontend_process(osb_frontend* h, const uint8_t* image
   return fe_refresh_counts(h, st);     // the one synchronisation of the keyframe
 }
 
+extern "C" osb_status osb_frontend_set_cameras(osb_frontend* h, const double* intrinsics, const double* left_extrinsics,
+                                               const double* right_extrinsics, double triangle_thres) {
+  OSB_REQUIRE(h && intrinsics && left_extrinsics && right_extrinsics, "null argument");
+  OSB_REQUIRE(intrinsics[0] > 0 && intrinsics[1] > 0 && triangle_thres > 0, "bad intrinsics / threshold");
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (int i = 0; i < 4; ++i) h->K[i] = intrinsics[i];
+  for (int d = 0; d < h->cfg.n_dirs; ++d)
+    for (int i = 0; i < 7; ++i) { h->left_ext[d][i] = left_extrinsics[d * 7 + i]; h->right_ext[d][i] = right_extrinsics[d * 7 + i]; }
+  h->triangle_thres = triangle_thres;
+  h->have_cameras = true;
+  return OSB_OK;
+}
+
+extern "C" osb_status osb_frontend_set_drone_pose(osb_frontend* h, const double* pose_drone) {
+  OSB_REQUIRE(h && pose_drone, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (int i = 0; i < 7; ++i) h->pose_drone[i] = pose_drone[i];
+  return OSB_OK;
+}
+
 extern "C" osb_status osb_frontend_set_profiling(osb_frontend* h, int enable) {
   OSB_REQUIRE(h != nullptr, "null handle");
   std::lock_guard<std::mutex> lk(h->mu);
@@ -772,7 +839,9 @@ extern "C" osb_status osb_frontend_db_set_geometry(osb_frontend* h, int remote, 
   const int mn = h->cfg.max_num;
   OSB_CUDA(cudaMemcpyAsync(S.kpts + (size_t)first_row * mn * 2, kpts, (size_t)n * mn * 2 * sizeof(float),
                            cudaMemcpyHostToDevice, st));
-  OSB_CUDA(cudaMemcpyAsync(S.smatch + (size_t)first_row * mn, stereo_match, (size_t)n * mn * sizeof(int32_t),
+  std::vector<int32_t> flags((size_t)n * mn);
+  for (size_t i = 0; i < flags.size(); ++i) flags[i] = stereo_match[i] >= 0 ? 1 : 0;       // landmarks_flag of the rows
+  OSB_CUDA(cudaMemcpyAsync(S.smatch + (size_t)first_row * mn, flags.data(), flags.size() * sizeof(int32_t),
                            cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaStreamSynchronize(st));
   return OSB_OK;
@@ -805,7 +874,7 @@ extern "C" osb_status osb_frontend_db_load(osb_frontend* h, int remote, int64_t 
                              (size_t)n * mn * OSB_FEATURE_DESC_SIZE * sizeof(float), cudaMemcpyHostToDevice, st));
   // rows loaded without geometry: landmarks at the origin, every landmark flagged (osb_frontend_db_set_geometry fills them)
   OSB_CUDA(cudaMemsetAsync(S.kpts + (size_t)base * mn * 2, 0, (size_t)n * mn * 2 * sizeof(float), st));
-  OSB_CUDA(cudaMemsetAsync(S.smatch + (size_t)base * mn, 0, (size_t)n * mn * sizeof(int32_t), st));
+  OSB_CUDA(cudaMemsetAsync(S.smatch + (size_t)base * mn, 1, (size_t)n * mn * sizeof(int32_t), st));
   OSB_CUDA(cudaMemcpyAsync(S.nk + base, nk.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(S.row_frame + base, rf.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(S.row_dir + base, rd.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));

@@ -413,6 +413,16 @@ class KeyframeFrontend:
         _l.check(self._lib.osb_frontend_stage_ms(self._h, _l.ptr(ms)))
         return {k: float(v) for k, v in zip(self.STAGES, ms)}
 
+    def set_cameras(self, intrinsics, left_extrinsics, right_extrinsics, triangle_thres=0.006):
+        """stereo triangulation inside extract: the record then carries landmarks_3d / landmarks_flag (loop_cam.cpp:393-432)"""
+        K = np.ascontiguousarray(intrinsics, np.float64)
+        le, re = np.ascontiguousarray(left_extrinsics, np.float64), np.ascontiguousarray(right_extrinsics, np.float64)
+        _l.check(self._lib.osb_frontend_set_cameras(self._h, _l.ptr(K), _l.ptr(le), _l.ptr(re), float(triangle_thres)))
+
+    def set_drone_pose(self, pose_drone):
+        p = np.ascontiguousarray(pose_drone, np.float64)
+        _l.check(self._lib.osb_frontend_set_drone_pose(self._h, _l.ptr(p)))
+
     def db_size(self, remote=False) -> int:
         return int(self._lib.osb_frontend_db_size(self._h, int(remote)))
 
@@ -429,6 +439,38 @@ class KeyframeFrontend:
         """landmarks_2d [n][max_num][2] and stereo_match [n][max_num] of rows put in with db_load"""
         k = _f32(kpts); sm = np.ascontiguousarray(stereo_match, np.int32)
         _l.check(self._lib.osb_frontend_db_set_geometry(self._h, int(remote), first_row, k.shape[0], _l.ptr(k), _l.ptr(sm)))
+
+
+def stereo_lift(kp_up, kp_down, stereo_match, n_up, n_down, intrinsics, pose_up, pose_down, triangle_thres=0.006,
+                accept_min_3d_pts=0):
+    """loop_cam.cpp:393-432 for n_dirs directions: kp_* [n_dirs,max_n,2] f32, stereo_match [n_dirs,max_n] i32,
+    poses [n_dirs,7] -> (pts3d [n_dirs,max_n,3] f32, flag_up, flag_down [n_dirs,max_n] u8)"""
+    lib = _l.load()
+    ku, kd = _f32(kp_up), _f32(kp_down)
+    nd, mn = ku.shape[0], ku.shape[1]
+    sm = np.ascontiguousarray(stereo_match, np.int32)
+    nu, ndn = np.ascontiguousarray(n_up, np.int32), np.ascontiguousarray(n_down, np.int32)
+    K = np.ascontiguousarray(intrinsics, np.float64)
+    pu, pd = np.ascontiguousarray(pose_up, np.float64), np.ascontiguousarray(pose_down, np.float64)
+    pts = np.zeros((nd, mn, 3), np.float32); fu = np.zeros((nd, mn), np.uint8); fd = np.zeros((nd, mn), np.uint8)
+    _l.check(lib.osb_stereo_lift(_l.ptr(ku), _l.ptr(kd), _l.ptr(sm), _l.ptr(nu), _l.ptr(ndn), nd, mn, _l.ptr(K), _l.ptr(pu),
+                                 _l.ptr(pd), float(triangle_thres), int(accept_min_3d_pts), _l.ptr(pts), _l.ptr(fu), _l.ptr(fd)))
+    return pts, fu, fd
+
+
+def depth_lift(kp, n, depth_mm, intrinsics, pose_cam, near=0.3, far=10.0, accept_min_3d_pts=0):
+    """loop_cam.cpp:276-302: kp [n_dirs,max_n,2], depth_mm [n_dirs,H,W] u16, pose_cam [n_dirs,7] -> (pts3d, flag)"""
+    lib = _l.load()
+    k = _f32(kp)
+    nd, mn = k.shape[0], k.shape[1]
+    nn = np.ascontiguousarray(n, np.int32)
+    dep = np.ascontiguousarray(depth_mm, np.uint16)
+    K = np.ascontiguousarray(intrinsics, np.float64)
+    pc = np.ascontiguousarray(pose_cam, np.float64)
+    pts = np.zeros((nd, mn, 3), np.float32); fl = np.zeros((nd, mn), np.uint8)
+    _l.check(lib.osb_depth_lift(_l.ptr(k), _l.ptr(nn), nd, mn, _l.ptr(dep), dep.shape[1], dep.shape[2], _l.ptr(K), _l.ptr(pc),
+                                float(near), float(far), int(accept_min_3d_pts), _l.ptr(pts), _l.ptr(fl)))
+    return pts, fl
 
 
 def pnp_ransac(cases, max_n: int | None = None):

@@ -45,7 +45,9 @@ class KeyframeRecord(C.Structure):
                 ("global_desc", (C.c_float * DEEP_DESC_SIZE) * MAX_DIRS),
                 ("local_desc", ((C.c_float * FEATURE_DESC_SIZE) * MAX_KPTS) * MAX_DIRS),
                 ("kpts", ((C.c_float * 2) * MAX_KPTS) * MAX_DIRS),
-                ("stereo_match", (C.c_int32 * MAX_KPTS) * MAX_DIRS)]
+                ("stereo_match", (C.c_int32 * MAX_KPTS) * MAX_DIRS),
+                ("landmarks_3d", ((C.c_float * 3) * MAX_KPTS) * MAX_DIRS),
+                ("landmarks_flag", (C.c_int32 * MAX_KPTS) * MAX_DIRS)]
 
 
 class LoopResult(C.Structure):
@@ -152,6 +154,12 @@ _SIG = {
     "osb_frontend_db_reset": (C.c_int, [_P]),
     "osb_frontend_db_load": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P]),
     "osb_frontend_db_set_geometry": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, _P]),
+    "osb_stereo_lift": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P]),
+    "osb_stereo_lift_dev": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P, _P]),
+    "osb_depth_lift": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_double, C.c_double, C.c_int, _P, _P]),
+    "osb_depth_lift_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_double, C.c_double, C.c_int, _P, _P, _P]),
+    "osb_frontend_set_cameras": (C.c_int, [_P, _P, _P, _P, C.c_double]),
+    "osb_frontend_set_drone_pose": (C.c_int, [_P, _P]),
     "osb_pnp_ransac": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "osb_pnp_ransac_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "osb_pcm": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P]),

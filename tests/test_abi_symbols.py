@@ -27,8 +27,11 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_sizes_match_header():
-    # osb_keyframe_record: 4+4+4 ints header/counts, 4*4096 + 4*200*64 + 4*200*2 floats, 4*200 ints
-    assert lib.RECORD_BYTES == 4 * (4 + 4 + 4) + 4 * (4 * 4096 + 4 * 200 * 64 + 4 * 200 * 2) + 4 * 4 * 200
+    # osb_keyframe_record: 4+4+4 ints header/counts, 4*4096 + 4*200*64 + 4*200*2 floats, 4*200 ints (stereo_match),
+    # 4*200*3 floats (landmarks_3d), 4*200 ints (landmarks_flag)
+    assert lib.RECORD_BYTES == 4 * (4 + 4 + 4) + 4 * (4 * 4096 + 4 * 200 * 64 + 4 * 200 * 2) + 4 * 4 * 200 \
+        + 4 * 4 * 200 * 3 + 4 * 4 * 200
+    assert C.sizeof(lib.LoopEdge) == 8 + 59 * 8 and C.sizeof(lib.PnpResult) == 6 * 4 + 8 * (2 + 7 + 4)
     assert C.sizeof(lib.SolveOptions) == 8 + 8 * 6 + 8   # + preconditioner, reserved
     assert C.sizeof(lib.SolveSummary) == 8 * 3 + 4 * 4
 

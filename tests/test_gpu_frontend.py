@@ -202,6 +202,7 @@ def test_geometric_filter_on_loaded_rows(gpu):
     np.ctypeslib.as_array(rec.kpts[1])[:] = k_new
     smn = np.zeros(mn, np.int32); smn[100:120] = -1                              # 20 new landmarks without a 3-D flag
     np.ctypeslib.as_array(rec.stereo_match[1])[:] = smn
+    np.ctypeslib.as_array(rec.landmarks_flag[1])[:] = (smn >= 0)                 # landmarks_flag is what the filter tests (:574)
     stream = torch.cuda.current_stream().cuda_stream
     rec_t = torch.frombuffer(bytearray(bytes(rec)), dtype=torch.uint8).cuda()
     res_t = torch.zeros(lib.RESULT_BYTES, dtype=torch.uint8, device="cuda")
