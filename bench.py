@@ -404,6 +404,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_issue = [0.0]
+
     def timed(fn, steps, warmup, base, sampler=None):
         for i in range(warmup):
             fn(base + i)
@@ -431,6 +433,13 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_total, launches = timed(step_resident, args.steps, args.warmup, 0, sampler)
+    # host cost of ENQUEUEING a keyframe with an empty launch queue (8 keyframes right after a synchronisation: no back-pressure)
+    fe.finish(st); barrier()
+    th = time.perf_counter()
+    for k in range(8):
+        keyframe_resident(900_000 + k)
+    host_issue_resident = (time.perf_counter() - th) * 1e3 / 8
+    fe.finish(st); barrier()
     clocks = sampler.stop()
     ms_step = ms_total / args.steps
     ms_keyframe = ms_step / KF_PER_STEP
@@ -489,7 +498,8 @@ def run_ours(args):
                     "pipeline": "blocking between extract and ingest" if args.blocking_exchange else
                                 "asynchronous: round i's ncclAllGather (osb_swarm_exchange_async, side stream) runs behind the "
                                 "extraction of keyframe i+1; its foreign records are ingested one round later",
-                    "api": "osb_swarm_* (C ABI, ncclAllGather on the library's communicator)"}
+                    "async_transport": sw.transport,
+                    "api": "osb_swarm_* (C ABI; exchange_us times the blocking ncclAllGather form)"}
 
     # ---- rooflines ----
     # dominant kernel: the conv1b launch of conv_umma_kernel<64> (43 % of the network's FLOPs).  Its own duration comes
@@ -699,6 +709,7 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world), "gpu_launches": int(launches),
                 "keyframes_timed": args.steps * KF_PER_STEP, "ms_per_keyframe": ms_keyframe,
+                "host_enqueue_ms_per_keyframe": host_issue_resident,
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "keyframes/s",
                         "h2d_bytes_per_step": KF_PER_STEP * 2 * N_DIRS * W * H,

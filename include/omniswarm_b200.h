@@ -496,7 +496,12 @@ osb_status osb_frontend_stage_ms(osb_frontend* h, float* ms8);
  * exchange_async + wait: the reference's exchange is asynchronous (loop_net.cpp:142-172), so the collective may run on
  *            the handle's own stream behind an event of `stream` while the next keyframe is extracted; osb_swarm_wait
  *            makes `stream` wait for the LAST exchange_async.  One exchange in flight per handle; the caller
- *            double-buffers record_dev / gathered_dev.   world == 1: a device copy, no NCCL needed. */
+ *            double-buffers record_dev / gathered_dev.   world == 1: a device copy, no NCCL needed.
+ *            Transport of exchange_async: when the ranks can map each other's memory (CUDA IPC, one node), every record is
+ *            PUSHED into the peers' inboxes by the copy engines over NVLink and completion travels as 32-bit round stamps
+ *            that the streams wait on (cuStreamWaitValue32) -- no kernel, no SM, nothing spinning while a peer is late;
+ *            otherwise (or with OSB_SWARM_P2P=0) it is the ncclAllGather on the handle's stream.  Every rank must call
+ *            exchange_async and wait the same number of times. */
 #define OSB_SWARM_ID_BYTES 128
 typedef struct osb_swarm osb_swarm;
 osb_status osb_swarm_unique_id(uint8_t* id_out /*[OSB_SWARM_ID_BYTES]*/);
@@ -508,6 +513,8 @@ osb_status osb_swarm_exchange(osb_swarm* h, const osb_keyframe_record* record_de
 osb_status osb_swarm_exchange_async(osb_swarm* h, const osb_keyframe_record* record_dev, osb_keyframe_record* gathered_dev,
                                     void* stream);
 osb_status osb_swarm_wait(osb_swarm* h, void* stream);
+int osb_swarm_transport(osb_swarm* h);     /* what exchange_async uses: 1 = peer-to-peer copy engines (CUDA IPC inboxes, stream
+                                              stamps; no SM, no NCCL kernel), 0 = ncclAllGather on the side stream */
 int osb_swarm_rank(osb_swarm* h);
 int osb_swarm_world(osb_swarm* h);
 

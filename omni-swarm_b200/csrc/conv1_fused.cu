@@ -62,6 +62,7 @@ struct Fused1Args {
   float inv_scale;         // 1 / (act_scale * w_scale)
   float out_scale;         // scale of the stored planes
   unsigned long long* dbg; // optional [16] cycle counters of CTA 0 (null = off): see umma_conv1_fused_forward
+  int pool;                // 1: fused 2x2 max-pool (output [B][H/2][W/2][64]); 0: output [B][H][W][64]   (FIRST = false only)
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
@@ -71,8 +72,19 @@ __device__ __forceinline__ void st_shared_128(uint32_t addr, uint32_t a, uint32_
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// FIRST = true : the halo tile is COMPUTED (conv1a from the u8 image, 8 producer warps) -- SuperPoint's first two layers.
+// FIRST = false: the halo tile is LOADED -- the same kernel as a 64 -> 64 3x3 layer on split-fp16 planes (conv2a, conv2b):
+//                one TMA box per window part instead of the three kx-shifted boxes of conv_umma_kernel (46 KB of
+//                activations per tile instead of 120 KB through L2 and shared memory).  A window is two boxes per plane:
+//                {64 ch, 10 px, 15 rows} for the rows private to it and {64 ch, 10 px, 3 rows} for the rows it shares with
+//                the other window, the latter issued only after the previous tile's MMAs have retired.  TMA writes
+//                SWIZZLE_128B by absolute shared-memory address too, 128-byte aligned destinations suffice
+//                (scripts/microbench/tma_swizzle_probe.cu, profiles/r02_tma_swizzle_probe.txt).
+template <bool FIRST>
 __global__ void __launch_bounds__(F1_THREADS, 1)
-conv1_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, Fused1Args P) {
+conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                   const __grid_constant__ CUtensorMap tm_a15_hi, const __grid_constant__ CUtensorMap tm_a15_lo,
+                   const __grid_constant__ CUtensorMap tm_a3_hi, const __grid_constant__ CUtensorMap tm_a3_lo, Fused1Args P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();                              // the plan has no slack for re-aligning
@@ -91,7 +103,7 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
 
   if (threadIdx.x == 0) {
     mbar_init(b_full, 1);
-    for (int w = 0; w < 2; ++w) { mbar_init(a_full(w), F1_NPROD); mbar_init(mma_done(w), 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(a_full(w), FIRST ? F1_NPROD : 1); mbar_init(mma_done(w), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -167,9 +179,11 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       if (prof) t0 = clock64();
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
       // pooled pixel of (even row, even col): max over lanes l, l+1, l+8, l+9; writer lanes have row and col even
+      const bool pool = FIRST || P.pool;
       const int py = ty * (F1_TH / 2) + 2 * q + (lane >> 4), px = tx * (F1_TW / 2) + ((lane & 7) >> 1);
-      const bool writer = !(lane & 8) && !(lane & 1) && py < Hp && px < Wp;
-      const size_t ppix = ((size_t)b * Hp + py) * Wp + px;
+      const int y = ty * F1_TH + 4 * q + (lane >> 3), x = tx * F1_TW + (lane & 7);
+      const bool writer = pool ? (!(lane & 8) && !(lane & 1) && py < Hp && px < Wp) : (y < P.H && x < P.W);
+      const size_t ppix = pool ? ((size_t)b * Hp + py) * Wp + px : ((size_t)b * P.H + y) * P.W + x;
       mbar_wait(tfull_bar(acc), acc_phase);
       if (prof) t1 = clock64();
       tc_fence_after();
@@ -185,10 +199,12 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
           const float a = fmaf(__uint_as_float(v[i]) + __uint_as_float(vc[i]), P.inv_scale, __ldg(P.bias + n0 + i));
           f[i] = fmaxf(a, 0.f);
         }
+        if (pool) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          f[i] = fmaxf(f[i], __shfl_down_sync(0xffffffffu, f[i], 1));
-          f[i] = fmaxf(f[i], __shfl_down_sync(0xffffffffu, f[i], 8));
+          for (int i = 0; i < 16; ++i) {
+            f[i] = fmaxf(f[i], __shfl_down_sync(0xffffffffu, f[i], 1));
+            f[i] = fmaxf(f[i], __shfl_down_sync(0xffffffffu, f[i], 8));
+          }
         }
         if (!writer) continue;
         uint32_t hi[8], lo[8];
@@ -211,7 +227,27 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       if (prof) { c_wait += t1 - t0; c_work += clock64() - t1; }
     }
     if (prof) { P.dbg[7] = c_wait; P.dbg[8] = c_work; }
-  } else if (warp < 4 || (warp >= 8 && warp < 12)) {
+  } else if (!FIRST && warp == 0 && lane == 0) {
+    // ===================== halo windows by TMA (64 -> 64 layers on split planes) =====================
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // the planes are the previous kernel's output (no-op without PDL)
+    uint32_t i = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+      const int w = i & 1;
+      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+      const int x0 = tx * F1_TW - 1, y0 = ty * F1_TH - 1;     // image coordinates of halo pixel (0, 0)
+      // halo rows private to the window: 0..14 of window 0 (smem rows 0..14), 3..17 of window 1 (smem rows 18..32);
+      // shared: 15..17 of window 0 = 0..2 of window 1 (smem rows 15..17)
+      const int prow = w ? 3 : 0, srow = w ? 0 : 15;
+      const uint32_t pdst = (uint32_t)((w ? F1_WIN1 + 3 : 0) * F1_PITCH), sdst = (uint32_t)(F1_WIN1 * F1_PITCH);
+      if (i >= 2) mbar_wait(mma_done(w), ((i >> 1) - 1) & 1);
+      mbar_expect_tx(a_full(w), 2u * F1_HR * F1_PITCH);
+      tma_load_4d(a_hi_base + pdst, &tm_a15_hi, a_full(w), 0, x0, y0 + prow, b);
+      tma_load_4d(a_lo_base + pdst, &tm_a15_lo, a_full(w), 0, x0, y0 + prow, b);
+      if (i >= 1) mbar_wait(mma_done(w ^ 1), ((i - 1) >> 1) & 1);
+      tma_load_4d(a_hi_base + sdst, &tm_a3_hi, a_full(w), 0, x0, y0 + srow, b);
+      tma_load_4d(a_lo_base + sdst, &tm_a3_lo, a_full(w), 0, x0, y0 + srow, b);
+    }
+  } else if (FIRST && (warp < 4 || (warp >= 8 && warp < 12))) {
     // ===================== conv1a producers (8 warps, two per scheduler) =====================
     // lane = (pixel slot, 8 output channels): the 8 lanes of a pixel are adjacent, so a quarter-warp writes the eight
     // 16-byte chunks of one 128-byte pixel row -- conflict-free 128-bit shared stores.  32 pixel slots per step: steps
@@ -350,14 +386,48 @@ osb_status umma_conv1_fused_forward(const UmmaLayer& L1b, const float* w1a, cons
   P.img = img; P.w1a = w1a; P.b1a = b1a; P.bias = L1b.bias; P.out_hi = out_hi; P.out_lo = out_lo;
   P.H = H; P.W = W; P.B = B;
   P.alpha = (float)(1.0 / 255.0);
-  P.dbg = dbg;
+  P.dbg = dbg; P.pool = 1;
   P.act_scale = act_scale; P.inv_scale = 1.0f / (act_scale * L1b.w_scale); P.out_scale = out_scale;
-  OSB_SMEM_OPT_IN(conv1_fused_kernel, F1_SMEM);
+  OSB_SMEM_OPT_IN(conv64_halo_kernel<true>, F1_SMEM);
   const int tiles = B * cdiv(W, F1_TW) * cdiv(H, F1_TH);
   const int grid = std::min(tiles, max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms());
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(F1_THREADS); cfg.dynamicSmemBytes = F1_SMEM; cfg.stream = st;
-  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv1_fused_kernel, L1b.tm_hi, L1b.tm_lo, P));
+  // (the activation maps are unused by the FIRST instantiation: the weight maps stand in)
+  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv64_halo_kernel<true>, L1b.tm_hi, L1b.tm_lo, L1b.tm_hi, L1b.tm_lo, L1b.tm_hi, L1b.tm_lo, P));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return OSB_OK;
+}
+
+// TMA descriptors of a 64-channel activation tensor for the halo-window kernel: boxes {64 ch, 10 px, 15 rows} and
+// {64 ch, 10 px, 3 rows} on each plane ([B][H][W][64] fp16)
+osb_status umma_halo_maps(HaloMaps* M, __half* p_hi, __half* p_lo, int B, int H, int W) {
+  const uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {64 * 2, (uint64_t)W * 64 * 2, (uint64_t)H * W * 64 * 2};
+  const uint32_t box15[4] = {64, F1_HC, F1_WIN1, 1}, box3[4] = {64, F1_HC, F1_HR - F1_WIN1, 1};
+  osb_status s;
+  if ((s = umma_make_tmap(&M->a15_hi, p_hi, 4, dims, strides, box15)) != OSB_OK) return s;
+  if ((s = umma_make_tmap(&M->a15_lo, p_lo, 4, dims, strides, box15)) != OSB_OK) return s;
+  if ((s = umma_make_tmap(&M->a3_hi, p_hi, 4, dims, strides, box3)) != OSB_OK) return s;
+  return umma_make_tmap(&M->a3_lo, p_lo, 4, dims, strides, box3);
+}
+
+// 64 -> 64 3x3 convolution + bias + ReLU (+ optional 2x2 max-pool) on split planes with the halo-window kernel
+osb_status umma_conv64_halo_forward(const UmmaLayer& L, const HaloMaps& M, int B, int H, int W, float act_scale, __half* out_hi,
+                                    __half* out_lo, float out_scale, int pool, cudaStream_t st, int max_ctas,
+                                    unsigned long long* dbg) {
+  OSB_REQUIRE(L.n_pad == 64 && L.cin == 64 && L.ks == 3, "halo-window kernel expects a 64 -> 64 3x3 layer");
+  OSB_REQUIRE(!pool || (H % 2 == 0 && W % 2 == 0), "fused max-pool needs even H and W");
+  Fused1Args P;
+  P.img = nullptr; P.w1a = nullptr; P.b1a = nullptr; P.bias = L.bias; P.out_hi = out_hi; P.out_lo = out_lo;
+  P.H = H; P.W = W; P.B = B; P.alpha = 0.f; P.dbg = dbg; P.pool = pool;
+  P.act_scale = act_scale; P.inv_scale = 1.0f / (act_scale * L.w_scale); P.out_scale = out_scale;
+  OSB_SMEM_OPT_IN(conv64_halo_kernel<false>, F1_SMEM);
+  const int tiles = B * cdiv(W, F1_TW) * cdiv(H, F1_TH);
+  const int grid = std::min(tiles, max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(F1_THREADS); cfg.dynamicSmemBytes = F1_SMEM; cfg.stream = st;
+  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv64_halo_kernel<false>, L.tm_hi, L.tm_lo, M.a15_hi, M.a15_lo, M.a3_hi, M.a3_lo, P));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return OSB_OK;
 }

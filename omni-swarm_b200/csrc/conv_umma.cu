@@ -463,8 +463,8 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static osb_status make_tmap(CUtensorMap* tm, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                            const uint32_t* box) {
+osb_status umma_make_tmap(CUtensorMap* tm, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("conv_umma", "cuTensorMapEncodeTiled entry point not available"); return OSB_ERR_CUDA; }
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
@@ -510,12 +510,12 @@ osb_status umma_layer_upload(UmmaLayer* L, const float* w_oihw, const float* bia
   const uint64_t strides[2] = {(uint64_t)cin * 2, (uint64_t)cin * L->n_pad * 2};
   const uint32_t box[3] = {UM_KC, (uint32_t)std::min(L->n_pad, 256), 1};
   osb_status s;
-  if ((s = make_tmap(&L->tm_hi, L->w_hi, 3, dims, strides, box)) != OSB_OK) return s;
-  if ((s = make_tmap(&L->tm_lo, L->w_lo, 3, dims, strides, box)) != OSB_OK) return s;
+  if ((s = umma_make_tmap(&L->tm_hi, L->w_hi, 3, dims, strides, box)) != OSB_OK) return s;
+  if ((s = umma_make_tmap(&L->tm_lo, L->w_lo, 3, dims, strides, box)) != OSB_OK) return s;
   if (L->n_pad >= 256) {                       // 128-row boxes: the layer as n_pad / 128 work items per tile
     const uint32_t box128[3] = {UM_KC, 128, 1};
-    if ((s = make_tmap(&L->tm_hi128, L->w_hi, 3, dims, strides, box128)) != OSB_OK) return s;
-    if ((s = make_tmap(&L->tm_lo128, L->w_lo, 3, dims, strides, box128)) != OSB_OK) return s;
+    if ((s = umma_make_tmap(&L->tm_hi128, L->w_hi, 3, dims, strides, box128)) != OSB_OK) return s;
+    if ((s = umma_make_tmap(&L->tm_lo128, L->w_lo, 3, dims, strides, box128)) != OSB_OK) return s;
   }
   return OSB_OK;
 }
@@ -532,8 +532,8 @@ osb_status umma_act_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half*
   // the box carries the vertical halo of the layer that READS these planes (ks x ks filter)
   const uint32_t box[4] = {UM_KC, UM_TW, (uint32_t)(UM_TH + 2 * (ks / 2)), 1};
   osb_status s;
-  if ((s = make_tmap(hi, p_hi, 4, dims, strides, box)) != OSB_OK) return s;
-  return make_tmap(lo, p_lo, 4, dims, strides, box);
+  if ((s = umma_make_tmap(hi, p_hi, 4, dims, strides, box)) != OSB_OK) return s;
+  return umma_make_tmap(lo, p_lo, 4, dims, strides, box);
 }
 
 // OSB_CONV_PDL=1 launches the convolutions with programmatic dependent launch.  Off by default: measured (r01f) it

@@ -38,6 +38,15 @@ osb_status umma_conv1_fused_forward(const UmmaLayer& L1b, const float* w1a, cons
 // dbg (optional, [16] device words): SM-clock cycles of CTA 0 summed over its tiles -- [0] producer wait (window free),
 // [1] producer compute + stores, [2] producer wait (shared rows), [3] producer loop total, [4] MMA issuer wait (TMEM free),
 // [5] wait (halo tile full), [6] issue, [7] epilogue wait, [8] epilogue work, [9] tiles of CTA 0
+// halo-window form of the 64 -> 64 3x3 layers (conv1_fused.cu, FIRST = false): one halo tile per output tile instead of
+// three kx-shifted boxes
+struct HaloMaps { CUtensorMap a15_hi, a15_lo, a3_hi, a3_lo; };
+osb_status umma_halo_maps(HaloMaps* M, __half* p_hi, __half* p_lo, int B, int H, int W);
+osb_status umma_conv64_halo_forward(const UmmaLayer& L, const HaloMaps& M, int B, int H, int W, float act_scale, __half* out_hi,
+                                    __half* out_lo, float out_scale, int pool, cudaStream_t st, int max_ctas = 0,
+                                    unsigned long long* dbg = nullptr);
+osb_status umma_make_tmap(CUtensorMap* tm, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box);
 // depthwise 3x3 + bias + ReLU6, fp32 NHWC in, split fp16 planes out (feeds a pointwise tcgen05 conv)
 osb_status umma_dwconv_forward(const float* w_tap_c, const float* bias, const float* x, __half* out_hi, __half* out_lo,
                                int B, int H, int W, int C, int stride, float out_scale, cudaStream_t st);

@@ -40,6 +40,7 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
   if (const char* e = getenv("OSB_SP_OVERLAP")) overlap_kp = atoi(e) != 0;
   if (const char* e = getenv("OSB_SP_FUSED_SOFTMAX")) fused_softmax = atoi(e) != 0;
   if (const char* e = getenv("OSB_SP_FUSE1")) fuse_first = atoi(e) != 0;
+  if (const char* e = getenv("OSB_SP_HALO64")) halo64 = atoi(e) != 0;
   // ---- weights ----
   const float* p = weights;
   {
@@ -106,6 +107,10 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
       in_lo[i] = base + (size_t)max_batch * h * w * c;
       osb_status s = umma_act_maps(&tmA[i], &tmB[i], in_hi[i], in_lo[i], max_batch, h, w, c, SP_KS[i]);
       if (s != OSB_OK) return s;
+      if (i == 2 || i == 3) {
+        s = umma_halo_maps(&halo[i], in_hi[i], in_lo[i], max_batch, h, w);
+        if (s != OSB_OK) return s;
+      }
     }
   }
   OSB_CUDA(cudaMalloc(&d_f1dbg, 16 * sizeof(unsigned long long)));
@@ -158,7 +163,7 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
   if (fuse_first) {
     mark(st);                                                                             // (conv1a has no launch of its own)
     RUN(umma_conv1_fused_forward(UL[1], w1a, b1a, img_dev, B, H, W, SA, in_hi[2], in_lo[2], SA, st, 0,
-                                 layer_prof ? d_f1dbg : nullptr));   // conv1a+conv1b+pool -> B
+                                 (layer_prof && !(getenv("OSB_F1_DBG_LAYER") && atoi(getenv("OSB_F1_DBG_LAYER")) != 1)) ? d_f1dbg : nullptr));   // conv1a+conv1b+pool -> B
     mark(st);
   } else {
     RUN(umma_first_forward(w1a, b1a, lut, img_dev, in_hi[1], in_lo[1], B, H, W, SA, st)); // conv1a            -> A
@@ -166,10 +171,20 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
     RUN(conv(1, H, W, 2, 1));                                                             // conv1b + pool     -> B
     mark(st);
   }
-  RUN(conv(2, H / 2, W / 2, 3, 0));                                                       // conv2a            -> A
-  mark(st);
-  RUN(conv(3, H / 2, W / 2, 4, 1));                                                       // conv2b + pool     -> B
-  mark(st);
+  if (halo64) {
+    static const int dbg_layer = [] { const char* e = getenv("OSB_F1_DBG_LAYER"); return e ? atoi(e) : 1; }();
+    RUN(umma_conv64_halo_forward(UL[2], halo[2], B, H / 2, W / 2, SA, in_hi[3], in_lo[3], SA, 0, st, 0,
+                                 (layer_prof && dbg_layer == 2) ? d_f1dbg : nullptr));                  // conv2a   -> A
+    mark(st);
+    RUN(umma_conv64_halo_forward(UL[3], halo[3], B, H / 2, W / 2, SA, in_hi[4], in_lo[4], SA, 1, st, 0,
+                                 (layer_prof && dbg_layer == 3) ? d_f1dbg : nullptr));                  // conv2b + pool -> B
+    mark(st);
+  } else {
+    RUN(conv(2, H / 2, W / 2, 3, 0));                                                     // conv2a            -> A
+    mark(st);
+    RUN(conv(3, H / 2, W / 2, 4, 1));                                                     // conv2b + pool     -> B
+    mark(st);
+  }
   RUN(conv(4, H / 4, W / 4, 5, 0));                                                       // conv3a            -> A
   mark(st);
   RUN(conv(5, H / 4, W / 4, 6, 1));                                                       // conv3b + pool     -> B

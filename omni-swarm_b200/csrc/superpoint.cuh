@@ -44,6 +44,8 @@ struct SuperPoint {
   cudaEvent_t ev_semi = nullptr, ev_kp = nullptr;
   bool overlap_kp = true;
   unsigned long long* d_f1dbg = nullptr;   // cycle counters of the fused first-layers kernel (filled while layer_prof is on)
+  HaloMaps halo[4];               // [2], [3]: conv2a / conv2b inputs for the halo-window kernel
+  bool halo64 = true;             // conv2a / conv2b through conv64_halo_kernel (OSB_SP_HALO64=0: conv_umma_kernel<64,RES>)
   bool fuse_first = true;          // conv1a computed inside conv1b's kernel (conv1_fused.cu; OSB_SP_FUSE1=0: two kernels)
   bool fused_softmax = true;       // detector-head softmax + pixel shuffle in convPb's epilogue (OSB_SP_FUSED_SOFTMAX=0: two kernels)
   osb_status network(const uint8_t* img_dev, int B, cudaStream_t st, const KpJob* kp = nullptr);

@@ -10,12 +10,24 @@
 // dependency on it (a single-drone host without NCCL can still load the library; osb_swarm_* then return OSB_ERR_INVALID
 // with a message).  world == 1 needs no NCCL at all.
 //
+// Two transports:
+//   * NCCL (osb_swarm_exchange): one ncclAllGather kernel.
+//   * peer-to-peer copy engines (osb_swarm_exchange_async when the ranks can map each other's memory through CUDA IPC;
+//     OSB_SWARM_P2P=0 disables it): every rank owns a double-buffered inbox [2][world] of records, exported once with
+//     cudaIpcGetMemHandle.  A round is world-1 cudaMemcpyAsync pushes of the 286 KB record straight into the peers' inboxes
+//     over NVLink, each followed by a 32-bit round stamp (cuMemsetD32Async) in the peer's flag table; the receiver's stream
+//     waits for the stamps with cuStreamWaitValue32 and acknowledges with stamps in the senders' ack tables, which gate the
+//     reuse of an inbox slot two rounds later.  No SM is used and nothing spins: an NCCL all-gather kernel that waits for a
+//     late peer holds SMs that the persistent convolution CTAs of the next keyframe need.
+//
 // The reference's exchange is asynchronous (its LCM thread delivers remote keyframes whenever they arrive, loop_net.cpp
 // :142-172), so nothing forces keyframe i's gather to finish before keyframe i+1's extraction starts:
 // osb_swarm_exchange_async runs the collective on the handle's own stream behind an event of the caller's stream, and
 // osb_swarm_wait makes a stream wait for it -- the caller ingests round i's foreign records while round i+1 is in flight.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace osb {
@@ -63,14 +75,85 @@ static NcclApi* nccl_api() {
 
 using namespace osb;
 
+typedef CUresult (*PFN_streamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*PFN_memsetD32Async)(CUdeviceptr, unsigned int, size_t, CUstream);
+
+constexpr int SWARM_MAX_WORLD = 64;
+
 struct osb_swarm {
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
-  cudaStream_t side = nullptr;                 // the collective's own stream (exchange_async)
+  cudaStream_t side = nullptr;                 // the exchange's own stream (exchange_async)
   cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
   bool in_flight = false;
   std::mutex mu;
+  // peer-to-peer transport
+  bool p2p = false;
+  uint8_t* inbox = nullptr;                    // own allocation: records [2][world], then data stamps [2][world], ack stamps [2][world]
+  uint8_t* peer[SWARM_MAX_WORLD] = {};         // IPC-mapped inboxes of the other ranks (peer[rank] = inbox)
+  uint32_t round = 0;                          // rounds issued so far
+  osb_keyframe_record* last_gathered = nullptr;
+  PFN_streamWaitValue32 wait32 = nullptr;
+  PFN_memsetD32Async memset32 = nullptr;
+  size_t rec_off(int b, int r) const { return ((size_t)b * world + r) * sizeof(osb_keyframe_record); }
+  size_t data_off(int b, int r) const { return (size_t)2 * world * sizeof(osb_keyframe_record) + ((size_t)b * world + r) * 4; }
+  size_t ack_off(int b, int r) const { return data_off(2, 0) + ((size_t)b * world + r) * 4; }
+  size_t bytes() const { return ack_off(2, 0); }
 };
+
+// set up the copy-engine transport: allocate the inbox, exchange IPC handles over the NCCL communicator, map the peers
+static bool swarm_setup_p2p(osb_swarm* h, NcclApi* api) {
+  if (const char* e = getenv("OSB_SWARM_P2P")) if (atoi(e) == 0) return false;
+  if (h->world > SWARM_MAX_WORLD) return false;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return false;
+  h->wait32 = (PFN_streamWaitValue32)fn;
+  if (cudaGetDriverEntryPoint("cuMemsetD32Async", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return false;
+  h->memset32 = (PFN_memsetD32Async)fn;
+  if (cudaMalloc(&h->inbox, h->bytes()) != cudaSuccess) { cudaGetLastError(); h->inbox = nullptr; return false; }
+  cudaMemset(h->inbox, 0, h->bytes());
+  cudaIpcMemHandle_t mine;
+  bool ok = cudaIpcGetMemHandle(&mine, h->inbox) == cudaSuccess;
+  // all ranks must take the same decision: gather (handle, ok) from everyone
+  struct Slot { cudaIpcMemHandle_t hdl; int ok; int pad[3]; };
+  Slot local; memset(&local, 0, sizeof(local)); local.hdl = mine; local.ok = ok ? 1 : 0;
+  Slot* d_all = nullptr;
+  std::vector<Slot> all(h->world);
+  if (cudaMalloc(&d_all, h->world * sizeof(Slot)) != cudaSuccess) { cudaGetLastError(); return false; }
+  cudaMemcpy(d_all + h->rank, &local, sizeof(Slot), cudaMemcpyHostToDevice);
+  bool gathered = api->AllGather(d_all + h->rank, d_all, sizeof(Slot), ncclUint8, h->comm, h->side) == ncclSuccess &&
+                  cudaStreamSynchronize(h->side) == cudaSuccess;
+  if (gathered) cudaMemcpy(all.data(), d_all, h->world * sizeof(Slot), cudaMemcpyDeviceToHost);
+  cudaFree(d_all);
+  if (!gathered) { cudaGetLastError(); return false; }
+  for (int r = 0; r < h->world; ++r) ok = ok && all[r].ok;
+  if (ok) {
+    for (int r = 0; r < h->world; ++r) {
+      if (r == h->rank) { h->peer[r] = h->inbox; continue; }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r].hdl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      h->peer[r] = (uint8_t*)p;
+    }
+  }
+  // second agreement round: did every rank map every peer?
+  int* d_flag = nullptr;
+  std::vector<int> flags(h->world, 0);
+  const int mine_ok = ok ? 1 : 0;
+  if (cudaMalloc(&d_flag, h->world * sizeof(int)) == cudaSuccess) {
+    cudaMemcpy(d_flag + h->rank, &mine_ok, sizeof(int), cudaMemcpyHostToDevice);
+    if (api->AllGather(d_flag + h->rank, d_flag, sizeof(int), ncclUint8, h->comm, h->side) == ncclSuccess &&
+        cudaStreamSynchronize(h->side) == cudaSuccess)
+      cudaMemcpy(flags.data(), d_flag, h->world * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d_flag);
+  }
+  for (int r = 0; r < h->world; ++r) ok = ok && flags[r];
+  if (!ok) {
+    for (int r = 0; r < h->world; ++r) if (r != h->rank && h->peer[r]) { cudaIpcCloseMemHandle(h->peer[r]); h->peer[r] = nullptr; }
+    cudaGetLastError();
+  }
+  return ok;
+}
 
 static_assert(sizeof(ncclUniqueId) == OSB_SWARM_ID_BYTES, "ncclUniqueId size");
 
@@ -87,6 +170,9 @@ extern "C" osb_status osb_swarm_unique_id(uint8_t* id_out) {
 extern "C" osb_status osb_swarm_destroy(osb_swarm* h) {
   if (!h) return OSB_OK;
   if (h->side) cudaStreamSynchronize(h->side);
+  for (int r = 0; r < SWARM_MAX_WORLD; ++r)
+    if (r != h->rank && h->peer[r]) cudaIpcCloseMemHandle(h->peer[r]);
+  if (h->inbox) cudaFree(h->inbox);
   if (h->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(h->comm); }
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
@@ -122,6 +208,7 @@ extern "C" osb_status osb_swarm_init(osb_swarm** out, const uint8_t* id, int ran
       osb_swarm_destroy(h);
       return OSB_ERR_CUDA;
     }
+    h->p2p = swarm_setup_p2p(h, api);
   }
   *out = h;
   return OSB_OK;
@@ -151,6 +238,28 @@ extern "C" osb_status osb_swarm_exchange_async(osb_swarm* h, const osb_keyframe_
   std::lock_guard<std::mutex> lk(h->mu);
   OSB_CUDA(cudaEventRecord(h->ev_ready, (cudaStream_t)stream));      // the record is complete on the caller's stream
   OSB_CUDA(cudaStreamWaitEvent(h->side, h->ev_ready, 0));
+  if (h->p2p) {
+    // copy-engine transport: push my record into slot [b][rank] of every inbox, then its round stamp
+    const uint32_t i = h->round;
+    const int b = (int)(i & 1u);
+    OSB_CUDA(cudaMemcpyAsync(h->inbox + h->rec_off(b, h->rank), record_dev, sizeof(osb_keyframe_record), cudaMemcpyDeviceToDevice, h->side));
+    for (int k = 1; k < h->world; ++k) {
+      const int p = (h->rank + k) % h->world;                         // staggered: rank r starts with r+1
+      if (i >= 2) {
+        // peer p acknowledged round i-2 (stamp i-1 in MY ack table) before its slot of buffer b is overwritten
+        CUresult r = h->wait32((CUstream)h->side, (CUdeviceptr)(h->inbox + h->ack_off(b, p)), i - 1, CU_STREAM_WAIT_VALUE_GEQ);
+        if (r != CUDA_SUCCESS) { set_error("osb_swarm_exchange_async", "cuStreamWaitValue32 failed"); return OSB_ERR_CUDA; }
+      }
+      OSB_CUDA(cudaMemcpyAsync(h->peer[p] + h->rec_off(b, h->rank), record_dev, sizeof(osb_keyframe_record), cudaMemcpyDeviceToDevice, h->side));
+      CUresult r = h->memset32((CUdeviceptr)(h->peer[p] + h->data_off(b, h->rank)), i + 1, 1, (CUstream)h->side);
+      if (r != CUDA_SUCCESS) { set_error("osb_swarm_exchange_async", "cuMemsetD32Async on peer memory failed"); return OSB_ERR_CUDA; }
+    }
+    OSB_CUDA(cudaEventRecord(h->ev_done, h->side));
+    h->last_gathered = gathered_dev;
+    h->round = i + 1;
+    h->in_flight = true;
+    return OSB_OK;
+  }
   osb_status s = swarm_gather(h, record_dev, gathered_dev, h->side);
   if (s != OSB_OK) return s;
   OSB_CUDA(cudaEventRecord(h->ev_done, h->side));
@@ -161,9 +270,32 @@ extern "C" osb_status osb_swarm_exchange_async(osb_swarm* h, const osb_keyframe_
 extern "C" osb_status osb_swarm_wait(osb_swarm* h, void* stream) {
   OSB_REQUIRE(h != nullptr, "null handle");
   std::lock_guard<std::mutex> lk(h->mu);
-  if (h->in_flight) OSB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_done, 0));
+  if (!h->in_flight) return OSB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  OSB_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
+  if (h->p2p) {
+    // the last round's records have arrived when every peer's stamp is there; then hand them to the caller's buffer and
+    // acknowledge, which frees my slot in the peers' inboxes for the round after next
+    const uint32_t i = h->round - 1;
+    const int b = (int)(i & 1u);
+    for (int p = 0; p < h->world; ++p) {
+      if (p == h->rank) continue;
+      CUresult r = h->wait32((CUstream)st, (CUdeviceptr)(h->inbox + h->data_off(b, p)), i + 1, CU_STREAM_WAIT_VALUE_GEQ);
+      if (r != CUDA_SUCCESS) { set_error("osb_swarm_wait", "cuStreamWaitValue32 failed"); return OSB_ERR_CUDA; }
+    }
+    OSB_CUDA(cudaMemcpyAsync(h->last_gathered, h->inbox + h->rec_off(b, 0), (size_t)h->world * sizeof(osb_keyframe_record),
+                             cudaMemcpyDeviceToDevice, st));
+    for (int p = 0; p < h->world; ++p) {
+      if (p == h->rank) continue;
+      CUresult r = h->memset32((CUdeviceptr)(h->peer[p] + h->ack_off(b, h->rank)), i + 1, 1, (CUstream)st);
+      if (r != CUDA_SUCCESS) { set_error("osb_swarm_wait", "cuMemsetD32Async on peer memory failed"); return OSB_ERR_CUDA; }
+    }
+    h->in_flight = false;
+  }
   return OSB_OK;
 }
+
+extern "C" int osb_swarm_transport(osb_swarm* h) { return h ? (h->p2p ? 1 : 0) : -1; }
 
 extern "C" int osb_swarm_rank(osb_swarm* h) { return h ? h->rank : -1; }
 extern "C" int osb_swarm_world(osb_swarm* h) { return h ? h->world : -1; }

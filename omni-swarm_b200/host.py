@@ -550,6 +550,7 @@ class Swarm:
             idbuf = (C.c_uint8 * _l.SWARM_ID_BYTES).from_buffer_copy(uid)
         _l.check(self._lib.osb_swarm_init(C.byref(self._h), idbuf, rank, world))
         self.rank, self.world = rank, world
+        self.transport = "p2p copy engines" if self._lib.osb_swarm_transport(self._h) == 1 else "nccl"
 
     def close(self):
         if getattr(self, "_h", None):

@@ -171,6 +171,7 @@ _SIG = {
     "osb_swarm_exchange_async": (C.c_int, [_P, _P, _P, _P]),
     "osb_swarm_wait": (C.c_int, [_P, _P]),
     "osb_swarm_rank": (C.c_int, [_P]),
+    "osb_swarm_transport": (C.c_int, [_P]),
     "osb_swarm_world": (C.c_int, [_P]),
 }
 

@@ -215,9 +215,10 @@ def test_tensor_core_path_vs_cuda_core_path(gpu):
 @pytest.mark.parametrize("size", [(640, 480), (400, 208), (96, 64), (200, 120)])
 def test_fused_first_layers_bit_identical(gpu, size):
     """conv1a computed inside conv1b's kernel (conv1_fused.cu: one shared-memory copy of the halo tile, nine descriptor
-    views) against the two-kernel path (conv1a planes through HBM, TMA boxes): same fp32 FMA order in conv1a, same MMA
-    accumulation order in conv1b, so heat-map and descriptor map must be BIT-identical -- including ragged tiles
-    (208 = 13 x 16 rows, 200 x 120: half tiles in both directions) and the blanked bottom quarter."""
+    views) and conv2a / conv2b through the same halo-window kernel fed by TMA, against the TMA-box kernels (conv1a planes
+    through HBM, three kx-shifted boxes per tile): same fp32 FMA order in conv1a, same MMA accumulation order in the 64 -> 64
+    layers, so heat-map and descriptor map must be BIT-identical -- including ragged tiles (208 = 13 x 16 rows, 200 x 120:
+    half tiles in both directions at every resolution) and the blanked bottom quarter."""
     W, H = size
     comp, mean = synth.pca_matrices(0)
     wts = synth.flatten_sp_weights(synth.superpoint_weights(0))
@@ -225,13 +226,14 @@ def test_fused_first_layers_bit_identical(gpu, size):
                      np.zeros((H, W), np.uint8)])
     imgs[2, ::7, ::5] = 255
     out = {}
-    for mode in ("1", "0"):
+    for mode in ("1", "0"):                       # "1": fused first layers + halo-window conv2a/2b; "0": the TMA-box kernels
         os.environ["OSB_SP_FUSE1"] = mode
+        os.environ["OSB_SP_HALO64"] = mode
         sp = host.SuperPoint(wts, comp, mean, W, H, 0.015, 200, max_batch=3)
         res = sp.inference_batch(imgs)
         out[mode] = [(sp.read("semi", b), sp.read("desc", b), res[b][0], res[b][1]) for b in range(3)]
         sp.close()
-    os.environ.pop("OSB_SP_FUSE1")
+    os.environ.pop("OSB_SP_FUSE1"); os.environ.pop("OSB_SP_HALO64")
     for b in range(3):
         for a, c in zip(out["1"][b], out["0"][b]):
             assert np.array_equal(a, c, equal_nan=True), f"image {b}: fused and unfused paths differ"
