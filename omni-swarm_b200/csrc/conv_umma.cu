@@ -512,6 +512,10 @@ osb_status umma_layer_upload(UmmaLayer* L, const float* w_oihw, const float* bia
   osb_status s;
   if ((s = umma_make_tmap(&L->tm_hi, L->w_hi, 3, dims, strides, box)) != OSB_OK) return s;
   if ((s = umma_make_tmap(&L->tm_lo, L->w_lo, 3, dims, strides, box)) != OSB_OK) return s;
+  if (L->n_pad == 64) {
+    const uint32_t box32[3] = {UM_KC, 32, 1};
+    if ((s = umma_make_tmap(&L->tm_hi32, L->w_hi, 3, dims, strides, box32)) != OSB_OK) return s;
+  }
   if (L->n_pad >= 256) {                       // 128-row boxes: the layer as n_pad / 128 work items per tile
     const uint32_t box128[3] = {UM_KC, 128, 1};
     if ((s = umma_make_tmap(&L->tm_hi128, L->w_hi, 3, dims, strides, box128)) != OSB_OK) return s;

@@ -14,6 +14,7 @@ struct UmmaLayer {
   float* bias = nullptr;
   CUtensorMap tm_hi, tm_lo;
   CUtensorMap tm_hi128, tm_lo128;     // same planes with 128-row boxes (n_pad >= 256 only)
+  CUtensorMap tm_hi32;                // W_hi with 32-row boxes (n_pad == 64: the CTA-pair kernel's half of the N = 64 operand)
 };
 
 osb_status umma_layer_upload(UmmaLayer* L, const float* w_oihw, const float* bias, int cin, int cout, int ks,
@@ -47,6 +48,14 @@ osb_status umma_conv64_halo_forward(const UmmaLayer& L, const HaloMaps& M, int B
                                     unsigned long long* dbg = nullptr);
 osb_status umma_make_tmap(CUtensorMap* tm, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                           const uint32_t* box);
+// CTA-pair form (conv64_pair.cu: tcgen05.mma.cta_group::2, M = 256, weights split across the pair, two full halo windows)
+osb_status umma_pair_first_forward(const UmmaLayer& L1b, const float* w1a, const float* b1a, const uint8_t* img, int B, int H,
+                                   int W, float act_scale, __half* out_hi, __half* out_lo, float out_scale, cudaStream_t st,
+                                   int max_ctas = 0, unsigned long long* dbg = nullptr);
+osb_status umma_pair_maps(CUtensorMap* hi, CUtensorMap* lo, __half* p_hi, __half* p_lo, int B, int H, int W);
+osb_status umma_pair_conv64_forward(const UmmaLayer& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int B, int H, int W,
+                                    float act_scale, __half* out_hi, __half* out_lo, float out_scale, int pool, cudaStream_t st,
+                                    int max_ctas = 0, unsigned long long* dbg = nullptr);
 // depthwise 3x3 + bias + ReLU6, fp32 NHWC in, split fp16 planes out (feeds a pointwise tcgen05 conv)
 osb_status umma_dwconv_forward(const float* w_tap_c, const float* bias, const float* x, __half* out_hi, __half* out_lo,
                                int B, int H, int W, int C, int stride, float out_scale, cudaStream_t st);

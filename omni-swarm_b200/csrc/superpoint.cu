@@ -41,6 +41,7 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
   if (const char* e = getenv("OSB_SP_FUSED_SOFTMAX")) fused_softmax = atoi(e) != 0;
   if (const char* e = getenv("OSB_SP_FUSE1")) fuse_first = atoi(e) != 0;
   if (const char* e = getenv("OSB_SP_HALO64")) halo64 = atoi(e) != 0;
+  if (const char* e = getenv("OSB_SP_PAIR")) pair64 = atoi(e) != 0;
   // ---- weights ----
   const float* p = weights;
   {
@@ -110,6 +111,8 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
       if (i == 2 || i == 3) {
         s = umma_halo_maps(&halo[i], in_hi[i], in_lo[i], max_batch, h, w);
         if (s != OSB_OK) return s;
+        s = umma_pair_maps(&pairA[i], &pairB[i], in_hi[i], in_lo[i], max_batch, h, w);
+        if (s != OSB_OK) return s;
       }
     }
   }
@@ -160,7 +163,13 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
     return umma_conv_forward(UL[i], tmA[i], tmB[i], B, h, w, SA, in_hi[out_layer], in_lo[out_layer], nullptr,
                              SP_COUT[i], SP_COUT[i], SA, 1, pool, st);
   };
-  if (fuse_first) {
+  static const int dbg_layer = [] { const char* e = getenv("OSB_F1_DBG_LAYER"); return e ? atoi(e) : 1; }();
+  if (fuse_first && pair64) {
+    mark(st);
+    RUN(umma_pair_first_forward(UL[1], w1a, b1a, img_dev, B, H, W, SA, in_hi[2], in_lo[2], SA, st, 0,
+                                (layer_prof && dbg_layer == 1) ? d_f1dbg : nullptr));     // conv1a+conv1b+pool -> B
+    mark(st);
+  } else if (fuse_first) {
     mark(st);                                                                             // (conv1a has no launch of its own)
     RUN(umma_conv1_fused_forward(UL[1], w1a, b1a, img_dev, B, H, W, SA, in_hi[2], in_lo[2], SA, st, 0,
                                  (layer_prof && !(getenv("OSB_F1_DBG_LAYER") && atoi(getenv("OSB_F1_DBG_LAYER")) != 1)) ? d_f1dbg : nullptr));   // conv1a+conv1b+pool -> B
@@ -171,8 +180,14 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
     RUN(conv(1, H, W, 2, 1));                                                             // conv1b + pool     -> B
     mark(st);
   }
-  if (halo64) {
-    static const int dbg_layer = [] { const char* e = getenv("OSB_F1_DBG_LAYER"); return e ? atoi(e) : 1; }();
+  if (pair64) {
+    RUN(umma_pair_conv64_forward(UL[2], pairA[2], pairB[2], B, H / 2, W / 2, SA, in_hi[3], in_lo[3], SA, 0, st, 0,
+                                 (layer_prof && dbg_layer == 2) ? d_f1dbg : nullptr));                  // conv2a   -> A
+    mark(st);
+    RUN(umma_pair_conv64_forward(UL[3], pairA[3], pairB[3], B, H / 2, W / 2, SA, in_hi[4], in_lo[4], SA, 1, st, 0,
+                                 (layer_prof && dbg_layer == 3) ? d_f1dbg : nullptr));                  // conv2b + pool -> B
+    mark(st);
+  } else if (halo64) {
     RUN(umma_conv64_halo_forward(UL[2], halo[2], B, H / 2, W / 2, SA, in_hi[3], in_lo[3], SA, 0, st, 0,
                                  (layer_prof && dbg_layer == 2) ? d_f1dbg : nullptr));                  // conv2a   -> A
     mark(st);

@@ -44,8 +44,14 @@ struct SuperPoint {
   cudaEvent_t ev_semi = nullptr, ev_kp = nullptr;
   bool overlap_kp = true;
   unsigned long long* d_f1dbg = nullptr;   // cycle counters of the fused first-layers kernel (filled while layer_prof is on)
+  CUtensorMap pairA[4], pairB[4]; // [2], [3]: conv2a / conv2b inputs for the CTA-pair kernel (one 18-row box per plane)
+  bool pair64 = false;            // OSB_SP_PAIR=1: conv1a+1b, conv2a, conv2b on CTA pairs (conv64_pair.cu, tcgen05.mma.cta_group::2).
+                                  // Bit-identical, measured SLOWER than the single-CTA kernels (r02: conv1 0.57 vs 0.47 ms, conv2a
+                                  // 0.120 vs 0.116 ms; the pair's MMA stream ran at 134 cycles per K step against 114) -- kept as a switch
   HaloMaps halo[4];               // [2], [3]: conv2a / conv2b inputs for the halo-window kernel
-  bool halo64 = true;             // conv2a / conv2b through conv64_halo_kernel (OSB_SP_HALO64=0: conv_umma_kernel<64,RES>)
+  bool halo64 = false;            // OSB_SP_HALO64=1: conv2a / conv2b through conv64_halo_kernel<false> (one TMA halo window per tile:
+                                  // 2.6x less activation traffic, but the 3 rows the two windows share are loaded after the previous
+                                  // tile's MMAs and cost a ~1200-cycle bubble per tile: 0.118 vs 0.116 ms, r02) -- kept as a switch
   bool fuse_first = true;          // conv1a computed inside conv1b's kernel (conv1_fused.cu; OSB_SP_FUSE1=0: two kernels)
   bool fused_softmax = true;       // detector-head softmax + pixel shuffle in convPb's epilogue (OSB_SP_FUSED_SOFTMAX=0: two kernels)
   osb_status network(const uint8_t* img_dev, int B, cudaStream_t st, const KpJob* kp = nullptr);

@@ -226,14 +226,18 @@ def test_fused_first_layers_bit_identical(gpu, size):
                      np.zeros((H, W), np.uint8)])
     imgs[2, ::7, ::5] = 255
     out = {}
-    for mode in ("1", "0"):                       # "1": fused first layers + halo-window conv2a/2b; "0": the TMA-box kernels
-        os.environ["OSB_SP_FUSE1"] = mode
-        os.environ["OSB_SP_HALO64"] = mode
+    # "pair": CTA-pair kernels (tcgen05.mma.cta_group::2) for conv1a+1b, conv2a, conv2b; "halo": their single-CTA forms;
+    # "box": conv1a through HBM + the TMA-box kernel for every layer
+    modes = {"pair": ("1", "1", "1"), "halo": ("1", "1", "0"), "box": ("0", "0", "0")}
+    for name, (f1, h64, pr) in modes.items():
+        os.environ["OSB_SP_FUSE1"], os.environ["OSB_SP_HALO64"], os.environ["OSB_SP_PAIR"] = f1, h64, pr
         sp = host.SuperPoint(wts, comp, mean, W, H, 0.015, 200, max_batch=3)
         res = sp.inference_batch(imgs)
-        out[mode] = [(sp.read("semi", b), sp.read("desc", b), res[b][0], res[b][1]) for b in range(3)]
+        out[name] = [(sp.read("semi", b), sp.read("desc", b), res[b][0], res[b][1]) for b in range(3)]
         sp.close()
-    os.environ.pop("OSB_SP_FUSE1"); os.environ.pop("OSB_SP_HALO64")
+    for k in ("OSB_SP_FUSE1", "OSB_SP_HALO64", "OSB_SP_PAIR"):
+        os.environ.pop(k)
     for b in range(3):
-        for a, c in zip(out["1"][b], out["0"][b]):
-            assert np.array_equal(a, c, equal_nan=True), f"image {b}: fused and unfused paths differ"
+        for name in ("pair", "halo"):
+            for a, c in zip(out[name][b], out["box"][b]):
+                assert np.array_equal(a, c, equal_nan=True), f"image {b}: the {name} kernels and the TMA-box kernels differ"
