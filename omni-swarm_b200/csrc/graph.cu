@@ -983,6 +983,12 @@ struct osb_solver {
   std::vector<int32_t> g_type, g_ia, g_ib;
   size_t g_uploaded = 0;            // factors whose type / huber / payload are already on the device
   bool g_static_valid = false;      // false after a one-shot osb_solver_solve overwrote the device factor arrays
+  // topology cache of the resident graph: the path cover, the internal numbering and the CSR / slot tables depend only on
+  // (fixed, type, ia, ib, payload weights), not on the poses -- a window that is re-solved without new frames (or after
+  // set_poses) re-uses them on the host AND on the device (0.5 ms of host work per solve otherwise)
+  unsigned long long g_topo_version = 1, cached_topo = 0;
+  std::vector<int32_t> cached_order;
+  int cached_nres = 0;
 };
 
 extern "C" void osb_solve_default_options(osb_solve_options* o) {
@@ -1147,17 +1153,30 @@ static osb_status validate_graph(int n_nodes, int n_factors, const int32_t* type
 static osb_status solver_run(osb_solver* h, int n_nodes, double* poses, const uint8_t* fixed, int n_factors,
                              const int32_t* type, const int32_t* ia, const int32_t* ib, const double* payload,
                              const uint8_t* huber, bool upload_static, const osb_solve_options* opt,
-                             osb_solve_summary* summary) {
+                             osb_solve_summary* summary, unsigned long long topo_key = 0) {
   osb_solve_options o;
   if (opt) o = *opt; else osb_solve_default_options(&o);
   // Internal node numbering: the paths of the chain plan are runs of consecutive ids (fixed nodes last).  Everything on
   // the device uses the internal ids; poses are permuted on the way in and out.
   const size_t n = n_nodes, m = n_factors;
+  cudaStream_t st = h->stream;
+  std::vector<double> x_p(4 * n);
+  // resident graph with unchanged topology: plan, numbering and every index table are already on the device
+  const bool reuse = topo_key != 0 && topo_key == h->cached_topo && h->cached_order.size() == n;
+  std::vector<int32_t> order_local;
+  int n_res = 0;
+  if (reuse) {
+    for (size_t i = 0; i < n; ++i) {
+      const int o2 = h->cached_order[i];
+      for (int k = 0; k < 4; ++k) x_p[4 * i + k] = poses[4 * (size_t)o2 + k];
+    }
+    n_res = h->cached_nres;
+    OSB_CUDA(cudaMemcpyAsync(h->d_x0, x_p.data(), 4 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else {
   ChainPlan plan;
   build_chain_plan(n_nodes, fixed, n_factors, type, ia, ib, payload, plan);
   std::vector<int32_t> ia_p(m), ib_p(m);
   std::vector<uint8_t> fixed_p(n);
-  std::vector<double> x_p(4 * n);
   for (size_t f = 0; f < m; ++f) { ia_p[f] = plan.inv[ia[f]]; ib_p[f] = plan.inv[ib[f]]; }
   for (size_t i = 0; i < n; ++i) {
     const int o = plan.order[i];
@@ -1187,11 +1206,9 @@ static osb_status solver_run(osb_solver* h, int n_nodes, double* poses, const ui
     std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
     for (size_t f = 0; f < m; ++f) { slot_a[f] = fill[ia_p[f]]++; slot_b[f] = fill[ib_p[f]]++; }
   }
-  int n_res = 0;
   for (size_t f = 0; f < m; ++f)
     n_res += type[f] == OSB_FACTOR_DISTANCE ? 1 : type[f] == OSB_FACTOR_RELPOSE ? 4
              : (((int)payload[f * OSB_PAYLOAD_LEN + 10] & 1) ? 3 : 2);
-  cudaStream_t st = h->stream;
   OSB_CUDA(cudaMemcpyAsync(h->d_fixed, fixed_p.data(), n, cudaMemcpyHostToDevice, st));
   if (upload_static) {
     OSB_CUDA(cudaMemcpyAsync(h->d_huber, huber, m, cudaMemcpyHostToDevice, st));
@@ -1207,6 +1224,13 @@ static osb_status solver_run(osb_solver* h, int n_nodes, double* poses, const ui
   OSB_CUDA(cudaMemcpyAsync(h->d_link, plan.link.data(), n, cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_es_ptr, es_ptr.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   OSB_CUDA(cudaMemcpyAsync(h->d_es_slot, es_slot.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  // the staging vectors above die at the end of this block: the copies must have left them
+  OSB_CUDA(cudaStreamSynchronize(st));
+  h->cached_order = plan.order;
+  h->cached_nres = n_res;
+  h->cached_topo = topo_key;               // 0 (one-shot solve) never matches
+  }
+  const std::vector<int32_t>& order = h->cached_order;
 
   SolverDev P;
   P.n = n_nodes; P.m = n_factors;
@@ -1280,7 +1304,7 @@ static osb_status solver_run(osb_solver* h, int n_nodes, double* poses, const ui
   OSB_CUDA(cudaMemcpyAsync(summary, h->d_summary, sizeof(osb_solve_summary), cudaMemcpyDeviceToHost, st));
   OSB_CUDA(cudaStreamSynchronize(st));
   for (size_t i = 0; i < n; ++i)
-    for (int k = 0; k < 4; ++k) poses[4 * (size_t)plan.order[i] + k] = x_p[4 * i + k];
+    for (int k = 0; k < 4; ++k) poses[4 * (size_t)order[i] + k] = x_p[4 * i + k];
   float ms = 0.f;
   OSB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   summary->solve_ms = ms;
@@ -1299,6 +1323,7 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
   if (s != OSB_OK) return s;
   std::lock_guard<std::mutex> lk(h->mu);
   h->g_static_valid = false;              // the device factor arrays now hold this graph, not the resident one
+  h->cached_topo = 0;                     // ... and so do the index tables
   return solver_run(h, n_nodes, poses, fixed, n_factors, type, ia, ib, payload, huber, true, opt, summary);
 }
 
@@ -1315,6 +1340,7 @@ extern "C" osb_status osb_solver_graph_clear(osb_solver* h) {
   h->g_poses.clear(); h->g_payload.clear(); h->g_fixed.clear(); h->g_huber.clear();
   h->g_type.clear(); h->g_ia.clear(); h->g_ib.clear();
   h->g_uploaded = 0; h->g_static_valid = true;
+  ++h->g_topo_version;
   return OSB_OK;
 }
 
@@ -1327,6 +1353,7 @@ extern "C" osb_status osb_solver_graph_add_nodes(osb_solver* h, int n, const dou
   if (first_id) *first_id = (int32_t)have;
   h->g_poses.insert(h->g_poses.end(), poses, poses + 4 * (size_t)n);
   for (int i = 0; i < n; ++i) h->g_fixed.push_back(fixed ? fixed[i] : 0);
+  ++h->g_topo_version;
   return OSB_OK;
 }
 
@@ -1343,6 +1370,7 @@ extern "C" osb_status osb_solver_graph_add_factors(osb_solver* h, int m, const i
   h->g_ib.insert(h->g_ib.end(), ib, ib + m);
   h->g_huber.insert(h->g_huber.end(), huber, huber + m);
   h->g_payload.insert(h->g_payload.end(), payload, payload + (size_t)m * OSB_PAYLOAD_LEN);
+  ++h->g_topo_version;
   return OSB_OK;
 }
 
@@ -1351,6 +1379,7 @@ extern "C" osb_status osb_solver_graph_set_fixed(osb_solver* h, int node, int fi
   std::lock_guard<std::mutex> lk(h->mu);
   OSB_REQUIRE(node >= 0 && (size_t)node < h->g_fixed.size(), "node out of range");
   h->g_fixed[node] = fixed ? 1 : 0;
+  ++h->g_topo_version;
   return OSB_OK;
 }
 
@@ -1398,6 +1427,7 @@ extern "C" osb_status osb_solver_graph_drop_oldest(osb_solver* h, int n_nodes) {
   }
   h->g_type.resize(w); h->g_ia.resize(w); h->g_ib.resize(w); h->g_huber.resize(w); h->g_payload.resize(w * OSB_PAYLOAD_LEN);
   h->g_uploaded = 0;                       // factor positions moved: re-send on the next solve
+  ++h->g_topo_version;
   return OSB_OK;
 }
 
@@ -1406,7 +1436,7 @@ extern "C" osb_status osb_solver_solve_resident(osb_solver* h, const osb_solve_o
   std::lock_guard<std::mutex> lk(h->mu);
   const size_t n = h->g_fixed.size(), m = h->g_type.size();
   OSB_REQUIRE(n > 0 && m > 0, "the resident graph is empty");
-  if (!h->g_static_valid) { h->g_uploaded = 0; h->g_static_valid = true; }
+  if (!h->g_static_valid) { h->g_uploaded = 0; h->g_static_valid = true; h->cached_topo = 0; }
   if (h->g_uploaded < m) {                 // only the factors added since the last solve cross PCIe
     const size_t f0 = h->g_uploaded, k = m - f0;
     cudaStream_t st = h->stream;
@@ -1417,7 +1447,7 @@ extern "C" osb_status osb_solver_solve_resident(osb_solver* h, const osb_solve_o
     h->g_uploaded = m;
   }
   return solver_run(h, (int)n, h->g_poses.data(), h->g_fixed.data(), (int)m, h->g_type.data(), h->g_ia.data(),
-                    h->g_ib.data(), h->g_payload.data(), h->g_huber.data(), false, opt, summary);
+                    h->g_ib.data(), h->g_payload.data(), h->g_huber.data(), false, opt, summary, h->g_topo_version);
 }
 
 extern "C" osb_status osb_solver_phase_cycles(osb_solver* h, double* out12) {
