@@ -518,6 +518,10 @@ int osb_swarm_transport(osb_swarm* h);     /* what exchange_async uses: 1 = peer
 int osb_swarm_rank(osb_swarm* h);
 int osb_swarm_world(osb_swarm* h);
 
+/* The convolution kernels are persistent (one CTA per SM, statically strided tiles): they run at full speed only when all of
+ * their CTAs are resident.  A host that keeps another kernel on the GPU beside the front-end -- the pose-graph solve holds a
+ * 16-CTA cluster for milliseconds -- caps them at n_sms (process-wide; 0 = every SM). */
+void osb_set_sm_budget(int n_sms);
 /* number of kernels launched by this library since it was loaded (all handles), for bench.py's gpu_launches */
 int64_t osb_launch_count(void);
 

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <string>
 #include <utility>
+#include <unordered_map>
 #include <vector>
 
 #include "omniswarm_b200.h"
@@ -157,9 +158,11 @@ class BFMatcherB200 {
 class FlatPoseGraph {
  public:
   // every distinct pose block (double[4]) gets a node index; shared blocks (not-moving keyframes, :291-294) map once
-  int node(double* pose) {
-    for (size_t i = 0; i < ptr_.size(); ++i) if (ptr_[i] == pose) return (int)i;
+  int node(double* pose) {                                          // O(1): a C5 window has 2 000 blocks, 24 000 look-ups
+    auto it = index_.find(pose);
+    if (it != index_.end()) return it->second;
     ptr_.push_back(pose); fixed_.push_back(0);
+    index_.emplace(pose, (int)ptr_.size() - 1);
     return (int)ptr_.size() - 1;
   }
   void set_constant(double* pose) { fixed_[node(pose)] = 1; }                       // SetParameterBlockConstant (:1198)
@@ -175,6 +178,24 @@ class FlatPoseGraph {
     for (int i = 0; i < 4; ++i) pl[i] = meas[i];
     for (int i = 0; i < 16; ++i) pl[4 + i] = S[i];
     push(OSB_FACTOR_RELPOSE, pa, pb, pl, huber);
+  }
+  // DroneDetection4dFactor::Create (swarm_localization_factors.hpp:273-367; reached at swarm_localization_solver.cpp:1088-1094):
+  // dir = unit bearing [3], tan_base = detect_tan_base 2x3 row-major, inv_dep and its flag, the antenna z offset OR the two
+  // pre-composed dposes (x y z yaw each), DETECTION_SPHERE_STD / DETECTION_INV_DEP_STD.  Payload layout: omniswarm_b200.h.
+  void add_detection(double* pa, double* pb, const double dir[3], const double tan_base[6], double inv_dep, bool enable_depth,
+                     double extrinsic_z, const double* dposea /*[4] or null*/, const double* dposeb /*[4] or null*/,
+                     double sphere_std, double inv_dep_std, bool huber) {
+    if (pa == pb) return;
+    double pl[OSB_PAYLOAD_LEN] = {0};
+    for (int i = 0; i < 3; ++i) pl[i] = dir[i];
+    for (int i = 0; i < 6; ++i) pl[3 + i] = tan_base[i];
+    pl[9] = inv_dep;
+    const bool dpose = dposea != nullptr && dposeb != nullptr;
+    pl[10] = (double)((enable_depth ? 1 : 0) | (dpose ? 2 : 0));
+    pl[11] = extrinsic_z;
+    if (dpose) for (int i = 0; i < 4; ++i) { pl[12 + i] = dposea[i]; pl[16 + i] = dposeb[i]; }
+    pl[20] = sphere_std; pl[21] = inv_dep_std;
+    push(OSB_FACTOR_DETECTION, pa, pb, pl, huber);
   }
   osb_solve_summary solve(osb_solver* solver, const osb_solve_options* opt = nullptr) {
     const int n = (int)ptr_.size(), m = (int)type_.size();
@@ -194,6 +215,7 @@ class FlatPoseGraph {
     payload_.insert(payload_.end(), pl, pl + OSB_PAYLOAD_LEN);
   }
   std::vector<double*> ptr_;
+  std::unordered_map<double*, int> index_;
   std::vector<uint8_t> fixed_, huber_;
   std::vector<int32_t> type_, ia_, ib_;
   std::vector<double> payload_;
@@ -206,9 +228,11 @@ class ResidentPoseGraph {
  public:
   explicit ResidentPoseGraph(osb_solver* solver) : solver_(solver) { check(osb_solver_graph_clear(solver_), "osb_solver_graph_clear"); }
   int node(double* pose) {
-    for (size_t i = 0; i < ptr_.size(); ++i) if (ptr_[i] == pose) return (int)i;
+    auto it = index_.find(pose);
+    if (it != index_.end()) return it->second;
     ptr_.push_back(pose);
     new_fixed_.push_back(0);
+    index_.emplace(pose, (int)ptr_.size() - 1);
     return (int)ptr_.size() - 1;
   }
   void set_constant(double* pose) {
@@ -227,6 +251,24 @@ class ResidentPoseGraph {
     for (int i = 0; i < 4; ++i) pl[i] = meas[i];
     for (int i = 0; i < 16; ++i) pl[4 + i] = S[i];
     push(OSB_FACTOR_RELPOSE, pa, pb, pl, huber);
+  }
+  // DroneDetection4dFactor::Create (swarm_localization_factors.hpp:273-367; reached at swarm_localization_solver.cpp:1088-1094):
+  // dir = unit bearing [3], tan_base = detect_tan_base 2x3 row-major, inv_dep and its flag, the antenna z offset OR the two
+  // pre-composed dposes (x y z yaw each), DETECTION_SPHERE_STD / DETECTION_INV_DEP_STD.  Payload layout: omniswarm_b200.h.
+  void add_detection(double* pa, double* pb, const double dir[3], const double tan_base[6], double inv_dep, bool enable_depth,
+                     double extrinsic_z, const double* dposea /*[4] or null*/, const double* dposeb /*[4] or null*/,
+                     double sphere_std, double inv_dep_std, bool huber) {
+    if (pa == pb) return;
+    double pl[OSB_PAYLOAD_LEN] = {0};
+    for (int i = 0; i < 3; ++i) pl[i] = dir[i];
+    for (int i = 0; i < 6; ++i) pl[3 + i] = tan_base[i];
+    pl[9] = inv_dep;
+    const bool dpose = dposea != nullptr && dposeb != nullptr;
+    pl[10] = (double)((enable_depth ? 1 : 0) | (dpose ? 2 : 0));
+    pl[11] = extrinsic_z;
+    if (dpose) for (int i = 0; i < 4; ++i) { pl[12 + i] = dposea[i]; pl[16 + i] = dposeb[i]; }
+    pl[20] = sphere_std; pl[21] = inv_dep_std;
+    push(OSB_FACTOR_DETECTION, pa, pb, pl, huber);
   }
   osb_solve_summary solve(const osb_solve_options* opt = nullptr) {
     flush();
@@ -261,6 +303,7 @@ class ResidentPoseGraph {
   osb_solver* solver_;
   int sent_nodes_ = 0;
   std::vector<double*> ptr_;
+  std::unordered_map<double*, int> index_;
   std::vector<uint8_t> new_fixed_, huber_;
   std::vector<int32_t> type_, ia_, ib_;
   std::vector<double> payload_;

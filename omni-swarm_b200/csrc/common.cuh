@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -54,6 +55,18 @@ inline int current_device() {
   cudaGetDevice(&dev);
   return (dev >= 0 && dev < 64) ? dev : 0;
 }
+// Every handle remembers the device it was created on and its entry points run there whatever the calling thread's current
+// device is (a new host thread starts on device 0: the reference's nodelet calls from several spinner threads).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    int cur = 0;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != dev) { prev = cur; cudaSetDevice(dev); }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 struct PerDeviceOnce {                     // first(dev) is true exactly once per device, thread-safe
   std::atomic<unsigned long long> mask{0};
   bool first(int dev) { return !((mask.fetch_or(1ull << dev, std::memory_order_acq_rel) >> dev) & 1ull); }
@@ -80,6 +93,18 @@ inline int num_sms() {
     cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+// SM budget of the PERSISTENT kernels (one CTA per SM, statically strided tiles): such a grid only makes progress at full
+// speed when every CTA is resident, so a host that runs something else on the GPU beside the front-end (the pose-graph
+// solve holds 16 SMs for milliseconds) caps them with osb_set_sm_budget; 0 = all SMs.
+extern std::atomic<int> g_sm_budget;
+inline int persistent_ctas(int max_ctas = 0) {
+  int n = num_sms();
+  const int b = g_sm_budget.load(std::memory_order_relaxed);
+  if (b > 0) n = std::min(n, b);
+  if (max_ctas > 0) n = std::min(n, max_ctas);
+  return std::max(1, n);
 }
 
 inline osb_status require_device() {

@@ -390,7 +390,7 @@ osb_status umma_conv1_fused_forward(const UmmaLayer& L1b, const float* w1a, cons
   P.act_scale = act_scale; P.inv_scale = 1.0f / (act_scale * L1b.w_scale); P.out_scale = out_scale;
   OSB_SMEM_OPT_IN(conv64_halo_kernel<true>, F1_SMEM);
   const int tiles = B * cdiv(W, F1_TW) * cdiv(H, F1_TH);
-  const int grid = std::min(tiles, max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms());
+  const int grid = std::min(tiles, persistent_ctas(max_ctas));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(F1_THREADS); cfg.dynamicSmemBytes = F1_SMEM; cfg.stream = st;
   // (the activation maps are unused by the FIRST instantiation: the weight maps stand in)
@@ -424,7 +424,7 @@ osb_status umma_conv64_halo_forward(const UmmaLayer& L, const HaloMaps& M, int B
   P.act_scale = act_scale; P.inv_scale = 1.0f / (act_scale * L.w_scale); P.out_scale = out_scale;
   OSB_SMEM_OPT_IN(conv64_halo_kernel<false>, F1_SMEM);
   const int tiles = B * cdiv(W, F1_TW) * cdiv(H, F1_TH);
-  const int grid = std::min(tiles, max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms());
+  const int grid = std::min(tiles, persistent_ctas(max_ctas));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(F1_THREADS); cfg.dynamicSmemBytes = F1_SMEM; cfg.stream = st;
   OSB_CUDA(cudaLaunchKernelEx(&cfg, conv64_halo_kernel<false>, L.tm_hi, L.tm_lo, M.a15_hi, M.a15_lo, M.a3_hi, M.a3_lo, P));

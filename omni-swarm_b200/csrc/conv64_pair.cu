@@ -378,7 +378,7 @@ static osb_status launch_pair(bool first, const UmmaLayer& L, const CUtensorMap&
                               cudaStream_t st, int max_ctas) {
   const int tiles = P.B * cdiv(P.W, P2_TW) * cdiv(P.H, P2_TH);
   const int pairs = (tiles + 1) / 2;
-  int ctas = max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms();
+  int ctas = persistent_ctas(max_ctas);
   ctas = std::max(2, std::min(ctas & ~1, 2 * pairs));          // whole clusters
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(P2_THREADS); cfg.dynamicSmemBytes = P2_SMEM; cfg.stream = st;

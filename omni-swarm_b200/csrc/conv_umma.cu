@@ -555,7 +555,7 @@ static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, 
   OSB_SMEM_OPT_IN((conv_umma_kernel<N, RES, SPLIT>), Cfg::SMEM_BYTES);
   const int tiles = P.B * cdiv(P.W, UM_TW) * cdiv(P.H, UM_TH) * P.n_split;
   // persistent CTAs, one per SM; `max_ctas` leaves SMs free for a kernel running beside this one on another stream
-  const int grid = std::min(tiles, max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms());
+  const int grid = std::min(tiles, persistent_ctas(max_ctas));
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;

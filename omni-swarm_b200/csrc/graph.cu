@@ -974,6 +974,13 @@ struct osb_solver {
   osb_solve_summary* d_summary = nullptr;
   long long* d_dbg = nullptr;
   uint8_t* d_link = nullptr;
+  // pinned staging for what crosses PCIe on EVERY solve (poses in, poses + summary out): a copy to / from pageable memory
+  // blocks inside the driver until the stream reaches it -- for the results that is the whole solve, and other host threads
+  // (the keyframe front-end of the same process) could not launch meanwhile (measured: 640 -> 57 keyframes/s beside a
+  // back-to-back solver thread).  Pinned copies are asynchronous; the one wait is a cudaStreamSynchronize.
+  double* h_x = nullptr;
+  osb_solve_summary* h_summary = nullptr;
+  int device = 0;
   int32_t *d_es_ptr = nullptr, *d_es_slot = nullptr;
   double *d_es = nullptr, *d_En = nullptr;
   int last_grid = 0, last_cluster = 0, last_jsmem = 0, last_chain = 0, last_f32 = 0;
@@ -1047,6 +1054,9 @@ extern "C" osb_status osb_solver_create(osb_solver** out, int max_nodes, int max
   OSB_CUDA(cudaMalloc(&h->d_es_slot, m * sizeof(int32_t)));
   OSB_CUDA(cudaMalloc(&h->d_es, 16 * m * sizeof(double)));
   OSB_CUDA(cudaMalloc(&h->d_En, 16 * n * sizeof(double)));
+  OSB_CUDA(cudaHostAlloc((void**)&h->h_x, 4 * n * sizeof(double), cudaHostAllocDefault));
+  OSB_CUDA(cudaHostAlloc((void**)&h->h_summary, sizeof(osb_solve_summary), cudaHostAllocDefault));
+  h->device = current_device();
   *out = h;
   return OSB_OK;
 }
@@ -1058,6 +1068,8 @@ extern "C" osb_status osb_solver_destroy(osb_solver* h) {
   cudaFree(h->d_x1); cudaFree(h->d_Jg); cudaFree(h->d_lin); cudaFree(h->d_nodevec); cudaFree(h->d_cs); cudaFree(h->d_gs); cudaFree(h->d_hs);
   cudaFree(h->d_partial); cudaFree(h->d_out); cudaFree(h->d_summary); cudaFree(h->d_dbg);
   cudaFree(h->d_link); cudaFree(h->d_es_ptr); cudaFree(h->d_es_slot); cudaFree(h->d_es); cudaFree(h->d_En);
+  if (h->h_x) cudaFreeHost(h->h_x);
+  if (h->h_summary) cudaFreeHost(h->h_summary);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1171,7 +1183,8 @@ static osb_status solver_run(osb_solver* h, int n_nodes, double* poses, const ui
       for (int k = 0; k < 4; ++k) x_p[4 * i + k] = poses[4 * (size_t)o2 + k];
     }
     n_res = h->cached_nres;
-    OSB_CUDA(cudaMemcpyAsync(h->d_x0, x_p.data(), 4 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    memcpy(h->h_x, x_p.data(), 4 * n * sizeof(double));
+    OSB_CUDA(cudaMemcpyAsync(h->d_x0, h->h_x, 4 * n * sizeof(double), cudaMemcpyHostToDevice, st));
   } else {
   ChainPlan plan;
   build_chain_plan(n_nodes, fixed, n_factors, type, ia, ib, payload, plan);
@@ -1300,9 +1313,11 @@ static osb_status solver_run(osb_solver* h, int n_nodes, double* poses, const ui
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   OSB_CUDA(cudaEventRecord(h->ev1, st));
-  OSB_CUDA(cudaMemcpyAsync(x_p.data(), h->d_out, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  OSB_CUDA(cudaMemcpyAsync(summary, h->d_summary, sizeof(osb_solve_summary), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaMemcpyAsync(h->h_x, h->d_out, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaMemcpyAsync(h->h_summary, h->d_summary, sizeof(osb_solve_summary), cudaMemcpyDeviceToHost, st));
   OSB_CUDA(cudaStreamSynchronize(st));
+  memcpy(x_p.data(), h->h_x, 4 * n * sizeof(double));
+  *summary = *h->h_summary;
   for (size_t i = 0; i < n; ++i)
     for (int k = 0; k < 4; ++k) poses[4 * (size_t)order[i] + k] = x_p[4 * i + k];
   float ms = 0.f;
@@ -1322,6 +1337,7 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
   osb_status s = validate_graph(n_nodes, n_factors, type, ia, ib);
   if (s != OSB_OK) return s;
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   h->g_static_valid = false;              // the device factor arrays now hold this graph, not the resident one
   h->cached_topo = 0;                     // ... and so do the index tables
   return solver_run(h, n_nodes, poses, fixed, n_factors, type, ia, ib, payload, huber, true, opt, summary);
@@ -1337,6 +1353,7 @@ extern "C" osb_status osb_solver_solve(osb_solver* h, int n_nodes, double* poses
 extern "C" osb_status osb_solver_graph_clear(osb_solver* h) {
   OSB_REQUIRE(h != nullptr, "null handle");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   h->g_poses.clear(); h->g_payload.clear(); h->g_fixed.clear(); h->g_huber.clear();
   h->g_type.clear(); h->g_ia.clear(); h->g_ib.clear();
   h->g_uploaded = 0; h->g_static_valid = true;
@@ -1348,6 +1365,7 @@ extern "C" osb_status osb_solver_graph_add_nodes(osb_solver* h, int n, const dou
                                                  int32_t* first_id) {
   OSB_REQUIRE(h != nullptr && n > 0 && poses != nullptr, "bad argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   const size_t have = h->g_fixed.size();
   if (have + (size_t)n > (size_t)h->max_nodes) { set_error("osb_solver_graph_add_nodes", "node capacity exceeded"); return OSB_ERR_CAPACITY; }
   if (first_id) *first_id = (int32_t)have;
@@ -1361,6 +1379,7 @@ extern "C" osb_status osb_solver_graph_add_factors(osb_solver* h, int m, const i
                                                    const int32_t* ib, const double* payload, const uint8_t* huber) {
   OSB_REQUIRE(h != nullptr && m > 0 && type && ia && ib && payload && huber, "bad argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   const size_t have = h->g_type.size();
   if (have + (size_t)m > (size_t)h->max_factors) { set_error("osb_solver_graph_add_factors", "factor capacity exceeded"); return OSB_ERR_CAPACITY; }
   osb_status s = validate_graph((int)h->g_fixed.size(), m, type, ia, ib);
@@ -1377,6 +1396,7 @@ extern "C" osb_status osb_solver_graph_add_factors(osb_solver* h, int m, const i
 extern "C" osb_status osb_solver_graph_set_fixed(osb_solver* h, int node, int fixed) {
   OSB_REQUIRE(h != nullptr, "null handle");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   OSB_REQUIRE(node >= 0 && (size_t)node < h->g_fixed.size(), "node out of range");
   h->g_fixed[node] = fixed ? 1 : 0;
   ++h->g_topo_version;
@@ -1386,6 +1406,7 @@ extern "C" osb_status osb_solver_graph_set_fixed(osb_solver* h, int node, int fi
 extern "C" osb_status osb_solver_graph_set_poses(osb_solver* h, int first, int n, const double* poses) {
   OSB_REQUIRE(h != nullptr && poses != nullptr, "bad argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   OSB_REQUIRE(first >= 0 && n >= 0 && (size_t)(first + n) <= h->g_fixed.size(), "node range out of bounds");
   std::copy(poses, poses + 4 * (size_t)n, h->g_poses.begin() + 4 * (size_t)first);
   return OSB_OK;
@@ -1394,6 +1415,7 @@ extern "C" osb_status osb_solver_graph_set_poses(osb_solver* h, int first, int n
 extern "C" osb_status osb_solver_graph_get_poses(osb_solver* h, int first, int n, double* poses) {
   OSB_REQUIRE(h != nullptr && poses != nullptr, "bad argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   OSB_REQUIRE(first >= 0 && n >= 0 && (size_t)(first + n) <= h->g_fixed.size(), "node range out of bounds");
   std::copy(h->g_poses.begin() + 4 * (size_t)first, h->g_poses.begin() + 4 * (size_t)(first + n), poses);
   return OSB_OK;
@@ -1402,6 +1424,7 @@ extern "C" osb_status osb_solver_graph_get_poses(osb_solver* h, int first, int n
 extern "C" osb_status osb_solver_graph_size(osb_solver* h, int32_t* n_nodes, int32_t* n_factors) {
   OSB_REQUIRE(h != nullptr, "null handle");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   if (n_nodes) *n_nodes = (int32_t)h->g_fixed.size();
   if (n_factors) *n_factors = (int32_t)h->g_type.size();
   return OSB_OK;
@@ -1412,6 +1435,7 @@ extern "C" osb_status osb_solver_graph_size(osb_solver* h, int32_t* n_nodes, int
 extern "C" osb_status osb_solver_graph_drop_oldest(osb_solver* h, int n_nodes) {
   OSB_REQUIRE(h != nullptr && n_nodes >= 0, "bad argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   OSB_REQUIRE((size_t)n_nodes <= h->g_fixed.size(), "cannot drop more nodes than the graph holds");
   if (n_nodes == 0) return OSB_OK;
   h->g_poses.erase(h->g_poses.begin(), h->g_poses.begin() + 4 * (size_t)n_nodes);
@@ -1434,6 +1458,7 @@ extern "C" osb_status osb_solver_graph_drop_oldest(osb_solver* h, int n_nodes) {
 extern "C" osb_status osb_solver_solve_resident(osb_solver* h, const osb_solve_options* opt, osb_solve_summary* summary) {
   OSB_REQUIRE(h != nullptr && summary != nullptr, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   const size_t n = h->g_fixed.size(), m = h->g_type.size();
   OSB_REQUIRE(n > 0 && m > 0, "the resident graph is empty");
   if (!h->g_static_valid) { h->g_uploaded = 0; h->g_static_valid = true; h->cached_topo = 0; }
@@ -1453,6 +1478,7 @@ extern "C" osb_status osb_solver_solve_resident(osb_solver* h, const osb_solve_o
 extern "C" osb_status osb_solver_phase_cycles(osb_solver* h, double* out12) {
   OSB_REQUIRE(h != nullptr && out12 != nullptr, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   long long c[8];
   OSB_CUDA(cudaMemcpy(c, h->d_dbg, sizeof(c), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 8; ++i) out12[i] = (double)c[i];
@@ -1464,6 +1490,7 @@ extern "C" osb_status osb_solver_phase_cycles(osb_solver* h, double* out12) {
 extern "C" osb_status osb_solver_chain_cycles(osb_solver* h, double* out128) {
   OSB_REQUIRE(h != nullptr && out128 != nullptr, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   long long c[128];
   OSB_CUDA(cudaMemcpy(c, h->d_dbg + 8, sizeof(c), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 128; ++i) out128[i] = (double)c[i];
@@ -1479,6 +1506,7 @@ extern "C" osb_status osb_solver_linearize(osb_solver* h, int n_nodes, const dou
   osb_status s = validate_graph(n_nodes, n_factors, type, ia, ib);
   if (s != OSB_OK) return s;
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   const size_t n = n_nodes, m = n_factors;
   cudaStream_t st = h->stream;
   OSB_CUDA(cudaMemcpyAsync(h->d_type, type, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));

@@ -342,6 +342,7 @@ using namespace osb;
 
 struct osb_frontend {
   osb_frontend_config cfg;
+  int device = 0;
   std::mutex mu;
   cudaStream_t stream = nullptr;
   SuperPoint sp;
@@ -377,6 +378,8 @@ struct osb_frontend {
   cudaStream_t stream2 = nullptr;                 // NetVLAD runs here, overlapped with the keypoint kernels
   cudaStream_t stream_sp = nullptr;               // SuperPoint runs here at the highest stream priority (null: caller's stream)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sp = nullptr;
+  DbDev* h_cnt = nullptr;                         // pinned [2]: row counters read back without blocking the driver (a copy
+                                                  // to pageable memory would hold other host threads' launches until it ran)
   cudaEvent_t ev_ingest = nullptr;                // recorded after the last ingest on ITS stream
   bool ingest_pending = false;
   bool profiling = false;
@@ -437,6 +440,7 @@ extern "C" osb_status osb_frontend_create(osb_frontend** out, const osb_frontend
   if (s != OSB_OK) return s;
   osb_frontend* h = new osb_frontend();
   h->cfg = *cfg;
+  h->device = current_device();
   const int nd = cfg->n_dirs, mn = cfg->max_num;
 #define FE_TRY(x) do { s = (x); if (s != OSB_OK) { osb_frontend_destroy(h); return s; } } while (0)
 #define FE_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error("osb_frontend_create", cudaGetErrorString(e_)); osb_frontend_destroy(h); return OSB_ERR_CUDA; } } while (0)
@@ -457,6 +461,7 @@ extern "C" osb_status osb_frontend_create(osb_frontend** out, const osb_frontend
   FE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   FE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   FE_CUDA(cudaEventCreateWithFlags(&h->ev_ingest, cudaEventDisableTiming));
+  FE_CUDA(cudaHostAlloc((void**)&h->h_cnt, 2 * sizeof(DbDev), cudaHostAllocDefault));
   FE_TRY(h->sp.init(sp_weights, n_sp_weights, cfg->width, cfg->height, cfg->sp_thres, mn, pca_comp, pca_mean, 2 * nd));
   h->sp.ks.write_surv = false;       // the survivor plane is only a parity hook of the standalone SuperPoint handle
   FE_TRY(h->nv.init(nv_weights, n_nv_weights, cfg->width, cfg->height, nd));
@@ -527,6 +532,7 @@ extern "C" osb_status osb_frontend_destroy(osb_frontend* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_ingest) cudaEventDestroy(h->ev_ingest);
+  if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream_sp) cudaStreamDestroy(h->stream_sp);
   if (h->ev_sp) cudaEventDestroy(h->ev_sp);
@@ -615,6 +621,7 @@ extern "C" osb_status osb_frontend_extract_dev(osb_frontend* h, const uint8_t* i
                                                osb_keyframe_record* record_dev, void* stream) {
   OSB_REQUIRE(h && images_up_dev && images_down_dev && record_dev, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t half = (size_t)h->cfg.n_dirs * h->cfg.width * h->cfg.height;
   OSB_CUDA(cudaMemcpyAsync(h->d_img, images_up_dev, half, cudaMemcpyDeviceToDevice, st));
@@ -626,6 +633,7 @@ extern "C" osb_status osb_frontend_extract(osb_frontend* h, const uint8_t* image
                                            int32_t msg_id, osb_keyframe_record* record_dev, void* stream) {
   OSB_REQUIRE(h && images_up && images_down && record_dev, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t half = (size_t)h->cfg.n_dirs * h->cfg.width * h->cfg.height;
   OSB_CUDA(cudaMemcpyAsync(h->d_img, images_up, half, cudaMemcpyHostToDevice, st));
@@ -677,6 +685,7 @@ extern "C" osb_status osb_frontend_ingest(osb_frontend* h, const osb_keyframe_re
                                           int skip, void* stream) {
   OSB_REQUIRE(h && records_dev, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   return fe_ingest(h, records_dev, n_records, skip, (cudaStream_t)stream);
 }
 
@@ -726,6 +735,7 @@ extern "C" osb_status osb_frontend_query(osb_frontend* h, const osb_keyframe_rec
                                          int nonkeyframe, osb_loop_result* result_dev, void* stream) {
   OSB_REQUIRE(h && record_dev && result_dev, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   return fe_query(h, record_dev, init_mode, nonkeyframe, result_dev, (cudaStream_t)stream);
 }
 
@@ -734,11 +744,10 @@ extern "C" osb_status osb_frontend_query(osb_frontend* h, const osb_keyframe_rec
 // rows are still being appended -- the scan grid is sized from it.
 static osb_status fe_refresh_counts(osb_frontend* h, cudaStream_t st) {
   if (h->ingest_pending) OSB_CUDA(cudaStreamWaitEvent(st, h->ev_ingest, 0));
-  DbDev hl, hr;
-  OSB_CUDA(cudaMemcpyAsync(&hl, h->db[0].dev, sizeof(DbDev), cudaMemcpyDeviceToHost, st));
-  OSB_CUDA(cudaMemcpyAsync(&hr, h->db[1].dev, sizeof(DbDev), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaMemcpyAsync(&h->h_cnt[0], h->db[0].dev, sizeof(DbDev), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(cudaMemcpyAsync(&h->h_cnt[1], h->db[1].dev, sizeof(DbDev), cudaMemcpyDeviceToHost, st));
   OSB_CUDA(cudaStreamSynchronize(st));
-  h->db[0].upper = hl.ntotal; h->db[1].upper = hr.ntotal;
+  h->db[0].upper = h->h_cnt[0].ntotal; h->db[1].upper = h->h_cnt[1].ntotal;
   h->ingest_pending = false;
   return OSB_OK;
 }
@@ -748,6 +757,7 @@ extern "C" osb_status osb_frontend_process(osb_frontend* h, const uint8_t* image
                                            osb_loop_result* result_host) {
   OSB_REQUIRE(h && images_up && images_down, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   cudaStream_t st = h->stream;
   const size_t half = (size_t)h->cfg.n_dirs * h->cfg.width * h->cfg.height;
   OSB_CUDA(cudaMemcpyAsync(h->d_img, images_up, half, cudaMemcpyHostToDevice, st));
@@ -766,6 +776,7 @@ extern "C" osb_status osb_frontend_set_cameras(osb_frontend* h, const double* in
   OSB_REQUIRE(h && intrinsics && left_extrinsics && right_extrinsics, "null argument");
   OSB_REQUIRE(intrinsics[0] > 0 && intrinsics[1] > 0 && triangle_thres > 0, "bad intrinsics / threshold");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   for (int i = 0; i < 4; ++i) h->K[i] = intrinsics[i];
   for (int d = 0; d < h->cfg.n_dirs; ++d)
     for (int i = 0; i < 7; ++i) { h->left_ext[d][i] = left_extrinsics[d * 7 + i]; h->right_ext[d][i] = right_extrinsics[d * 7 + i]; }
@@ -777,6 +788,7 @@ extern "C" osb_status osb_frontend_set_cameras(osb_frontend* h, const double* in
 extern "C" osb_status osb_frontend_set_drone_pose(osb_frontend* h, const double* pose_drone) {
   OSB_REQUIRE(h && pose_drone, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   for (int i = 0; i < 7; ++i) h->pose_drone[i] = pose_drone[i];
   return OSB_OK;
 }
@@ -784,6 +796,7 @@ extern "C" osb_status osb_frontend_set_drone_pose(osb_frontend* h, const double*
 extern "C" osb_status osb_frontend_set_profiling(osb_frontend* h, int enable) {
   OSB_REQUIRE(h != nullptr, "null handle");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   h->profiling = enable != 0;
   for (int i = 0; i < 9; ++i) h->ev_valid[i] = false;
   return OSB_OK;
@@ -792,6 +805,7 @@ extern "C" osb_status osb_frontend_set_profiling(osb_frontend* h, int enable) {
 extern "C" osb_status osb_frontend_stage_ms(osb_frontend* h, float* ms8) {
   OSB_REQUIRE(h != nullptr && ms8 != nullptr, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   for (int i = 0; i < 8; ++i) {
     ms8[i] = 0.f;
     if (i < 7 && h->ev_valid[i] && h->ev_valid[i + 1]) {
@@ -805,12 +819,14 @@ extern "C" osb_status osb_frontend_stage_ms(osb_frontend* h, float* ms8) {
 extern "C" osb_status osb_frontend_finish(osb_frontend* h, void* stream) {
   OSB_REQUIRE(h != nullptr, "null handle");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   return fe_refresh_counts(h, (cudaStream_t)stream);
 }
 
 extern "C" int64_t osb_frontend_db_size(osb_frontend* h, int remote) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   if (fe_refresh_counts(h, h->stream) != OSB_OK) return -1;
   return h->db[remote ? 1 : 0].upper;
 }
@@ -818,6 +834,7 @@ extern "C" int64_t osb_frontend_db_size(osb_frontend* h, int remote) {
 extern "C" osb_status osb_frontend_db_reset(osb_frontend* h) {
   OSB_REQUIRE(h != nullptr, "null handle");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   for (int i = 0; i < 2; ++i) {
     OSB_CUDA(cudaMemsetAsync(h->db[i].dev, 0, sizeof(DbDev), h->stream));
     h->db[i].upper = 0;
@@ -832,6 +849,7 @@ extern "C" osb_status osb_frontend_db_set_geometry(osb_frontend* h, int remote, 
                                                    const float* kpts, const int32_t* stereo_match) {
   OSB_REQUIRE(h && kpts && stereo_match && n >= 0 && first_row >= 0, "bad arguments");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   cudaStream_t st = h->stream;
   if (fe_refresh_counts(h, st) != OSB_OK) return OSB_ERR_CUDA;
   DbStore& S = h->db[remote ? 1 : 0];
@@ -851,6 +869,7 @@ extern "C" osb_status osb_frontend_db_load(osb_frontend* h, int remote, int64_t 
                                            const float* local_desc, const int32_t* n_kpts) {
   OSB_REQUIRE(h && global_desc && n >= 0, "bad arguments");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   cudaStream_t st = h->stream;
   if (fe_refresh_counts(h, st) != OSB_OK) return OSB_ERR_CUDA;
   DbStore& S = h->db[remote ? 1 : 0];

@@ -506,6 +506,7 @@ osb_status bf_match_device(int n_pairs, int max_n, int out_stride, const float* 
 using namespace osb;
 
 struct osb_db {
+  int device = 0;
   int dim = 0;
   int64_t cap = 0, ntotal = 0;
   float* rows = nullptr;
@@ -525,6 +526,7 @@ extern "C" osb_status osb_db_create(osb_db** out, int dim, int64_t capacity) {
   osb_status s = require_device();
   if (s != OSB_OK) return s;
   osb_db* h = new osb_db();
+  h->device = current_device();
   h->dim = dim; h->cap = capacity;
   int64_t chunk;
   h->grid_max = db_scan_grid(capacity, &chunk);
@@ -555,6 +557,7 @@ extern "C" int64_t osb_db_size(osb_db* h) { return h ? h->ntotal : -1; }
 extern "C" osb_status osb_db_reset(osb_db* h) {
   OSB_REQUIRE(h != nullptr, "null handle");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   h->ntotal = 0;
   return OSB_OK;
 }
@@ -563,6 +566,7 @@ static osb_status db_add_impl(osb_db* h, int64_t n, const float* x, int64_t* fir
                               cudaStream_t st, bool sync) {
   OSB_REQUIRE(h != nullptr && n >= 0 && (x != nullptr || n == 0), "bad arguments");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   if (h->ntotal + n > h->cap) { set_error("osb_db_add", "capacity exceeded"); return OSB_ERR_CAPACITY; }
   if (n > 0)
     OSB_CUDA(cudaMemcpyAsync(h->rows + (size_t)h->ntotal * h->dim, x, (size_t)n * h->dim * sizeof(float), kind, st));
@@ -587,6 +591,7 @@ extern "C" osb_status osb_db_search_dev(osb_db* h, int64_t nq, const float* q_de
   OSB_REQUIRE(h != nullptr && q_dev && scores_dev && ids_dev, "null argument");
   OSB_REQUIRE(k > 0 && k <= h->kmax && nq > 0, "k must be in 1..64 and nq > 0");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   return db_search_device(h->rows, h->ntotal, nullptr, h->dim, q_dev, (int)nq, k, h->part_scores, h->part_ids, h->done, scores_dev,
                           ids_dev, (cudaStream_t)stream);
 }
@@ -629,6 +634,7 @@ extern "C" osb_status osb_db_search(osb_db* h, int64_t nq, const float* q, int k
   OSB_REQUIRE(h != nullptr && q && scores && ids, "null argument");
   OSB_REQUIRE(k > 0 && k <= h->kmax && nq > 0, "k must be in 1..64 and nq > 0");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   for (int64_t q0 = 0; q0 < nq; q0 += h->qmax) {
     const int nb = (int)std::min<int64_t>(h->qmax, nq - q0);
     OSB_CUDA(cudaMemcpyAsync(h->d_q, q + (size_t)q0 * h->dim, (size_t)nb * h->dim * sizeof(float),
@@ -649,6 +655,7 @@ extern "C" osb_status osb_db_search(osb_db* h, int64_t nq, const float* q, int k
 // C ABI: osb_matcher
 // =============================================================================================================
 struct osb_matcher {
+  int device = 0;
   int max_pairs = 0, max_n = 0, dim = 0;
   float *d_q = nullptr, *d_t = nullptr, *d_dist = nullptr, *d_dout = nullptr;
   int32_t *d_nq = nullptr, *d_nt = nullptr, *d_qi = nullptr, *d_ti = nullptr, *d_nout = nullptr;
@@ -674,6 +681,7 @@ extern "C" osb_status osb_matcher_create(osb_matcher** out, int max_pairs, int m
   osb_status s = require_device();
   if (s != OSB_OK) return s;
   osb_matcher* h = new osb_matcher();
+  h->device = current_device();
   h->max_pairs = max_pairs; h->max_n = max_n; h->dim = dim;
   const size_t pn = (size_t)max_pairs * max_n;
   OSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -705,6 +713,7 @@ extern "C" osb_status osb_matcher_match_dev(osb_matcher* h, int n_pairs, const f
                                             int32_t* ti_dev, float* dist_dev, int32_t* n_out_dev, void* stream) {
   OSB_REQUIRE(h != nullptr && n_pairs >= 0 && n_pairs <= h->max_pairs, "n_pairs out of range");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   osb_status s = matcher_tables(h, n_pairs, q_dev, t_dev, (cudaStream_t)stream);
   if (s != OSB_OK) return s;
   return bf_match_device(n_pairs, h->max_n, h->max_n, h->d_ptrs, nq_dev, h->d_ptrs + h->max_pairs, nt_dev, h->d_dist, qi_dev,
@@ -719,6 +728,7 @@ extern "C" osb_status osb_matcher_match(osb_matcher* h, int n_pairs, const float
   for (int p = 0; p < n_pairs; ++p)
     OSB_REQUIRE(nq[p] >= 0 && nq[p] <= h->max_n && nt[p] >= 0 && nt[p] <= h->max_n, "row count out of range");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   const size_t pn = (size_t)n_pairs * h->max_n;
   cudaStream_t st = h->stream;
   OSB_CUDA(cudaMemcpyAsync(h->d_q, q, pn * h->dim * sizeof(float), cudaMemcpyHostToDevice, st));

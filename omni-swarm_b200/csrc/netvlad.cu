@@ -374,6 +374,7 @@ osb_status NetVLAD::infer_dev(const uint8_t* img_dev, int B, float* out_dev, cud
 using namespace osb;
 
 struct osb_netvlad {
+  int device = 0;
   NetVLAD nv;
   std::mutex mu;
 };
@@ -384,6 +385,7 @@ extern "C" osb_status osb_netvlad_create(osb_netvlad** out, const float* weights
   osb_status s = require_device();
   if (s != OSB_OK) return s;
   osb_netvlad* h = new osb_netvlad();
+  h->device = current_device();
   s = h->nv.init(weights, n_weights, width, height, max_batch);
   if (s != OSB_OK) { h->nv.release(); delete h; return s; }
   *out = h;
@@ -401,12 +403,14 @@ extern "C" osb_status osb_netvlad_infer_dev(osb_netvlad* h, const uint8_t* image
                                             void* stream) {
   OSB_REQUIRE(h && images_dev && out_dev, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   return h->nv.infer_dev(images_dev, batch, out_dev, (cudaStream_t)stream);
 }
 
 extern "C" osb_status osb_netvlad_infer(osb_netvlad* h, const uint8_t* images, int batch, float* out) {
   OSB_REQUIRE(h && images && out, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   NetVLAD& nv = h->nv;
   OSB_REQUIRE(batch > 0 && batch <= nv.max_batch, "batch out of range");
   cudaStream_t st = nv.stream;

@@ -163,7 +163,9 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
     return umma_conv_forward(UL[i], tmA[i], tmB[i], B, h, w, SA, in_hi[out_layer], in_lo[out_layer], nullptr,
                              SP_COUT[i], SP_COUT[i], SA, 1, pool, st);
   };
-  static const int dbg_layer = [] { const char* e = getenv("OSB_F1_DBG_LAYER"); return e ? atoi(e) : 1; }();
+  // cycle counters of the 64 -> 64 kernels (osb_superpoint_read what = 5): OSB_F1_DEBUG=<1|2|3> selects conv1 / conv2a / conv2b;
+  // off by default because the clock reads cost a few percent of the kernel
+  static const int dbg_layer = [] { const char* e = getenv("OSB_F1_DEBUG"); return e ? atoi(e) : 0; }();
   if (fuse_first && pair64) {
     mark(st);
     RUN(umma_pair_first_forward(UL[1], w1a, b1a, img_dev, B, H, W, SA, in_hi[2], in_lo[2], SA, st, 0,
@@ -172,7 +174,7 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
   } else if (fuse_first) {
     mark(st);                                                                             // (conv1a has no launch of its own)
     RUN(umma_conv1_fused_forward(UL[1], w1a, b1a, img_dev, B, H, W, SA, in_hi[2], in_lo[2], SA, st, 0,
-                                 (layer_prof && !(getenv("OSB_F1_DBG_LAYER") && atoi(getenv("OSB_F1_DBG_LAYER")) != 1)) ? d_f1dbg : nullptr));   // conv1a+conv1b+pool -> B
+                                 (layer_prof && dbg_layer == 1) ? d_f1dbg : nullptr));   // conv1a+conv1b+pool -> B
     mark(st);
   } else {
     RUN(umma_first_forward(w1a, b1a, lut, img_dev, in_hi[1], in_lo[1], B, H, W, SA, st)); // conv1a            -> A
@@ -226,7 +228,7 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
     OSB_CUDA(cudaStreamWaitEvent(kp_stream, ev_semi, 0));
     RUN(keypoints(B, *kp, kp_stream));
     OSB_CUDA(cudaEventRecord(ev_kp, kp_stream));
-    head_ctas = std::max(1, num_sms() - B);
+    head_ctas = std::max(1, persistent_ctas() - B);
   }
   RUN(umma_conv_forward(UL[10], tmA[10], tmB[10], B, Hc, Wc, SA, in_hi[11], in_lo[11], nullptr, SP_COUT[10], SP_COUT[10],
                         SA, 1, 0, st, head_ctas));                                        // convDa (reads B)  -> A
@@ -302,6 +304,7 @@ osb_status SuperPoint::infer_dev(const uint8_t* img_dev, int B, int32_t* nk, flo
 using namespace osb;
 
 struct osb_superpoint {
+  int device = 0;
   SuperPoint sp;
   std::mutex mu;
 };
@@ -313,6 +316,7 @@ extern "C" osb_status osb_superpoint_create(osb_superpoint** out, const float* w
   osb_status s = require_device();
   if (s != OSB_OK) return s;
   osb_superpoint* h = new osb_superpoint();
+  h->device = current_device();
   s = h->sp.init(weights, n_weights, width, height, thres, max_num, pca_comp, pca_mean, max_batch);
   if (s != OSB_OK) { h->sp.release(); delete h; return s; }
   *out = h;
@@ -338,6 +342,7 @@ extern "C" osb_status osb_superpoint_infer(osb_superpoint* h, const uint8_t* ima
                                            float* kpts, float* desc) {
   OSB_REQUIRE(h && images && n_kpts && kpts && desc, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   SuperPoint& sp = h->sp;
   OSB_REQUIRE(batch > 0 && batch <= sp.max_batch, "batch out of range");
   cudaStream_t st = sp.stream;
@@ -351,6 +356,7 @@ extern "C" osb_status osb_superpoint_infer_dev(osb_superpoint* h, const uint8_t*
                                                int32_t* n_kpts_dev, float* kpts_dev, float* desc_dev, void* stream) {
   OSB_REQUIRE(h && images_dev && n_kpts_dev && kpts_dev && desc_dev, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   return h->sp.infer_dev(images_dev, batch, n_kpts_dev, kpts_dev, desc_dev, (cudaStream_t)stream);
 }
 
@@ -358,6 +364,7 @@ extern "C" osb_status osb_superpoint_postprocess(osb_superpoint* h, const float*
                                                  int batch, int32_t* n_kpts, float* kpts, float* desc) {
   OSB_REQUIRE(h && semi && desc_nchw && n_kpts && kpts && desc, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   SuperPoint& sp = h->sp;
   OSB_REQUIRE(batch > 0 && batch <= sp.max_batch, "batch out of range");
   cudaStream_t st = sp.stream;
@@ -375,6 +382,7 @@ extern "C" osb_status osb_superpoint_postprocess(osb_superpoint* h, const float*
 extern "C" osb_status osb_superpoint_set_profiling(osb_superpoint* h, int enable) {
   OSB_REQUIRE(h != nullptr, "null handle");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   h->sp.layer_prof = enable != 0;
   h->sp.n_lev = 0;
   return OSB_OK;
@@ -383,6 +391,7 @@ extern "C" osb_status osb_superpoint_set_profiling(osb_superpoint* h, int enable
 extern "C" osb_status osb_superpoint_layer_ms(osb_superpoint* h, float* ms, int n) {
   OSB_REQUIRE(h != nullptr && ms != nullptr && n >= 12, "need room for 12 layer times");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   SuperPoint& sp = h->sp;
   OSB_CUDA(cudaStreamSynchronize(sp.stream));
   for (int i = 0; i < n; ++i) ms[i] = 0.f;
@@ -396,6 +405,7 @@ extern "C" osb_status osb_superpoint_layer_ms(osb_superpoint* h, float* ms, int 
 extern "C" osb_status osb_superpoint_read(osb_superpoint* h, int what, int image, float* out, size_t n_floats) {
   OSB_REQUIRE(h && out, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   SuperPoint& sp = h->sp;
   OSB_REQUIRE(image >= 0 && image < sp.max_batch, "image index out of range");
   cudaStream_t st = sp.stream;

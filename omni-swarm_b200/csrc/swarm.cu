@@ -81,6 +81,7 @@ typedef CUresult (*PFN_memsetD32Async)(CUdeviceptr, unsigned int, size_t, CUstre
 constexpr int SWARM_MAX_WORLD = 64;
 
 struct osb_swarm {
+  int device = 0;
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
   cudaStream_t side = nullptr;                 // the exchange's own stream (exchange_async)
@@ -187,6 +188,7 @@ extern "C" osb_status osb_swarm_init(osb_swarm** out, const uint8_t* id, int ran
   if (s != OSB_OK) return s;
   osb_swarm* h = new osb_swarm();
   h->rank = rank; h->world = world;
+  h->device = current_device();
 #define SW_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error("osb_swarm_init", cudaGetErrorString(e_)); osb_swarm_destroy(h); return OSB_ERR_CUDA; } } while (0)
   SW_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   SW_CUDA(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
@@ -229,6 +231,7 @@ extern "C" osb_status osb_swarm_exchange(osb_swarm* h, const osb_keyframe_record
                                          osb_keyframe_record* gathered_dev, void* stream) {
   OSB_REQUIRE(h && record_dev && gathered_dev, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   return swarm_gather(h, record_dev, gathered_dev, (cudaStream_t)stream);
 }
 
@@ -236,6 +239,7 @@ extern "C" osb_status osb_swarm_exchange_async(osb_swarm* h, const osb_keyframe_
                                                osb_keyframe_record* gathered_dev, void* stream) {
   OSB_REQUIRE(h && record_dev && gathered_dev, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   OSB_CUDA(cudaEventRecord(h->ev_ready, (cudaStream_t)stream));      // the record is complete on the caller's stream
   OSB_CUDA(cudaStreamWaitEvent(h->side, h->ev_ready, 0));
   if (h->p2p) {
@@ -270,6 +274,7 @@ extern "C" osb_status osb_swarm_exchange_async(osb_swarm* h, const osb_keyframe_
 extern "C" osb_status osb_swarm_wait(osb_swarm* h, void* stream) {
   OSB_REQUIRE(h != nullptr, "null handle");
   std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
   if (!h->in_flight) return OSB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   OSB_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));

@@ -6,6 +6,7 @@ from omniswarm_b200 import synth, host
 comp, mean = synth.pca_matrices(0)
 spw = synth.flatten_sp_weights(synth.superpoint_weights(0))
 imgs = np.stack([synth.image(s) for s in range(8)])
+os.environ.setdefault("OSB_F1_DEBUG", "1")          # cycle counters on (layer 1 = the fused first layers)
 for fuse in (os.environ.get("F1_MODES", "1,0").split(",")):
     os.environ["OSB_SP_FUSE1"] = fuse
     sp = host.SuperPoint(spw, comp, mean, 640, 480, 0.015, 200, max_batch=8)

@@ -111,7 +111,9 @@ def main():
             return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
         return f("dram__bytes_read.sum") + f("dram__bytes_write.sum")
 
-    for name, key in (("dbscan", "db_scan_dram_bytes_per_launch"), ("conv", "conv1b_dram_bytes_per_launch")):
+    for name, key in (("dbscan", "db_scan_dram_bytes_per_launch"), ("conv", "conv1_fused_dram_bytes_per_launch"),
+                      ("conv_mid", "conv_n128_dram_bytes_per_launch"), ("conv_heads", "conv_heads_dram_bytes_per_launch"),
+                      ("conv_box64", "conv2_box64_dram_bytes_per_launch")):
         rep = os.path.join(OUT, f"prof_{name}.ncu-rep")
         if os.path.exists(rep):
             out = ncu_summary(tag, name, rep)

@@ -51,6 +51,21 @@ int main() {
       return 5;
     }
   }
+  {
+    // bearing detection (DroneDetection4dFactor through the adapter, solver.cpp:1088-1094): drone B is seen from A along +x at
+    // 2 m; with the odometry edge pulling it elsewhere in y the detection's tangent residual drags it back towards y = 0
+    double d0[4] = {0, 0, 0, 0}, d1[4] = {1.8, 0.6, 0.1, 0.0};
+    const double dir[3] = {1, 0, 0}, tan_base[6] = {0, 1, 0, 0, 0, 1};
+    osb::FlatPoseGraph dg;
+    dg.add_detection(d0, d1, dir, tan_base, /*inv_dep=*/0.5, /*enable_depth=*/true, /*extrinsic_z=*/0.0, nullptr, nullptr,
+                     /*sphere_std=*/0.01, /*inv_dep_std=*/0.01, false);
+    dg.set_constant(d0);
+    osb_solve_summary ds = dg.solve(solver);
+    if (dg.num_factors() != 1 || ds.n_residuals != 3 || std::fabs(d1[0] - 2.0) > 1e-4 || std::fabs(d1[1]) > 1e-4 || std::fabs(d1[2]) > 1e-4) {
+      std::printf("detection solve wrong: %f %f %f (%d residuals, cost %g)\n", d1[0], d1[1], d1[2], ds.n_residuals, ds.final_cost);
+      return 6;
+    }
+  }
   osb_solver_destroy(solver);
   if (std::fabs(b[0] - 1.0) > 1e-6 || std::fabs(b[3] - 0.1) > 1e-6 || a[0] != 0.0) {
     std::printf("solve wrong: %f %f %f %f cost %g\n", b[0], b[1], b[2], b[3], s.final_cost);
