@@ -49,6 +49,13 @@ constexpr int F1_SMEM = F1_PATCH_OFF + F1_PR * F1_PC;
 static_assert(F1_SMEM <= 227 * 1024, "shared memory plan exceeds 227 KB");
 static_assert(F1_PR * F1_PC <= F1_NPROD * 32, "one patch byte per producer thread");
 
+// measurement only (make EXTRA=-DF1_ABLATE=<bits> after touching this file, results are WRONG when set): 1 producers do not store, 2 no patch loads,
+// 4 epilogue only drains TMEM, 8 no lo*hi MMA, 16 producers do not compute.  profiles/r02_f1_ablate.txt
+#ifndef F1_ABLATE
+#define F1_ABLATE 0
+#endif
+constexpr int kAblate = F1_ABLATE;
+
 struct Fused1Args {
   const uint8_t* img;      // [B][H][W]
   const float* w1a;        // conv1a weights [tap][64]
@@ -68,6 +75,13 @@ struct Fused1Args {
 __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 -- one issue slot for two IEEE fp32 operations; the producers are issue bound)
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ void st_shared_128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -117,7 +131,7 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (warp == 13 && lane == 0) {
+  if (warp == 13 && elect_one()) {
     // ===================== conv1b weights: all 9 taps once, resident for the CTA's life =====================
     mbar_expect_tx(b_full, F1_W_BYTES);
     for (int t = 0; t < 9; ++t) {
@@ -157,7 +171,7 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
             // one MMA of width 128 over [W_hi | W_lo]: hi*hi -> main, hi*lo -> cross; then lo*hi -> cross
             umma_f16(d_main, a_hi + adv, b_hi + adv, idesc2, (first && k == 0) ? 0u : 1u);
-            umma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+            if (!(kAblate & 8)) umma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, 1u);
           }
           first = 0;
         }
@@ -193,6 +207,7 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
         uint32_t v[16], vc[16];
         tmem_ld16(t_row + n0, v);
         tmem_ld16(t_row + 64 + n0, vc);
+        if (kAblate & 4) continue;
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -227,7 +242,7 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       if (prof) { c_wait += t1 - t0; c_work += clock64() - t1; }
     }
     if (prof) { P.dbg[7] = c_wait; P.dbg[8] = c_work; }
-  } else if (!FIRST && warp == 0 && lane == 0) {
+  } else if (!FIRST && warp == 0 && elect_one()) {
     // ===================== halo windows by TMA (64 -> 64 layers on split planes) =====================
     asm volatile("griddepcontrol.wait;" ::: "memory");       // the planes are the previous kernel's output (no-op without PDL)
     uint32_t i = 0;
@@ -258,23 +273,21 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
     const int cg = lane & 7;
     const int ptid = pw * 32 + lane;               // 0 .. 255: byte of the input patch this thread stages
     const int pr = ptid / F1_PC, pc = ptid - pr * F1_PC;
+    const int tap_off = (cg / 3) * F1_PC + cg % 3;   // the input tap this lane converts for its pixel
     uint8_t* patch = smem_raw + F1_PATCH_OFF;
-    float wr[9][8], br[8];
+    uint64_t wr[9][4], br[4];                     // channel pairs (2j, 2j+1), pre-multiplied by the plane scale (a power of two: exact)
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.w1a + t * 64 + cg * 8));
       const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.w1a + t * 64 + cg * 8 + 4));
-      wr[t][0] = w0.x; wr[t][1] = w0.y; wr[t][2] = w0.z; wr[t][3] = w0.w;
-      wr[t][4] = w1.x; wr[t][5] = w1.y; wr[t][6] = w1.z; wr[t][7] = w1.w;
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) wr[t][jj] *= P.act_scale;      // power of two: exact
+      wr[t][0] = pk2(w0.x * P.act_scale, w0.y * P.act_scale); wr[t][1] = pk2(w0.z * P.act_scale, w0.w * P.act_scale);
+      wr[t][2] = pk2(w1.x * P.act_scale, w1.y * P.act_scale); wr[t][3] = pk2(w1.z * P.act_scale, w1.w * P.act_scale);
     }
     {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(P.b1a + cg * 8));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(P.b1a + cg * 8 + 4));
-      br[0] = b0.x; br[1] = b0.y; br[2] = b0.z; br[3] = b0.w; br[4] = b1.x; br[5] = b1.y; br[6] = b1.z; br[7] = b1.w;
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) br[jj] *= P.act_scale;
+      br[0] = pk2(b0.x * P.act_scale, b0.y * P.act_scale); br[1] = pk2(b0.z * P.act_scale, b0.w * P.act_scale);
+      br[2] = pk2(b1.x * P.act_scale, b1.y * P.act_scale); br[3] = pk2(b1.z * P.act_scale, b1.w * P.act_scale);
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");       // the image is the previous kernel's output (no-op without PDL)
     // input patch of a tile: rows y0-2 .. y0+17, columns x0-2 .. x0+9 of the u8 image, zero outside (conv1a's padding)
@@ -297,34 +310,63 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       const int next = tile + gridDim.x;
       const uint32_t nb = next < n_tiles ? patch_byte(next) : 0u;      // next tile's patch byte: in flight for the whole tile
       const uint32_t row0 = w ? F1_WIN1 : 0;
+      // a tile whose halo stays inside the image needs no validity test (warp-uniform)
+      const bool border = tx == 0 || ty == 0 || (tx + 1) * F1_TW + 1 > P.W || (ty + 1) * F1_TH + 1 > P.H;
       // conv1a of halo pixel (r, c) -> split fp16 chunks of this thread's 8 channels
-      auto compute = [&](int r, int c, uint32_t (&h)[4], uint32_t (&l)[4]) {
+      // the 8 lanes of a pixel need the same 9 inputs: lane cg converts tap cg (lane 0 also tap 8) and a width-8 shuffle hands
+      // them round -- 2 byte loads + 2 conversions per lane instead of 9.  The two bytes of step s+1 are loaded while step s
+      // computes: shared memory is saturated by the MMAs' operand reads, a load issued when it is needed waits for hundreds
+      // of cycles.
+      auto coords = [&](int step, int& r, int& c) {            // steps 0..4: private rows, step 5: the shared rows
+        const int qc = step < 5 ? min(step * 32 + slot, 149) : min(slot, 29);
+        const int rr = qc / F1_HC;
+        c = qc - rr * F1_HC;
+        r = step < 5 ? rr + (w ? 3 : 0) : rr + (w ? 0 : 15);
+      };
+      auto load_in = [&](int r, int c, float& v_own, float& v_8) {
         const uint8_t* pp = patch + r * F1_PC + c;
-        float in[3][3];
+        if (kAblate & 2) { v_own = (float)(r + c); v_8 = (float)c; return; }
+        v_own = __fmul_rn(__uint2float_rn((uint32_t)pp[tap_off]), P.alpha);
+        v_8 = __fmul_rn(__uint2float_rn((uint32_t)pp[2 * F1_PC + 2]), P.alpha);
+      };
+      // conv1a of halo pixel (r, c) -> split fp16 chunks of this thread's 8 channels.  Taps outermost: every channel's fma
+      // chain still runs over the taps in ascending order (bit-identical to conv_first_split_kernel).
+      auto compute = [&](int r, int c, float v_own, float v_8, uint32_t (&h)[4], uint32_t (&l)[4]) {
+        uint64_t acc[4] = {br[0], br[1], br[2], br[3]};
+        float vin[9];                                          // all eight shuffles first: their latencies overlap
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
+        for (int t = 0; t < 8; ++t) vin[t] = __shfl_sync(0xffffffffu, v_own, t, 8);
+        vin[8] = v_8;
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) in[dy][dx] = __fmul_rn(__uint2float_rn((uint32_t)pp[dy * F1_PC + dx]), P.alpha);
-        const int iy = ty * F1_TH - 1 + r, ix = tx * F1_TW - 1 + c;
-        const bool valid = iy >= 0 && iy < P.H && ix >= 0 && ix < P.W;          // outside the image: conv1b's zero padding
+        for (int t = 0; t < 9; ++t) {
+          const uint64_t vv = pk2(vin[t], vin[t]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fma2(vv, wr[t][j], acc[j]);
+        }
 #pragma unroll
         for (int j2 = 0; j2 < 4; ++j2) {
-          float a0 = br[2 * j2], a1 = br[2 * j2 + 1];
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            a0 = fmaf(in[t / 3][t % 3], wr[t][2 * j2], a0);
-            a1 = fmaf(in[t / 3][t % 3], wr[t][2 * j2 + 1], a1);
-          }
+          float a0, a1;
+          upk2(acc[j2], a0, a1);
           const float s0 = fmaxf(a0, 0.f), s1 = fmaxf(a1, 0.f);
           // one packed conversion per pair (cvt.rn.f16x2.f32: same roundings as two scalar conversions, off the slow pipe)
           const __half2 hp = __floats2half2_rn(s0, s1);
           const float2 hf = __half22float2(hp);
-          const __half2 lp = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
-          h[j2] = valid ? *reinterpret_cast<const uint32_t*>(&hp) : 0u;
-          l[j2] = valid ? *reinterpret_cast<const uint32_t*>(&lp) : 0u;
+          float d0, d1;
+          upk2(sub2(pk2(s0, s1), pk2(hf.x, hf.y)), d0, d1);
+          const __half2 lp = __floats2half2_rn(d0, d1);
+          h[j2] = *reinterpret_cast<const uint32_t*>(&hp);
+          l[j2] = *reinterpret_cast<const uint32_t*>(&lp);
+        }
+        if (border) {                                         // outside the image: conv1b's zero padding (border tiles only)
+          const int iy = ty * F1_TH - 1 + r, ix = tx * F1_TW - 1 + c;
+          if (!(iy >= 0 && iy < P.H && ix >= 0 && ix < P.W)) {
+#pragma unroll
+            for (int j2 = 0; j2 < 4; ++j2) { h[j2] = 0u; l[j2] = 0u; }
+          }
         }
       };
       auto store = [&](int r, int c, const uint32_t (&h)[4], const uint32_t (&l)[4]) {
+        if (kAblate & 1) return;
         const uint32_t off = ((row0 + r) * F1_HC + c) * 128;
         const uint32_t ah = a_hi_base + off, al = a_lo_base + off;
         st_shared_128(ah + (((uint32_t)cg ^ ((ah >> 7) & 7u)) << 4), h[0], h[1], h[2], h[3]);
@@ -335,22 +377,26 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       if (i >= 2) mbar_wait(mma_done(w), ((i >> 1) - 1) & 1);
       if (prof) t1 = clock64();
       // private rows: halo rows 0..14 of window 0, 3..17 of window 1
+      int r, c;
+      float v_own, v_8;
+      coords((kAblate & 16) ? 5 : 0, r, c);
+      load_in(r, c, v_own, v_8);
 #pragma unroll 1
-      for (int step = 0; step < 5; ++step) {
-        const int q = step * 32 + slot;
-        const int qc = min(q, 149);                            // idle slots of the last private step redo pixel 149, unstored
-        const int r = qc / F1_HC, c = qc - r * F1_HC;
+      for (int step = (kAblate & 16) ? 5 : 0; step < 5; ++step) {
+        int rn, cn;
+        float n_own, n_8;
+        coords(step + 1, rn, cn);
+        load_in(rn, cn, n_own, n_8);
         uint32_t h[4], l[4];
-        compute(r + (w ? 3 : 0), c, h, l);
-        if (q < 150) store(r + (w ? 3 : 0), c, h, l);
+        compute(r, c, v_own, v_8, h, l);
+        if (step * 32 + slot < 150) store(r, c, h, l);
+        r = rn; c = cn; v_own = n_own; v_8 = n_8;
       }
       {
         // the three rows shared with the other window (15..17 of window 0 = 0..2 of window 1): computed now, stored only
         // after the previous tile's MMAs have read them
-        const int qc = min(slot, 29);
-        const int r = qc / F1_HC + (w ? 0 : 15), c = qc % F1_HC;
         uint32_t h[4], l[4];
-        compute(r, c, h, l);
+        compute(r, c, v_own, v_8, h, l);
         if (prof) t2 = clock64();
         if (i >= 1) mbar_wait(mma_done(w ^ 1), ((i - 1) >> 1) & 1);
         if (prof) t3 = clock64();

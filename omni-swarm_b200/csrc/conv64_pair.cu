@@ -137,7 +137,7 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
   // tile of this CTA in pair-iteration i; the second tile of an odd last pair repeats the last tile and stores nothing
   auto tile_of = [&](int pair) { return 2 * pair + (int)rank; };
 
-  if (warp == 13 && lane == 0) {
+  if (warp == 13 && elect_one()) {
     // ===================== weights: this CTA's share of every tap, resident for the kernel's life =====================
     // leader: X = W_hi rows 0..63, Y = W_hi rows 0..31;  peer: X = W_lo rows 0..63, Y = W_hi rows 32..63
     mbar_expect_tx(b_full, P2_W_BYTES);
@@ -252,7 +252,7 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       if (prof) { c_wait += t1 - t0; c_work += clock64() - t1; }
     }
     if (prof) { P.dbg[7] = c_wait; P.dbg[8] = c_work; }
-  } else if (!FIRST && warp == 0 && lane == 0) {
+  } else if (!FIRST && warp == 0 && elect_one()) {
     // ===================== halo tiles by TMA: one box {64 ch, 10 px, 18 rows} per plane =====================
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t af0 = mapa_u32(a_full(0), 0), af1 = mapa_u32(a_full(1), 0);

@@ -120,7 +120,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   // grid in their own griddepcontrol.wait before touching activations)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ===================== TMA producer =====================
     int as = 0; uint32_t aph = 0;
     int bs = 0; uint32_t bph = 0;
@@ -160,7 +160,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ===================== MMA issuer =====================
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = f16 (0), K-major both,
     // N >> 3 at bit 17, M >> 4 at bit 24

@@ -12,6 +12,7 @@
 // a single host synchronisation at the very end (the reference synchronised after every engine call,
 // swarm_loop/src/tensorrt_generic.cpp:73).
 #include "superpoint.cuh"
+#include <atomic>
 
 namespace osb {
 
@@ -19,6 +20,16 @@ struct DbDev {                 // device-resident database (one for own keyframe
   int64_t ntotal;              // rows (faiss ntotal)
   int nframes;
   int overflow;                // set when a row could not be added
+};
+
+// Row-count feedback of the ingest kernel, written into mapped pinned host memory (no copy, no synchronisation): the host's
+// bounds are conservative (every ingested record is charged to BOTH stores because its drone_id is only known on the
+// device); the last ingest that has actually run reports the true counts together with how much had been charged when it
+// was enqueued, so bound = count + what was charged since.  seq_begin / seq_end make a torn read detectable.
+struct FeFeedback {
+  volatile long long seq_begin;
+  volatile long long n_local, n_remote, charged;
+  volatile long long seq_end;
 };
 
 struct DbStore {
@@ -98,7 +109,8 @@ __global__ void fe_assign_kernel(const osb_keyframe_record* __restrict__ recs, i
                                  int32_t* __restrict__ r_row_frame, int32_t* __restrict__ r_row_dir,
                                  int32_t* __restrict__ r_frame_rows, int32_t* __restrict__ r_frame_msg,
                                  int32_t* __restrict__ l_frame_drone, int32_t* __restrict__ r_frame_drone,
-                                 int32_t* __restrict__ assign /*[n_records][4]: row | (remote<<30), or -1*/) {
+                                 int32_t* __restrict__ assign /*[n_records][4]: row | (remote<<30), or -1*/,
+                                 FeFeedback* __restrict__ fb, long long seq, long long charged) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   for (int r = 0; r < n_records; ++r) {
     for (int d = 0; d < OSB_MAX_DIRS; ++d) assign[r * OSB_MAX_DIRS + d] = -1;
@@ -125,6 +137,11 @@ __global__ void fe_assign_kernel(const osb_keyframe_record* __restrict__ recs, i
       assign[r * OSB_MAX_DIRS + d] = row | (is_remote ? (1 << 30) : 0);
     }
   }
+  fb->seq_begin = seq;
+  __threadfence_system();
+  fb->n_local = local->ntotal; fb->n_remote = remote->ntotal; fb->charged = charged;
+  __threadfence_system();
+  fb->seq_end = seq;
 }
 
 // phase 2: copy global + local descriptors of every assigned (record, direction) into its row
@@ -380,6 +397,10 @@ struct osb_frontend {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sp = nullptr;
   DbDev* h_cnt = nullptr;                         // pinned [2]: row counters read back without blocking the driver (a copy
                                                   // to pageable memory would hold other host threads' launches until it ran)
+  FeFeedback* fb_host = nullptr;                  // mapped pinned memory + its device alias
+  FeFeedback* fb_dev = nullptr;
+  long long ingest_seq = 0, fb_min_seq = 1;       // feedback older than fb_min_seq predates a load / reset and is ignored
+  long long charged = 0;                          // rows charged to each store by ingests so far
   cudaEvent_t ev_ingest = nullptr;                // recorded after the last ingest on ITS stream
   bool ingest_pending = false;
   bool profiling = false;
@@ -418,6 +439,7 @@ static osb_status dbstore_alloc(DbStore& s, int64_t cap, int max_num) {
   OSB_CUDA(cudaMemset(s.done, 0, sizeof(unsigned int)));
   OSB_CUDA(cudaMalloc(&s.top_scores, FE_KMAX * sizeof(float)));
   OSB_CUDA(cudaMalloc(&s.top_ids, FE_KMAX * sizeof(int64_t)));
+  OSB_CUDA(cudaMemset(s.top_ids, 0xFF, FE_KMAX * sizeof(int64_t)));     // "no result" (-1) until the first scan of this store
   return OSB_OK;
 }
 
@@ -462,6 +484,9 @@ extern "C" osb_status osb_frontend_create(osb_frontend** out, const osb_frontend
   FE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   FE_CUDA(cudaEventCreateWithFlags(&h->ev_ingest, cudaEventDisableTiming));
   FE_CUDA(cudaHostAlloc((void**)&h->h_cnt, 2 * sizeof(DbDev), cudaHostAllocDefault));
+  FE_CUDA(cudaHostAlloc((void**)&h->fb_host, sizeof(FeFeedback), cudaHostAllocMapped));
+  memset((void*)h->fb_host, 0, sizeof(FeFeedback));
+  FE_CUDA(cudaHostGetDevicePointer((void**)&h->fb_dev, (void*)h->fb_host, 0));
   FE_TRY(h->sp.init(sp_weights, n_sp_weights, cfg->width, cfg->height, cfg->sp_thres, mn, pca_comp, pca_mean, 2 * nd));
   h->sp.ks.write_surv = false;       // the survivor plane is only a parity hook of the standalone SuperPoint handle
   FE_TRY(h->nv.init(nv_weights, n_nv_weights, cfg->width, cfg->height, nd));
@@ -533,6 +558,7 @@ extern "C" osb_status osb_frontend_destroy(osb_frontend* h) {
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_ingest) cudaEventDestroy(h->ev_ingest);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
+  if (h->fb_host) cudaFreeHost((void*)h->fb_host);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream_sp) cudaStreamDestroy(h->stream_sp);
   if (h->ev_sp) cudaEventDestroy(h->ev_sp);
@@ -643,10 +669,25 @@ extern "C" osb_status osb_frontend_extract(osb_frontend* h, const uint8_t* image
 
 static osb_status fe_refresh_counts(osb_frontend* h, cudaStream_t st);
 
+// lower the host bounds with what the most recent EXECUTED ingest reported (no synchronisation; see FeFeedback)
+static void fe_tighten_bounds(osb_frontend* h) {
+  const FeFeedback* fb = h->fb_host;
+  const long long e = fb->seq_end;
+  std::atomic_thread_fence(std::memory_order_acquire);
+  const long long nl = fb->n_local, nr = fb->n_remote, ch = fb->charged;
+  std::atomic_thread_fence(std::memory_order_acquire);
+  const long long b = fb->seq_begin;
+  if (b != e || e < h->fb_min_seq) return;
+  const long long since = h->charged - ch;
+  h->db[0].upper = std::min<int64_t>(h->db[0].upper, nl + since);
+  h->db[1].upper = std::min<int64_t>(h->db[1].upper, nr + since);
+}
+
 static osb_status fe_ingest(osb_frontend* h, const osb_keyframe_record* recs, int n_records, int skip, cudaStream_t st) {
   OSB_REQUIRE(n_records >= 0 && n_records <= h->max_records, "too many records in one ingest (max 64)");
   if (n_records == 0) return OSB_OK;
   DbStore &L = h->db[0], &R = h->db[1];
+  fe_tighten_bounds(h);
   if (L.upper + (int64_t)n_records * OSB_MAX_DIRS > L.cap || R.upper + (int64_t)n_records * OSB_MAX_DIRS > R.cap) {
     // the upper bounds are conservative (every record charged to both databases): make them exact, and count which
     // database each record of this batch really goes to, before giving up
@@ -668,8 +709,11 @@ static osb_status fe_ingest(osb_frontend* h, const osb_keyframe_record* recs, in
   fe_mark(h, 4, st);
   OSB_LAUNCH(fe_assign_kernel, 1, 32, 0, st, recs, n_records, skip, h->cfg.self_id, L.dev, R.dev, (long long)L.cap,
              L.row_frame, L.row_dir, L.frame_rows, L.frame_msg, R.row_frame, R.row_dir, R.frame_rows, R.frame_msg,
-             L.frame_drone, R.frame_drone, h->d_assign);
+             L.frame_drone, R.frame_drone, h->d_assign, h->fb_dev, h->ingest_seq + 1,
+             h->charged + (long long)n_records * OSB_MAX_DIRS);
   OSB_CHECK_LAUNCH();
+  ++h->ingest_seq;
+  h->charged += (long long)n_records * OSB_MAX_DIRS;
   OSB_LAUNCH(fe_copy_rows_kernel, n_records * OSB_MAX_DIRS, 256, 0, st, recs, h->d_assign, h->cfg.max_num, L.rows,
              L.ldesc, L.nk, R.rows, R.ldesc, R.nk, L.kpts, L.smatch, R.kpts, R.smatch);
   OSB_CHECK_LAUNCH();
@@ -697,7 +741,11 @@ static osb_status fe_query(osb_frontend* h, const osb_keyframe_record* rec, int 
   const int k_local = 5 + c.match_index_dist, k_remote = 5 + 1;    // SEARCH_NEAREST_NUM + max_index
   osb_status s;
   fe_mark(h, 5, st);
-  if ((s = db_search_device(R.rows, std::min(R.upper, R.cap), &R.dev->ntotal, OSB_DEEP_DESC_SIZE, q, 1, k_remote,
+  fe_tighten_bounds(h);
+  // a store that has never received a row needs no scan: its top-k list still holds the -1 labels it was created with
+  // (upper is an upper bound of ntotal, so 0 is exact)
+  if (R.upper > 0 &&
+      (s = db_search_device(R.rows, std::min(R.upper, R.cap), &R.dev->ntotal, OSB_DEEP_DESC_SIZE, q, 1, k_remote,
                             R.part_scores, R.part_ids, R.done, R.top_scores, R.top_ids, st)) != OSB_OK) return s;
   if ((s = db_search_device(L.rows, std::min(L.upper, L.cap), &L.dev->ntotal, OSB_DEEP_DESC_SIZE, q, 1, k_local,
                             L.part_scores, L.part_ids, L.done, L.top_scores, L.top_ids, st)) != OSB_OK) return s;
@@ -749,6 +797,7 @@ static osb_status fe_refresh_counts(osb_frontend* h, cudaStream_t st) {
   OSB_CUDA(cudaStreamSynchronize(st));
   h->db[0].upper = h->h_cnt[0].ntotal; h->db[1].upper = h->h_cnt[1].ntotal;
   h->ingest_pending = false;
+  h->fb_min_seq = h->ingest_seq + 1;            // exact now: older feedback carries nothing new
   return OSB_OK;
 }
 
@@ -837,8 +886,10 @@ extern "C" osb_status osb_frontend_db_reset(osb_frontend* h) {
   DeviceGuard dg(h->device);
   for (int i = 0; i < 2; ++i) {
     OSB_CUDA(cudaMemsetAsync(h->db[i].dev, 0, sizeof(DbDev), h->stream));
+    OSB_CUDA(cudaMemsetAsync(h->db[i].top_ids, 0xFF, FE_KMAX * sizeof(int64_t), h->stream));
     h->db[i].upper = 0;
   }
+  h->fb_min_seq = h->ingest_seq + 1;
   OSB_CUDA(cudaStreamSynchronize(h->stream));
   return OSB_OK;
 }

@@ -58,9 +58,9 @@ def shard_rows(n_rows: int, rank: int, world: int) -> tuple[int, int]:
 
 class RowShardedIndex:
     """faiss::IndexFlatIP semantics (loop_detector.h:27-29, loop_detector.cpp:213) over a database whose ROWS are split
-    across the ranks: two exchange steps per search -- all-gather the queries (world x dim floats), every rank scans its
-    own shard for all of them (one pass over the shard, up to 8 queries per pass), all-gather the k candidates per
-    (shard, query), and each rank merges world x k candidates for its own query.  Global row ids = shard-local row +
+    across the ranks: two collectives per search -- all-gather the queries (world x dim floats), every rank scans its
+    own shard for all of them (one pass over the shard, up to 8 queries per pass), ONE all-gather of the k candidates per
+    (shard, query) with score and row id packed together, and each rank merges world x k candidates for its own query.  Global row ids = shard-local row +
     the shard's first row; order = score descending, ties by ascending global id, -1 / -inf padding.
 
     `shard` is this rank's rows [n_local, dim] (float32 numpy, or a CUDA tensor); `n_rows_total` fixes every rank's
@@ -121,11 +121,14 @@ class RowShardedIndex:
             q_all.copy_(query.reshape(1, self.dim))
         sc, ids = self._local_search(q_all, k)                       # [w queries, k] over my shard
         if w > 1:
-            sc_all = torch.empty(w, w, k, dtype=torch.float32, device=query.device)     # [shard, query, k]
-            id_all = torch.empty(w, w, k, dtype=torch.int64, device=query.device)
-            dist.all_gather_into_tensor(sc_all.view(w * w, k), sc.contiguous(), group=self.group)
-            dist.all_gather_into_tensor(id_all.view(w * w, k), ids.contiguous(), group=self.group)
-            sc, ids = sc_all[:, self.rank, :].contiguous(), id_all[:, self.rank, :].contiguous()
+            # ONE exchange back: (score bits, shard-local row id) packed as three int32 words per candidate
+            mine = torch.cat([sc.contiguous().view(torch.int32).unsqueeze(-1),
+                              ids.contiguous().view(torch.int32).view(w, k, 2)], dim=-1).contiguous()   # [query, k, 3]
+            packed = torch.empty(w, w, k, 3, dtype=torch.int32, device=query.device)                    # [shard, query, k, 3]
+            dist.all_gather_into_tensor(packed.view(w * w, k * 3), mine.view(w, k * 3), group=self.group)
+            got = packed[:, self.rank]                                                                   # [shard, k, 3]
+            sc = got[..., 0].contiguous().view(torch.float32)
+            ids = got[..., 1:].contiguous().view(torch.int64).view(w, k)
         return self._merge(sc, ids, k)
 
     def close(self):
