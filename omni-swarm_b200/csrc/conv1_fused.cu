@@ -28,6 +28,7 @@
 // shared memory one tile ahead (thread = 8 output channels of one halo pixel column, 72 weights in registers, fp32 FMAs in the order of
 // conv_first_split_kernel, so the fused and unfused paths are bit-identical).
 #include "conv_umma.cuh"
+#include <type_traits>
 #include "umma_ptx.cuh"
 
 namespace osb {
@@ -40,8 +41,10 @@ constexpr int F1_WIN1 = F1_ROWS - F1_HR;                // 15: first row of wind
 constexpr int F1_PLANE = F1_ROWS * F1_PITCH;            // 42 240 B
 constexpr int F1_W_SLOT = 2 * 64 * 128;                 // one tap: [W_hi (64 rows) | W_lo (64 rows)] x 128 B
 constexpr int F1_W_BYTES = 9 * F1_W_SLOT;               // 147 456 B
-constexpr int F1_NPROD = 8;                             // producer warps: 8 x 4 pixel slots per step
-constexpr int F1_THREADS = 14 * 32;                     // 448 (register allocation rounds to 16 warps: 128 registers)
+constexpr int F1_NPROD = 12;                            // producer warps: lane = halo pixel, warp = (pixel block, channel half)
+constexpr int F1_EPI0 = 12;                             // warps 12..15: epilogue (TMEM lane quarter = warp & 3)
+constexpr int F1_MMAW = 16;                             // warp 16: TMEM allocation, weight TMA, MMA issue
+constexpr int F1_THREADS = 17 * 32;                     // 544 -> at most 120 registers per thread
 constexpr int F1_BAR_OFF = F1_W_BYTES + 2 * F1_PLANE;
 constexpr int F1_PR = F1_HR + 2, F1_PC = F1_HC + 2;     // u8 input patch of a tile: 20 rows x 12 columns
 constexpr int F1_PATCH_OFF = F1_BAR_OFF + 80;           // 9 mbarriers + the TMEM base slot, then the patch
@@ -55,6 +58,11 @@ static_assert(F1_PR * F1_PC <= F1_NPROD * 32, "one patch byte per producer threa
 #define F1_ABLATE 0
 #endif
 constexpr int kAblate = F1_ABLATE;
+
+// conv1a's weights and bias, pre-multiplied by the plane scale, as a KERNEL PARAMETER: with lane = pixel every FFMA of a warp
+// uses the same weight, so it comes from the constant bank through a uniform register (LDCU.128 + FFMA2 R, R.F32, UR, R)
+// instead of occupying 72 registers per thread
+struct Conv1aW { float w[9][64]; float b[64]; };
 
 struct Fused1Args {
   const uint8_t* img;      // [B][H][W]
@@ -98,7 +106,8 @@ template <bool FIRST>
 __global__ void __launch_bounds__(F1_THREADS, 1)
 conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                    const __grid_constant__ CUtensorMap tm_a15_hi, const __grid_constant__ CUtensorMap tm_a15_lo,
-                   const __grid_constant__ CUtensorMap tm_a3_hi, const __grid_constant__ CUtensorMap tm_a3_lo, Fused1Args P) {
+                   const __grid_constant__ CUtensorMap tm_a3_hi, const __grid_constant__ CUtensorMap tm_a3_lo,
+                   const __grid_constant__ Conv1aW W1, Fused1Args P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();                              // the plan has no slack for re-aligning
@@ -121,7 +130,7 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
+  if (warp == F1_MMAW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(bar_base + 72u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -131,7 +140,7 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (warp == 13 && elect_one()) {
+  if (warp == F1_MMAW && elect_one()) {
     // ===================== conv1b weights: all 9 taps once, resident for the CTA's life =====================
     mbar_expect_tx(b_full, F1_W_BYTES);
     for (int t = 0; t < 9; ++t) {
@@ -182,12 +191,12 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       if (prof) { c_te += t1 - t0; c_af += t2 - t1; c_is += clock64() - t2; }
     }
     if (prof) { P.dbg[4] = c_te; P.dbg[5] = c_af; P.dbg[6] = c_is; P.dbg[9] = i; }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= F1_EPI0 && warp < F1_EPI0 + 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;                        // TMEM lane quarter = tile rows 4q .. 4q+3 (lane = (row & 3) * 8 + col)
     int acc = 0; uint32_t acc_phase = 0;
     const int Hp = P.H >> 1, Wp = P.W >> 1;
-    const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
+    const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == F1_EPI0 && lane == 0;
     long long c_wait = 0, c_work = 0, t0 = 0, t1 = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       if (prof) t0 = clock64();
@@ -262,33 +271,24 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       tma_load_4d(a_hi_base + sdst, &tm_a3_hi, a_full(w), 0, x0, y0 + srow, b);
       tma_load_4d(a_lo_base + sdst, &tm_a3_lo, a_full(w), 0, x0, y0 + srow, b);
     }
-  } else if (FIRST && (warp < 4 || (warp >= 8 && warp < 12))) {
-    // ===================== conv1a producers (8 warps, two per scheduler) =====================
-    // lane = (pixel slot, 8 output channels): the 8 lanes of a pixel are adjacent, so a quarter-warp writes the eight
-    // 16-byte chunks of one 128-byte pixel row -- conflict-free 128-bit shared stores.  32 pixel slots per step: steps
-    // 0..4 take the 150 halo pixels private to this window, step 5 the 30 pixels of the three rows shared with the other
-    // window (computed before, stored after the previous tile's MMAs have retired).
-    const int pw = warp < 4 ? warp : warp - 4;     // 0 .. 7
-    const int slot = pw * 4 + (lane >> 3);         // 0 .. 31
-    const int cg = lane & 7;
-    const int ptid = pw * 32 + lane;               // 0 .. 255: byte of the input patch this thread stages
+  } else if (FIRST && warp < F1_NPROD) {
+    // ===================== conv1a producers (12 warps, three per scheduler) =====================
+    // lane = halo pixel, warp = (block of 32 pixels, half of the 64 channels).  Warps 0..9 take the 150 pixels of the rows
+    // private to the window (5 blocks x 2 halves), warps 10 and 11 the 30 pixels of the three rows shared with the other
+    // window, which may only be overwritten after the previous tile's MMAs have retired.  A thread converts its pixel's
+    // nine inputs once and runs its 32 channels in four groups of eight: 36 FFMA2 per group with the weights from the
+    // constant bank, then ReLU, the fp16 split and one 16-byte store per plane (the eight pixels of a quarter-warp sit in
+    // eight consecutive 128-byte rows, whose swizzle phases differ: conflict-free).
+    const int pw = warp;
+    const bool sh = pw >= 10;
+    const int half = pw & 1;
+    const int q = sh ? lane : (pw >> 1) * 32 + lane;          // pixel index inside its part
+    const bool active = sh ? lane < 30 : q < 150;
+    const int qc = sh ? min(q, 29) : min(q, 149);
+    const int rr = qc / F1_HC, cc = qc - rr * F1_HC;
+    const int ptid = warp * 32 + lane;                        // 0 .. 383: byte of the input patch this thread stages
     const int pr = ptid / F1_PC, pc = ptid - pr * F1_PC;
-    const int tap_off = (cg / 3) * F1_PC + cg % 3;   // the input tap this lane converts for its pixel
     uint8_t* patch = smem_raw + F1_PATCH_OFF;
-    uint64_t wr[9][4], br[4];                     // channel pairs (2j, 2j+1), pre-multiplied by the plane scale (a power of two: exact)
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.w1a + t * 64 + cg * 8));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.w1a + t * 64 + cg * 8 + 4));
-      wr[t][0] = pk2(w0.x * P.act_scale, w0.y * P.act_scale); wr[t][1] = pk2(w0.z * P.act_scale, w0.w * P.act_scale);
-      wr[t][2] = pk2(w1.x * P.act_scale, w1.y * P.act_scale); wr[t][3] = pk2(w1.z * P.act_scale, w1.w * P.act_scale);
-    }
-    {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(P.b1a + cg * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(P.b1a + cg * 8 + 4));
-      br[0] = pk2(b0.x * P.act_scale, b0.y * P.act_scale); br[1] = pk2(b0.z * P.act_scale, b0.w * P.act_scale);
-      br[2] = pk2(b1.x * P.act_scale, b1.y * P.act_scale); br[3] = pk2(b1.z * P.act_scale, b1.w * P.act_scale);
-    }
     asm volatile("griddepcontrol.wait;" ::: "memory");       // the image is the previous kernel's output (no-op without PDL)
     // input patch of a tile: rows y0-2 .. y0+17, columns x0-2 .. x0+9 of the u8 image, zero outside (conv1a's padding)
     auto patch_byte = [&](int tile) -> uint32_t {
@@ -299,123 +299,98 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
     };
     int tile = blockIdx.x;
     if (ptid < F1_PR * F1_PC) patch[ptid] = (uint8_t)(tile < n_tiles ? patch_byte(tile) : 0u);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, 384;" ::: "memory");
     uint32_t i = 0;
     const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
-    long long c_w1 = 0, c_cmp = 0, c_w2 = 0, t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    long long c_w1 = 0, c_cmp = 0, t0 = 0, t1 = 0, t2 = 0;
     const long long t_begin = clock64();
     for (; tile < n_tiles; tile += gridDim.x, ++i) {
       const int w = i & 1;
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y;
       const int next = tile + gridDim.x;
       const uint32_t nb = next < n_tiles ? patch_byte(next) : 0u;      // next tile's patch byte: in flight for the whole tile
-      const uint32_t row0 = w ? F1_WIN1 : 0;
-      // a tile whose halo stays inside the image needs no validity test (warp-uniform)
-      const bool border = tx == 0 || ty == 0 || (tx + 1) * F1_TW + 1 > P.W || (ty + 1) * F1_TH + 1 > P.H;
-      // conv1a of halo pixel (r, c) -> split fp16 chunks of this thread's 8 channels
-      // the 8 lanes of a pixel need the same 9 inputs: lane cg converts tap cg (lane 0 also tap 8) and a width-8 shuffle hands
-      // them round -- 2 byte loads + 2 conversions per lane instead of 9.  The two bytes of step s+1 are loaded while step s
-      // computes: shared memory is saturated by the MMAs' operand reads, a load issued when it is needed waits for hundreds
-      // of cycles.
-      auto coords = [&](int step, int& r, int& c) {            // steps 0..4: private rows, step 5: the shared rows
-        const int qc = step < 5 ? min(step * 32 + slot, 149) : min(slot, 29);
-        const int rr = qc / F1_HC;
-        c = qc - rr * F1_HC;
-        r = step < 5 ? rr + (w ? 3 : 0) : rr + (w ? 0 : 15);
-      };
-      auto load_in = [&](int r, int c, float& v_own, float& v_8) {
-        const uint8_t* pp = patch + r * F1_PC + c;
-        if (kAblate & 2) { v_own = (float)(r + c); v_8 = (float)c; return; }
-        v_own = __fmul_rn(__uint2float_rn((uint32_t)pp[tap_off]), P.alpha);
-        v_8 = __fmul_rn(__uint2float_rn((uint32_t)pp[2 * F1_PC + 2]), P.alpha);
-      };
-      // conv1a of halo pixel (r, c) -> split fp16 chunks of this thread's 8 channels.  Taps outermost: every channel's fma
-      // chain still runs over the taps in ascending order (bit-identical to conv_first_split_kernel).
-      auto compute = [&](int r, int c, float v_own, float v_8, uint32_t (&h)[4], uint32_t (&l)[4]) {
-        uint64_t acc[4] = {br[0], br[1], br[2], br[3]};
-        float vin[9];                                          // all eight shuffles first: their latencies overlap
-#pragma unroll
-        for (int t = 0; t < 8; ++t) vin[t] = __shfl_sync(0xffffffffu, v_own, t, 8);
-        vin[8] = v_8;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const uint64_t vv = pk2(vin[t], vin[t]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = fma2(vv, wr[t][j], acc[j]);
-        }
-#pragma unroll
-        for (int j2 = 0; j2 < 4; ++j2) {
-          float a0, a1;
-          upk2(acc[j2], a0, a1);
-          const float s0 = fmaxf(a0, 0.f), s1 = fmaxf(a1, 0.f);
-          // one packed conversion per pair (cvt.rn.f16x2.f32: same roundings as two scalar conversions, off the slow pipe)
-          const __half2 hp = __floats2half2_rn(s0, s1);
-          const float2 hf = __half22float2(hp);
-          float d0, d1;
-          upk2(sub2(pk2(s0, s1), pk2(hf.x, hf.y)), d0, d1);
-          const __half2 lp = __floats2half2_rn(d0, d1);
-          h[j2] = *reinterpret_cast<const uint32_t*>(&hp);
-          l[j2] = *reinterpret_cast<const uint32_t*>(&lp);
-        }
-        if (border) {                                         // outside the image: conv1b's zero padding (border tiles only)
-          const int iy = ty * F1_TH - 1 + r, ix = tx * F1_TW - 1 + c;
-          if (!(iy >= 0 && iy < P.H && ix >= 0 && ix < P.W)) {
-#pragma unroll
-            for (int j2 = 0; j2 < 4; ++j2) { h[j2] = 0u; l[j2] = 0u; }
-          }
-        }
-      };
-      auto store = [&](int r, int c, const uint32_t (&h)[4], const uint32_t (&l)[4]) {
-        if (kAblate & 1) return;
-        const uint32_t off = ((row0 + r) * F1_HC + c) * 128;
-        const uint32_t ah = a_hi_base + off, al = a_lo_base + off;
-        st_shared_128(ah + (((uint32_t)cg ^ ((ah >> 7) & 7u)) << 4), h[0], h[1], h[2], h[3]);
-        st_shared_128(al + (((uint32_t)cg ^ ((al >> 7) & 7u)) << 4), l[0], l[1], l[2], l[3]);
-      };
-      // rows private to this window are free once the tile two back (same window) has retired
-      if (prof) t0 = clock64();
-      if (i >= 2) mbar_wait(mma_done(w), ((i >> 1) - 1) & 1);
-      if (prof) t1 = clock64();
-      // private rows: halo rows 0..14 of window 0, 3..17 of window 1
-      int r, c;
-      float v_own, v_8;
-      coords((kAblate & 16) ? 5 : 0, r, c);
-      load_in(r, c, v_own, v_8);
-#pragma unroll 1
-      for (int step = (kAblate & 16) ? 5 : 0; step < 5; ++step) {
-        int rn, cn;
-        float n_own, n_8;
-        coords(step + 1, rn, cn);
-        load_in(rn, cn, n_own, n_8);
-        uint32_t h[4], l[4];
-        compute(r, c, v_own, v_8, h, l);
-        if (step * 32 + slot < 150) store(r, c, h, l);
-        r = rn; c = cn; v_own = n_own; v_8 = n_8;
-      }
+      // halo row of the pixel and its byte offset in a plane: private rows 0..14 of window 0 sit in buffer rows 0..14, rows
+      // 3..17 of window 1 in buffer rows 18..32; the shared rows (15..17 of window 0 = 0..2 of window 1) in rows 15..17
+      const int r = sh ? rr + (w ? 0 : 15) : rr + (w ? 3 : 0);
+      const uint32_t off = (uint32_t)(((sh ? F1_WIN1 : (w ? F1_WIN1 + 3 : 0)) * F1_HC + qc) * 128);
+      const uint32_t ah = a_hi_base + off, al = a_lo_base + off;
+      const uint32_t ph = (ah >> 7) & 7u, pl = (al >> 7) & 7u;          // swizzle phases of the pixel's two rows
+      // outside the image: conv1b's zero padding (only tiles on the image border have such pixels)
+      const int iy = ty * F1_TH - 1 + r, ix = tx * F1_TW - 1 + cc;
+      const bool valid = iy >= 0 && iy < P.H && ix >= 0 && ix < P.W;
+      float in[9];
       {
-        // the three rows shared with the other window (15..17 of window 0 = 0..2 of window 1): computed now, stored only
-        // after the previous tile's MMAs have read them
-        uint32_t h[4], l[4];
-        compute(r, c, v_own, v_8, h, l);
-        if (prof) t2 = clock64();
-        if (i >= 1) mbar_wait(mma_done(w ^ 1), ((i - 1) >> 1) & 1);
-        if (prof) t3 = clock64();
-        if (slot < 30) store(r, c, h, l);
+        const uint8_t* pp = patch + r * F1_PC + cc;
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          in[t] = (kAblate & 2) ? (float)(t + r) : __fmul_rn(__uint2float_rn((uint32_t)pp[(t / 3) * F1_PC + t % 3]), P.alpha);
       }
+      if (prof) t0 = clock64();
+      // the rows may be overwritten once the MMAs that read them have retired: the tile two back (same window) for the
+      // private rows -- long gone -- and the PREVIOUS tile for the shared ones, which therefore sit on the critical path
+      // between two tiles' MMAs: their warps compute into registers first and only then wait, so that nothing but the
+      // stores is left to do when the rows are released
+      if (!sh && i >= 2) mbar_wait(mma_done(w), ((i >> 1) - 1) & 1);
+      if (prof) t1 = clock64();
+      uint32_t hq[4][4], lq[4][4];
+      if (!(kAblate & 16)) {
+        auto groups = [&](auto HALF) {
+          constexpr int C0 = decltype(HALF)::value * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint64_t acc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = pk2(W1.b[C0 + g * 8 + 2 * j], W1.b[C0 + g * 8 + 2 * j + 1]);
+            // taps ascending for every channel: the fma chain of conv_first_split_kernel, bit for bit
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const uint64_t vv = pk2(in[t], in[t]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                acc[j] = fma2(vv, pk2(W1.w[t][C0 + g * 8 + 2 * j], W1.w[t][C0 + g * 8 + 2 * j + 1]), acc[j]);
+            }
+#pragma unroll
+            for (int j2 = 0; j2 < 4; ++j2) {
+              float a0, a1;
+              upk2(acc[j2], a0, a1);
+              const float s0 = fmaxf(a0, 0.f), s1 = fmaxf(a1, 0.f);
+              // one packed conversion per pair (cvt.rn.f16x2.f32: same roundings as two scalar conversions)
+              const __half2 hp = __floats2half2_rn(s0, s1);
+              const float2 hf = __half22float2(hp);
+              float d0, d1;
+              upk2(sub2(pk2(s0, s1), pk2(hf.x, hf.y)), d0, d1);
+              const __half2 lp = __floats2half2_rn(d0, d1);
+              hq[g][j2] = valid ? *reinterpret_cast<const uint32_t*>(&hp) : 0u;
+              lq[g][j2] = valid ? *reinterpret_cast<const uint32_t*>(&lp) : 0u;
+            }
+          }
+        };
+        if (half) groups(std::integral_constant<int, 1>{}); else groups(std::integral_constant<int, 0>{});
+      }
+      if (sh && i >= 1) mbar_wait(mma_done(w ^ 1), ((i - 1) >> 1) & 1);
+      if (active && !(kAblate & (1 | 16))) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t chunk = (uint32_t)(half * 4 + g);
+          st_shared_128(ah + ((chunk ^ ph) << 4), hq[g][0], hq[g][1], hq[g][2], hq[g][3]);
+          st_shared_128(al + ((chunk ^ pl) << 4), lq[g][0], lq[g][1], lq[g][2], lq[g][3]);
+        }
+      }
+      if (prof) t2 = clock64();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(w));
       // hand the patch over to the next tile: everyone has read this one, then everyone sees the next
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 384;" ::: "memory");
       if (ptid < F1_PR * F1_PC) patch[ptid] = (uint8_t)nb;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (prof) { c_w1 += t1 - t0; c_cmp += t2 - t1; c_w2 += t3 - t2; }
+      asm volatile("bar.sync 1, 384;" ::: "memory");
+      if (prof) { c_w1 += t1 - t0; c_cmp += t2 - t1; }
     }
-    if (prof) { P.dbg[0] = c_w1; P.dbg[1] = c_cmp; P.dbg[2] = c_w2; P.dbg[3] = clock64() - t_begin; }
+    if (prof) { P.dbg[0] = c_w1; P.dbg[1] = c_cmp; P.dbg[2] = 0; P.dbg[3] = clock64() - t_begin; }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == F1_MMAW) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
   }
@@ -423,16 +398,20 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
 
 // conv1a + ReLU + conv1b + ReLU + 2x2 max-pool: u8 images -> the split planes conv2a reads.  L1b = conv1b's weights
 // (n_pad 64, Cin 64, 3x3) as uploaded by umma_layer_upload; w1a [tap][64], b1a [64] fp32.
-osb_status umma_conv1_fused_forward(const UmmaLayer& L1b, const float* w1a, const float* b1a, const uint8_t* img, int B, int H,
-                                    int W, float act_scale, __half* out_hi, __half* out_lo, float out_scale, cudaStream_t st,
+osb_status umma_conv1_fused_forward(const UmmaLayer& L1b, const float* w1a_host, const float* b1a_host, const uint8_t* img, int B,
+                                    int H, int W, float act_scale, __half* out_hi, __half* out_lo, float out_scale, cudaStream_t st,
                                     int max_ctas, unsigned long long* dbg) {
   OSB_REQUIRE(L1b.n_pad == 64 && L1b.cin == 64 && L1b.ks == 3, "fused first layers expect the 64 -> 64 3x3 layer");
   OSB_REQUIRE(H % 2 == 0 && W % 2 == 0, "fused max-pool needs even H and W");
   Fused1Args P;
-  P.img = img; P.w1a = w1a; P.b1a = b1a; P.bias = L1b.bias; P.out_hi = out_hi; P.out_lo = out_lo;
+  P.img = img; P.w1a = nullptr; P.b1a = nullptr; P.bias = L1b.bias; P.out_hi = out_hi; P.out_lo = out_lo;
   P.H = H; P.W = W; P.B = B;
   P.alpha = (float)(1.0 / 255.0);
   P.dbg = dbg; P.pool = 1;
+  Conv1aW W1;                                             // the plane scale is a power of two: the products are exact
+  for (int t = 0; t < 9; ++t)
+    for (int c = 0; c < 64; ++c) W1.w[t][c] = w1a_host[t * 64 + c] * act_scale;
+  for (int c = 0; c < 64; ++c) W1.b[c] = b1a_host[c] * act_scale;
   P.act_scale = act_scale; P.inv_scale = 1.0f / (act_scale * L1b.w_scale); P.out_scale = out_scale;
   OSB_SMEM_OPT_IN(conv64_halo_kernel<true>, F1_SMEM);
   const int tiles = B * cdiv(W, F1_TW) * cdiv(H, F1_TH);
@@ -440,7 +419,7 @@ osb_status umma_conv1_fused_forward(const UmmaLayer& L1b, const float* w1a, cons
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(F1_THREADS); cfg.dynamicSmemBytes = F1_SMEM; cfg.stream = st;
   // (the activation maps are unused by the FIRST instantiation: the weight maps stand in)
-  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv64_halo_kernel<true>, L1b.tm_hi, L1b.tm_lo, L1b.tm_hi, L1b.tm_lo, L1b.tm_hi, L1b.tm_lo, P));
+  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv64_halo_kernel<true>, L1b.tm_hi, L1b.tm_lo, L1b.tm_hi, L1b.tm_lo, L1b.tm_hi, L1b.tm_lo, W1, P));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return OSB_OK;
 }
@@ -473,7 +452,8 @@ osb_status umma_conv64_halo_forward(const UmmaLayer& L, const HaloMaps& M, int B
   const int grid = std::min(tiles, persistent_ctas(max_ctas));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(F1_THREADS); cfg.dynamicSmemBytes = F1_SMEM; cfg.stream = st;
-  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv64_halo_kernel<false>, L.tm_hi, L.tm_lo, M.a15_hi, M.a15_lo, M.a3_hi, M.a3_lo, P));
+  static const Conv1aW no_w1 = {};
+  OSB_CUDA(cudaLaunchKernelEx(&cfg, conv64_halo_kernel<false>, L.tm_hi, L.tm_lo, M.a15_hi, M.a15_lo, M.a3_hi, M.a3_lo, no_w1, P));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return OSB_OK;
 }

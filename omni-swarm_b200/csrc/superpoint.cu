@@ -53,6 +53,8 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
     OSB_CUDA(cudaMalloc(&b1a, 64 * sizeof(float)));
     OSB_CUDA(cudaMemcpy(w1a, w9.data(), 9 * 64 * sizeof(float), cudaMemcpyHostToDevice));
     OSB_CUDA(cudaMemcpy(b1a, p + 64 * 9, 64 * sizeof(float), cudaMemcpyHostToDevice));
+    w1a_host = w9;
+    b1a_host.assign(p + 64 * 9, p + 64 * 9 + 64);
     p += 64 * 9 + 64;
   }
   {
@@ -173,7 +175,7 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
     mark(st);
   } else if (fuse_first) {
     mark(st);                                                                             // (conv1a has no launch of its own)
-    RUN(umma_conv1_fused_forward(UL[1], w1a, b1a, img_dev, B, H, W, SA, in_hi[2], in_lo[2], SA, st, 0,
+    RUN(umma_conv1_fused_forward(UL[1], w1a_host.data(), b1a_host.data(), img_dev, B, H, W, SA, in_hi[2], in_lo[2], SA, st, 0,
                                  (layer_prof && dbg_layer == 1) ? d_f1dbg : nullptr));   // conv1a+conv1b+pool -> B
     mark(st);
   } else {

@@ -15,6 +15,7 @@ struct SuperPoint {
   cudaStream_t stream = nullptr;
   // weights
   float *w1a = nullptr, *b1a = nullptr, *lut = nullptr, *pca_compT = nullptr, *pca_mean_d = nullptr;
+  std::vector<float> w1a_host, b1a_host;          // conv1a [tap][64] and bias: the fused first-layers kernel takes them as a kernel parameter
   ConvLayer L[12];
   // activations / outputs (device)
   uint8_t* d_img = nullptr;
