@@ -127,7 +127,7 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
   if (threadIdx.x == 0) {
     mbar_init(b_full, 1);
     for (int w = 0; w < 2; ++w) { mbar_init(a_full(w), FIRST ? F1_NPROD : 1); mbar_init(mma_done(w), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), FIRST ? 4 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == F1_MMAW) {
@@ -168,7 +168,9 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       const uint32_t row0 = w ? F1_WIN1 : 0;
       uint32_t first = 1;
       // tap order (kx outer, ky inner, K ascending) = the accumulation order of conv_umma_kernel: bit-identical sums
-      for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll 1
+      for (int kx = 0; kx < 3; ++kx) {                       // (not unrolled: 27 hoisted descriptors would spill)
+#pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           const uint32_t off = ((row0 + ky) * F1_HC + kx) * 128;
           const uint64_t a_hi = umma_desc_sw128_sbo(a_hi_base + off, F1_PITCH);
@@ -191,12 +193,15 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       if (prof) { c_te += t1 - t0; c_af += t2 - t1; c_is += clock64() - t2; }
     }
     if (prof) { P.dbg[4] = c_te; P.dbg[5] = c_af; P.dbg[6] = c_is; P.dbg[9] = i; }
-  } else if (warp >= F1_EPI0 && warp < F1_EPI0 + 4) {
-    // ===================== epilogue =====================
+  } else if (FIRST ? (warp >= F1_EPI0 && warp < F1_EPI0 + 4) : (warp >= 4 && warp < 12)) {
+    // ===================== epilogue (FIRST: warps 12..15; otherwise the eight warps the producers would be, two per TMEM
+    //                       lane quarter taking the 16-column chunks alternately) =====================
     const int q = warp & 3;                        // TMEM lane quarter = tile rows 4q .. 4q+3 (lane = (row & 3) * 8 + col)
     int acc = 0; uint32_t acc_phase = 0;
     const int Hp = P.H >> 1, Wp = P.W >> 1;
-    const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == F1_EPI0 && lane == 0;
+    const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == (FIRST ? F1_EPI0 : 4) && lane == 0;
+    const int eset = FIRST ? 0 : (warp - 4) >> 2;
+    constexpr int NSET = FIRST ? 1 : 2;
     long long c_wait = 0, c_work = 0, t0 = 0, t1 = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       if (prof) t0 = clock64();
@@ -212,7 +217,7 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
 #pragma unroll 1
-      for (int n0 = 0; n0 < 64; n0 += 16) {
+      for (int n0 = eset * 16; n0 < 64; n0 += 16 * NSET) {
         uint32_t v[16], vc[16];
         tmem_ld16(t_row + n0, v);
         tmem_ld16(t_row + 64 + n0, vc);

@@ -17,8 +17,9 @@
 // for 2N <= 256 one MMA of width 2N covers hi*hi and hi*lo at once.  Both planes together are 4 bytes per element -- the
 // same HBM/L2 footprint as fp32 activations -- and the fp16 MACs cost 1.5x one TF32 MMA.  Measured against the oracle:
 // see tests/test_gpu_superpoint.py.
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane each), warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (tcgen05.ld -> bias/ReLU -> re-split -> NHWC stores).  Persistent over tiles.
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane each), warp 2 = TMEM
+// allocator, warps 4-11 = epilogue (tcgen05.ld -> bias/ReLU -> re-split -> NHWC stores; two warps per TMEM lane quarter).
+// Persistent over tiles.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -38,6 +39,7 @@ constexpr int UM_KC = 64;                       // fp16 channels per K slab (= 1
 // The weights of each tap stream through their own ring.
 constexpr int UM_A_SLOT = (UM_TH + 2) * UM_TW * 128;   // 20 KB per plane: 10 rows x 16 px x 128 B
 constexpr int UM_A_SLOTS = 2;
+constexpr int UM_THREADS = 384;                 // 12 warps: TMA, MMA, TMEM allocator, (idle), 8 x epilogue
 // RES = true (64 -> 64 channel 3x3 layers: conv1b, conv2a, conv2b = 65 % of the network's FLOPs): the 9 taps' weight
 // planes (144 KB) stay resident in shared memory for the CTA's whole life instead of streaming through a ring, which
 // removes more than half of the remaining L2 -> shared-memory traffic.
@@ -74,7 +76,7 @@ struct UmmaArgs {
 };
 
 template <int N, bool RES, bool SPLIT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(UM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, UmmaArgs P) {
   using Cfg = UmmaCfg<N, RES>;
@@ -103,7 +105,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < AS; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     // (with NBUF == 1 only index 0 is used; with RES the b_full barriers are filled once and b_empty stays unused)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -231,7 +233,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // eight warps: two per TMEM lane quarter, which take the 16-column chunks alternately -- one warp per quarter leaves
+    // the epilogue, not the MMAs, as the pace of the 64-channel layers (a chunk is a long dependent chain: TMEM load,
+    // arithmetic, conversions, stores)
     const int q = warp & 3;                                    // TMEM lane quarter this warp may access
+    const int eset = (warp - 4) >> 2;                          // 0 / 1: which chunks of the quarter
     const int m = q * 32 + lane;                               // output pixel within the tile
     const int r = m / UM_TW, c = m % UM_TW;
     int acc = 0; uint32_t acc_phase = 0;
@@ -250,6 +256,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       const bool pool_writer = P.pool && lane < 16 && !(lane & 1) && py < (P.H >> 1) && px < (P.W >> 1);
       const size_t ppix = ((size_t)b * (P.H >> 1) + py) * (P.W >> 1) + px;
       if (P.epi == 1) {
+        if (eset == 0) {
         // fused detector head (superpoint.ipynb:190-198): the thread holds one cell's 65 logits in TMEM.  Three passes over
         // the columns (max, sum in channel order, normalise + pixel shuffle) -- the arithmetic of sp_softmax_shuffle_kernel,
         // so the heat map is bit-identical to the two-kernel path.
@@ -294,9 +301,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             dst[1] = make_float4(e[8 * r2 + 4], e[8 * r2 + 5], e[8 * r2 + 6], e[8 * r2 + 7]);
           }
         }
+        }      // (the second warp of the quarter has nothing to do for this head: it only releases the accumulator)
       } else
 #pragma unroll 1
-      for (int n0 = 0; n0 < N; n0 += 16) {
+      for (int n0 = eset * 16; n0 < N; n0 += 32) {
         uint32_t v[16], vc[16];
         tmem_ld16(t_row + n0, v);
         tmem_ld16(t_row + N + n0, vc);
@@ -332,10 +340,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float s0 = f[2 * i] * P.out_scale, s1 = f[2 * i + 1] * P.out_scale;
-            const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
-            const __half l0 = __float2half_rn(s0 - __half2float(h0)), l1 = __float2half_rn(s1 - __half2float(h1));
-            hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            // packed conversions (cvt.rn.f16x2.f32: the roundings of two scalar conversions, off the slow F2F pipe)
+            const __half2 hp = __floats2half2_rn(s0, s1);
+            const float2 hf = __half22float2(hp);
+            const __half2 lp = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+            hi[i] = *reinterpret_cast<const uint32_t*>(&hp);
+            lo[i] = *reinterpret_cast<const uint32_t*>(&lp);
           }
           st_global_256(P.out_hi + opix * P.out_cstride + n_off + n0, hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7]);
           st_global_256(P.out_lo + opix * P.out_cstride + n_off + n0, lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7]);
@@ -343,7 +353,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));              // 4 epilogue warps -> count 4
+      if (lane == 0) mbar_arrive(tempty_bar(acc));              // 8 epilogue warps -> count 8
       if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -558,7 +568,7 @@ static osb_status launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, 
   const int grid = std::min(tiles, persistent_ctas(max_ctas));
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = g_conv_pdl ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
