@@ -41,16 +41,16 @@ constexpr int F1_WIN1 = F1_ROWS - F1_HR;                // 15: first row of wind
 constexpr int F1_PLANE = F1_ROWS * F1_PITCH;            // 42 240 B
 constexpr int F1_W_SLOT = 2 * 64 * 128;                 // one tap: [W_hi (64 rows) | W_lo (64 rows)] x 128 B
 constexpr int F1_W_BYTES = 9 * F1_W_SLOT;               // 147 456 B
-constexpr int F1_NPROD = 12;                            // producer warps: lane = halo pixel, warp = (pixel block, channel half)
-constexpr int F1_EPI0 = 12;                             // warps 12..15: epilogue (TMEM lane quarter = warp & 3)
-constexpr int F1_MMAW = 16;                             // warp 16: TMEM allocation, weight TMA, MMA issue
-constexpr int F1_THREADS = 17 * 32;                     // 544 -> at most 120 registers per thread
+constexpr int F1_NPROD = 6;                             // producer warps: lane = halo pixel, warp = block of 32 pixels
+constexpr int F1_EPI0 = 6;                              // warps 6..13: epilogue, two per TMEM lane quarter (= warp & 3)
+constexpr int F1_MMAW = 14;                             // warp 14: TMEM allocation, weight TMA, MMA issue
+constexpr int F1_THREADS = 15 * 32;                     // 480 (16-warp allocation: 128 registers per thread)
 constexpr int F1_BAR_OFF = F1_W_BYTES + 2 * F1_PLANE;
 constexpr int F1_PR = F1_HR + 2, F1_PC = F1_HC + 2;     // u8 input patch of a tile: 20 rows x 12 columns
 constexpr int F1_PATCH_OFF = F1_BAR_OFF + 80;           // 9 mbarriers + the TMEM base slot, then the patch
 constexpr int F1_SMEM = F1_PATCH_OFF + F1_PR * F1_PC;
 static_assert(F1_SMEM <= 227 * 1024, "shared memory plan exceeds 227 KB");
-static_assert(F1_PR * F1_PC <= F1_NPROD * 32, "one patch byte per producer thread");
+static_assert(F1_PR * F1_PC <= 2 * F1_NPROD * 32, "two patch bytes per producer thread");
 
 // measurement only (make EXTRA=-DF1_ABLATE=<bits> after touching this file, results are WRONG when set): 1 producers do not store, 2 no patch loads,
 // 4 epilogue only drains TMEM, 8 no lo*hi MMA, 16 producers do not compute.  profiles/r02_f1_ablate.txt
@@ -127,7 +127,7 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
   if (threadIdx.x == 0) {
     mbar_init(b_full, 1);
     for (int w = 0; w < 2; ++w) { mbar_init(a_full(w), FIRST ? F1_NPROD : 1); mbar_init(mma_done(w), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), FIRST ? 4 : 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == F1_MMAW) {
@@ -193,15 +193,15 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       if (prof) { c_te += t1 - t0; c_af += t2 - t1; c_is += clock64() - t2; }
     }
     if (prof) { P.dbg[4] = c_te; P.dbg[5] = c_af; P.dbg[6] = c_is; P.dbg[9] = i; }
-  } else if (FIRST ? (warp >= F1_EPI0 && warp < F1_EPI0 + 4) : (warp >= 4 && warp < 12)) {
-    // ===================== epilogue (FIRST: warps 12..15; otherwise the eight warps the producers would be, two per TMEM
-    //                       lane quarter taking the 16-column chunks alternately) =====================
+  } else if (warp >= F1_EPI0 && warp < F1_EPI0 + 8) {
+    // ===================== epilogue: eight warps, two per TMEM lane quarter, taking the 16-column chunks alternately (one
+    //                       warp per quarter is slower than the MMAs: a chunk is one long dependent chain) =====================
     const int q = warp & 3;                        // TMEM lane quarter = tile rows 4q .. 4q+3 (lane = (row & 3) * 8 + col)
     int acc = 0; uint32_t acc_phase = 0;
     const int Hp = P.H >> 1, Wp = P.W >> 1;
-    const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == (FIRST ? F1_EPI0 : 4) && lane == 0;
-    const int eset = FIRST ? 0 : (warp - 4) >> 2;
-    constexpr int NSET = FIRST ? 1 : 2;
+    const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == F1_EPI0 && lane == 0;
+    const int eset = (warp - F1_EPI0) >> 2;
+    constexpr int NSET = 2;
     long long c_wait = 0, c_work = 0, t0 = 0, t1 = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       if (prof) t0 = clock64();
@@ -277,34 +277,34 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       tma_load_4d(a_lo_base + sdst, &tm_a3_lo, a_full(w), 0, x0, y0 + srow, b);
     }
   } else if (FIRST && warp < F1_NPROD) {
-    // ===================== conv1a producers (12 warps, three per scheduler) =====================
-    // lane = halo pixel, warp = (block of 32 pixels, half of the 64 channels).  Warps 0..9 take the 150 pixels of the rows
-    // private to the window (5 blocks x 2 halves), warps 10 and 11 the 30 pixels of the three rows shared with the other
-    // window, which may only be overwritten after the previous tile's MMAs have retired.  A thread converts its pixel's
-    // nine inputs once and runs its 32 channels in four groups of eight: 36 FFMA2 per group with the weights from the
-    // constant bank, then ReLU, the fp16 split and one 16-byte store per plane (the eight pixels of a quarter-warp sit in
-    // eight consecutive 128-byte rows, whose swizzle phases differ: conflict-free).
+    // ===================== conv1a producers (6 warps) =====================
+    // lane = halo pixel.  Warps 0..4 take the 150 pixels of the rows private to the window, warp 5 the 30 pixels of the
+    // three rows shared with the other window, which may only be overwritten after the previous tile's MMAs have retired.
+    // A thread converts its pixel's nine inputs once and runs the 64 channels in eight groups of eight: 36 FFMA2 per group
+    // with the weights from the constant bank, then ReLU, the fp16 split and one 16-byte store per plane (the eight pixels
+    // of a quarter-warp sit in eight consecutive 128-byte rows, whose swizzle phases differ: conflict-free).
     const int pw = warp;
-    const bool sh = pw >= 10;
-    const int half = pw & 1;
-    const int q = sh ? lane : (pw >> 1) * 32 + lane;          // pixel index inside its part
+    const bool sh = pw == 5;
+    const int q = sh ? lane : pw * 32 + lane;                 // pixel index inside its part
     const bool active = sh ? lane < 30 : q < 150;
     const int qc = sh ? min(q, 29) : min(q, 149);
     const int rr = qc / F1_HC, cc = qc - rr * F1_HC;
-    const int ptid = warp * 32 + lane;                        // 0 .. 383: byte of the input patch this thread stages
-    const int pr = ptid / F1_PC, pc = ptid - pr * F1_PC;
+    const int ptid = warp * 32 + lane;                        // 0 .. 191: stages patch bytes ptid and ptid + 192
     uint8_t* patch = smem_raw + F1_PATCH_OFF;
     asm volatile("griddepcontrol.wait;" ::: "memory");       // the image is the previous kernel's output (no-op without PDL)
     // input patch of a tile: rows y0-2 .. y0+17, columns x0-2 .. x0+9 of the u8 image, zero outside (conv1a's padding)
-    auto patch_byte = [&](int tile) -> uint32_t {
+    auto patch_byte = [&](int tile, int idx) -> uint32_t {
+      const int pr = idx / F1_PC, pc = idx - pr * F1_PC;
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
       const int gy = ty * F1_TH - 2 + pr, gx = tx * F1_TW - 2 + pc;
-      const bool in = ptid < F1_PR * F1_PC && gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
+      const bool in = idx < F1_PR * F1_PC && gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
       return in ? (uint32_t)__ldg(P.img + ((size_t)b * P.H + gy) * P.W + gx) : 0u;
     };
+    constexpr int NPT = F1_NPROD * 32;
     int tile = blockIdx.x;
-    if (ptid < F1_PR * F1_PC) patch[ptid] = (uint8_t)(tile < n_tiles ? patch_byte(tile) : 0u);
-    asm volatile("bar.sync 1, 384;" ::: "memory");
+    patch[ptid] = (uint8_t)(tile < n_tiles ? patch_byte(tile, ptid) : 0u);
+    if (ptid + NPT < F1_PR * F1_PC) patch[ptid + NPT] = (uint8_t)(tile < n_tiles ? patch_byte(tile, ptid + NPT) : 0u);
+    asm volatile("bar.sync 1, 192;" ::: "memory");
     uint32_t i = 0;
     const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
     long long c_w1 = 0, c_cmp = 0, t0 = 0, t1 = 0, t2 = 0;
@@ -313,7 +313,9 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       const int w = i & 1;
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y;
       const int next = tile + gridDim.x;
-      const uint32_t nb = next < n_tiles ? patch_byte(next) : 0u;      // next tile's patch byte: in flight for the whole tile
+      // next tile's patch bytes: in flight for the whole tile
+      const uint32_t nb0 = next < n_tiles ? patch_byte(next, ptid) : 0u;
+      const uint32_t nb1 = next < n_tiles ? patch_byte(next, ptid + NPT) : 0u;
       // halo row of the pixel and its byte offset in a plane: private rows 0..14 of window 0 sit in buffer rows 0..14, rows
       // 3..17 of window 1 in buffer rows 18..32; the shared rows (15..17 of window 0 = 0..2 of window 1) in rows 15..17
       const int r = sh ? rr + (w ? 0 : 15) : rr + (w ? 3 : 0);
@@ -333,62 +335,72 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       if (prof) t0 = clock64();
       // the rows may be overwritten once the MMAs that read them have retired: the tile two back (same window) for the
       // private rows -- long gone -- and the PREVIOUS tile for the shared ones, which therefore sit on the critical path
-      // between two tiles' MMAs: their warps compute into registers first and only then wait, so that nothing but the
-      // stores is left to do when the rows are released
+      // between two tiles' MMAs: their warp computes all 64 channels into registers first and only then waits, so that
+      // nothing but the stores is left to do when the rows are released
       if (!sh && i >= 2) mbar_wait(mma_done(w), ((i >> 1) - 1) & 1);
       if (prof) t1 = clock64();
-      uint32_t hq[4][4], lq[4][4];
-      if (!(kAblate & 16)) {
-        auto groups = [&](auto HALF) {
-          constexpr int C0 = decltype(HALF)::value * 32;
+      // one group of eight channels -> packed split fp16 (hi, lo); taps ascending for every channel: the fma chain of
+      // conv_first_split_kernel, bit for bit
+      auto group = [&](auto G, uint32_t (&h)[4], uint32_t (&l)[4]) {
+        constexpr int C0 = decltype(G)::value * 8;
+        uint64_t acc[4];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint64_t acc[4];
+        for (int j = 0; j < 4; ++j) acc[j] = pk2(W1.b[C0 + 2 * j], W1.b[C0 + 2 * j + 1]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = pk2(W1.b[C0 + g * 8 + 2 * j], W1.b[C0 + g * 8 + 2 * j + 1]);
-            // taps ascending for every channel: the fma chain of conv_first_split_kernel, bit for bit
+        for (int t = 0; t < 9; ++t) {
+          const uint64_t vv = pk2(in[t], in[t]);
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              const uint64_t vv = pk2(in[t], in[t]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                acc[j] = fma2(vv, pk2(W1.w[t][C0 + g * 8 + 2 * j], W1.w[t][C0 + g * 8 + 2 * j + 1]), acc[j]);
-            }
-#pragma unroll
-            for (int j2 = 0; j2 < 4; ++j2) {
-              float a0, a1;
-              upk2(acc[j2], a0, a1);
-              const float s0 = fmaxf(a0, 0.f), s1 = fmaxf(a1, 0.f);
-              // one packed conversion per pair (cvt.rn.f16x2.f32: same roundings as two scalar conversions)
-              const __half2 hp = __floats2half2_rn(s0, s1);
-              const float2 hf = __half22float2(hp);
-              float d0, d1;
-              upk2(sub2(pk2(s0, s1), pk2(hf.x, hf.y)), d0, d1);
-              const __half2 lp = __floats2half2_rn(d0, d1);
-              hq[g][j2] = valid ? *reinterpret_cast<const uint32_t*>(&hp) : 0u;
-              lq[g][j2] = valid ? *reinterpret_cast<const uint32_t*>(&lp) : 0u;
-            }
-          }
-        };
-        if (half) groups(std::integral_constant<int, 1>{}); else groups(std::integral_constant<int, 0>{});
-      }
-      if (sh && i >= 1) mbar_wait(mma_done(w ^ 1), ((i - 1) >> 1) & 1);
-      if (active && !(kAblate & (1 | 16))) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t chunk = (uint32_t)(half * 4 + g);
-          st_shared_128(ah + ((chunk ^ ph) << 4), hq[g][0], hq[g][1], hq[g][2], hq[g][3]);
-          st_shared_128(al + ((chunk ^ pl) << 4), lq[g][0], lq[g][1], lq[g][2], lq[g][3]);
+          for (int j = 0; j < 4; ++j) acc[j] = fma2(vv, pk2(W1.w[t][C0 + 2 * j], W1.w[t][C0 + 2 * j + 1]), acc[j]);
         }
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          float a0, a1;
+          upk2(acc[j2], a0, a1);
+          const float s0 = fmaxf(a0, 0.f), s1 = fmaxf(a1, 0.f);
+          // one packed conversion per pair (cvt.rn.f16x2.f32: same roundings as two scalar conversions)
+          const __half2 hp = __floats2half2_rn(s0, s1);
+          const float2 hf = __half22float2(hp);
+          float d0, d1;
+          upk2(sub2(pk2(s0, s1), pk2(hf.x, hf.y)), d0, d1);
+          const __half2 lp = __floats2half2_rn(d0, d1);
+          h[j2] = valid ? *reinterpret_cast<const uint32_t*>(&hp) : 0u;
+          l[j2] = valid ? *reinterpret_cast<const uint32_t*>(&lp) : 0u;
+        }
+      };
+      auto put = [&](int g, const uint32_t (&h)[4], const uint32_t (&l)[4]) {
+        if (!active || (kAblate & 1)) return;
+        st_shared_128(ah + (((uint32_t)g ^ ph) << 4), h[0], h[1], h[2], h[3]);
+        st_shared_128(al + (((uint32_t)g ^ pl) << 4), l[0], l[1], l[2], l[3]);
+      };
+      if (!(kAblate & 16)) {
+        if (!sh) {
+          auto run = [&](auto G) { uint32_t h[4], l[4]; group(G, h, l); put(decltype(G)::value, h, l); };
+          run(std::integral_constant<int, 0>{}); run(std::integral_constant<int, 1>{});
+          run(std::integral_constant<int, 2>{}); run(std::integral_constant<int, 3>{});
+          run(std::integral_constant<int, 4>{}); run(std::integral_constant<int, 5>{});
+          run(std::integral_constant<int, 6>{}); run(std::integral_constant<int, 7>{});
+        } else {
+          uint32_t hq[8][4], lq[8][4];
+          group(std::integral_constant<int, 0>{}, hq[0], lq[0]); group(std::integral_constant<int, 1>{}, hq[1], lq[1]);
+          group(std::integral_constant<int, 2>{}, hq[2], lq[2]); group(std::integral_constant<int, 3>{}, hq[3], lq[3]);
+          group(std::integral_constant<int, 4>{}, hq[4], lq[4]); group(std::integral_constant<int, 5>{}, hq[5], lq[5]);
+          group(std::integral_constant<int, 6>{}, hq[6], lq[6]); group(std::integral_constant<int, 7>{}, hq[7], lq[7]);
+          if (i >= 1) mbar_wait(mma_done(w ^ 1), ((i - 1) >> 1) & 1);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) put(g, hq[g], lq[g]);
+        }
+      } else if (sh && i >= 1) {
+        mbar_wait(mma_done(w ^ 1), ((i - 1) >> 1) & 1);
       }
       if (prof) t2 = clock64();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(w));
       // hand the patch over to the next tile: everyone has read this one, then everyone sees the next
-      asm volatile("bar.sync 1, 384;" ::: "memory");
-      if (ptid < F1_PR * F1_PC) patch[ptid] = (uint8_t)nb;
-      asm volatile("bar.sync 1, 384;" ::: "memory");
+      asm volatile("bar.sync 1, 192;" ::: "memory");
+      patch[ptid] = (uint8_t)nb0;
+      if (ptid + NPT < F1_PR * F1_PC) patch[ptid + NPT] = (uint8_t)nb1;
+      asm volatile("bar.sync 1, 192;" ::: "memory");
       if (prof) { c_w1 += t1 - t0; c_cmp += t2 - t1; }
     }
     if (prof) { P.dbg[0] = c_w1; P.dbg[1] = c_cmp; P.dbg[2] = 0; P.dbg[3] = clock64() - t_begin; }
