@@ -119,7 +119,7 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       mbar_init(a_local(w), 1);
       mbar_init(mma_done(w), 1);
     }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), FIRST ? 8 : 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 12) {
@@ -167,7 +167,9 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
         tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)(acc * 128), d_cross = d_main + 64;
         uint32_t first = 1;
+#pragma unroll 1
         for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
             const uint32_t off = (uint32_t)w * P2_WIN + (uint32_t)((ky * P2_HC + kx) * 128);
             const uint64_t a_hi = p2_desc_sbo(a_hi_base + off, P2_PITCH);
@@ -190,9 +192,12 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       }
       if (prof) { P.dbg[4] = c_te; P.dbg[5] = c_af; P.dbg[6] = c_is; P.dbg[9] = i; }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== epilogue (each CTA drains its own TMEM) =====================
+  } else if (warp >= 4 && warp < (FIRST ? 8 : 12)) {
+    // ===================== epilogue (each CTA drains its own TMEM; without producers eight warps, two per lane quarter,
+    //                       take the 16-column chunks alternately) =====================
     const int q = warp & 3;
+    const int eset = (warp - 4) >> 2;
+    constexpr int NSET = FIRST ? 1 : 2;
     int acc = 0; uint32_t acc_phase = 0;
     const int Hp = P.H >> 1, Wp = P.W >> 1;
     const uint32_t tempty0 = mapa_u32(tempty_bar(0), 0), tempty1 = mapa_u32(tempty_bar(1), 0);
@@ -214,7 +219,7 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
 #pragma unroll 1
-      for (int n0 = 0; n0 < 64; n0 += 16) {
+      for (int n0 = eset * 16; n0 < 64; n0 += 16 * NSET) {
         uint32_t v[16], vc[16];
         tmem_ld16(t_row + n0, v);
         tmem_ld16(t_row + 64 + n0, vc);

@@ -41,7 +41,7 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
   if (const char* e = getenv("OSB_SP_FUSED_SOFTMAX")) fused_softmax = atoi(e) != 0;
   if (const char* e = getenv("OSB_SP_FUSE1")) fuse_first = atoi(e) != 0;
   if (const char* e = getenv("OSB_SP_HALO64")) halo64 = atoi(e) != 0;
-  if (const char* e = getenv("OSB_SP_PAIR")) pair64 = atoi(e) != 0;
+  if (const char* e = getenv("OSB_SP_PAIR")) { pair64 = atoi(e) != 0; pair_first = atoi(e) == 1; }
   // ---- weights ----
   const float* p = weights;
   {
@@ -168,7 +168,7 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
   // cycle counters of the 64 -> 64 kernels (osb_superpoint_read what = 5): OSB_F1_DEBUG=<1|2|3> selects conv1 / conv2a / conv2b;
   // off by default because the clock reads cost a few percent of the kernel
   static const int dbg_layer = [] { const char* e = getenv("OSB_F1_DEBUG"); return e ? atoi(e) : 0; }();
-  if (fuse_first && pair64) {
+  if (fuse_first && pair64 && pair_first) {
     mark(st);
     RUN(umma_pair_first_forward(UL[1], w1a, b1a, img_dev, B, H, W, SA, in_hi[2], in_lo[2], SA, st, 0,
                                 (layer_prof && dbg_layer == 1) ? d_f1dbg : nullptr));     // conv1a+conv1b+pool -> B
