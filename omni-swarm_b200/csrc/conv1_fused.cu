@@ -59,11 +59,6 @@ static_assert(F1_PR * F1_PC <= 2 * F1_NPROD * 32, "two patch bytes per producer 
 #endif
 constexpr int kAblate = F1_ABLATE;
 
-// conv1a's weights and bias, pre-multiplied by the plane scale, as a KERNEL PARAMETER: with lane = pixel every FFMA of a warp
-// uses the same weight, so it comes from the constant bank through a uniform register (LDCU.128 + FFMA2 R, R.F32, UR, R)
-// instead of occupying 72 registers per thread
-struct Conv1aW { float w[9][64]; float b[64]; };
-
 struct Fused1Args {
   const uint8_t* img;      // [B][H][W]
   const float* w1a;        // conv1a weights [tap][64]
@@ -83,13 +78,6 @@ struct Fused1Args {
 __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// packed fp32 pairs (sm_100: FFMA2 / FADD2 -- one issue slot for two IEEE fp32 operations; the producers are issue bound)
-__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
-}
-__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ void st_shared_128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -306,7 +294,7 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
     if (ptid + NPT < F1_PR * F1_PC) patch[ptid + NPT] = (uint8_t)(tile < n_tiles ? patch_byte(tile, ptid + NPT) : 0u);
     asm volatile("bar.sync 1, 192;" ::: "memory");
     uint32_t i = 0;
-    const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
+    const bool prof = P.dbg != nullptr && blockIdx.x == 0 && lane == 0;        // every producer warp: dbg[10 + warp] = its busy cycles
     long long c_w1 = 0, c_cmp = 0, t0 = 0, t1 = 0, t2 = 0;
     const long long t_begin = clock64();
     for (; tile < n_tiles; tile += gridDim.x, ++i) {
@@ -403,7 +391,8 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       asm volatile("bar.sync 1, 192;" ::: "memory");
       if (prof) { c_w1 += t1 - t0; c_cmp += t2 - t1; }
     }
-    if (prof) { P.dbg[0] = c_w1; P.dbg[1] = c_cmp; P.dbg[2] = 0; P.dbg[3] = clock64() - t_begin; }
+    if (prof && warp == 0) { P.dbg[0] = c_w1; P.dbg[1] = c_cmp; P.dbg[2] = 0; P.dbg[3] = clock64() - t_begin; }
+    if (prof) P.dbg[10 + warp] = c_cmp + c_w1;
   }
   tc_fence_before();
   __syncthreads();

@@ -18,6 +18,7 @@
 // Bit-identical to conv_umma_kernel<64,RES> / conv1_fused.cu: same operand values, same accumulation order per output row.
 #include "conv_umma.cuh"
 #include "umma_ptx.cuh"
+#include <type_traits>
 
 namespace osb {
 
@@ -29,8 +30,10 @@ constexpr int P2_PLANE = 2 * P2_WIN;                    // two windows
 constexpr int P2_WX = 64 * 128, P2_WY = 32 * 128;       // weight regions of a tap: X = 64 rows, Y = 32 rows
 constexpr int P2_W_SLOT = P2_WX + P2_WY;                // 12 288 B
 constexpr int P2_W_BYTES = 9 * P2_W_SLOT;               // 110 592 B
-constexpr int P2_NPROD = 8;
-constexpr int P2_THREADS = 14 * 32;
+constexpr int P2_NPROD = 6;                             // producer warps: lane = halo pixel (180 of 192 lanes)
+constexpr int P2_EPI0 = 6;                              // warps 6..13: epilogue, two per TMEM lane quarter
+constexpr int P2_MMAW = 14;                             // warp 14: TMEM allocation, weight TMA, MMA issue (leader)
+constexpr int P2_THREADS = 15 * 32;
 constexpr int P2_BAR_OFF = P2_W_BYTES + 2 * P2_PLANE;   // 202 752
 constexpr int P2_PR = P2_HR + 2, P2_PC = P2_HC + 2;     // u8 patch 20 x 12
 constexpr int P2_PATCH_OFF = P2_BAR_OFF + 128;          // 12 mbarriers + TMEM slot
@@ -89,7 +92,7 @@ template <bool FIRST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
 conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                    const __grid_constant__ CUtensorMap tm_w_hi32, const __grid_constant__ CUtensorMap tm_a_hi,
-                   const __grid_constant__ CUtensorMap tm_a_lo, PairArgs P) {
+                   const __grid_constant__ CUtensorMap tm_a_lo, const __grid_constant__ Conv1aW W1, PairArgs P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();
@@ -119,10 +122,10 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       mbar_init(a_local(w), 1);
       mbar_init(mma_done(w), 1);
     }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), FIRST ? 8 : 16); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
+  if (warp == P2_MMAW) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(bar_base + 96u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
@@ -137,7 +140,7 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
   // tile of this CTA in pair-iteration i; the second tile of an odd last pair repeats the last tile and stores nothing
   auto tile_of = [&](int pair) { return 2 * pair + (int)rank; };
 
-  if (warp == 13 && elect_one()) {
+  if (warp == P2_MMAW && elect_one()) {
     // ===================== weights: this CTA's share of every tap, resident for the kernel's life =====================
     // leader: X = W_hi rows 0..63, Y = W_hi rows 0..31;  peer: X = W_lo rows 0..63, Y = W_hi rows 32..63
     mbar_expect_tx(b_full, P2_W_BYTES);
@@ -192,16 +195,16 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       }
       if (prof) { P.dbg[4] = c_te; P.dbg[5] = c_af; P.dbg[6] = c_is; P.dbg[9] = i; }
     }
-  } else if (warp >= 4 && warp < (FIRST ? 8 : 12)) {
-    // ===================== epilogue (each CTA drains its own TMEM; without producers eight warps, two per lane quarter,
-    //                       take the 16-column chunks alternately) =====================
+  } else if (warp >= P2_EPI0 && warp < P2_EPI0 + 8) {
+    // ===================== epilogue (each CTA drains its own TMEM; eight warps, two per lane quarter, take the
+    //                       16-column chunks alternately) =====================
     const int q = warp & 3;
-    const int eset = (warp - 4) >> 2;
-    constexpr int NSET = FIRST ? 1 : 2;
+    const int eset = (warp - P2_EPI0) >> 2;
+    constexpr int NSET = 2;
     int acc = 0; uint32_t acc_phase = 0;
     const int Hp = P.H >> 1, Wp = P.W >> 1;
     const uint32_t tempty0 = mapa_u32(tempty_bar(0), 0), tempty1 = mapa_u32(tempty_bar(1), 0);
-    const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
+    const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == P2_EPI0 && lane == 0;
     long long c_wait = 0, c_work = 0, t0 = 0, t1 = 0;
     for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
       const int tile_raw = tile_of(pair);
@@ -273,42 +276,32 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       mbar_wait(a_local(w), (i >> 1) & 1);                    // landed here -> tell the leader
       mbar_arrive_cluster(w ? af1 : af0);
     }
-  } else if (FIRST && (warp < 4 || (warp >= 8 && warp < 12))) {
-    // ===================== conv1a producers (8 warps per CTA) =====================
-    const int pw = warp < 4 ? warp : warp - 4;
-    const int slot = pw * 4 + (lane >> 3);
-    const int cg = lane & 7;
-    const int ptid = pw * 32 + lane;
-    const int pr = ptid / P2_PC, pc = ptid - pr * P2_PC;
+  } else if (FIRST && warp < P2_NPROD) {
+    // ===================== conv1a producers (6 warps per CTA): lane = halo pixel, all 64 channels in eight groups of
+    // eight, weights from the constant bank (conv1_fused.cu has the same producers; here every window is a full one) =====
+    const int q = warp * 32 + lane;
+    const bool active = q < P2_HR * P2_HC;
+    const int qc = min(q, P2_HR * P2_HC - 1);
+    const int r = qc / P2_HC, c = qc - r * P2_HC;
+    const int ptid = warp * 32 + lane;                       // stages patch bytes ptid and ptid + 192
+    constexpr int NPT = P2_NPROD * 32;
     uint8_t* patch0 = smem_raw + P2_PATCH_OFF;
     const uint32_t af0 = mapa_u32(a_full(0), 0), af1 = mapa_u32(a_full(1), 0);
-    float wr[9][8], br[8];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.w1a + t * 64 + cg * 8));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.w1a + t * 64 + cg * 8 + 4));
-      wr[t][0] = w0.x; wr[t][1] = w0.y; wr[t][2] = w0.z; wr[t][3] = w0.w;
-      wr[t][4] = w1.x; wr[t][5] = w1.y; wr[t][6] = w1.z; wr[t][7] = w1.w;
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) wr[t][jj] *= P.act_scale;
-    }
-    {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(P.b1a + cg * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(P.b1a + cg * 8 + 4));
-      br[0] = b0.x; br[1] = b0.y; br[2] = b0.z; br[3] = b0.w; br[4] = b1.x; br[5] = b1.y; br[6] = b1.z; br[7] = b1.w;
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) br[jj] *= P.act_scale;
-    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    auto patch_byte = [&](int tile) -> uint32_t {
+    auto patch_byte = [&](int tile, int idx) -> uint32_t {
+      const int pr = idx / P2_PC, pc = idx - pr * P2_PC;
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
       const int gy = ty * P2_TH - 2 + pr, gx = tx * P2_TW - 2 + pc;
-      const bool in = ptid < P2_PR * P2_PC && gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
+      const bool in = idx < P2_PR * P2_PC && gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
       return in ? (uint32_t)__ldg(P.img + ((size_t)b * P.H + gy) * P.W + gx) : 0u;
     };
     int pair = cluster_id;
-    if (pair < n_pairs && ptid < P2_PR * P2_PC) patch0[ptid] = (uint8_t)patch_byte(min(tile_of(pair), n_tiles - 1));
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (pair < n_pairs) {
+      const int t0 = min(tile_of(pair), n_tiles - 1);
+      patch0[ptid] = (uint8_t)patch_byte(t0, ptid);
+      if (ptid + NPT < P2_PR * P2_PC) patch0[ptid + NPT] = (uint8_t)patch_byte(t0, ptid + NPT);
+    }
+    asm volatile("bar.sync 1, 192;" ::: "memory");
     uint32_t i = 0;
     const bool prof = P.dbg != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
     long long c_w1 = 0, c_cmp = 0, t0 = 0, t1 = 0, t2 = 0;
@@ -318,69 +311,81 @@ conv64_pair_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       const int tile = min(tile_of(pair), n_tiles - 1);
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y;
       const int next = pair + n_clusters;
-      const uint32_t nb = next < n_pairs ? patch_byte(min(tile_of(next), n_tiles - 1)) : 0u;
+      const int ntile = min(tile_of(next), n_tiles - 1);
+      const uint32_t nb0 = next < n_pairs ? patch_byte(ntile, ptid) : 0u;
+      const uint32_t nb1 = next < n_pairs ? patch_byte(ntile, ptid + NPT) : 0u;
       const uint8_t* patch = patch0 + (i & 1) * 256;
       uint8_t* patch_next = patch0 + ((i + 1) & 1) * 256;            // last read in iteration i-1, before its closing barrier
-      const uint32_t wbase = (uint32_t)w * P2_WIN;
+      const uint32_t off = (uint32_t)w * P2_WIN + (uint32_t)(qc * 128);
+      const uint32_t ah = a_hi_base + off, al = a_lo_base + off;
+      const uint32_t ph = (ah >> 7) & 7u, pl = (al >> 7) & 7u;
+      const int iy = ty * P2_TH - 1 + r, ix = tx * P2_TW - 1 + c;
+      const bool valid = iy >= 0 && iy < P.H && ix >= 0 && ix < P.W;
+      float in[9];
+      {
+        const uint8_t* pp = patch + r * P2_PC + c;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) in[t] = __fmul_rn(__uint2float_rn((uint32_t)pp[(t / 3) * P2_PC + t % 3]), P.alpha);
+      }
       if (prof) t0 = clock64();
       if (i >= 2) mbar_wait(mma_done(w), ((i >> 1) - 1) & 1);
       if (prof) t1 = clock64();
-#pragma unroll 1
-      for (int step = 0; step < 6; ++step) {
-        const int q = step * 32 + slot;
-        const int qc = min(q, P2_HR * P2_HC - 1);
-        const int r = qc / P2_HC, c = qc - r * P2_HC;
-        const uint8_t* pp = patch + r * P2_PC + c;
-        float in[3][3];
+      auto run = [&](auto G) {
+        constexpr int C0 = decltype(G)::value * 8;
+        uint64_t acc[4];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
+        for (int j = 0; j < 4; ++j) acc[j] = pk2(W1.b[C0 + 2 * j], W1.b[C0 + 2 * j + 1]);
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) in[dy][dx] = __fmul_rn(__uint2float_rn((uint32_t)pp[dy * P2_PC + dx]), P.alpha);
-        const int iy = ty * P2_TH - 1 + r, ix = tx * P2_TW - 1 + c;
-        const bool valid = iy >= 0 && iy < P.H && ix >= 0 && ix < P.W;
+        for (int t = 0; t < 9; ++t) {                         // taps ascending per channel: conv_first_split_kernel's fma chain
+          const uint64_t vv = pk2(in[t], in[t]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fma2(vv, pk2(W1.w[t][C0 + 2 * j], W1.w[t][C0 + 2 * j + 1]), acc[j]);
+        }
         uint32_t h[4], l[4];
 #pragma unroll
         for (int j2 = 0; j2 < 4; ++j2) {
-          float a0 = br[2 * j2], a1 = br[2 * j2 + 1];
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            a0 = fmaf(in[t / 3][t % 3], wr[t][2 * j2], a0);
-            a1 = fmaf(in[t / 3][t % 3], wr[t][2 * j2 + 1], a1);
-          }
+          float a0, a1;
+          upk2(acc[j2], a0, a1);
           const float s0 = fmaxf(a0, 0.f), s1 = fmaxf(a1, 0.f);
           const __half2 hp = __floats2half2_rn(s0, s1);
           const float2 hf = __half22float2(hp);
-          const __half2 lp = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+          float d0, d1;
+          upk2(sub2(pk2(s0, s1), pk2(hf.x, hf.y)), d0, d1);
+          const __half2 lp = __floats2half2_rn(d0, d1);
           h[j2] = valid ? *reinterpret_cast<const uint32_t*>(&hp) : 0u;
           l[j2] = valid ? *reinterpret_cast<const uint32_t*>(&lp) : 0u;
         }
-        if (q < P2_HR * P2_HC) {
-          const uint32_t off = wbase + (uint32_t)((r * P2_HC + c) * 128);
-          const uint32_t ah = a_hi_base + off, al = a_lo_base + off;
-          p2_st_shared_128(ah + (((uint32_t)cg ^ ((ah >> 7) & 7u)) << 4), h[0], h[1], h[2], h[3]);
-          p2_st_shared_128(al + (((uint32_t)cg ^ ((al >> 7) & 7u)) << 4), l[0], l[1], l[2], l[3]);
+        if (active) {
+          const uint32_t g = (uint32_t)decltype(G)::value;
+          p2_st_shared_128(ah + ((g ^ ph) << 4), h[0], h[1], h[2], h[3]);
+          p2_st_shared_128(al + ((g ^ pl) << 4), l[0], l[1], l[2], l[3]);
         }
-      }
+      };
+      run(std::integral_constant<int, 0>{}); run(std::integral_constant<int, 1>{});
+      run(std::integral_constant<int, 2>{}); run(std::integral_constant<int, 3>{});
+      run(std::integral_constant<int, 4>{}); run(std::integral_constant<int, 5>{});
+      run(std::integral_constant<int, 6>{}); run(std::integral_constant<int, 7>{});
       if (prof) t2 = clock64();
       asm volatile("fence.proxy.async;" ::: "memory");         // generic-proxy stores -> visible to the pair's MMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(w ? af1 : af0);
-      if (ptid < P2_PR * P2_PC) patch_next[ptid] = (uint8_t)nb;  // the next tile's patch byte (its load had the whole tile to land)
-      asm volatile("bar.sync 1, 256;" ::: "memory");           // patch_next written by all, this patch read by all
+      patch_next[ptid] = (uint8_t)nb0;                         // the next tile's patch bytes (their loads had the whole tile to land)
+      if (ptid + NPT < P2_PR * P2_PC) patch_next[ptid + NPT] = (uint8_t)nb1;
+      asm volatile("bar.sync 1, 192;" ::: "memory");           // patch_next written by all, this patch read by all
       if (prof) { c_w1 += t1 - t0; c_cmp += t2 - t1; }
     }
     if (prof) { P.dbg[0] = c_w1; P.dbg[1] = c_cmp; P.dbg[2] = 0; P.dbg[3] = clock64() - t_begin; }
   }
   tc_fence_before();
   cluster_sync_all();                                          // nobody leaves while the peer may still signal or read
-  if (warp == 12) {
+  if (warp == P2_MMAW) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
   }
 }
 
-static osb_status launch_pair(bool first, const UmmaLayer& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const PairArgs& P,
-                              cudaStream_t st, int max_ctas) {
+static osb_status launch_pair(bool first, const UmmaLayer& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const Conv1aW& W1,
+                              const PairArgs& P, cudaStream_t st, int max_ctas) {
   const int tiles = P.B * cdiv(P.W, P2_TW) * cdiv(P.H, P2_TH);
   const int pairs = (tiles + 1) / 2;
   int ctas = persistent_ctas(max_ctas);
@@ -389,25 +394,29 @@ static osb_status launch_pair(bool first, const UmmaLayer& L, const CUtensorMap&
   cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(P2_THREADS); cfg.dynamicSmemBytes = P2_SMEM; cfg.stream = st;
   if (first) {
     OSB_SMEM_OPT_IN(conv64_pair_kernel<true>, P2_SMEM);
-    OSB_CUDA(cudaLaunchKernelEx(&cfg, conv64_pair_kernel<true>, L.tm_hi, L.tm_lo, L.tm_hi32, a_hi, a_lo, P));
+    OSB_CUDA(cudaLaunchKernelEx(&cfg, conv64_pair_kernel<true>, L.tm_hi, L.tm_lo, L.tm_hi32, a_hi, a_lo, W1, P));
   } else {
     OSB_SMEM_OPT_IN(conv64_pair_kernel<false>, P2_SMEM);
-    OSB_CUDA(cudaLaunchKernelEx(&cfg, conv64_pair_kernel<false>, L.tm_hi, L.tm_lo, L.tm_hi32, a_hi, a_lo, P));
+    OSB_CUDA(cudaLaunchKernelEx(&cfg, conv64_pair_kernel<false>, L.tm_hi, L.tm_lo, L.tm_hi32, a_hi, a_lo, W1, P));
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return OSB_OK;
 }
 
-osb_status umma_pair_first_forward(const UmmaLayer& L1b, const float* w1a, const float* b1a, const uint8_t* img, int B, int H,
-                                   int W, float act_scale, __half* out_hi, __half* out_lo, float out_scale, cudaStream_t st,
+osb_status umma_pair_first_forward(const UmmaLayer& L1b, const float* w1a_host, const float* b1a_host, const uint8_t* img, int B,
+                                   int H, int W, float act_scale, __half* out_hi, __half* out_lo, float out_scale, cudaStream_t st,
                                    int max_ctas, unsigned long long* dbg) {
   OSB_REQUIRE(L1b.n_pad == 64 && L1b.cin == 64 && L1b.ks == 3, "pair kernel expects the 64 -> 64 3x3 layer");
   OSB_REQUIRE(H % 2 == 0 && W % 2 == 0, "fused max-pool needs even H and W");
   PairArgs P;
-  P.img = img; P.w1a = w1a; P.b1a = b1a; P.bias = L1b.bias; P.out_hi = out_hi; P.out_lo = out_lo;
+  P.img = img; P.w1a = nullptr; P.b1a = nullptr; P.bias = L1b.bias; P.out_hi = out_hi; P.out_lo = out_lo;
   P.H = H; P.W = W; P.B = B; P.alpha = (float)(1.0 / 255.0); P.pool = 1; P.dbg = dbg;
   P.act_scale = act_scale; P.inv_scale = 1.0f / (act_scale * L1b.w_scale); P.out_scale = out_scale;
-  return launch_pair(true, L1b, L1b.tm_hi, L1b.tm_lo, P, st, max_ctas);     // (activation maps unused)
+  Conv1aW W1;                                             // the plane scale is a power of two: the products are exact
+  for (int t = 0; t < 9; ++t)
+    for (int c = 0; c < 64; ++c) W1.w[t][c] = w1a_host[t * 64 + c] * act_scale;
+  for (int c = 0; c < 64; ++c) W1.b[c] = b1a_host[c] * act_scale;
+  return launch_pair(true, L1b, L1b.tm_hi, L1b.tm_lo, W1, P, st, max_ctas);     // (activation maps unused)
 }
 
 // descriptors of a 64-channel activation tensor for the pair kernel: one box {64 ch, 10 px, 18 rows} per plane
@@ -429,7 +438,8 @@ osb_status umma_pair_conv64_forward(const UmmaLayer& L, const CUtensorMap& a_hi,
   P.img = nullptr; P.w1a = nullptr; P.b1a = nullptr; P.bias = L.bias; P.out_hi = out_hi; P.out_lo = out_lo;
   P.H = H; P.W = W; P.B = B; P.alpha = 0.f; P.pool = pool; P.dbg = dbg;
   P.act_scale = act_scale; P.inv_scale = 1.0f / (act_scale * L.w_scale); P.out_scale = out_scale;
-  return launch_pair(false, L, a_hi, a_lo, P, st, max_ctas);
+  static const Conv1aW no_w1 = {};
+  return launch_pair(false, L, a_hi, a_lo, no_w1, P, st, max_ctas);
 }
 
 }  // namespace osb

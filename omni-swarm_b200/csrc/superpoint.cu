@@ -41,7 +41,7 @@ osb_status SuperPoint::init(const float* weights, size_t n_weights, int width, i
   if (const char* e = getenv("OSB_SP_FUSED_SOFTMAX")) fused_softmax = atoi(e) != 0;
   if (const char* e = getenv("OSB_SP_FUSE1")) fuse_first = atoi(e) != 0;
   if (const char* e = getenv("OSB_SP_HALO64")) halo64 = atoi(e) != 0;
-  if (const char* e = getenv("OSB_SP_PAIR")) { pair64 = atoi(e) != 0; pair_first = atoi(e) == 1; }
+  if (const char* e = getenv("OSB_SP_PAIR")) { pair64 = atoi(e) != 0; pair_first = atoi(e) == 1; pair_2a = atoi(e) != 3; }
   // ---- weights ----
   const float* p = weights;
   {
@@ -170,7 +170,7 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
   static const int dbg_layer = [] { const char* e = getenv("OSB_F1_DEBUG"); return e ? atoi(e) : 0; }();
   if (fuse_first && pair64 && pair_first) {
     mark(st);
-    RUN(umma_pair_first_forward(UL[1], w1a, b1a, img_dev, B, H, W, SA, in_hi[2], in_lo[2], SA, st, 0,
+    RUN(umma_pair_first_forward(UL[1], w1a_host.data(), b1a_host.data(), img_dev, B, H, W, SA, in_hi[2], in_lo[2], SA, st, 0,
                                 (layer_prof && dbg_layer == 1) ? d_f1dbg : nullptr));     // conv1a+conv1b+pool -> B
     mark(st);
   } else if (fuse_first) {
@@ -185,8 +185,11 @@ osb_status SuperPoint::network_umma(const uint8_t* img_dev, int B, cudaStream_t 
     mark(st);
   }
   if (pair64) {
-    RUN(umma_pair_conv64_forward(UL[2], pairA[2], pairB[2], B, H / 2, W / 2, SA, in_hi[3], in_lo[3], SA, 0, st, 0,
-                                 (layer_prof && dbg_layer == 2) ? d_f1dbg : nullptr));                  // conv2a   -> A
+    if (pair_2a)
+      RUN(umma_pair_conv64_forward(UL[2], pairA[2], pairB[2], B, H / 2, W / 2, SA, in_hi[3], in_lo[3], SA, 0, st, 0,
+                                   (layer_prof && dbg_layer == 2) ? d_f1dbg : nullptr));                // conv2a   -> A
+    else
+      RUN(conv(2, H / 2, W / 2, 3, 0));
     mark(st);
     RUN(umma_pair_conv64_forward(UL[3], pairA[3], pairB[3], B, H / 2, W / 2, SA, in_hi[4], in_lo[4], SA, 1, st, 0,
                                  (layer_prof && dbg_layer == 3) ? d_f1dbg : nullptr));                  // conv2b + pool -> B

@@ -46,7 +46,8 @@ struct SuperPoint {
   bool overlap_kp = true;
   unsigned long long* d_f1dbg = nullptr;   // cycle counters of the fused first-layers kernel (filled while layer_prof is on)
   CUtensorMap pairA[4], pairB[4]; // [2], [3]: conv2a / conv2b inputs for the CTA-pair kernel (one 18-row box per plane)
-  bool pair_first = false;        // OSB_SP_PAIR=1: the first layers on CTA pairs too; OSB_SP_PAIR=2: only conv2a / conv2b
+  bool pair_first = false;        // OSB_SP_PAIR=1: the first layers on CTA pairs too; =2: only conv2a / conv2b; =3: only conv2b
+  bool pair_2a = true;
   bool pair64 = false;            // OSB_SP_PAIR=1: conv1a+1b, conv2a, conv2b on CTA pairs (conv64_pair.cu, tcgen05.mma.cta_group::2).
                                   // Bit-identical, measured SLOWER than the single-CTA kernels (r02: conv1 0.57 vs 0.47 ms, conv2a
                                   // 0.120 vs 0.116 ms; the pair's MMA stream ran at 134 cycles per K step against 114) -- kept as a switch

@@ -20,4 +20,5 @@ for fuse in (os.environ.get("F1_MODES", "1,0").split(",")):
         names = ["prod_wait_window", "prod_compute", "prod_wait_shared", "prod_total", "mma_wait_tmem", "mma_wait_tile",
                  "mma_issue", "epi_wait", "epi_work", "tiles"]
         print({k: round(float(v / n), 1) for k, v in zip(names, c[:9])}, "tiles", int(c[9]))
+        print("producer warps busy+wait per tile:", [round(float(v / n), 1) for v in c[10:16]])
     sp.close()
