@@ -339,7 +339,7 @@ def run_ours(args):
     # random unit-norm rows with local descriptors up to db_rows
     for i in range(POOL_IN_DB):
         fe.extract(dev_up[i].data_ptr(), dev_dn[i].data_ptr(), 10_000 + i, rec_dev.data_ptr(), st, device_images=True)
-        fe.ingest(rec_dev.data_ptr(), 1, -1, st)
+        fe.ingest_own(rec_dev.data_ptr(), st)
     fe.finish(st)
     n_fill = args.db_rows - fe.db_size(False)
     chunk = 2000
@@ -360,7 +360,7 @@ def run_ours(args):
             fe.ingest(gathered.data_ptr(), world, -1, st)
             return
         b = i & 1
-        fe.ingest(rec.data_ptr(), 1, -1, st)                                  # add_to_database of the own keyframe
+        fe.ingest_own(rec.data_ptr(), st)                                     # add_to_database of the own keyframe
         if pending[0]:
             sw.wait(st)
             fe.ingest(gath2[b ^ 1].data_ptr(), world, rank, st)               # last round's foreign keyframes (own slot skipped)
@@ -376,7 +376,7 @@ def run_ours(args):
             fe.query(rec.data_ptr(), res_dev.data_ptr(), st)
         else:
             fe.extract(dev_up[j].data_ptr(), dev_dn[j].data_ptr(), i, rec_dev.data_ptr(), st, device_images=True)
-            fe.ingest(rec_dev.data_ptr(), 1, -1, st)
+            fe.ingest_own(rec_dev.data_ptr(), st)
             fe.query(rec_dev.data_ptr(), res_dev.data_ptr(), st)
 
     def keyframe_e2e(i):
@@ -743,7 +743,7 @@ def run_ours(args):
         def kf5(i):
             j = i % POOL
             fe5.extract(dev_up[j].data_ptr(), dev_dn[j].data_ptr(), i, rec5.data_ptr(), st, device_images=True)
-            fe5.ingest(rec5.data_ptr(), 1, -1, st)
+            fe5.ingest_own(rec5.data_ptr(), st)
             fe5.query(rec5.data_ptr(), res_dev.data_ptr(), st)
         for i in range(5):
             kf5(i)

@@ -448,6 +448,11 @@ osb_status osb_frontend_extract_dev(osb_frontend* h, const uint8_t* images_up_de
  * local database, others to the remote one; index `skip` is ignored, pass -1 to ingest all) -- add_to_database. */
 osb_status osb_frontend_ingest(osb_frontend* h, const osb_keyframe_record* records_dev, int n_records, int skip,
                                void* stream);
+/* the same for ONE record that the caller knows to be this drone's own (the record extract has just written: on_image_recv's
+ * add_to_database, loop_detector.cpp:89).  The routing is still by drone_id on the device; what the promise buys is that the
+ * host does not have to assume the record might have gone to the remote database, so a drone that has never received a
+ * foreign keyframe does not scan an empty remote store on every query. */
+osb_status osb_frontend_ingest_own(osb_frontend* h, const osb_keyframe_record* record_dev, void* stream);
 /* query: run query_from_database for the keyframe in `record_dev` (must already be ingested if it is an own keyframe,
  * as on_image_recv does) and, on a hit, the per-direction cross-check match against the stored keyframe; the result
  * is written to `result_dev` (DEVICE).  init_mode / nonkeyframe as loop_detector.cpp:176. */

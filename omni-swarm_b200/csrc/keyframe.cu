@@ -683,12 +683,16 @@ static void fe_tighten_bounds(osb_frontend* h) {
   h->db[1].upper = std::min<int64_t>(h->db[1].upper, nr + since);
 }
 
-static osb_status fe_ingest(osb_frontend* h, const osb_keyframe_record* recs, int n_records, int skip, cudaStream_t st) {
+// side: which store the host CHARGES for the batch (its bounds): 0 = unknown (both), 1 = all records are this drone's own,
+// 2 = all records are foreign.  The kernel always routes by drone_id.
+static osb_status fe_ingest(osb_frontend* h, const osb_keyframe_record* recs, int n_records, int skip, cudaStream_t st,
+                            int side = 0) {
   OSB_REQUIRE(n_records >= 0 && n_records <= h->max_records, "too many records in one ingest (max 64)");
   if (n_records == 0) return OSB_OK;
   DbStore &L = h->db[0], &R = h->db[1];
   fe_tighten_bounds(h);
-  if (L.upper + (int64_t)n_records * OSB_MAX_DIRS > L.cap || R.upper + (int64_t)n_records * OSB_MAX_DIRS > R.cap) {
+  const int64_t chg_l = side == 2 ? 0 : (int64_t)n_records * OSB_MAX_DIRS, chg_r = side == 1 ? 0 : (int64_t)n_records * OSB_MAX_DIRS;
+  if (L.upper + chg_l > L.cap || R.upper + chg_r > R.cap) {
     // the upper bounds are conservative (every record charged to both databases): make them exact, and count which
     // database each record of this batch really goes to, before giving up
     osb_status rs = fe_refresh_counts(h, st);
@@ -717,12 +721,19 @@ static osb_status fe_ingest(osb_frontend* h, const osb_keyframe_record* recs, in
   OSB_LAUNCH(fe_copy_rows_kernel, n_records * OSB_MAX_DIRS, 256, 0, st, recs, h->d_assign, h->cfg.max_num, L.rows,
              L.ldesc, L.nk, R.rows, R.ldesc, R.nk, L.kpts, L.smatch, R.kpts, R.smatch);
   OSB_CHECK_LAUNCH();
-  L.upper += (int64_t)n_records * OSB_MAX_DIRS;
-  R.upper += (int64_t)n_records * OSB_MAX_DIRS;
+  L.upper += chg_l;
+  R.upper += chg_r;
   OSB_CUDA(cudaEventRecord(h->ev_ingest, st));
   h->ingest_pending = true;
   fe_mark(h, 5, st);
   return OSB_OK;
+}
+
+extern "C" osb_status osb_frontend_ingest_own(osb_frontend* h, const osb_keyframe_record* record_dev, void* stream) {
+  OSB_REQUIRE(h && record_dev, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard dg(h->device);
+  return fe_ingest(h, record_dev, 1, -1, (cudaStream_t)stream, 1);
 }
 
 extern "C" osb_status osb_frontend_ingest(osb_frontend* h, const osb_keyframe_record* records_dev, int n_records,
@@ -813,7 +824,7 @@ extern "C" osb_status osb_frontend_process(osb_frontend* h, const uint8_t* image
   OSB_CUDA(cudaMemcpyAsync(h->d_img + half, images_down, half, cudaMemcpyHostToDevice, st));
   osb_status s;
   if ((s = fe_extract_dev(h, h->d_img, msg_id, h->d_record, st)) != OSB_OK) return s;
-  if ((s = fe_ingest(h, h->d_record, 1, -1, st)) != OSB_OK) return s;      // add_to_database (loop_detector.cpp:89)
+  if ((s = fe_ingest(h, h->d_record, 1, -1, st, 1)) != OSB_OK) return s;   // add_to_database (loop_detector.cpp:89): own record
   if ((s = fe_query(h, h->d_record, 0, 0, h->d_result, st)) != OSB_OK) return s;
   if (record_host) OSB_CUDA(cudaMemcpyAsync(record_host, h->d_record, sizeof(osb_keyframe_record), cudaMemcpyDeviceToHost, st));
   if (result_host) OSB_CUDA(cudaMemcpyAsync(result_host, h->d_result, sizeof(osb_loop_result), cudaMemcpyDeviceToHost, st));

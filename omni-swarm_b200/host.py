@@ -395,6 +395,10 @@ class KeyframeFrontend:
     def ingest(self, records_dev: int, n_records: int, skip: int, stream: int):
         _l.check(self._lib.osb_frontend_ingest(self._h, C.c_void_p(records_dev), n_records, skip, C.c_void_p(stream)))
 
+    def ingest_own(self, record_dev: int, stream: int):
+        """add_to_database of the record `extract` has just written (this drone's own)"""
+        _l.check(self._lib.osb_frontend_ingest_own(self._h, C.c_void_p(record_dev), C.c_void_p(stream)))
+
     def query(self, record_dev: int, result_dev: int, stream: int, init_mode=False, nonkeyframe=False):
         _l.check(self._lib.osb_frontend_query(self._h, C.c_void_p(record_dev), int(init_mode), int(nonkeyframe),
                                               C.c_void_p(result_dev), C.c_void_p(stream)))

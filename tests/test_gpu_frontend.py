@@ -366,3 +366,48 @@ def test_swarm_exchange_single_rank_and_ingest(gpu):
     with pytest.raises(host._l.OsbError):
         host.Swarm(None, 0, 2)                     # world > 1 needs the unique id
     sw.close(); fe.close()
+
+
+def test_ingest_own_equals_ingest_and_remote_store_wakes_up(gpu):
+    """osb_frontend_ingest_own is osb_frontend_ingest of one own record with a promise to the host's bookkeeping: the same
+    rows, the same query results -- and the remote store, unscanned while nothing foreign has arrived, takes part in the
+    query as soon as a foreign keyframe is ingested afterwards."""
+    import torch
+    stream = torch.cuda.current_stream().cuda_stream
+    frames = [frame_images(40 + s) for s in range(3)]
+    results = []
+    for own in (False, True):
+        fe = make_frontend(match_index_dist=1)
+        rec_t = torch.zeros(lib.RECORD_BYTES, dtype=torch.uint8, device="cuda")
+        res_t = torch.zeros(lib.RESULT_BYTES, dtype=torch.uint8, device="cuda")
+        out = []
+        for i, (up, down) in enumerate(frames + [frames[0]]):
+            up = np.ascontiguousarray(up); down = np.ascontiguousarray(down)
+            fe.extract(up.ctypes.data, down.ctypes.data, 900 + i, rec_t.data_ptr(), stream)
+            if own:
+                fe.ingest_own(rec_t.data_ptr(), stream)
+            else:
+                fe.ingest(rec_t.data_ptr(), 1, -1, stream)
+            fe.query(rec_t.data_ptr(), res_t.data_ptr(), stream)
+            fe.finish(stream)
+            out.append(res_t.cpu().numpy().tobytes())
+        assert fe.db_size(False) == 16 and fe.db_size(True) == 0
+        if own:
+            # a foreign copy of keyframe 1 arrives: an own NON-keyframe that looks like it must now hit the remote store
+            up, down = (np.ascontiguousarray(a) for a in frames[1])
+            fe.extract(up.ctypes.data, down.ctypes.data, 950, rec_t.data_ptr(), stream)
+            fe.finish(stream)
+            raw = bytearray(rec_t.cpu().numpy().tobytes())
+            lib.KeyframeRecord.from_buffer(raw).drone_id = 7
+            f_t = torch.frombuffer(raw, dtype=torch.uint8).cuda()
+            fe.ingest(f_t.data_ptr(), 1, -1, stream)
+            fe.query(rec_t.data_ptr(), res_t.data_ptr(), stream, nonkeyframe=True)
+            fe.finish(stream)
+            res = lib.LoopResult.from_buffer_copy(res_t.cpu().numpy().tobytes())
+            assert fe.db_size(True) == 4
+            assert res.accepted == 1 and res.hit_id >= lib.REMOTE_MAGIN_NUMBER and res.hit_drone_id == 7
+        results.append(out)
+        fe.close()
+    assert results[0] == results[1]
+    last = lib.LoopResult.from_buffer_copy(results[1][-1])
+    assert last.accepted == 1 and last.hit_msg_id == 900
