@@ -528,7 +528,7 @@ def run_ours(args):
     scan_ms = stages["db_scan"]
     scan_bytes = (db_rows_now + db_rows_remote) * 4096 * 4.0        # local + remote database, each row read once
     scan_gbs = scan_bytes / scan_ms / 1e6
-    roofline = {"kernel": "conv1_fused_kernel (conv1a 1->64 computed in the SM by 8 producer warps + conv1b 64->64 3x3 @640x480 on "
+    roofline = {"kernel": "conv1_fused_kernel (conv1a 1->64 computed in the SM by 6 producer warps (lane = pixel, constant-bank weights, FFMA2) + conv1b 64->64 3x3 @640x480 on "
                           "tcgen05 from ONE shared-memory halo copy (9 descriptor views) + fused 2x2 max-pool; split-fp16: hi*hi + "
                           "hi*lo as one MMA of width 128, lo*hi as one of width 64 per K step)",
                 "bound": "tensor", "achieved": dom_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",

@@ -14,7 +14,7 @@
 // to tensor-pipe bound.
 // Barriers: producers and epilogue warps of BOTH CTAs arrive on the leader's mbarriers (mapa + mbarrier.arrive
 // .shared::cluster); the leader's tcgen05.commit multicasts "accumulators full" and "halo window free" to both CTAs.
-// FIRST = true: halo tile computed from the u8 image (conv1a, 8 producer warps per CTA); false: loaded by TMA (conv2a/2b).
+// FIRST = true: halo tile computed from the u8 image (conv1a, 6 producer warps per CTA); false: loaded by TMA (conv2a/2b).
 // Bit-identical to conv_umma_kernel<64,RES> / conv1_fused.cu: same operand values, same accumulation order per output row.
 #include "conv_umma.cuh"
 #include "umma_ptx.cuh"
