@@ -308,8 +308,12 @@ def run_ours(args):
     comp, mean = synth.pca_matrices(0)
     spw = synth.flatten_sp_weights(synth.superpoint_weights(0))
     nvw = synth.flatten_nv_weights(synth.netvlad_weights(0))
+    # database capacity: the preloaded rows plus everything this run will add.  Every keyframe round adds 4 rows per drone
+    # (own -> local store, foreign -> remote store), and the rounds are: both timed regions (warm-up included), the host-issue
+    # and stage-profile passes and the C4 replay.  (An undersized store made the 8-rank run fail in the replay leg.)
+    rounds_total = 2 * (args.warmup + args.steps) * KF_PER_STEP + 8 + 5 + 120 + 64
     fe = host.KeyframeFrontend(spw, comp, mean, nvw, width=W, height=H, n_dirs=N_DIRS, max_num=MAX_NUM, sp_thres=0.015,
-                               self_id=rank, db_capacity=args.db_rows + 4096, inner_product_thres=0.3,
+                               self_id=rank, db_capacity=args.db_rows + N_DIRS * (world + 1) * rounds_total + 1024, inner_product_thres=0.3,
                                match_index_dist=5, zero_bottom_quarter=True, accept_min_3d_pts=10)
     st = torch.cuda.current_stream().cuda_stream
 
@@ -924,7 +928,15 @@ if __name__ == "__main__":
     _JSON_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
+    except BaseException:
+        # fail FAST: a rank that unwinds normally here would run the CUDA teardown, which blocks for ever on streams that wait
+        # for a peer's exchange stamp -- and torchrun would keep the other ranks waiting until the caller's time limit
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
