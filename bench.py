@@ -42,6 +42,21 @@ DB_ROWS = 10000
 POOL = 8                      # distinct keyframes cycled through; the first POOL_IN_DB are in the database beforehand (their
 POOL_IN_DB = 4                # queries hit from the start), the others are new the first time and revisits afterwards
 KF_PER_STEP = 10              # keyframes per step: --steps 20 times 200 keyframes
+HOST_ISSUE_KF, STAGE_KF, REPLAY_KF = 8, 5, 120      # keyframes of the untimed / replay passes through the same front-end
+
+
+def keyframe_rounds(steps: int, warmup: int) -> int:
+    """keyframe rounds that go through the main front-end in one run: both timed regions (resident and end to end, warm-up
+    included), the host-issue and stage-profile passes, the C4 replay"""
+    return 2 * (warmup + steps) * KF_PER_STEP + HOST_ISSUE_KF + STAGE_KF + REPLAY_KF
+
+
+def db_capacity(db_rows: int, world: int, steps: int, warmup: int) -> int:
+    """rows per store: the preloaded rows plus what the run can add -- per round 4 own rows (local store) and 4 rows of every
+    other drone (remote store) -- with the host's conservative bound in mind, which charges every gathered record, the
+    skipped own slot included, to BOTH stores ((world + 1) * 4 per round), so that it never has to synchronise to find out
+    that there is room.  (An undersized store made an 8-rank run fail in its replay leg.)"""
+    return db_rows + N_DIRS * (world + 1) * (keyframe_rounds(steps, warmup) + 64) + 1024
 SP_GFLOP_PER_IMAGE = 52.10    # SURVEY.md section 8d / BASELINE.md section 2
 
 
@@ -311,9 +326,9 @@ def run_ours(args):
     # database capacity: the preloaded rows plus everything this run will add.  Every keyframe round adds 4 rows per drone
     # (own -> local store, foreign -> remote store), and the rounds are: both timed regions (warm-up included), the host-issue
     # and stage-profile passes and the C4 replay.  (An undersized store made the 8-rank run fail in the replay leg.)
-    rounds_total = 2 * (args.warmup + args.steps) * KF_PER_STEP + 8 + 5 + 120 + 64
     fe = host.KeyframeFrontend(spw, comp, mean, nvw, width=W, height=H, n_dirs=N_DIRS, max_num=MAX_NUM, sp_thres=0.015,
-                               self_id=rank, db_capacity=args.db_rows + N_DIRS * (world + 1) * rounds_total + 1024, inner_product_thres=0.3,
+                               self_id=rank, db_capacity=db_capacity(args.db_rows, world, args.steps, args.warmup),
+                               inner_product_thres=0.3,
                                match_index_dist=5, zero_bottom_quarter=True, accept_min_3d_pts=10)
     st = torch.cuda.current_stream().cuda_stream
 
@@ -440,9 +455,9 @@ def run_ours(args):
     # host cost of ENQUEUEING a keyframe with an empty launch queue (8 keyframes right after a synchronisation: no back-pressure)
     fe.finish(st); barrier()
     th = time.perf_counter()
-    for k in range(8):
+    for k in range(HOST_ISSUE_KF):
         keyframe_resident(900_000 + k)
-    host_issue_resident = (time.perf_counter() - th) * 1e3 / 8
+    host_issue_resident = (time.perf_counter() - th) * 1e3 / HOST_ISSUE_KF
     fe.finish(st); barrier()
     clocks = sampler.stop()
     ms_step = ms_total / args.steps
@@ -470,7 +485,7 @@ def run_ours(args):
     # ---- stage breakdown (CUDA events inside the library, one extra profiled pass; not part of `value`) ----
     fe.set_profiling(True)
     stage_acc = {}
-    for i in range(5):
+    for i in range(STAGE_KF):
         keyframe_resident(700_000 + i)
         fe.finish(st)
         for k, v in fe.stage_ms().items():
@@ -716,7 +731,7 @@ def run_ours(args):
         fe.finish(st); barrier()
         L.osb_set_sm_budget(148 - 16)                # the solve's cluster holds 16 SMs: keep the persistent conv grids off them
         th = threading.Thread(target=solver_loop); th.start()
-        n_kf = 120
+        n_kf = REPLAY_KF
         t0r = time.perf_counter()
         for k in range(n_kf):
             keyframe_resident(800_000 + k)

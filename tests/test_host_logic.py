@@ -59,3 +59,24 @@ def test_solver_chain_plan_recovers_odometry_chains():
     lk = np.nonzero(link)[0]
     same_drone = (orig[lk] % 5) == (orig[lk - 1] % 5)
     assert same_drone.mean() > 0.95 and (np.abs(orig[lk] // 5 - orig[lk - 1] // 5)[same_drone] == 1).all()
+
+
+def test_bench_database_capacity_covers_every_round():
+    """bench.py sizes the keyframe stores from the rounds of the run: per round a drone adds 4 own rows to its local store and
+    4 rows per other drone to its remote store, and the host's conservative bound charges every gathered record to both
+    stores.  Neither the true counts nor the bound may reach the capacity, for any world size and step count the driver
+    may pass (an undersized remote store once failed an 8-rank run in its replay leg)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for world in (1, 2, 4, 8):
+        for steps, warmup in ((20, 3), (1, 0), (100, 10), (2, 1)):
+            rounds = bench.keyframe_rounds(steps, warmup)
+            assert rounds == 2 * (steps + warmup) * bench.KF_PER_STEP + 8 + 5 + 120
+            cap = bench.db_capacity(10_000, world, steps, warmup)
+            local_rows = 10_000 + 4 * rounds
+            remote_rows = 4 * (world - 1) * rounds
+            bound = 10_000 + 4 * rounds + 4 * world * rounds          # own ingest + every gathered record
+            assert cap > local_rows and cap > remote_rows and cap > bound, (world, steps, cap, bound)
