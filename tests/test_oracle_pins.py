@@ -310,3 +310,37 @@ def test_pnp_oracle_pinned_against_opencv():
     old_in_wn = pr.pose_mul(pr.pose_inv(res["pose"]), pr.pose_inv(c["extrinsic"]))      # old drone in the new drone's frame
     d = pn.delta_pose(old_in_wn, c["drone_pose_now"], True)
     assert np.abs(v["dp"][:3] - d[:3]).max() < 1e-9 and abs(v["dp"][3] - 0.3 * -1) < 0.02   # yaw(new) - yaw(old) = -0.3
+
+
+def test_solver_oracle_minimum_agrees_with_an_independent_optimiser():
+    """Pins the oracle's Levenberg-Marquardt (step control, Huber corrector, fixed nodes) against an optimiser that shares no
+    code with it: scipy's trust-region-reflective least_squares on the SAME objective, written as plain residuals
+    r' = r * sqrt(rho(s) / s) per factor (so that |r'|^2 = rho(|r|^2), Ceres' robustified cost).  Both must land on the same
+    minimum of a small swarm graph with outliers (some Huber terms active) -- poses and cost."""
+    import scipy.optimize as so
+    from oracle import solver_ref as sr
+    from omniswarm_b200 import synth
+    g = synth.pose_graph(3, 10, n_uwb=18, n_loop=12, n_det=8, n_bearing=0, seed=11, outlier_frac=0.15)
+    ref = sr.solve(g)
+    free = np.nonzero(g["fixed"] == 0)[0]
+
+    def residuals(xf):
+        x = g["init"].astype(np.float64).copy()
+        x[free] = xf.reshape(-1, 4)
+        out = []
+        for f in range(len(g["ftype"])):
+            r, _, _ = sr.factor_residual_jacobian(int(g["ftype"][f]), x[int(g["ia"][f])], x[int(g["ib"][f])], g["payload"][f])
+            s = float(r @ r)
+            if g["huber"][f] and s > 1.0:
+                r = r * np.sqrt((2.0 * np.sqrt(s) - 1.0) / s)
+            out.append(np.pad(r, (0, 4 - len(r))))
+        return np.concatenate(out)
+
+    x0 = g["init"].astype(np.float64)[free].reshape(-1)
+    sol = so.least_squares(residuals, x0, method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-13, max_nfev=400)
+    n_active = sum(1 for f in range(len(g["ftype"])) if g["huber"][f] and
+                   float(np.sum(sr.factor_residual_jacobian(int(g["ftype"][f]), ref["poses"][int(g["ia"][f])],
+                                                            ref["poses"][int(g["ib"][f])], g["payload"][f])[0] ** 2)) > 1.0)
+    assert n_active >= 1, "the graph should keep some Huber terms active at the minimum"
+    assert abs(sol.cost - ref["final_cost"]) <= 1e-9 * max(1.0, ref["final_cost"])
+    assert np.abs(sol.x.reshape(-1, 4) - ref["poses"][free]).max() < 1e-6
