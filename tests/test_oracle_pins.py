@@ -344,3 +344,36 @@ def test_solver_oracle_minimum_agrees_with_an_independent_optimiser():
     assert n_active >= 1, "the graph should keep some Huber terms active at the minimum"
     assert abs(sol.cost - ref["final_cost"]) <= 1e-9 * max(1.0, ref["final_cost"])
     assert np.abs(sol.x.reshape(-1, 4) - ref["poses"][free]).max() < 1e-6
+
+
+def test_pose_algebra_agrees_with_homogeneous_matrices():
+    """The 4-DoF relative pose of RelativePoseFactor4d (DeltaPose, factors.hpp:139-149) and the 7-vector Swarm::Pose algebra the
+    PCM / PnP oracles define (swarm_msgs is not in the reference tree) are checked against the textbook statement of the same
+    things: 4x4 homogeneous transforms composed and inverted with numpy, rotations from scipy."""
+    from scipy.spatial.transform import Rotation as Rot
+    from oracle import solver_ref as sr, pcm_ref as pr
+    rng = np.random.default_rng(5)
+
+    def T4(p):                                   # (x y z yaw) -> 4x4
+        T = np.eye(4); T[:3, :3] = Rot.from_euler("z", p[3]).as_matrix(); T[:3, 3] = p[:3]; return T
+
+    def T7(p):                                   # (x y z, qw qx qy qz) -> 4x4
+        T = np.eye(4); T[:3, :3] = Rot.from_quat([p[4], p[5], p[6], p[3]]).as_matrix(); T[:3, 3] = p[:3]; return T
+
+    for _ in range(50):
+        pa = np.concatenate([rng.normal(0, 3, 3), rng.uniform(-3.1, 3.1, 1)])
+        pb = np.concatenate([rng.normal(0, 3, 3), rng.uniform(-3.1, 3.1, 1)])
+        pl = np.zeros(24); pl[4:20] = np.eye(4).reshape(-1)          # measurement 0, sqrt information I: r = -est
+        r, _, _ = sr.factor_residual_jacobian(sr.FACTOR_RELPOSE, pa, pb, pl)
+        D = np.linalg.inv(T4(pa)) @ T4(pb)
+        est = np.array([D[0, 3], D[1, 3], D[2, 3], np.arctan2(D[1, 0], D[0, 0])])
+        assert np.allclose(-r[:3], est[:3], atol=1e-12)
+        assert abs(sr.normalize_angle(-r[3] - est[3])) < 1e-12
+        # Swarm::Pose: composition, inverse, log map
+        qa, qb = Rot.random(random_state=int(rng.integers(1 << 30))), Rot.random(random_state=int(rng.integers(1 << 30)))
+        A = np.concatenate([rng.normal(0, 2, 3), np.roll(qa.as_quat(), 1)])
+        B = np.concatenate([rng.normal(0, 2, 3), np.roll(qb.as_quat(), 1)])
+        assert np.allclose(T7(pr.pose_mul(A, B)), T7(A) @ T7(B), atol=1e-12)
+        assert np.allclose(T7(pr.pose_inv(A)), np.linalg.inv(T7(A)), atol=1e-12)
+        lm = pr.log_map(A)
+        assert np.allclose(lm[:3], A[:3]) and np.allclose(lm[3:], qa.as_rotvec(), atol=1e-10)
