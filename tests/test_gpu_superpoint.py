@@ -241,3 +241,16 @@ def test_fused_first_layers_bit_identical(gpu, size):
         for name in ("pair", "halo"):
             for a, c in zip(out[name][b], out["box"][b]):
                 assert np.array_equal(a, c, equal_nan=True), f"image {b}: the {name} kernels and the TMA-box kernels differ"
+
+
+def test_network_vs_the_references_own_module(small_sp):
+    """The CUDA network against golden vectors that do NOT come from the oracle: tests/golden/ref_superpoint.npz was written
+    by the reference's own `SuperPointNet` (swarm_loop/superpoint.ipynb, the module its TensorRT engine is exported from),
+    executed in place by tests/golden/make_ref_superpoint.py with the seeded weights and the C++ runtime's input scaling."""
+    z = np.load(os.path.join(GOLDEN, "ref_superpoint.npz"))
+    img = z["img_0"]
+    assert img.shape == (H0, W0)
+    small_sp.inference(img)
+    semi, desc = small_sp.read("semi"), small_sp.read("desc")
+    assert rel_err(semi, z["semi_0"]) < 1e-4 and np.abs(semi - z["semi_0"]).max() < 1e-4
+    assert rel_err(desc, z["desc_0"]) < 1e-4

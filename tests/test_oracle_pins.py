@@ -377,3 +377,40 @@ def test_pose_algebra_agrees_with_homogeneous_matrices():
         assert np.allclose(T7(pr.pose_inv(A)), np.linalg.inv(T7(A)), atol=1e-12)
         lm = pr.log_map(A)
         assert np.allclose(lm[:3], A[:3]) and np.allclose(lm[3:], qa.as_rotvec(), atol=1e-10)
+
+
+def test_network_oracle_matches_the_references_own_module():
+    """The SuperPoint stage of the oracle against the REFERENCE ITSELF: tests/golden/ref_superpoint.npz holds the outputs of the
+    `SuperPointNet` class of swarm_loop/superpoint.ipynb (the module the reference exports its TensorRT engine from),
+    executed in place by tests/golden/make_ref_superpoint.py with the seeded weights.  oracle/frontend_ref.py must
+    reproduce them (same torch kernels underneath: a few ulp); with the reference tree present the notebook is executed
+    again, so the fixture cannot drift from it."""
+    import os
+    from oracle import frontend_ref as fr
+    from omniswarm_b200 import synth
+    here = os.path.dirname(os.path.abspath(__file__))
+    z = np.load(os.path.join(here, "golden", "ref_superpoint.npz"))
+    w = synth.superpoint_weights(0)
+    seeds = sorted(int(k.split("_")[1]) for k in z.files if k.startswith("img_"))
+    assert len(seeds) == 3
+    for s in seeds:
+        img = z[f"img_{s}"]
+        assert np.array_equal(img, synth.image(s, *img.shape))            # the fixture's inputs are reproducible
+        semi, desc = fr.superpoint_net(img, w, num_threads=1)
+        assert semi.shape == z[f"semi_{s}"].shape and desc.shape == z[f"desc_{s}"].shape
+        assert np.abs(semi - z[f"semi_{s}"]).max() <= 2e-7 and np.abs(desc - z[f"desc_{s}"]).max() <= 2e-7
+        # the decision the pipeline takes on it -- which pixels exceed the threshold -- is identical
+        assert np.array_equal(semi > np.float32(0.015), z[f"semi_{s}"] > np.float32(0.015))
+    # the notebook scales its input with `/255`, the C++ runtime with `* (float)(1/255.0)` (what runs on the drone, and what the
+    # oracle restates): one ulp on some pixels, a few 1e-6 on the heat map
+    semi0, _ = fr.superpoint_net(z["img_0"], w, num_threads=1)
+    assert 0 < np.abs(semi0 - z["semi_div_0"]).max() < 1e-5
+    if os.path.exists("/root/reference/swarm_loop/superpoint.ipynb"):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("make_ref_superpoint", os.path.join(here, "golden", "make_ref_superpoint.py"))
+        m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+        import torch
+        torch.set_num_threads(1)
+        s = seeds[0]
+        semi_r, desc_r = m.run_reference(z[f"img_{s}"], w)
+        assert np.array_equal(semi_r, z[f"semi_{s}"]) and np.array_equal(desc_r, z[f"desc_{s}"])
