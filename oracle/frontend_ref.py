@@ -8,7 +8,9 @@ cannot be compiled or imported here (no ROS/TensorRT/OpenCV-C++/faiss/libtorch-C
 section 8c) and ships no golden vectors, so the pins are:
   * torch.nn.functional.grid_sample  == torch::grid_sampler  (same ATen kernel)       -> PINNED
   * cv2.BFMatcher(NORM_L2, True)     == cv::BFMatcher        (same OpenCV algorithm)  -> PINNED
-  * SuperPoint network: torch module of superpoint.ipynb:135-205, seeded weights      -> parity unpinned
+  * SuperPoint network: torch module of superpoint.ipynb:135-205, seeded weights      -> pinned against the reference's own
+    SuperPointNet class executed in place (tests/golden/make_ref_superpoint.py, ref_superpoint.npz): 2e-7; the trained
+    weights and the fp16 TensorRT engine's rounding remain unpinned
     (no reference outputs exist; the engine ran fp16 TensorRT)
   * NMS2 / getKeyPoints: literal restatement incl. flat-address wrap, u16 index plane  -> parity unpinned
     (out-of-buffer neighbour = skip; sort ties = stable raster order; both are *defined* here)
