@@ -414,3 +414,25 @@ def test_network_oracle_matches_the_references_own_module():
         s = seeds[0]
         semi_r, desc_r = m.run_reference(z[f"img_{s}"], w)
         assert np.array_equal(semi_r, z[f"semi_{s}"]) and np.array_equal(desc_r, z[f"desc_{s}"])
+
+
+def test_euler_convention_matches_the_references_python_helpers():
+    """`quat2eulers` and the angle wrap that the PnP / PCM oracles define (their C++ originals live in swarm_msgs, which is not in
+    the tree) against the reference's own Python statement of them, swarm_localization/scripts/utils.py, executed in place by
+    tests/golden/make_ref_utils.py."""
+    import os
+    from oracle import pnp_ref as pr
+    from oracle import solver_ref as sr
+    here = os.path.dirname(os.path.abspath(__file__))
+    z = np.load(os.path.join(here, "golden", "ref_utils.npz"))
+    for q, ypr in zip(z["quat_wxyz"], z["ypr"]):
+        rpy = pr.quat2eulers(q)
+        assert np.allclose(rpy[::-1], ypr, atol=1e-12)                # the reference returns (yaw, pitch, roll)
+    for a, w in zip(z["angle"], z["wrapped"]):
+        assert abs(pr.wrap(a) - w) < 1e-12 and abs(sr.normalize_angle(a) - w) < 1e-12
+    if os.path.exists("/root/reference/swarm_localization/scripts/utils.py"):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("make_ref_utils", os.path.join(here, "golden", "make_ref_utils.py"))
+        m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+        q2e, _ = m.reference_functions()
+        assert np.allclose(q2e(*z["quat_wxyz"][0]), z["ypr"][0], atol=0)
