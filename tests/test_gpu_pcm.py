@@ -4,6 +4,7 @@ import pytest
 
 from omniswarm_b200 import synth, host
 from oracle import pcm_ref as pr
+from oracle import fmc_ref
 
 pytestmark = pytest.mark.gpu
 THRES, POS, ANG = 15.0, 1e-4, 1e-5
@@ -22,6 +23,8 @@ def test_pcm_matches_oracle(gpu, n, out, seed):
     assert np.array_equal(adj, radj)                                  # consistency graph bit-exact
     rclique, rsize = pr.max_clique_heu(radj)
     assert clique.tolist() == rclique                                 # same vertices in maxCliqueHeu's order
+    if fmc_ref.available():                                           # ... and in the order of the REFERENCE's own library
+        assert clique.tolist() == fmc_ref.max_clique_heu(radj)[0]     # (oracle/_ref/libfmc_ref.so, built from its sources)
     if n > 30:
         assert all(edges[i]["inlier"] for i in clique) and len(clique) >= 0.4 * sum(e["inlier"] for e in edges)
 
@@ -42,6 +45,8 @@ def test_pcm_large_graph_bitmatrix_in_global_memory(gpu):
         assert adj[i, j] == (s < THRES)
     rclique, _ = pr.max_clique_heu(adj)
     assert clique.tolist() == rclique
+    if fmc_ref.available():
+        assert clique.tolist() == fmc_ref.max_clique_heu(adj)[0]
     assert all(edges[i]["inlier"] for i in clique) and len(clique) > 100
 
 

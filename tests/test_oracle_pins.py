@@ -436,3 +436,32 @@ def test_euler_convention_matches_the_references_python_helpers():
         m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
         q2e, _ = m.reference_functions()
         assert np.allclose(q2e(*z["quat_wxyz"][0]), z["ypr"][0], atol=0)
+
+
+def test_max_clique_restatement_equals_the_references_own_library():
+    """FMC::maxCliqueHeu is plain C++ inside the reference tree (third_party/fast_max-clique_finder), so it is COMPILED from its
+    sources in place (oracle/ref_build/Makefile -> oracle/_ref/libfmc_ref.so, nothing copied) and the restatement in
+    oracle/pcm_ref.py -- what the CUDA clique kernel is compared with -- must return the same clique, vertex by vertex in the
+    same order, on random graphs of every density and on the degenerate ones."""
+    from oracle import fmc_ref, pcm_ref
+    if not fmc_ref.build():
+        pytest.skip("oracle/_ref/libfmc_ref.so is not built and the reference tree is not here to build it from")
+    rng = np.random.default_rng(1)
+    graphs = [np.zeros((1, 1), np.uint8), np.zeros((7, 7), np.uint8), (1 - np.eye(9, dtype=np.uint8))]
+    for _ in range(400):
+        n = int(rng.integers(2, 60))
+        a = np.triu(rng.uniform(size=(n, n)) < rng.uniform(0.02, 0.95), 1)
+        graphs.append((a | a.T).astype(np.uint8))
+    # PCM-shaped graphs: a big consistent block plus scattered false links
+    for _ in range(20):
+        n = int(rng.integers(30, 120)); k = int(0.5 * n)
+        a = np.zeros((n, n), bool)
+        idx = rng.choice(n, k, replace=False)
+        a[np.ix_(idx, idx)] = True
+        a |= np.triu(rng.uniform(size=(n, n)) < 0.05, 1); a = np.triu(a, 1); a = a | a.T
+        graphs.append(a.astype(np.uint8))
+    for a in graphs:
+        ref_clique, ref_size = fmc_ref.max_clique_heu(a)
+        clique, size = pcm_ref.max_clique_heu(a)
+        assert clique == ref_clique and size == ref_size
+        assert all(a[u, v] for i, u in enumerate(clique) for v in clique[i + 1:])      # and it is a clique
