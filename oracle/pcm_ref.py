@@ -9,7 +9,9 @@ Follows (paths relative to /root/reference):
       graph iff smd < pcm_thres (:231-235); edge1 is the LATER-inserted loop of the pair (:180,190);
   * FMC::maxCliqueHeu (Josh Mangelson's variant that returns the clique)
       swarm_localization/src/swarm_outlier_rejection/third_party/fast_max-clique_finder/src/findCliqueHeu.cpp:120-244
-      -- restated literally, prunings 1/3/5 and the "last element of S" choice (:185) included.
+      -- restated literally, prunings 1/3/5 and the "last element of S" choice (:185) included; PINNED against the
+      reference's own library compiled from these very sources (oracle/fmc_ref.py, oracle/_ref/libfmc_ref.so):
+      tests/test_oracle_pins.py::test_max_clique_restatement_equals_the_references_own_library.
 
 Third-party arithmetic that is ABSENT from the reference tree (HKUST-Swarm/swarm_msgs, un-vendored, no commit pinned):
 `Swarm::Pose` composition / inverse / `log_map`, `LoopEdge::get_covariance`, `computeSquaredMahalanobisDistance` and
